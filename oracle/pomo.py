@@ -1,0 +1,172 @@
+"""ctypes front end of the CPU parity ORACLE (oracle/libpomo.so).
+
+TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED (see oracle/pomo.h).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product (extpom_b200) never does.
+
+The class mirrors extpom_b200.PomGpu's Python surface (load / get / step and the
+reference's subroutine names) so that parity tests drive both the same way.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+F3D = ("aam advx advy drhox drhoy dtef kh km kq l q2b q2 q2lb q2l rho rmean sb sclim s "
+       "tb tclim t ub uf u vb vf v w wr zflux trstr trstrb trstrf srstr srstrb srstrf "
+       "taurstr taurstrb taurstrf").split()
+F2D = ("aam2d advua advva adx2d ady2d art aru arv cbc cor d drx2d dry2d dt dum dvm dx dy "
+       "e_atmos egb egf el elb elf et etb etf fluxua fluxva fsm h swrad ssurf tsurf tps ua "
+       "uab uaf utb utf va vab vaf vtb vtf vfluxb vfluxf wssurf wtsurf wubot wusurf wvbot "
+       "wvsurf").split()
+BJ = "ele elw uabe uabw vabe vabw".split()
+BI = "eln els vabn vabs uabn uabs".split()
+BJK = "tbe sbe tbw sbw".split()
+BIK = "tbn sbn tbs sbs".split()
+F1D = "z zz dz dzz".split()
+
+
+def build(force=False):
+    """Compile oracle/libpomo.so with the committed Makefile (gcc, -ffp-contract=off)."""
+    so = os.path.join(_HERE, "libpomo.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libpomo.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.pomo_create.restype = C.c_void_p
+        L.pomo_create.argtypes = [C.c_int] * 3
+        L.pomo_destroy.argtypes = [C.c_void_p]
+        L.pomo_field.restype = C.POINTER(C.c_double)
+        L.pomo_field.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_long)]
+        L.pomo_set.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.pomo_get.restype = C.c_double
+        L.pomo_get.argtypes = [C.c_void_p, C.c_char_p]
+        L.pomo_check_velocity.restype = C.c_double
+        for n in ("step lateral_viscosity mode_interaction mode_external mode_internal advave "
+                  "advct advu advv baropg profq profu profv vertvl realvertvl "
+                  "restore_interior check_velocity").split():
+            getattr(L, "pomo_" + n).argtypes = [C.c_void_p]
+        P = C.c_void_p
+        L.pomo_advq.argtypes = [P] * 4
+        L.pomo_advt1.argtypes = [P] * 5
+        L.pomo_advt2.argtypes = [P] * 5
+        L.pomo_dens.argtypes = [P] * 4
+        L.pomo_proft.argtypes = [P, P, P, P, C.c_int]
+        L.pomo_smol_adif.argtypes = [P] * 5
+        L.pomo_bcond.argtypes = [P, C.c_int]
+        L.pomo_bcondorl.argtypes = [P, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+class Oracle:
+    """One sub-domain of the reference model on the CPU (fp64, no FMA)."""
+
+    def __init__(self, im, jm, kb):
+        self.L = lib()
+        self.im, self.jm, self.kb = im, jm, kb
+        self.h = self.L.pomo_create(im, jm, kb)
+        self.f = {}
+        shapes = {}
+        for n in F3D: shapes[n] = (im, jm, kb)
+        for n in F2D: shapes[n] = (im, jm)
+        for n in BJ: shapes[n] = (jm,)
+        for n in BI: shapes[n] = (im,)
+        for n in BJK: shapes[n] = (jm, kb)
+        for n in BIK: shapes[n] = (im, kb)
+        for n in F1D: shapes[n] = (kb,)
+        self.shapes = shapes
+        for n, shp in shapes.items():
+            cnt = C.c_long(0)
+            p = self.L.pomo_field(self.h, n.encode(), C.byref(cnt))
+            assert cnt.value == int(np.prod(shp)), n
+            a = np.ctypeslib.as_array(p, shape=(cnt.value,))
+            self.f[n] = a.reshape(shp, order="F")  # column-major view, i fastest
+
+    def close(self):
+        if self.h:
+            self.f.clear()
+            self.L.pomo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- state I/O -------------------------------------------------------
+    def set(self, name, v):
+        if self.L.pomo_set(self.h, name.encode(), float(v)) != 0:
+            raise KeyError(name)
+
+    def getc(self, name):
+        return self.L.pomo_get(self.h, name.encode())
+
+    def load(self, state):
+        """state = {'consts': {...}, 'fields': {name: ndarray}} (see extpom_b200.synthetic)."""
+        for k, v in state["consts"].items():
+            self.L.pomo_set(self.h, k.encode(), float(v))  # unknown names ignored
+        for k, v in state["fields"].items():
+            if k in self.f:
+                self.f[k][...] = v
+
+    def get(self, name):
+        return np.array(self.f[name], order="F", copy=True)
+
+    def put(self, name, arr):
+        self.f[name][...] = arr
+
+    def _p(self, x):
+        if isinstance(x, str):
+            x = self.f[x]
+        return x.ctypes.data_as(C.c_void_p)
+
+    # -- the reference's subroutine surface --------------------------------
+    def step(self, iint, time=None):
+        """advance.f:21-32 for internal step `iint` (get_time restated: advance.f:62-75)."""
+        self.set("iint", iint)
+        dti, time0 = self.getc("dti"), self.getc("time0")
+        self.set("time", dti * float(iint) / 86400.0 + time0 if time is None else time)
+        self.L.pomo_step(self.h)
+
+    def check_velocity(self):
+        return self.L.pomo_check_velocity(self.h)
+
+    def lateral_viscosity(self): self.L.pomo_lateral_viscosity(self.h)
+    def mode_interaction(self): self.L.pomo_mode_interaction(self.h)
+    def mode_external(self, iext):
+        self.set("iext", iext); self.L.pomo_mode_external(self.h)
+    def mode_internal(self, iint):
+        self.set("iint", iint); self.L.pomo_mode_internal(self.h)
+    def advave(self): self.L.pomo_advave(self.h)
+    def advct(self): self.L.pomo_advct(self.h)
+    def advu(self): self.L.pomo_advu(self.h)
+    def advv(self): self.L.pomo_advv(self.h)
+    def baropg(self): self.L.pomo_baropg(self.h)
+    def profq(self): self.L.pomo_profq(self.h)
+    def profu(self): self.L.pomo_profu(self.h)
+    def profv(self): self.L.pomo_profv(self.h)
+    def vertvl(self): self.L.pomo_vertvl(self.h)
+    def realvertvl(self): self.L.pomo_realvertvl(self.h)
+    def restore_interior(self): self.L.pomo_restore_interior(self.h)
+    def bcond(self, idx): self.L.pomo_bcond(self.h, idx)
+    def bcondorl(self, idx): self.L.pomo_bcondorl(self.h, idx)
+    def advq(self, qb, q, qf): self.L.pomo_advq(self.h, self._p(qb), self._p(q), self._p(qf))
+    def advt1(self, fb, f, fclim, ff):
+        self.L.pomo_advt1(self.h, self._p(fb), self._p(f), self._p(fclim), self._p(ff))
+    def advt2(self, fb, f, fclim, ff):
+        self.L.pomo_advt2(self.h, self._p(fb), self._p(f), self._p(fclim), self._p(ff))
+    def dens(self, si, ti, rhoo): self.L.pomo_dens(self.h, self._p(si), self._p(ti), self._p(rhoo))
+    def proft(self, f, wfsurf, fsurf, nbc):
+        self.L.pomo_proft(self.h, self._p(f), self._p(wfsurf), self._p(fsurf), int(nbc))

@@ -1,0 +1,299 @@
+/* pomo_advance.c -- CPU ORACLE restatement of pom/advance.f:96-537
+ * (lateral_viscosity, mode_interaction, mode_external, mode_internal) and
+ * the hot-path part of advance (advance.f:21-32).
+ * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (see pomo.h). */
+#define POMO_IMPL
+#include "pomo.h"
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+/* advance.f:96-141 */
+void pomo_lateral_viscosity(pomo_t *S) {
+  DIMS;
+  if (S->mode != 2) {
+    pomo_advct(S);
+    if (S->npg == 1) {
+      pomo_baropg(S);
+    } else {
+      /* npg=2 (baropg_mcc) is a "next" row */
+      S->error_status = 1;
+      fprintf(stderr, "\nError: invalid value for npg\n");
+    }
+    /* :122-136 */
+    OMP_FOR
+    DO(k, 1, kbm1) DO(j, 2, jmm1) DO(i, 2, imm1) {
+      double a1=(u(i+1,j,k)-u(i,j,k))/dx(i,j);
+      double a2=(v(i,j+1,k)-v(i,j,k))/dy(i,j);
+      double a3=.25*(u(i,j+1,k)+u(i+1,j+1,k)
+                     -u(i,j-1,k)-u(i+1,j-1,k))
+                /dy(i,j)
+               +.25*(v(i+1,j,k)+v(i+1,j+1,k)
+                     -v(i-1,j,k)-v(i-1,j+1,k))
+                /dx(i,j);
+      aam(i,j,k)=horcon*dx(i,j)*dy(i,j)
+                 *sqrt( a1*a1
+                       +a2*a2
+                 +.5*(a3*a3));
+    }
+  }
+}
+
+/* advance.f:144-202 */
+void pomo_mode_interaction(pomo_t *S) {
+  DIMS;
+  if (S->mode != 2) {
+    memset(S->adx2d, 0, sizeof(double) * N2);
+    memset(S->ady2d, 0, sizeof(double) * N2);
+    memset(S->drx2d, 0, sizeof(double) * N2);
+    memset(S->dry2d, 0, sizeof(double) * N2);
+    memset(S->aam2d, 0, sizeof(double) * N2);
+    /* :158-168 */
+    DO(k, 1, kbm1) {
+      OMP_FOR
+      DO(j, 1, jm) DO(i, 1, im) {
+        adx2d(i,j)=adx2d(i,j)+advx(i,j,k)*dz(k);
+        ady2d(i,j)=ady2d(i,j)+advy(i,j,k)*dz(k);
+        drx2d(i,j)=drx2d(i,j)+drhox(i,j,k)*dz(k);
+        dry2d(i,j)=dry2d(i,j)+drhoy(i,j,k)*dz(k);
+        aam2d(i,j)=aam2d(i,j)+aam(i,j,k)*dz(k);
+      }
+    }
+    pomo_advave(S);
+    /* :172-177 */
+    DO(j, 1, jm) DO(i, 1, im) {
+      adx2d(i,j)=adx2d(i,j)-advua(i,j);
+      ady2d(i,j)=ady2d(i,j)-advva(i,j);
+    }
+  }
+  /* :181-196 */
+  DO(j, 1, jm) DO(i, 1, im) egf(i,j)=el(i,j)*ispi;
+  DO(j, 1, jm) DO(i, 2, im) utf(i,j)=ua(i,j)*(d(i,j)+d(i-1,j))*isp2i;
+  DO(j, 2, jm) DO(i, 1, im) vtf(i,j)=va(i,j)*(d(i,j)+d(i,j-1))*isp2i;
+}
+
+/* advance.f:205-353 */
+void pomo_mode_external(pomo_t *S) {
+  DIMS;
+  const int iext = S->iext, isplit = S->isplit;
+  /* :211-218 */
+  OMP_FOR
+  DO(j, 2, jm) DO(i, 2, im) {
+    fluxua(i,j)=.25*(d(i,j)+d(i-1,j))
+                *(dy(i,j)+dy(i-1,j))*ua(i,j);
+    fluxva(i,j)=.25*(d(i,j)+d(i,j-1))
+                *(dx(i,j)+dx(i,j-1))*va(i,j);
+  }
+  /* :222-229 */
+  OMP_FOR
+  DO(j, 2, jmm1) DO(i, 2, imm1)
+    elf(i,j)=elb(i,j)
+             +dte2*(-(fluxua(i+1,j)-fluxua(i,j)
+                     +fluxva(i,j+1)-fluxva(i,j))/art(i,j)
+                     -vfluxf(i,j));
+  pomo_bcond(S, 1); /* :231 */
+  if (iext % S->ispadv == 0) pomo_advave(S); /* :235 */
+  /* :237-252 */
+  OMP_FOR
+  DO(j, 2, jmm1) DO(i, 2, im)
+    uaf(i,j)=adx2d(i,j)+advua(i,j)
+             -aru(i,j)*.25
+               *(cor(i,j)*d(i,j)*(va(i,j+1)+va(i,j))
+                +cor(i-1,j)*d(i-1,j)*(va(i-1,j+1)+va(i-1,j)))
+             +.25*grav*(dy(i,j)+dy(i-1,j))
+               *(d(i,j)+d(i-1,j))
+               *((1.-2.*alpha)
+                  *(el(i,j)-el(i-1,j))
+                 +alpha*(elb(i,j)-elb(i-1,j)
+                        +elf(i,j)-elf(i-1,j))
+                 +e_atmos(i,j)-e_atmos(i-1,j))
+             +drx2d(i,j)+aru(i,j)*(wusurf(i,j)-wubot(i,j));
+  /* :254-262 */
+  OMP_FOR
+  DO(j, 2, jmm1) DO(i, 2, im)
+    uaf(i,j)=((h(i,j)+elb(i,j)+h(i-1,j)+elb(i-1,j))
+               *aru(i,j)*uab(i,j)
+             -4.*dte*uaf(i,j))
+            /((h(i,j)+elf(i,j)+h(i-1,j)+elf(i-1,j))
+                *aru(i,j));
+  /* :264-278 */
+  OMP_FOR
+  DO(j, 2, jm) DO(i, 2, imm1)
+    vaf(i,j)=ady2d(i,j)+advva(i,j)
+             +arv(i,j)*.25
+               *(cor(i,j)*d(i,j)*(ua(i+1,j)+ua(i,j))
+              +cor(i,j-1)*d(i,j-1)*(ua(i+1,j-1)+ua(i,j-1)))
+             +.25*grav*(dx(i,j)+dx(i,j-1))
+               *(d(i,j)+d(i,j-1))
+               *((1.-2.*alpha)*(el(i,j)-el(i,j-1))
+                 +alpha*(elb(i,j)-elb(i,j-1)
+                        +elf(i,j)-elf(i,j-1))
+                 +e_atmos(i,j)-e_atmos(i,j-1))
+             +dry2d(i,j)+arv(i,j)*(wvsurf(i,j)-wvbot(i,j));
+  /* :280-288 */
+  OMP_FOR
+  DO(j, 2, jm) DO(i, 2, imm1)
+    vaf(i,j)=((h(i,j)+elb(i,j)+h(i,j-1)+elb(i,j-1))
+               *arv(i,j)*vab(i,j)
+             -4.*dte*vaf(i,j))
+            /((h(i,j)+elf(i,j)+h(i,j-1)+elf(i,j-1))
+                *arv(i,j));
+  pomo_bcond(S, 2); /* :290 */
+  /* :295-318 */
+  if (iext == (isplit-2)) {
+    DO(j, 1, jm) DO(i, 1, im) S->etf[I2(i,j)]=.25*smoth*elf(i,j);
+  } else if (iext == (isplit-1)) {
+    DO(j, 1, jm) DO(i, 1, im) S->etf[I2(i,j)]=S->etf[I2(i,j)]+.5*(1.-.5*smoth)*elf(i,j);
+  } else if (iext == isplit) {
+    DO(j, 1, jm) DO(i, 1, im) S->etf[I2(i,j)]=(S->etf[I2(i,j)]+.5*elf(i,j))*fsm(i,j);
+  }
+  /* :321-330 whole-array filter and time rotation */
+  OMP_FOR
+  for (size_t n = 0; n < N2; ++n) {
+    S->ua[n] = S->ua[n]+.5*smoth*(S->uab[n]-2.*S->ua[n]+S->uaf[n]);
+    S->va[n] = S->va[n]+.5*smoth*(S->vab[n]-2.*S->va[n]+S->vaf[n]);
+    S->el[n] = S->el[n]+.5*smoth*(S->elb[n]-2.*S->el[n]+S->elf[n]);
+    S->elb[n] = S->el[n];
+    S->el[n] = S->elf[n];
+    S->d[n] = S->h[n]+S->el[n];
+    S->uab[n] = S->ua[n];
+    S->ua[n] = S->uaf[n];
+    S->vab[n] = S->va[n];
+    S->va[n] = S->vaf[n];
+  }
+  /* :332-350 */
+  if (iext != isplit) {
+    DO(j, 1, jm) DO(i, 1, im) egf(i,j)=egf(i,j)+el(i,j)*ispi;
+    DO(j, 1, jm) DO(i, 2, im) utf(i,j)=utf(i,j)+ua(i,j)*(d(i,j)+d(i-1,j))*isp2i;
+    DO(j, 2, jm) DO(i, 1, im) vtf(i,j)=vtf(i,j)+va(i,j)*(d(i,j)+d(i,j-1))*isp2i;
+  }
+}
+
+/* advance.f:356-537 */
+void pomo_mode_internal(pomo_t *S) {
+  DIMS;
+  if ((S->iint != 1 || S->time0 != 0.) && S->mode != 2) {
+    /* :365-378 */
+    memset(S->tps, 0, sizeof(double) * N2);
+    DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im) tps(i,j)=tps(i,j)+u(i,j,k)*dz(k);
+    OMP_FOR
+    DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 2, im)
+      u(i,j,k)=(u(i,j,k)-tps(i,j))+
+               (utb(i,j)+utf(i,j))/(dt(i,j)+dt(i-1,j));
+    /* :380-393 */
+    memset(S->tps, 0, sizeof(double) * N2);
+    DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im) tps(i,j)=tps(i,j)+v(i,j,k)*dz(k);
+    OMP_FOR
+    DO(k, 1, kbm1) DO(j, 2, jm) DO(i, 1, im)
+      v(i,j,k)=(v(i,j,k)-tps(i,j))+
+               (vtb(i,j)+vtf(i,j))/(dt(i,j)+dt(i,j-1));
+    /* :396-400 */
+    pomo_vertvl(S);
+    pomo_bcondorl(S, 5);
+    /* :403-404 */
+    memset(S->uf, 0, sizeof(double) * N3);
+    memset(S->vf, 0, sizeof(double) * N3);
+    /* :407-409 */
+    pomo_advq(S, S->q2b, S->q2, S->uf);
+    pomo_advq(S, S->q2lb, S->q2l, S->vf);
+    pomo_profq(S);
+    pomo_bcond(S, 6); /* :414 */
+    /* :416-421 */
+    OMP_FOR
+    for (size_t n = 0; n < N3; ++n) {
+      S->q2[n] = S->q2[n]+.5*smoth*(S->uf[n]+S->q2b[n]-2.*S->q2[n]);
+      S->q2l[n] = S->q2l[n]+.5*smoth*(S->vf[n]+S->q2lb[n]-2.*S->q2l[n]);
+      S->q2b[n] = S->q2[n];
+      S->q2[n] = S->uf[n];
+      S->q2lb[n] = S->q2l[n];
+      S->q2l[n] = S->vf[n];
+    }
+    /* :424-456 */
+    if (S->mode != 4) {
+      if (S->nadv == 1) {
+        pomo_advt1(S, S->tb, S->t, S->tclim, S->uf);
+        pomo_advt1(S, S->sb, S->s, S->sclim, S->vf);
+      } else if (S->nadv == 2) {
+        pomo_advt2(S, S->tb, S->t, S->tclim, S->uf);
+        pomo_advt2(S, S->sb, S->s, S->sclim, S->vf);
+      } else {
+        S->error_status = 1;
+        fprintf(stderr, "\nError: invalid value for nadv\n");
+      }
+      pomo_proft(S, S->uf, S->wtsurf, S->tsurf, S->nbct);
+      pomo_proft(S, S->vf, S->wssurf, S->ssurf, S->nbcs);
+      pomo_bcond(S, 4);
+      OMP_FOR
+      for (size_t n = 0; n < N3; ++n) {
+        S->t[n] = S->t[n]+.5*smoth*(S->uf[n]+S->tb[n]-2.*S->t[n]);
+        S->s[n] = S->s[n]+.5*smoth*(S->vf[n]+S->sb[n]-2.*S->s[n]);
+        S->tb[n] = S->t[n];
+        S->t[n] = S->uf[n];
+        S->sb[n] = S->s[n];
+        S->s[n] = S->vf[n];
+      }
+      pomo_restore_interior(S); /* :452 */
+      pomo_dens(S, S->s, S->t, S->rho); /* :454 */
+    }
+    /* :459-464 */
+    pomo_advu(S);
+    pomo_advv(S);
+    pomo_profu(S);
+    pomo_profv(S);
+    pomo_bcondorl(S, 3);
+    /* :469-488 */
+    memset(S->tps, 0, sizeof(double) * N2);
+    DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im)
+      tps(i,j)=tps(i,j)
+               +(uf(i,j,k)+ub(i,j,k)-2.*u(i,j,k))*dz(k);
+    OMP_FOR
+    DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im)
+      u(i,j,k)=u(i,j,k)
+               +.5*smoth*(uf(i,j,k)+ub(i,j,k)
+                          -2.*u(i,j,k)-tps(i,j));
+    /* :490-509 */
+    memset(S->tps, 0, sizeof(double) * N2);
+    DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im)
+      tps(i,j)=tps(i,j)
+               +(vf(i,j,k)+vb(i,j,k)-2.*v(i,j,k))*dz(k);
+    OMP_FOR
+    DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im)
+      v(i,j,k)=v(i,j,k)
+               +.5*smoth*(vf(i,j,k)+vb(i,j,k)
+                          -2.*v(i,j,k)-tps(i,j));
+    /* :511-514 */
+    memcpy(S->ub, S->u, sizeof(double) * N3);
+    memcpy(S->u, S->uf, sizeof(double) * N3);
+    memcpy(S->vb, S->v, sizeof(double) * N3);
+    memcpy(S->v, S->vf, sizeof(double) * N3);
+  }
+  /* :525-531 */
+  memcpy(S->egb, S->egf, sizeof(double) * N2);
+  memcpy(S->etb, S->et, sizeof(double) * N2);
+  memcpy(S->et, S->etf, sizeof(double) * N2);
+  for (size_t n = 0; n < N2; ++n) S->dt[n] = S->h[n]+S->et[n];
+  memcpy(S->utb, S->utf, sizeof(double) * N2);
+  memcpy(S->vtb, S->vtf, sizeof(double) * N2);
+  memcpy(S->vfluxb, S->vfluxf, sizeof(double) * N2);
+  pomo_realvertvl(S); /* :534 */
+}
+
+/* advance.f:21-32: the hot path of one internal step.  The caller sets
+ * iint (and time/ramp, advance.f:62-75) like the Fortran driver does. */
+void pomo_step(pomo_t *S) {
+  pomo_lateral_viscosity(S);
+  pomo_mode_interaction(S);
+  for (S->iext = 1; S->iext <= S->isplit; ++S->iext) pomo_mode_external(S);
+  S->iext = S->isplit + 1; /* Fortran do-loop exit value */
+  pomo_mode_internal(S);
+}
+
+/* advance.f:611-641 */
+double pomo_check_velocity(pomo_t *S) {
+  DIMS;
+  double vamax = 0.;
+  DO(j, 1, jm) DO(i, 1, im)
+    if (fabs(vaf(i,j)) >= vamax) vamax = fabs(vaf(i,j));
+  if (vamax > S->vmaxl) S->error_status = 1;
+  return vamax;
+}

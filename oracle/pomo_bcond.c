@@ -1,0 +1,296 @@
+/* pomo_bcond.c -- CPU ORACLE restatement of the boundary-condition and
+ * restoring arithmetic of pom/bounds_forcing.f that runs inside the step.
+ * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (see pomo.h).
+ * bcond: bounds_forcing.f:6-328 (idx 1,2,4,5,6; idx 3 is never called on
+ * the path, advance.f:464 uses bcondorl(3)); bcondorl: :331-590 (idx 3,5;
+ * the others are never called); restore_interior arithmetic: :1083-1118. */
+#define POMO_IMPL
+#include "pomo.h"
+#include <math.h>
+
+void pomo_bcond(pomo_t *S, int idx) {
+  DIMS;
+  double u1, wm;
+  if (idx == 1) {
+    /* :21-39 */
+    if (n_west == -1) DO(j, 1, jm) elf(1,j)=elf(2,j);
+    if (n_east == -1) DO(j, 1, jm) elf(im,j)=elf(imm1,j);
+    if (n_south == -1) DO(i, 1, im) elf(i,1)=elf(i,2);
+    if (n_north == -1) DO(i, 1, im) elf(i,jm)=elf(i,jmm1);
+    DO(j, 1, jm) DO(i, 1, im) elf(i,j)=elf(i,j)*fsm(i,j);
+    return;
+  } else if (idx == 2) {
+    /* :47-53 west */
+    if (n_west == -1) {
+      DO(j, 2, jmm1) uaf(2,j)=uabw(j)
+                     -rfw*sqrt(grav/d(2,j))*(el(2,j)-elw(j));
+      DO(j, 2, jmm1) uaf(2,j)=ramp*uaf(2,j);
+      DO(j, 2, jmm1) uaf(1,j)=uaf(2,j);
+      DO(j, 2, jmm1) vaf(1,j)=vabw(j);
+    }
+    /* :56-61 east */
+    if (n_east == -1) {
+      DO(j, 2, jmm1) uaf(im,j)=uabe(j)
+                     +rfe*sqrt(grav/d(imm1,j))*(el(imm1,j)-ele(j));
+      DO(j, 2, jmm1) uaf(im,j)=ramp*uaf(im,j);
+      DO(j, 2, jmm1) vaf(im,j)=vabe(j);
+    }
+    /* :64-70 south */
+    if (n_south == -1) {
+      DO(i, 2, imm1) vaf(i,2)=vabs(i)
+                     -rfs*sqrt(grav/d(i,2))*(el(i,2)-els(i));
+      DO(i, 2, imm1) vaf(i,2)=ramp*vaf(i,2);
+      DO(i, 2, imm1) vaf(i,1)=vaf(i,2);
+      DO(i, 2, imm1) uaf(i,1)=uabs(i);
+    }
+    /* :73-78 north */
+    if (n_north == -1) {
+      DO(i, 2, imm1) vaf(i,jm)=vabn(i)
+                     +rfn*sqrt(grav/d(i,jmm1))*(el(i,jmm1)-eln(i));
+      DO(i, 2, imm1) vaf(i,jm)=ramp*vaf(i,jm);
+      DO(i, 2, imm1) uaf(i,jm)=uabn(i);
+    }
+    /* :80-81 */
+    DO(j, 1, jm) DO(i, 1, im) { uaf(i,j)=uaf(i,j)*dum(i,j); }
+    DO(j, 1, jm) DO(i, 1, im) { vaf(i,j)=vaf(i,j)*dvm(i,j); }
+    return;
+  } else if (idx == 4) {
+    /* :155-231 */
+    DO(k, 1, kbm1) {
+      DO(j, 1, jm) {
+        if (n_east == -1) {
+          u1=2.*u(im,j,k)*dti/(dx(im,j)+dx(imm1,j));
+          if (u1 <= 0.) {
+            uf(im,j,k)=t(im,j,k)-u1*(tbe(j,k)-t(im,j,k));
+            vf(im,j,k)=s(im,j,k)-u1*(sbe(j,k)-s(im,j,k));
+          } else {
+            uf(im,j,k)=t(im,j,k)-u1*(t(im,j,k)-t(imm1,j,k));
+            vf(im,j,k)=s(im,j,k)-u1*(s(im,j,k)-s(imm1,j,k));
+            if (k != 1 && k != kbm1) {
+              wm=.5*(w(imm1,j,k)+w(imm1,j,k+1))*dti
+                 /((zz(k-1)-zz(k+1))*dt(imm1,j));
+              uf(im,j,k)=uf(im,j,k)-wm*(t(imm1,j,k-1)-t(imm1,j,k+1));
+              vf(im,j,k)=vf(im,j,k)-wm*(s(imm1,j,k-1)-s(imm1,j,k+1));
+            }
+          }
+        }
+        if (n_west == -1) {
+          u1=2.*u(2,j,k)*dti/(dx(1,j)+dx(2,j));
+          if (u1 >= 0.) {
+            uf(1,j,k)=t(1,j,k)-u1*(t(1,j,k)-tbw(j,k));
+            vf(1,j,k)=s(1,j,k)-u1*(s(1,j,k)-sbw(j,k));
+          } else {
+            uf(1,j,k)=t(1,j,k)-u1*(t(2,j,k)-t(1,j,k));
+            vf(1,j,k)=s(1,j,k)-u1*(s(2,j,k)-s(1,j,k));
+            if (k != 1 && k != kbm1) {
+              wm=.5*(w(2,j,k)+w(2,j,k+1))*dti
+                 /((zz(k-1)-zz(k+1))*dt(2,j));
+              uf(1,j,k)=uf(1,j,k)-wm*(t(2,j,k-1)-t(2,j,k+1));
+              vf(1,j,k)=vf(1,j,k)-wm*(s(2,j,k-1)-s(2,j,k+1));
+            }
+          }
+        }
+      }
+      DO(i, 1, im) {
+        if (n_south == -1) {
+          u1=2.*v(i,2,k)*dti/(dy(i,1)+dy(i,2));
+          if (u1 >= 0.) {
+            uf(i,1,k)=t(i,1,k)-u1*(t(i,1,k)-tbs(i,k));
+            vf(i,1,k)=s(i,1,k)-u1*(s(i,1,k)-sbs(i,k));
+          } else {
+            uf(i,1,k)=t(i,1,k)-u1*(t(i,2,k)-t(i,1,k));
+            vf(i,1,k)=s(i,1,k)-u1*(s(i,2,k)-s(i,1,k));
+            if (k != 1 && k != kbm1) {
+              wm=.5*(w(i,2,k)+w(i,2,k+1))*dti
+                 /((zz(k-1)-zz(k+1))*dt(i,2));
+              uf(i,1,k)=uf(i,1,k)-wm*(t(i,2,k-1)-t(i,2,k+1));
+              vf(i,1,k)=vf(i,1,k)-wm*(s(i,2,k-1)-s(i,2,k+1));
+            }
+          }
+        }
+        if (n_north == -1) {
+          u1=2.*v(i,jm,k)*dti/(dy(i,jm)+dy(i,jmm1));
+          if (u1 <= 0.) {
+            uf(i,jm,k)=t(i,jm,k)-u1*(tbn(i,k)-t(i,jm,k));
+            vf(i,jm,k)=s(i,jm,k)-u1*(sbn(i,k)-s(i,jm,k));
+          } else {
+            uf(i,jm,k)=t(i,jm,k)-u1*(t(i,jm,k)-t(i,jmm1,k));
+            vf(i,jm,k)=s(i,jm,k)-u1*(s(i,jm,k)-s(i,jmm1,k));
+            if (k != 1 && k != kbm1) {
+              wm=.5*(w(i,jmm1,k)+w(i,jmm1,k+1))*dti
+                 /((zz(k-1)-zz(k+1))*dt(i,jmm1));
+              uf(i,jm,k)=uf(i,jm,k)-wm*(t(i,jmm1,k-1)-t(i,jmm1,k+1));
+              vf(i,jm,k)=vf(i,jm,k)-wm*(s(i,jmm1,k-1)-s(i,jmm1,k+1));
+            }
+          }
+        }
+      }
+    }
+    /* :233-240 */
+    DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im) {
+      uf(i,j,k)=uf(i,j,k)*fsm(i,j);
+      vf(i,j,k)=vf(i,j,k)*fsm(i,j);
+    }
+    return;
+  } else if (idx == 5) {
+    /* :247-253 */
+    DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im) w(i,j,k)=w(i,j,k)*fsm(i,j);
+    return;
+  } else if (idx == 6) {
+    /* :261-313 */
+    DO(k, 1, kb) {
+      DO(j, 1, jm) {
+        if (n_west == -1) {
+          u1=2.*u(2,j,k)*dti/(dx(1,j)+dx(2,j));
+          if (u1 >= 0.) {
+            uf(1,j,k)=q2(1,j,k)-u1*(q2(1,j,k)-small);
+            vf(1,j,k)=q2l(1,j,k)-u1*(q2l(1,j,k)-small);
+          } else {
+            uf(1,j,k)=q2(1,j,k)-u1*(q2(2,j,k)-q2(1,j,k));
+            vf(1,j,k)=q2l(1,j,k)-u1*(q2l(2,j,k)-q2l(1,j,k));
+          }
+        }
+        if (n_east == -1) {
+          u1=2.*u(im,j,k)*dti/(dx(im,j)+dx(imm1,j));
+          if (u1 <= 0.) {
+            uf(im,j,k)=q2(im,j,k)-u1*(small-q2(im,j,k));
+            vf(im,j,k)=q2l(im,j,k)-u1*(small-q2l(im,j,k));
+          } else {
+            uf(im,j,k)=q2(im,j,k)-u1*(q2(im,j,k)-q2(imm1,j,k));
+            vf(im,j,k)=q2l(im,j,k)-u1*(q2l(im,j,k)-q2l(imm1,j,k));
+          }
+        }
+      }
+      DO(i, 1, im) {
+        if (n_south == -1) {
+          u1=2.*v(i,2,k)*dti/(dy(i,1)+dy(i,2));
+          if (u1 >= 0.) {
+            uf(i,1,k)=q2(i,1,k)-u1*(q2(i,1,k)-small);
+            vf(i,1,k)=q2l(i,1,k)-u1*(q2l(i,1,k)-small);
+          } else {
+            uf(i,1,k)=q2(i,1,k)-u1*(q2(i,2,k)-q2(i,1,k));
+            vf(i,1,k)=q2l(i,1,k)-u1*(q2l(i,2,k)-q2l(i,1,k));
+          }
+        }
+        if (n_north == -1) {
+          u1=2.*v(i,jm,k)*dti/(dy(i,jm)+dy(i,jmm1));
+          if (u1 <= 0.) {
+            uf(i,jm,k)=q2(i,jm,k)-u1*(small-q2(i,jm,k));
+            vf(i,jm,k)=q2l(i,jm,k)-u1*(small-q2l(i,jm,k));
+          } else {
+            uf(i,jm,k)=q2(i,jm,k)-u1*(q2(i,jm,k)-q2(i,jmm1,k));
+            vf(i,jm,k)=q2l(i,jm,k)-u1*(q2l(i,jm,k)-q2l(i,jmm1,k));
+          }
+        }
+      }
+    }
+    /* :315-322 */
+    DO(k, 1, kb) DO(j, 1, jm) DO(i, 1, im) {
+      uf(i,j,k)=uf(i,j,k)*fsm(i,j)+1.e-10;
+      vf(i,j,k)=vf(i,j,k)*fsm(i,j)+1.e-10;
+    }
+    return;
+  }
+}
+
+void pomo_bcondorl(pomo_t *S, int idx) {
+  DIMS;
+  double cl, denom;
+  if (idx == 3) {
+    /* :422-476 */
+    DO(k, 1, kbm1) {
+      DO(j, 2, jmm1) {
+        if (n_east == -1) {
+          denom=(uf(im-1,j,k)+ub(im-1,j,k)-2.*u(im-2,j,k));
+          if (denom == 0.) denom=0.01;
+          cl=(ub(im-1,j,k)-uf(im-1,j,k))/denom;
+          if (cl > 1.) cl=1.;
+          if (cl < 0.) cl=0.;
+          uf(im,j,k)=(ub(im,j,k)*(1.-cl)+2.*cl*u(im-1,j,k))
+                     /(1.+cl);
+          vf(im,j,k)=0.;
+        }
+        if (n_west == -1) {
+          denom=(uf(3,j,k)+ub(3,j,k)-2.*u(4,j,k));
+          if (denom == 0.) denom=0.01;
+          cl=(ub(3,j,k)-uf(3,j,k))/denom;
+          if (cl > 1.) cl=1.;
+          if (cl < 0.) cl=0.;
+          uf(2,j,k)=(ub(2,j,k)*(1.-cl)+2.*cl*u(3,j,k))
+                    /(1.+cl);
+          uf(1,j,k)=uf(2,j,k);
+          vf(1,j,k)=0.;
+        }
+      }
+      DO(i, 2, imm1) {
+        if (n_south == -1) {
+          denom=(vf(i,3,k)+vb(i,3,k)-2.*v(i,4,k));
+          if (fabs(denom) == 0.0) denom=0.01;
+          cl=(vb(i,3,k)-vf(i,3,k))/denom;
+          if (cl > 1.) cl=1.;
+          if (cl < 0.) cl=0.;
+          vf(i,2,k)=(vb(i,2,k)*(1.-cl)+2.*cl*v(i,3,k))
+                    /(1.+cl);
+          vf(i,1,k)=vf(i,2,k);
+          uf(i,1,k)=0.;
+        }
+        if (n_north == -1) {
+          denom=(vf(i,jm-1,k)+vb(i,jm-1,k)-2.*v(i,jm-2,k));
+          if (fabs(denom) == 0.0) denom=0.01;
+          cl=(vb(i,jm-1,k)-vf(i,jm-1,k))/denom;
+          if (cl > 1.) cl=1.;
+          if (cl < 0.) cl=0.;
+          vf(i,jm,k)=(vb(i,jm,k)*(1.-cl)+2.*cl*v(i,jm-1,k))
+                     /(1.+cl);
+          uf(i,jm,k)=0.;
+        }
+      }
+    }
+    /* :478-485 */
+    DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im) {
+      uf(i,j,k)=uf(i,j,k)*dum(i,j);
+      vf(i,j,k)=vf(i,j,k)*dvm(i,j);
+    }
+    return;
+  } else if (idx == 5) {
+    /* :553-559 */
+    DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im) w(i,j,k)=w(i,j,k)*fsm(i,j);
+    return;
+  }
+}
+
+/* bounds_forcing.f:1083-1118: time interpolation, nudging and re-masking.
+ * The PnetCDF reads (:1039-1081) stay in the Fortran driver; here the
+ * bracketing records trstrb/f, srstrb/f, taurstrb/f are inputs. */
+void pomo_restore_interior(pomo_t *S) {
+  DIMS;
+  const double trst = 30.; /* :1033 */
+  int ntime = (int)(S->time / trst);
+  double fnew = S->time / trst - ntime;
+  double fold = 1. - fnew;
+  if (S->lrestore) {
+    DO(k, 1, kbm1) DO(i, 1, im) DO(j, 1, jm) {
+      trstr(i,j,k)=fold*trstrb(i,j,k)+fnew*trstrf(i,j,k);
+      srstr(i,j,k)=fold*srstrb(i,j,k)+fnew*srstrf(i,j,k);
+      taurstr(i,j,k)=fold*taurstrb(i,j,k)+fnew*taurstrf(i,j,k);
+    }
+    DO(k, 1, kbm1) DO(i, 1, im) DO(j, 1, jm) {
+      t(i,j,k)=t(i,j,k)+2.*dti/86400.*taurstr(i,j,k)*
+               (trstr(i,j,k)-t(i,j,k));
+      tb(i,j,k)=tb(i,j,k)+2.*dti/86400.*taurstr(i,j,k)*
+                (trstr(i,j,k)-tb(i,j,k));
+      s(i,j,k)=s(i,j,k)+2.*dti/86400.*taurstr(i,j,k)*
+               (srstr(i,j,k)-s(i,j,k));
+      sb(i,j,k)=sb(i,j,k)+2.*dti/86400.*taurstr(i,j,k)*
+                (srstr(i,j,k)-sb(i,j,k));
+    }
+  }
+  /* lrestore==0 stands for taurstr==0 everywhere: x + c*0*(y-x) == x for
+   * finite x,y, so only the re-masking :1113-1118 has an effect */
+  DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im) {
+    t(i,j,k)=t(i,j,k)*fsm(i,j);
+    tb(i,j,k)=tb(i,j,k)*fsm(i,j);
+    s(i,j,k)=s(i,j,k)*fsm(i,j);
+    sb(i,j,k)=sb(i,j,k)*fsm(i,j);
+  }
+}
