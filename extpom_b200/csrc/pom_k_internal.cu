@@ -1,0 +1,897 @@
+// pom_k_internal.cu -- the 3-D internal mode (advance.f:356-537) and the
+// solver.f kernels it drives.  One thread per (i,j) column marching in k; the
+// tridiagonal (Thomas) sweeps keep their ee/gg coefficients in per-thread
+// arrays so no a/c/ee/gg 3-D temporaries (solver.f:1224-1230,1552-1554,
+// 1692-1693) ever reach HBM.  Expression order follows the Fortran.
+#include "pom_core.h"
+#include "pom_names.h"
+
+#define KMAX 64
+
+namespace pom {
+
+// ---------------------------------------------------------------------------
+// advance.f:365-393: adjust u(z), v(z) so that their depth means match (utb+utf)
+struct UvAdjustK : KBase {
+  using KBase::KBase;
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    double tu = 0., tv = 0.;
+    for (int k = 1; k <= kbm1; ++k) {
+      tu=tu+u(i,j,k)*dz(k);
+      tv=tv+v(i,j,k)*dz(k);
+    }
+    if (i >= 2) {
+      const double r=(utb(i,j)+utf(i,j))/(dt(i,j)+dt(i-1,j));
+      for (int k = 1; k <= kbm1; ++k) u(i,j,k)=(u(i,j,k)-tu)+r;
+    }
+    if (j >= 2) {
+      const double r=(vtb(i,j)+vtf(i,j))/(dt(i,j)+dt(i,j-1));
+      for (int k = 1; k <= kbm1; ++k) v(i,j,k)=(v(i,j,k)-tv)+r;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// vertvl (solver.f:1970-2021) + bcondorl(5) (bounds_forcing.f:553-559)
+struct VertvlK : KBase {
+  using KBase::KBase;
+  POM_HD double xf(int i, int j, int k) const {   // :1984-1985
+    return .25*(dy(i,j)+dy(i-1,j))*(dt(i,j)+dt(i-1,j))*u(i,j,k);
+  }
+  POM_HD double yf(int i, int j, int k) const {   // :1993-1994
+    return .25*(dx(i,j)+dx(i,j-1))*(dt(i,j)+dt(i,j-1))*v(i,j,k);
+  }
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    const double m = fsm(i,j);
+    if (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1) {
+      double wk=0.5*(vfluxb(i,j)+vfluxf(i,j));                          // :2004
+      const double dxy=dx(i,j)*dy(i,j);
+      const double de=(etf(i,j)-etb(i,j))/dti2;
+      for (int k = 1; k <= kbm1; ++k) {
+        w(i,j,k)=wk*m;
+        wk=wk+dz(k)*((xf(i+1,j,k)-xf(i,j,k)+yf(i,j+1,k)-yf(i,j,k))/dxy+de);   // :2011-2015
+      }
+      w(i,j,kb)=wk;
+    } else {
+      for (int k = 1; k <= kbm1; ++k) w(i,j,k)=w(i,j,k)*m;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// advq (solver.f:411-477) for q2 -> uf and q2l -> vf in one pass
+struct AdvqK : KBase {
+  using KBase::KBase;
+  POM_HD double xfl(const double* q, const double* qb, int i, int j, int k) const {
+    double a=.125*(A3(q,i,j,k)+A3(q,i-1,j,k))*(dt(i,j)+dt(i-1,j))*(u(i,j,k)+u(i,j,k-1));   // :428-429
+    a=a-.25*(aam(i,j,k)+aam(i-1,j,k)+aam(i,j,k-1)+aam(i-1,j,k-1))
+         *(h(i,j)+h(i-1,j))
+         *(A3(qb,i,j,k)-A3(qb,i-1,j,k))*dum(i,j)
+         /(dx(i,j)+dx(i-1,j));                                          // :440-445
+    return .5*(dy(i,j)+dy(i-1,j))*a;                                    // :452
+  }
+  POM_HD double yfl(const double* q, const double* qb, int i, int j, int k) const {
+    double a=.125*(A3(q,i,j,k)+A3(q,i,j-1,k))*(dt(i,j)+dt(i,j-1))*(v(i,j,k)+v(i,j,k-1));   // :430-431
+    a=a-.25*(aam(i,j,k)+aam(i,j-1,k)+aam(i,j,k-1)+aam(i,j-1,k-1))
+         *(h(i,j)+h(i,j-1))
+         *(A3(qb,i,j,k)-A3(qb,i,j-1,k))*dvm(i,j)
+         /(dy(i,j)+dy(i,j-1));                                          // :446-451
+    return .5*(dx(i,j)+dx(i,j-1))*a;                                    // :453
+  }
+  POM_HD double qfv(const double* q, const double* qb, int i, int j, int k) const {
+    double r=(w(i,j,k-1)*A3(q,i,j,k-1)-w(i,j,k+1)*A3(q,i,j,k+1))
+             *art(i,j)/(dz(k)+dz(k-1))
+             +xfl(q,qb,i+1,j,k)-xfl(q,qb,i,j,k)
+             +yfl(q,qb,i,j+1,k)-yfl(q,qb,i,j,k);                        // :465-468
+    return ((h(i,j)+etb(i,j))*art(i,j)*A3(qb,i,j,k)-dti2*r)
+           /((h(i,j)+etf(i,j))*art(i,j));                               // :469-471
+  }
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    const bool interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
+    uf(i,j,1)=0.; vf(i,j,1)=0.;                                         // advance.f:403-404
+    uf(i,j,kb)=0.; vf(i,j,kb)=0.;
+    for (int k = 2; k <= kbm1; ++k) {
+      double a = 0., b = 0.;
+      if (interior) {
+        a=qfv(p.q2,p.q2b,i,j,k);
+        b=qfv(p.q2l,p.q2lb,i,j,k);
+      }
+      uf(i,j,k)=a;
+      vf(i,j,k)=b;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// profq (solver.f:1212-1538): Mellor-Yamada 2.5 with the wave-breaking surface
+// condition; two Thomas solves per column (q2 -> uf, q2l -> vf), then km,kh,kq.
+struct ProfqK : KBase {
+  double cgg, const1;
+  ProfqK(const Ctx* x) : KBase(x) {
+    // solver.f:1297: (15.8*cbcnst)**(2./3.) with single-precision literals promoted
+    // to double; solver.f:1273 const1
+    const double cbcnst = 100.;
+    cgg = pow((double)15.8f * cbcnst, (double)(2.f / 3.f));
+    const1 = pow(16.6, 2. / 3.) * 1.;
+  }
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    const double a1 = 0.92, b1 = 16.6, a2 = 0.74, b2 = 10.1, c1 = 0.08;     // :1241
+    const double e1 = 1.8, e2 = 1.33, sef = 1., surfl = 2.e5, shiw = 0.;     // :1242-1244
+    double ee[KMAX], gg[KMAX], lk[KMAX], ghk[KMAX], prk[KMAX], dtk[KMAX];
+    const bool interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
+    const double dh=h(i,j)+etf(i,j);                                          // :1248
+    double utau2 = 0.;
+    if (i <= imm1 && j <= jmm1) {                                             // :1281-1288
+      double su=.5*(wusurf(i,j)+wusurf(i+1,j)), sv=.5*(wvsurf(i,j)+wvsurf(i,j+1));
+      utau2=sqrt(su*su+sv*sv);
+      double bu=.5*(wubot(i,j)+wubot(i+1,j)), bv=.5*(wvbot(i,j)+wvbot(i,j+1));
+      uf(i,j,kb)=sqrt(bu*bu+bv*bv)*const1;
+    }
+    const double l0=surfl*utau2/grav;                                         // :1299
+    ee[1]=0.;                                                                 // :1296
+    gg[1]=cgg*utau2;                                                          // :1297
+    // speed of sound squared (:1304-1319), buoyancy gradient (:1322-1333),
+    // length scale and gh (:1335-1356), production (:1359-1373)
+    lk[1]=kappa*l0; lk[kb]=0.; ghk[1]=0.; ghk[kb]=0.;
+    double ccm = 0.;  // cc(k-1)
+    {
+      double tp=t(i,j,1)+tbias, sp=s(i,j,1)+sbias;
+      double pp=grav*rhoref*(-zz(1)*h(i,j))*1.e-4;
+      double cv=1449.1+.00821*pp+4.55*tp-.045*(tp*tp)+1.34*(sp-35.0);
+      ccm=cv/sqrt((1.-.01642*pp/cv)*(1.-0.40*pp/(cv*cv)));
+    }
+    for (int k = 2; k <= kbm1; ++k) {
+      double tp=t(i,j,k)+tbias, sp=s(i,j,k)+sbias;
+      double pp=grav*rhoref*(-zz(k)*h(i,j))*1.e-4;
+      double cv=1449.1+.00821*pp+4.55*tp-.045*(tp*tp)+1.34*(sp-35.0);
+      double cck=cv/sqrt((1.-.01642*pp/cv)*(1.-0.40*pp/(cv*cv)));
+      double qb=fabs(q2b(i,j,k)), qlb=fabs(q2lb(i,j,k));
+      q2b(i,j,k)=qb;                                                          // :1325-1326
+      q2lb(i,j,k)=qlb;
+      double boygr=grav*(rho(i,j,k-1)-rho(i,j,k))/(dzz(k-1)*h(i,j))
+                   +(grav*grav)*2./(ccm*ccm+cck*cck);                         // :1327-1330
+      ccm=cck;
+      double ll=fabs(qlb/qb);                                                 // :1338
+      if (z(k) > -0.5) ll=fmax(ll,kappa*l0);                                  // :1339
+      double gh=(ll*ll)*boygr/qb;                                             // :1343
+      gh=fmin(gh,.028);                                                       // :1344
+      lk[k]=ll; ghk[k]=gh;
+      double pr = 0.;
+      if (interior) {
+        double su=u(i,j,k)-u(i,j,k-1)+u(i+1,j,k)-u(i+1,j,k-1);
+        double sv=v(i,j,k)-v(i,j,k-1)+v(i,j+1,k)-v(i,j+1,k-1);
+        double dd=dzz(k-1)*dh;
+        pr=km(i,j,k)*.25*sef*(su*su+sv*sv)/(dd*dd)-shiw*km(i,j,k)*boygr;      // :1362-1369
+        pr=pr+kh(i,j,k)*boygr;                                                // :1370
+      }
+      prk[k]=pr;
+    }
+    // :1380-1392 dtef for k=1..kb (stf=1)
+    for (int k = 1; k <= kb; ++k)
+      dtk[k]=sqrt(fabs(q2b(i,j,k)))*1./(b1*lk[k]+small);
+    // Boundary columns: the reference solves them too, but bcond(6) overwrites uf,vf there
+    // right after (advance.f:414), so the solves are skipped on those columns.
+    if (interior) {
+    // q2 solve (:1258-1267 a,c; :1394-1413)
+      for (int k = 2; k <= kbm1; ++k) {
+        double a=-dti2*(kq(i,j,k+1)+kq(i,j,k)+2.*umol)*.5/(dzz(k-1)*dz(k)*dh*dh);
+        double cq=-dti2*(kq(i,j,k-1)+kq(i,j,k)+2.*umol)*.5/(dzz(k-1)*dz(k-1)*dh*dh);
+        double gi=1./(a+cq*(1.-ee[k-1])-(2.*dti2*dtk[k]+1.));
+        ee[k]=a*gi;
+        gg[k]=(-2.*dti2*prk[k]+cq*gg[k-1]-uf(i,j,k))*gi;
+      }
+      {
+        double up=uf(i,j,kb);
+        for (int ki = kbm1; ki >= 1; --ki) {
+          up=ee[ki]*up+gg[ki];
+          uf(i,j,ki)=(ki >= 2) ? fabs(up) : up;                                 // :1410, :1467
+        }
+      }
+      // q2l solve (:1417-1455)
+      ee[2]=0.;
+      gg[2]=-kappa*z(2)*dh*q2(i,j,2);
+      for (int k = 2; k <= kbm1; ++k) {                                         // :1426-1435
+        double r=(1./fabs(z(k)-z(1))+1./fabs(z(k)-z(kb)))*lk[k]/(dh*kappa);
+        dtk[k]=dtk[k]*(1.+e2*(r*r));
+      }
+      for (int k = 3; k <= kbm1; ++k) {
+        double a=-dti2*(kq(i,j,k+1)+kq(i,j,k)+2.*umol)*.5/(dzz(k-1)*dz(k)*dh*dh);
+        double cq=-dti2*(kq(i,j,k-1)+kq(i,j,k)+2.*umol)*.5/(dzz(k-1)*dz(k-1)*dh*dh);
+        double gi=1./(a+cq*(1.-ee[k-1])-(dti2*dtk[k]+1.));
+        ee[k]=a*gi;
+        // :1423 assigns vf(kbm1)=kappa*(1+z(kbm1))*dh*q2(kbm1) before this sweep reads it
+        double vk=(k == kbm1) ? kappa*(1+z(kbm1))*dh*q2(i,j,kbm1) : vf(i,j,k);
+        gg[k]=(dti2*(-prk[k]*lk[k]*e1)+cq*gg[k-1]-vk)*gi;
+      }
+      {
+        double vp = 0.;                                                         // vf(kb)=0 (:1420)
+        vf(i,j,kb)=0.;
+        for (int ki = kbm1; ki >= 2; --ki) {
+          vp=ee[ki]*vp+gg[ki];
+          vf(i,j,ki)=fabs(vp);                                                  // :1452, :1468
+        }
+        vf(i,j,1)=0.;                                                           // :1419
+      }
+    }
+    // note: the Thomas recurrences above use the signed iterate (up, vp); abs() is
+    // applied by the reference only after both back-substitutions (:1460-1471)
+    // km, kh, kq (:1474-1506), cosmetics (:1510-1529) and mask (:1531-1535)
+    const double coef4=18.*a1*a1+9.*a1*a2, coef5=9.*a1*a2;
+    const double coef1=a2*(1.-6.*a1/b1*1.);
+    const double coef2=3.*a2*b2/1.+18.*a1*a2;
+    const double coef3=a1*(1.-3.*c1-6.*a1/b1*1.);
+    const double m = fsm(i,j);
+    for (int k = 1; k <= kb; ++k) {
+      l(i,j,k)=lk[k];
+      double sh=coef1/(1.-coef2*ghk[k]);
+      double sm=coef3+sh*coef4*ghk[k];
+      sm=sm/(1.-coef5*ghk[k]);
+      double pr=lk[k]*sqrt(fabs(q2(i,j,k)));
+      double nkq=(pr*.41*sh+kq(i,j,k))*.5;
+      double nkm=(pr*sm+km(i,j,k))*.5;
+      double nkh=(pr*sh+kh(i,j,k))*.5;
+      if (interior) {
+        kq(i,j,k)=nkq*m; km(i,j,k)=nkm*m; kh(i,j,k)=nkh*m;
+        // boundary columns copy the neighbouring interior value (N,S,E,W order =
+        // index clamped into the interior), then take their own mask
+        const int il = (i == 2) ? 1 : 0, ir = (i == imm1) ? 1 : 0;
+        const int jl = (j == 2) ? 1 : 0, jr = (j == jmm1) ? 1 : 0;
+        for (int dj = -jl; dj <= jr; ++dj)
+          for (int di = -il; di <= ir; ++di) {
+            if (di == 0 && dj == 0) continue;
+            const double me = fsm(i+di,j+dj);
+            kq(i+di,j+dj,k)=nkq*me; km(i+di,j+dj,k)=nkm*me; kh(i+di,j+dj,k)=nkh*me;
+          }
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// bcond(6) (bounds_forcing.f:257-324) + Asselin filter and rotation of q2,q2l
+// (advance.f:416-421).  Filtered q2 -> q2b buffer, new q2 stays in uf; the host
+// rotates pointers.
+struct QFilterK : KBase {
+  using KBase::KBase;
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    const double m = fsm(i,j);
+    for (int k = 1; k <= kb; ++k) {
+      double a=uf(i,j,k), b=vf(i,j,k);
+      if (j == 1) {                                                     // south (:290-299)
+        double u1=2.*v(i,2,k)*dti/(dy(i,1)+dy(i,2));
+        if (u1 >= 0.) { a=q2(i,1,k)-u1*(q2(i,1,k)-small); b=q2l(i,1,k)-u1*(q2l(i,1,k)-small); }
+        else { a=q2(i,1,k)-u1*(q2(i,2,k)-q2(i,1,k)); b=q2l(i,1,k)-u1*(q2l(i,2,k)-q2l(i,1,k)); }
+      } else if (j == jm) {                                             // north (:302-311)
+        double u1=2.*v(i,jm,k)*dti/(dy(i,jm)+dy(i,jmm1));
+        if (u1 <= 0.) { a=q2(i,jm,k)-u1*(small-q2(i,jm,k)); b=q2l(i,jm,k)-u1*(small-q2l(i,jm,k)); }
+        else { a=q2(i,jm,k)-u1*(q2(i,jm,k)-q2(i,jmm1,k)); b=q2l(i,jm,k)-u1*(q2l(i,jm,k)-q2l(i,jmm1,k)); }
+      } else if (i == 1) {                                              // west (:264-273)
+        double u1=2.*u(2,j,k)*dti/(dx(1,j)+dx(2,j));
+        if (u1 >= 0.) { a=q2(1,j,k)-u1*(q2(1,j,k)-small); b=q2l(1,j,k)-u1*(q2l(1,j,k)-small); }
+        else { a=q2(1,j,k)-u1*(q2(2,j,k)-q2(1,j,k)); b=q2l(1,j,k)-u1*(q2l(2,j,k)-q2l(1,j,k)); }
+      } else if (i == im) {                                             // east (:276-285)
+        double u1=2.*u(im,j,k)*dti/(dx(im,j)+dx(imm1,j));
+        if (u1 <= 0.) { a=q2(im,j,k)-u1*(small-q2(im,j,k)); b=q2l(im,j,k)-u1*(small-q2l(im,j,k)); }
+        else { a=q2(im,j,k)-u1*(q2(im,j,k)-q2(imm1,j,k)); b=q2l(im,j,k)-u1*(q2l(im,j,k)-q2l(imm1,j,k)); }
+      }
+      a=a*m+1.e-10;                                                     // :318-319
+      b=b*m+1.e-10;
+      uf(i,j,k)=a;
+      vf(i,j,k)=b;
+      q2b(i,j,k)=q2(i,j,k)+.5*smoth*(a+q2b(i,j,k)-2.*q2(i,j,k));        // advance.f:416,418
+      q2lb(i,j,k)=q2l(i,j,k)+.5*smoth*(b+q2lb(i,j,k)-2.*q2l(i,j,k));    // advance.f:417,420
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// advt2 with nitera=1 (solver.f:577-731 + the fsm mask of smol_adif :1898-1900):
+// upstream advection, leapfrog update, horizontal diffusion of (fb-fclim).
+struct AdvT2K : KBase {
+  const double *fb_, *f_, *fc_;
+  double* ff_;
+  AdvT2K(const Ctx* x, const double* fb, const double* f, const double* fc, double* ff)
+      : KBase(x), fb_(fb), f_(f), fc_(fc), ff_(ff) {}
+  POM_HD double xfl(int i, int j, int k) const {                        // :605-606, :631-635
+    double xm=0.25*(dy(i-1,j)+dy(i,j))*(dt(i-1,j)+dt(i,j))*u(i,j,k);
+    return 0.5*((xm+fabs(xm))*A3(fb_,i-1,j,k)+(xm-fabs(xm))*A3(fb_,i,j,k));
+  }
+  POM_HD double yfl(int i, int j, int k) const {                        // :612-613, :637-641
+    double ym=0.25*(dx(i,j-1)+dx(i,j))*(dt(i,j-1)+dt(i,j))*v(i,j,k);
+    return 0.5*((ym+fabs(ym))*A3(fb_,i,j-1,k)+(ym-fabs(ym))*A3(fb_,i,j,k));
+  }
+  POM_HD double fbd(int i, int j, int k) const { return A3(fb_,i,j,k)-A3(fc_,i,j,k); }   // :691
+  POM_HD double xdf(int i, int j, int k) const {                        // :696, :705-707
+    double xm=0.5*(aam(i,j,k)+aam(i-1,j,k));
+    return -xm*(h(i,j)+h(i-1,j))*tprni*(fbd(i,j,k)-fbd(i-1,j,k))*dum(i,j)
+           *(dy(i,j)+dy(i-1,j))*0.5/(dx(i,j)+dx(i-1,j));
+  }
+  POM_HD double ydf(int i, int j, int k) const {                        // :697, :708-710
+    double ym=0.5*(aam(i,j,k)+aam(i,j-1,k));
+    return -ym*(h(i,j)+h(i,j-1))*tprni*(fbd(i,j,k)-fbd(i,j-1,k))*dvm(i,j)
+           *(dx(i,j)+dx(i,j-1))*0.5/(dy(i,j)+dy(i,j-1));
+  }
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    if (!(i >= 2 && i <= imm1 && j >= 2 && j <= jmm1)) {
+      // ff is not assigned here by the reference; bcond(4) sets it afterwards
+      for (int k = 1; k <= kb; ++k) A3(ff_,i,j,k)=A3(ff_,i,j,k)*fsm(i,j);
+      return;
+    }
+    const double m=fsm(i,j);
+    A3(ff_,i,j,kb)=A3(ff_,i,j,kb)*m;
+    const double ar=art(i,j);
+    const double eb=(h(i,j)+etb(i,j))*ar, ef=(h(i,j)+etf(i,j))*ar;
+    double zk=w(i,j,1)*A3(f_,i,j,1)*ar;                                 // :648 (itera==1)
+    for (int k = 1; k <= kbm1; ++k) {
+      double zk1 = 0.;                                                  // zflux(k+1); :651 at kb
+      if (k + 1 <= kbm1) {
+        double zw=w(i,j,k+1);
+        zk1=0.5*((zw+fabs(zw))*A3(fb_,i,j,k+1)+(zw-fabs(zw))*A3(fb_,i,j,k));   // :656-660
+        zk1=zk1*ar;                                                     // :661
+      }
+      double r=xfl(i+1,j,k)-xfl(i,j,k)+yfl(i,j+1,k)-yfl(i,j,k)+(zk-zk1)/dz(k);   // :670-672
+      r=(A3(fb_,i,j,k)*eb-dti2*r)/ef;                                   // :673-674
+      r=r*m;                                                            // smol_adif :1899
+      r=r-dti2*(xdf(i+1,j,k)-xdf(i,j,k)+ydf(i,j+1,k)-ydf(i,j,k))/ef;    // :721-723
+      A3(ff_,i,j,k)=r;
+      zk=zk1;
+    }
+  }
+};
+
+// advt1 (solver.f:480-574): centred advection + diffusion of (fb-fclim)
+struct AdvT1K : KBase {
+  const double *fb_, *f_, *fc_;
+  double* ff_;
+  AdvT1K(const Ctx* x, const double* fb, const double* f, const double* fc, double* ff)
+      : KBase(x), fb_(fb), f_(f), fc_(fc), ff_(ff) {}
+  POM_HD double fbd(int i, int j, int k) const { return A3(fb_,i,j,k)-A3(fc_,i,j,k); }   // :511
+  POM_HD double xfl(int i, int j, int k) const {
+    double a=.25*((dt(i,j)+dt(i-1,j))*(A3(f_,i,j,k)+A3(f_,i-1,j,k))*u(i,j,k));          // :502-503
+    a=a-.5*(aam(i,j,k)+aam(i-1,j,k))*(h(i,j)+h(i-1,j))*tprni
+        *(fbd(i,j,k)-fbd(i-1,j,k))*dum(i,j)/(dx(i,j)+dx(i-1,j));                        // :516-520
+    return .5*(dy(i,j)+dy(i-1,j))*a;                                                    // :526
+  }
+  POM_HD double yfl(int i, int j, int k) const {
+    double a=.25*((dt(i,j)+dt(i,j-1))*(A3(f_,i,j,k)+A3(f_,i,j-1,k))*v(i,j,k));          // :504-505
+    a=a-.5*(aam(i,j,k)+aam(i,j-1,k))*(h(i,j)+h(i,j-1))*tprni
+        *(fbd(i,j,k)-fbd(i,j-1,k))*dvm(i,j)/(dy(i,j)+dy(i,j-1));                        // :521-525
+    return .5*(dx(i,j)+dx(i,j-1))*a;                                                    // :527
+  }
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    if (!(i >= 2 && i <= imm1 && j >= 2 && j <= jmm1)) return;
+    const double ar=art(i,j);
+    double zk=A3(f_,i,j,1)*w(i,j,1)*ar;                                 // :537
+    for (int k = 1; k <= kbm1; ++k) {
+      double zk1 = 0.;                                                  // :538 at kb
+      if (k + 1 <= kbm1) zk1=.5*(A3(f_,i,j,k)+A3(f_,i,j,k+1))*w(i,j,k+1)*ar;   // :545
+      double r=xfl(i+1,j,k)-xfl(i,j,k)+yfl(i,j+1,k)-yfl(i,j,k)+(zk-zk1)/dz(k);   // :563-565
+      // (fb-fclim)+fclim is what fb holds when :566 reads it (:511,:532)
+      double fbr=fbd(i,j,k)+A3(fc_,i,j,k);
+      A3(ff_,i,j,k)=(fbr*(h(i,j)+etb(i,j))*ar-dti2*r)/((h(i,j)+etf(i,j))*ar);   // :566-570
+      zk=zk1;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// proft (solver.f:1541-1683): implicit vertical diffusion of one tracer
+struct ProftK : KBase {
+  double* f_;
+  const double *wfsurf_, *fsurf_;
+  int nbc;
+  ProftK(const Ctx* x, double* f, const double* wf, const double* fs, int nb)
+      : KBase(x), f_(f), wfsurf_(wf), fsurf_(fs), nbc(nb) {}
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    double ee[KMAX], gg[KMAX], rad[KMAX];
+    const double dh=h(i,j)+etf(i,j);                                    // :1580
+    const bool pen = (nbc == 2 || nbc == 4);
+    if (pen) {                                                          // :1604-1615
+      const double r[5] = {.58, .62, .67, .77, .78};
+      const double ad1[5] = {.35, .60, 1.0, 1.5, 1.4};
+      const double ad2[5] = {23., 20., 17., 14., 7.9};
+      const int n = c.ntp - 1;
+      for (int k = 1; k <= kbm1; ++k)
+        rad[k]=A2(p.swrad,i,j)*(r[n]*exp(z(k)*dh/ad1[n])+(1.-r[n])*exp(z(k)*dh/ad2[n]));
+      rad[kb]=0.;
+    }
+    // a(k-1), c(k) from kh(k), k=2..kbm1 (:1589-1598); a(kbm1)=0, c(1)=0 (zero fill)
+    double ak=-dti2*(kh(i,j,2)+umol)/(dz(1)*dzz(1)*dh*dh);              // a(1)
+    if (nbc == 1) {                                                     // :1619-1625
+      ee[1]=ak/(ak-1.);
+      gg[1]=dti2*A2(wfsurf_,i,j)/(dz(1)*dh)-A3(f_,i,j,1);
+      gg[1]=gg[1]/(ak-1.);
+    } else if (nbc == 2) {                                              // :1629-1637
+      ee[1]=ak/(ak-1.);
+      gg[1]=dti2*(A2(wfsurf_,i,j)+rad[1]-rad[2])/(dz(1)*dh)-A3(f_,i,j,1);
+      gg[1]=gg[1]/(ak-1.);
+    } else if (nbc == 3 || nbc == 4) {                                  // :1641-1646
+      ee[1]=0.;
+      gg[1]=A2(fsurf_,i,j);
+    } else {
+      ee[1]=0.; gg[1]=0.;
+    }
+    for (int k = 2; k <= kbm2; ++k) {                                   // :1650-1661
+      ak=-dti2*(kh(i,j,k+1)+umol)/(dz(k)*dzz(k)*dh*dh);                 // a(k)
+      double ck=-dti2*(kh(i,j,k)+umol)/(dz(k)*dzz(k-1)*dh*dh);          // c(k)
+      double gi=1./(ak+ck*(1.-ee[k-1])-1.);
+      ee[k]=ak*gi;
+      double rhs=ck*gg[k-1]-A3(f_,i,j,k);
+      if (pen) rhs=rhs+dti2*(rad[k]-rad[k+1])/(dh*dz(k));
+      gg[k]=rhs*gi;
+    }
+    {                                                                   // :1664-1671
+      double ck=-dti2*(kh(i,j,kbm1)+umol)/(dz(kbm1)*dzz(kbm2)*dh*dh);   // c(kbm1)
+      double rhs=ck*gg[kbm2]-A3(f_,i,j,kbm1);
+      if (pen) rhs=rhs+dti2*(rad[kbm1]-rad[kb])/(dh*dz(kbm1));
+      double fk=rhs/(ck*(1.-ee[kbm2])-1.);
+      A3(f_,i,j,kbm1)=fk;
+      for (int ki = kb-2; ki >= 1; --ki) {                              // :1673-1680
+        fk=ee[ki]*fk+gg[ki];
+        A3(f_,i,j,ki)=fk;
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// bcond(4) (bounds_forcing.f:151-242) + Asselin filter/rotation of t,s
+// (advance.f:444-449) + restore_interior arithmetic and mask
+// (bounds_forcing.f:1083-1118).  Filtered t,s -> tb,sb buffers; new t,s stay
+// in uf,vf; the host rotates pointers.
+struct TsFilterK : KBase {
+  double fold, fnew;
+  TsFilterK(const Ctx* x) : KBase(x) {
+    const double trst = 30.;                                             // bounds_forcing.f:1033
+    int ntime = (int)(x->c.time / trst);
+    fnew = x->c.time / trst - ntime;
+    fold = 1. - fnew;
+  }
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    const double m = fsm(i,j);
+    for (int k = 1; k <= kbm1; ++k) {
+      double a=uf(i,j,k), b=vf(i,j,k);
+      const bool vadv = (k != 1 && k != kbm1);
+      if (j == 1) {                                                     // south (:196-211)
+        double u1=2.*v(i,2,k)*dti/(dy(i,1)+dy(i,2));
+        if (u1 >= 0.) {
+          a=t(i,1,k)-u1*(t(i,1,k)-tbs(i,k));
+          b=s(i,1,k)-u1*(s(i,1,k)-sbs(i,k));
+        } else {
+          a=t(i,1,k)-u1*(t(i,2,k)-t(i,1,k));
+          b=s(i,1,k)-u1*(s(i,2,k)-s(i,1,k));
+          if (vadv) {
+            double wm=.5*(w(i,2,k)+w(i,2,k+1))*dti/((zz(k-1)-zz(k+1))*dt(i,2));
+            a=a-wm*(t(i,2,k-1)-t(i,2,k+1));
+            b=b-wm*(s(i,2,k-1)-s(i,2,k+1));
+          }
+        }
+      } else if (j == jm) {                                             // north (:214-229)
+        double u1=2.*v(i,jm,k)*dti/(dy(i,jm)+dy(i,jmm1));
+        if (u1 <= 0.) {
+          a=t(i,jm,k)-u1*(tbn(i,k)-t(i,jm,k));
+          b=s(i,jm,k)-u1*(sbn(i,k)-s(i,jm,k));
+        } else {
+          a=t(i,jm,k)-u1*(t(i,jm,k)-t(i,jmm1,k));
+          b=s(i,jm,k)-u1*(s(i,jm,k)-s(i,jmm1,k));
+          if (vadv) {
+            double wm=.5*(w(i,jmm1,k)+w(i,jmm1,k+1))*dti/((zz(k-1)-zz(k+1))*dt(i,jmm1));
+            a=a-wm*(t(i,jmm1,k-1)-t(i,jmm1,k+1));
+            b=b-wm*(s(i,jmm1,k-1)-s(i,jmm1,k+1));
+          }
+        }
+      } else if (i == im) {                                             // east (:158-173)
+        double u1=2.*u(im,j,k)*dti/(dx(im,j)+dx(imm1,j));
+        if (u1 <= 0.) {
+          a=t(im,j,k)-u1*(tbe(j,k)-t(im,j,k));
+          b=s(im,j,k)-u1*(sbe(j,k)-s(im,j,k));
+        } else {
+          a=t(im,j,k)-u1*(t(im,j,k)-t(imm1,j,k));
+          b=s(im,j,k)-u1*(s(im,j,k)-s(imm1,j,k));
+          if (vadv) {
+            double wm=.5*(w(imm1,j,k)+w(imm1,j,k+1))*dti/((zz(k-1)-zz(k+1))*dt(imm1,j));
+            a=a-wm*(t(imm1,j,k-1)-t(imm1,j,k+1));
+            b=b-wm*(s(imm1,j,k-1)-s(imm1,j,k+1));
+          }
+        }
+      } else if (i == 1) {                                              // west (:176-191)
+        double u1=2.*u(2,j,k)*dti/(dx(1,j)+dx(2,j));
+        if (u1 >= 0.) {
+          a=t(1,j,k)-u1*(t(1,j,k)-tbw(j,k));
+          b=s(1,j,k)-u1*(s(1,j,k)-sbw(j,k));
+        } else {
+          a=t(1,j,k)-u1*(t(2,j,k)-t(1,j,k));
+          b=s(1,j,k)-u1*(s(2,j,k)-s(1,j,k));
+          if (vadv) {
+            double wm=.5*(w(2,j,k)+w(2,j,k+1))*dti/((zz(k-1)-zz(k+1))*dt(2,j));
+            a=a-wm*(t(2,j,k-1)-t(2,j,k+1));
+            b=b-wm*(s(2,j,k-1)-s(2,j,k+1));
+          }
+        }
+      }
+      a=a*m;                                                            // :236-237
+      b=b*m;
+      // tb,sb as left behind by advt1/advt2: (fb-fclim)+fclim (solver.f:691,715)
+      double tbr=(tb(i,j,k)-tclim(i,j,k))+tclim(i,j,k);
+      double sbr=(sb(i,j,k)-sclim(i,j,k))+sclim(i,j,k);
+      double tf=t(i,j,k)+.5*smoth*(a+tbr-2.*t(i,j,k));                  // advance.f:444
+      double sf=s(i,j,k)+.5*smoth*(b+sbr-2.*s(i,j,k));                  // advance.f:445
+      if (c.lrestore) {                                                 // bounds_forcing.f:1083-1110
+        double tr=fold*trstrb(i,j,k)+fnew*trstrf(i,j,k);
+        double sr=fold*srstrb(i,j,k)+fnew*srstrf(i,j,k);
+        double ta=fold*taurstrb(i,j,k)+fnew*taurstrf(i,j,k);
+        a=a+2.*dti/86400.*ta*(tr-a);
+        tf=tf+2.*dti/86400.*ta*(tr-tf);
+        b=b+2.*dti/86400.*ta*(sr-b);
+        sf=sf+2.*dti/86400.*ta*(sr-sf);
+      }
+      uf(i,j,k)=a*m;                                                    // :1113-1118
+      vf(i,j,k)=b*m;
+      tb(i,j,k)=tf*m;
+      sb(i,j,k)=sf*m;
+    }
+  }
+};
+
+// x**1.5 for x>=0, rounded like a correctly-rounded pow(x,1.5): sqrt is IEEE-exact to
+// 0.5 ulp, its residual and the product are recovered exactly with fma.
+POM_HD double pow15(double x) {
+  if (!(x > 0.)) return 0.;
+  double sq=sqrt(x);
+  double res=fma(-sq,sq,x);          // x - sq*sq exactly
+  double ds=res/(2.*sq);             // sqrt(x) = sq + ds
+  double pr=x*sq;
+  double er=fma(x,sq,-pr);           // x*sq = pr + er exactly
+  return pr+(er+x*ds);
+}
+
+// dens (solver.f:1162-1209)
+struct DensK : KBase {
+  const double *si_, *ti_;
+  double* ro_;
+  DensK(const Ctx* x, const double* si, const double* ti, double* ro) : KBase(x), si_(si), ti_(ti), ro_(ro) {}
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    const double m=fsm(i,j), hh=h(i,j);
+    for (int k = 1; k <= kbm1; ++k) {
+      double tr=A3(ti_,i,j,k)+tbias;
+      double sr=A3(si_,i,j,k)+sbias;
+      double tr2=tr*tr, tr3=tr2*tr, tr4=tr3*tr;
+      double pp=grav*rhoref*(-zz(k)*hh)*1.e-5;
+      double rhor=-0.157406+6.793952e-2*tr-9.095290e-3*tr2+1.001685e-4*tr3
+                  -1.120083e-6*tr4+6.536332e-9*tr4*tr;
+      rhor=rhor+(0.824493-4.0899e-3*tr+7.6438e-5*tr2-8.2467e-7*tr3+5.3875e-9*tr4)*sr
+               +(-5.72466e-3+1.0227e-4*tr-1.6546e-6*tr2)*pow15(fabs(sr))
+               +4.8314e-4*sr*sr;
+      double cr=1449.1+.0821*pp+4.55*tr-.045*tr2+1.34*(sr-35.);
+      rhor=rhor+1.e5*pp/(cr*cr)*(1.-2.*pp/(cr*cr));
+      A3(ro_,i,j,k)=rhor/rhoref*m;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// advu / advv (solver.f:734-845)
+struct AdvuK : KBase {
+  using KBase::KBase;
+  POM_HD double vfl(int i, int j, int k) const {                        // :747-748
+    return .25*(w(i,j,k)+w(i-1,j,k))*(u(i,j,k)+u(i,j,k-1));
+  }
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    if (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1) {
+      const double ar=aru(i,j);
+      const double sl=grav*.125*(dt(i,j)+dt(i-1,j))
+                      *(egf(i,j)-egf(i-1,j)+egb(i,j)-egb(i-1,j)
+                        +(e_atmos(i,j)-e_atmos(i-1,j))*2.)
+                      *(dy(i,j)+dy(i-1,j));                             // :765-768
+      const double hb=(h(i,j)+etb(i,j)+h(i-1,j)+etb(i-1,j))*ar;
+      const double hf=(h(i,j)+etf(i,j)+h(i-1,j)+etf(i-1,j))*ar;
+      double fk = 0.;                                                   // uf(i,j,1)=0 (:742)
+      for (int k = 1; k <= kbm1; ++k) {
+        double fk1 = (k + 1 <= kbm1) ? vfl(i,j,k+1) : 0.;
+        double r=advx(i,j,k)+(fk-fk1)*ar/dz(k)
+                 -ar*.25*(cor(i,j)*dt(i,j)*(v(i,j+1,k)+v(i,j,k))
+                          +cor(i-1,j)*dt(i-1,j)*(v(i-1,j+1,k)+v(i-1,j,k)))
+                 +sl+drhox(i,j,k);                                      // :758-769
+        uf(i,j,k)=(hb*ub(i,j,k)-2.*dti2*r)/hf;                          // :778-782
+        fk=fk1;
+      }
+      uf(i,j,kb)=0.;
+    } else {
+      // outside the interior only the vertical-flux intermediate survives (:744-751)
+      uf(i,j,1)=0.; uf(i,j,kb)=0.;
+      for (int k = 2; k <= kbm1; ++k) uf(i,j,k)=(i >= 2) ? vfl(i,j,k) : 0.;
+    }
+  }
+};
+
+struct AdvvK : KBase {
+  using KBase::KBase;
+  POM_HD double vfl(int i, int j, int k) const {                        // :804-805
+    return .25*(w(i,j,k)+w(i,j-1,k))*(v(i,j,k)+v(i,j,k-1));
+  }
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    if (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1) {
+      const double ar=arv(i,j);
+      const double sl=grav*.125*(dt(i,j)+dt(i,j-1))
+                      *(egf(i,j)-egf(i,j-1)+egb(i,j)-egb(i,j-1)
+                        +(e_atmos(i,j)-e_atmos(i,j-1))*2.)
+                      *(dx(i,j)+dx(i,j-1));                             // :822-825
+      const double hb=(h(i,j)+etb(i,j)+h(i,j-1)+etb(i,j-1))*ar;
+      const double hf=(h(i,j)+etf(i,j)+h(i,j-1)+etf(i,j-1))*ar;
+      double fk = 0.;
+      for (int k = 1; k <= kbm1; ++k) {
+        double fk1 = (k + 1 <= kbm1) ? vfl(i,j,k+1) : 0.;
+        double r=advy(i,j,k)+(fk-fk1)*ar/dz(k)
+                 +ar*.25*(cor(i,j)*dt(i,j)*(u(i+1,j,k)+u(i,j,k))
+                          +cor(i,j-1)*dt(i,j-1)*(u(i+1,j-1,k)+u(i,j-1,k)))
+                 +sl+drhoy(i,j,k);                                      // :815-826
+        vf(i,j,k)=(hb*vb(i,j,k)-2.*dti2*r)/hf;                          // :835-839
+        fk=fk1;
+      }
+      vf(i,j,kb)=0.;
+    } else {
+      vf(i,j,1)=0.; vf(i,j,kb)=0.;
+      for (int k = 2; k <= kbm1; ++k) vf(i,j,k)=(j >= 2) ? vfl(i,j,k) : 0.;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// profu / profv (solver.f:1686-1877): implicit vertical viscosity + bottom drag
+struct ProfuK : KBase {
+  using KBase::KBase;
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    if (!(i >= 2 && i <= imm1 && j >= 2 && j <= jmm1)) return;
+    double ee[KMAX], gg[KMAX];
+    const double dh=(h(i,j)+etf(i,j)+h(i-1,j)+etf(i-1,j))*.5;           // :1703
+    double cn=(km(i,j,2)+km(i-1,j,2))*.5;                               // :1715 at k=2
+    double ak=-dti2*(cn+umol)/(dz(1)*dzz(1)*dh*dh);                     // a(1) (:1723)
+    ee[1]=ak/(ak-1.);                                                   // :1733
+    gg[1]=(-dti2*wusurf(i,j)/(-dz(1)*dh)-uf(i,j,1))/(ak-1.);            // :1734-1736
+    double ck=-dti2*(cn+umol)/(dz(2)*dzz(1)*dh*dh);                     // c(2) (:1725)
+    for (int k = 2; k <= kbm2; ++k) {                                   // :1740-1748
+      cn=(km(i,j,k+1)+km(i-1,j,k+1))*.5;
+      ak=-dti2*(cn+umol)/(dz(k)*dzz(k)*dh*dh);                          // a(k)
+      double gi=1./(ak+ck*(1.-ee[k-1])-1.);
+      ee[k]=ak*gi;
+      gg[k]=(ck*gg[k-1]-uf(i,j,k))*gi;
+      ck=-dti2*(cn+umol)/(dz(k+1)*dzz(k)*dh*dh);                        // c(k+1)
+    }
+    // ck == c(kbm1)
+    double vbar=.25*(vb(i,j,kbm1)+vb(i,j+1,kbm1)+vb(i-1,j,kbm1)+vb(i-1,j+1,kbm1));
+    double tp=0.5*(cbc(i,j)+cbc(i-1,j))
+              *sqrt(ub(i,j,kbm1)*ub(i,j,kbm1)+vbar*vbar);               // :1752-1755
+    double fk=(ck*gg[kbm2]-uf(i,j,kbm1))
+              /(tp*dti2/(-dz(kbm1)*dh)-1.-(ee[kbm2]-1.)*ck);            // :1756-1758
+    const double m=dum(i,j);
+    fk=fk*m;                                                            // :1759
+    uf(i,j,kbm1)=fk;
+    wubot(i,j)=-tp*fk;                                                  // :1774
+    for (int ki = kb-2; ki >= 1; --ki) {                                // :1763-1770
+      fk=(ee[ki]*fk+gg[ki])*m;
+      uf(i,j,ki)=fk;
+    }
+  }
+};
+
+struct ProfvK : KBase {
+  using KBase::KBase;
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    if (!(i >= 2 && i <= imm1 && j >= 2 && j <= jmm1)) return;
+    double ee[KMAX], gg[KMAX];
+    const double dh=.5*(h(i,j)+etf(i,j)+h(i,j-1)+etf(i,j-1));           // :1801
+    double cn=(km(i,j,2)+km(i,j-1,2))*.5;                               // :1813
+    double ak=-dti2*(cn+umol)/(dz(1)*dzz(1)*dh*dh);                     // :1821
+    ee[1]=ak/(ak-1.);                                                   // :1831
+    gg[1]=(-dti2*wvsurf(i,j)/(-dz(1)*dh)-vf(i,j,1))/(ak-1.);            // :1832-1833
+    double ck=-dti2*(cn+umol)/(dz(2)*dzz(1)*dh*dh);                     // :1823
+    for (int k = 2; k <= kbm2; ++k) {                                   // :1837-1845
+      cn=(km(i,j,k+1)+km(i,j-1,k+1))*.5;
+      ak=-dti2*(cn+umol)/(dz(k)*dzz(k)*dh*dh);
+      double gi=1./(ak+ck*(1.-ee[k-1])-1.);
+      ee[k]=ak*gi;
+      gg[k]=(ck*gg[k-1]-vf(i,j,k))*gi;
+      ck=-dti2*(cn+umol)/(dz(k+1)*dzz(k)*dh*dh);
+    }
+    double ubar=.25*(ub(i,j,kbm1)+ub(i+1,j,kbm1)+ub(i,j-1,kbm1)+ub(i+1,j-1,kbm1));
+    double tp=0.5*(cbc(i,j)+cbc(i,j-1))
+              *sqrt(ubar*ubar+vb(i,j,kbm1)*vb(i,j,kbm1));               // :1849-1852
+    double fk=(ck*gg[kbm2]-vf(i,j,kbm1))
+              /(tp*dti2/(-dz(kbm1)*dh)-1.-(ee[kbm2]-1.)*ck);            // :1853-1855
+    const double m=dvm(i,j);
+    fk=fk*m;                                                            // :1856
+    vf(i,j,kbm1)=fk;
+    wvbot(i,j)=-tp*fk;                                                  // :1871
+    for (int ki = kb-2; ki >= 1; --ki) {                                // :1860-1867
+      fk=(ee[ki]*fk+gg[ki])*m;
+      vf(i,j,ki)=fk;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// bcondorl(3) (bounds_forcing.f:418-487) + Asselin filter with depth-mean
+// removal and rotation of u,v (advance.f:469-514).  The Orlanski points read ub,vb
+// of their neighbours, so the filtered u,v go to the scratch buffers s3a,s3b (which
+// become ub,vb); new u,v stay in uf,vf; the host rotates pointers.
+struct UvFilterK : KBase {
+  using KBase::KBase;
+  // Orlanski radiation value from the point `1` cell inside (xf1,xb1), two inside (x2),
+  // and the boundary point's own xb0 and x at one inside (x1)
+  POM_HD static double orl(double xf1, double xb1, double x2, double xb0, double x1) {
+    double denom=(xf1+xb1-2.*x2);
+    if (denom == 0.) denom=0.01;
+    double cl=(xb1-xf1)/denom;
+    if (cl > 1.) cl=1.;
+    if (cl < 0.) cl=0.;
+    return (xb0*(1.-cl)+2.*cl*x1)/(1.+cl);
+  }
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    const bool jin = (j >= 2 && j <= jmm1), iin = (i >= 2 && i <= imm1);
+    const double mu=dum(i,j), mv=dvm(i,j);
+    double su = 0., sv = 0.;
+    double nu[KMAX], nv[KMAX];
+    for (int k = 1; k <= kbm1; ++k) {
+      double a=uf(i,j,k), b=vf(i,j,k);
+      if (jin) {
+        if (i == im) {                                                  // east (:425-434)
+          a=orl(uf(im-1,j,k),ub(im-1,j,k),u(im-2,j,k),ub(im,j,k),u(im-1,j,k));
+          b=0.;
+        } else if (i == 2 || i == 1) {                                  // west (:437-447)
+          a=orl(uf(3,j,k),ub(3,j,k),u(4,j,k),ub(2,j,k),u(3,j,k));
+          if (i == 1) b=0.;
+        }
+      }
+      if (iin) {
+        if (j == jm) {                                                  // north (:465-474)
+          b=orl(vf(i,jm-1,k),vb(i,jm-1,k),v(i,jm-2,k),vb(i,jm,k),v(i,jm-1,k));
+          a=0.;
+        } else if (j == 2 || j == 1) {                                  // south (:452-462)
+          b=orl(vf(i,3,k),vb(i,3,k),v(i,4,k),vb(i,2,k),v(i,3,k));
+          if (j == 1) a=0.;
+        }
+      }
+      a=a*mu;                                                           // :481-482
+      b=b*mv;
+      nu[k]=a; nv[k]=b;
+      su=su+(a+ub(i,j,k)-2.*u(i,j,k))*dz(k);                            // advance.f:474-475
+      sv=sv+(b+vb(i,j,k)-2.*v(i,j,k))*dz(k);                            // advance.f:495-496
+    }
+    const bool edge = !(iin && jin) || i == 2 || j == 2;
+    for (int k = 1; k <= kbm1; ++k) {
+      double a=nu[k], b=nv[k];
+      double un=u(i,j,k)+.5*smoth*(a+ub(i,j,k)-2.*u(i,j,k)-su);         // advance.f:483-485
+      double vn=v(i,j,k)+.5*smoth*(b+vb(i,j,k)-2.*v(i,j,k)-sv);         // advance.f:504-506
+      A3(p.s3a,i,j,k)=un;
+      A3(p.s3b,i,j,k)=vn;
+      if (edge) { uf(i,j,k)=a; vf(i,j,k)=b; }   // interior values are already masked (profu :1767)
+    }
+    A3(p.s3a,i,j,kb)=u(i,j,kb);                                         // advance.f:511,513
+    A3(p.s3b,i,j,kb)=v(i,j,kb);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// advance.f:525-531: end-of-step 2-D rotations
+struct EndStep2dK : KBase {
+  using KBase::KBase;
+  POM_HD void operator()(int i, int j) const {
+    egb(i,j)=egf(i,j);
+    etb(i,j)=et(i,j);
+    const double e=etf(i,j);
+    et(i,j)=e;
+    dt(i,j)=h(i,j)+e;
+    utb(i,j)=utf(i,j);
+    vtb(i,j)=vtf(i,j);
+    vfluxb(i,j)=vfluxf(i,j);
+  }
+};
+
+// realvertvl (solver.f:2024-2066)
+struct RealvertvlK : KBase {
+  using KBase::KBase;
+  POM_HD double tp(int i, int j, int k) const { return zz(k)*dt(i,j)+et(i,j); }   // :2036
+  POM_HD double wri(int i, int j, int k) const {                        // :2041-2050
+    double dxr=2.0/(dx(i+1,j)+dx(i,j));
+    double dxl=2.0/(dx(i,j)+dx(i-1,j));
+    double dyt=2.0/(dy(i,j+1)+dy(i,j));
+    double dyb=2.0/(dy(i,j)+dy(i,j-1));
+    return 0.5*(w(i,j,k)+w(i,j,k+1))+0.5*
+           (u(i+1,j,k)*(tp(i+1,j,k)-tp(i,j,k))*dxr+
+            u(i,j,k)*(tp(i,j,k)-tp(i-1,j,k))*dxl+
+            v(i,j+1,k)*(tp(i,j+1,k)-tp(i,j,k))*dyt+
+            v(i,j,k)*(tp(i,j,k)-tp(i,j-1,k))*dyb)
+           +(1.0+zz(k))*(etf(i,j)-etb(i,j))/dti2;
+  }
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    // edge copies S,N then W,E (:2057-2060) = value at the index clamped inside
+    int ic = i < 2 ? 2 : (i > imm1 ? imm1 : i);
+    int jc = j < 2 ? 2 : (j > jmm1 ? jmm1 : j);
+    const double m=fsm(i,j);
+    for (int k = 1; k <= kbm1; ++k) wr(i,j,k)=m*wri(ic,jc,k);           // :2063
+    wr(i,j,kb)=0.;
+  }
+};
+
+// in-place (fb-fclim)+fclim and fb(kb)=fb(kbm1): the side effects advt1/advt2 leave on
+// their fb argument (solver.f:496,511,532 / 618,691,715); used by the unit-mode entry
+struct FbRoundTripK : KBase {
+  double* fb_;
+  const double* fc_;
+  double* f_;
+  FbRoundTripK(const Ctx* x, double* fb, const double* fc, double* f) : KBase(x), fb_(fb), fc_(fc), f_(f) {}
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    A3(fb_,i,j,kb)=A3(fb_,i,j,kbm1);
+    if (f_) A3(f_,i,j,kb)=A3(f_,i,j,kbm1);
+    for (int k = 1; k <= kb; ++k) A3(fb_,i,j,k)=(A3(fb_,i,j,k)-A3(fc_,i,j,k))+A3(fc_,i,j,k);
+  }
+};
+
+#define ALLI 1, c->g.im
+void run_uvadjust(Ctx* c, int j0, int j1) { launch_cols(c, UvAdjustK(c), ALLI, j0, j1); }
+void run_vertvl(Ctx* c, int j0, int j1) { launch_cols(c, VertvlK(c), ALLI, j0, j1); }
+void run_advq(Ctx* c, int j0, int j1) { launch_cols(c, AdvqK(c), ALLI, j0, j1); }
+void run_profq(Ctx* c, int j0, int j1) { launch_cols(c, ProfqK(c), ALLI, j0, j1); }
+void run_qfilter(Ctx* c, int j0, int j1) {
+  launch_cols(c, QFilterK(c), ALLI, j0, j1);
+  Ptrs& p = c->p;
+  double* t;
+  // (q2b,q2,uf) <- (q2b[filtered], uf, old q2 as scratch)  advance.f:418-421
+  t = p.q2; p.q2 = p.uf; p.uf = t;
+  t = p.q2l; p.q2l = p.vf; p.vf = t;
+}
+void run_advt(Ctx* c, int nadv, const double* fb, const double* f, const double* fc, double* ff, int j0, int j1) {
+  if (nadv == 1) launch_cols(c, AdvT1K(c, fb, f, fc, ff), ALLI, j0, j1);
+  else launch_cols(c, AdvT2K(c, fb, f, fc, ff), ALLI, j0, j1);
+}
+void run_fb_roundtrip(Ctx* c, double* fb, const double* fc, double* f, int j0, int j1) {
+  launch_cols(c, FbRoundTripK(c, fb, fc, f), ALLI, j0, j1);
+}
+void run_proft(Ctx* c, double* f, const double* wf, const double* fs, int nbc, int j0, int j1) {
+  launch_cols(c, ProftK(c, f, wf, fs, nbc), ALLI, j0, j1);
+}
+void run_tsfilter(Ctx* c, int j0, int j1) {
+  launch_cols(c, TsFilterK(c), ALLI, j0, j1);
+  Ptrs& p = c->p;
+  double* t;
+  t = p.t; p.t = p.uf; p.uf = t;     // advance.f:446-449
+  t = p.s; p.s = p.vf; p.vf = t;
+}
+void run_dens(Ctx* c, const double* si, const double* ti, double* ro, int j0, int j1) {
+  launch_cols(c, DensK(c, si, ti, ro), ALLI, j0, j1);
+}
+void run_advu(Ctx* c, int j0, int j1) { launch_cols(c, AdvuK(c), ALLI, j0, j1); }
+void run_advv(Ctx* c, int j0, int j1) { launch_cols(c, AdvvK(c), ALLI, j0, j1); }
+void run_profu(Ctx* c, int j0, int j1) { launch_cols(c, ProfuK(c), ALLI, j0, j1); }
+void run_profv(Ctx* c, int j0, int j1) { launch_cols(c, ProfvK(c), ALLI, j0, j1); }
+void run_uvfilter(Ctx* c, int j0, int j1) {
+  launch_cols(c, UvFilterK(c), ALLI, j0, j1);
+  Ptrs& p = c->p;
+  double* t;
+  // (ub,u,uf,s3a) <- (s3a[filtered], uf, old u, old ub)   advance.f:511-514
+  t = p.u; p.u = p.uf; p.uf = t;
+  t = p.v; p.v = p.vf; p.vf = t;
+  t = p.ub; p.ub = p.s3a; p.s3a = t;
+  t = p.vb; p.vb = p.s3b; p.s3b = t;
+}
+void run_endstep2d(Ctx* c, int j0, int j1) { launch_cols(c, EndStep2dK(c), ALLI, j0, j1); }
+void run_realvertvl(Ctx* c, int j0, int j1) { launch_cols(c, RealvertvlK(c), ALLI, j0, j1); }
+
+}  // namespace pom

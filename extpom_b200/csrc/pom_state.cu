@@ -1,0 +1,217 @@
+// pom_state.cu -- context lifecycle, field registry and host<->HBM transfers.
+// Device copies of the reference's COMMON blocks (pom.h_dist:142-198,208-212,
+// 291-364,410-450,532-608) with run-time extents; the driver's host arrays stay
+// authoritative only at init, after a pull, and for per-step forcing pushes
+// (SURVEY.md 8(b)).
+#include "pom_core.h"
+#include <cstdlib>
+
+namespace pom {
+
+static const FieldInfo g_fields[] = {
+#define X(n) {#n, K3D, offsetof(Ptrs, n), false, false},
+    POM_F3D(X)
+#undef X
+#define X(n) {#n, K3D, offsetof(Ptrs, n), true, false},
+    POM_F3D_OPT(X)
+#undef X
+#define X(n) {#n, K3D, offsetof(Ptrs, n), false, true},
+    POM_F3D_SCR(X)
+#undef X
+#define X(n) {#n, K2D, offsetof(Ptrs, n), false, false},
+    POM_F2D(X)
+#undef X
+#define X(n) {#n, K2D, offsetof(Ptrs, n), false, true},
+    POM_F2D_SCR(X)
+#undef X
+#define X(n) {#n, KBJ, offsetof(Ptrs, n), false, false},
+    POM_BJ(X)
+#undef X
+#define X(n) {#n, KBI, offsetof(Ptrs, n), false, false},
+    POM_BI(X)
+#undef X
+#define X(n) {#n, KBJK, offsetof(Ptrs, n), false, false},
+    POM_BJK(X)
+#undef X
+#define X(n) {#n, KBIK, offsetof(Ptrs, n), false, false},
+    POM_BIK(X)
+#undef X
+#define X(n) {#n, K1D, offsetof(Ptrs, n), false, false},
+    POM_F1D(X)
+#undef X
+};
+
+const FieldInfo* field_table(int* n) {
+  *n = (int)(sizeof(g_fields) / sizeof(g_fields[0]));
+  return g_fields;
+}
+
+const FieldInfo* find_field(const char* name) {
+  int n;
+  const FieldInfo* t = field_table(&n);
+  for (int i = 0; i < n; ++i)
+    if (!strcmp(t[i].name, name)) return &t[i];
+  return nullptr;
+}
+
+size_t field_elems(const Ctx* c, const FieldInfo* f) {
+  const Geo& g = c->g;
+  switch (f->kind) {
+    case K3D: return g.n2 * g.kb;
+    case K2D: return g.n2;
+    case KBJ: return g.jml;
+    case KBI: return g.im;
+    case KBJK: return (size_t)g.jml * g.kb;
+    case KBIK: return (size_t)g.im * g.kb;
+    case K1D: return g.kb;
+  }
+  return 0;
+}
+
+// ---- backend -----------------------------------------------------------------
+#ifdef POMGPU_EMU
+int dev_init(Ctx* c) { c->stream = nullptr; c->d_red = (double*)calloc(4096, 8); c->h_red = (double*)calloc(4096, 8); return 0; }
+int dev_alloc(Ctx*, double** p, size_t n) { *p = (double*)calloc(n ? n : 1, sizeof(double)); return *p ? 0 : 1; }
+void dev_free(Ctx*, double* p) { free(p); }
+int dev_h2d(Ctx*, double* d, const double* s, size_t n) { memcpy(d, s, n * 8); return 0; }
+int dev_d2h(Ctx*, double* d, const double* s, size_t n) { memcpy(d, s, n * 8); return 0; }
+int dev_d2d(Ctx*, double* d, const double* s, size_t n) { memmove(d, s, n * 8); return 0; }
+int dev_zero(Ctx*, double* p, size_t n) { memset(p, 0, n * 8); return 0; }
+int dev_sync(Ctx*) { return 0; }
+#else
+static int cuda_fail(Ctx* c, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  snprintf(c->err, sizeof(c->err), "CUDA error in %s: %s", what, cudaGetErrorString(e));
+  fprintf(stderr, "pomgpu: %s\n", c->err);
+  c->c.error_status = 1;  // reference error convention (advance.f:118,556-563)
+  return 1;
+}
+int dev_init(Ctx* c) {
+  int n = 0;
+  if (cuda_fail(c, cudaGetDeviceCount(&n), "cudaGetDeviceCount") || n == 0) {
+    snprintf(c->err, sizeof(c->err), "no CUDA device: libpomgpu has no CPU fallback");
+    fprintf(stderr, "pomgpu: %s\n", c->err);
+    return 1;
+  }
+  if (cuda_fail(c, cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+  cudaStream_t s;
+  if (cuda_fail(c, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
+  c->stream = (void*)s;
+  if (cuda_fail(c, cudaMalloc((void**)&c->d_red, 4096 * 8), "cudaMalloc")) return 1;
+  if (cuda_fail(c, cudaMallocHost((void**)&c->h_red, 4096 * 8), "cudaMallocHost")) return 1;
+  return 0;
+}
+int dev_alloc(Ctx* c, double** p, size_t n) {
+  cudaSetDevice(c->device);
+  if (cuda_fail(c, cudaMalloc((void**)p, (n ? n : 1) * sizeof(double)), "cudaMalloc")) return 1;
+  return cuda_fail(c, cudaMemsetAsync(*p, 0, (n ? n : 1) * sizeof(double), (cudaStream_t)c->stream), "cudaMemset");
+}
+void dev_free(Ctx* c, double* p) { cudaSetDevice(c->device); cudaFree(p); }
+int dev_h2d(Ctx* c, double* d, const double* s, size_t n) {
+  cudaSetDevice(c->device);
+  if (cuda_fail(c, cudaMemcpyAsync(d, s, n * 8, cudaMemcpyHostToDevice, (cudaStream_t)c->stream), "H2D")) return 1;
+  return cuda_fail(c, cudaStreamSynchronize((cudaStream_t)c->stream), "H2D sync");
+}
+int dev_d2h(Ctx* c, double* d, const double* s, size_t n) {
+  cudaSetDevice(c->device);
+  if (cuda_fail(c, cudaMemcpyAsync(d, s, n * 8, cudaMemcpyDeviceToHost, (cudaStream_t)c->stream), "D2H")) return 1;
+  return cuda_fail(c, cudaStreamSynchronize((cudaStream_t)c->stream), "D2H sync");
+}
+int dev_d2d(Ctx* c, double* d, const double* s, size_t n) {
+  return cuda_fail(c, cudaMemcpyAsync(d, s, n * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)c->stream), "D2D");
+}
+int dev_zero(Ctx* c, double* p, size_t n) {
+  return cuda_fail(c, cudaMemsetAsync(p, 0, n * 8, (cudaStream_t)c->stream), "memset");
+}
+int dev_sync(Ctx* c) {
+  cudaSetDevice(c->device);
+  if (cuda_fail(c, cudaStreamSynchronize((cudaStream_t)c->stream), "stream sync")) return 1;
+  return cuda_fail(c, cudaGetLastError(), "kernel launch");
+}
+#endif
+
+// ---- lifecycle ------------------------------------------------------------------
+Ctx* ctx_create(int im, int jm_global, int kb, int j_first, int j_last, int ghost, int device) {
+  if (im < 6 || jm_global < 6 || kb < 4 || kb > 128) return nullptr;
+  Ctx* c = (Ctx*)calloc(1, sizeof(Ctx));
+  c->device = device;
+  c->jown0 = j_first; c->jown1 = j_last; c->ghost = ghost;
+  int r0 = j_first - ghost; if (r0 < 1) r0 = 1;
+  int r1 = j_last + ghost; if (r1 > jm_global) r1 = jm_global;
+  c->g.im = im; c->g.kb = kb; c->g.jmg = jm_global;
+  c->g.joff = r0 - 1; c->g.jml = r1 - r0 + 1;
+  c->g.n2 = (size_t)im * c->g.jml;
+  if (dev_init(c)) { free(c); return nullptr; }
+  int n;
+  const FieldInfo* t = field_table(&n);
+  for (int i = 0; i < n; ++i) {
+    double** slot = (double**)((char*)&c->p + t[i].offset);
+    *slot = nullptr;
+    if (t[i].optional) continue;
+    if (dev_alloc(c, slot, field_elems(c, &t[i]))) { return nullptr; }
+  }
+  dev_sync(c);
+  return c;
+}
+
+void ctx_destroy(Ctx* c) {
+  if (!c) return;
+  int n;
+  const FieldInfo* t = field_table(&n);
+  dev_sync(c);
+  for (int i = 0; i < n; ++i) {
+    double** slot = (double**)((char*)&c->p + t[i].offset);
+    if (*slot) dev_free(c, *slot);
+  }
+#ifdef POMGPU_EMU
+  free(c->d_red); free(c->h_red);
+#else
+  cudaFree(c->d_red); cudaFreeHost(c->h_red);
+  cudaStreamDestroy((cudaStream_t)c->stream);
+#endif
+  free(c);
+}
+
+double** ctx_slot(Ctx* c, const char* name, const FieldInfo** fi) {
+  const FieldInfo* f = find_field(name);
+  if (fi) *fi = f;
+  if (!f) return nullptr;
+  return (double**)((char*)&c->p + f->offset);
+}
+
+int ctx_push(Ctx* c, const char* name, const double* host) {
+  const FieldInfo* f;
+  double** slot = ctx_slot(c, name, &f);
+  if (!slot) { snprintf(c->err, sizeof(c->err), "unknown field '%s'", name); return 2; }
+  if (!*slot && dev_alloc(c, slot, field_elems(c, f))) return 1;
+  return dev_h2d(c, *slot, host, field_elems(c, f));
+}
+
+int ctx_pull(Ctx* c, const char* name, double* host) {
+  const FieldInfo* f;
+  double** slot = ctx_slot(c, name, &f);
+  if (!slot || !*slot) { snprintf(c->err, sizeof(c->err), "unknown or unallocated field '%s'", name); return 2; }
+  return dev_d2h(c, host, *slot, field_elems(c, f));
+}
+
+int ctx_set_const(Ctx* c, const char* name, double v) {
+#define X(n) if (!strcmp(name, #n)) { c->c.n = v; return 0; }
+  POM_SCAL_D(X)
+#undef X
+#define X(n) if (!strcmp(name, #n)) { c->c.n = (int)v; return 0; }
+  POM_SCAL_I(X)
+#undef X
+  return 2;
+}
+
+int ctx_get_const(Ctx* c, const char* name, double* v) {
+#define X(n) if (!strcmp(name, #n)) { *v = c->c.n; return 0; }
+  POM_SCAL_D(X)
+#undef X
+#define X(n) if (!strcmp(name, #n)) { *v = (double)c->c.n; return 0; }
+  POM_SCAL_I(X)
+#undef X
+  return 2;
+}
+
+}  // namespace pom

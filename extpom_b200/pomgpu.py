@@ -1,0 +1,209 @@
+"""Host-side mirror of the reference's time-stepping interface over libpomgpu's C ABI.
+
+The reference (RinceWND/extPOM) is a Fortran program whose hot path is a set of
+argument-less external subroutines working on COMMON blocks (pom/advance.f:21-32,
+pom/solver.f).  `PomGpu` exposes the same subroutine names and the same array layout
+(fp64, column-major, i fastest) over include/pomgpu.h; fields are addressed by their
+COMMON member names.  All compute happens in the hand-written CUDA kernels of
+extpom_b200/csrc (sm_100a); there is no CPU fallback: constructing a PomGpu without
+the built library or without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(_HERE, "libpomgpu.so")
+
+F3D = ("aam advx advy drhox drhoy kh km kq l q2b q2 q2lb q2l rho rmean sb sclim s tb tclim t "
+       "ub uf u vb vf v w wr").split()
+F3D_OPT = "trstrb trstrf srstrb srstrf taurstrb taurstrf".split()
+F2D = ("aam2d advua advva adx2d ady2d art aru arv cbc cor d drx2d dry2d dt dum dvm dx dy "
+       "e_atmos egb egf el elb elf et etb etf fsm h swrad ssurf tsurf ua uab uaf utb utf va "
+       "vab vaf vtb vtf vfluxb vfluxf wssurf wtsurf wubot wusurf wvbot wvsurf").split()
+BJ = "ele elw uabe uabw vabe vabw".split()
+BI = "eln els vabn vabs uabn uabs".split()
+BJK = "tbe sbe tbw sbw".split()
+BIK = "tbn sbn tbs sbs".split()
+F1D = "z zz dz dzz".split()
+
+
+class PomGpuError(RuntimeError):
+    pass
+
+
+def _bind(path):
+    if not os.path.exists(path):
+        raise PomGpuError(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(libpomgpu has no CPU fallback)")
+    L = C.CDLL(path)
+    P = C.c_void_p
+    L.pomgpu_create.restype = P
+    L.pomgpu_create.argtypes = [C.c_int] * 4
+    L.pomgpu_create_strip.restype = P
+    L.pomgpu_create_strip.argtypes = [C.c_int] * 7
+    L.pomgpu_destroy.argtypes = [P]
+    L.pomgpu_local_rows.argtypes = [P]
+    L.pomgpu_row_offset.argtypes = [P]
+    L.pomgpu_last_error.restype = C.c_char_p
+    L.pomgpu_last_error.argtypes = [P]
+    L.pomgpu_set_const.argtypes = [P, C.c_char_p, C.c_double]
+    L.pomgpu_get_const.argtypes = [P, C.c_char_p, C.POINTER(C.c_double)]
+    L.pomgpu_push.argtypes = [P, C.c_char_p, P]
+    L.pomgpu_pull.argtypes = [P, C.c_char_p, P]
+    L.pomgpu_field_elems.restype = C.c_long
+    L.pomgpu_field_elems.argtypes = [P, C.c_char_p]
+    L.pomgpu_step.argtypes = [P, C.c_int, C.c_double, C.c_double]
+    L.pomgpu_sync.argtypes = [P]
+    L.pomgpu_check_velocity.restype = C.c_double
+    L.pomgpu_check_velocity.argtypes = [P]
+    L.pomgpu_launch_count.restype = C.c_long
+    L.pomgpu_launch_count.argtypes = [P, C.c_int]
+    for n in ("lateral_viscosity mode_interaction advave advct advq advu advv baropg profq profu "
+              "profv vertvl realvertvl").split():
+        getattr(L, "pomgpu_" + n).argtypes = [P]
+    L.pomgpu_mode_external.argtypes = [P, C.c_int]
+    L.pomgpu_mode_internal.argtypes = [P, C.c_int]
+    L.pomgpu_internal_stage.argtypes = [P, C.c_int, C.c_int]
+    L.pomgpu_advt1.argtypes = [P] + [C.c_char_p] * 4
+    L.pomgpu_advt2.argtypes = [P] + [C.c_char_p] * 4
+    L.pomgpu_dens.argtypes = [P] + [C.c_char_p] * 3
+    L.pomgpu_proft.argtypes = [P] + [C.c_char_p] * 3 + [C.c_int]
+    return L
+
+
+_LIBS = {}
+
+
+def _lib(path):
+    if path not in _LIBS:
+        _LIBS[path] = _bind(path)
+    return _LIBS[path]
+
+
+class PomGpu:
+    """One j-strip (default: the whole domain) of the model, resident in HBM on one B200."""
+
+    def __init__(self, im, jm, kb, device=0, strip=None, ghost=0, _libpath=None):
+        self.L = _lib(_libpath or LIBPATH)
+        self.im, self.jm, self.kb = im, jm, kb
+        if strip is None:
+            self.h = self.L.pomgpu_create(im, jm, kb, device)
+        else:
+            self.h = self.L.pomgpu_create_strip(im, jm, kb, strip[0], strip[1], ghost, device)
+        if not self.h:
+            raise PomGpuError("pomgpu_create failed (no CUDA device, bad extents or out of memory); "
+                              "there is no CPU fallback")
+        self.jml = self.L.pomgpu_local_rows(self.h)
+        self.joff = self.L.pomgpu_row_offset(self.h)
+        jl = self.jml
+        self.shapes = {}
+        for n in F3D + F3D_OPT: self.shapes[n] = (im, jl, kb)
+        for n in F2D: self.shapes[n] = (im, jl)
+        for n in BJ: self.shapes[n] = (jl,)
+        for n in BI: self.shapes[n] = (im,)
+        for n in BJK: self.shapes[n] = (jl, kb)
+        for n in BIK: self.shapes[n] = (im, kb)
+        for n in F1D: self.shapes[n] = (kb,)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pomgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise PomGpuError(f"{what} failed (rc={rc}): {self.L.pomgpu_last_error(self.h).decode()}")
+
+    # -- state I/O -----------------------------------------------------------
+    def set(self, name, v):
+        self._ck(self.L.pomgpu_set_const(self.h, name.encode(), float(v)), f"set_const({name})")
+
+    def getc(self, name):
+        v = C.c_double(0)
+        self._ck(self.L.pomgpu_get_const(self.h, name.encode(), C.byref(v)), f"get_const({name})")
+        return v.value
+
+    def _rows(self, name, arr):
+        """Slice a global-sized host array down to this strip's rows."""
+        shp = self.shapes[name]
+        a = np.asarray(arr, dtype=np.float64)
+        if a.shape == shp:
+            return a
+        j0, j1 = self.joff, self.joff + self.jml
+        if name in F2D or name in F3D or name in F3D_OPT:
+            return a[:, j0:j1]
+        if name in BJ or name in BJK:
+            return a[j0:j1]
+        raise ValueError(f"{name}: shape {a.shape} != {shp}")
+
+    def put(self, name, arr):
+        a = np.asfortranarray(self._rows(name, arr), dtype=np.float64)
+        assert a.shape == self.shapes[name], (name, a.shape, self.shapes[name])
+        self._ck(self.L.pomgpu_push(self.h, name.encode(), a.ctypes.data_as(C.c_void_p)), f"push({name})")
+
+    def get(self, name):
+        out = np.empty(self.shapes[name], dtype=np.float64, order="F")
+        self._ck(self.L.pomgpu_pull(self.h, name.encode(), out.ctypes.data_as(C.c_void_p)), f"pull({name})")
+        return out
+
+    def load(self, state):
+        """state = {'consts': {...}, 'fields': {name: ndarray}} (extpom_b200.synthetic)."""
+        for k, v in state["consts"].items():
+            self.L.pomgpu_set_const(self.h, k.encode(), float(v))  # names outside blkcon are ignored
+        for k, v in state["fields"].items():
+            if k in self.shapes and (k not in F3D_OPT):
+                self.put(k, v)
+
+    # -- the reference's subroutine surface ------------------------------------
+    def step(self, iint, time=None, ramp=1.0):
+        """pom/advance.f:21-32 for internal step iint; time as get_time (advance.f:66)."""
+        if time is None:
+            time = self.getc("dti") * float(iint) / 86400.0 + self.getc("time0")
+        self._ck(self.L.pomgpu_step(self.h, int(iint), float(time), float(ramp)), "step")
+
+    def sync(self):
+        self._ck(self.L.pomgpu_sync(self.h), "sync")
+
+    def check_velocity(self):
+        return self.L.pomgpu_check_velocity(self.h)
+
+    def launch_count(self, reset=False):
+        return self.L.pomgpu_launch_count(self.h, int(reset))
+
+    def lateral_viscosity(self): self._ck(self.L.pomgpu_lateral_viscosity(self.h), "lateral_viscosity")
+    def mode_interaction(self): self._ck(self.L.pomgpu_mode_interaction(self.h), "mode_interaction")
+    def mode_external(self, iext): self._ck(self.L.pomgpu_mode_external(self.h, iext), "mode_external")
+    def mode_internal(self, iint): self._ck(self.L.pomgpu_mode_internal(self.h, iint), "mode_internal")
+    def internal_stage(self, iint, stage):
+        self._ck(self.L.pomgpu_internal_stage(self.h, int(iint), int(stage)), "internal_stage")
+    def advave(self): self._ck(self.L.pomgpu_advave(self.h), "advave")
+    def advct(self): self._ck(self.L.pomgpu_advct(self.h), "advct")
+    def advq(self): self._ck(self.L.pomgpu_advq(self.h), "advq")
+    def advu(self): self._ck(self.L.pomgpu_advu(self.h), "advu")
+    def advv(self): self._ck(self.L.pomgpu_advv(self.h), "advv")
+    def baropg(self): self._ck(self.L.pomgpu_baropg(self.h), "baropg")
+    def profq(self): self._ck(self.L.pomgpu_profq(self.h), "profq")
+    def profu(self): self._ck(self.L.pomgpu_profu(self.h), "profu")
+    def profv(self): self._ck(self.L.pomgpu_profv(self.h), "profv")
+    def vertvl(self): self._ck(self.L.pomgpu_vertvl(self.h), "vertvl")
+    def realvertvl(self): self._ck(self.L.pomgpu_realvertvl(self.h), "realvertvl")
+
+    def advt1(self, fb, f, fclim, ff):
+        self._ck(self.L.pomgpu_advt1(self.h, fb.encode(), f.encode(), fclim.encode(), ff.encode()), "advt1")
+
+    def advt2(self, fb, f, fclim, ff):
+        self._ck(self.L.pomgpu_advt2(self.h, fb.encode(), f.encode(), fclim.encode(), ff.encode()), "advt2")
+
+    def dens(self, si, ti, rhoo):
+        self._ck(self.L.pomgpu_dens(self.h, si.encode(), ti.encode(), rhoo.encode()), "dens")
+
+    def proft(self, f, wfsurf, fsurf, nbc):
+        self._ck(self.L.pomgpu_proft(self.h, f.encode(), wfsurf.encode(), fsurf.encode(), int(nbc)), "proft")

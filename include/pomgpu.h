@@ -1,0 +1,96 @@
+/* pomgpu.h -- C ABI of libpomgpu, the B200-native drop-in for extPOM's
+ * time-stepping hot path (pom/advance.f:21-32 and the pom/solver.f kernels it
+ * drives).  Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * The reference passes all model state through Fortran COMMON blocks with
+ * compile-time extents (pom.h_dist:22-28,291-364,410-450,532-608) and calls
+ * argument-less external subroutines (advance.f:21-32).  This ABI keeps the
+ * same names and the same array layout (fp64, column-major, i fastest,
+ * (im_local, jm_local[, kb])), but with run-time extents and an explicit
+ * context that owns the HBM-resident copies.  Fields are addressed by their
+ * COMMON member name ("u", "tb", "wusurf", "tbe", ...).
+ *
+ * Return codes: 0 = ok, 1 = CUDA failure (also sets blkcon's error_status=1,
+ * the reference's error convention, advance.f:118,556-563), 2 = bad argument.
+ * The library never calls exit() and has NO CPU fallback: pomgpu_create fails
+ * when no CUDA device is present.
+ */
+#ifndef POMGPU_H
+#define POMGPU_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pomgpu pomgpu_t;
+
+/* ---- lifecycle ------------------------------------------------------------
+ * Replaces distribute_mpi (pom/parallel_mpi.f:34-122).  pomgpu_create holds the
+ * whole (im, jm, kb) domain on one GPU.  pomgpu_create_strip holds global rows
+ * j_first..j_last (1-based, inclusive) of a (im, jm_global, kb) domain plus
+ * `ghost` rows on each interior seam; host arrays passed to push/pull then
+ * have jm_local = pomgpu_local_rows() rows starting at pomgpu_row_offset(). */
+pomgpu_t* pomgpu_create(int im, int jm, int kb, int device);
+pomgpu_t* pomgpu_create_strip(int im, int jm_global, int kb, int j_first,
+                              int j_last, int ghost, int device);
+void pomgpu_destroy(pomgpu_t* ctx);
+int pomgpu_local_rows(const pomgpu_t* ctx);
+int pomgpu_row_offset(const pomgpu_t* ctx); /* global 0-based row of local row 0 */
+const char* pomgpu_last_error(const pomgpu_t* ctx);
+
+/* ---- blkcon scalars (pom.h_dist:69-198; set by read_input, pom/initialize.f:67-191)
+ * by name: "dti2", "smoth", "isplit", "nadv", ... */
+int pomgpu_set_const(pomgpu_t* ctx, const char* name, double value);
+int pomgpu_get_const(pomgpu_t* ctx, const char* name, double* value);
+
+/* ---- host <-> HBM, by COMMON member name.  Synchronous w.r.t. the host buffer.
+ * push: driver-owned host array -> device (init, per-step forcing of
+ *       pom/bounds_forcing.f:844-865,908-909,954-955,978).
+ * pull: device -> host (output/restart steps, pom/advance.f:35-49). */
+int pomgpu_push(pomgpu_t* ctx, const char* name, const double* host);
+int pomgpu_pull(pomgpu_t* ctx, const char* name, double* host);
+long pomgpu_field_elems(pomgpu_t* ctx, const char* name); /* 0 if unknown */
+
+/* ---- resident-mode time stepping -------------------------------------------
+ * pomgpu_step = pom/advance.f:21-32 (lateral_viscosity, mode_interaction,
+ * isplit x mode_external, mode_internal) for internal step `iint`; `time` and
+ * `ramp` are what get_time (advance.f:62-75) computed.  Asynchronous: returns
+ * after enqueueing; pomgpu_sync / pull / check_velocity wait. */
+int pomgpu_step(pomgpu_t* ctx, int iint, double time, double ramp);
+int pomgpu_sync(pomgpu_t* ctx);
+/* check_velocity (advance.f:611-641) as a device max-reduction: returns
+ * max|vaf| and sets error_status when it exceeds vmaxl. */
+double pomgpu_check_velocity(pomgpu_t* ctx);
+long pomgpu_launch_count(pomgpu_t* ctx, int reset);
+
+/* ---- the reference's subroutines on the resident state (same names) ---------
+ * advance.f */
+int pomgpu_lateral_viscosity(pomgpu_t* ctx);       /* advance.f:96  */
+int pomgpu_mode_interaction(pomgpu_t* ctx);        /* advance.f:144 */
+int pomgpu_mode_external(pomgpu_t* ctx, int iext); /* advance.f:205 */
+int pomgpu_mode_internal(pomgpu_t* ctx, int iint); /* advance.f:356 */
+/* one block of mode_internal (test hook): 0 u/v adjust :365-393, 1 vertvl+bcondorl(5), 2 advq x2,
+ * 3 profq, 4 bcond(6)+filter, 5/6 advt T/S, 7/8 proft T/S, 9 bcond(4)+filter+restore, 10 dens,
+ * 11 advu, 12 advv, 13 profu, 14 profv, 15 bcondorl(3)+filter, 16 2-D rotations :525-531, 17 realvertvl */
+int pomgpu_internal_stage(pomgpu_t* ctx, int iint, int stage);
+/* solver.f; array arguments are COMMON member names (the reference passes
+ * q2b,q2,uf / tb,t,tclim,uf / s,t,rho / uf,wtsurf,tsurf,nbct, advance.f:407-454) */
+int pomgpu_advave(pomgpu_t* ctx);                  /* solver.f:6    */
+int pomgpu_advct(pomgpu_t* ctx);                   /* solver.f:201  */
+int pomgpu_advq(pomgpu_t* ctx);                    /* solver.f:411, both q2->uf and q2l->vf */
+int pomgpu_advt1(pomgpu_t* ctx, const char* fb, const char* f, const char* fclim, const char* ff); /* :480 */
+int pomgpu_advt2(pomgpu_t* ctx, const char* fb, const char* f, const char* fclim, const char* ff); /* :577 */
+int pomgpu_advu(pomgpu_t* ctx);                    /* solver.f:734  */
+int pomgpu_advv(pomgpu_t* ctx);                    /* solver.f:791  */
+int pomgpu_baropg(pomgpu_t* ctx);                  /* solver.f:848  */
+int pomgpu_dens(pomgpu_t* ctx, const char* si, const char* ti, const char* rhoo); /* solver.f:1162 */
+int pomgpu_profq(pomgpu_t* ctx);                   /* solver.f:1212 */
+int pomgpu_proft(pomgpu_t* ctx, const char* f, const char* wfsurf, const char* fsurf, int nbc); /* :1541 */
+int pomgpu_profu(pomgpu_t* ctx);                   /* solver.f:1686 */
+int pomgpu_profv(pomgpu_t* ctx);                   /* solver.f:1783 */
+int pomgpu_vertvl(pomgpu_t* ctx);                  /* solver.f:1970 (+ bcondorl(5)) */
+int pomgpu_realvertvl(pomgpu_t* ctx);              /* solver.f:2024 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -95,6 +95,7 @@ void pomo_lateral_viscosity(pomo_t *S);
 void pomo_mode_interaction(pomo_t *S);
 void pomo_mode_external(pomo_t *S);
 void pomo_mode_internal(pomo_t *S);
+void pomo_internal_stage(pomo_t *S, int stage); /* blocks of advance.f:356-537 */
 double pomo_check_velocity(pomo_t *S); /* advance.f:611-641, returns vamax */
 /* solver.f */
 void pomo_advave(pomo_t *S);

@@ -65,6 +65,7 @@ def lib():
         L.pomo_smol_adif.argtypes = [P] * 5
         L.pomo_bcond.argtypes = [P, C.c_int]
         L.pomo_bcondorl.argtypes = [P, C.c_int]
+        L.pomo_internal_stage.argtypes = [P, C.c_int]
         _LIB = L
     return _LIB
 
@@ -149,6 +150,8 @@ class Oracle:
         self.set("iext", iext); self.L.pomo_mode_external(self.h)
     def mode_internal(self, iint):
         self.set("iint", iint); self.L.pomo_mode_internal(self.h)
+    def internal_stage(self, iint, stage):
+        self.set("iint", iint); self.L.pomo_internal_stage(self.h, stage)
     def advave(self): self.L.pomo_advave(self.h)
     def advct(self): self.L.pomo_advct(self.h)
     def advu(self): self.L.pomo_advu(self.h)

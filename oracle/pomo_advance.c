@@ -169,36 +169,42 @@ void pomo_mode_external(pomo_t *S) {
   }
 }
 
-/* advance.f:356-537 */
-void pomo_mode_internal(pomo_t *S) {
+/* advance.f:356-537, split into stages so that tests can compare the GPU
+ * path block by block (pomo_internal_stage); pomo_mode_internal runs them all. */
+static int internal_active(pomo_t *S) {
+  return (S->iint != 1 || S->time0 != 0.) && S->mode != 2; /* :362 */
+}
+
+void pomo_internal_stage(pomo_t *S, int stage) {
   DIMS;
-  if ((S->iint != 1 || S->time0 != 0.) && S->mode != 2) {
-    /* :365-378 */
+  switch (stage) {
+  case 0: /* :365-393 */
     memset(S->tps, 0, sizeof(double) * N2);
     DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im) tps(i,j)=tps(i,j)+u(i,j,k)*dz(k);
     OMP_FOR
     DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 2, im)
       u(i,j,k)=(u(i,j,k)-tps(i,j))+
                (utb(i,j)+utf(i,j))/(dt(i,j)+dt(i-1,j));
-    /* :380-393 */
     memset(S->tps, 0, sizeof(double) * N2);
     DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im) tps(i,j)=tps(i,j)+v(i,j,k)*dz(k);
     OMP_FOR
     DO(k, 1, kbm1) DO(j, 2, jm) DO(i, 1, im)
       v(i,j,k)=(v(i,j,k)-tps(i,j))+
                (vtb(i,j)+vtf(i,j))/(dt(i,j)+dt(i,j-1));
-    /* :396-400 */
+    break;
+  case 1: /* :396-400 */
     pomo_vertvl(S);
     pomo_bcondorl(S, 5);
-    /* :403-404 */
+    break;
+  case 2: /* :403-408 */
     memset(S->uf, 0, sizeof(double) * N3);
     memset(S->vf, 0, sizeof(double) * N3);
-    /* :407-409 */
     pomo_advq(S, S->q2b, S->q2, S->uf);
     pomo_advq(S, S->q2lb, S->q2l, S->vf);
-    pomo_profq(S);
-    pomo_bcond(S, 6); /* :414 */
-    /* :416-421 */
+    break;
+  case 3: pomo_profq(S); break; /* :409 */
+  case 4: /* :414-421 */
+    pomo_bcond(S, 6);
     OMP_FOR
     for (size_t n = 0; n < N3; ++n) {
       S->q2[n] = S->q2[n]+.5*smoth*(S->uf[n]+S->q2b[n]-2.*S->q2[n]);
@@ -208,40 +214,41 @@ void pomo_mode_internal(pomo_t *S) {
       S->q2lb[n] = S->q2l[n];
       S->q2l[n] = S->vf[n];
     }
-    /* :424-456 */
-    if (S->mode != 4) {
-      if (S->nadv == 1) {
-        pomo_advt1(S, S->tb, S->t, S->tclim, S->uf);
-        pomo_advt1(S, S->sb, S->s, S->sclim, S->vf);
-      } else if (S->nadv == 2) {
-        pomo_advt2(S, S->tb, S->t, S->tclim, S->uf);
-        pomo_advt2(S, S->sb, S->s, S->sclim, S->vf);
-      } else {
-        S->error_status = 1;
-        fprintf(stderr, "\nError: invalid value for nadv\n");
-      }
-      pomo_proft(S, S->uf, S->wtsurf, S->tsurf, S->nbct);
-      pomo_proft(S, S->vf, S->wssurf, S->ssurf, S->nbcs);
-      pomo_bcond(S, 4);
-      OMP_FOR
-      for (size_t n = 0; n < N3; ++n) {
-        S->t[n] = S->t[n]+.5*smoth*(S->uf[n]+S->tb[n]-2.*S->t[n]);
-        S->s[n] = S->s[n]+.5*smoth*(S->vf[n]+S->sb[n]-2.*S->s[n]);
-        S->tb[n] = S->t[n];
-        S->t[n] = S->uf[n];
-        S->sb[n] = S->s[n];
-        S->s[n] = S->vf[n];
-      }
-      pomo_restore_interior(S); /* :452 */
-      pomo_dens(S, S->s, S->t, S->rho); /* :454 */
+    break;
+  case 5: /* :425-434 (T) */
+    if (S->mode == 4) break;
+    if (S->nadv == 1) pomo_advt1(S, S->tb, S->t, S->tclim, S->uf);
+    else if (S->nadv == 2) pomo_advt2(S, S->tb, S->t, S->tclim, S->uf);
+    else { S->error_status = 1; fprintf(stderr, "\nError: invalid value for nadv\n"); }
+    break;
+  case 6: /* :425-434 (S) */
+    if (S->mode == 4) break;
+    if (S->nadv == 1) pomo_advt1(S, S->sb, S->s, S->sclim, S->vf);
+    else if (S->nadv == 2) pomo_advt2(S, S->sb, S->s, S->sclim, S->vf);
+    break;
+  case 7: if (S->mode != 4) pomo_proft(S, S->uf, S->wtsurf, S->tsurf, S->nbct); break; /* :439 */
+  case 8: if (S->mode != 4) pomo_proft(S, S->vf, S->wssurf, S->ssurf, S->nbcs); break; /* :440 */
+  case 9: /* :442-452 */
+    if (S->mode == 4) break;
+    pomo_bcond(S, 4);
+    OMP_FOR
+    for (size_t n = 0; n < N3; ++n) {
+      S->t[n] = S->t[n]+.5*smoth*(S->uf[n]+S->tb[n]-2.*S->t[n]);
+      S->s[n] = S->s[n]+.5*smoth*(S->vf[n]+S->sb[n]-2.*S->s[n]);
+      S->tb[n] = S->t[n];
+      S->t[n] = S->uf[n];
+      S->sb[n] = S->s[n];
+      S->s[n] = S->vf[n];
     }
-    /* :459-464 */
-    pomo_advu(S);
-    pomo_advv(S);
-    pomo_profu(S);
-    pomo_profv(S);
+    pomo_restore_interior(S);
+    break;
+  case 10: if (S->mode != 4) pomo_dens(S, S->s, S->t, S->rho); break; /* :454 */
+  case 11: pomo_advu(S); break; /* :459 */
+  case 12: pomo_advv(S); break;
+  case 13: pomo_profu(S); break;
+  case 14: pomo_profv(S); break;
+  case 15: /* :464-514 */
     pomo_bcondorl(S, 3);
-    /* :469-488 */
     memset(S->tps, 0, sizeof(double) * N2);
     DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im)
       tps(i,j)=tps(i,j)
@@ -251,7 +258,6 @@ void pomo_mode_internal(pomo_t *S) {
       u(i,j,k)=u(i,j,k)
                +.5*smoth*(uf(i,j,k)+ub(i,j,k)
                           -2.*u(i,j,k)-tps(i,j));
-    /* :490-509 */
     memset(S->tps, 0, sizeof(double) * N2);
     DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im)
       tps(i,j)=tps(i,j)
@@ -261,21 +267,29 @@ void pomo_mode_internal(pomo_t *S) {
       v(i,j,k)=v(i,j,k)
                +.5*smoth*(vf(i,j,k)+vb(i,j,k)
                           -2.*v(i,j,k)-tps(i,j));
-    /* :511-514 */
     memcpy(S->ub, S->u, sizeof(double) * N3);
     memcpy(S->u, S->uf, sizeof(double) * N3);
     memcpy(S->vb, S->v, sizeof(double) * N3);
     memcpy(S->v, S->vf, sizeof(double) * N3);
+    break;
+  case 16: /* :525-531 */
+    memcpy(S->egb, S->egf, sizeof(double) * N2);
+    memcpy(S->etb, S->et, sizeof(double) * N2);
+    memcpy(S->et, S->etf, sizeof(double) * N2);
+    for (size_t n = 0; n < N2; ++n) S->dt[n] = S->h[n]+S->et[n];
+    memcpy(S->utb, S->utf, sizeof(double) * N2);
+    memcpy(S->vtb, S->vtf, sizeof(double) * N2);
+    memcpy(S->vfluxb, S->vfluxf, sizeof(double) * N2);
+    break;
+  case 17: pomo_realvertvl(S); break; /* :534 */
   }
-  /* :525-531 */
-  memcpy(S->egb, S->egf, sizeof(double) * N2);
-  memcpy(S->etb, S->et, sizeof(double) * N2);
-  memcpy(S->et, S->etf, sizeof(double) * N2);
-  for (size_t n = 0; n < N2; ++n) S->dt[n] = S->h[n]+S->et[n];
-  memcpy(S->utb, S->utf, sizeof(double) * N2);
-  memcpy(S->vtb, S->vtf, sizeof(double) * N2);
-  memcpy(S->vfluxb, S->vfluxf, sizeof(double) * N2);
-  pomo_realvertvl(S); /* :534 */
+}
+
+void pomo_mode_internal(pomo_t *S) {
+  if (internal_active(S))
+    for (int st = 0; st <= 15; ++st) pomo_internal_stage(S, st);
+  pomo_internal_stage(S, 16);
+  pomo_internal_stage(S, 17);
 }
 
 /* advance.f:21-32: the hot path of one internal step.  The caller sets
