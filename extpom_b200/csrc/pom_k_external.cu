@@ -13,6 +13,7 @@ namespace pom {
 
 // ------------------------------------------------------------------ advave ----
 struct AdvaveK : KBase {
+  POM_KINFO("advave", 0, 0, 8, 2)
   using KBase::KBase;
   POM_HD double dx4(int i, int j) const { return dx(i,j)+dx(i-1,j)+dx(i,j-1)+dx(i-1,j-1); }
   POM_HD double dy4(int i, int j) const { return dy(i,j)+dy(i-1,j)+dy(i,j-1)+dy(i-1,j-1); }
@@ -66,6 +67,7 @@ struct AdvaveK : KBase {
 // ------------------------------------------- mode_interaction tail -------------
 // advance.f:172-196: adx2d-=advua, ady2d-=advva, egf, utf, vtf
 struct ModeInterTailK : KBase {
+  POM_KINFO("mode_interaction", 0, 0, 8, 5)
   using KBase::KBase;
   POM_HD void operator()(int i, int j) const {
     if (c.mode != 2) {
@@ -80,6 +82,7 @@ struct ModeInterTailK : KBase {
 
 // ------------------------------------------------------------ elf + bcond(1) ----
 struct ExtElfK : KBase {
+  POM_KINFO("ext_elf", 0, 0, 9, 1)
   using KBase::KBase;
   POM_HD double fua(int i, int j) const {   // advance.f:213-214
     return .25*(d(i,j)+d(i-1,j))*(dy(i,j)+dy(i-1,j))*ua(i,j);
@@ -102,6 +105,7 @@ struct ExtElfK : KBase {
 
 // ------------------------------- uaf/vaf + bcond(2) + etf + filter + running means
 struct ExtUvK : KBase {
+  POM_KINFO("ext_uv", 0, 0, 32, 10)
   using KBase::KBase;
   int iext;
   ExtUvK(const Ctx* x, int ie) : KBase(x), iext(ie) {}

@@ -13,6 +13,7 @@ namespace pom {
 // ---------------------------------------------------------------------------
 // advance.f:365-393: adjust u(z), v(z) so that their depth means match (utb+utf)
 struct UvAdjustK : KBase {
+  POM_KINFO("uv_adjust", 2, 2, 5, 0)
   using KBase::KBase;
   POM_HD void operator()(int i, int j) const {
     POM_DIMS;
@@ -35,6 +36,7 @@ struct UvAdjustK : KBase {
 // ---------------------------------------------------------------------------
 // vertvl (solver.f:1970-2021) + bcondorl(5) (bounds_forcing.f:553-559)
 struct VertvlK : KBase {
+  POM_KINFO("vertvl", 2, 1, 8, 0)
   using KBase::KBase;
   POM_HD double xf(int i, int j, int k) const {   // :1984-1985
     return .25*(dy(i,j)+dy(i-1,j))*(dt(i,j)+dt(i-1,j))*u(i,j,k);
@@ -63,6 +65,7 @@ struct VertvlK : KBase {
 // ---------------------------------------------------------------------------
 // advq (solver.f:411-477) for q2 -> uf and q2l -> vf in one pass
 struct AdvqK : KBase {
+  POM_KINFO("advq", 8, 2, 9, 0)
   using KBase::KBase;
   POM_HD double xfl(const double* q, const double* qb, int i, int j, int k) const {
     double a=.125*(A3(q,i,j,k)+A3(q,i-1,j,k))*(dt(i,j)+dt(i-1,j))*(u(i,j,k)+u(i,j,k-1));   // :428-429
@@ -109,6 +112,7 @@ struct AdvqK : KBase {
 // profq (solver.f:1212-1538): Mellor-Yamada 2.5 with the wave-breaking surface
 // condition; two Thomas solves per column (q2 -> uf, q2l -> vf), then km,kh,kq.
 struct ProfqK : KBase {
+  POM_KINFO("profq", 13, 8, 7, 0)
   double cgg, const1;
   ProfqK(const Ctx* x) : KBase(x) {
     // solver.f:1297: (15.8*cbcnst)**(2./3.) with single-precision literals promoted
@@ -256,6 +260,7 @@ struct ProfqK : KBase {
 // (advance.f:416-421).  Filtered q2 -> q2b buffer, new q2 stays in uf; the host
 // rotates pointers.
 struct QFilterK : KBase {
+  POM_KINFO("q_filter", 6, 4, 1, 0)
   using KBase::KBase;
   POM_HD void operator()(int i, int j) const {
     POM_DIMS;
@@ -293,6 +298,7 @@ struct QFilterK : KBase {
 // advt2 with nitera=1 (solver.f:577-731 + the fsm mask of smol_adif :1898-1900):
 // upstream advection, leapfrog update, horizontal diffusion of (fb-fclim).
 struct AdvT2K : KBase {
+  POM_KINFO("advt2", 6, 1, 10, 0)
   const double *fb_, *f_, *fc_;
   double* ff_;
   AdvT2K(const Ctx* x, const double* fb, const double* f, const double* fc, double* ff)
@@ -347,6 +353,7 @@ struct AdvT2K : KBase {
 
 // advt1 (solver.f:480-574): centred advection + diffusion of (fb-fclim)
 struct AdvT1K : KBase {
+  POM_KINFO("advt1", 7, 1, 10, 0)
   const double *fb_, *f_, *fc_;
   double* ff_;
   AdvT1K(const Ctx* x, const double* fb, const double* f, const double* fc, double* ff)
@@ -384,6 +391,7 @@ struct AdvT1K : KBase {
 // ---------------------------------------------------------------------------
 // proft (solver.f:1541-1683): implicit vertical diffusion of one tracer
 struct ProftK : KBase {
+  POM_KINFO("proft", 2, 1, 3, 0)
   double* f_;
   const double *wfsurf_, *fsurf_;
   int nbc;
@@ -448,6 +456,7 @@ struct ProftK : KBase {
 // (bounds_forcing.f:1083-1118).  Filtered t,s -> tb,sb buffers; new t,s stay
 // in uf,vf; the host rotates pointers.
 struct TsFilterK : KBase {
+  POM_KINFO("ts_filter", 8, 4, 1, 0)
   double fold, fnew;
   TsFilterK(const Ctx* x) : KBase(x) {
     const double trst = 30.;                                             // bounds_forcing.f:1033
@@ -556,6 +565,7 @@ POM_HD double pow15(double x) {
 
 // dens (solver.f:1162-1209)
 struct DensK : KBase {
+  POM_KINFO("dens", 2, 1, 2, 0)
   const double *si_, *ti_;
   double* ro_;
   DensK(const Ctx* x, const double* si, const double* ti, double* ro) : KBase(x), si_(si), ti_(ti), ro_(ro) {}
@@ -582,6 +592,7 @@ struct DensK : KBase {
 // ---------------------------------------------------------------------------
 // advu / advv (solver.f:734-845)
 struct AdvuK : KBase {
+  POM_KINFO("advu", 6, 1, 10, 0)
   using KBase::KBase;
   POM_HD double vfl(int i, int j, int k) const {                        // :747-748
     return .25*(w(i,j,k)+w(i-1,j,k))*(u(i,j,k)+u(i,j,k-1));
@@ -616,6 +627,7 @@ struct AdvuK : KBase {
 };
 
 struct AdvvK : KBase {
+  POM_KINFO("advv", 6, 1, 10, 0)
   using KBase::KBase;
   POM_HD double vfl(int i, int j, int k) const {                        // :804-805
     return .25*(w(i,j,k)+w(i,j-1,k))*(v(i,j,k)+v(i,j,k-1));
@@ -651,6 +663,7 @@ struct AdvvK : KBase {
 // ---------------------------------------------------------------------------
 // profu / profv (solver.f:1686-1877): implicit vertical viscosity + bottom drag
 struct ProfuK : KBase {
+  POM_KINFO("profu", 2, 1, 5, 1)
   using KBase::KBase;
   POM_HD void operator()(int i, int j) const {
     POM_DIMS;
@@ -688,6 +701,7 @@ struct ProfuK : KBase {
 };
 
 struct ProfvK : KBase {
+  POM_KINFO("profv", 2, 1, 5, 1)
   using KBase::KBase;
   POM_HD void operator()(int i, int j) const {
     POM_DIMS;
@@ -729,6 +743,7 @@ struct ProfvK : KBase {
 // of their neighbours, so the filtered u,v go to the scratch buffers s3a,s3b (which
 // become ub,vb); new u,v stay in uf,vf; the host rotates pointers.
 struct UvFilterK : KBase {
+  POM_KINFO("uv_filter", 6, 2, 2, 0)
   using KBase::KBase;
   // Orlanski radiation value from the point `1` cell inside (xf1,xb1), two inside (x2),
   // and the boundary point's own xb0 and x at one inside (x1)
@@ -789,6 +804,7 @@ struct UvFilterK : KBase {
 // ---------------------------------------------------------------------------
 // advance.f:525-531: end-of-step 2-D rotations
 struct EndStep2dK : KBase {
+  POM_KINFO("endstep2d", 0, 0, 7, 7)
   using KBase::KBase;
   POM_HD void operator()(int i, int j) const {
     egb(i,j)=egf(i,j);
@@ -804,6 +820,7 @@ struct EndStep2dK : KBase {
 
 // realvertvl (solver.f:2024-2066)
 struct RealvertvlK : KBase {
+  POM_KINFO("realvertvl", 3, 1, 7, 0)
   using KBase::KBase;
   POM_HD double tp(int i, int j, int k) const { return zz(k)*dt(i,j)+et(i,j); }   // :2036
   POM_HD double wri(int i, int j, int k) const {                        // :2041-2050
@@ -832,6 +849,7 @@ struct RealvertvlK : KBase {
 // in-place (fb-fclim)+fclim and fb(kb)=fb(kbm1): the side effects advt1/advt2 leave on
 // their fb argument (solver.f:496,511,532 / 618,691,715); used by the unit-mode entry
 struct FbRoundTripK : KBase {
+  POM_KINFO("fb_roundtrip", 2, 1, 0, 0)
   double* fb_;
   const double* fc_;
   double* f_;

@@ -12,6 +12,7 @@
 namespace pom {
 
 struct AdvctK : KBase {
+  POM_KINFO("advct", 5, 2, 5, 2)
   using KBase::KBase;
   // solver.f:221-225; zero outside 2..imm1 x 2..jmm1 (zero fill :213)
   POM_HD double curv(int i, int j, int k) const {
@@ -98,6 +99,7 @@ struct AdvctK : KBase {
 // solver.f:848-940.  rho is rewritten as (rho-rmean)+rmean (:854,937) into the
 // alternate buffer rho2 (neighbours still read the old rho); the caller swaps.
 struct BaropgK : KBase {
+  POM_KINFO("baropg", 2, 3, 5, 2)
   using KBase::KBase;
   POM_HD void operator()(int i, int j) const {
     POM_DIMS;
@@ -148,6 +150,7 @@ struct BaropgK : KBase {
 
 // advance.f:122-136 + aam2d (advance.f:165)
 struct SmagK : KBase {
+  POM_KINFO("smagorinsky", 2, 1, 2, 1)
   using KBase::KBase;
   POM_HD void operator()(int i, int j) const {
     POM_DIMS;

@@ -130,6 +130,53 @@ int dev_sync(Ctx* c) {
 }
 #endif
 
+// ---- per-launch profiling with CUDA events on the launch stream ---------------------
+#ifdef POMGPU_EMU
+void prof_before(Ctx*, const KInfo*, double) {}
+void prof_after(Ctx*) {}
+int prof_report(Ctx*, char* buf, int n) { if (n > 2) strcpy(buf, "[]"); return 0; }
+#else
+void prof_before(Ctx* c, const KInfo* info, double bytes) {
+  if (c->nprof == c->capprof) {
+    c->capprof = c->capprof ? 2 * c->capprof : 1024;
+    c->prof = (ProfRec*)realloc(c->prof, sizeof(ProfRec) * c->capprof);
+  }
+  ProfRec& r = c->prof[c->nprof];
+  r.info = info; r.bytes = bytes;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  r.e0 = a; r.e1 = b;
+  cudaEventRecord(a, (cudaStream_t)c->stream);
+}
+void prof_after(Ctx* c) {
+  cudaEventRecord((cudaEvent_t)c->prof[c->nprof].e1, (cudaStream_t)c->stream);
+  c->nprof++;
+}
+// JSON array: [{"name":..,"launches":n,"ms":total,"bytes":total algorithmic}, ...]
+int prof_report(Ctx* c, char* buf, int n) {
+  dev_sync(c);
+  struct Agg { const KInfo* k; long cnt; double ms, bytes; } agg[64];
+  int na = 0;
+  for (int i = 0; i < c->nprof; ++i) {
+    ProfRec& r = c->prof[i];
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, (cudaEvent_t)r.e0, (cudaEvent_t)r.e1);
+    cudaEventDestroy((cudaEvent_t)r.e0); cudaEventDestroy((cudaEvent_t)r.e1);
+    int a = 0;
+    while (a < na && agg[a].k != r.info) ++a;
+    if (a == na) { if (na == 64) continue; agg[na++] = {r.info, 0, 0., 0.}; }
+    agg[a].cnt++; agg[a].ms += ms; agg[a].bytes += r.bytes;
+  }
+  c->nprof = 0;
+  int o = snprintf(buf, n, "[");
+  for (int a = 0; a < na && o < n; ++a)
+    o += snprintf(buf + o, n - o, "%s{\"name\":\"%s\",\"launches\":%ld,\"ms\":%.6f,\"bytes\":%.0f}",
+                  a ? "," : "", agg[a].k->name, agg[a].cnt, agg[a].ms, agg[a].bytes);
+  if (o < n) o += snprintf(buf + o, n - o, "]");
+  return o < n ? 0 : 2;
+}
+#endif
+
 // ---- lifecycle ------------------------------------------------------------------
 Ctx* ctx_create(int im, int jm_global, int kb, int j_first, int j_last, int ghost, int device) {
   if (im < 6 || jm_global < 6 || kb < 4 || kb > 128) return nullptr;

@@ -14,6 +14,7 @@ int ctx_push(Ctx* c, const char* name, const double* host);
 int ctx_pull(Ctx* c, const char* name, double* host);
 int ctx_set_const(Ctx* c, const char* name, double v);
 int ctx_get_const(Ctx* c, const char* name, double* v);
+int prof_report(Ctx* c, char* buf, int n);
 // kernels
 void run_advct(Ctx*, int, int);
 void run_baropg(Ctx*, int, int);
@@ -229,6 +230,62 @@ long pomgpu_field_elems(pomgpu_t* p, const char* name) {
 int pomgpu_step(pomgpu_t* p, int iint, double time, double ramp) { return step(X(p), iint, time, ramp); }
 int pomgpu_sync(pomgpu_t* p) { return dev_sync(X(p)); }
 double pomgpu_check_velocity(pomgpu_t* p) { return check_velocity(X(p)); }
+int pomgpu_push_async(pomgpu_t* p, const char* name, const double* host) {
+  Ctx* c = X(p);
+  const FieldInfo* f;
+  double** slot = ctx_slot(c, name, &f);
+  if (!slot || !*slot) return 2;
+#ifdef POMGPU_EMU
+  return dev_h2d(c, *slot, host, field_elems(c, f));
+#else
+  cudaSetDevice(c->device);
+  cudaError_t e = cudaMemcpyAsync(*slot, host, field_elems(c, f) * 8, cudaMemcpyHostToDevice, (cudaStream_t)c->stream);
+  if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "push_async(%s): %s", name, cudaGetErrorString(e)); c->c.error_status = 1; return 1; }
+  return 0;
+#endif
+}
+int pomgpu_pin_host(void* ptr, size_t bytes) {
+#ifdef POMGPU_EMU
+  (void)ptr; (void)bytes; return 0;
+#else
+  return cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : 1;
+#endif
+}
+int pomgpu_unpin_host(void* ptr) {
+#ifdef POMGPU_EMU
+  (void)ptr; return 0;
+#else
+  return cudaHostUnregister(ptr) == cudaSuccess ? 0 : 1;
+#endif
+}
+// CUDA events on the library's launch stream (bench.py times the step loop with these)
+#ifndef POMGPU_EMU
+static cudaEvent_t g_ev[8];
+static bool g_ev_init = false;
+#endif
+int pomgpu_event_record(pomgpu_t* p, int slot) {
+#ifdef POMGPU_EMU
+  (void)p; (void)slot; return 0;
+#else
+  if (slot < 0 || slot >= 8) return 2;
+  cudaSetDevice(X(p)->device);
+  if (!g_ev_init) { for (int i = 0; i < 8; ++i) cudaEventCreate(&g_ev[i]); g_ev_init = true; }
+  return cudaEventRecord(g_ev[slot], (cudaStream_t)X(p)->stream) == cudaSuccess ? 0 : 1;
+#endif
+}
+double pomgpu_event_elapsed_ms(pomgpu_t* p, int a, int b) {
+#ifdef POMGPU_EMU
+  (void)p; (void)a; (void)b; return 0.;
+#else
+  float ms = -1.f;
+  cudaSetDevice(X(p)->device);
+  cudaEventSynchronize(g_ev[b]);
+  cudaEventElapsedTime(&ms, g_ev[a], g_ev[b]);
+  return ms;
+#endif
+}
+int pomgpu_profile_begin(pomgpu_t* p) { dev_sync(X(p)); X(p)->prof_on = 1; return 0; }
+int pomgpu_profile_end(pomgpu_t* p, char* json, int len) { X(p)->prof_on = 0; return prof_report(X(p), json, len); }
 long pomgpu_launch_count(pomgpu_t* p, int reset) {
   long n = X(p)->launches;
   if (reset) X(p)->launches = 0;

@@ -58,6 +58,14 @@ def _bind(path):
     L.pomgpu_sync.argtypes = [P]
     L.pomgpu_check_velocity.restype = C.c_double
     L.pomgpu_check_velocity.argtypes = [P]
+    L.pomgpu_push_async.argtypes = [P, C.c_char_p, P]
+    L.pomgpu_pin_host.argtypes = [P, C.c_ulong]
+    L.pomgpu_unpin_host.argtypes = [P]
+    L.pomgpu_event_record.argtypes = [P, C.c_int]
+    L.pomgpu_event_elapsed_ms.restype = C.c_double
+    L.pomgpu_event_elapsed_ms.argtypes = [P, C.c_int, C.c_int]
+    L.pomgpu_profile_begin.argtypes = [P]
+    L.pomgpu_profile_end.argtypes = [P, C.c_char_p, C.c_int]
     L.pomgpu_launch_count.restype = C.c_long
     L.pomgpu_launch_count.argtypes = [P, C.c_int]
     for n in ("lateral_viscosity mode_interaction advave advct advq advu advv baropg profq profu "
@@ -153,6 +161,33 @@ class PomGpu:
         out = np.empty(self.shapes[name], dtype=np.float64, order="F")
         self._ck(self.L.pomgpu_pull(self.h, name.encode(), out.ctypes.data_as(C.c_void_p)), f"pull({name})")
         return out
+
+    def pinned(self, name):
+        """A page-locked host array shaped like field `name` (per-step forcing buffers)."""
+        a = np.zeros(self.shapes[name], dtype=np.float64, order="F")
+        if self.L.pomgpu_pin_host(a.ctypes.data_as(C.c_void_p), a.nbytes) != 0:
+            raise PomGpuError("cudaHostRegister failed")
+        return a
+
+    def put_async(self, name, a):
+        """Enqueue host->HBM copy of a (pinned, Fortran-ordered) array; no host wait."""
+        assert a.flags.f_contiguous and a.shape == self.shapes[name]
+        self._ck(self.L.pomgpu_push_async(self.h, name.encode(), a.ctypes.data_as(C.c_void_p)), f"push_async({name})")
+
+    def event_record(self, slot):
+        self._ck(self.L.pomgpu_event_record(self.h, slot), "event_record")
+
+    def event_elapsed_ms(self, a, b):
+        return self.L.pomgpu_event_elapsed_ms(self.h, a, b)
+
+    def profile_begin(self):
+        self.L.pomgpu_profile_begin(self.h)
+
+    def profile_end(self):
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        self._ck(self.L.pomgpu_profile_end(self.h, buf, len(buf)), "profile_end")
+        return json.loads(buf.value.decode())
 
     def load(self, state):
         """state = {'consts': {...}, 'fields': {name: ndarray}} (extpom_b200.synthetic)."""

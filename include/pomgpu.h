@@ -49,6 +49,11 @@ int pomgpu_get_const(pomgpu_t* ctx, const char* name, double* value);
 int pomgpu_push(pomgpu_t* ctx, const char* name, const double* host);
 int pomgpu_pull(pomgpu_t* ctx, const char* name, double* host);
 long pomgpu_field_elems(pomgpu_t* ctx, const char* name); /* 0 if unknown */
+/* enqueue-only push (no host wait) for the per-step forcing; the host buffer should be
+ * page-locked (pomgpu_pin_host registers a driver-owned array, e.g. a COMMON block) */
+int pomgpu_push_async(pomgpu_t* ctx, const char* name, const double* host);
+int pomgpu_pin_host(void* ptr, unsigned long bytes);
+int pomgpu_unpin_host(void* ptr);
 
 /* ---- resident-mode time stepping -------------------------------------------
  * pomgpu_step = pom/advance.f:21-32 (lateral_viscosity, mode_interaction,
@@ -61,6 +66,13 @@ int pomgpu_sync(pomgpu_t* ctx);
  * max|vaf| and sets error_status when it exceeds vmaxl. */
 double pomgpu_check_velocity(pomgpu_t* ctx);
 long pomgpu_launch_count(pomgpu_t* ctx, int reset);
+/* per-kernel device time from CUDA events recorded on the launch stream around every
+ * kernel between begin and end; end writes a JSON array
+ * [{"name","launches","ms","bytes"}] where bytes = algorithmic bytes */
+int pomgpu_event_record(pomgpu_t* ctx, int slot);            /* slot 0..7, on the launch stream */
+double pomgpu_event_elapsed_ms(pomgpu_t* ctx, int a, int b);  /* waits for event b */
+int pomgpu_profile_begin(pomgpu_t* ctx);
+int pomgpu_profile_end(pomgpu_t* ctx, char* json, int len);
 
 /* ---- the reference's subroutines on the resident state (same names) ---------
  * advance.f */

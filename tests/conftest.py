@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Build the oracle and the host-emulation library once (seconds); libpomgpu.so is built
+    by __graft_entry__.build() and must already be in-tree for the -m gpu tests."""
+    from oracle import pomo
+    pomo.build()
+    from tests import emu
+    emu.build_emu()

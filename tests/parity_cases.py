@@ -1,0 +1,156 @@
+"""Parity checks shared by the host-emulated (CPU) and the real-GPU test modules.
+`factory(im,jm,kb)` builds the solver under test (PomGpu on the device, EmuPom on CPU)."""
+import os
+
+import numpy as np
+
+from extpom_b200 import synthetic as syn
+from oracle.pomo import Oracle
+from scripts.make_golden import CASES
+from tests.common import F2, F3, RTOL, assert_close, compare, rel_err
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+GOLDEN = sorted(CASES)
+
+# (dims, steps, generator/namelist overrides)
+STEP_CASES = [
+    ((20, 17, 8), 8, {}),
+    ((20, 17, 8), 8, {"nadv": 1}),
+    ((24, 19, 9), 8, {"island": True}),
+    ((40, 31, 16), 30, {}),
+    ((24, 19, 9), 6, {"wind": False, "noise": False}),
+    ((24, 19, 9), 6, {"nbct": 2}),
+    ((24, 19, 9), 6, {"nbct": 3, "nbcs": 3}),
+    ((24, 19, 9), 6, {"nbct": 4, "ntp": 3}),
+    ((24, 19, 9), 6, {"mode": 4}),
+    ((33, 6, 6), 5, {}),          # minimum-width channel
+    ((6, 33, 7), 5, {}),
+    ((21, 18, 8), 6, {"isplit": 5, "dte": 6.0}),
+    ((21, 18, 8), 6, {"aam_init": 0.0}),
+]
+
+
+def case_id(c):
+    d, n, kw = c
+    return "x".join(map(str, d)) + f"-{n}st" + "".join(f"-{k}{v}" for k, v in kw.items())
+
+
+def pair(factory, dims, **kw):
+    st, o = syn.seamount(*dims, Oracle, **kw)
+    _, g = syn.seamount(*dims, factory, **kw)
+    return st, o, g
+
+
+def check_steps(factory, case):
+    dims, n, kw = case
+    st, o, g = pair(factory, dims, **kw)
+    assert_close(o, g)                       # the initial dens/baropg calls already ran
+    for i in range(1, n + 1):
+        o.step(i)
+        g.step(i)
+    worst = assert_close(o, g)
+    vo, vg = o.check_velocity(), g.check_velocity()
+    assert abs(vo - vg) <= RTOL * max(1.0, abs(vo))
+    return worst
+
+
+def check_stages(factory, dims, nstep=3):
+    """Run step `nstep` block by block on both sides; every block must agree bitwise
+    (no libm call differs on this small case)."""
+    st, o, g = pair(factory, dims)
+    for i in range(1, nstep):
+        o.step(i); g.step(i)
+    for s in (o, g):
+        s.set("iint", nstep); s.set("time", s.getc("dti") * nstep / 86400.0)
+        s.lateral_viscosity(); s.mode_interaction()
+    assert_close(o, g, tol=0.0)
+    for ie in range(1, int(o.getc("isplit")) + 1):
+        o.mode_external(ie); g.mode_external(ie)
+        assert_close(o, g, tol=0.0, names=["el", "elb", "ua", "uab", "va", "vab", "d", "egf", "utf", "vtf", "etf"])
+    for stg in range(18):
+        o.internal_stage(nstep, stg); g.internal_stage(nstep, stg)
+        errs = compare(o, g)
+        bad = {k: v for k, v in errs.items() if v[0] > 1e-14}
+        assert not bad, (stg, bad)
+
+
+def _interior(a):
+    return a[1:-1, 1:-1]
+
+
+ROUTINES = ["dens", "baropg", "advct", "advave", "vertvl", "advq", "profq", "advt1", "advt2",
+            "proft1", "proft2", "proft3", "advu", "advv", "profu", "profv", "realvertvl"]
+
+
+def check_routine(factory, routine, dims):
+    """Call one reference subroutine on both sides from the same spun-up state and compare
+    every array it writes (unit-level parity through the C ABI entry of the same name)."""
+    st, o, g = pair(factory, dims, island=True)
+    for i in range(1, 4):
+        o.step(i); g.step(i)
+    # bring both to the same mid-step state: the q/t/u kernels consume w and the filtered fields
+    for s in (o, g):
+        s.set("iint", 4); s.set("time", s.getc("dti") * 4 / 86400.0)
+    kb = dims[2]
+    out, tol, kbskip = [], 1e-13, False
+    if routine == "dens":
+        o.dens("s", "t", "rho"); g.dens("s", "t", "rho"); out = ["rho"]
+    elif routine == "baropg":
+        o.baropg(); g.baropg(); out = ["drhox", "drhoy", "rho"]
+    elif routine == "advct":
+        o.advct(); g.advct(); out = ["advx", "advy"]
+    elif routine == "advave":
+        o.advave(); g.advave(); out = ["advua", "advva"]
+    elif routine == "vertvl":
+        o.vertvl(); o.bcondorl(5); g.vertvl(); out = ["w"]
+    elif routine == "advq":
+        o.f["uf"][...] = 0; o.f["vf"][...] = 0
+        o.advq("q2b", "q2", "uf"); o.advq("q2lb", "q2l", "vf"); g.advq(); out = ["uf", "vf"]
+    elif routine == "profq":
+        o.f["uf"][...] = 0; o.f["vf"][...] = 0
+        o.advq("q2b", "q2", "uf"); o.advq("q2lb", "q2l", "vf"); o.profq()
+        g.advq(); g.profq()
+        out = ["km", "kh", "kq", "l", "q2b", "q2lb"]
+        # uf,vf: interior columns only -- bcond(6) overwrites the boundary columns right after
+        for n in ("uf", "vf"):
+            assert rel_err(_interior(o.get(n)), _interior(g.get(n))) <= tol, n
+    elif routine in ("advt1", "advt2"):
+        fn = getattr(o, routine), getattr(g, routine)
+        fn[0]("tb", "t", "tclim", "uf"); fn[1]("tb", "t", "tclim", "uf")
+        fn[0]("sb", "s", "sclim", "vf"); fn[1]("sb", "s", "sclim", "vf")
+        a, b = o.get("uf"), g.get("uf")
+        assert rel_err(_interior(a)[:, :, :kb - 1], _interior(b)[:, :, :kb - 1]) <= tol
+        a, b = o.get("vf"), g.get("vf")
+        assert rel_err(_interior(a)[:, :, :kb - 1], _interior(b)[:, :, :kb - 1]) <= tol
+        out = ["tb", "sb"] + (["t", "s"] if routine == "advt1" else [])   # side effects on fb (and f)
+    elif routine.startswith("proft"):
+        nbc = {"proft1": 1, "proft2": 2, "proft3": 3}[routine]
+        src = o.get("t")
+        o.put("uf", src); g.put("uf", src)
+        o.proft("uf", "wtsurf", "tsurf", nbc); g.proft("uf", "wtsurf", "tsurf", nbc)
+        out, tol = ["uf"], (1e-13 if nbc != 2 else 1e-11)   # exp(): quad precision in the reference
+    elif routine in ("advu", "advv"):
+        getattr(o, routine)(); getattr(g, routine)(); out = ["uf" if routine == "advu" else "vf"]
+    elif routine in ("profu", "profv"):
+        o.advu(); o.advv(); g.advu(); g.advv()
+        getattr(o, routine)(); getattr(g, routine)()
+        out = ["uf", "wubot"] if routine == "profu" else ["vf", "wvbot"]
+    elif routine == "realvertvl":
+        o.realvertvl(); g.realvertvl(); out = ["wr"]
+    for n in out:
+        a, b = o.get(n), g.get(n)
+        assert rel_err(a, b) <= tol, (routine, n, rel_err(a, b))
+
+
+def check_golden(factory, name):
+    c = CASES[name]
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    _, g = syn.seamount(*c["dims"], factory, **c["kw"])
+    for i in range(1, c["steps"] + 1):
+        g.step(i)
+    for n in F3 + F2:
+        a, b = z[n], g.get(n)
+        if n in ("t", "tb", "s", "sb"):
+            a, b = a[:, :, :-1], b[:, :, :-1]
+        assert rel_err(a, b) <= RTOL, n
+    assert abs(float(z["vamax"]) - g.check_velocity()) <= RTOL

@@ -1,0 +1,83 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs; plus size-independent properties at BASELINE.json's full size."""
+import numpy as np
+import pytest
+
+from extpom_b200 import synthetic as syn
+from tests import parity_cases as pc
+from tests.common import RTOL, digest
+
+pytestmark = pytest.mark.gpu
+
+
+def _factory(im, jm, kb):
+    from extpom_b200.pomgpu import PomGpu
+    return PomGpu(im, jm, kb)
+
+
+@pytest.mark.parametrize("case", pc.STEP_CASES, ids=pc.case_id)
+def test_steps_match_oracle(case):
+    pc.check_steps(_factory, case)
+
+
+def test_stage_by_stage_is_bitwise_equal():
+    pc.check_stages(_factory, (26, 21, 10), nstep=3)
+
+
+@pytest.mark.parametrize("routine", pc.ROUTINES)
+def test_routine_matches_oracle(routine):
+    pc.check_routine(_factory, routine, (28, 22, 10))
+
+
+@pytest.mark.parametrize("name", pc.GOLDEN)
+def test_matches_golden(name):
+    pc.check_golden(_factory, name)
+
+
+def test_reference_default_grid_100_steps():
+    """BASELINE configs[0] shape (282x306x40, pom.h_dist:22-28) is too slow for the oracle in CI
+    at 100 steps; a 141x153x40 quarter of it is compared after 40 steps."""
+    worst = pc.check_steps(_factory, ((141, 153, 40), 40, {}))
+    print("worst rel max-abs error after 40 steps:", worst)
+
+
+def test_full_size_properties():
+    """1024x1024x41 (BASELINE configs[1]): (a) two independent runs are bitwise identical,
+    (b) fields stay finite and below the blow-up bound, (c) land stays masked,
+    (d) a strip of the result equals the oracle run on ... is covered at smaller sizes."""
+    im = jm = 1024; kb = 41
+    dig = []
+    for rep in range(2):
+        st, g = syn.seamount(im, jm, kb, _factory)
+        for i in range(1, 6):
+            g.step(i)
+        v = g.check_velocity()
+        assert np.isfinite(v) and v < 1.0
+        fields = {n: g.get(n) for n in ("u", "t", "q2", "el")}
+        dig.append({n: digest(a) for n, a in fields.items()})
+        if rep == 0:
+            fsm = st["fields"]["fsm"]
+            for n, a in fields.items():
+                assert np.isfinite(a).all(), n
+            assert np.abs(fields["t"][:, :, :kb - 1][fsm == 0]).max() == 0.0
+            assert np.abs(fields["el"][fsm == 0]).max() == 0.0
+        del g, st
+    assert dig[0] == dig[1]
+
+
+def test_rest_state_at_scale():
+    """Uniform T,S, no wind, no inflow on 512x512x41: stays at rest (|u| < 1e-10)."""
+    im = jm = 512; kb = 41
+    st = syn.make_state(im, jm, kb, wind=False, noise=False)
+    f = st["fields"]
+    for n in ("tb", "t", "tclim"): f[n][...] = 10.0
+    for n in ("ub", "u", "uab", "ua", "uabe", "uabw"): f[n][...] = 0.0
+    f["tsurf"][...] = 10.0
+    for n in ("tbe", "tbw", "tbn", "tbs"): f[n][:, :kb - 1] = 10.0
+    g = _factory(im, jm, kb)
+    g.load(st)
+    syn.finish_init(st, g)
+    for i in range(1, 6):
+        g.step(i)
+    for n in ("u", "v", "ua", "el", "w"):
+        assert np.abs(g.get(n)).max() <= 1e-10, n
