@@ -9,90 +9,120 @@
 #include "pom_core.h"
 #include "pom_names.h"
 
+#ifndef POM_ADVCT_TY
+#define POM_ADVCT_TY 16
+#define POM_ADVCT_MINB 1
+#endif
+
 namespace pom {
 
+// advct as a shared-memory tile kernel: per level every thread evaluates the five fluxes
+// of its own point once -- x-part xflux (X), x-part yflux (Y), y-part xflux (XP), y-part
+// yflux (YP), and the curvature products (CV, CU) -- and the tile interior differences them.
 struct AdvctK : KBase {
   POM_KINFO("advct", 5, 2, 5, 2)
   using KBase::KBase;
-  // solver.f:221-225; zero outside 2..imm1 x 2..jmm1 (zero fill :213)
-  POM_HD double curv(int i, int j, int k) const {
+  static constexpr int NV = 6, HL = 1, HR = 1, HB = 1, HT = 1, TY = POM_ADVCT_TY, MINB = POM_ADVCT_MINB;
+  enum { X, Y, XP, YP, CV, CU };
+  struct State {
+    double dtE, dtW, dtS, dtN, dtSW, dtWS, q4, dtc, dxc, dyc, qdx4, qdy4, dyd, dxd;
+    RDiv ddx, ddy, ddy4, ddx4, ddxdy;   // hoisted divisors dx, dy, dy4, dx4, dx*dy
+    double aru25, arv25, sx, sy;
+    bool fx, fy, fxp, fyp, interior, i3, j3;
+  };
+  POM_HD int k0() const { return 1; }
+  POM_HD int k1() const { return g.kb - 1; }
+  POM_HD void pre(int i, int j, bool inside, bool out, State& s) const {
     POM_DIMS;
-    if (i < 2 || i > imm1 || j < 2 || j > jmm1) return 0.;
-    return .25*((v(i,j+1,k)+v(i,j,k))*(dy(i+1,j)-dy(i-1,j))
-                -(u(i+1,j,k)+u(i,j,k))*(dx(i,j+1)-dx(i,j-1)))
-           /(dx(i,j)*dy(i,j));
-  }
-  // corner diffusive term shared by yflux (x-part, :261-270) and xflux (y-part, :348-357)
-  POM_HD double cornerdiff(int i, int j, int k, double dy4, double dx4) const {
-    double dtaam=.25*(dt(i,j)+dt(i-1,j)+dt(i,j-1)+dt(i-1,j-1))
-                 *(aam(i,j,k)+aam(i-1,j,k)+aam(i,j-1,k)+aam(i-1,j-1,k));
-    return dtaam*((ub(i,j,k)-ub(i,j-1,k))/dy4
-                  +(vb(i,j,k)-vb(i-1,j,k))/dx4);
-  }
-  // x-part xflux(i,j,k), 1<=i<=imm1 (:237-239,258-260,272); xflux(1,j,k)=0 (:215)
-  POM_HD double xfx(int i, int j, int k) const {
-    if (i < 2) return 0.;
-    double a=.125*((dt(i+1,j)+dt(i,j))*u(i+1,j,k)
-                   +(dt(i,j)+dt(i-1,j))*u(i,j,k))
-                  *(u(i+1,j,k)+u(i,j,k));
-    a=a-dt(i,j)*aam(i,j,k)*2.*(ub(i+1,j,k)-ub(i,j,k))/dx(i,j);
-    return dy(i,j)*a;
-  }
-  // x-part yflux(i,j,k), 2<=i<=imm1, 2<=j<=jm (:247-249,264-274)
-  POM_HD double yfx(int i, int j, int k) const {
-    double dy4=dy(i,j)+dy(i-1,j)+dy(i,j-1)+dy(i-1,j-1);
-    double dx4=dx(i,j)+dx(i-1,j)+dx(i,j-1)+dx(i-1,j-1);
-    double a=.125*((dt(i,j)+dt(i,j-1))*v(i,j,k)
-                   +(dt(i-1,j)+dt(i-1,j-1))*v(i-1,j,k))
-                  *(u(i,j,k)+u(i,j-1,k));
-    a=a-cornerdiff(i,j,k,dy4,dx4);
-    return .25*dx4*a;
-  }
-  // y-part xflux(i,j,k), 2<=i<=im, 2<=j<=jmm1 (:327-329,351-363)
-  POM_HD double xfy(int i, int j, int k) const {
-    double dy4=dy(i,j)+dy(i-1,j)+dy(i,j-1)+dy(i-1,j-1);
-    double dx4=dx(i,j)+dx(i-1,j)+dx(i,j-1)+dx(i-1,j-1);
-    double a=.125*((dt(i,j)+dt(i-1,j))*u(i,j,k)
-                   +(dt(i,j-1)+dt(i-1,j-1))*u(i,j-1,k))
-                  *(v(i,j,k)+v(i-1,j,k));
-    a=a-cornerdiff(i,j,k,dy4,dx4);
-    return .25*dy4*a;
-  }
-  // y-part yflux(i,j,k), 1<=j<=jmm1 (:337-339,358-364); yflux(i,1,k)=0 (:321)
-  POM_HD double yfy(int i, int j, int k) const {
-    if (j < 2) return 0.;
-    double a=.125*((dt(i,j+1)+dt(i,j))*v(i,j+1,k)
-                   +(dt(i,j)+dt(i,j-1))*v(i,j,k))
-                  *(v(i,j+1,k)+v(i,j,k));
-    a=a-dt(i,j)*aam(i,j,k)*2.*(vb(i,j+1,k)-vb(i,j,k))/dy(i,j);
-    return dx(i,j)*a;
-  }
-  POM_HD void operator()(int i, int j) const {
-    POM_DIMS;
-    const bool interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
-    double sx = 0., sy = 0.;
-    for (int k = 1; k <= kbm1; ++k) {
-      double ax = 0., ay = 0.;
-      if (interior) {
-        double c00 = curv(i,j,k);
-        ax=xfx(i,j,k)-xfx(i-1,j,k)+yfx(i,j+1,k)-yfx(i,j,k);            // :285-286
-        if (i >= 3)                                                     // :293-300 (n_west==-1)
-          ax=ax-aru(i,j)*.25*(c00*dt(i,j)*(v(i,j+1,k)+v(i,j,k))
-                              +curv(i-1,j,k)*dt(i-1,j)*(v(i-1,j+1,k)+v(i-1,j,k)));
-        ay=xfy(i+1,j,k)-xfy(i,j,k)+yfy(i,j,k)-yfy(i,j-1,k);            // :375-376
-        if (j >= 3)                                                     // :383-390 (n_south==-1)
-          ay=ay+arv(i,j)*.25*(c00*dt(i,j)*(u(i+1,j,k)+u(i,j,k))
-                              +curv(i,j-1,k)*dt(i,j-1)*(u(i+1,j-1,k)+u(i,j-1,k)));
-      }
-      advx(i,j,k)=ax;
-      advy(i,j,k)=ay;
-      sx=sx+ax*dz(k);                                                   // advance.f:161-162
-      sy=sy+ay*dz(k);
+    const int jlo = g.joff + 1, jhi = g.joff + g.jml;
+    s.sx = 0.; s.sy = 0.;
+    // definition ranges (zero fill elsewhere, solver.f:213-216,319-321), limited to rows in memory
+    s.fx  = inside && i >= 2 && i <= imm1 && j >= 2 && j <= jmm1;                 // :234-277
+    s.fy  = inside && i >= 2 && i <= imm1 && j >= 2 && j <= jm && j - 1 >= jlo;   // :244-276
+    s.fxp = inside && i >= 2 && i <= im && j >= 2 && j <= jmm1 && j - 1 >= jlo;   // :324-366
+    s.fyp = inside && i >= 2 && i <= imm1 && j >= 2 && j <= jmm1 && j - 1 >= jlo && j + 1 <= jhi;   // :334-366, curv :218-228
+    s.interior = out && i >= 2 && i <= imm1 && j >= 2 && j <= jmm1;
+    s.i3 = i >= 3; s.j3 = j >= 3;
+    if (!(s.fx || s.fy || s.fxp || s.fyp)) return;
+    s.dtc = dt(i,j); s.dxc = dx(i,j); s.dyc = dy(i,j);
+    s.ddx.set(s.dxc); s.ddy.set(s.dyc);
+    s.dtW = dt(i,j)+dt(i-1,j);
+    if (s.fx || s.fyp) s.dtE = dt(i+1,j)+dt(i,j);
+    if (s.fy || s.fxp) {
+      s.dtS = dt(i,j)+dt(i,j-1);
+      s.dtSW = dt(i-1,j)+dt(i-1,j-1);
+      s.dtWS = dt(i,j-1)+dt(i-1,j-1);
+      s.q4 = .25*(dt(i,j)+dt(i-1,j)+dt(i,j-1)+dt(i-1,j-1));
+      const double dy4 = dy(i,j)+dy(i-1,j)+dy(i,j-1)+dy(i-1,j-1);
+      const double dx4 = dx(i,j)+dx(i-1,j)+dx(i,j-1)+dx(i-1,j-1);
+      s.ddy4.set(dy4); s.ddx4.set(dx4);
+      s.qdx4 = .25*dx4; s.qdy4 = .25*dy4;
     }
+    if (s.fyp) {
+      s.dtN = dt(i,j+1)+dt(i,j);
+      s.dyd = dy(i+1,j)-dy(i-1,j);
+      s.dxd = dx(i,j+1)-dx(i,j-1);
+      s.ddxdy.set(dx(i,j)*dy(i,j));
+    }
+    if (s.interior) { s.aru25 = aru(i,j)*.25; s.arv25 = arv(i,j)*.25; }
+  }
+  struct Regs { double u00, uE, uS, v00, vW, vN, ub00, ubE, ubS, vb00, vbW, vbN, a00, aW, aS, aSW; };
+  POM_HD void fetch(int i, int j, int k, const State& s, Regs& r) const {
+    if (!(s.fx || s.fy || s.fxp || s.fyp)) return;
+    const int o = POM_I3(i,j,k), im = g.im;
+    r.u00 = POM_LDG(p.u+o); r.v00 = POM_LDG(p.v+o); r.ub00 = POM_LDG(p.ub+o); r.vb00 = POM_LDG(p.vb+o);
+    r.a00 = POM_LDG(p.aam+o);
+    if (s.fx || s.fyp) { r.uE = POM_LDG(p.u+o+1); r.ubE = POM_LDG(p.ub+o+1); }
+    if (s.fyp) { r.vN = POM_LDG(p.v+o+im); r.vbN = POM_LDG(p.vb+o+im); }
+    if (s.fy || s.fxp) {
+      r.uS = POM_LDG(p.u+o-im); r.vW = POM_LDG(p.v+o-1); r.ubS = POM_LDG(p.ub+o-im); r.vbW = POM_LDG(p.vb+o-1);
+      r.aW = POM_LDG(p.aam+o-1); r.aS = POM_LDG(p.aam+o-im); r.aSW = POM_LDG(p.aam+o-im-1);
+    }
+  }
+  POM_HD void stage(int i, int j, int k, State& s, const Regs& r, double* v) const {
+    if (!(s.fx || s.fy || s.fxp || s.fyp)) return;
+    const double u00 = r.u00, v00 = r.v00, ub00 = r.ub00, vb00 = r.vb00, a00 = r.a00;
+    const double uE = r.uE, ubE = r.ubE, vN = r.vN, vbN = r.vbN;
+    if (s.fx) {                                                          // :237-239,258-260,272
+      double a=.125*(s.dtE*uE+s.dtW*u00)*(uE+u00);
+      a=a-s.ddx(s.dtc*a00*2.*(ubE-ub00));
+      v[X]=s.dyc*a;
+    }
+    if (s.fy || s.fxp) {
+      const double uS = r.uS, vW = r.vW, ubS = r.ubS, vbW = r.vbW;
+      const double dtaam=s.q4*(a00+r.aW+r.aS+r.aSW);                       // :261-263,348-350
+      const double cd=dtaam*(s.ddy4(ub00-ubS)+s.ddx4(vb00-vbW));          // :265-270,352-357
+      if (s.fy) { double a=.125*(s.dtS*v00+s.dtSW*vW)*(u00+uS); v[Y]=s.qdx4*(a-cd); }     // :247-249,273-274
+      if (s.fxp) { double a=.125*(s.dtW*u00+s.dtWS*uS)*(v00+vW); v[XP]=s.qdy4*(a-cd); }   // :327-329,362-363
+    }
+    if (s.fyp) {
+      double a=.125*(s.dtN*vN+s.dtS*v00)*(vN+v00);                        // :337-339
+      a=a-s.ddy(s.dtc*a00*2.*(vbN-vb00));                                  // :358-360
+      v[YP]=s.dxc*a;                                                      // :364
+      const double cv=s.ddxdy(.25*((vN+v00)*s.dyd-(uE+u00)*s.dxd));         // :221-225
+      v[CV]=cv*s.dtc*(vN+v00);                                            // :297-298
+      v[CU]=cv*s.dtc*(uE+u00);                                            // :387-388
+    }
+  }
+  POM_HD void combine(int i, int j, int k, State& s, const Tile& tl) const {
+    double ax = 0., ay = 0.;
+    if (s.interior) {
+      ax=tl(X,0,0)-tl(X,-1,0)+tl(Y,0,1)-tl(Y,0,0);                            // :285-286
+      if (s.i3) ax=ax-s.aru25*(tl(CV,0,0)+tl(CV,-1,0));                     // :293-300 (n_west==-1)
+      ay=tl(XP,1,0)-tl(XP,0,0)+tl(YP,0,0)-tl(YP,0,-1);                        // :375-376
+      if (s.j3) ay=ay+s.arv25*(tl(CU,0,0)+tl(CU,0,-1));                     // :383-390 (n_south==-1)
+    }
+    advx(i,j,k)=ax;
+    advy(i,j,k)=ay;
+    s.sx=s.sx+ax*dz(k);                                                   // advance.f:161-162
+    s.sy=s.sy+ay*dz(k);
+  }
+  POM_HD void post(int i, int j, State& s) const {
+    const int kb = g.kb;
     advx(i,j,kb)=0.;
     advy(i,j,kb)=0.;
-    adx2d(i,j)=sx;
-    ady2d(i,j)=sy;
+    adx2d(i,j)=s.sx;
+    ady2d(i,j)=s.sy;
   }
 };
 
@@ -174,7 +204,7 @@ struct SmagK : KBase {
   }
 };
 
-void run_advct(Ctx* c, int j0, int j1) { launch_cols(c, AdvctK(c), 1, c->g.im, j0, j1); }
+void run_advct(Ctx* c, int j0, int j1) { launch_tiles(c, AdvctK(c), 1, c->g.im, j0, j1); }
 void run_baropg(Ctx* c, int j0, int j1) {
   launch_cols(c, BaropgK(c), 1, c->g.im, j0, j1);
   double* tmp = c->p.rho; c->p.rho = c->p.rho2; c->p.rho2 = tmp;

@@ -57,8 +57,8 @@ const FieldInfo* find_field(const char* name) {
 size_t field_elems(const Ctx* c, const FieldInfo* f) {
   const Geo& g = c->g;
   switch (f->kind) {
-    case K3D: return g.n2 * g.kb;
-    case K2D: return g.n2;
+    case K3D: return (size_t)g.n2 * g.kb;
+    case K2D: return (size_t)g.n2;
     case KBJ: return g.jml;
     case KBI: return g.im;
     case KBJK: return (size_t)g.jml * g.kb;
@@ -179,7 +179,7 @@ int prof_report(Ctx* c, char* buf, int n) {
 
 // ---- lifecycle ------------------------------------------------------------------
 Ctx* ctx_create(int im, int jm_global, int kb, int j_first, int j_last, int ghost, int device) {
-  if (im < 6 || jm_global < 6 || kb < 4 || kb > 128) return nullptr;
+  if (im < 6 || jm_global < 6 || kb < 4 || kb > 64) return nullptr;   // KMAX of the column solvers
   Ctx* c = (Ctx*)calloc(1, sizeof(Ctx));
   c->device = device;
   c->jown0 = j_first; c->jown1 = j_last; c->ghost = ghost;
@@ -187,7 +187,8 @@ Ctx* ctx_create(int im, int jm_global, int kb, int j_first, int j_last, int ghos
   int r1 = j_last + ghost; if (r1 > jm_global) r1 = jm_global;
   c->g.im = im; c->g.kb = kb; c->g.jmg = jm_global;
   c->g.joff = r0 - 1; c->g.jml = r1 - r0 + 1;
-  c->g.n2 = (size_t)im * c->g.jml;
+  if ((double)im * c->g.jml * kb >= 2147483647.) { free(c); return nullptr; }
+  c->g.n2 = im * c->g.jml;
   if (dev_init(c)) { free(c); return nullptr; }
   int n;
   const FieldInfo* t = field_table(&n);

@@ -63,7 +63,7 @@ extern "C" {
 #define POMO_SCAL_I(X) \
   X(iint) X(mode) X(ntp) X(iext) X(ispadv) X(isplit) X(nadv) X(nbct) X(nbcs) \
   X(nitera) X(npg) X(error_status) X(n_west) X(n_east) X(n_south) X(n_north) \
-  X(lrestore)
+  X(lrestore) X(pow_mode)
 
 #define POMO_NSCR3 12
 #define POMO_NSCR2 6

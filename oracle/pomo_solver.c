@@ -653,6 +653,21 @@ void pomo_baropg(pomo_t *S) {
 }
 
 /* ------------------------------------------------------------------ */
+/* |S|**1.5 (solver.f:1195).  pow_mode 0 (default): libm pow, what gfortran emits for a real
+ * exponent.  pow_mode 1: x*sqrt(x) with the rounding errors of sqrt and of the product
+ * recovered by fma -- the routine the CUDA path uses; tests switch to it to show that this
+ * libm call is the ONLY source of GPU/oracle differences (everything else is bitwise). */
+static double pow15(const pomo_t *S, double x) {
+  if (S->pow_mode == 0) return pow(x, 1.5);
+  if (!(x > 0.)) return 0.;
+  double sq = sqrt(x);
+  double res = fma(-sq, sq, x);
+  double ds = res / (2. * sq);
+  double pr = x * sq;
+  double er = fma(x, sq, -pr);
+  return pr + (er + x * ds);
+}
+
 /* solver.f:1162-1209 dens */
 void pomo_dens(pomo_t *S, double *sip, double *tip, double *rhoop) {
   DIMS;
@@ -674,7 +689,7 @@ void pomo_dens(pomo_t *S, double *sip, double *tip, double *rhoop) {
                +7.6438e-5*tr2-8.2467e-7*tr3
                +5.3875e-9*tr4)*sr
              +(-5.72466e-3+1.0227e-4*tr
-               -1.6546e-6*tr2)*pow(fabs(sr),1.5)
+               -1.6546e-6*tr2)*pow15(S,fabs(sr))
              +4.8314e-4*sr*sr;
     double cr=1449.1+.0821*p+4.55*tr-.045*tr2
               +1.34*(sr-35.);

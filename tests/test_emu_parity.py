@@ -15,6 +15,11 @@ def test_steps_match_oracle(case):
     pc.check_steps(EmuPom, case)
 
 
+def test_bitwise_equal_over_40_steps_with_common_pow():
+    assert pc.check_steps(EmuPom, ((60, 50, 20), 40, {}), pow_mode=1, tol=0.0) == 0.0
+    pc.check_steps(EmuPom, ((60, 50, 20), 40, {}), pow_mode=0, tol=1e-9)
+
+
 def test_stage_by_stage_is_bitwise_equal():
     pc.check_stages(EmuPom, (26, 21, 10), nstep=3)
 

@@ -34,11 +34,16 @@ def test_matches_golden(name):
     pc.check_golden(_factory, name)
 
 
-def test_reference_default_grid_100_steps():
-    """BASELINE configs[0] shape (282x306x40, pom.h_dist:22-28) is too slow for the oracle in CI
-    at 100 steps; a 141x153x40 quarter of it is compared after 40 steps."""
-    worst = pc.check_steps(_factory, ((141, 153, 40), 40, {}))
-    print("worst rel max-abs error after 40 steps:", worst)
+def test_quarter_of_reference_default_grid_40_steps():
+    """BASELINE configs[0] is the reference's own 282x306x40 grid (pom.h_dist:22-28); a
+    141x153x40 quarter of it keeps the oracle within CI time.  After 40 internal steps:
+    (a) bitwise equal when |S|**1.5 uses the same routine on both sides,
+    (b) <= 1e-8 (max-abs / field max) against libm pow -- 1-ulp density differences amplified
+        by the turbulence closure (q2l is the most sensitive field, ~1.5e-9 measured)."""
+    case = ((141, 153, 40), 40, {})
+    assert pc.check_steps(_factory, case, pow_mode=1, tol=0.0) == 0.0
+    worst = pc.check_steps(_factory, case, pow_mode=0, tol=1e-8)
+    print("worst rel max-abs error after 40 steps vs libm-pow oracle:", worst)
 
 
 def test_full_size_properties():
