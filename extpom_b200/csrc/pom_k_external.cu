@@ -12,56 +12,64 @@
 namespace pom {
 
 // ------------------------------------------------------------------ advave ----
+// Tile kernel (single "level"): every thread evaluates the four fluxes of its own point --
+// u-half fluxua (FXU) / fluxva (FYU), v-half fluxua (FXV) / fluxva (FYV) -- once, sharing
+// tps (solver.f:47-53,106) between the two halves like the reference does.
 struct AdvaveK : KBase {
   POM_KINFO("advave", 0, 0, 8, 2)
   using KBase::KBase;
-  POM_HD double dx4(int i, int j) const { return dx(i,j)+dx(i-1,j)+dx(i,j-1)+dx(i-1,j-1); }
-  POM_HD double dy4(int i, int j) const { return dy(i,j)+dy(i-1,j)+dy(i,j-1)+dy(i-1,j-1); }
-  // tps(i,j), 2<=i<=im, 2<=j<=jm (solver.f:47-53); reused by the v half (:106)
-  POM_HD double tpsf(int i, int j) const {
-    return .25*(d(i,j)+d(i-1,j)+d(i,j-1)+d(i-1,j-1))
-           *(aam2d(i,j)+aam2d(i,j-1)+aam2d(i-1,j)+aam2d(i-1,j-1))
-           *((uab(i,j)-uab(i,j-1))/dy4(i,j)
-             +(vab(i,j)-vab(i-1,j))/dx4(i,j));
-  }
-  // u half: fluxua(i,j) for 1<=i<=imm1, 2<=j<=jm (:22-24,39-41,54); fluxua(1,j)=0
-  POM_HD double fxu(int i, int j) const {
-    if (i < 2) return 0.;
-    double a=.125*((d(i+1,j)+d(i,j))*ua(i+1,j)+(d(i,j)+d(i-1,j))*ua(i,j))
-                 *(ua(i+1,j)+ua(i,j));
-    a=a-d(i,j)*2.*aam2d(i,j)*(uab(i+1,j)-uab(i,j))/dx(i,j);
-    return a*dy(i,j);
-  }
-  // u half: fluxva(i,j), 2<=i<=im, 2<=j<=jm (:30-32,55-56)
-  POM_HD double fyu(int i, int j) const {
-    double a=.125*((d(i,j)+d(i,j-1))*va(i,j)+(d(i-1,j)+d(i-1,j-1))*va(i-1,j))
-                 *(ua(i,j)+ua(i,j-1));
-    return (a-tpsf(i,j))*.25*dx4(i,j);
-  }
-  // v half: fluxua(i,j), 2<=i<=im, 2<=j<=jm (:80-82,106-107)
-  POM_HD double fxv(int i, int j) const {
-    double a=.125*((d(i,j)+d(i-1,j))*ua(i,j)+(d(i,j-1)+d(i-1,j-1))*ua(i,j-1))
-                 *(va(i-1,j)+va(i,j));
-    return (a-tpsf(i,j))*.25*dy4(i,j);
-  }
-  // v half: fluxva(i,j), 1<=j<=jmm1 (:88-90,97-99,105); fluxva(i,1)=0
-  POM_HD double fyv(int i, int j) const {
-    if (j < 2) return 0.;
-    double a=.125*((d(i,j+1)+d(i,j))*va(i,j+1)+(d(i,j)+d(i,j-1))*va(i,j))
-                 *(va(i,j+1)+va(i,j));
-    a=a-d(i,j)*2.*aam2d(i,j)*(vab(i,j+1)-vab(i,j))/dy(i,j);
-    return a*dx(i,j);
-  }
-  POM_HD void operator()(int i, int j) const {
+  static constexpr int NV = 4, HL = 1, HR = 1, HB = 1, HT = 1, TY = 16, MINB = 2;
+  enum { FXU, FYU, FXV, FYV };
+  struct State { bool interior; };
+  struct Regs {};
+  POM_HD int k0() const { return 1; }
+  POM_HD int k1() const { return 1; }
+  POM_HD void pre(int i, int j, bool, bool out, State& s) const {
     POM_DIMS;
+    s.interior = out && i >= 2 && i <= imm1 && j >= 2 && j <= jmm1;
+  }
+  POM_HD void fetch(int, int, int, const State&, Regs&) const {}
+  POM_HD void stage(int i, int j, int, State&, const Regs&, double* v) const {
+    POM_DIMS;
+    const int jlo = g.joff + 1, jhi = g.joff + g.jml;
+    if (i < 2 || j < 2 || j - 1 < jlo) return;
+    const double d00=d(i,j), dW=d(i-1,j), dS=d(i,j-1), dSW=d(i-1,j-1);
+    const double ua00=ua(i,j), va00=va(i,j), uaS=ua(i,j-1), vaW=va(i-1,j);
+    const double dx4=dx(i,j)+dx(i-1,j)+dx(i,j-1)+dx(i-1,j-1);
+    const double dy4=dy(i,j)+dy(i-1,j)+dy(i,j-1)+dy(i-1,j-1);
+    // tps(i,j), 2<=i<=im, 2<=j<=jm (:47-53)
+    const double tp=.25*(d00+dW+dS+dSW)
+                    *(aam2d(i,j)+aam2d(i,j-1)+aam2d(i-1,j)+aam2d(i-1,j-1))
+                    *((uab(i,j)-uab(i,j-1))/dy4+(vab(i,j)-vab(i-1,j))/dx4);
+    {   // u half fluxva (:30-32,55-56) and v half fluxua (:80-82,106-107)
+      double a=.125*((d00+dS)*va00+(dW+dSW)*vaW)*(ua00+uaS);
+      v[FYU]=(a-tp)*.25*dx4;
+      double b=.125*((d00+dW)*ua00+(dS+dSW)*uaS)*(vaW+va00);
+      v[FXV]=(b-tp)*.25*dy4;
+    }
+    if (i <= imm1) {   // u half fluxua (:22-24,39-41,54)
+      const double dE=d(i+1,j), uaE=ua(i+1,j);
+      double a=.125*((dE+d00)*uaE+(d00+dW)*ua00)*(uaE+ua00);
+      a=a-d00*2.*aam2d(i,j)*(uab(i+1,j)-uab(i,j))/dx(i,j);
+      v[FXU]=a*dy(i,j);
+    }
+    if (j <= jmm1 && j + 1 <= jhi) {   // v half fluxva (:88-90,97-99,105)
+      const double dN=d(i,j+1), vaN=va(i,j+1);
+      double a=.125*((dN+d00)*vaN+(d00+dS)*va00)*(vaN+va00);
+      a=a-d00*2.*aam2d(i,j)*(vab(i,j+1)-vab(i,j))/dy(i,j);
+      v[FYV]=a*dx(i,j);
+    }
+  }
+  POM_HD void combine(int i, int j, int, State& s, const Regs&, const Tile& tl) const {
     double au = 0., av = 0.;
-    if (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1) {
-      au=fxu(i,j)-fxu(i-1,j)+fyu(i,j+1)-fyu(i,j);       // :65-66
-      av=fxv(i+1,j)-fxv(i,j)+fyv(i,j)-fyv(i,j-1);       // :116-117
+    if (s.interior) {
+      au=tl(FXU,0,0)-tl(FXU,-1,0)+tl(FYU,0,1)-tl(FYU,0,0);       // :65-66
+      av=tl(FXV,1,0)-tl(FXV,0,0)+tl(FYV,0,0)-tl(FYV,0,-1);       // :116-117
     }
     advua(i,j)=au;
     advva(i,j)=av;
   }
+  POM_HD void post(int, int, State&) const {}
 };
 
 // ------------------------------------------- mode_interaction tail -------------
@@ -201,7 +209,7 @@ struct ExtUvK : KBase {
   }
 };
 
-void run_advave(Ctx* c, int j0, int j1) { launch_cols(c, AdvaveK(c), 1, c->g.im, j0, j1); }
+void run_advave(Ctx* c, int j0, int j1) { launch_tiles(c, AdvaveK(c), 1, c->g.im, j0, j1); }
 void run_mode_inter_tail(Ctx* c, int j0, int j1) { launch_cols(c, ModeInterTailK(c), 1, c->g.im, j0, j1); }
 void run_ext_elf(Ctx* c, int j0, int j1) { launch_cols(c, ExtElfK(c), 1, c->g.im, j0, j1); }
 

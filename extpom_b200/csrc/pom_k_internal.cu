@@ -19,6 +19,7 @@ struct UvAdjustK : KBase {
     POM_DIMS;
     double tu = 0., tv = 0.;
     for (int k = 1; k <= kbm1; ++k) {
+      PF3(p.u,i,j,k+3); PF3(p.v,i,j,k+3);
       tu=tu+u(i,j,k)*dz(k);
       tv=tv+v(i,j,k)*dz(k);
     }
@@ -52,6 +53,7 @@ struct VertvlK : KBase {
       const double dxy=dx(i,j)*dy(i,j);
       const double de=(etf(i,j)-etb(i,j))/dti2;
       for (int k = 1; k <= kbm1; ++k) {
+        PF3(p.u,i,j,k+2); PF3(p.v,i,j,k+2); PF3(p.v,i,j+1,k+2);
         w(i,j,k)=wk*m;
         wk=wk+dz(k)*((xf(i+1,j,k)-xf(i,j,k)+yf(i,j+1,k)-yf(i,j,k))/dxy+de);   // :2011-2015
       }
@@ -63,49 +65,109 @@ struct VertvlK : KBase {
 };
 
 // ---------------------------------------------------------------------------
-// advq (solver.f:411-477) for q2 -> uf and q2l -> vf in one pass
+// advq (solver.f:411-477) for q2 -> uf and q2l -> vf in one pass, as a tile kernel: each
+// thread evaluates the x/y fluxes of both quantities at its own point once per level.
 struct AdvqK : KBase {
   POM_KINFO("advq", 8, 2, 9, 0)
   using KBase::KBase;
-  POM_HD double xfl(const double* q, const double* qb, int i, int j, int k) const {
-    double a=.125*(A3(q,i,j,k)+A3(q,i-1,j,k))*(dt(i,j)+dt(i-1,j))*(u(i,j,k)+u(i,j,k-1));   // :428-429
-    a=a-.25*(aam(i,j,k)+aam(i-1,j,k)+aam(i,j,k-1)+aam(i-1,j,k-1))
-         *(h(i,j)+h(i-1,j))
-         *(A3(qb,i,j,k)-A3(qb,i-1,j,k))*dum(i,j)
-         /(dx(i,j)+dx(i-1,j));                                          // :440-445
-    return .5*(dy(i,j)+dy(i-1,j))*a;                                    // :452
-  }
-  POM_HD double yfl(const double* q, const double* qb, int i, int j, int k) const {
-    double a=.125*(A3(q,i,j,k)+A3(q,i,j-1,k))*(dt(i,j)+dt(i,j-1))*(v(i,j,k)+v(i,j,k-1));   // :430-431
-    a=a-.25*(aam(i,j,k)+aam(i,j-1,k)+aam(i,j,k-1)+aam(i,j-1,k-1))
-         *(h(i,j)+h(i,j-1))
-         *(A3(qb,i,j,k)-A3(qb,i,j-1,k))*dvm(i,j)
-         /(dy(i,j)+dy(i,j-1));                                          // :446-451
-    return .5*(dx(i,j)+dx(i,j-1))*a;                                    // :453
-  }
-  POM_HD double qfv(const double* q, const double* qb, int i, int j, int k) const {
-    double r=(w(i,j,k-1)*A3(q,i,j,k-1)-w(i,j,k+1)*A3(q,i,j,k+1))
-             *art(i,j)/(dz(k)+dz(k-1))
-             +xfl(q,qb,i+1,j,k)-xfl(q,qb,i,j,k)
-             +yfl(q,qb,i,j+1,k)-yfl(q,qb,i,j,k);                        // :465-468
-    return ((h(i,j)+etb(i,j))*art(i,j)*A3(qb,i,j,k)-dti2*r)
-           /((h(i,j)+etf(i,j))*art(i,j));                               // :469-471
-  }
-  POM_HD void operator()(int i, int j) const {
+  static constexpr int NV = 4, HL = 0, HR = 1, HB = 0, HT = 1, TY = 16, MINB = 1;
+  enum { XA, YA, XB, YB };
+  struct State {
+    double dtx, dty, hx, hy, dumc, dvmc, hdy, hdx;   // (dt+dt), (h+h), masks, .5*(dy+dy), .5*(dx+dx)
+    RDiv ddxs, ddys, dhf;                             // (dx+dx(i-1)), (dy+dy(j-1)), (h+etf)*art
+    double hb, ar;                                    // (h+etb)*art, art
+    double um, vm, a0m, aWm, aSm;                     // level k-1: u, v, aam(i,j), aam(i-1,j), aam(i,j-1)
+    double wm, w0, qam, qbm, qa0, qb0;                // w(k-1), w(k), q(k-1), q(k) of q2 / q2l (output columns)
+    bool fxa, fya, interior;
+  };
+  struct Regs { double qa, qaW, qaS, qab, qabW, qabS, qb, qbW, qbS, qbb, qbbW, qbbS, u0, v0, a0, aW, aS, w1, qa1, qb1; };
+  POM_HD int k0() const { return 2; }
+  POM_HD int k1() const { return g.kb - 1; }
+  POM_HD void pre(int i, int j, bool inside, bool out, State& s) const {
     POM_DIMS;
-    const bool interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
-    uf(i,j,1)=0.; vf(i,j,1)=0.;                                         // advance.f:403-404
-    uf(i,j,kb)=0.; vf(i,j,kb)=0.;
-    for (int k = 2; k <= kbm1; ++k) {
-      double a = 0., b = 0.;
-      if (interior) {
-        a=qfv(p.q2,p.q2b,i,j,k);
-        b=qfv(p.q2l,p.q2lb,i,j,k);
-      }
-      uf(i,j,k)=a;
-      vf(i,j,k)=b;
+    const int jlo = g.joff + 1;
+    s.fxa = inside && i >= 2 && j >= 2;                       // :426-427 (j<=jm, i<=im)
+    s.fya = inside && i >= 2 && j >= 2 && j - 1 >= jlo;
+    s.interior = out && i >= 2 && i <= imm1 && j >= 2 && j <= jmm1;
+    if (out) {                                                // advance.f:403-404 and levels 1, kb
+      uf(i,j,1)=0.; vf(i,j,1)=0.; uf(i,j,kb)=0.; vf(i,j,kb)=0.;
+    }
+    if (!(s.fxa || s.fya)) return;
+    s.dtx = dt(i,j)+dt(i-1,j); s.hx = h(i,j)+h(i-1,j); s.dumc = dum(i,j);
+    s.hdy = .5*(dy(i,j)+dy(i-1,j)); s.ddxs.set(dx(i,j)+dx(i-1,j));
+    s.um = u(i,j,1); s.a0m = aam(i,j,1); s.aWm = aam(i-1,j,1);
+    if (s.fya) {
+      s.dty = dt(i,j)+dt(i,j-1); s.hy = h(i,j)+h(i,j-1); s.dvmc = dvm(i,j);
+      s.hdx = .5*(dx(i,j)+dx(i,j-1)); s.ddys.set(dy(i,j)+dy(i,j-1));
+      s.vm = v(i,j,1); s.aSm = aam(i,j-1,1);
+    }
+    if (s.interior) {
+      s.ar = art(i,j);
+      s.hb = (h(i,j)+etb(i,j))*s.ar;
+      s.dhf.set((h(i,j)+etf(i,j))*s.ar);
+      s.wm = w(i,j,1); s.w0 = w(i,j,2); s.qam = q2(i,j,1); s.qbm = q2l(i,j,1);
+      s.qa0 = q2(i,j,2); s.qb0 = q2l(i,j,2);
     }
   }
+  POM_HD void fetch(int i, int j, int k, const State& s, Regs& r) const {
+    if (!(s.fxa || s.fya)) return;
+    const int o = POM_I3(i,j,k), im = g.im;
+    r.qa = POM_LDG(p.q2+o); r.qaW = POM_LDG(p.q2+o-1); r.qab = POM_LDG(p.q2b+o); r.qabW = POM_LDG(p.q2b+o-1);
+    r.qb = POM_LDG(p.q2l+o); r.qbW = POM_LDG(p.q2l+o-1); r.qbb = POM_LDG(p.q2lb+o); r.qbbW = POM_LDG(p.q2lb+o-1);
+    r.u0 = POM_LDG(p.u+o); r.a0 = POM_LDG(p.aam+o); r.aW = POM_LDG(p.aam+o-1);
+    if (k + 1 <= g.kb - 1) {
+      const int n = o + g.n2;
+      POM_PREFETCH(p.q2+n); POM_PREFETCH(p.q2b+n); POM_PREFETCH(p.q2l+n); POM_PREFETCH(p.q2lb+n);
+      POM_PREFETCH(p.u+n); POM_PREFETCH(p.v+n); POM_PREFETCH(p.aam+n); POM_PREFETCH(p.w+n+g.n2);
+    }
+    if (s.fya) {
+      r.qaS = POM_LDG(p.q2+o-im); r.qabS = POM_LDG(p.q2b+o-im); r.qbS = POM_LDG(p.q2l+o-im); r.qbbS = POM_LDG(p.q2lb+o-im);
+      r.v0 = POM_LDG(p.v+o); r.aS = POM_LDG(p.aam+o-im);
+    }
+    if (s.interior) { r.w1 = POM_LDG(p.w+o+g.n2); r.qa1 = POM_LDG(p.q2+o+g.n2); r.qb1 = POM_LDG(p.q2l+o+g.n2); }
+  }
+  POM_HD void stage(int i, int j, int k, State& s, const Regs& r, double* v) const {
+    if (s.fxa) {
+      const double a4=r.a0+r.aW+s.a0m+s.aWm;                   // :441-442
+      const double us=r.u0+s.um;
+      double a=.125*(r.qa+r.qaW)*s.dtx*us;                     // :428-429
+      a=a-s.ddxs(.25*a4*s.hx*(r.qab-r.qabW)*s.dumc);           // :440-445
+      v[XA]=s.hdy*a;                                           // :452
+      double b=.125*(r.qb+r.qbW)*s.dtx*us;
+      b=b-s.ddxs(.25*a4*s.hx*(r.qbb-r.qbbW)*s.dumc);
+      v[XB]=s.hdy*b;
+      s.um=r.u0; s.aWm=r.aW;
+    }
+    if (s.fya) {
+      const double a4=r.a0+r.aS+s.a0m+s.aSm;                   // :447-448
+      const double vs=r.v0+s.vm;
+      double a=.125*(r.qa+r.qaS)*s.dty*vs;                     // :430-431
+      a=a-s.ddys(.25*a4*s.hy*(r.qab-r.qabS)*s.dvmc);           // :446-451
+      v[YA]=s.hdx*a;                                           // :453
+      double b=.125*(r.qb+r.qbS)*s.dty*vs;
+      b=b-s.ddys(.25*a4*s.hy*(r.qbb-r.qbbS)*s.dvmc);
+      v[YB]=s.hdx*b;
+      s.vm=r.v0; s.aSm=r.aS;
+    }
+    s.a0m=r.a0;
+  }
+  POM_HD void combine(int i, int j, int k, State& s, const Regs& r, const Tile& tl) const {
+    double a = 0., b = 0.;
+    if (s.interior) {
+      const double dzk=dz(k)+dz(k-1);
+      double ra=(s.wm*s.qam-r.w1*r.qa1)*s.ar/dzk
+                +tl(XA,1,0)-tl(XA,0,0)+tl(YA,0,1)-tl(YA,0,0);  // :465-468
+      a=s.dhf(s.hb*r.qab-dti2*ra);                             // :469-471
+      double rb=(s.wm*s.qbm-r.w1*r.qb1)*s.ar/dzk
+                +tl(XB,1,0)-tl(XB,0,0)+tl(YB,0,1)-tl(YB,0,0);
+      b=s.dhf(s.hb*r.qbb-dti2*rb);
+      s.wm=s.w0; s.w0=r.w1;
+      s.qam=s.qa0; s.qbm=s.qb0; s.qa0=r.qa1; s.qb0=r.qb1;
+    }
+    uf(i,j,k)=a;
+    vf(i,j,k)=b;
+  }
+  POM_HD void post(int, int, State&) const {}
 };
 
 // ---------------------------------------------------------------------------
@@ -121,13 +183,21 @@ struct ProfqK : KBase {
     cgg = pow((double)15.8f * cbcnst, (double)(2.f / 3.f));
     const1 = pow(16.6, 2. / 3.) * 1.;
   }
+  // One downward sweep per column computes, level by level, the speed of sound, buoyancy
+  // gradient, length scale, gh, production, the forward eliminations of BOTH tridiagonal
+  // systems and the km/kh/kq update (in place, old kq kept in rolling registers); two upward
+  // sweeps back-substitute.  Only the four ee/gg vectors live in per-thread memory.
   POM_HD void operator()(int i, int j) const {
     POM_DIMS;
     const double a1 = 0.92, b1 = 16.6, a2 = 0.74, b2 = 10.1, c1 = 0.08;     // :1241
     const double e1 = 1.8, e2 = 1.33, sef = 1., surfl = 2.e5, shiw = 0.;     // :1242-1244
-    double ee[KMAX], gg[KMAX], lk[KMAX], ghk[KMAX], prk[KMAX], dtk[KMAX];
+    const double coef4=18.*a1*a1+9.*a1*a2, coef5=9.*a1*a2;                   // :1474-1475
+    const double coef1=a2*(1.-6.*a1/b1*1.);                                  // :1481-1483 (stf=1)
+    const double coef2=3.*a2*b2/1.+18.*a1*a2;
+    const double coef3=a1*(1.-3.*c1-6.*a1/b1*1.);
     const bool interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
-    const double dh=h(i,j)+etf(i,j);                                          // :1248
+    const double hh=h(i,j);
+    const double dh=hh+etf(i,j);                                              // :1248
     double utau2 = 0.;
     if (i <= imm1 && j <= jmm1) {                                             // :1281-1288
       double su=.5*(wusurf(i,j)+wusurf(i+1,j)), sv=.5*(wvsurf(i,j)+wvsurf(i,j+1));
@@ -136,121 +206,162 @@ struct ProfqK : KBase {
       uf(i,j,kb)=sqrt(bu*bu+bv*bv)*const1;
     }
     const double l0=surfl*utau2/grav;                                         // :1299
-    ee[1]=0.;                                                                 // :1296
-    gg[1]=cgg*utau2;                                                          // :1297
-    // speed of sound squared (:1304-1319), buoyancy gradient (:1322-1333),
-    // length scale and gh (:1335-1356), production (:1359-1373)
-    lk[1]=kappa*l0; lk[kb]=0.; ghk[1]=0.; ghk[kb]=0.;
-    double ccm = 0.;  // cc(k-1)
+    const double kl0=kappa*l0;
+    l(i,j,1)=kl0; l(i,j,kb)=0.;                                               // :1351-1352
+    if (!interior) {
+      // boundary columns: only l is kept; the reference's solves there are overwritten by
+      // bcond(6) (advance.f:414) and km,kh,kq by the copies of :1510-1529
+      for (int k = 2; k <= kbm1; ++k) {
+        double qb=fabs(q2b(i,j,k)), qlb=fabs(q2lb(i,j,k));
+        q2b(i,j,k)=qb; q2lb(i,j,k)=qlb;                                       // :1325-1326
+        double ll=fabs(qlb/qb);
+        if (z(k) > -0.5) ll=fmax(ll,kl0);
+        l(i,j,k)=ll;
+      }
+      return;
+    }
+    double ee[KMAX], gg[KMAX], e2v[KMAX], g2v[KMAX];
+    const int il = (i == 2) ? 1 : 0, ir = (i == imm1) ? 1 : 0;
+    const int jl = (j == 2) ? 1 : 0, jr = (j == jmm1) ? 1 : 0;
+    const double m = fsm(i,j);
+    // new km,kh,kq of one level: own cell masked; boundary neighbours get the unmasked value
+    // times their own mask (N,S,E,W copies of :1510-1529 = index clamped into the interior)
+#define POM_PUT_K(k, nkq, nkm, nkh)                                             \
+    do {                                                                        \
+      kq(i,j,k)=(nkq)*m; km(i,j,k)=(nkm)*m; kh(i,j,k)=(nkh)*m;                  \
+      if (il | ir | jl | jr)                                                    \
+        for (int dj = -jl; dj <= jr; ++dj)                                      \
+          for (int di = -il; di <= ir; ++di) {                                  \
+            if (di == 0 && dj == 0) continue;                                   \
+            const double me = fsm(i+di,j+dj);                                   \
+            kq(i+di,j+dj,k)=(nkq)*me; km(i+di,j+dj,k)=(nkm)*me; kh(i+di,j+dj,k)=(nkh)*me; \
+          }                                                                     \
+    } while (0)
+    // ---- level 1 ----
+    double ccm;                                                               // cc(k-1) (:1304-1319)
     {
       double tp=t(i,j,1)+tbias, sp=s(i,j,1)+sbias;
-      double pp=grav*rhoref*(-zz(1)*h(i,j))*1.e-4;
+      double pp=grav*rhoref*(-zz(1)*hh)*1.e-4;
       double cv=1449.1+.00821*pp+4.55*tp-.045*(tp*tp)+1.34*(sp-35.0);
       ccm=cv/sqrt((1.-.01642*pp/cv)*(1.-0.40*pp/(cv*cv)));
     }
+    double kqm=kq(i,j,1), kq0=kq(i,j,2);                                      // old kq(k-1), kq(k)
+    {
+      // gh(1)=0 (:1353): sh=coef1, sm=coef3 (:1484-1486 with gh=0)
+      double sh=coef1/(1.-coef2*0.);
+      double sm=coef3+sh*coef4*0.;
+      sm=sm/(1.-coef5*0.);
+      double pr=kl0*sqrt(fabs(q2(i,j,1)));                                    // :1499
+      const double nq=(pr*.41*sh+kqm)*.5, nm=(pr*sm+km(i,j,1))*.5, nh=(pr*sh+kh(i,j,1))*.5;   // :1500-1503
+      POM_PUT_K(1, nq, nm, nh);
+    }
+    double rhom=rho(i,j,1);
+    double um=u(i,j,1), uEm=u(i+1,j,1), vm=v(i,j,1), vNm=v(i,j+1,1);
+    double eem = 0., ggm = cgg*utau2;                                         // ee(1), gg(1) :1296-1297
+    double e2m = 0., g2m = 0.;
+    ee[1]=eem; gg[1]=ggm;
+    const double q2_2=q2(i,j,2);
+    // ---- levels 2..kbm1 ----
     for (int k = 2; k <= kbm1; ++k) {
+      {   // prefetch the operands of level k+1 (kq: k+2)
+        const int o = POM_I3(i,j,k+1);
+        POM_PREFETCH(p.t+o); POM_PREFETCH(p.s+o); POM_PREFETCH(p.q2b+o); POM_PREFETCH(p.q2lb+o);
+        POM_PREFETCH(p.rho+o); POM_PREFETCH(p.u+o); POM_PREFETCH(p.v+o); POM_PREFETCH(p.v+o+g.im);
+        POM_PREFETCH(p.km+o); POM_PREFETCH(p.kh+o); POM_PREFETCH(p.uf+o); POM_PREFETCH(p.vf+o);
+        POM_PREFETCH(p.q2+o);
+        if (k + 2 <= kb) POM_PREFETCH(p.kq+o+g.n2);
+      }
       double tp=t(i,j,k)+tbias, sp=s(i,j,k)+sbias;
-      double pp=grav*rhoref*(-zz(k)*h(i,j))*1.e-4;
+      double pp=grav*rhoref*(-zz(k)*hh)*1.e-4;
       double cv=1449.1+.00821*pp+4.55*tp-.045*(tp*tp)+1.34*(sp-35.0);
       double cck=cv/sqrt((1.-.01642*pp/cv)*(1.-0.40*pp/(cv*cv)));
       double qb=fabs(q2b(i,j,k)), qlb=fabs(q2lb(i,j,k));
       q2b(i,j,k)=qb;                                                          // :1325-1326
       q2lb(i,j,k)=qlb;
-      double boygr=grav*(rho(i,j,k-1)-rho(i,j,k))/(dzz(k-1)*h(i,j))
+      const double rhok=rho(i,j,k);
+      double boygr=grav*(rhom-rhok)/(dzz(k-1)*hh)
                    +(grav*grav)*2./(ccm*ccm+cck*cck);                         // :1327-1330
-      ccm=cck;
+      ccm=cck; rhom=rhok;
       double ll=fabs(qlb/qb);                                                 // :1338
-      if (z(k) > -0.5) ll=fmax(ll,kappa*l0);                                  // :1339
+      if (z(k) > -0.5) ll=fmax(ll,kl0);                                       // :1339
       double gh=(ll*ll)*boygr/qb;                                             // :1343
       gh=fmin(gh,.028);                                                       // :1344
-      lk[k]=ll; ghk[k]=gh;
-      double pr = 0.;
-      if (interior) {
-        double su=u(i,j,k)-u(i,j,k-1)+u(i+1,j,k)-u(i+1,j,k-1);
-        double sv=v(i,j,k)-v(i,j,k-1)+v(i,j+1,k)-v(i,j+1,k-1);
+      l(i,j,k)=ll;
+      const double u0=u(i,j,k), uE=u(i+1,j,k), v0=v(i,j,k), vN=v(i,j+1,k);
+      const double kmk=km(i,j,k), khk=kh(i,j,k);
+      double pr;
+      {
+        double su=u0-um+uE-uEm;
+        double sv=v0-vm+vN-vNm;
         double dd=dzz(k-1)*dh;
-        pr=km(i,j,k)*.25*sef*(su*su+sv*sv)/(dd*dd)-shiw*km(i,j,k)*boygr;      // :1362-1369
-        pr=pr+kh(i,j,k)*boygr;                                                // :1370
+        pr=kmk*.25*sef*(su*su+sv*sv)/(dd*dd)-shiw*kmk*boygr;                  // :1362-1369
+        pr=pr+khk*boygr;                                                      // :1370
       }
-      prk[k]=pr;
-    }
-    // :1380-1392 dtef for k=1..kb (stf=1)
-    for (int k = 1; k <= kb; ++k)
-      dtk[k]=sqrt(fabs(q2b(i,j,k)))*1./(b1*lk[k]+small);
-    // Boundary columns: the reference solves them too, but bcond(6) overwrites uf,vf there
-    // right after (advance.f:414), so the solves are skipped on those columns.
-    if (interior) {
-    // q2 solve (:1258-1267 a,c; :1394-1413)
-      for (int k = 2; k <= kbm1; ++k) {
-        double a=-dti2*(kq(i,j,k+1)+kq(i,j,k)+2.*umol)*.5/(dzz(k-1)*dz(k)*dh*dh);
-        double cq=-dti2*(kq(i,j,k-1)+kq(i,j,k)+2.*umol)*.5/(dzz(k-1)*dz(k-1)*dh*dh);
-        double gi=1./(a+cq*(1.-ee[k-1])-(2.*dti2*dtk[k]+1.));
-        ee[k]=a*gi;
-        gg[k]=(-2.*dti2*prk[k]+cq*gg[k-1]-uf(i,j,k))*gi;
-      }
+      um=u0; uEm=uE; vm=v0; vNm=vN;
+      double dtf=sqrt(fabs(qb))*1./(b1*ll+small);                             // :1388-1389 (stf=1)
+      // tridiagonal coefficients from the OLD kq (:1258-1267)
+      const double kqp=kq(i,j,k+1);
+      const double a=-dti2*(kqp+kq0+2.*umol)*.5/(dzz(k-1)*dz(k)*dh*dh);
+      const double cq=-dti2*(kqm+kq0+2.*umol)*.5/(dzz(k-1)*dz(k-1)*dh*dh);
+      // q2 forward elimination (:1394-1404)
       {
-        double up=uf(i,j,kb);
-        for (int ki = kbm1; ki >= 1; --ki) {
-          up=ee[ki]*up+gg[ki];
-          uf(i,j,ki)=(ki >= 2) ? fabs(up) : up;                                 // :1410, :1467
-        }
+        double gi=1./(a+cq*(1.-eem)-(2.*dti2*dtf+1.));
+        eem=a*gi;
+        ggm=(-2.*dti2*pr+cq*ggm-uf(i,j,k))*gi;
+        ee[k]=eem; gg[k]=ggm;
       }
-      // q2l solve (:1417-1455)
-      ee[2]=0.;
-      gg[2]=-kappa*z(2)*dh*q2(i,j,2);
-      for (int k = 2; k <= kbm1; ++k) {                                         // :1426-1435
-        double r=(1./fabs(z(k)-z(1))+1./fabs(z(k)-z(kb)))*lk[k]/(dh*kappa);
-        dtk[k]=dtk[k]*(1.+e2*(r*r));
-      }
-      for (int k = 3; k <= kbm1; ++k) {
-        double a=-dti2*(kq(i,j,k+1)+kq(i,j,k)+2.*umol)*.5/(dzz(k-1)*dz(k)*dh*dh);
-        double cq=-dti2*(kq(i,j,k-1)+kq(i,j,k)+2.*umol)*.5/(dzz(k-1)*dz(k-1)*dh*dh);
-        double gi=1./(a+cq*(1.-ee[k-1])-(dti2*dtk[k]+1.));
-        ee[k]=a*gi;
-        // :1423 assigns vf(kbm1)=kappa*(1+z(kbm1))*dh*q2(kbm1) before this sweep reads it
-        double vk=(k == kbm1) ? kappa*(1+z(kbm1))*dh*q2(i,j,kbm1) : vf(i,j,k);
-        gg[k]=(dti2*(-prk[k]*lk[k]*e1)+cq*gg[k-1]-vk)*gi;
-      }
+      // q2l forward elimination (:1417-1446)
       {
-        double vp = 0.;                                                         // vf(kb)=0 (:1420)
-        vf(i,j,kb)=0.;
-        for (int ki = kbm1; ki >= 2; --ki) {
-          vp=ee[ki]*vp+gg[ki];
-          vf(i,j,ki)=fabs(vp);                                                  // :1452, :1468
+        double r=(1./fabs(z(k)-z(1))+1./fabs(z(k)-z(kb)))*ll/(dh*kappa);
+        double dtf2=dtf*(1.+e2*(r*r));                                        // :1429-1432
+        if (k == 2) {
+          e2m=0.;                                                             // :1421
+          g2m=-kappa*z(2)*dh*q2_2;                                            // :1422
+        } else {
+          // :1423 assigns vf(kbm1)=kappa*(1+z(kbm1))*dh*q2(kbm1) before this sweep reads it
+          double vk=(k == kbm1) ? kappa*(1+z(kbm1))*dh*q2(i,j,kbm1) : vf(i,j,k);
+          double gi=1./(a+cq*(1.-e2m)-(dti2*dtf2+1.));
+          e2m=a*gi;
+          g2m=(dti2*(-pr*ll*e1)+cq*g2m-vk)*gi;
         }
-        vf(i,j,1)=0.;                                                           // :1419
+        e2v[k]=e2m; g2v[k]=g2m;
       }
+      // km, kh, kq (:1478-1506) -- in place; kq's old value stays in kqm for level k+1
+      {
+        double sh=coef1/(1.-coef2*gh);
+        double sm=coef3+sh*coef4*gh;
+        sm=sm/(1.-coef5*gh);
+        double pq=ll*sqrt(fabs(q2(i,j,k)));
+        const double nq=(pq*.41*sh+kq0)*.5, nm=(pq*sm+kmk)*.5, nh=(pq*sh+khk)*.5;
+        POM_PUT_K(k, nq, nm, nh);
+      }
+      kqm=kq0; kq0=kqp;
     }
-    // note: the Thomas recurrences above use the signed iterate (up, vp); abs() is
-    // applied by the reference only after both back-substitutions (:1460-1471)
-    // km, kh, kq (:1474-1506), cosmetics (:1510-1529) and mask (:1531-1535)
-    const double coef4=18.*a1*a1+9.*a1*a2, coef5=9.*a1*a2;
-    const double coef1=a2*(1.-6.*a1/b1*1.);
-    const double coef2=3.*a2*b2/1.+18.*a1*a2;
-    const double coef3=a1*(1.-3.*c1-6.*a1/b1*1.);
-    const double m = fsm(i,j);
-    for (int k = 1; k <= kb; ++k) {
-      l(i,j,k)=lk[k];
-      double sh=coef1/(1.-coef2*ghk[k]);
-      double sm=coef3+sh*coef4*ghk[k];
-      sm=sm/(1.-coef5*ghk[k]);
-      double pr=lk[k]*sqrt(fabs(q2(i,j,k)));
-      double nkq=(pr*.41*sh+kq(i,j,k))*.5;
-      double nkm=(pr*sm+km(i,j,k))*.5;
-      double nkh=(pr*sh+kh(i,j,k))*.5;
-      if (interior) {
-        kq(i,j,k)=nkq*m; km(i,j,k)=nkm*m; kh(i,j,k)=nkh*m;
-        // boundary columns copy the neighbouring interior value (N,S,E,W order =
-        // index clamped into the interior), then take their own mask
-        const int il = (i == 2) ? 1 : 0, ir = (i == imm1) ? 1 : 0;
-        const int jl = (j == 2) ? 1 : 0, jr = (j == jmm1) ? 1 : 0;
-        for (int dj = -jl; dj <= jr; ++dj)
-          for (int di = -il; di <= ir; ++di) {
-            if (di == 0 && dj == 0) continue;
-            const double me = fsm(i+di,j+dj);
-            kq(i+di,j+dj,k)=nkq*me; km(i+di,j+dj,k)=nkm*me; kh(i+di,j+dj,k)=nkh*me;
-          }
+    // ---- level kb: l=0, gh=0 ----
+    {
+      double sh=coef1/(1.-coef2*0.);
+      double sm=coef3+sh*coef4*0.;
+      sm=sm/(1.-coef5*0.);
+      double pq=0.*sqrt(fabs(q2(i,j,kb)));
+      const double nq=(pq*.41*sh+kq0)*.5, nm=(pq*sm+km(i,j,kb))*.5, nh=(pq*sh+kh(i,j,kb))*.5;
+      POM_PUT_K(kb, nq, nm, nh);
+    }
+#undef POM_PUT_K
+    // ---- back-substitutions (:1406-1413, :1448-1455) and abs (:1460-1471) ----
+    // the recurrences use the signed iterate; abs() is applied by the reference afterwards
+    {
+      double up=uf(i,j,kb);
+      for (int ki = kbm1; ki >= 1; --ki) {
+        up=ee[ki]*up+gg[ki];
+        uf(i,j,ki)=(ki >= 2) ? fabs(up) : up;
       }
+      double vp = 0.;                                                         // vf(kb)=0 (:1420)
+      vf(i,j,kb)=0.;
+      for (int ki = kbm1; ki >= 2; --ki) {
+        vp=e2v[ki]*vp+g2v[ki];
+        vf(i,j,ki)=fabs(vp);
+      }
+      vf(i,j,1)=0.;                                                           // :1419
     }
   }
 };
@@ -296,58 +407,99 @@ struct QFilterK : KBase {
 
 // ---------------------------------------------------------------------------
 // advt2 with nitera=1 (solver.f:577-731 + the fsm mask of smol_adif :1898-1900):
-// upstream advection, leapfrog update, horizontal diffusion of (fb-fclim).
+// upstream advection, leapfrog update, horizontal diffusion of (fb-fclim); tile kernel:
+// every thread evaluates the upwind and the diffusive x/y fluxes of its own point once.
 struct AdvT2K : KBase {
   POM_KINFO("advt2", 6, 1, 10, 0)
   const double *fb_, *f_, *fc_;
   double* ff_;
   AdvT2K(const Ctx* x, const double* fb, const double* f, const double* fc, double* ff)
       : KBase(x), fb_(fb), f_(f), fc_(fc), ff_(ff) {}
-  POM_HD double xfl(int i, int j, int k) const {                        // :605-606, :631-635
-    double xm=0.25*(dy(i-1,j)+dy(i,j))*(dt(i-1,j)+dt(i,j))*u(i,j,k);
-    return 0.5*((xm+fabs(xm))*A3(fb_,i-1,j,k)+(xm-fabs(xm))*A3(fb_,i,j,k));
-  }
-  POM_HD double yfl(int i, int j, int k) const {                        // :612-613, :637-641
-    double ym=0.25*(dx(i,j-1)+dx(i,j))*(dt(i,j-1)+dt(i,j))*v(i,j,k);
-    return 0.5*((ym+fabs(ym))*A3(fb_,i,j-1,k)+(ym-fabs(ym))*A3(fb_,i,j,k));
-  }
-  POM_HD double fbd(int i, int j, int k) const { return A3(fb_,i,j,k)-A3(fc_,i,j,k); }   // :691
-  POM_HD double xdf(int i, int j, int k) const {                        // :696, :705-707
-    double xm=0.5*(aam(i,j,k)+aam(i-1,j,k));
-    return -xm*(h(i,j)+h(i-1,j))*tprni*(fbd(i,j,k)-fbd(i-1,j,k))*dum(i,j)
-           *(dy(i,j)+dy(i-1,j))*0.5/(dx(i,j)+dx(i-1,j));
-  }
-  POM_HD double ydf(int i, int j, int k) const {                        // :697, :708-710
-    double ym=0.5*(aam(i,j,k)+aam(i,j-1,k));
-    return -ym*(h(i,j)+h(i,j-1))*tprni*(fbd(i,j,k)-fbd(i,j-1,k))*dvm(i,j)
-           *(dx(i,j)+dx(i,j-1))*0.5/(dy(i,j)+dy(i,j-1));
-  }
-  POM_HD void operator()(int i, int j) const {
+  static constexpr int NV = 4, HL = 0, HR = 1, HB = 0, HT = 1, TY = 16, MINB = 1;
+  enum { XF, YF, XD, YD };
+  struct State {
+    double cx, cy, hx, hy, dumc, dvmc, dys, dxs;   // .25*(dy+dy)*(dt+dt), (h+h), masks, (dy+dy(i-1)), (dx+dx(j-1))
+    RDiv ddxs, ddys, def;                          // (dx+dx(i-1)), (dy+dy(j-1)), (h+etf)*art
+    double eb, ar, m, zk;                          // (h+etb)*art, art, fsm, zflux(k)
+    bool fxa, fya, interior;
+  };
+  struct Regs { double fb0, fbW, fbS, fc0, fcW, fcS, u0, v0, a0, aW, aS, w1, fb1; };
+  POM_HD int k0() const { return 1; }
+  POM_HD int k1() const { return g.kb - 1; }
+  POM_HD void pre(int i, int j, bool inside, bool out, State& s) const {
     POM_DIMS;
-    if (!(i >= 2 && i <= imm1 && j >= 2 && j <= jmm1)) {
-      // ff is not assigned here by the reference; bcond(4) sets it afterwards
-      for (int k = 1; k <= kb; ++k) A3(ff_,i,j,k)=A3(ff_,i,j,k)*fsm(i,j);
+    const int jlo = g.joff + 1;
+    s.fxa = inside && i >= 2 && j >= 2 && j <= jmm1;                    // xmassflux range :603-608
+    s.fya = inside && i >= 2 && i <= imm1 && j >= 2 && j - 1 >= jlo;    // ymassflux range :610-615
+    s.interior = out && i >= 2 && i <= imm1 && j >= 2 && j <= jmm1;
+    s.m = out ? fsm(i,j) : 0.;
+    if (s.fxa) {
+      s.cx = 0.25*(dy(i-1,j)+dy(i,j))*(dt(i-1,j)+dt(i,j));              // :605-606
+      s.hx = h(i,j)+h(i-1,j); s.dumc = dum(i,j); s.dys = dy(i,j)+dy(i-1,j);
+      s.ddxs.set(dx(i,j)+dx(i-1,j));
+    }
+    if (s.fya) {
+      s.cy = 0.25*(dx(i,j-1)+dx(i,j))*(dt(i,j-1)+dt(i,j));              // :612-613
+      s.hy = h(i,j)+h(i,j-1); s.dvmc = dvm(i,j); s.dxs = dx(i,j)+dx(i,j-1);
+      s.ddys.set(dy(i,j)+dy(i,j-1));
+    }
+    if (s.interior) {
+      s.ar = art(i,j);
+      s.eb = (h(i,j)+etb(i,j))*s.ar;
+      s.def.set((h(i,j)+etf(i,j))*s.ar);
+      s.zk = w(i,j,1)*A3(f_,i,j,1)*s.ar;                                // :648 (itera==1)
+    }
+  }
+  POM_HD void fetch(int i, int j, int k, const State& s, Regs& r) const {
+    if (!(s.fxa || s.fya || s.interior)) return;
+    const int o = POM_I3(i,j,k), im = g.im;
+    r.fb0 = POM_LDG(fb_+o); r.fc0 = POM_LDG(fc_+o); r.a0 = POM_LDG(p.aam+o);
+    if (k + 1 <= g.kb - 1) {
+      const int n = o + g.n2;
+      POM_PREFETCH(fb_+n); POM_PREFETCH(fc_+n); POM_PREFETCH(p.aam+n); POM_PREFETCH(p.u+n); POM_PREFETCH(p.v+n);
+      POM_PREFETCH(p.w+n);
+    }
+    if (s.fxa) { r.fbW = POM_LDG(fb_+o-1); r.fcW = POM_LDG(fc_+o-1); r.aW = POM_LDG(p.aam+o-1); r.u0 = POM_LDG(p.u+o); }
+    if (s.fya) { r.fbS = POM_LDG(fb_+o-im); r.fcS = POM_LDG(fc_+o-im); r.aS = POM_LDG(p.aam+o-im); r.v0 = POM_LDG(p.v+o); }
+    if (s.interior && k + 1 <= g.kb - 1) { r.w1 = POM_LDG(p.w+o+g.n2); r.fb1 = POM_LDG(fb_+o+g.n2); }
+  }
+  POM_HD void stage(int i, int j, int k, State& s, const Regs& r, double* v) const {
+    const double fd0=r.fb0-r.fc0;                                       // fb-fclim (:691)
+    if (s.fxa) {
+      const double xm=s.cx*r.u0;                                        // :605-606
+      v[XF]=0.5*((xm+fabs(xm))*r.fbW+(xm-fabs(xm))*r.fb0);              // :631-635
+      const double xd=0.5*(r.a0+r.aW);                                  // :696
+      v[XD]=s.ddxs(-xd*s.hx*tprni*(fd0-(r.fbW-r.fcW))*s.dumc*s.dys*0.5);   // :705-707
+    }
+    if (s.fya) {
+      const double ym=s.cy*r.v0;                                        // :612-613
+      v[YF]=0.5*((ym+fabs(ym))*r.fbS+(ym-fabs(ym))*r.fb0);              // :637-641
+      const double yd=0.5*(r.a0+r.aS);                                  // :697
+      v[YD]=s.ddys(-yd*s.hy*tprni*(fd0-(r.fbS-r.fcS))*s.dvmc*s.dxs*0.5);   // :708-710
+    }
+  }
+  POM_HD void combine(int i, int j, int k, State& s, const Regs& r, const Tile& tl) const {
+    if (!s.interior) {
+      // ff is not assigned here by the reference (bcond(4) sets it afterwards); only the
+      // smol_adif mask applies
+      A3(ff_,i,j,k)=A3(ff_,i,j,k)*s.m;
       return;
     }
-    const double m=fsm(i,j);
-    A3(ff_,i,j,kb)=A3(ff_,i,j,kb)*m;
-    const double ar=art(i,j);
-    const double eb=(h(i,j)+etb(i,j))*ar, ef=(h(i,j)+etf(i,j))*ar;
-    double zk=w(i,j,1)*A3(f_,i,j,1)*ar;                                 // :648 (itera==1)
-    for (int k = 1; k <= kbm1; ++k) {
-      double zk1 = 0.;                                                  // zflux(k+1); :651 at kb
-      if (k + 1 <= kbm1) {
-        double zw=w(i,j,k+1);
-        zk1=0.5*((zw+fabs(zw))*A3(fb_,i,j,k+1)+(zw-fabs(zw))*A3(fb_,i,j,k));   // :656-660
-        zk1=zk1*ar;                                                     // :661
-      }
-      double r=xfl(i+1,j,k)-xfl(i,j,k)+yfl(i,j+1,k)-yfl(i,j,k)+(zk-zk1)/dz(k);   // :670-672
-      r=(A3(fb_,i,j,k)*eb-dti2*r)/ef;                                   // :673-674
-      r=r*m;                                                            // smol_adif :1899
-      r=r-dti2*(xdf(i+1,j,k)-xdf(i,j,k)+ydf(i,j+1,k)-ydf(i,j,k))/ef;    // :721-723
-      A3(ff_,i,j,k)=r;
-      zk=zk1;
+    double zk1 = 0.;                                                    // zflux(k+1); :651 at kb
+    if (k + 1 <= g.kb - 1) {
+      zk1=0.5*((r.w1+fabs(r.w1))*r.fb1+(r.w1-fabs(r.w1))*r.fb0);        // :656-660
+      zk1=zk1*s.ar;                                                     // :661
     }
+    double q=tl(XF,1,0)-tl(XF,0,0)+tl(YF,0,1)-tl(YF,0,0)+(s.zk-zk1)/dz(k);   // :670-672
+    q=s.def(r.fb0*s.eb-dti2*q);                                         // :673-674
+    q=q*s.m;                                                            // smol_adif :1899
+    q=q-s.def(dti2*(tl(XD,1,0)-tl(XD,0,0)+tl(YD,0,1)-tl(YD,0,0)));      // :721-723
+    A3(ff_,i,j,k)=q;
+    s.zk=zk1;
+  }
+  POM_HD void post(int i, int j, State& s) const {
+    const int kb = g.kb;
+    A3(ff_,i,j,kb)=A3(ff_,i,j,kb)*s.m;                                  // smol_adif mask, level kb
   }
 };
 
@@ -428,6 +580,7 @@ struct ProftK : KBase {
       ee[1]=0.; gg[1]=0.;
     }
     for (int k = 2; k <= kbm2; ++k) {                                   // :1650-1661
+      PF3(p.kh,i,j,k+3); PF3(f_,i,j,k+2);
       ak=-dti2*(kh(i,j,k+1)+umol)/(dz(k)*dzz(k)*dh*dh);                 // a(k)
       double ck=-dti2*(kh(i,j,k)+umol)/(dz(k)*dzz(k-1)*dh*dh);          // c(k)
       double gi=1./(ak+ck*(1.-ee[k-1])-1.);
@@ -573,6 +726,7 @@ struct DensK : KBase {
     POM_DIMS;
     const double m=fsm(i,j), hh=h(i,j);
     for (int k = 1; k <= kbm1; ++k) {
+      PF3(ti_,i,j,k+2); PF3(si_,i,j,k+2);
       double tr=A3(ti_,i,j,k)+tbias;
       double sr=A3(si_,i,j,k)+sbias;
       double tr2=tr*tr, tr3=tr2*tr, tr4=tr3*tr;
@@ -609,6 +763,8 @@ struct AdvuK : KBase {
       const double hf=(h(i,j)+etf(i,j)+h(i-1,j)+etf(i-1,j))*ar;
       double fk = 0.;                                                   // uf(i,j,1)=0 (:742)
       for (int k = 1; k <= kbm1; ++k) {
+        PF3(p.w,i,j,k+3); PF3(p.u,i,j,k+3); PF3(p.v,i,j,k+2); PF3(p.v,i,j+1,k+2);
+        PF3(p.advx,i,j,k+2); PF3(p.drhox,i,j,k+2); PF3(p.ub,i,j,k+2);
         double fk1 = (k + 1 <= kbm1) ? vfl(i,j,k+1) : 0.;
         double r=advx(i,j,k)+(fk-fk1)*ar/dz(k)
                  -ar*.25*(cor(i,j)*dt(i,j)*(v(i,j+1,k)+v(i,j,k))
@@ -644,6 +800,8 @@ struct AdvvK : KBase {
       const double hf=(h(i,j)+etf(i,j)+h(i,j-1)+etf(i,j-1))*ar;
       double fk = 0.;
       for (int k = 1; k <= kbm1; ++k) {
+        PF3(p.w,i,j,k+3); PF3(p.w,i,j-1,k+3); PF3(p.v,i,j,k+3); PF3(p.u,i,j,k+2); PF3(p.u,i,j-1,k+2);
+        PF3(p.advy,i,j,k+2); PF3(p.drhoy,i,j,k+2); PF3(p.vb,i,j,k+2);
         double fk1 = (k + 1 <= kbm1) ? vfl(i,j,k+1) : 0.;
         double r=advy(i,j,k)+(fk-fk1)*ar/dz(k)
                  +ar*.25*(cor(i,j)*dt(i,j)*(u(i+1,j,k)+u(i,j,k))
@@ -676,6 +834,7 @@ struct ProfuK : KBase {
     gg[1]=(-dti2*wusurf(i,j)/(-dz(1)*dh)-uf(i,j,1))/(ak-1.);            // :1734-1736
     double ck=-dti2*(cn+umol)/(dz(2)*dzz(1)*dh*dh);                     // c(2) (:1725)
     for (int k = 2; k <= kbm2; ++k) {                                   // :1740-1748
+      PF3(p.km,i,j,k+3); PF3(p.uf,i,j,k+2);
       cn=(km(i,j,k+1)+km(i-1,j,k+1))*.5;
       ak=-dti2*(cn+umol)/(dz(k)*dzz(k)*dh*dh);                          // a(k)
       double gi=1./(ak+ck*(1.-ee[k-1])-1.);
@@ -714,6 +873,7 @@ struct ProfvK : KBase {
     gg[1]=(-dti2*wvsurf(i,j)/(-dz(1)*dh)-vf(i,j,1))/(ak-1.);            // :1832-1833
     double ck=-dti2*(cn+umol)/(dz(2)*dzz(1)*dh*dh);                     // :1823
     for (int k = 2; k <= kbm2; ++k) {                                   // :1837-1845
+      PF3(p.km,i,j,k+3); PF3(p.km,i,j-1,k+3); PF3(p.vf,i,j,k+2);
       cn=(km(i,j,k+1)+km(i,j-1,k+1))*.5;
       ak=-dti2*(cn+umol)/(dz(k)*dzz(k)*dh*dh);
       double gi=1./(ak+ck*(1.-ee[k-1])-1.);
@@ -762,6 +922,7 @@ struct UvFilterK : KBase {
     double su = 0., sv = 0.;
     double nu[KMAX], nv[KMAX];
     for (int k = 1; k <= kbm1; ++k) {
+      PF3(p.uf,i,j,k+2); PF3(p.vf,i,j,k+2); PF3(p.ub,i,j,k+2); PF3(p.vb,i,j,k+2); PF3(p.u,i,j,k+2); PF3(p.v,i,j,k+2);
       double a=uf(i,j,k), b=vf(i,j,k);
       if (jin) {
         if (i == im) {                                                  // east (:425-434)
@@ -841,7 +1002,10 @@ struct RealvertvlK : KBase {
     int ic = i < 2 ? 2 : (i > imm1 ? imm1 : i);
     int jc = j < 2 ? 2 : (j > jmm1 ? jmm1 : j);
     const double m=fsm(i,j);
-    for (int k = 1; k <= kbm1; ++k) wr(i,j,k)=m*wri(ic,jc,k);           // :2063
+    for (int k = 1; k <= kbm1; ++k) {
+      PF3(p.w,ic,jc,k+3); PF3(p.u,ic,jc,k+2); PF3(p.v,ic,jc,k+2); PF3(p.v,ic,jc+1,k+2);
+      wr(i,j,k)=m*wri(ic,jc,k);                                         // :2063
+    }
     wr(i,j,kb)=0.;
   }
 };
@@ -865,7 +1029,7 @@ struct FbRoundTripK : KBase {
 #define ALLI 1, c->g.im
 void run_uvadjust(Ctx* c, int j0, int j1) { launch_cols(c, UvAdjustK(c), ALLI, j0, j1); }
 void run_vertvl(Ctx* c, int j0, int j1) { launch_cols(c, VertvlK(c), ALLI, j0, j1); }
-void run_advq(Ctx* c, int j0, int j1) { launch_cols(c, AdvqK(c), ALLI, j0, j1); }
+void run_advq(Ctx* c, int j0, int j1) { launch_tiles(c, AdvqK(c), ALLI, j0, j1); }
 void run_profq(Ctx* c, int j0, int j1) { launch_cols(c, ProfqK(c), ALLI, j0, j1); }
 void run_qfilter(Ctx* c, int j0, int j1) {
   launch_cols(c, QFilterK(c), ALLI, j0, j1);
@@ -877,7 +1041,7 @@ void run_qfilter(Ctx* c, int j0, int j1) {
 }
 void run_advt(Ctx* c, int nadv, const double* fb, const double* f, const double* fc, double* ff, int j0, int j1) {
   if (nadv == 1) launch_cols(c, AdvT1K(c, fb, f, fc, ff), ALLI, j0, j1);
-  else launch_cols(c, AdvT2K(c, fb, f, fc, ff), ALLI, j0, j1);
+  else launch_tiles(c, AdvT2K(c, fb, f, fc, ff), ALLI, j0, j1);
 }
 void run_fb_roundtrip(Ctx* c, double* fb, const double* fc, double* f, int j0, int j1) {
   launch_cols(c, FbRoundTripK(c, fb, fc, f), ALLI, j0, j1);

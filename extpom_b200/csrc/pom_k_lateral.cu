@@ -72,6 +72,10 @@ struct AdvctK : KBase {
     const int o = POM_I3(i,j,k), im = g.im;
     r.u00 = POM_LDG(p.u+o); r.v00 = POM_LDG(p.v+o); r.ub00 = POM_LDG(p.ub+o); r.vb00 = POM_LDG(p.vb+o);
     r.a00 = POM_LDG(p.aam+o);
+    if (k + 1 <= g.kb - 1) {   // next level's lines into L1 (rows j, j-1, j+1 of this thread's i)
+      const int n = o + g.n2;
+      POM_PREFETCH(p.u+n); POM_PREFETCH(p.v+n); POM_PREFETCH(p.ub+n); POM_PREFETCH(p.vb+n); POM_PREFETCH(p.aam+n);
+    }
     if (s.fx || s.fyp) { r.uE = POM_LDG(p.u+o+1); r.ubE = POM_LDG(p.ub+o+1); }
     if (s.fyp) { r.vN = POM_LDG(p.v+o+im); r.vbN = POM_LDG(p.vb+o+im); }
     if (s.fy || s.fxp) {
@@ -104,7 +108,7 @@ struct AdvctK : KBase {
       v[CU]=cv*s.dtc*(uE+u00);                                            // :387-388
     }
   }
-  POM_HD void combine(int i, int j, int k, State& s, const Tile& tl) const {
+  POM_HD void combine(int i, int j, int k, State& s, const Regs&, const Tile& tl) const {
     double ax = 0., ay = 0.;
     if (s.interior) {
       ax=tl(X,0,0)-tl(X,-1,0)+tl(Y,0,1)-tl(Y,0,0);                            // :285-286
@@ -146,6 +150,7 @@ struct BaropgK : KBase {
       double px=.5*grav*(-zz(1))*dtx*(a0-ax);                          // :859-860
       double py=.5*grav*(-zz(1))*dty*(a0-ay);                          // :895-896
       for (int k = 1; k <= kbm1; ++k) {
+        PF3(p.rho,i,j,k+2); PF3(p.rmean,i,j,k+2); PF3(p.rho,i,j-1,k+2); PF3(p.rmean,i,j-1,k+2);
         if (k >= 2) {
           double b0=rho(i,j,k)-rmean(i,j,k);
           double bx=rho(i-1,j,k)-rmean(i-1,j,k);
@@ -188,7 +193,9 @@ struct SmagK : KBase {
     double sa = 0.;
     for (int k = 1; k <= kbm1; ++k) {
       double a;
+      PF3(p.u,i,j,k+2); PF3(p.v,i,j,k+2);
       if (interior) {
+        PF3(p.u,i,j+1,k+2); PF3(p.u,i,j-1,k+2); PF3(p.v,i,j+1,k+2);
         double a1=(u(i+1,j,k)-u(i,j,k))/dx(i,j);
         double a2=(v(i,j+1,k)-v(i,j,k))/dy(i,j);
         double a3=.25*(u(i,j+1,k)+u(i+1,j+1,k)-u(i,j-1,k)-u(i+1,j-1,k))/dy(i,j)
