@@ -1,0 +1,42 @@
+// pom_halo.h -- strip group: ghost-row validity tracking + halo exchange (see pom_halo.cu)
+#pragma once
+#include "pom_core.h"
+
+namespace pom {
+
+constexpr int HALO_MAXF = 16;   // fields per pack kernel launch
+
+struct NcclId { char internal[128]; };
+
+// host transport used by the CPU tests (gloo): exchange with the south / north neighbour
+// process; buffers are the strips' staging buffers (host memory in the emulation build)
+typedef int (*halo_cb)(void* user, const double* send_s, double* recv_s, long n_s,
+                       const double* send_n, double* recv_n, long n_n);
+
+struct Req { int f; int r; };   // field id, j-radius it is read with
+
+struct Group {
+  int n;                 // strips held by this process, south -> north
+  Ctx* c[16];
+  int ghost;
+  bool seams;            // any interior seam at all (false: single domain, no bookkeeping)
+  int valid[F_COUNT];    // valid ghost rows per field (identical on every seam by construction)
+  double* buf[16][4];    // staging: send south, send north, recv south, recv north
+  size_t bufcap[16][4];
+  void* nccl;            // ncclComm_t (one process per GPU)
+  int rank, world;
+  halo_cb cb; void* cb_user;
+  long n_exchanges, n_fields_exchanged;
+};
+
+Group* group_create(int n, Ctx** ctxs);
+void group_destroy(Group* G);
+int group_connect_nccl(Group* G, const void* id128, int rank, int world);
+void group_set_callback(Group* G, halo_cb cb, void* user);
+int nccl_unique_id(void* out128);
+int group_exchange(Group* G, const int* fields, int nf);
+int group_need(Group* G, const Req* in, int n);
+void group_produced(Group* G, int e, const int* out, int n);
+void group_swap(Group* G, int fa, int fb);
+
+}  // namespace pom

@@ -213,18 +213,8 @@ void run_advave(Ctx* c, int j0, int j1) { launch_tiles(c, AdvaveK(c), 1, c->g.im
 void run_mode_inter_tail(Ctx* c, int j0, int j1) { launch_cols(c, ModeInterTailK(c), 1, c->g.im, j0, j1); }
 void run_ext_elf(Ctx* c, int j0, int j1) { launch_cols(c, ExtElfK(c), 1, c->g.im, j0, j1); }
 
-// After the kernel: time rotation by pointer swaps (advance.f:324-330)
-void run_ext_uv(Ctx* c, int iext, int j0, int j1) {
-  launch_cols(c, ExtUvK(c, iext), 1, c->g.im, j0, j1);
-  Ptrs& p = c->p;
-  double* t;
-  // (uab,ua,uaf) <- (filtered[in uab], uaf, old ua as next uaf buffer)
-  t = p.ua; p.ua = p.uaf; p.uaf = t;
-  t = p.va; p.va = p.vaf; p.vaf = t;
-  // (elb,el,elf,el2) <- (el2[filtered], elf, old el, old elb)
-  t = p.elb; p.elb = p.el2; p.el2 = t;
-  t = p.el; p.el = p.elf; p.elf = t;
-  t = p.d; p.d = p.d2; p.d2 = t;
-}
+// The caller then rotates the time levels by pointer swaps (advance.f:324-330):
+// ua<->uaf, va<->vaf, elb<->el2, el<->elf, d<->d2
+void run_ext_uv(Ctx* c, int iext, int j0, int j1) { launch_cols(c, ExtUvK(c, iext), 1, c->g.im, j0, j1); }
 
 }  // namespace pom

@@ -1031,14 +1031,8 @@ void run_uvadjust(Ctx* c, int j0, int j1) { launch_cols(c, UvAdjustK(c), ALLI, j
 void run_vertvl(Ctx* c, int j0, int j1) { launch_cols(c, VertvlK(c), ALLI, j0, j1); }
 void run_advq(Ctx* c, int j0, int j1) { launch_tiles(c, AdvqK(c), ALLI, j0, j1); }
 void run_profq(Ctx* c, int j0, int j1) { launch_cols(c, ProfqK(c), ALLI, j0, j1); }
-void run_qfilter(Ctx* c, int j0, int j1) {
-  launch_cols(c, QFilterK(c), ALLI, j0, j1);
-  Ptrs& p = c->p;
-  double* t;
-  // (q2b,q2,uf) <- (q2b[filtered], uf, old q2 as scratch)  advance.f:418-421
-  t = p.q2; p.q2 = p.uf; p.uf = t;
-  t = p.q2l; p.q2l = p.vf; p.vf = t;
-}
+// caller swaps q2<->uf, q2l<->vf (advance.f:418-421)
+void run_qfilter(Ctx* c, int j0, int j1) { launch_cols(c, QFilterK(c), ALLI, j0, j1); }
 void run_advt(Ctx* c, int nadv, const double* fb, const double* f, const double* fc, double* ff, int j0, int j1) {
   if (nadv == 1) launch_cols(c, AdvT1K(c, fb, f, fc, ff), ALLI, j0, j1);
   else launch_tiles(c, AdvT2K(c, fb, f, fc, ff), ALLI, j0, j1);
@@ -1049,13 +1043,8 @@ void run_fb_roundtrip(Ctx* c, double* fb, const double* fc, double* f, int j0, i
 void run_proft(Ctx* c, double* f, const double* wf, const double* fs, int nbc, int j0, int j1) {
   launch_cols(c, ProftK(c, f, wf, fs, nbc), ALLI, j0, j1);
 }
-void run_tsfilter(Ctx* c, int j0, int j1) {
-  launch_cols(c, TsFilterK(c), ALLI, j0, j1);
-  Ptrs& p = c->p;
-  double* t;
-  t = p.t; p.t = p.uf; p.uf = t;     // advance.f:446-449
-  t = p.s; p.s = p.vf; p.vf = t;
-}
+// caller swaps t<->uf, s<->vf (advance.f:446-449)
+void run_tsfilter(Ctx* c, int j0, int j1) { launch_cols(c, TsFilterK(c), ALLI, j0, j1); }
 void run_dens(Ctx* c, const double* si, const double* ti, double* ro, int j0, int j1) {
   launch_cols(c, DensK(c, si, ti, ro), ALLI, j0, j1);
 }
@@ -1063,16 +1052,8 @@ void run_advu(Ctx* c, int j0, int j1) { launch_cols(c, AdvuK(c), ALLI, j0, j1); 
 void run_advv(Ctx* c, int j0, int j1) { launch_cols(c, AdvvK(c), ALLI, j0, j1); }
 void run_profu(Ctx* c, int j0, int j1) { launch_cols(c, ProfuK(c), ALLI, j0, j1); }
 void run_profv(Ctx* c, int j0, int j1) { launch_cols(c, ProfvK(c), ALLI, j0, j1); }
-void run_uvfilter(Ctx* c, int j0, int j1) {
-  launch_cols(c, UvFilterK(c), ALLI, j0, j1);
-  Ptrs& p = c->p;
-  double* t;
-  // (ub,u,uf,s3a) <- (s3a[filtered], uf, old u, old ub)   advance.f:511-514
-  t = p.u; p.u = p.uf; p.uf = t;
-  t = p.v; p.v = p.vf; p.vf = t;
-  t = p.ub; p.ub = p.s3a; p.s3a = t;
-  t = p.vb; p.vb = p.s3b; p.s3b = t;
-}
+// caller swaps u<->uf, v<->vf, ub<->s3a, vb<->s3b (advance.f:511-514)
+void run_uvfilter(Ctx* c, int j0, int j1) { launch_cols(c, UvFilterK(c), ALLI, j0, j1); }
 void run_endstep2d(Ctx* c, int j0, int j1) { launch_cols(c, EndStep2dK(c), ALLI, j0, j1); }
 void run_realvertvl(Ctx* c, int j0, int j1) { launch_cols(c, RealvertvlK(c), ALLI, j0, j1); }
 

@@ -212,10 +212,8 @@ struct SmagK : KBase {
 };
 
 void run_advct(Ctx* c, int j0, int j1) { launch_tiles(c, AdvctK(c), 1, c->g.im, j0, j1); }
-void run_baropg(Ctx* c, int j0, int j1) {
-  launch_cols(c, BaropgK(c), 1, c->g.im, j0, j1);
-  double* tmp = c->p.rho; c->p.rho = c->p.rho2; c->p.rho2 = tmp;
-}
+// the caller swaps rho <-> rho2 afterwards
+void run_baropg(Ctx* c, int j0, int j1) { launch_cols(c, BaropgK(c), 1, c->g.im, j0, j1); }
 void run_smag(Ctx* c, int j0, int j1) { launch_cols(c, SmagK(c), 1, c->g.im, j0, j1); }
 
 }  // namespace pom

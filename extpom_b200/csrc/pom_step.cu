@@ -1,7 +1,10 @@
-// pom_step.cu -- orchestration of one internal step (advance.f:21-32) on the
-// HBM-resident state, the check_velocity reduction (advance.f:611-641) and the
+// pom_step.cu -- orchestration of one internal step (advance.f:21-32) on the HBM-resident
+// state of a group of j-strips, the check_velocity reduction (advance.f:611-641) and the
 // C ABI declared in include/pomgpu.h.
-#include "pom_core.h"
+//
+// Every kernel launch is described by the fields it reads (with the j-radius of the read)
+// and the fields it writes; pom_halo.cu turns that into launch windows and halo exchanges.
+#include "pom_halo.h"
 #include "../../include/pomgpu.h"
 #include <cstdlib>
 
@@ -41,12 +44,23 @@ void run_uvfilter(Ctx*, int, int);
 void run_endstep2d(Ctx*, int, int);
 void run_realvertvl(Ctx*, int, int);
 
-static inline int J0(Ctx* c) { return c->g.joff + 1; }
-static inline int J1(Ctx* c) { return c->g.joff + c->g.jml; }
+// ---- launch windows ---------------------------------------------------------------------
+static inline int WLO(const Ctx* c, int e) { return c->jown0 > 1 ? c->jown0 - e : 1; }
+static inline int WHI(const Ctx* c, int e) { return c->jown1 < c->g.jmg ? c->jown1 + e : c->g.jmg; }
+static inline double* FP(Ctx* c, int f) {
+  int n;
+  const FieldInfo* t = field_table(&n);
+  return *(double**)((char*)&c->p + t[f].offset);
+}
+#define NEED(...) ([&]() { const Req rq[] = {__VA_ARGS__}; return group_need(G, rq, (int)(sizeof(rq) / sizeof(rq[0]))); }())
+#define MADE(e, ...) do { const int ou[] = {__VA_ARGS__}; group_produced(G, e, ou, (int)(sizeof(ou) / sizeof(ou[0]))); } while (0)
+#define EACH(stmt) for (int r_ = 0; r_ < G->n; ++r_) { Ctx* c = G->c[r_]; const int j0 = WLO(c, e), j1 = WHI(c, e); (void)j0; (void)j1; stmt; }
+#define CSYNC() for (int r_ = 1; r_ < G->n; ++r_) G->c[r_]->c = G->c[0]->c
 
-static int check_switches(Ctx* c) {
+static int check_switches(Group* G) {
   // run-time switches honoured; others follow the reference's error
   // convention: error_status=1 and a message (advance.f:118-119,432-433)
+  Ctx* c = G->c[0];
   const Consts& k = c->c;
   const char* bad = nullptr;
   if (k.mode != 3 && k.mode != 4) bad = "mode (3 or 4 supported)";
@@ -58,7 +72,7 @@ static int check_switches(Ctx* c) {
   if (bad) {
     snprintf(c->err, sizeof(c->err), "Error: invalid value for %s", bad);
     fprintf(stderr, "\npomgpu: %s\n", c->err);
-    c->c.error_status = 1;
+    for (int r = 0; r < G->n; ++r) G->c[r]->c.error_status = 1;
     return 2;
   }
   if (k.lrestore && !(c->p.trstrb && c->p.trstrf && c->p.srstrb && c->p.srstrf && c->p.taurstrb && c->p.taurstrf)) {
@@ -69,100 +83,213 @@ static int check_switches(Ctx* c) {
   return 0;
 }
 
-// advance.f:96-141
-int lateral_viscosity(Ctx* c) {
-  if (c->c.mode != 2) {
-    run_advct(c, J0(c), J1(c));
-    run_baropg(c, J0(c), J1(c));
-    run_smag(c, J0(c), J1(c));
-  }
+// ---- the kernels of the path, with what they read (field, j-radius) and write ------------
+static void k_advct(Group* G) {
+  int e = NEED({F_u, 1}, {F_v, 1}, {F_ub, 1}, {F_vb, 1}, {F_aam, 1}, {F_dt, 2});
+  EACH(run_advct(c, j0, j1));
+  MADE(e, F_advx, F_advy, F_adx2d, F_ady2d);
+}
+static void k_baropg(Group* G) {
+  // (drhox/drhoy/aam/w are also read in place on the i=1,im columns, whose values never change)
+  int e = NEED({F_rho, 1}, {F_dt, 1});
+  EACH(run_baropg(c, j0, j1));
+  MADE(e, F_drhox, F_drhoy, F_drx2d, F_dry2d, F_rho2);
+  group_swap(G, F_rho, F_rho2);   // rho <- (rho-rmean)+rmean (solver.f:854,937)
+}
+static void k_smag(Group* G) {
+  int e = NEED({F_u, 1}, {F_v, 1});
+  EACH(run_smag(c, j0, j1));
+  MADE(e, F_aam, F_aam2d);
+}
+static void k_advave(Group* G) {
+  int e = NEED({F_d, 2}, {F_ua, 1}, {F_va, 1}, {F_uab, 1}, {F_vab, 1}, {F_aam2d, 1});
+  EACH(run_advave(c, j0, j1));
+  MADE(e, F_advua, F_advva);
+}
+static void k_mode_inter_tail(Group* G) {
+  int e = NEED({F_adx2d, 0}, {F_ady2d, 0}, {F_advua, 0}, {F_advva, 0}, {F_el, 0}, {F_ua, 0}, {F_va, 0}, {F_d, 1});
+  EACH(run_mode_inter_tail(c, j0, j1));
+  MADE(e, F_adx2d, F_ady2d, F_egf, F_utf, F_vtf);
+}
+static void k_ext_elf(Group* G) {
+  int e = NEED({F_d, 1}, {F_va, 1}, {F_ua, 0}, {F_elb, 0});
+  EACH(run_ext_elf(c, j0, j1));
+  MADE(e, F_elf);
+}
+static void k_ext_uv(Group* G, int iext) {
+  const int isplit = G->c[0]->c.isplit;
+  int e = NEED({F_adx2d, 0}, {F_advua, 0}, {F_ady2d, 0}, {F_advva, 0}, {F_d, 1}, {F_va, 1}, {F_ua, 1},
+               {F_el, 1}, {F_elb, 1}, {F_elf, 1}, {F_drx2d, 0}, {F_dry2d, 0}, {F_wubot, 0}, {F_wvbot, 0},
+               {F_uab, 0}, {F_vab, 0}, {F_egf, 0}, {F_utf, 0}, {F_vtf, 0});
+  if (iext > isplit - 2) { const Req q[] = {{F_etf, 0}}; int e2 = group_need(G, q, 1); if (e2 < e) e = e2; }
+  EACH(run_ext_uv(c, iext, j0, j1));
+  MADE(e, F_uaf, F_vaf, F_uab, F_vab, F_el2, F_d2, F_ua, F_va);
+  if (iext >= isplit - 2) MADE(e, F_etf);
+  if (iext != isplit) MADE(e, F_egf, F_utf, F_vtf);
+  // time rotation (advance.f:324-330)
+  group_swap(G, F_ua, F_uaf); group_swap(G, F_va, F_vaf);
+  group_swap(G, F_elb, F_el2); group_swap(G, F_el, F_elf);
+  group_swap(G, F_d, F_d2);
+}
+static void k_uvadjust(Group* G) {
+  int e = NEED({F_u, 0}, {F_v, 0}, {F_utb, 0}, {F_utf, 0}, {F_vtb, 0}, {F_vtf, 0}, {F_dt, 1});
+  EACH(run_uvadjust(c, j0, j1));
+  MADE(e, F_u, F_v);
+}
+static void k_vertvl(Group* G) {
+  int e = NEED({F_u, 0}, {F_v, 1}, {F_dt, 1}, {F_etf, 0}, {F_etb, 0}, {F_vfluxb, 0});
+  EACH(run_vertvl(c, j0, j1));
+  MADE(e, F_w);
+}
+static void k_advq(Group* G) {
+  int e = NEED({F_q2, 1}, {F_q2b, 1}, {F_q2l, 1}, {F_q2lb, 1}, {F_u, 0}, {F_v, 1}, {F_aam, 1}, {F_dt, 1},
+               {F_w, 0}, {F_etb, 0}, {F_etf, 0});
+  EACH(run_advq(c, j0, j1));
+  MADE(e, F_uf, F_vf);
+}
+static void k_profq(Group* G) {
+  int e = NEED({F_t, 0}, {F_s, 0}, {F_rho, 0}, {F_q2b, 0}, {F_q2lb, 0}, {F_q2, 0}, {F_u, 0}, {F_v, 1},
+               {F_km, 0}, {F_kh, 0}, {F_kq, 0}, {F_uf, 0}, {F_vf, 0}, {F_etf, 0}, {F_wubot, 0}, {F_wvbot, 1});
+  EACH(run_profq(c, j0, j1));
+  MADE(e, F_uf, F_vf, F_km, F_kh, F_kq, F_l, F_q2b, F_q2lb);
+}
+static void k_qfilter(Group* G) {
+  int e = NEED({F_uf, 0}, {F_vf, 0}, {F_q2, 0}, {F_q2b, 0}, {F_q2l, 0}, {F_q2lb, 0}, {F_u, 0}, {F_v, 0});
+  EACH(run_qfilter(c, j0, j1));
+  MADE(e, F_uf, F_vf, F_q2b, F_q2lb);
+  group_swap(G, F_q2, F_uf); group_swap(G, F_q2l, F_vf);   // advance.f:418-421
+}
+static void k_advt(Group* G, int fb, int f, int fc, int ff) {
+  int e = NEED({fb, 1}, {f, 0}, {F_u, 0}, {F_v, 1}, {F_w, 0}, {F_aam, 1}, {F_dt, 1}, {F_etb, 0}, {F_etf, 0});
+  EACH(run_advt(c, c->c.nadv, FP(c, fb), FP(c, f), FP(c, fc), FP(c, ff), j0, j1));
+  MADE(e, ff);
+}
+static void k_proft(Group* G, int f, int wf, int fs, int nbc) {
+  int e = NEED({f, 0}, {F_kh, 0}, {F_etf, 0});
+  EACH(run_proft(c, FP(c, f), FP(c, wf), FP(c, fs), nbc, j0, j1));
+  MADE(e, f);
+}
+static void k_tsfilter(Group* G) {
+  int e = NEED({F_uf, 0}, {F_vf, 0}, {F_t, 0}, {F_s, 0}, {F_tb, 0}, {F_sb, 0}, {F_u, 0}, {F_v, 0}, {F_w, 0}, {F_dt, 0});
+  EACH(run_tsfilter(c, j0, j1));
+  MADE(e, F_uf, F_vf, F_tb, F_sb);
+  group_swap(G, F_t, F_uf); group_swap(G, F_s, F_vf);      // advance.f:446-449
+}
+static void k_dens(Group* G, int si, int ti, int ro) {
+  int e = NEED({si, 0}, {ti, 0});
+  EACH(run_dens(c, FP(c, si), FP(c, ti), FP(c, ro), j0, j1));
+  MADE(e, ro);
+}
+static void k_advu(Group* G) {
+  int e = NEED({F_w, 0}, {F_u, 0}, {F_v, 1}, {F_advx, 0}, {F_drhox, 0}, {F_ub, 0}, {F_dt, 0}, {F_egf, 0},
+               {F_egb, 0}, {F_etb, 0}, {F_etf, 0});
+  EACH(run_advu(c, j0, j1));
+  MADE(e, F_uf);
+}
+static void k_advv(Group* G) {
+  int e = NEED({F_w, 1}, {F_v, 0}, {F_u, 1}, {F_advy, 0}, {F_drhoy, 0}, {F_vb, 0}, {F_dt, 1}, {F_egf, 1},
+               {F_egb, 1}, {F_etb, 1}, {F_etf, 1});
+  EACH(run_advv(c, j0, j1));
+  MADE(e, F_vf);
+}
+static void k_profu(Group* G) {
+  int e = NEED({F_km, 0}, {F_uf, 0}, {F_ub, 0}, {F_vb, 1}, {F_etf, 0}, {F_wubot, 0});
+  EACH(run_profu(c, j0, j1));
+  MADE(e, F_uf, F_wubot);
+}
+static void k_profv(Group* G) {
+  int e = NEED({F_km, 1}, {F_vf, 0}, {F_vb, 0}, {F_ub, 1}, {F_etf, 1}, {F_wvbot, 0});
+  EACH(run_profv(c, j0, j1));
+  MADE(e, F_vf, F_wvbot);
+}
+static void k_uvfilter(Group* G) {
+  int e = NEED({F_uf, 0}, {F_vf, 0}, {F_u, 0}, {F_v, 0}, {F_ub, 0}, {F_vb, 0});
+  EACH(run_uvfilter(c, j0, j1));
+  MADE(e, F_uf, F_vf, F_s3a, F_s3b);
+  group_swap(G, F_u, F_uf); group_swap(G, F_v, F_vf);      // advance.f:511-514
+  group_swap(G, F_ub, F_s3a); group_swap(G, F_vb, F_s3b);
+}
+static void k_endstep2d(Group* G) {
+  int e = NEED({F_egf, 0}, {F_et, 0}, {F_etf, 0}, {F_utf, 0}, {F_vtf, 0});
+  EACH(run_endstep2d(c, j0, j1));
+  MADE(e, F_egb, F_etb, F_et, F_dt, F_utb, F_vtb, F_vfluxb);
+}
+static void k_realvertvl(Group* G) {
+  int e = NEED({F_w, 0}, {F_u, 0}, {F_v, 1}, {F_dt, 1}, {F_et, 1}, {F_etf, 0}, {F_etb, 0});
+  EACH(run_realvertvl(c, j0, j1));
+  MADE(e, F_wr);
+}
+
+// ---- advance.f:96-141 ---------------------------------------------------------------------
+static int lateral_viscosity(Group* G) {
+  if (G->c[0]->c.mode != 2) { k_advct(G); k_baropg(G); k_smag(G); }
   return 0;
 }
 // advance.f:144-202 (the vertical integrals were accumulated by the producers)
-int mode_interaction(Ctx* c) {
-  if (c->c.mode != 2) run_advave(c, J0(c), J1(c));
-  run_mode_inter_tail(c, J0(c), J1(c));
+static int mode_interaction(Group* G) {
+  if (G->c[0]->c.mode != 2) k_advave(G);
+  k_mode_inter_tail(G);
   return 0;
 }
 // advance.f:205-353
-int mode_external(Ctx* c, int iext) {
-  c->c.iext = iext;
-  run_ext_elf(c, J0(c), J1(c));
-  if (iext % c->c.ispadv == 0) run_advave(c, J0(c), J1(c));
-  run_ext_uv(c, iext, J0(c), J1(c));
+static int mode_external(Group* G, int iext) {
+  G->c[0]->c.iext = iext; CSYNC();
+  k_ext_elf(G);
+  if (iext % G->c[0]->c.ispadv == 0) k_advave(G);
+  k_ext_uv(G, iext);
   return 0;
 }
-// advance.f:356-537
-int mode_internal(Ctx* c, int iint) {
-  c->c.iint = iint;
-  Ptrs& p = c->p;
-  if ((iint != 1 || c->c.time0 != 0.) && c->c.mode != 2) {
-    run_uvadjust(c, J0(c), J1(c));
-    run_vertvl(c, J0(c), J1(c));
-    run_advq(c, J0(c), J1(c));
-    run_profq(c, J0(c), J1(c));
-    run_qfilter(c, J0(c), J1(c));
-    if (c->c.mode != 4) {
-      run_advt(c, c->c.nadv, p.tb, p.t, p.tclim, p.uf, J0(c), J1(c));
-      run_advt(c, c->c.nadv, p.sb, p.s, p.sclim, p.vf, J0(c), J1(c));
-      run_proft(c, p.uf, p.wtsurf, p.tsurf, c->c.nbct, J0(c), J1(c));
-      run_proft(c, p.vf, p.wssurf, p.ssurf, c->c.nbcs, J0(c), J1(c));
-      run_tsfilter(c, J0(c), J1(c));
-      run_dens(c, p.s, p.t, p.rho, J0(c), J1(c));
-    }
-    run_advu(c, J0(c), J1(c));
-    run_advv(c, J0(c), J1(c));
-    run_profu(c, J0(c), J1(c));
-    run_profv(c, J0(c), J1(c));
-    run_uvfilter(c, J0(c), J1(c));
-  }
-  run_endstep2d(c, J0(c), J1(c));
-  run_realvertvl(c, J0(c), J1(c));
-  return 0;
-}
-
-// one block of mode_internal (same numbering as the oracle's pomo_internal_stage): lets
-// tests compare block by block
-int internal_stage(Ctx* c, int iint, int st) {
-  c->c.iint = iint;
-  Ptrs& p = c->p;
-  const bool ts = (c->c.mode != 4);
+// one block of mode_internal (same numbering as the oracle's pomo_internal_stage)
+static int internal_stage(Group* G, int iint, int st) {
+  G->c[0]->c.iint = iint; CSYNC();
+  const Consts& k = G->c[0]->c;
+  const bool ts = (k.mode != 4);
   switch (st) {
-    case 0: run_uvadjust(c, J0(c), J1(c)); break;
-    case 1: run_vertvl(c, J0(c), J1(c)); break;
-    case 2: run_advq(c, J0(c), J1(c)); break;
-    case 3: run_profq(c, J0(c), J1(c)); break;
-    case 4: run_qfilter(c, J0(c), J1(c)); break;
-    case 5: if (ts) run_advt(c, c->c.nadv, p.tb, p.t, p.tclim, p.uf, J0(c), J1(c)); break;
-    case 6: if (ts) run_advt(c, c->c.nadv, p.sb, p.s, p.sclim, p.vf, J0(c), J1(c)); break;
-    case 7: if (ts) run_proft(c, p.uf, p.wtsurf, p.tsurf, c->c.nbct, J0(c), J1(c)); break;
-    case 8: if (ts) run_proft(c, p.vf, p.wssurf, p.ssurf, c->c.nbcs, J0(c), J1(c)); break;
-    case 9: if (ts) run_tsfilter(c, J0(c), J1(c)); break;
-    case 10: if (ts) run_dens(c, p.s, p.t, p.rho, J0(c), J1(c)); break;
-    case 11: run_advu(c, J0(c), J1(c)); break;
-    case 12: run_advv(c, J0(c), J1(c)); break;
-    case 13: run_profu(c, J0(c), J1(c)); break;
-    case 14: run_profv(c, J0(c), J1(c)); break;
-    case 15: run_uvfilter(c, J0(c), J1(c)); break;
-    case 16: run_endstep2d(c, J0(c), J1(c)); break;
-    case 17: run_realvertvl(c, J0(c), J1(c)); break;
+    case 0: k_uvadjust(G); break;
+    case 1: k_vertvl(G); break;
+    case 2: k_advq(G); break;
+    case 3: k_profq(G); break;
+    case 4: k_qfilter(G); break;
+    case 5: if (ts) k_advt(G, F_tb, F_t, F_tclim, F_uf); break;
+    case 6: if (ts) k_advt(G, F_sb, F_s, F_sclim, F_vf); break;
+    case 7: if (ts) k_proft(G, F_uf, F_wtsurf, F_tsurf, k.nbct); break;
+    case 8: if (ts) k_proft(G, F_vf, F_wssurf, F_ssurf, k.nbcs); break;
+    case 9: if (ts) k_tsfilter(G); break;
+    case 10: if (ts) k_dens(G, F_s, F_t, F_rho); break;
+    case 11: k_advu(G); break;
+    case 12: k_advv(G); break;
+    case 13: k_profu(G); break;
+    case 14: k_profv(G); break;
+    case 15: k_uvfilter(G); break;
+    case 16: k_endstep2d(G); break;
+    case 17: k_realvertvl(G); break;
     default: return 2;
   }
   return 0;
 }
-
-int step(Ctx* c, int iint, double time, double ramp) {
-  c->c.iint = iint; c->c.time = time; c->c.ramp = ramp;
-  if (int r = check_switches(c)) return r;
-  lateral_viscosity(c);
-  mode_interaction(c);
-  for (int iext = 1; iext <= c->c.isplit; ++iext) mode_external(c, iext);
-  c->c.iext = c->c.isplit + 1;
-  mode_internal(c, iint);
+// advance.f:356-537
+static int mode_internal(Group* G, int iint) {
+  const Consts& k = G->c[0]->c;
+  if ((iint != 1 || k.time0 != 0.) && k.mode != 2)
+    for (int st = 0; st <= 15; ++st) internal_stage(G, iint, st);
+  internal_stage(G, iint, 16);
+  internal_stage(G, iint, 17);
   return 0;
 }
 
-// ---- check_velocity: max|vaf| (after the substep rotation vaf's values live in va)
+static int step(Group* G, int iint, double time, double ramp) {
+  Ctx* c0 = G->c[0];
+  c0->c.iint = iint; c0->c.time = time; c0->c.ramp = ramp; CSYNC();
+  if (int r = check_switches(G)) return r;
+  lateral_viscosity(G);
+  mode_interaction(G);
+  for (int iext = 1; iext <= c0->c.isplit; ++iext) mode_external(G, iext);
+  c0->c.iext = c0->c.isplit + 1; CSYNC();
+  mode_internal(G, iint);
+  return c0->c.error_status ? 1 : 0;
+}
+
+// ---- check_velocity: max|vaf| over the owned rows (after the rotation vaf lives in va) ----
 #ifndef POMGPU_EMU
 __global__ void absmax_kernel(const double* __restrict__ a, size_t n, unsigned long long* out) {
   double m = 0.;
@@ -178,9 +305,9 @@ __global__ void absmax_kernel(const double* __restrict__ a, size_t n, unsigned l
 }
 #endif
 
-double check_velocity(Ctx* c) {
-  const double* a = c->p.va;
-  size_t n = c->g.n2;
+static double check_velocity(Ctx* c) {
+  const double* a = c->p.va + (size_t)(c->jown0 - 1 - c->g.joff) * c->g.im;
+  size_t n = (size_t)(c->jown1 - c->jown0 + 1) * c->g.im;
   double vamax = 0.;
 #ifdef POMGPU_EMU
   for (size_t i = 0; i < n; ++i) { double v = fabs(a[i]); if (!(v <= vamax)) vamax = v; }
@@ -203,8 +330,13 @@ double check_velocity(Ctx* c) {
 
 // =============================== C ABI =======================================
 using namespace pom;
-struct pomgpu { Ctx c; };
 static inline Ctx* X(pomgpu_t* p) { return (Ctx*)p; }
+static inline Group* GG(pomgpu_group_t* g) { return (Group*)g; }
+// every context owns a group of one, so the single-strip entry points share the code path
+static Group* self_group(Ctx* c) {
+  if (!c->self) { Ctx* a[1] = {c}; c->self = group_create(1, a); }
+  return (Group*)c->self;
+}
 
 extern "C" {
 
@@ -213,9 +345,14 @@ pomgpu_t* pomgpu_create(int im, int jm, int kb, int device) {
 }
 pomgpu_t* pomgpu_create_strip(int im, int jm_global, int kb, int j_first, int j_last, int ghost, int device) {
   if (j_first < 1 || j_last > jm_global || j_last < j_first || ghost < 0) return nullptr;
+  if ((j_first > 1 || j_last < jm_global) && ghost < 2) return nullptr;   // advct reads dt two rows away
   return (pomgpu_t*)ctx_create(im, jm_global, kb, j_first, j_last, ghost, device);
 }
-void pomgpu_destroy(pomgpu_t* p) { ctx_destroy(X(p)); }
+void pomgpu_destroy(pomgpu_t* p) {
+  if (!p) return;
+  if (X(p)->self) group_destroy((Group*)X(p)->self);
+  ctx_destroy(X(p));
+}
 int pomgpu_local_rows(const pomgpu_t* p) { return ((const Ctx*)p)->g.jml; }
 int pomgpu_row_offset(const pomgpu_t* p) { return ((const Ctx*)p)->g.joff; }
 const char* pomgpu_last_error(const pomgpu_t* p) { return ((const Ctx*)p)->err; }
@@ -227,9 +364,6 @@ long pomgpu_field_elems(pomgpu_t* p, const char* name) {
   const FieldInfo* f = find_field(name);
   return f ? (long)field_elems(X(p), f) : 0;
 }
-int pomgpu_step(pomgpu_t* p, int iint, double time, double ramp) { return step(X(p), iint, time, ramp); }
-int pomgpu_sync(pomgpu_t* p) { return dev_sync(X(p)); }
-double pomgpu_check_velocity(pomgpu_t* p) { return check_velocity(X(p)); }
 int pomgpu_push_async(pomgpu_t* p, const char* name, const double* host) {
   Ctx* c = X(p);
   const FieldInfo* f;
@@ -244,7 +378,7 @@ int pomgpu_push_async(pomgpu_t* p, const char* name, const double* host) {
   return 0;
 #endif
 }
-int pomgpu_pin_host(void* ptr, size_t bytes) {
+int pomgpu_pin_host(void* ptr, unsigned long bytes) {
 #ifdef POMGPU_EMU
   (void)ptr; (void)bytes; return 0;
 #else
@@ -258,6 +392,15 @@ int pomgpu_unpin_host(void* ptr) {
   return cudaHostUnregister(ptr) == cudaSuccess ? 0 : 1;
 #endif
 }
+int pomgpu_step(pomgpu_t* p, int iint, double time, double ramp) { return step(self_group(X(p)), iint, time, ramp); }
+int pomgpu_sync(pomgpu_t* p) { return dev_sync(X(p)); }
+double pomgpu_check_velocity(pomgpu_t* p) { return check_velocity(X(p)); }
+long pomgpu_launch_count(pomgpu_t* p, int reset) {
+  long n = X(p)->launches;
+  if (reset) X(p)->launches = 0;
+  return n;
+}
+
 // CUDA events on the library's launch stream (bench.py times the step loop with these)
 #ifndef POMGPU_EMU
 static cudaEvent_t g_ev[8];
@@ -286,58 +429,93 @@ double pomgpu_event_elapsed_ms(pomgpu_t* p, int a, int b) {
 }
 int pomgpu_profile_begin(pomgpu_t* p) { dev_sync(X(p)); X(p)->prof_on = 1; return 0; }
 int pomgpu_profile_end(pomgpu_t* p, char* json, int len) { X(p)->prof_on = 0; return prof_report(X(p), json, len); }
-long pomgpu_launch_count(pomgpu_t* p, int reset) {
-  long n = X(p)->launches;
-  if (reset) X(p)->launches = 0;
+
+// ---- strip groups (multi-GPU) ----------------------------------------------------------------
+pomgpu_group_t* pomgpu_group_create(int n, pomgpu_t** ctxs) { return (pomgpu_group_t*)group_create(n, (Ctx**)ctxs); }
+void pomgpu_group_destroy(pomgpu_group_t* g) { group_destroy(GG(g)); }
+int pomgpu_nccl_unique_id(void* out128) { return nccl_unique_id(out128); }
+int pomgpu_group_connect_nccl(pomgpu_group_t* g, const void* id128, int rank, int world) {
+  return group_connect_nccl(GG(g), id128, rank, world);
+}
+void pomgpu_group_set_transport(pomgpu_group_t* g, pomgpu_halo_cb cb, void* user) { group_set_callback(GG(g), (halo_cb)cb, user); }
+int pomgpu_group_step(pomgpu_group_t* g, int iint, double time, double ramp) { return step(GG(g), iint, time, ramp); }
+double pomgpu_group_check_velocity(pomgpu_group_t* g) {
+  double m = 0.;
+  for (int r = 0; r < GG(g)->n; ++r) { double v = check_velocity(GG(g)->c[r]); if (!(v <= m)) m = v; }
+  return m;
+}
+long pomgpu_group_exchanges(pomgpu_group_t* g, long* fields, int reset) {
+  long n = GG(g)->n_exchanges;
+  if (fields) *fields = GG(g)->n_fields_exchanged;
+  if (reset) { GG(g)->n_exchanges = 0; GG(g)->n_fields_exchanged = 0; }
   return n;
 }
 
-int pomgpu_lateral_viscosity(pomgpu_t* p) { if (int r = check_switches(X(p))) return r; return lateral_viscosity(X(p)); }
-int pomgpu_mode_interaction(pomgpu_t* p) { return mode_interaction(X(p)); }
-int pomgpu_mode_external(pomgpu_t* p, int iext) { if (int r = check_switches(X(p))) return r; return mode_external(X(p), iext); }
-int pomgpu_internal_stage(pomgpu_t* p, int iint, int stage) { return internal_stage(X(p), iint, stage); }
-int pomgpu_mode_internal(pomgpu_t* p, int iint) { if (int r = check_switches(X(p))) return r; return mode_internal(X(p), iint); }
+// dens / baropg on a group: what the Fortran `initialize` calls before the first step
+// (initialize.f:416,425,502)
+static int fid(const char* name);
+int pomgpu_group_dens(pomgpu_group_t* g, const char* si, const char* ti, const char* rhoo) {
+  int a = fid(si), b = fid(ti), o = fid(rhoo);
+  if (a < 0 || b < 0 || o < 0) return 2;
+  k_dens(GG(g), a, b, o);
+  return 0;
+}
+int pomgpu_group_baropg(pomgpu_group_t* g) { k_baropg(GG(g)); return 0; }
 
-#define W0 J0(c), J1(c)
-int pomgpu_advave(pomgpu_t* p) { Ctx* c = X(p); run_advave(c, W0); return 0; }
-int pomgpu_advct(pomgpu_t* p) { Ctx* c = X(p); run_advct(c, W0); return 0; }
-int pomgpu_advq(pomgpu_t* p) { Ctx* c = X(p); run_advq(c, W0); return 0; }
-int pomgpu_advu(pomgpu_t* p) { Ctx* c = X(p); run_advu(c, W0); return 0; }
-int pomgpu_advv(pomgpu_t* p) { Ctx* c = X(p); run_advv(c, W0); return 0; }
-int pomgpu_baropg(pomgpu_t* p) { Ctx* c = X(p); run_baropg(c, W0); return 0; }
-int pomgpu_profq(pomgpu_t* p) { Ctx* c = X(p); run_profq(c, W0); return 0; }
-int pomgpu_profu(pomgpu_t* p) { Ctx* c = X(p); run_profu(c, W0); return 0; }
-int pomgpu_profv(pomgpu_t* p) { Ctx* c = X(p); run_profv(c, W0); return 0; }
-int pomgpu_vertvl(pomgpu_t* p) { Ctx* c = X(p); run_vertvl(c, W0); return 0; }
-int pomgpu_realvertvl(pomgpu_t* p) { Ctx* c = X(p); run_realvertvl(c, W0); return 0; }
+// ---- the reference's subroutines on the resident state ----------------------------------------
+#define SG Group* G = self_group(X(p))
+int pomgpu_lateral_viscosity(pomgpu_t* p) { SG; if (int r = check_switches(G)) return r; return lateral_viscosity(G); }
+int pomgpu_mode_interaction(pomgpu_t* p) { SG; return mode_interaction(G); }
+int pomgpu_mode_external(pomgpu_t* p, int iext) { SG; if (int r = check_switches(G)) return r; return mode_external(G, iext); }
+int pomgpu_internal_stage(pomgpu_t* p, int iint, int stage) { SG; return internal_stage(G, iint, stage); }
+int pomgpu_mode_internal(pomgpu_t* p, int iint) { SG; if (int r = check_switches(G)) return r; return mode_internal(G, iint); }
+int pomgpu_advave(pomgpu_t* p) { SG; k_advave(G); return 0; }
+int pomgpu_advct(pomgpu_t* p) { SG; k_advct(G); return 0; }
+int pomgpu_advq(pomgpu_t* p) { SG; k_advq(G); return 0; }
+int pomgpu_advu(pomgpu_t* p) { SG; k_advu(G); return 0; }
+int pomgpu_advv(pomgpu_t* p) { SG; k_advv(G); return 0; }
+int pomgpu_baropg(pomgpu_t* p) { SG; k_baropg(G); return 0; }
+int pomgpu_profq(pomgpu_t* p) { SG; k_profq(G); return 0; }
+int pomgpu_profu(pomgpu_t* p) { SG; k_profu(G); return 0; }
+int pomgpu_profv(pomgpu_t* p) { SG; k_profv(G); return 0; }
+int pomgpu_vertvl(pomgpu_t* p) { SG; k_vertvl(G); return 0; }
+int pomgpu_realvertvl(pomgpu_t* p) { SG; k_realvertvl(G); return 0; }
 
-static double* fld(Ctx* c, const char* name) {
-  double** s = ctx_slot(c, name, nullptr);
-  return s ? *s : nullptr;
+static int fid(const char* name) {
+  int n;
+  const FieldInfo* t = field_table(&n);
+  for (int i = 0; i < n; ++i)
+    if (!strcmp(t[i].name, name)) return i;
+  return -1;
 }
 static int advt(pomgpu_t* p, int nadv, const char* fb, const char* f, const char* fclim, const char* ff) {
+  SG;
   Ctx* c = X(p);
-  double *a = fld(c, fb), *b = fld(c, f), *cl = fld(c, fclim), *o = fld(c, ff);
-  if (!a || !b || !cl || !o) return 2;
+  int a = fid(fb), b = fid(f), cl = fid(fclim), o = fid(ff);
+  if (a < 0 || b < 0 || cl < 0 || o < 0) return 2;
   if (nadv == 2 && c->c.nitera != 1) return 2;
-  run_advt(c, nadv, a, b, cl, o, W0);
-  run_fb_roundtrip(c, a, cl, nadv == 1 ? b : nullptr, W0);   // side effects on fb (and f for advt1)
+  const int keep = c->c.nadv;
+  c->c.nadv = nadv;
+  k_advt(G, a, b, cl, o);
+  c->c.nadv = keep;
+  // side effects the reference leaves on fb (and f for advt1): solver.f:496,511,532 / 618,691,715
+  run_fb_roundtrip(c, FP(c, a), FP(c, cl), nadv == 1 ? FP(c, b) : nullptr, 1, c->g.jmg);
   return 0;
 }
 int pomgpu_advt1(pomgpu_t* p, const char* fb, const char* f, const char* fclim, const char* ff) { return advt(p, 1, fb, f, fclim, ff); }
 int pomgpu_advt2(pomgpu_t* p, const char* fb, const char* f, const char* fclim, const char* ff) { return advt(p, 2, fb, f, fclim, ff); }
 int pomgpu_dens(pomgpu_t* p, const char* si, const char* ti, const char* rhoo) {
-  Ctx* c = X(p);
-  double *a = fld(c, si), *b = fld(c, ti), *o = fld(c, rhoo);
-  if (!a || !b || !o) return 2;
-  run_dens(c, a, b, o, W0);
+  SG;
+  int a = fid(si), b = fid(ti), o = fid(rhoo);
+  if (a < 0 || b < 0 || o < 0) return 2;
+  k_dens(G, a, b, o);
   return 0;
 }
 int pomgpu_proft(pomgpu_t* p, const char* f, const char* wfsurf, const char* fsurf, int nbc) {
-  Ctx* c = X(p);
-  double *a = fld(c, f), *b = fld(c, wfsurf), *s = fld(c, fsurf);
-  if (!a || !b || !s) return 2;
-  run_proft(c, a, b, s, nbc, W0);
+  SG;
+  int a = fid(f), b = fid(wfsurf), s = fid(fsurf);
+  if (a < 0 || b < 0 || s < 0) return 2;
+  k_proft(G, a, b, s, nbc);
   return 0;
 }
 

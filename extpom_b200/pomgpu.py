@@ -74,6 +74,19 @@ def _bind(path):
     L.pomgpu_mode_external.argtypes = [P, C.c_int]
     L.pomgpu_mode_internal.argtypes = [P, C.c_int]
     L.pomgpu_internal_stage.argtypes = [P, C.c_int, C.c_int]
+    L.pomgpu_group_create.restype = P
+    L.pomgpu_group_create.argtypes = [C.c_int, C.POINTER(P)]
+    L.pomgpu_group_destroy.argtypes = [P]
+    L.pomgpu_nccl_unique_id.argtypes = [P]
+    L.pomgpu_group_connect_nccl.argtypes = [P, P, C.c_int, C.c_int]
+    L.pomgpu_group_set_transport.argtypes = [P, P, P]
+    L.pomgpu_group_step.argtypes = [P, C.c_int, C.c_double, C.c_double]
+    L.pomgpu_group_dens.argtypes = [P] + [C.c_char_p] * 3
+    L.pomgpu_group_baropg.argtypes = [P]
+    L.pomgpu_group_check_velocity.restype = C.c_double
+    L.pomgpu_group_check_velocity.argtypes = [P]
+    L.pomgpu_group_exchanges.restype = C.c_long
+    L.pomgpu_group_exchanges.argtypes = [P, C.POINTER(C.c_long), C.c_int]
     L.pomgpu_advt1.argtypes = [P] + [C.c_char_p] * 4
     L.pomgpu_advt2.argtypes = [P] + [C.c_char_p] * 4
     L.pomgpu_dens.argtypes = [P] + [C.c_char_p] * 3
@@ -103,6 +116,7 @@ class PomGpu:
         if not self.h:
             raise PomGpuError("pomgpu_create failed (no CUDA device, bad extents or out of memory); "
                               "there is no CPU fallback")
+        self.own = (1, jm) if strip is None else tuple(strip)
         self.jml = self.L.pomgpu_local_rows(self.h)
         self.joff = self.L.pomgpu_row_offset(self.h)
         jl = self.jml
@@ -242,3 +256,95 @@ class PomGpu:
 
     def proft(self, f, wfsurf, fsurf, nbc):
         self._ck(self.L.pomgpu_proft(self.h, f.encode(), wfsurf.encode(), fsurf.encode(), int(nbc)), "proft")
+
+
+HALO_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_long,
+                      C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_long)
+
+
+class PomGroup:
+    """The ordered (south -> north) strips held by this process, stepped together; halo rows
+    are exchanged inside the step only when a kernel would read a stale one (csrc/pom_halo.cu)."""
+
+    def __init__(self, strips):
+        self.strips = list(strips)
+        self.L = self.strips[0].L
+        arr = (C.c_void_p * len(self.strips))(*[s.h for s in self.strips])
+        self.h = self.L.pomgpu_group_create(len(self.strips), arr)
+        if not self.h:
+            raise PomGpuError("pomgpu_group_create failed (strips not contiguous, different ghost widths, "
+                              "or a strip thinner than ghost+4 rows)")
+        self._cb = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pomgpu_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def nccl_unique_id(lib):
+        buf = C.create_string_buffer(128)
+        if lib.pomgpu_nccl_unique_id(buf) != 0:
+            raise PomGpuError("ncclGetUniqueId failed (libnccl.so.2 not found?)")
+        return buf.raw
+
+    def connect_nccl(self, uid, rank, world):
+        if self.L.pomgpu_group_connect_nccl(self.h, uid, rank, world) != 0:
+            raise PomGpuError("ncclCommInitRank failed: " + self.L.pomgpu_last_error(self.strips[0].h).decode())
+
+    def set_transport(self, fn):
+        """fn(send_s, recv_s, send_n, recv_n): numpy views of the staging buffers (None = no neighbour)."""
+        def cb(user, ss, rs, ns, sn, rn, nn):
+            try:
+                a = lambda p, n: np.ctypeslib.as_array(p, shape=(n,)) if n else None
+                fn(a(ss, ns), a(rs, ns), a(sn, nn), a(rn, nn))
+                return 0
+            except Exception as e:  # noqa: BLE001
+                print("halo transport failed:", e)
+                return 1
+        self._cb = HALO_CB(cb)
+        self.L.pomgpu_group_set_transport(self.h, C.cast(self._cb, C.c_void_p), None)
+
+    def step(self, iint, time=None, ramp=1.0):
+        s0 = self.strips[0]
+        if time is None:
+            time = s0.getc("dti") * float(iint) / 86400.0 + s0.getc("time0")
+        rc = self.L.pomgpu_group_step(self.h, int(iint), float(time), float(ramp))
+        if rc != 0:
+            raise PomGpuError(f"group_step failed (rc={rc}): {self.L.pomgpu_last_error(s0.h).decode()}")
+
+    def dens(self, si, ti, rhoo):
+        if self.L.pomgpu_group_dens(self.h, si.encode(), ti.encode(), rhoo.encode()) != 0:
+            raise PomGpuError("group dens failed")
+
+    def baropg(self):
+        self.L.pomgpu_group_baropg(self.h)
+
+    def check_velocity(self):
+        return self.L.pomgpu_group_check_velocity(self.h)
+
+    def exchanges(self, reset=False):
+        f = C.c_long(0)
+        n = self.L.pomgpu_group_exchanges(self.h, C.byref(f), int(reset))
+        return n, f.value
+
+    def gather(self, name):
+        """Owned rows of every strip of this process stacked in j (tests)."""
+        parts = []
+        for s in self.strips:
+            a = s.get(name)
+            lo = s.own[0] - 1 - s.joff
+            hi = s.own[1] - s.joff
+            if a.ndim >= 2 and a.shape[1] == s.jml and name not in BIK:
+                parts.append(a[:, lo:hi])
+            elif a.shape[0] == s.jml and (name in BJ or name in BJK):
+                parts.append(a[lo:hi])
+            else:
+                return a
+        return np.concatenate(parts, axis=1 if parts[0].ndim >= 2 and name not in BJ + BJK else 0)

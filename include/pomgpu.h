@@ -22,6 +22,7 @@ extern "C" {
 #endif
 
 typedef struct pomgpu pomgpu_t;
+typedef struct pomgpu_group pomgpu_group_t;
 
 /* ---- lifecycle ------------------------------------------------------------
  * Replaces distribute_mpi (pom/parallel_mpi.f:34-122).  pomgpu_create holds the
@@ -73,6 +74,30 @@ int pomgpu_event_record(pomgpu_t* ctx, int slot);            /* slot 0..7, on th
 double pomgpu_event_elapsed_ms(pomgpu_t* ctx, int a, int b);  /* waits for event b */
 int pomgpu_profile_begin(pomgpu_t* ctx);
 int pomgpu_profile_end(pomgpu_t* ctx, char* json, int len);
+
+/* ---- multi-GPU: j-strips with redundant ghost rows -----------------------------
+ * Replaces exchange2d_mpi / exchange3d_mpi (pom/parallel_mpi.f:154-351).  A group is
+ * the ordered (south -> north) list of strips held by THIS process: all strips of the
+ * domain in one process (tests), or one strip per process/GPU connected over NCCL
+ * (pomgpu_nccl_unique_id on rank 0, broadcast by the driver's MPI, then
+ * pomgpu_group_connect_nccl everywhere).  pomgpu_group_step = pomgpu_step on the
+ * group; halo exchanges are issued inside, only when a kernel would read a stale row.
+ * An N-strip run is bitwise equal to the single-domain run. */
+pomgpu_group_t* pomgpu_group_create(int n, pomgpu_t** strips);
+void pomgpu_group_destroy(pomgpu_group_t* g);
+int pomgpu_nccl_unique_id(void* out128);
+int pomgpu_group_connect_nccl(pomgpu_group_t* g, const void* id128, int rank, int world);
+/* host transport (CPU tests): called with the packed south / north send buffers and the
+ * receive buffers to fill; n_* = doubles per direction (0 = no neighbour on that side) */
+typedef int (*pomgpu_halo_cb)(void* user, const double* send_s, double* recv_s, long n_s,
+                              const double* send_n, double* recv_n, long n_n);
+void pomgpu_group_set_transport(pomgpu_group_t* g, pomgpu_halo_cb cb, void* user);
+int pomgpu_group_step(pomgpu_group_t* g, int iint, double time, double ramp);
+/* the two solver.f routines `initialize` calls (initialize.f:416,425,502), on a group */
+int pomgpu_group_dens(pomgpu_group_t* g, const char* si, const char* ti, const char* rhoo);
+int pomgpu_group_baropg(pomgpu_group_t* g);
+double pomgpu_group_check_velocity(pomgpu_group_t* g); /* max over this process's strips */
+long pomgpu_group_exchanges(pomgpu_group_t* g, long* fields, int reset); /* halo messages so far */
 
 /* ---- the reference's subroutines on the resident state (same names) ---------
  * advance.f */
