@@ -66,32 +66,55 @@ def cflmin(f, grav, small):
     return float(cfl[cfl > 0].min())
 
 
-def make_state(im, jm, kb, delta=8000.0, wind=True, noise=True, island=False, **nml):
+def _row_noise(kind, tag, im, rows, nk):
+    """Symmetry-breaking noise that depends only on (seed, field tag, GLOBAL row j): a strip
+    of the domain generates exactly the values the whole-domain state holds in its rows."""
+    out = np.empty((im, len(rows), nk), order="F")
+    for n, j in enumerate(rows):
+        rng = np.random.default_rng([SEED, tag, int(j)])
+        out[:, n, :] = rng.standard_normal((im, nk)) if kind == "normal" else rng.uniform(-1, 1, (im, nk))
+    return out
+
+
+def make_state(im, jm, kb, delta=8000.0, wind=True, noise=True, island=False, rows=None, **nml):
     """Everything `initialize` sets that does not need dens/baropg.  Arrays are
-    Fortran-ordered (i fastest) float64 with shapes (im,jm[,kb])."""
+    Fortran-ordered (i fastest) float64 with shapes (im,jm[,kb]).
+
+    rows=(j_lo, j_hi) (global, 1-based, inclusive) generates only that band of rows of the
+    (im, jm, kb) domain -- what one rank of distribute_mpi (pom/parallel_mpi.f:76-119) holds --
+    without ever materialising the global arrays; every value equals the whole-domain one."""
     c = default_consts(**nml)
     F = lambda *shp: np.zeros(shp, order="F")
     f = {}
     z, zz, dz, dzz = sigma_levels(kb)
     f.update(z=z, zz=zz, dz=dz, dzz=dzz)
+    jlo, jhi = (1, jm) if rows is None else (int(rows[0]), int(rows[1]))
+    assert 1 <= jlo <= jhi <= jm
+    jmg, jrows = jm, np.arange(jlo, jhi + 1)
+    # one extra row to the south (dvm, arv look at j-1); dropped again before returning
+    pad = 1 if jlo > 1 else 0
+    jall = np.arange(jlo - pad, jhi + 1)
+    jm = len(jall)                        # local extent from here on (global: jmg)
 
     i1 = np.arange(1, im + 1, dtype=np.float64)[:, None]
-    j1 = np.arange(1, jm + 1, dtype=np.float64)[None, :]
+    j1 = jall.astype(np.float64)[None, :]
     dx = F(im, jm); dy = F(im, jm)
     dx[...] = delta - delta * np.sin(np.pi * i1 / im) / 2.0
-    dy[...] = delta - delta * np.sin(np.pi * j1 / jm) / 2.0
+    dy[...] = delta - delta * np.sin(np.pi * j1 / jmg) / 2.0
+    dyg = delta - delta * np.sin(np.pi * np.arange(1, jmg + 1, dtype=np.float64) / jmg) / 2.0
     x = np.cumsum(dx[:, 0]) - 0.5 * dx[:, 0]
-    y = np.cumsum(dy[0, :]) - 0.5 * dy[0, :]
-    xc, yc = x[im // 2], y[jm // 2]
+    yg = np.cumsum(dyg) - 0.5 * dyg
+    y = yg[jall - 1]
+    xc, yc = x[im // 2], yg[jmg // 2]
     ra = 25.0e3 * (im / 65.0)
     r2 = (x[:, None] - xc) ** 2 + (y[None, :] - yc) ** 2
     h = F(im, jm)
     h[...] = 4500.0 * (1.0 - 0.9 * np.exp(-r2 / ra ** 2))
-    h[:, 0] = 1.0
-    h[:, jm - 1] = 1.0            # closed channel walls
+    h[:, jall == 1] = 1.0
+    h[:, jall == jmg] = 1.0       # closed channel walls
     if island:                     # a dry patch so that interior masks are exercised
-        ic, jc = im // 3, (2 * jm) // 3
-        h[ic - 1:ic + 2, jc - 1:jc + 2] = 1.0
+        ic, jc = im // 3, (2 * jmg) // 3
+        h[ic - 1:ic + 2, (jall >= jc) & (jall <= jc + 2)] = 1.0
     fsm = F(im, jm); fsm[...] = np.where(h > 1.0, 1.0, 0.0)
     dum = fsm.copy(order="F"); dvm = fsm.copy(order="F")
     # io_pnetcdf.F:2243-2254
@@ -103,10 +126,10 @@ def make_state(im, jm, kb, delta=8000.0, wind=True, noise=True, island=False, **
     aru[1:, 1:] = 0.25 * (dx[1:, 1:] + dx[:-1, 1:]) * (dy[1:, 1:] + dy[:-1, 1:])   # :366-371
     arv[1:, 1:] = 0.25 * (dx[1:, 1:] + dx[1:, :-1]) * (dy[1:, 1:] + dy[1:, :-1])
     aru[0, :] = aru[1, :]; arv[0, :] = arv[1, :]               # :375-378
-    aru[:, 0] = aru[:, 1]; arv[:, 0] = arv[:, 1]               # :380-383
+    if jall[0] == 1:
+        aru[:, 0] = aru[:, 1]; arv[:, 0] = arv[:, 1]           # :380-383
     f.update(dx=dx, dy=dy, h=h, fsm=fsm, dum=dum, dvm=dvm, cor=cor, art=art, aru=aru, arv=arv)
 
-    rng = np.random.default_rng(SEED)
     tb = F(im, jm, kb); sb = F(im, jm, kb)
     tb[...] = 5.0 + 15.0 * np.exp(zz[None, None, :] * h[:, :, None] / 1000.0)
     sb[...] = 35.0
@@ -116,16 +139,16 @@ def make_state(im, jm, kb, delta=8000.0, wind=True, noise=True, island=False, **
     uab = F(im, jm); uab[...] = 0.2 * dum
     vab = F(im, jm)
     if noise:   # both branches of every upwind / abs() test must run
-        tb[...] += 1.0e-2 * rng.standard_normal((im, jm, kb)) * fsm[:, :, None]
-        ub[:, :, :kb - 1] += 1.0e-2 * rng.uniform(-1, 1, (im, jm, kb - 1)) * dum[:, :, None]
-        vb[:, :, :kb - 1] += 1.0e-2 * rng.uniform(-1, 1, (im, jm, kb - 1)) * dvm[:, :, None]
+        tb[...] += 1.0e-2 * _row_noise("normal", 1, im, jall, kb) * fsm[:, :, None]
+        ub[:, :, :kb - 1] += 1.0e-2 * _row_noise("uniform", 2, im, jall, kb - 1) * dum[:, :, None]
+        vb[:, :, :kb - 1] += 1.0e-2 * _row_noise("uniform", 3, im, jall, kb - 1) * dvm[:, :, None]
     f.update(tb=tb, sb=sb, tclim=tclim, sclim=sclim, ub=ub, vb=vb, uab=uab, vab=vab)
     for n in "elb etb e_atmos vfluxb vfluxf wusurf wvsurf wtsurf wssurf swrad".split():
         f[n] = F(im, jm)                                         # initialize_arrays :270-294
     if wind:
-        f["wusurf"][...] = -0.5e-4 * (1.0 + 0.5 * np.sin(2 * np.pi * j1 / jm)) * fsm
+        f["wusurf"][...] = -0.5e-4 * (1.0 + 0.5 * np.sin(2 * np.pi * j1 / jmg)) * fsm
         f["wvsurf"][...] = 0.2e-4 * np.cos(2 * np.pi * i1 / im) * fsm
-        f["wtsurf"][...] = 2.0e-5 * np.sin(2 * np.pi * i1 / im) * np.cos(np.pi * j1 / jm) * fsm
+        f["wtsurf"][...] = 2.0e-5 * np.sin(2 * np.pi * i1 / im) * np.cos(np.pi * j1 / jmg) * fsm
         f["swrad"][...] = -1.0e-5 * fsm
     f["tsurf"] = tb[:, :, 0].copy(order="F")                     # initialize.f:441-442
     f["ssurf"] = sb[:, :, 0].copy(order="F")
@@ -134,7 +157,8 @@ def make_state(im, jm, kb, delta=8000.0, wind=True, noise=True, island=False, **
         e = np.zeros((jm, kb), order="F"); w_ = np.zeros((jm, kb), order="F")
         n_ = np.zeros((im, kb), order="F"); s_ = np.zeros((im, kb), order="F")
         e[:, :km1] = src[im - 1, :, :km1]; w_[:, :km1] = src[0, :, :km1]
-        n_[:, :km1] = src[:, jm - 1, :km1]; s_[:, :km1] = src[:, 0, :km1]
+        if jall[-1] == jmg: n_[:, :km1] = src[:, jm - 1, :km1]      # only the strips that hold the
+        if jall[0] == 1: s_[:, :km1] = src[:, 0, :km1]             # north / south edge use these
         f[nm + "be"], f[nm + "bw"], f[nm + "bn"], f[nm + "bs"] = e, w_, n_, s_
     f["uabw"] = uab[1, :].copy(); f["uabe"] = uab[im - 2, :].copy()
     for n in ("ele", "elw", "vabe", "vabw"): f[n] = np.zeros(jm)
@@ -165,7 +189,18 @@ def make_state(im, jm, kb, delta=8000.0, wind=True, noise=True, island=False, **
         f[n] = F(im, jm, kb)
     cmin = cflmin(f, c["grav"], c["small"])
     assert cmin >= c["dte"], f"dte={c['dte']} violates CFL ({cmin:.3f})"
-    return {"dims": (im, jm, kb), "consts": c, "fields": f, "cflmin": cmin}
+    if pad:                               # drop the helper row south of the band
+        for n, a in f.items():
+            if n in ("z", "zz", "dz", "dzz") or n[1:] in ("bn", "bs") or n in ("eln", "els", "vabn", "vabs", "uabn", "uabs"):
+                continue
+            if a.ndim >= 2 and a.shape[0] == im and a.shape[1] == jm:
+                f[n] = np.asfortranarray(a[:, pad:])
+            elif a.shape[0] == jm:
+                f[n] = np.asfortranarray(a[pad:])
+            else:
+                raise AssertionError((n, a.shape))
+    return {"dims": (im, len(jrows), kb), "global_jm": jmg, "rows": (jlo, jhi), "consts": c, "fields": f,
+            "cflmin": cmin}
 
 
 def finish_init(state, solver):

@@ -86,3 +86,28 @@ def test_rest_state_at_scale():
         g.step(i)
     for n in ("u", "v", "ua", "el", "w"):
         assert np.abs(g.get(n)).max() <= 1e-10, n
+
+
+@pytest.mark.parametrize("nstrips,ghost", [(2, 4), (3, 2)])
+def test_strips_on_one_gpu_equal_single_domain_bitwise(nstrips, ghost):
+    """The j-strip decomposition (csrc/pom_halo.cu) with all strips on this GPU: pack kernels,
+    device-to-device halo copies and the validity bookkeeping; must reproduce the single-domain
+    run bitwise (the NCCL transport between processes is checked by scripts/strip_check.py)."""
+    from extpom_b200 import strips as sp
+    from extpom_b200.pomgpu import PomGpu, PomGroup
+    from tests.common import F2, F3
+    dims, nstep = (64, 90, 12), 5
+    fac = lambda a, b, c, strip=None, ghost=0: PomGpu(a, b, c, strip=strip, ghost=ghost)
+    _, whole = syn.seamount(*dims, lambda a, b, c: PomGpu(a, b, c), island=True)
+    strips = [sp.make_strip(*dims, own, ghost, fac, island=True)[1] for own in sp.partition(dims[1], nstrips)]
+    grp = PomGroup(strips)
+    sp.finish_init_group(None, grp)
+    for i in range(1, nstep + 1):
+        whole.step(i)
+        grp.step(i)
+    for n in F3 + F2:
+        a, b = whole.get(n), grp.gather(n)
+        if n in ("t", "tb", "s", "sb"):
+            a, b = a[:, :, :-1], b[:, :, :-1]
+        assert np.array_equal(a, b), n
+    assert whole.check_velocity() == grp.check_velocity()

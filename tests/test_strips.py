@@ -1,0 +1,137 @@
+"""CPU tests of the j-strip decomposition (csrc/pom_halo.cu; replaces distribute_mpi and
+exchange2d/3d_mpi, pom/parallel_mpi.f:34-122,154-351) on the host-emulated build.
+
+With all neighbours -1 (n_proc=1) every reference exchange is a no-op, so the single-domain
+run is the canonical answer and an N-strip run must reproduce it; here
+bitwise, because every kernel computes with global-index semantics."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from extpom_b200 import strips as sp
+from extpom_b200 import synthetic as syn
+from extpom_b200.pomgpu import PomGpu, PomGroup
+from tests import emu
+from tests.common import F2, F3
+
+
+def _factory(im, jm, kb, strip=None, ghost=0):
+    return PomGpu(im, jm, kb, strip=strip, ghost=ghost, _libpath=emu.build_emu())
+
+
+def _whole(dims, nstep, **kw):
+    st, g = syn.seamount(*dims, lambda a, b, c: _factory(a, b, c), **kw)
+    for i in range(1, nstep + 1):
+        g.step(i)
+    return g
+
+
+def _group(dims, nstrips, ghost, **kw):
+    im, jm, kb = dims
+    strips = []
+    for own in sp.partition(jm, nstrips):
+        st, g = sp.make_strip(im, jm, kb, own, ghost, _factory, **kw)
+        strips.append(g)
+    grp = PomGroup(strips)
+    sp.finish_init_group(None, grp)
+    return grp
+
+
+def _assert_same(whole, grp, names=F3 + F2):
+    for n in names:
+        a, b = whole.get(n), grp.gather(n)
+        assert a.shape == b.shape, (n, a.shape, b.shape)
+        if n in ("t", "tb", "s", "sb"):
+            a, b = a[:, :, :-1], b[:, :, :-1]
+        assert np.array_equal(a, b), (n, float(np.abs(a - b).max()))
+
+
+def test_partition_covers_uneven_rows():
+    rows = sp.partition(4094 + 2, 8)
+    assert rows[0][0] == 1 and rows[-1][1] == 4096
+    assert all(rows[r + 1][0] == rows[r][1] + 1 for r in range(7))
+    assert max(b - a for a, b in rows) - min(b - a for a, b in rows) <= 1
+
+
+@pytest.mark.parametrize("nstrips,ghost", [(2, 2), (2, 4), (3, 3), (4, 4)])
+def test_strips_equal_single_domain_bitwise(nstrips, ghost):
+    dims, nstep = (22, 41, 8), 6
+    whole = _whole(dims, nstep, island=True)
+    grp = _group(dims, nstrips, ghost, island=True)
+    for i in range(1, nstep + 1):
+        grp.step(i)
+    _assert_same(whole, grp)
+    assert whole.check_velocity() == grp.check_velocity()
+    nex, nfields = grp.exchanges()
+    # the reference does 29 3-D + 340 2-D exchanges per step
+    print(f"{nstrips} strips ghost {ghost}: {nex / nstep:.1f} batched exchanges/step, {nfields / nstep:.0f} field-rows sets")
+    assert 0 < nex / nstep < 369
+
+
+@pytest.mark.parametrize("kw", [{"nadv": 1}, {"mode": 4}, {"nbct": 2, "ntp": 3}])
+def test_strips_namelist_variants(kw):
+    dims, nstep = (20, 30, 7), 4
+    whole = _whole(dims, nstep, **kw)
+    grp = _group(dims, 2, 3, **kw)
+    for i in range(1, nstep + 1):
+        grp.step(i)
+    _assert_same(whole, grp)
+
+
+def test_strip_too_thin_is_rejected():
+    im, jm, kb = 20, 24, 7
+    strips = [sp.make_strip(im, jm, kb, own, 4, _factory)[1] for own in sp.partition(jm, 4)]
+    with pytest.raises(Exception):
+        PomGroup(strips)          # 6 owned rows < ghost + 4
+
+
+def test_seam_without_transport_sets_error_status():
+    im, jm, kb = 20, 30, 7
+    st, g = sp.make_strip(im, jm, kb, (1, 15), 3, _factory)
+    grp = PomGroup([g])
+    with pytest.raises(Exception):
+        for i in range(1, 4):
+            grp.step(i)
+    assert g.getc("error_status") == 1
+
+
+# ---- two processes over gloo: the host-callback transport ---------------------------------
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, dims, nstep, ghost, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        im, jm, kb = dims
+        own = sp.partition(jm, world)[rank]
+        st, g = sp.make_strip(im, jm, kb, own, ghost, _factory, island=True)
+        grp = PomGroup([g])
+        grp.set_transport(sp.gloo_transport(dist, rank, world))
+        sp.finish_init_group(None, grp)
+        for i in range(1, nstep + 1):
+            grp.step(i)
+        np.savez(os.path.join(out, f"rank{rank}.npz"), vamax=grp.check_velocity(),
+                 **{n: grp.gather(n) for n in F3 + F2})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_processes_gloo_equal_single_domain(tmp_path):
+    import torch.multiprocessing as mp
+    dims, nstep, ghost, world = (20, 36, 7), 4, 3, 2
+    mp.spawn(_worker, args=(world, _free_port(), dims, nstep, ghost, str(tmp_path)), nprocs=world, join=True)
+    whole = _whole(dims, nstep, island=True)
+    parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    for n in F3 + F2:
+        a = whole.get(n)
+        b = np.concatenate([p[n] for p in parts], axis=1)
+        if n in ("t", "tb", "s", "sb"):
+            a, b = a[:, :, :-1], b[:, :, :-1]
+        assert np.array_equal(a, b), n
+    assert max(float(p["vamax"]) for p in parts) == whole.check_velocity()
