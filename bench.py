@@ -140,6 +140,9 @@ def main():
 
     dist = None
     if world > 1:
+        # NCCL_DEBUG=VERSION (set on some boxes) makes NCCL print to stdout; stdout carries ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

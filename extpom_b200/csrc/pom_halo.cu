@@ -132,9 +132,12 @@ Group* group_create(int n, Ctx** ctxs) {
 
 void group_destroy(Group* G) {
   if (!G) return;
-  for (int r = 0; r < G->n; ++r)
+  for (int r = 0; r < G->n; ++r) {
+    dev_sync(G->c[r]);
     for (int b = 0; b < 4; ++b)
       if (G->buf[r][b]) dev_free(G->c[r], G->buf[r][b]);
+    G->c[r]->stream = G->c[r]->own_stream;
+  }
 #ifndef POMGPU_EMU
   if (G->nccl) g_nccl.CommDestroy(G->nccl);
 #endif

@@ -39,23 +39,22 @@ struct UvAdjustK : KBase {
 struct VertvlK : KBase {
   POM_KINFO("vertvl", 2, 1, 8, 0)
   using KBase::KBase;
-  POM_HD double xf(int i, int j, int k) const {   // :1984-1985
-    return .25*(dy(i,j)+dy(i-1,j))*(dt(i,j)+dt(i-1,j))*u(i,j,k);
-  }
-  POM_HD double yf(int i, int j, int k) const {   // :1993-1994
-    return .25*(dx(i,j)+dx(i,j-1))*(dt(i,j)+dt(i,j-1))*v(i,j,k);
-  }
   POM_HD void operator()(int i, int j) const {
     POM_DIMS;
     const double m = fsm(i,j);
     if (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1) {
       double wk=0.5*(vfluxb(i,j)+vfluxf(i,j));                          // :2004
-      const double dxy=dx(i,j)*dy(i,j);
+      RDiv ddxy; ddxy.set(dx(i,j)*dy(i,j));
       const double de=(etf(i,j)-etb(i,j))/dti2;
+      // .25*(dy+dy)*(dt+dt) of the four faces (:1984-1985,1993-1994), constant along k
+      const double cW=.25*(dy(i,j)+dy(i-1,j))*(dt(i,j)+dt(i-1,j));
+      const double cE=.25*(dy(i+1,j)+dy(i,j))*(dt(i+1,j)+dt(i,j));
+      const double cS=.25*(dx(i,j)+dx(i,j-1))*(dt(i,j)+dt(i,j-1));
+      const double cN=.25*(dx(i,j+1)+dx(i,j))*(dt(i,j+1)+dt(i,j));
       for (int k = 1; k <= kbm1; ++k) {
         PF3(p.u,i,j,k+2); PF3(p.v,i,j,k+2); PF3(p.v,i,j+1,k+2);
         w(i,j,k)=wk*m;
-        wk=wk+dz(k)*((xf(i+1,j,k)-xf(i,j,k)+yf(i,j+1,k)-yf(i,j,k))/dxy+de);   // :2011-2015
+        wk=wk+dz(k)*(ddxy(cE*u(i+1,j,k)-cW*u(i,j,k)+cN*v(i,j+1,k)-cS*v(i,j,k))+de);   // :2011-2015
       }
       w(i,j,kb)=wk;
     } else {
@@ -983,28 +982,35 @@ struct EndStep2dK : KBase {
 struct RealvertvlK : KBase {
   POM_KINFO("realvertvl", 3, 1, 7, 0)
   using KBase::KBase;
-  POM_HD double tp(int i, int j, int k) const { return zz(k)*dt(i,j)+et(i,j); }   // :2036
-  POM_HD double wri(int i, int j, int k) const {                        // :2041-2050
-    double dxr=2.0/(dx(i+1,j)+dx(i,j));
-    double dxl=2.0/(dx(i,j)+dx(i-1,j));
-    double dyt=2.0/(dy(i,j+1)+dy(i,j));
-    double dyb=2.0/(dy(i,j)+dy(i,j-1));
-    return 0.5*(w(i,j,k)+w(i,j,k+1))+0.5*
-           (u(i+1,j,k)*(tp(i+1,j,k)-tp(i,j,k))*dxr+
-            u(i,j,k)*(tp(i,j,k)-tp(i-1,j,k))*dxl+
-            v(i,j+1,k)*(tp(i,j+1,k)-tp(i,j,k))*dyt+
-            v(i,j,k)*(tp(i,j,k)-tp(i,j-1,k))*dyb)
-           +(1.0+zz(k))*(etf(i,j)-etb(i,j))/dti2;
-  }
   POM_HD void operator()(int i, int j) const {
     POM_DIMS;
     // edge copies S,N then W,E (:2057-2060) = value at the index clamped inside
-    int ic = i < 2 ? 2 : (i > imm1 ? imm1 : i);
-    int jc = j < 2 ? 2 : (j > jmm1 ? jmm1 : j);
+    const int ic = i < 2 ? 2 : (i > imm1 ? imm1 : i);
+    const int jc = j < 2 ? 2 : (j > jmm1 ? jmm1 : j);
     const double m=fsm(i,j);
+    // the 2-D operands of the column, hoisted out of the k loop (:2036,2041-2044)
+    const double dxr=2.0/(dx(ic+1,jc)+dx(ic,jc));
+    const double dxl=2.0/(dx(ic,jc)+dx(ic-1,jc));
+    const double dyt=2.0/(dy(ic,jc+1)+dy(ic,jc));
+    const double dyb=2.0/(dy(ic,jc)+dy(ic,jc-1));
+    const double dt0=dt(ic,jc), dtE=dt(ic+1,jc), dtW=dt(ic-1,jc), dtN=dt(ic,jc+1), dtS=dt(ic,jc-1);
+    const double et0=et(ic,jc), etE=et(ic+1,jc), etW=et(ic-1,jc), etN=et(ic,jc+1), etS=et(ic,jc-1);
+    const double de=etf(ic,jc)-etb(ic,jc);
+    RDiv ddti2; ddti2.set(dti2);
+    double w0=w(ic,jc,1);
     for (int k = 1; k <= kbm1; ++k) {
       PF3(p.w,ic,jc,k+3); PF3(p.u,ic,jc,k+2); PF3(p.v,ic,jc,k+2); PF3(p.v,ic,jc+1,k+2);
-      wr(i,j,k)=m*wri(ic,jc,k);                                         // :2063
+      const double zk=zz(k);
+      const double tp0=zk*dt0+et0;                                      // :2036
+      const double w1=w(ic,jc,k+1);
+      const double r=0.5*(w0+w1)+0.5*
+           (u(ic+1,jc,k)*((zk*dtE+etE)-tp0)*dxr+
+            u(ic,jc,k)*(tp0-(zk*dtW+etW))*dxl+
+            v(ic,jc+1,k)*((zk*dtN+etN)-tp0)*dyt+
+            v(ic,jc,k)*(tp0-(zk*dtS+etS))*dyb)
+           +ddti2((1.0+zk)*de);                                         // :2045-2050
+      wr(i,j,k)=m*r;                                                    // :2063
+      w0=w1;
     }
     wr(i,j,kb)=0.;
   }

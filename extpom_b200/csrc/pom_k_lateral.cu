@@ -191,16 +191,19 @@ struct SmagK : KBase {
     POM_DIMS;
     const bool interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
     double sa = 0.;
+    RDiv ddx, ddy;
+    double hdd = 0.;
+    if (interior) { ddx.set(dx(i,j)); ddy.set(dy(i,j)); hdd=horcon*dx(i,j)*dy(i,j); }
     for (int k = 1; k <= kbm1; ++k) {
       double a;
       PF3(p.u,i,j,k+2); PF3(p.v,i,j,k+2);
       if (interior) {
         PF3(p.u,i,j+1,k+2); PF3(p.u,i,j-1,k+2); PF3(p.v,i,j+1,k+2);
-        double a1=(u(i+1,j,k)-u(i,j,k))/dx(i,j);
-        double a2=(v(i,j+1,k)-v(i,j,k))/dy(i,j);
-        double a3=.25*(u(i,j+1,k)+u(i+1,j+1,k)-u(i,j-1,k)-u(i+1,j-1,k))/dy(i,j)
-                 +.25*(v(i+1,j,k)+v(i+1,j+1,k)-v(i-1,j,k)-v(i-1,j+1,k))/dx(i,j);
-        a=horcon*dx(i,j)*dy(i,j)*sqrt(a1*a1+a2*a2+.5*(a3*a3));
+        double a1=ddx(u(i+1,j,k)-u(i,j,k));
+        double a2=ddy(v(i,j+1,k)-v(i,j,k));
+        double a3=ddy(.25*(u(i,j+1,k)+u(i+1,j+1,k)-u(i,j-1,k)-u(i+1,j-1,k)))
+                 +ddx(.25*(v(i+1,j,k)+v(i+1,j+1,k)-v(i-1,j,k)-v(i-1,j+1,k)));
+        a=hdd*sqrt(a1*a1+a2*a2+.5*(a3*a3));
         aam(i,j,k)=a;
       } else {
         a=aam(i,j,k);

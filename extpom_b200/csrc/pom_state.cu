@@ -70,7 +70,7 @@ size_t field_elems(const Ctx* c, const FieldInfo* f) {
 
 // ---- backend -----------------------------------------------------------------
 #ifdef POMGPU_EMU
-int dev_init(Ctx* c) { c->stream = nullptr; c->d_red = (double*)calloc(4096, 8); c->h_red = (double*)calloc(4096, 8); return 0; }
+int dev_init(Ctx* c) { c->stream = nullptr; c->own_stream = nullptr; c->d_red = (double*)calloc(4096, 8); c->h_red = (double*)calloc(4096, 8); return 0; }
 int dev_alloc(Ctx*, double** p, size_t n) { *p = (double*)calloc(n ? n : 1, sizeof(double)); return *p ? 0 : 1; }
 void dev_free(Ctx*, double* p) { free(p); }
 int dev_h2d(Ctx*, double* d, const double* s, size_t n) { memcpy(d, s, n * 8); return 0; }
@@ -97,6 +97,7 @@ int dev_init(Ctx* c) {
   cudaStream_t s;
   if (cuda_fail(c, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
   c->stream = (void*)s;
+  c->own_stream = (void*)s;
   if (cuda_fail(c, cudaMalloc((void**)&c->d_red, 4096 * 8), "cudaMalloc")) return 1;
   if (cuda_fail(c, cudaMallocHost((void**)&c->h_red, 4096 * 8), "cudaMallocHost")) return 1;
   return 0;
@@ -215,7 +216,7 @@ void ctx_destroy(Ctx* c) {
   free(c->d_red); free(c->h_red);
 #else
   cudaFree(c->d_red); cudaFreeHost(c->h_red);
-  cudaStreamDestroy((cudaStream_t)c->stream);
+  cudaStreamDestroy((cudaStream_t)c->own_stream);
 #endif
   free(c);
 }
