@@ -4,9 +4,19 @@
 // arrays so no a/c/ee/gg 3-D temporaries (solver.f:1224-1230,1552-1554,
 // 1692-1693) ever reach HBM.  Expression order follows the Fortran.
 #include "pom_core.h"
+#include "pom_tma.h"
 #include "pom_names.h"
 
 #define KMAX 64
+#ifndef POM_THOMAS_SMEM
+#define POM_THOMAS_SMEM 0
+#endif
+#ifndef POM_PFD
+#define POM_PFD 2
+#endif
+#ifndef POM_THOMAS_BY
+#define POM_THOMAS_BY 4
+#endif
 
 namespace pom {
 
@@ -414,17 +424,22 @@ struct AdvT2K : KBase {
   double* ff_;
   AdvT2K(const Ctx* x, const double* fb, const double* f, const double* fc, double* ff)
       : KBase(x), fb_(fb), f_(f), fc_(fc), ff_(ff) {}
-  static constexpr int NV = 4, HL = 0, HR = 1, HB = 0, HT = 1, TY = 16, MINB = 1;
+  static constexpr int NV = 4, HL = 0, HR = 1, HB = 0, HT = 1, TY = 16;
+  // operands staged by the TMA: box = thread tile + one column W and one row S (34 x 17)
+  static constexpr int NF = 6, NS = 4, OHL = 1, OHR = 0, OHB = 1, OHT = 0, BW = 34, BH = 17, NK = 0;
+  static constexpr bool UP = true;
+  enum { FB, FC, AAM, U, V, W };
   enum { XF, YF, XD, YD };
+  POM_HD void fields(const double** b) const { b[FB] = fb_; b[FC] = fc_; b[AAM] = p.aam; b[U] = p.u; b[V] = p.v; b[W] = p.w; }
   struct State {
     double cx, cy, hx, hy, dumc, dvmc, dys, dxs;   // .25*(dy+dy)*(dt+dt), (h+h), masks, (dy+dy(i-1)), (dx+dx(j-1))
     RDiv ddxs, ddys, def;                          // (dx+dx(i-1)), (dy+dy(j-1)), (h+etf)*art
-    double eb, ar, m, zk;                          // (h+etb)*art, art, fsm, zflux(k)
+    double eb, ar, m, zk, fb0;                     // (h+etb)*art, art, fsm, zflux(k), fb(i,j,k)
     bool fxa, fya, interior;
   };
-  struct Regs { double fb0, fbW, fbS, fc0, fcW, fcS, u0, v0, a0, aW, aS, w1, fb1; };
   POM_HD int k0() const { return 1; }
   POM_HD int k1() const { return g.kb - 1; }
+  POM_HD int kl1() const { return g.kb - 1; }
   POM_HD void pre(int i, int j, bool inside, bool out, State& s) const {
     POM_DIMS;
     const int jlo = g.joff + 1;
@@ -449,35 +464,29 @@ struct AdvT2K : KBase {
       s.zk = w(i,j,1)*A3(f_,i,j,1)*s.ar;                                // :648 (itera==1)
     }
   }
-  POM_HD void fetch(int i, int j, int k, const State& s, Regs& r) const {
+  template <class Op>
+  POM_HD void stage(int i, int j, int k, State& s, const Op& o, double* v) const {
     if (!(s.fxa || s.fya || s.interior)) return;
-    const int o = POM_I3(i,j,k), im = g.im;
-    r.fb0 = POM_LDG(fb_+o); r.fc0 = POM_LDG(fc_+o); r.a0 = POM_LDG(p.aam+o);
-    if (k + 1 <= g.kb - 1) {
-      const int n = o + g.n2;
-      POM_PREFETCH(fb_+n); POM_PREFETCH(fc_+n); POM_PREFETCH(p.aam+n); POM_PREFETCH(p.u+n); POM_PREFETCH(p.v+n);
-      POM_PREFETCH(p.w+n);
-    }
-    if (s.fxa) { r.fbW = POM_LDG(fb_+o-1); r.fcW = POM_LDG(fc_+o-1); r.aW = POM_LDG(p.aam+o-1); r.u0 = POM_LDG(p.u+o); }
-    if (s.fya) { r.fbS = POM_LDG(fb_+o-im); r.fcS = POM_LDG(fc_+o-im); r.aS = POM_LDG(p.aam+o-im); r.v0 = POM_LDG(p.v+o); }
-    if (s.interior && k + 1 <= g.kb - 1) { r.w1 = POM_LDG(p.w+o+g.n2); r.fb1 = POM_LDG(fb_+o+g.n2); }
-  }
-  POM_HD void stage(int i, int j, int k, State& s, const Regs& r, double* v) const {
-    const double fd0=r.fb0-r.fc0;                                       // fb-fclim (:691)
+    const double fb0=o(FB,0,0), a0=o(AAM,0,0);
+    const double fd0=fb0-o(FC,0,0);                                     // fb-fclim (:691)
+    s.fb0=fb0;
     if (s.fxa) {
-      const double xm=s.cx*r.u0;                                        // :605-606
-      v[XF]=0.5*((xm+fabs(xm))*r.fbW+(xm-fabs(xm))*r.fb0);              // :631-635
-      const double xd=0.5*(r.a0+r.aW);                                  // :696
-      v[XD]=s.ddxs(-xd*s.hx*tprni*(fd0-(r.fbW-r.fcW))*s.dumc*s.dys*0.5);   // :705-707
+      const double fbW=o(FB,-1,0);
+      const double xm=s.cx*o(U,0,0);                                    // :605-606
+      v[XF]=0.5*((xm+fabs(xm))*fbW+(xm-fabs(xm))*fb0);                  // :631-635
+      const double xd=0.5*(a0+o(AAM,-1,0));                             // :696
+      v[XD]=s.ddxs(-xd*s.hx*tprni*(fd0-(fbW-o(FC,-1,0)))*s.dumc*s.dys*0.5);   // :705-707
     }
     if (s.fya) {
-      const double ym=s.cy*r.v0;                                        // :612-613
-      v[YF]=0.5*((ym+fabs(ym))*r.fbS+(ym-fabs(ym))*r.fb0);              // :637-641
-      const double yd=0.5*(r.a0+r.aS);                                  // :697
-      v[YD]=s.ddys(-yd*s.hy*tprni*(fd0-(r.fbS-r.fcS))*s.dvmc*s.dxs*0.5);   // :708-710
+      const double fbS=o(FB,0,-1);
+      const double ym=s.cy*o(V,0,0);                                    // :612-613
+      v[YF]=0.5*((ym+fabs(ym))*fbS+(ym-fabs(ym))*fb0);                  // :637-641
+      const double yd=0.5*(a0+o(AAM,0,-1));                             // :697
+      v[YD]=s.ddys(-yd*s.hy*tprni*(fd0-(fbS-o(FC,0,-1)))*s.dvmc*s.dxs*0.5);   // :708-710
     }
   }
-  POM_HD void combine(int i, int j, int k, State& s, const Regs& r, const Tile& tl) const {
+  template <class Op>
+  POM_HD void combine(int i, int j, int k, State& s, const Op& o, const Tile2& tl) const {
     if (!s.interior) {
       // ff is not assigned here by the reference (bcond(4) sets it afterwards); only the
       // smol_adif mask applies
@@ -486,14 +495,15 @@ struct AdvT2K : KBase {
     }
     double zk1 = 0.;                                                    // zflux(k+1); :651 at kb
     if (k + 1 <= g.kb - 1) {
-      zk1=0.5*((r.w1+fabs(r.w1))*r.fb1+(r.w1-fabs(r.w1))*r.fb0);        // :656-660
+      const double w1=o.up(W), fb1=o.up(FB);
+      zk1=0.5*((w1+fabs(w1))*fb1+(w1-fabs(w1))*s.fb0);                  // :656-660
       zk1=zk1*s.ar;                                                     // :661
     }
     double q=tl(XF,1,0)-tl(XF,0,0)+tl(YF,0,1)-tl(YF,0,0)+(s.zk-zk1)/dz(k);   // :670-672
-    q=s.def(r.fb0*s.eb-dti2*q);                                         // :673-674
+    q=s.def(s.fb0*s.eb-dti2*q);                                         // :673-674
     q=q*s.m;                                                            // smol_adif :1899
     q=q-s.def(dti2*(tl(XD,1,0)-tl(XD,0,0)+tl(YD,0,1)-tl(YD,0,0)));      // :721-723
-    A3(ff_,i,j,k)=q;
+    POM_STCS(&A3(ff_,i,j,k),q);
     s.zk=zk1;
   }
   POM_HD void post(int i, int j, State& s) const {
@@ -546,59 +556,84 @@ struct ProftK : KBase {
   double* f_;
   const double *wfsurf_, *fsurf_;
   int nbc;
+  double rn, ad1n, ad2n;   // Jerlov water type ntp (:1568-1575)
   ProftK(const Ctx* x, double* f, const double* wf, const double* fs, int nb)
-      : KBase(x), f_(f), wfsurf_(wf), fsurf_(fs), nbc(nb) {}
+      : KBase(x), f_(f), wfsurf_(wf), fsurf_(fs), nbc(nb) {
+    const double r[5] = {.58, .62, .67, .77, .78};
+    const double ad1[5] = {.35, .60, 1.0, 1.5, 1.4};
+    const double ad2[5] = {23., 20., 17., 14., 7.9};
+    const int n = (x->c.ntp >= 1 && x->c.ntp <= 5) ? x->c.ntp - 1 : 1;
+    rn = r[n]; ad1n = ad1[n]; ad2n = ad2[n];
+  }
+  // short-wave penetration rad(k) (:1604-1615); rad(kb)=0
+  POM_HD double rad(int k, double dh, double sw0) const {
+    if (k >= g.kb) return 0.;
+    return sw0*(rn*exp(z(k)*dh/ad1n)+(1.-rn)*exp(z(k)*dh/ad2n));
+  }
+#if POM_THOMAS_SMEM
+  POM_HD void operator()(int i, int j, const ColMem& cm) const {
+#define EE(k) cm(0, k)
+#define GG(k) cm(1, k)
+#else
   POM_HD void operator()(int i, int j) const {
+    double ee_[KMAX], gg_[KMAX];
+#define EE(k) ee_[k]
+#define GG(k) gg_[k]
+#endif
     POM_DIMS;
-    double ee[KMAX], gg[KMAX], rad[KMAX];
     const double dh=h(i,j)+etf(i,j);                                    // :1580
     const bool pen = (nbc == 2 || nbc == 4);
-    if (pen) {                                                          // :1604-1615
-      const double r[5] = {.58, .62, .67, .77, .78};
-      const double ad1[5] = {.35, .60, 1.0, 1.5, 1.4};
-      const double ad2[5] = {23., 20., 17., 14., 7.9};
-      const int n = c.ntp - 1;
-      for (int k = 1; k <= kbm1; ++k)
-        rad[k]=A2(p.swrad,i,j)*(r[n]*exp(z(k)*dh/ad1[n])+(1.-r[n])*exp(z(k)*dh/ad2[n]));
-      rad[kb]=0.;
-    }
+    const double sw0 = pen ? A2(p.swrad,i,j) : 0.;
+    double radk = 0., radk1 = 0.;                                       // rad(k), rad(k+1)
     // a(k-1), c(k) from kh(k), k=2..kbm1 (:1589-1598); a(kbm1)=0, c(1)=0 (zero fill)
-    double ak=-dti2*(kh(i,j,2)+umol)/(dz(1)*dzz(1)*dh*dh);              // a(1)
+    double khk=POM_LDCS(&kh(i,j,2));
+    double ak=-dti2*(khk+umol)/(dz(1)*dzz(1)*dh*dh);                    // a(1)
+    double eem, ggm;
+    const double f1=POM_LDCS(&A3(f_,i,j,1));
     if (nbc == 1) {                                                     // :1619-1625
-      ee[1]=ak/(ak-1.);
-      gg[1]=dti2*A2(wfsurf_,i,j)/(dz(1)*dh)-A3(f_,i,j,1);
-      gg[1]=gg[1]/(ak-1.);
+      eem=ak/(ak-1.);
+      ggm=dti2*A2(wfsurf_,i,j)/(dz(1)*dh)-f1;
+      ggm=ggm/(ak-1.);
     } else if (nbc == 2) {                                              // :1629-1637
-      ee[1]=ak/(ak-1.);
-      gg[1]=dti2*(A2(wfsurf_,i,j)+rad[1]-rad[2])/(dz(1)*dh)-A3(f_,i,j,1);
-      gg[1]=gg[1]/(ak-1.);
+      radk=rad(1,dh,sw0); radk1=rad(2,dh,sw0);
+      eem=ak/(ak-1.);
+      ggm=dti2*(A2(wfsurf_,i,j)+radk-radk1)/(dz(1)*dh)-f1;
+      ggm=ggm/(ak-1.);
     } else if (nbc == 3 || nbc == 4) {                                  // :1641-1646
-      ee[1]=0.;
-      gg[1]=A2(fsurf_,i,j);
+      eem=0.;
+      ggm=A2(fsurf_,i,j);
     } else {
-      ee[1]=0.; gg[1]=0.;
+      eem=0.; ggm=0.;
     }
+    EE(1)=eem; GG(1)=ggm;
+    if (pen) radk1=rad(2,dh,sw0);
+    for (int q = 2; q < 2 + POM_PFD; ++q) { PF3(p.kh,i,j,q+1); PF3(f_,i,j,q); }
     for (int k = 2; k <= kbm2; ++k) {                                   // :1650-1661
-      PF3(p.kh,i,j,k+3); PF3(f_,i,j,k+2);
-      ak=-dti2*(kh(i,j,k+1)+umol)/(dz(k)*dzz(k)*dh*dh);                 // a(k)
-      double ck=-dti2*(kh(i,j,k)+umol)/(dz(k)*dzz(k-1)*dh*dh);          // c(k)
-      double gi=1./(ak+ck*(1.-ee[k-1])-1.);
-      ee[k]=ak*gi;
-      double rhs=ck*gg[k-1]-A3(f_,i,j,k);
-      if (pen) rhs=rhs+dti2*(rad[k]-rad[k+1])/(dh*dz(k));
-      gg[k]=rhs*gi;
+      PF3(p.kh,i,j,k+1+POM_PFD); PF3(f_,i,j,k+POM_PFD);
+      const double khn=POM_LDCS(&kh(i,j,k+1));
+      ak=-dti2*(khn+umol)/(dz(k)*dzz(k)*dh*dh);                         // a(k)
+      double ck=-dti2*(khk+umol)/(dz(k)*dzz(k-1)*dh*dh);                // c(k)
+      khk=khn;
+      double gi=1./(ak+ck*(1.-eem)-1.);
+      eem=ak*gi;
+      double rhs=ck*ggm-POM_LDCS(&A3(f_,i,j,k));
+      if (pen) { radk=radk1; radk1=rad(k+1,dh,sw0); rhs=rhs+dti2*(radk-radk1)/(dh*dz(k)); }
+      ggm=rhs*gi;
+      EE(k)=eem; GG(k)=ggm;
     }
     {                                                                   // :1664-1671
-      double ck=-dti2*(kh(i,j,kbm1)+umol)/(dz(kbm1)*dzz(kbm2)*dh*dh);   // c(kbm1)
-      double rhs=ck*gg[kbm2]-A3(f_,i,j,kbm1);
-      if (pen) rhs=rhs+dti2*(rad[kbm1]-rad[kb])/(dh*dz(kbm1));
-      double fk=rhs/(ck*(1.-ee[kbm2])-1.);
-      A3(f_,i,j,kbm1)=fk;
+      double ck=-dti2*(khk+umol)/(dz(kbm1)*dzz(kbm2)*dh*dh);            // c(kbm1), khk=kh(kbm1)
+      double rhs=ck*ggm-POM_LDCS(&A3(f_,i,j,kbm1));
+      if (pen) { radk=radk1; rhs=rhs+dti2*(radk-0.)/(dh*dz(kbm1)); }
+      double fk=rhs/(ck*(1.-eem)-1.);
+      POM_STCS(&A3(f_,i,j,kbm1),fk);
       for (int ki = kb-2; ki >= 1; --ki) {                              // :1673-1680
-        fk=ee[ki]*fk+gg[ki];
-        A3(f_,i,j,ki)=fk;
+        fk=EE(ki)*fk+GG(ki);
+        POM_STCS(&A3(f_,i,j,ki),fk);
       }
     }
+#undef EE
+#undef GG
   }
 };
 
@@ -1041,13 +1076,17 @@ void run_profq(Ctx* c, int j0, int j1) { launch_cols(c, ProfqK(c), ALLI, j0, j1)
 void run_qfilter(Ctx* c, int j0, int j1) { launch_cols(c, QFilterK(c), ALLI, j0, j1); }
 void run_advt(Ctx* c, int nadv, const double* fb, const double* f, const double* fc, double* ff, int j0, int j1) {
   if (nadv == 1) launch_cols(c, AdvT1K(c, fb, f, fc, ff), ALLI, j0, j1);
-  else launch_tiles(c, AdvT2K(c, fb, f, fc, ff), ALLI, j0, j1);
+  else launch_tma_tiles(c, AdvT2K(c, fb, f, fc, ff), ALLI, j0, j1);
 }
 void run_fb_roundtrip(Ctx* c, double* fb, const double* fc, double* f, int j0, int j1) {
   launch_cols(c, FbRoundTripK(c, fb, fc, f), ALLI, j0, j1);
 }
 void run_proft(Ctx* c, double* f, const double* wf, const double* fs, int nbc, int j0, int j1) {
+#if POM_THOMAS_SMEM
+  launch_cols_sm(c, ProftK(c, f, wf, fs, nbc), ALLI, j0, j1, 2, 32, POM_THOMAS_BY);
+#else
   launch_cols(c, ProftK(c, f, wf, fs, nbc), ALLI, j0, j1);
+#endif
 }
 // caller swaps t<->uf, s<->vf (advance.f:446-449)
 void run_tsfilter(Ctx* c, int j0, int j1) { launch_cols(c, TsFilterK(c), ALLI, j0, j1); }

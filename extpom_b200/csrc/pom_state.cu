@@ -4,6 +4,7 @@
 // authoritative only at init, after a pull, and for per-step forcing pushes
 // (SURVEY.md 8(b)).
 #include "pom_core.h"
+#include "pom_tma.h"
 #include <cstdlib>
 
 namespace pom {
@@ -131,6 +132,34 @@ int dev_sync(Ctx* c) {
 }
 #endif
 
+#ifndef POMGPU_EMU
+// ---- TMA tensor maps ------------------------------------------------------------------
+// A field is described to the TMA as a 3-D fp64 tensor (im, jml, nk), i fastest, box
+// (bw, bh, 1), no swizzle, out-of-range elements filled with zeros.  cuTensorMapEncodeTiled
+// is a pure host function; it is resolved through the runtime so that libpomgpu does not link
+// libcuda directly.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int tma_encode(Ctx* c, CUtensorMap* m, const double* base, int nk, int bw, int bh) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return 1;
+    fn = (EncodeTiledFn)p;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)c->g.im, (cuuint64_t)c->g.jml, (cuuint64_t)nk};
+  const cuuint64_t strides[2] = {(cuuint64_t)c->g.im * 8, (cuuint64_t)c->g.n2 * 8};
+  const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1;
+}
+#endif
+
 // ---- per-launch profiling with CUDA events on the launch stream ---------------------
 #ifdef POMGPU_EMU
 void prof_before(Ctx*, const KInfo*, double) {}
@@ -182,6 +211,7 @@ int prof_report(Ctx* c, char* buf, int n) {
 Ctx* ctx_create(int im, int jm_global, int kb, int j_first, int j_last, int ghost, int device) {
   if (im < 6 || jm_global < 6 || kb < 4 || kb > 64) return nullptr;   // KMAX of the column solvers
   Ctx* c = (Ctx*)calloc(1, sizeof(Ctx));
+  c->no_tma = (getenv("POMGPU_NO_TMA") != nullptr);
   c->device = device;
   c->jown0 = j_first; c->jown1 = j_last; c->ghost = ghost;
   int r0 = j_first - ghost; if (r0 < 1) r0 = 1;

@@ -1,0 +1,251 @@
+// pom_tma.h -- TMA-staged shared-memory tile kernels for the horizontal stencils.
+//
+// A block of 32 x TY threads owns a tile of points and marches in k.  The operand planes of
+// every level (tile + halo, NF fields) are brought from HBM into a ring of NS shared-memory
+// stages by the TMA (cp.async.bulk.tensor.3d, one elected thread, mbarrier complete_tx), two
+// or more levels AHEAD of the level being computed: the loads in flight per SM are
+// (NS-2) x NF x 4.6 kB whatever the register pressure / occupancy of the fp64 body is, which
+// is what these latency-bound kernels were missing.  Out-of-range box coordinates (domain
+// edge, strip edge) are zero-filled by the TMA.  Per level every thread evaluates the
+// flux-like values of ITS OWN point once from the staged operands into a double-buffered
+// flux tile (one __syncthreads per level); the tile interior differences its neighbours'.
+//
+// A functor F provides
+//   static constexpr int NF, NV, HL, HR, HB, HT, TY, NS;  flux halo of the thread tile
+//   static constexpr int OHL, OHR, OHB, OHT, BW, BH;       operand halo (W,E,S,N) and TMA box
+//   static constexpr bool UP;                              reads level k+1 at its own point
+//   void fields(const double* b[NF]);  k0(), k1(), kl1() (last level staged)
+//   pre(i,j,inside,out,State&);  stage(i,j,k,State&,op,v[NV]);  combine(i,j,k,State&,op,Tile);
+//   post(i,j,State&)
+// with op(F,di,dj) = field F at (i+di,j+dj,k) and op.up(F) = field F at (i,j,k+1).
+// The same functor runs on direct global loads (GlobalOp) in the host-emulated test build and
+// when the layout rules out a tensor map (odd im: row pitch not a multiple of 16 bytes).
+#pragma once
+#include "pom_core.h"
+#ifndef POMGPU_EMU
+#include <cuda.h>
+#endif
+
+namespace pom {
+
+POM_HD constexpr int tma_plane(int bw, int bh) { return ((bw * bh + 15) / 16) * 16; }   // 128-byte aligned planes
+
+template <class F>
+struct GlobalOp {
+  const double* const* fld;
+  Geo g;
+  int i, j, k;
+  POM_HD double operator()(int f, int di, int dj) const {
+    const int ii = i + di, jj = j + dj;
+    if (ii < 1 || ii > g.im || jj < g.joff + 1 || jj > g.joff + g.jml) return 0.;
+    return fld[f][POM_I3(ii, jj, k)];
+  }
+  POM_HD double up(int f) const { return (k + 1 <= g.kb) ? fld[f][POM_I3(i, j, k + 1)] : 0.; }
+};
+
+struct Tile2 {
+  const double* s; int tx, ty;
+  POM_HD double operator()(int v, int di, int dj) const { return s[(v * TILE_Y + (ty + dj)) * TILE_X + (tx + di)]; }
+};
+
+#ifndef POMGPU_EMU
+template <int NF> struct TmaMaps { CUtensorMap m[NF]; };
+int tma_encode(Ctx* c, CUtensorMap* m, const double* base, int nk, int bw, int bh);   // pom_state.cu
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+template <class F>
+struct SmemOp {
+  const double* cur;   // stage of level k, at this thread's own point
+  const double* nxt;   // stage of level k+1
+  static constexpr int PL = tma_plane(F::BW, F::BH);
+  __device__ __forceinline__ double operator()(int f, int di, int dj) const { return cur[f * PL + dj * F::BW + di]; }
+  __device__ __forceinline__ double up(int f) const { return nxt[f * PL]; }
+};
+
+template <class F>
+__global__ void __launch_bounds__(TILE_X * F::TY, 1)
+tmakernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1, int j0, int j1) {
+  constexpr int NF = F::NF, NS = F::NS, NV = F::NV, PL = tma_plane(F::BW, F::BH);
+  constexpr int OX = TILE_X - F::HL - F::HR, OY = F::TY - F::HB - F::HT;
+  extern __shared__ __align__(128) double pom_tsm[];
+  double* ring = pom_tsm;                                  // [NS][NF][PL]
+  double* S = ring + NS * NF * PL;                         // [2][NV][TILE_Y][TILE_X]
+  uint64_t* bar = (uint64_t*)(S + 2 * NV * TILE_Y * TILE_X);   // [NS]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ti0 = i0 + blockIdx.x * OX - F::HL, tj0 = j0 + blockIdx.y * OY - F::HB;
+  const int i = ti0 + tx, j = tj0 + ty;
+  // 0-based box origin in the arrays.  The TMA needs a 16-byte aligned start address, i.e. an
+  // even i-origin (measured: an odd one raises "illegal instruction"); negative origins and
+  // boxes that stick out of the array are fine (zero fill).  BW leaves room for the shift.
+  static_assert(F::BW % 2 == 0 && F::BW >= TILE_X + F::OHL + F::OHR + 1, "TMA box too narrow");
+  static_assert(F::BH >= F::TY + F::OHB + F::OHT, "TMA box too short");
+  const int n0 = ti0 - 1 - F::OHL, shift = n0 & 1;
+  const int c0 = n0 - shift, c1 = tj0 - 1 - f.g.joff - F::OHB;
+  const int k0 = f.k0(), k1 = f.k1(), kl1 = f.kl1();
+  const bool leader = (tx == 0 && ty == 0);
+  if (leader) {
+    for (int s = 0; s < NS; ++s) mbar_init(&bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int L) {
+    const int s = (L - k0) % NS;
+    mbar_expect_tx(&bar[s], (uint32_t)(NF * F::BW * F::BH * sizeof(double)));
+#pragma unroll
+    for (int n = 0; n < NF; ++n) tma_load_3d(ring + (s * NF + n) * PL, &maps.m[n], &bar[s], c0, c1, L - 1);
+  };
+  if (leader)
+    for (int L = k0; L < k0 + NS && L <= kl1; ++L) issue(L);
+  const bool inside = (i >= 1 && i <= f.g.im && j >= f.g.joff + 1 && j <= f.g.joff + f.g.jml);
+  const bool out = (tx >= F::HL && tx < TILE_X - F::HR && ty >= F::HB && ty < F::TY - F::HT && i <= i1 && j <= j1);
+  typename F::State st;
+  f.pre(i, j, inside, out, st);
+  const int own = (ty + F::OHB) * F::BW + tx + F::OHL + shift;
+  int buf = 0;
+  for (int k = k0; k <= k1; ++k) {
+    const int q0 = k - k0, s0 = q0 % NS;
+    mbar_wait(&bar[s0], (q0 / NS) & 1);
+    int s1 = s0;
+    if (F::UP && k + 1 <= kl1) {
+      s1 = (q0 + 1) % NS;
+      mbar_wait(&bar[s1], ((q0 + 1) / NS) & 1);
+    }
+    const SmemOp<F> op{ring + s0 * NF * PL + own, ring + s1 * NF * PL + own};
+    double v[NV];
+#pragma unroll
+    for (int n = 0; n < NV; ++n) v[n] = 0.;
+    if (inside) f.stage(i, j, k, st, op, v);
+    double* Sb = S + buf * NV * TILE_Y * TILE_X;
+#pragma unroll
+    for (int n = 0; n < NV; ++n) Sb[(n * TILE_Y + ty) * TILE_X + tx] = v[n];
+    __syncthreads();
+    // every thread is past combine(k-1): the stage of level k-1 is free for level k-1+NS
+    if (leader && k - 1 >= k0 && k - 1 + NS <= kl1) issue(k - 1 + NS);
+    if (out) f.combine(i, j, k, st, op, Tile2{Sb, tx, ty});
+    buf ^= 1;
+  }
+  if (out) f.post(i, j, st);
+}
+
+// the same functor on direct global loads (layouts the TMA cannot address)
+template <class F>
+__global__ void __launch_bounds__(TILE_X * F::TY, 1)
+tilekernel_g(const F f, int i0, int i1, int j0, int j1) {
+  constexpr int OX = TILE_X - F::HL - F::HR, OY = F::TY - F::HB - F::HT, NV = F::NV;
+  __shared__ double S[2 * NV * TILE_Y * TILE_X];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i = i0 + blockIdx.x * OX - F::HL + tx, j = j0 + blockIdx.y * OY - F::HB + ty;
+  const bool inside = (i >= 1 && i <= f.g.im && j >= f.g.joff + 1 && j <= f.g.joff + f.g.jml);
+  const bool out = (tx >= F::HL && tx < TILE_X - F::HR && ty >= F::HB && ty < F::TY - F::HT && i <= i1 && j <= j1);
+  const double* fld[F::NF];
+  f.fields(fld);
+  typename F::State st;
+  f.pre(i, j, inside, out, st);
+  int buf = 0;
+  const int k1 = f.k1();
+  for (int k = f.k0(); k <= k1; ++k) {
+    const GlobalOp<F> op{fld, f.g, i, j, k};
+    double v[NV];
+#pragma unroll
+    for (int n = 0; n < NV; ++n) v[n] = 0.;
+    if (inside) f.stage(i, j, k, st, op, v);
+    double* Sb = S + buf * NV * TILE_Y * TILE_X;
+#pragma unroll
+    for (int n = 0; n < NV; ++n) Sb[(n * TILE_Y + ty) * TILE_X + tx] = v[n];
+    __syncthreads();
+    if (out) f.combine(i, j, k, st, op, Tile2{Sb, tx, ty});
+    buf ^= 1;
+  }
+  if (out) f.post(i, j, st);
+}
+#endif
+
+template <class F>
+inline void launch_tma_tiles(Ctx* c, const F& f, int i0, int i1, int j0, int j1) {
+  if (i1 < i0 || j1 < j0) return;
+  c->launches++;
+  constexpr int OX = TILE_X - F::HL - F::HR, OY = F::TY - F::HB - F::HT;
+  const int nbx = (i1 - i0 + OX) / OX, nby = (j1 - j0 + OY) / OY;
+#ifdef POMGPU_EMU
+  static typename F::State st[TILE_Y][TILE_X];
+  static double S[F::NV * TILE_Y * TILE_X];
+  static bool ins[TILE_Y][TILE_X], outm[TILE_Y][TILE_X];
+  const double* fld[F::NF];
+  f.fields(fld);
+  for (int by = 0; by < nby; ++by)
+    for (int bx = 0; bx < nbx; ++bx) {
+      POM_TILE_LOOP {
+        POM_TILE_IJ;
+        ins[ty][tx] = (i >= 1 && i <= f.g.im && j >= f.g.joff + 1 && j <= f.g.joff + f.g.jml);
+        outm[ty][tx] = (tx >= F::HL && tx < TILE_X - F::HR && ty >= F::HB && ty < F::TY - F::HT && i <= i1 && j <= j1);
+        f.pre(i, j, ins[ty][tx], outm[ty][tx], st[ty][tx]);
+      }
+      for (int k = f.k0(); k <= f.k1(); ++k) {
+        POM_TILE_LOOP {
+          POM_TILE_IJ;
+          double v[F::NV];
+          for (int n = 0; n < F::NV; ++n) v[n] = 0.;
+          if (ins[ty][tx]) f.stage(i, j, k, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, k}, v);
+          for (int n = 0; n < F::NV; ++n) S[(n * TILE_Y + ty) * TILE_X + tx] = v[n];
+        }
+        POM_TILE_LOOP {
+          POM_TILE_IJ;
+          if (outm[ty][tx]) f.combine(i, j, k, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, k}, Tile2{S, tx, ty});
+        }
+      }
+      POM_TILE_LOOP {
+        POM_TILE_IJ;
+        if (outm[ty][tx]) f.post(i, j, st[ty][tx]);
+      }
+    }
+#else
+  if (c->prof_on) {
+    const KInfo& k = F::info();
+    double cols = (double)(i1 - i0 + 1) * (j1 - j0 + 1);
+    prof_before(c, &k, 8. * cols * ((k.r3 + k.w3) * (double)c->g.kb + (k.r2 + k.w2)));
+  }
+  dim3 b(TILE_X, F::TY), gr(nbx, nby);
+  bool tma_ok = (c->g.im % 2 == 0) && !c->no_tma;
+  if (tma_ok) {
+    TmaMaps<F::NF> maps;
+    const double* fld[F::NF];
+    f.fields(fld);
+    for (int n = 0; n < F::NF && tma_ok; ++n)
+      if (tma_encode(c, &maps.m[n], fld[n], F::NK ? F::NK : c->g.kb, F::BW, F::BH)) tma_ok = false;
+    if (tma_ok) {
+      constexpr size_t smem = (size_t)(F::NS * F::NF * tma_plane(F::BW, F::BH) + 2 * F::NV * TILE_Y * TILE_X) * sizeof(double) + F::NS * 8;
+      static bool granted = false;
+      if (!granted) {
+        cudaFuncSetAttribute(tmakernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        granted = true;
+      }
+      tmakernel<F><<<gr, b, smem, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
+    }
+  }
+  if (!tma_ok) tilekernel_g<F><<<gr, b, 0, (cudaStream_t)c->stream>>>(f, i0, i1, j0, j1);
+  if (c->prof_on) prof_after(c);
+#endif
+}
+
+}  // namespace pom

@@ -5,7 +5,9 @@ from extpom_b200 import synthetic as syn
 from extpom_b200.pomgpu import PomGpu
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 kb = int(sys.argv[2]) if len(sys.argv) > 2 else 41
-st, g = syn.seamount(n, n, kb, PomGpu)
+lib = os.environ.get("POMGPU_LIB")
+st, g = syn.seamount(n, n, kb, lambda a, b, c: PomGpu(a, b, c, _libpath=lib))
+print("lib:", lib or "default")
 del st
 for i in range(1, 4): g.step(i)
 g.sync()
@@ -19,5 +21,7 @@ prof = g.profile_end()
 prof.sort(key=lambda r: -r["ms"])
 tot = sum(r["ms"] for r in prof)
 print("sum of kernels ms/step %.3f" % (tot / 3))
+only = os.environ.get("KPROF_ONLY", "").split(",") if os.environ.get("KPROF_ONLY") else None
 for r in prof:
+    if only and r["name"] not in only: continue
     print("%-18s n=%3d  %8.3f ms/step  %7.1f GB/s  %5.1f%%" % (r["name"], r["launches"] // 3, r["ms"] / 3, r["bytes"] / r["ms"] / 1e6, 100 * r["ms"] / tot))
