@@ -79,19 +79,26 @@ struct VertvlK : KBase {
 struct AdvqK : KBase {
   POM_KINFO("advq", 8, 2, 9, 0)
   using KBase::KBase;
-  static constexpr int NV = 4, HL = 0, HR = 1, HB = 0, HT = 1, TY = 16, MINB = 1;
+  static constexpr int NV = 4, HL = 0, HR = 1, HB = 0, HT = 1, TY = 16;
+  static constexpr int NF = 8, NS = 4, OHL = 1, OHR = 0, OHB = 1, OHT = 0, BW = 34, BH = 17, NK = 0;
+  static constexpr bool UP = true;
+  enum { Q2, Q2B, Q2L, Q2LB, U, V, AAM, W };
   enum { XA, YA, XB, YB };
+  POM_HD void fields(const double** b) const {
+    b[Q2] = p.q2; b[Q2B] = p.q2b; b[Q2L] = p.q2l; b[Q2LB] = p.q2lb; b[U] = p.u; b[V] = p.v; b[AAM] = p.aam; b[W] = p.w;
+  }
   struct State {
     double dtx, dty, hx, hy, dumc, dvmc, hdy, hdx;   // (dt+dt), (h+h), masks, .5*(dy+dy), .5*(dx+dx)
     RDiv ddxs, ddys, dhf;                             // (dx+dx(i-1)), (dy+dy(j-1)), (h+etf)*art
     double hb, ar;                                    // (h+etb)*art, art
     double um, vm, a0m, aWm, aSm;                     // level k-1: u, v, aam(i,j), aam(i-1,j), aam(i,j-1)
     double wm, w0, qam, qbm, qa0, qb0;                // w(k-1), w(k), q(k-1), q(k) of q2 / q2l (output columns)
+    double qab, qbb;                                  // q2b, q2lb of this level (stage -> combine)
     bool fxa, fya, interior;
   };
-  struct Regs { double qa, qaW, qaS, qab, qabW, qabS, qb, qbW, qbS, qbb, qbbW, qbbS, u0, v0, a0, aW, aS, w1, qa1, qb1; };
   POM_HD int k0() const { return 2; }
   POM_HD int k1() const { return g.kb - 1; }
+  POM_HD int kl1() const { return g.kb; }
   POM_HD void pre(int i, int j, bool inside, bool out, State& s) const {
     POM_DIMS;
     const int jlo = g.joff + 1;
@@ -118,60 +125,51 @@ struct AdvqK : KBase {
       s.qa0 = q2(i,j,2); s.qb0 = q2l(i,j,2);
     }
   }
-  POM_HD void fetch(int i, int j, int k, const State& s, Regs& r) const {
+  template <class Op>
+  POM_HD void stage(int i, int j, int k, State& s, const Op& o, double* v) const {
     if (!(s.fxa || s.fya)) return;
-    const int o = POM_I3(i,j,k), im = g.im;
-    r.qa = POM_LDG(p.q2+o); r.qaW = POM_LDG(p.q2+o-1); r.qab = POM_LDG(p.q2b+o); r.qabW = POM_LDG(p.q2b+o-1);
-    r.qb = POM_LDG(p.q2l+o); r.qbW = POM_LDG(p.q2l+o-1); r.qbb = POM_LDG(p.q2lb+o); r.qbbW = POM_LDG(p.q2lb+o-1);
-    r.u0 = POM_LDG(p.u+o); r.a0 = POM_LDG(p.aam+o); r.aW = POM_LDG(p.aam+o-1);
-    if (k + 1 <= g.kb - 1) {
-      const int n = o + g.n2;
-      POM_PREFETCH(p.q2+n); POM_PREFETCH(p.q2b+n); POM_PREFETCH(p.q2l+n); POM_PREFETCH(p.q2lb+n);
-      POM_PREFETCH(p.u+n); POM_PREFETCH(p.v+n); POM_PREFETCH(p.aam+n); POM_PREFETCH(p.w+n+g.n2);
-    }
-    if (s.fya) {
-      r.qaS = POM_LDG(p.q2+o-im); r.qabS = POM_LDG(p.q2b+o-im); r.qbS = POM_LDG(p.q2l+o-im); r.qbbS = POM_LDG(p.q2lb+o-im);
-      r.v0 = POM_LDG(p.v+o); r.aS = POM_LDG(p.aam+o-im);
-    }
-    if (s.interior) { r.w1 = POM_LDG(p.w+o+g.n2); r.qa1 = POM_LDG(p.q2+o+g.n2); r.qb1 = POM_LDG(p.q2l+o+g.n2); }
-  }
-  POM_HD void stage(int i, int j, int k, State& s, const Regs& r, double* v) const {
+    const double qa=o(Q2,0,0), qab=o(Q2B,0,0), qb=o(Q2L,0,0), qbb=o(Q2LB,0,0), a0=o(AAM,0,0);
+    s.qab=qab; s.qbb=qbb;
     if (s.fxa) {
-      const double a4=r.a0+r.aW+s.a0m+s.aWm;                   // :441-442
-      const double us=r.u0+s.um;
-      double a=.125*(r.qa+r.qaW)*s.dtx*us;                     // :428-429
-      a=a-s.ddxs(.25*a4*s.hx*(r.qab-r.qabW)*s.dumc);           // :440-445
+      const double aW=o(AAM,-1,0), u0=o(U,0,0);
+      const double a4=a0+aW+s.a0m+s.aWm;                       // :441-442
+      const double us=u0+s.um;
+      double a=.125*(qa+o(Q2,-1,0))*s.dtx*us;                  // :428-429
+      a=a-s.ddxs(.25*a4*s.hx*(qab-o(Q2B,-1,0))*s.dumc);        // :440-445
       v[XA]=s.hdy*a;                                           // :452
-      double b=.125*(r.qb+r.qbW)*s.dtx*us;
-      b=b-s.ddxs(.25*a4*s.hx*(r.qbb-r.qbbW)*s.dumc);
+      double b=.125*(qb+o(Q2L,-1,0))*s.dtx*us;
+      b=b-s.ddxs(.25*a4*s.hx*(qbb-o(Q2LB,-1,0))*s.dumc);
       v[XB]=s.hdy*b;
-      s.um=r.u0; s.aWm=r.aW;
+      s.um=u0; s.aWm=aW;
     }
     if (s.fya) {
-      const double a4=r.a0+r.aS+s.a0m+s.aSm;                   // :447-448
-      const double vs=r.v0+s.vm;
-      double a=.125*(r.qa+r.qaS)*s.dty*vs;                     // :430-431
-      a=a-s.ddys(.25*a4*s.hy*(r.qab-r.qabS)*s.dvmc);           // :446-451
+      const double aS=o(AAM,0,-1), v0=o(V,0,0);
+      const double a4=a0+aS+s.a0m+s.aSm;                       // :447-448
+      const double vs=v0+s.vm;
+      double a=.125*(qa+o(Q2,0,-1))*s.dty*vs;                  // :430-431
+      a=a-s.ddys(.25*a4*s.hy*(qab-o(Q2B,0,-1))*s.dvmc);        // :446-451
       v[YA]=s.hdx*a;                                           // :453
-      double b=.125*(r.qb+r.qbS)*s.dty*vs;
-      b=b-s.ddys(.25*a4*s.hy*(r.qbb-r.qbbS)*s.dvmc);
+      double b=.125*(qb+o(Q2L,0,-1))*s.dty*vs;
+      b=b-s.ddys(.25*a4*s.hy*(qbb-o(Q2LB,0,-1))*s.dvmc);
       v[YB]=s.hdx*b;
-      s.vm=r.v0; s.aSm=r.aS;
+      s.vm=v0; s.aSm=aS;
     }
-    s.a0m=r.a0;
+    s.a0m=a0;
   }
-  POM_HD void combine(int i, int j, int k, State& s, const Regs& r, const Tile& tl) const {
+  template <class Op>
+  POM_HD void combine(int i, int j, int k, State& s, const Op& o, const Tile2& tl) const {
     double a = 0., b = 0.;
     if (s.interior) {
+      const double w1=o.up(W), qa1=o.up(Q2), qb1=o.up(Q2L);
       const double dzk=dz(k)+dz(k-1);
-      double ra=(s.wm*s.qam-r.w1*r.qa1)*s.ar/dzk
+      double ra=(s.wm*s.qam-w1*qa1)*s.ar/dzk
                 +tl(XA,1,0)-tl(XA,0,0)+tl(YA,0,1)-tl(YA,0,0);  // :465-468
-      a=s.dhf(s.hb*r.qab-dti2*ra);                             // :469-471
-      double rb=(s.wm*s.qbm-r.w1*r.qb1)*s.ar/dzk
+      a=s.dhf(s.hb*s.qab-dti2*ra);                             // :469-471
+      double rb=(s.wm*s.qbm-w1*qb1)*s.ar/dzk
                 +tl(XB,1,0)-tl(XB,0,0)+tl(YB,0,1)-tl(YB,0,0);
-      b=s.dhf(s.hb*r.qbb-dti2*rb);
-      s.wm=s.w0; s.w0=r.w1;
-      s.qam=s.qa0; s.qbm=s.qb0; s.qa0=r.qa1; s.qb0=r.qb1;
+      b=s.dhf(s.hb*s.qbb-dti2*rb);
+      s.wm=s.w0; s.w0=w1;
+      s.qam=s.qa0; s.qbm=s.qb0; s.qa0=qa1; s.qb0=qb1;
     }
     uf(i,j,k)=a;
     vf(i,j,k)=b;
@@ -1070,7 +1068,7 @@ struct FbRoundTripK : KBase {
 #define ALLI 1, c->g.im
 void run_uvadjust(Ctx* c, int j0, int j1) { launch_cols(c, UvAdjustK(c), ALLI, j0, j1); }
 void run_vertvl(Ctx* c, int j0, int j1) { launch_cols(c, VertvlK(c), ALLI, j0, j1); }
-void run_advq(Ctx* c, int j0, int j1) { launch_tiles(c, AdvqK(c), ALLI, j0, j1); }
+void run_advq(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvqK(c), ALLI, j0, j1); }
 void run_profq(Ctx* c, int j0, int j1) { launch_cols(c, ProfqK(c), ALLI, j0, j1); }
 // caller swaps q2<->uf, q2l<->vf (advance.f:418-421)
 void run_qfilter(Ctx* c, int j0, int j1) { launch_cols(c, QFilterK(c), ALLI, j0, j1); }

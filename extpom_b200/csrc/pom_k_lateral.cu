@@ -7,6 +7,7 @@
 // being staged through HBM.  Expression order follows the Fortran so that the
 // results are bit-identical to a no-FMA evaluation.
 #include "pom_core.h"
+#include "pom_tma.h"
 #include "pom_names.h"
 
 #ifndef POM_ADVCT_TY
@@ -22,8 +23,14 @@ namespace pom {
 struct AdvctK : KBase {
   POM_KINFO("advct", 5, 2, 5, 2)
   using KBase::KBase;
-  static constexpr int NV = 6, HL = 1, HR = 1, HB = 1, HT = 1, TY = POM_ADVCT_TY, MINB = POM_ADVCT_MINB;
+  static constexpr int NV = 6, HL = 1, HR = 1, HB = 1, HT = 1, TY = 16;
+  // operands staged by the TMA: thread tile + one point all around (36 x 18 box)
+  static constexpr int NF = 5, NS = 4, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = 18, NK = 0;
+  static constexpr bool UP = false;
+  enum { U, V, UB, VB, AAM };
   enum { X, Y, XP, YP, CV, CU };
+  POM_HD void fields(const double** b) const { b[U] = p.u; b[V] = p.v; b[UB] = p.ub; b[VB] = p.vb; b[AAM] = p.aam; }
+  POM_HD int kl1() const { return g.kb - 1; }
   struct State {
     double dtE, dtW, dtS, dtN, dtSW, dtWS, q4, dtc, dxc, dyc, qdx4, qdy4, dyd, dxd;
     RDiv ddx, ddy, ddy4, ddx4, ddxdy;   // hoisted divisors dx, dy, dy4, dx4, dx*dy
@@ -66,49 +73,36 @@ struct AdvctK : KBase {
     }
     if (s.interior) { s.aru25 = aru(i,j)*.25; s.arv25 = arv(i,j)*.25; }
   }
-  struct Regs { double u00, uE, uS, v00, vW, vN, ub00, ubE, ubS, vb00, vbW, vbN, a00, aW, aS, aSW; };
-  POM_HD void fetch(int i, int j, int k, const State& s, Regs& r) const {
+  template <class Op>
+  POM_HD void stage(int i, int j, int k, State& s, const Op& o, double* v) const {
     if (!(s.fx || s.fy || s.fxp || s.fyp)) return;
-    const int o = POM_I3(i,j,k), im = g.im;
-    r.u00 = POM_LDG(p.u+o); r.v00 = POM_LDG(p.v+o); r.ub00 = POM_LDG(p.ub+o); r.vb00 = POM_LDG(p.vb+o);
-    r.a00 = POM_LDG(p.aam+o);
-    if (k + 1 <= g.kb - 1) {   // next level's lines into L1 (rows j, j-1, j+1 of this thread's i)
-      const int n = o + g.n2;
-      POM_PREFETCH(p.u+n); POM_PREFETCH(p.v+n); POM_PREFETCH(p.ub+n); POM_PREFETCH(p.vb+n); POM_PREFETCH(p.aam+n);
-    }
-    if (s.fx || s.fyp) { r.uE = POM_LDG(p.u+o+1); r.ubE = POM_LDG(p.ub+o+1); }
-    if (s.fyp) { r.vN = POM_LDG(p.v+o+im); r.vbN = POM_LDG(p.vb+o+im); }
-    if (s.fy || s.fxp) {
-      r.uS = POM_LDG(p.u+o-im); r.vW = POM_LDG(p.v+o-1); r.ubS = POM_LDG(p.ub+o-im); r.vbW = POM_LDG(p.vb+o-1);
-      r.aW = POM_LDG(p.aam+o-1); r.aS = POM_LDG(p.aam+o-im); r.aSW = POM_LDG(p.aam+o-im-1);
-    }
-  }
-  POM_HD void stage(int i, int j, int k, State& s, const Regs& r, double* v) const {
-    if (!(s.fx || s.fy || s.fxp || s.fyp)) return;
-    const double u00 = r.u00, v00 = r.v00, ub00 = r.ub00, vb00 = r.vb00, a00 = r.a00;
-    const double uE = r.uE, ubE = r.ubE, vN = r.vN, vbN = r.vbN;
+    const double u00 = o(U,0,0), v00 = o(V,0,0), ub00 = o(UB,0,0), vb00 = o(VB,0,0), a00 = o(AAM,0,0);
+    double uE = 0., vN = 0.;
+    if (s.fx || s.fyp) uE = o(U,1,0);
     if (s.fx) {                                                          // :237-239,258-260,272
       double a=.125*(s.dtE*uE+s.dtW*u00)*(uE+u00);
-      a=a-s.ddx(s.dtc*a00*2.*(ubE-ub00));
+      a=a-s.ddx(s.dtc*a00*2.*(o(UB,1,0)-ub00));
       v[X]=s.dyc*a;
     }
     if (s.fy || s.fxp) {
-      const double uS = r.uS, vW = r.vW, ubS = r.ubS, vbW = r.vbW;
-      const double dtaam=s.q4*(a00+r.aW+r.aS+r.aSW);                       // :261-263,348-350
-      const double cd=dtaam*(s.ddy4(ub00-ubS)+s.ddx4(vb00-vbW));          // :265-270,352-357
+      const double uS = o(U,0,-1), vW = o(V,-1,0);
+      const double dtaam=s.q4*(a00+o(AAM,-1,0)+o(AAM,0,-1)+o(AAM,-1,-1));  // :261-263,348-350
+      const double cd=dtaam*(s.ddy4(ub00-o(UB,0,-1))+s.ddx4(vb00-o(VB,-1,0)));   // :265-270,352-357
       if (s.fy) { double a=.125*(s.dtS*v00+s.dtSW*vW)*(u00+uS); v[Y]=s.qdx4*(a-cd); }     // :247-249,273-274
       if (s.fxp) { double a=.125*(s.dtW*u00+s.dtWS*uS)*(v00+vW); v[XP]=s.qdy4*(a-cd); }   // :327-329,362-363
     }
     if (s.fyp) {
+      vN = o(V,0,1);
       double a=.125*(s.dtN*vN+s.dtS*v00)*(vN+v00);                        // :337-339
-      a=a-s.ddy(s.dtc*a00*2.*(vbN-vb00));                                  // :358-360
+      a=a-s.ddy(s.dtc*a00*2.*(o(VB,0,1)-vb00));                            // :358-360
       v[YP]=s.dxc*a;                                                      // :364
       const double cv=s.ddxdy(.25*((vN+v00)*s.dyd-(uE+u00)*s.dxd));         // :221-225
       v[CV]=cv*s.dtc*(vN+v00);                                            // :297-298
       v[CU]=cv*s.dtc*(uE+u00);                                            // :387-388
     }
   }
-  POM_HD void combine(int i, int j, int k, State& s, const Regs&, const Tile& tl) const {
+  template <class Op>
+  POM_HD void combine(int i, int j, int k, State& s, const Op&, const Tile2& tl) const {
     double ax = 0., ay = 0.;
     if (s.interior) {
       ax=tl(X,0,0)-tl(X,-1,0)+tl(Y,0,1)-tl(Y,0,0);                            // :285-286
@@ -214,7 +208,7 @@ struct SmagK : KBase {
   }
 };
 
-void run_advct(Ctx* c, int j0, int j1) { launch_tiles(c, AdvctK(c), 1, c->g.im, j0, j1); }
+void run_advct(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvctK(c), 1, c->g.im, j0, j1); }
 // the caller swaps rho <-> rho2 afterwards
 void run_baropg(Ctx* c, int j0, int j1) { launch_cols(c, BaropgK(c), 1, c->g.im, j0, j1); }
 void run_smag(Ctx* c, int j0, int j1) { launch_cols(c, SmagK(c), 1, c->g.im, j0, j1); }
