@@ -183,193 +183,214 @@ struct AdvqK : KBase {
 struct ProfqK : KBase {
   POM_KINFO("profq", 13, 8, 7, 0)
   double cgg, const1;
-  ProfqK(const Ctx* x) : KBase(x) {
+  double zr[KMAX];   // 1/|z(k)-z(1)| + 1/|z(k)-z(kb)| (:1429-1431), k-only: tabulated on the host
+  ProfqK(const Ctx* x, const double* hz) : KBase(x) {
     // solver.f:1297: (15.8*cbcnst)**(2./3.) with single-precision literals promoted
     // to double; solver.f:1273 const1
     const double cbcnst = 100.;
     cgg = pow((double)15.8f * cbcnst, (double)(2.f / 3.f));
     const1 = pow(16.6, 2. / 3.) * 1.;
+    const int kb = x->g.kb;
+    for (int k = 0; k < KMAX; ++k) zr[k] = 0.;
+    for (int k = 2; k <= kb - 1 && k < KMAX; ++k) zr[k] = 1. / fabs(hz[k - 1] - hz[0]) + 1. / fabs(hz[k - 1] - hz[kb - 1]);
   }
-  // One downward sweep per column computes, level by level, the speed of sound, buoyancy
-  // gradient, length scale, gh, production, the forward eliminations of BOTH tridiagonal
-  // systems and the km/kh/kq update (in place, old kq kept in rolling registers); two upward
-  // sweeps back-substitute.  Only the four ee/gg vectors live in per-thread memory.
-  POM_HD void operator()(int i, int j) const {
+  // TMA-fed column kernel: the 13 operand fields of every level are staged in shared memory
+  // by the TMA two levels ahead; one downward sweep computes, level by level, the speed of
+  // sound, buoyancy gradient, length scale, gh, production, the forward eliminations of BOTH
+  // tridiagonal systems and the km/kh/kq update (in place, old kq kept in rolling registers);
+  // `post` back-substitutes.  Only the four ee/gg vectors live in per-thread memory.
+  static constexpr int TY = 8, MINB = 2;
+  static constexpr int NF = 13, NS = 3, OHL = 0, OHR = 1, OHB = 0, OHT = 1, BW = 34, BH = 9, NK = 0;
+  static constexpr bool UP = true;
+  enum { T, S, RHO, Q2B, Q2LB, Q2, U, V, KM, KH, KQ, UF, VF };
+  POM_HD void fields(const double** b) const {
+    b[T] = p.t; b[S] = p.s; b[RHO] = p.rho; b[Q2B] = p.q2b; b[Q2LB] = p.q2lb; b[Q2] = p.q2; b[U] = p.u; b[V] = p.v;
+    b[KM] = p.km; b[KH] = p.kh; b[KQ] = p.kq; b[UF] = p.uf; b[VF] = p.vf;
+  }
+  struct Cols { double ee[KMAX], gg[KMAX], e2v[KMAX], g2v[KMAX]; };
+  struct State {
+    double hh, dh, kl0, m, ccm, kqm, kq0, rhom, um, uEm, vm, vNm, eem, ggm, e2m, g2m, q2_2, ufkb;
+    int il, ir, jl, jr;
+    bool interior;
+  };
+  POM_HD int k0() const { return 1; }
+  POM_HD int k1() const { return g.kb; }
+  POM_HD int kl1() const { return g.kb; }
+  // new km,kh,kq of one level: own cell masked; boundary neighbours get the unmasked value
+  // times their own mask (N,S,E,W copies of :1510-1529 = index clamped into the interior)
+  POM_HD void put_k(int i, int j, int k, const State& st, double nkq, double nkm, double nkh) const {
+    kq(i,j,k)=nkq*st.m; km(i,j,k)=nkm*st.m; kh(i,j,k)=nkh*st.m;
+    if (st.il | st.ir | st.jl | st.jr)
+      for (int dj = -st.jl; dj <= st.jr; ++dj)
+        for (int di = -st.il; di <= st.ir; ++di) {
+          if (di == 0 && dj == 0) continue;
+          const double me = fsm(i+di,j+dj);
+          kq(i+di,j+dj,k)=nkq*me; km(i+di,j+dj,k)=nkm*me; kh(i+di,j+dj,k)=nkh*me;
+        }
+  }
+  POM_HD void pre(int i, int j, State& st, Cols& cm) const {
     POM_DIMS;
-    const double a1 = 0.92, b1 = 16.6, a2 = 0.74, b2 = 10.1, c1 = 0.08;     // :1241
-    const double e1 = 1.8, e2 = 1.33, sef = 1., surfl = 2.e5, shiw = 0.;     // :1242-1244
-    const double coef4=18.*a1*a1+9.*a1*a2, coef5=9.*a1*a2;                   // :1474-1475
-    const double coef1=a2*(1.-6.*a1/b1*1.);                                  // :1481-1483 (stf=1)
-    const double coef2=3.*a2*b2/1.+18.*a1*a2;
-    const double coef3=a1*(1.-3.*c1-6.*a1/b1*1.);
-    const bool interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
-    const double hh=h(i,j);
-    const double dh=hh+etf(i,j);                                              // :1248
+    const double surfl = 2.e5;                                                // :1244
+    st.interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
+    st.hh=h(i,j);
+    st.dh=st.hh+etf(i,j);                                                     // :1248
     double utau2 = 0.;
+    st.ufkb = 0.;
     if (i <= imm1 && j <= jmm1) {                                             // :1281-1288
       double su=.5*(wusurf(i,j)+wusurf(i+1,j)), sv=.5*(wvsurf(i,j)+wvsurf(i,j+1));
       utau2=sqrt(su*su+sv*sv);
       double bu=.5*(wubot(i,j)+wubot(i+1,j)), bv=.5*(wvbot(i,j)+wvbot(i,j+1));
-      uf(i,j,kb)=sqrt(bu*bu+bv*bv)*const1;
+      st.ufkb=sqrt(bu*bu+bv*bv)*const1;
+      uf(i,j,kb)=st.ufkb;
     }
     const double l0=surfl*utau2/grav;                                         // :1299
-    const double kl0=kappa*l0;
-    l(i,j,1)=kl0; l(i,j,kb)=0.;                                               // :1351-1352
-    if (!interior) {
+    st.kl0=kappa*l0;
+    l(i,j,1)=st.kl0; l(i,j,kb)=0.;                                            // :1351-1352
+    st.il = (i == 2) ? 1 : 0; st.ir = (i == imm1) ? 1 : 0;
+    st.jl = (j == 2) ? 1 : 0; st.jr = (j == jmm1) ? 1 : 0;
+    st.m = fsm(i,j);
+    st.eem = 0.; st.ggm = cgg*utau2;                                          // ee(1), gg(1) :1296-1297
+    st.e2m = 0.; st.g2m = 0.;
+    cm.ee[1]=st.eem; cm.gg[1]=st.ggm;
+  }
+  template <class Op>
+  POM_HD void level(int i, int j, int k, State& st, Cols& cm, const Op& o) const {
+    POM_DIMS;
+    const double a1 = 0.92, b1 = 16.6, a2 = 0.74, b2 = 10.1, c1 = 0.08;     // :1241
+    const double e1 = 1.8, e2 = 1.33, sef = 1., shiw = 0.;                   // :1242-1244
+    const double coef4=18.*a1*a1+9.*a1*a2, coef5=9.*a1*a2;                   // :1474-1475
+    const double coef1=a2*(1.-6.*a1/b1*1.);                                  // :1481-1483 (stf=1)
+    const double coef2=3.*a2*b2/1.+18.*a1*a2;
+    const double coef3=a1*(1.-3.*c1-6.*a1/b1*1.);
+    if (!st.interior) {
       // boundary columns: only l is kept; the reference's solves there are overwritten by
       // bcond(6) (advance.f:414) and km,kh,kq by the copies of :1510-1529
-      for (int k = 2; k <= kbm1; ++k) {
-        double qb=fabs(q2b(i,j,k)), qlb=fabs(q2lb(i,j,k));
+      if (k >= 2 && k <= kbm1) {
+        double qb=fabs(o(Q2B,0,0)), qlb=fabs(o(Q2LB,0,0));
         q2b(i,j,k)=qb; q2lb(i,j,k)=qlb;                                       // :1325-1326
         double ll=fabs(qlb/qb);
-        if (z(k) > -0.5) ll=fmax(ll,kl0);
+        if (z(k) > -0.5) ll=fmax(ll,st.kl0);
         l(i,j,k)=ll;
       }
       return;
     }
-    double ee[KMAX], gg[KMAX], e2v[KMAX], g2v[KMAX];
-    const int il = (i == 2) ? 1 : 0, ir = (i == imm1) ? 1 : 0;
-    const int jl = (j == 2) ? 1 : 0, jr = (j == jmm1) ? 1 : 0;
-    const double m = fsm(i,j);
-    // new km,kh,kq of one level: own cell masked; boundary neighbours get the unmasked value
-    // times their own mask (N,S,E,W copies of :1510-1529 = index clamped into the interior)
-#define POM_PUT_K(k, nkq, nkm, nkh)                                             \
-    do {                                                                        \
-      kq(i,j,k)=(nkq)*m; km(i,j,k)=(nkm)*m; kh(i,j,k)=(nkh)*m;                  \
-      if (il | ir | jl | jr)                                                    \
-        for (int dj = -jl; dj <= jr; ++dj)                                      \
-          for (int di = -il; di <= ir; ++di) {                                  \
-            if (di == 0 && dj == 0) continue;                                   \
-            const double me = fsm(i+di,j+dj);                                   \
-            kq(i+di,j+dj,k)=(nkq)*me; km(i+di,j+dj,k)=(nkm)*me; kh(i+di,j+dj,k)=(nkh)*me; \
-          }                                                                     \
-    } while (0)
-    // ---- level 1 ----
-    double ccm;                                                               // cc(k-1) (:1304-1319)
-    {
-      double tp=t(i,j,1)+tbias, sp=s(i,j,1)+sbias;
-      double pp=grav*rhoref*(-zz(1)*hh)*1.e-4;
-      double cv=1449.1+.00821*pp+4.55*tp-.045*(tp*tp)+1.34*(sp-35.0);
-      ccm=cv/sqrt((1.-.01642*pp/cv)*(1.-0.40*pp/(cv*cv)));
+    const double hh=st.hh, dh=st.dh;
+    if (k == 1) {
+      {
+        double tp=o(T,0,0)+tbias, sp=o(S,0,0)+sbias;                          // cc(1) (:1304-1319)
+        double pp=grav*rhoref*(-zz(1)*hh)*1.e-4;
+        double cv=1449.1+.00821*pp+4.55*tp-.045*(tp*tp)+1.34*(sp-35.0);
+        st.ccm=cv/sqrt((1.-.01642*pp/cv)*(1.-0.40*pp/(cv*cv)));
+      }
+      st.kqm=o(KQ,0,0); st.kq0=o.up(KQ);                                      // old kq(1), kq(2)
+      {
+        // gh(1)=0 (:1353): sh=coef1, sm=coef3 (:1484-1486 with gh=0)
+        double sh=coef1/(1.-coef2*0.);
+        double sm=coef3+sh*coef4*0.;
+        sm=sm/(1.-coef5*0.);
+        double pr=st.kl0*sqrt(fabs(o(Q2,0,0)));                               // :1499
+        const double nq=(pr*.41*sh+st.kqm)*.5, nm=(pr*sm+o(KM,0,0))*.5, nh=(pr*sh+o(KH,0,0))*.5;   // :1500-1503
+        put_k(i,j,1,st,nq,nm,nh);
+      }
+      st.rhom=o(RHO,0,0);
+      st.um=o(U,0,0); st.uEm=o(U,1,0); st.vm=o(V,0,0); st.vNm=o(V,0,1);
+      st.q2_2=o.up(Q2);
+      return;
     }
-    double kqm=kq(i,j,1), kq0=kq(i,j,2);                                      // old kq(k-1), kq(k)
-    {
-      // gh(1)=0 (:1353): sh=coef1, sm=coef3 (:1484-1486 with gh=0)
+    if (k == kb) {                                                            // l=0, gh=0
       double sh=coef1/(1.-coef2*0.);
       double sm=coef3+sh*coef4*0.;
       sm=sm/(1.-coef5*0.);
-      double pr=kl0*sqrt(fabs(q2(i,j,1)));                                    // :1499
-      const double nq=(pr*.41*sh+kqm)*.5, nm=(pr*sm+km(i,j,1))*.5, nh=(pr*sh+kh(i,j,1))*.5;   // :1500-1503
-      POM_PUT_K(1, nq, nm, nh);
+      double pq=0.*sqrt(fabs(o(Q2,0,0)));
+      const double nq=(pq*.41*sh+st.kq0)*.5, nm=(pq*sm+o(KM,0,0))*.5, nh=(pq*sh+o(KH,0,0))*.5;
+      put_k(i,j,kb,st,nq,nm,nh);
+      return;
     }
-    double rhom=rho(i,j,1);
-    double um=u(i,j,1), uEm=u(i+1,j,1), vm=v(i,j,1), vNm=v(i,j+1,1);
-    double eem = 0., ggm = cgg*utau2;                                         // ee(1), gg(1) :1296-1297
-    double e2m = 0., g2m = 0.;
-    ee[1]=eem; gg[1]=ggm;
-    const double q2_2=q2(i,j,2);
     // ---- levels 2..kbm1 ----
-    for (int k = 2; k <= kbm1; ++k) {
-      {   // prefetch the operands of level k+1 (kq: k+2)
-        const int o = POM_I3(i,j,k+1);
-        POM_PREFETCH(p.t+o); POM_PREFETCH(p.s+o); POM_PREFETCH(p.q2b+o); POM_PREFETCH(p.q2lb+o);
-        POM_PREFETCH(p.rho+o); POM_PREFETCH(p.u+o); POM_PREFETCH(p.v+o); POM_PREFETCH(p.v+o+g.im);
-        POM_PREFETCH(p.km+o); POM_PREFETCH(p.kh+o); POM_PREFETCH(p.uf+o); POM_PREFETCH(p.vf+o);
-        POM_PREFETCH(p.q2+o);
-        if (k + 2 <= kb) POM_PREFETCH(p.kq+o+g.n2);
-      }
-      double tp=t(i,j,k)+tbias, sp=s(i,j,k)+sbias;
-      double pp=grav*rhoref*(-zz(k)*hh)*1.e-4;
-      double cv=1449.1+.00821*pp+4.55*tp-.045*(tp*tp)+1.34*(sp-35.0);
-      double cck=cv/sqrt((1.-.01642*pp/cv)*(1.-0.40*pp/(cv*cv)));
-      double qb=fabs(q2b(i,j,k)), qlb=fabs(q2lb(i,j,k));
-      q2b(i,j,k)=qb;                                                          // :1325-1326
-      q2lb(i,j,k)=qlb;
-      const double rhok=rho(i,j,k);
-      double boygr=grav*(rhom-rhok)/(dzz(k-1)*hh)
-                   +(grav*grav)*2./(ccm*ccm+cck*cck);                         // :1327-1330
-      ccm=cck; rhom=rhok;
-      double ll=fabs(qlb/qb);                                                 // :1338
-      if (z(k) > -0.5) ll=fmax(ll,kl0);                                       // :1339
-      double gh=(ll*ll)*boygr/qb;                                             // :1343
-      gh=fmin(gh,.028);                                                       // :1344
-      l(i,j,k)=ll;
-      const double u0=u(i,j,k), uE=u(i+1,j,k), v0=v(i,j,k), vN=v(i,j+1,k);
-      const double kmk=km(i,j,k), khk=kh(i,j,k);
-      double pr;
-      {
-        double su=u0-um+uE-uEm;
-        double sv=v0-vm+vN-vNm;
-        double dd=dzz(k-1)*dh;
-        pr=kmk*.25*sef*(su*su+sv*sv)/(dd*dd)-shiw*kmk*boygr;                  // :1362-1369
-        pr=pr+khk*boygr;                                                      // :1370
-      }
-      um=u0; uEm=uE; vm=v0; vNm=vN;
-      double dtf=sqrt(fabs(qb))*1./(b1*ll+small);                             // :1388-1389 (stf=1)
-      // tridiagonal coefficients from the OLD kq (:1258-1267)
-      const double kqp=kq(i,j,k+1);
-      const double a=-dti2*(kqp+kq0+2.*umol)*.5/(dzz(k-1)*dz(k)*dh*dh);
-      const double cq=-dti2*(kqm+kq0+2.*umol)*.5/(dzz(k-1)*dz(k-1)*dh*dh);
-      // q2 forward elimination (:1394-1404)
-      {
-        double gi=1./(a+cq*(1.-eem)-(2.*dti2*dtf+1.));
-        eem=a*gi;
-        ggm=(-2.*dti2*pr+cq*ggm-uf(i,j,k))*gi;
-        ee[k]=eem; gg[k]=ggm;
-      }
-      // q2l forward elimination (:1417-1446)
-      {
-        double r=(1./fabs(z(k)-z(1))+1./fabs(z(k)-z(kb)))*ll/(dh*kappa);
-        double dtf2=dtf*(1.+e2*(r*r));                                        // :1429-1432
-        if (k == 2) {
-          e2m=0.;                                                             // :1421
-          g2m=-kappa*z(2)*dh*q2_2;                                            // :1422
-        } else {
-          // :1423 assigns vf(kbm1)=kappa*(1+z(kbm1))*dh*q2(kbm1) before this sweep reads it
-          double vk=(k == kbm1) ? kappa*(1+z(kbm1))*dh*q2(i,j,kbm1) : vf(i,j,k);
-          double gi=1./(a+cq*(1.-e2m)-(dti2*dtf2+1.));
-          e2m=a*gi;
-          g2m=(dti2*(-pr*ll*e1)+cq*g2m-vk)*gi;
-        }
-        e2v[k]=e2m; g2v[k]=g2m;
-      }
-      // km, kh, kq (:1478-1506) -- in place; kq's old value stays in kqm for level k+1
-      {
-        double sh=coef1/(1.-coef2*gh);
-        double sm=coef3+sh*coef4*gh;
-        sm=sm/(1.-coef5*gh);
-        double pq=ll*sqrt(fabs(q2(i,j,k)));
-        const double nq=(pq*.41*sh+kq0)*.5, nm=(pq*sm+kmk)*.5, nh=(pq*sh+khk)*.5;
-        POM_PUT_K(k, nq, nm, nh);
-      }
-      kqm=kq0; kq0=kqp;
-    }
-    // ---- level kb: l=0, gh=0 ----
+    double tp=o(T,0,0)+tbias, sp=o(S,0,0)+sbias;
+    double pp=grav*rhoref*(-zz(k)*hh)*1.e-4;
+    double cv=1449.1+.00821*pp+4.55*tp-.045*(tp*tp)+1.34*(sp-35.0);
+    double cck=cv/sqrt((1.-.01642*pp/cv)*(1.-0.40*pp/(cv*cv)));
+    double qb=fabs(o(Q2B,0,0)), qlb=fabs(o(Q2LB,0,0));
+    q2b(i,j,k)=qb;                                                            // :1325-1326
+    q2lb(i,j,k)=qlb;
+    const double rhok=o(RHO,0,0);
+    double boygr=grav*(st.rhom-rhok)/(dzz(k-1)*hh)
+                 +(grav*grav)*2./(st.ccm*st.ccm+cck*cck);                     // :1327-1330
+    st.ccm=cck; st.rhom=rhok;
+    double ll=fabs(qlb/qb);                                                   // :1338
+    if (z(k) > -0.5) ll=fmax(ll,st.kl0);                                      // :1339
+    double gh=(ll*ll)*boygr/qb;                                               // :1343
+    gh=fmin(gh,.028);                                                         // :1344
+    l(i,j,k)=ll;
+    const double u0=o(U,0,0), uE=o(U,1,0), v0=o(V,0,0), vN=o(V,0,1);
+    const double kmk=o(KM,0,0), khk=o(KH,0,0);
+    double pr;
     {
-      double sh=coef1/(1.-coef2*0.);
-      double sm=coef3+sh*coef4*0.;
-      sm=sm/(1.-coef5*0.);
-      double pq=0.*sqrt(fabs(q2(i,j,kb)));
-      const double nq=(pq*.41*sh+kq0)*.5, nm=(pq*sm+km(i,j,kb))*.5, nh=(pq*sh+kh(i,j,kb))*.5;
-      POM_PUT_K(kb, nq, nm, nh);
+      double su=u0-st.um+uE-st.uEm;
+      double sv=v0-st.vm+vN-st.vNm;
+      double dd=dzz(k-1)*dh;
+      pr=kmk*.25*sef*(su*su+sv*sv)/(dd*dd)-shiw*kmk*boygr;                    // :1362-1369
+      pr=pr+khk*boygr;                                                        // :1370
     }
-#undef POM_PUT_K
-    // ---- back-substitutions (:1406-1413, :1448-1455) and abs (:1460-1471) ----
-    // the recurrences use the signed iterate; abs() is applied by the reference afterwards
+    st.um=u0; st.uEm=uE; st.vm=v0; st.vNm=vN;
+    double dtf=sqrt(fabs(qb))*1./(b1*ll+small);                               // :1388-1389 (stf=1)
+    // tridiagonal coefficients from the OLD kq (:1258-1267)
+    const double kqp=o.up(KQ);
+    const double kq0=st.kq0;
+    const double a=-dti2*(kqp+kq0+2.*umol)*.5/(dzz(k-1)*dz(k)*dh*dh);
+    const double cq=-dti2*(st.kqm+kq0+2.*umol)*.5/(dzz(k-1)*dz(k-1)*dh*dh);
+    // q2 forward elimination (:1394-1404)
     {
-      double up=uf(i,j,kb);
-      for (int ki = kbm1; ki >= 1; --ki) {
-        up=ee[ki]*up+gg[ki];
-        uf(i,j,ki)=(ki >= 2) ? fabs(up) : up;
-      }
-      double vp = 0.;                                                         // vf(kb)=0 (:1420)
-      vf(i,j,kb)=0.;
-      for (int ki = kbm1; ki >= 2; --ki) {
-        vp=e2v[ki]*vp+g2v[ki];
-        vf(i,j,ki)=fabs(vp);
-      }
-      vf(i,j,1)=0.;                                                           // :1419
+      double gi=1./(a+cq*(1.-st.eem)-(2.*dti2*dtf+1.));
+      st.eem=a*gi;
+      st.ggm=(-2.*dti2*pr+cq*st.ggm-o(UF,0,0))*gi;
+      cm.ee[k]=st.eem; cm.gg[k]=st.ggm;
     }
+    // q2l forward elimination (:1417-1446)
+    {
+      double r=zr[k]*ll/(dh*kappa);
+      double dtf2=dtf*(1.+e2*(r*r));                                          // :1429-1432
+      if (k == 2) {
+        st.e2m=0.;                                                            // :1421
+        st.g2m=-kappa*z(2)*dh*st.q2_2;                                        // :1422
+      } else {
+        // :1423 assigns vf(kbm1)=kappa*(1+z(kbm1))*dh*q2(kbm1) before this sweep reads it
+        double vk=(k == kbm1) ? kappa*(1+z(kbm1))*dh*o(Q2,0,0) : o(VF,0,0);
+        double gi=1./(a+cq*(1.-st.e2m)-(dti2*dtf2+1.));
+        st.e2m=a*gi;
+        st.g2m=(dti2*(-pr*ll*e1)+cq*st.g2m-vk)*gi;
+      }
+      cm.e2v[k]=st.e2m; cm.g2v[k]=st.g2m;
+    }
+    // km, kh, kq (:1478-1506) -- in place; kq's old value stays in kqm for level k+1
+    {
+      double sh=coef1/(1.-coef2*gh);
+      double sm=coef3+sh*coef4*gh;
+      sm=sm/(1.-coef5*gh);
+      double pq=ll*sqrt(fabs(o(Q2,0,0)));
+      const double nq=(pq*.41*sh+kq0)*.5, nm=(pq*sm+kmk)*.5, nh=(pq*sh+khk)*.5;
+      put_k(i,j,k,st,nq,nm,nh);
+    }
+    st.kqm=kq0; st.kq0=kqp;
+  }
+  // ---- back-substitutions (:1406-1413, :1448-1455) and abs (:1460-1471) ----
+  // the recurrences use the signed iterate; abs() is applied by the reference afterwards
+  POM_HD void post(int i, int j, State& st, Cols& cm) const {
+    POM_DIMS;
+    if (!st.interior) return;
+    double up=st.ufkb;
+    for (int ki = kbm1; ki >= 1; --ki) {
+      up=cm.ee[ki]*up+cm.gg[ki];
+      uf(i,j,ki)=(ki >= 2) ? fabs(up) : up;
+    }
+    double vp = 0.;                                                           // vf(kb)=0 (:1420)
+    vf(i,j,kb)=0.;
+    for (int ki = kbm1; ki >= 2; --ki) {
+      vp=cm.e2v[ki]*vp+cm.g2v[ki];
+      vf(i,j,ki)=fabs(vp);
+    }
+    vf(i,j,1)=0.;                                                             // :1419
   }
 };
 
@@ -1069,7 +1090,7 @@ struct FbRoundTripK : KBase {
 void run_uvadjust(Ctx* c, int j0, int j1) { launch_cols(c, UvAdjustK(c), ALLI, j0, j1); }
 void run_vertvl(Ctx* c, int j0, int j1) { launch_cols(c, VertvlK(c), ALLI, j0, j1); }
 void run_advq(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvqK(c), ALLI, j0, j1); }
-void run_profq(Ctx* c, int j0, int j1) { launch_cols(c, ProfqK(c), ALLI, j0, j1); }
+void run_profq(Ctx* c, int j0, int j1) { launch_tma_cols(c, ProfqK(c, c->hz), ALLI, j0, j1); }
 // caller swaps q2<->uf, q2l<->vf (advance.f:418-421)
 void run_qfilter(Ctx* c, int j0, int j1) { launch_cols(c, QFilterK(c), ALLI, j0, j1); }
 void run_advt(Ctx* c, int nadv, const double* fb, const double* f, const double* fc, double* ff, int j0, int j1) {

@@ -263,6 +263,8 @@ int ctx_push(Ctx* c, const char* name, const double* host) {
   double** slot = ctx_slot(c, name, &f);
   if (!slot) { snprintf(c->err, sizeof(c->err), "unknown field '%s'", name); return 2; }
   if (!*slot && dev_alloc(c, slot, field_elems(c, f))) return 1;
+  if (!strcmp(name, "z"))
+    for (int k = 0; k < c->g.kb && k < 128; ++k) c->hz[k] = host[k];
   return dev_h2d(c, *slot, host, field_elems(c, f));
 }
 

@@ -148,6 +148,77 @@ tmakernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1
   if (out) f.post(i, j, st);
 }
 
+// Column kernels on the same TMA ring: no flux exchange between threads (thread tile = output
+// tile), only the operand staging.  F provides NF, NS, TY, OHL/OHR/OHB/OHT, BW, BH, UP, NK,
+// fields(), k0(), k1(), kl1(), pre(i,j,State&,Cols&), level(i,j,k,State&,Cols&,op),
+// post(i,j,State&,Cols&); Cols holds the dynamically indexed per-thread arrays (local memory) so
+// that the scalars of State stay in registers.
+// `post` runs the upward sweeps (Thomas back-substitution) on the thread's own column.
+template <class F>
+__global__ void __launch_bounds__(TILE_X * F::TY, F::MINB)
+tmacolkernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1, int j0, int j1) {
+  constexpr int NF = F::NF, NS = F::NS, PL = tma_plane(F::BW, F::BH);
+  extern __shared__ __align__(128) double pom_tsm[];
+  double* ring = pom_tsm;
+  uint64_t* bar = (uint64_t*)(ring + NS * NF * PL);
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ti0 = i0 + blockIdx.x * TILE_X, tj0 = j0 + blockIdx.y * F::TY;
+  const int i = ti0 + tx, j = tj0 + ty;
+  static_assert(F::BW % 2 == 0 && F::BW >= TILE_X + F::OHL + F::OHR + 1, "TMA box too narrow");
+  static_assert(F::BH >= F::TY + F::OHB + F::OHT, "TMA box too short");
+  const int n0 = ti0 - 1 - F::OHL, shift = n0 & 1;
+  const int c0 = n0 - shift, c1 = tj0 - 1 - f.g.joff - F::OHB;
+  const int k0 = f.k0(), k1 = f.k1(), kl1 = f.kl1();
+  const bool leader = (tx == 0 && ty == 0);
+  if (leader) {
+    for (int s = 0; s < NS; ++s) mbar_init(&bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int L) {
+    const int s = (L - k0) % NS;
+    mbar_expect_tx(&bar[s], (uint32_t)(NF * F::BW * F::BH * sizeof(double)));
+#pragma unroll
+    for (int n = 0; n < NF; ++n) tma_load_3d(ring + (s * NF + n) * PL, &maps.m[n], &bar[s], c0, c1, L - 1);
+  };
+  if (leader)
+    for (int L = k0; L < k0 + NS && L <= kl1; ++L) issue(L);
+  const bool active = (i <= i1 && j <= j1);
+  typename F::State st;     // scalars: registers
+  typename F::Cols cm;      // per-thread column arrays (dynamically indexed: local memory)
+  if (active) f.pre(i, j, st, cm);
+  const int own = (ty + F::OHB) * F::BW + tx + F::OHL + shift;
+  for (int k = k0; k <= k1; ++k) {
+    const int q0 = k - k0, s0 = q0 % NS;
+    mbar_wait(&bar[s0], (q0 / NS) & 1);
+    int s1 = s0;
+    if (F::UP && k + 1 <= kl1) {
+      s1 = (q0 + 1) % NS;
+      mbar_wait(&bar[s1], ((q0 + 1) / NS) & 1);
+    }
+    const SmemOp<F> op{ring + s0 * NF * PL + own, ring + s1 * NF * PL + own};
+    if (active) f.level(i, j, k, st, cm, op);
+    __syncthreads();
+    if (leader && k + NS <= kl1) issue(k + NS);   // everyone is done with the stage of level k
+  }
+  if (active) f.post(i, j, st, cm);
+}
+
+template <class F>
+__global__ void __launch_bounds__(TILE_X * F::TY, F::MINB)
+colkernel_g(const F f, int i0, int i1, int j0, int j1) {
+  const int i = i0 + blockIdx.x * TILE_X + threadIdx.x, j = j0 + blockIdx.y * F::TY + threadIdx.y;
+  if (i > i1 || j > j1) return;
+  const double* fld[F::NF];
+  f.fields(fld);
+  typename F::State st;
+  typename F::Cols cm;
+  f.pre(i, j, st, cm);
+  const int k1 = f.k1();
+  for (int k = f.k0(); k <= k1; ++k) f.level(i, j, k, st, cm, GlobalOp<F>{fld, f.g, i, j, k});
+  f.post(i, j, st, cm);
+}
+
 // the same functor on direct global loads (layouts the TMA cannot address)
 template <class F>
 __global__ void __launch_bounds__(TILE_X * F::TY, 1)
@@ -244,6 +315,50 @@ inline void launch_tma_tiles(Ctx* c, const F& f, int i0, int i1, int j0, int j1)
     }
   }
   if (!tma_ok) tilekernel_g<F><<<gr, b, 0, (cudaStream_t)c->stream>>>(f, i0, i1, j0, j1);
+  if (c->prof_on) prof_after(c);
+#endif
+}
+
+template <class F>
+inline void launch_tma_cols(Ctx* c, const F& f, int i0, int i1, int j0, int j1) {
+  if (i1 < i0 || j1 < j0) return;
+  c->launches++;
+#ifdef POMGPU_EMU
+  const double* fld[F::NF];
+  f.fields(fld);
+  static typename F::State st;
+  static typename F::Cols cm;
+  for (int j = j0; j <= j1; ++j)
+    for (int i = i0; i <= i1; ++i) {
+      f.pre(i, j, st, cm);
+      for (int k = f.k0(); k <= f.k1(); ++k) f.level(i, j, k, st, cm, GlobalOp<F>{fld, f.g, i, j, k});
+      f.post(i, j, st, cm);
+    }
+#else
+  if (c->prof_on) {
+    const KInfo& k = F::info();
+    double cols = (double)(i1 - i0 + 1) * (j1 - j0 + 1);
+    prof_before(c, &k, 8. * cols * ((k.r3 + k.w3) * (double)c->g.kb + (k.r2 + k.w2)));
+  }
+  dim3 b(TILE_X, F::TY), gr((i1 - i0 + TILE_X) / TILE_X, (j1 - j0 + F::TY) / F::TY);
+  bool tma_ok = (c->g.im % 2 == 0) && !c->no_tma;
+  if (tma_ok) {
+    TmaMaps<F::NF> maps;
+    const double* fld[F::NF];
+    f.fields(fld);
+    for (int n = 0; n < F::NF && tma_ok; ++n)
+      if (tma_encode(c, &maps.m[n], fld[n], F::NK ? F::NK : c->g.kb, F::BW, F::BH)) tma_ok = false;
+    if (tma_ok) {
+      constexpr size_t smem = (size_t)(F::NS * F::NF * tma_plane(F::BW, F::BH)) * sizeof(double) + F::NS * 8;
+      static bool granted = false;
+      if (!granted) {
+        cudaFuncSetAttribute(tmacolkernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        granted = true;
+      }
+      tmacolkernel<F><<<gr, b, smem, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
+    }
+  }
+  if (!tma_ok) colkernel_g<F><<<gr, b, 0, (cudaStream_t)c->stream>>>(f, i0, i1, j0, j1);
   if (c->prof_on) prof_after(c);
 #endif
 }
