@@ -7,6 +7,7 @@
 // becomes a write of the filtered field into the dead "b" buffer followed by a
 // pointer rotation on the host.
 #include "pom_core.h"
+#include "pom_tma.h"
 #include "pom_names.h"
 
 namespace pom {
@@ -209,6 +210,192 @@ struct ExtUvK : KBase {
   }
 };
 
+// ------------------------------------------------------------------------------------------
+// One external substep in ONE kernel (advance.f:211-350): elf + bcond(1), advave, uaf/vaf +
+// bcond(2), etf, Asselin filter, running means.  Three phases on a TMA-staged tile with two
+// neighbour exchanges through shared memory (pom_tma.h: tile3kernel):
+//   A  own-point transports fua,fva (advance.f:211-218) and the four advave fluxes
+//   B  elf(i,j) with bcond(1) from the neighbours' transports; advua, advva (kept in registers)
+//   C  uaf,vaf (+bcond(2)) from elf(i,j), elf(i-1,j), elf(i,j-1); everything point-wise after
+// 13 fields are read with neighbours (staged, halo 1), 18 at the own point only.  The filtered
+// uab,vab go to the scratch buffers s2a,s2b (advave reads uab,vab of the neighbours); the
+// caller rotates ua<->uaf, va<->vaf, uab<->s2a, vab<->s2b, elb<->el2, el<->elf, d<->d2.
+struct ExtStepK : KBase {
+  POM_KINFO("ext_step", 0, 0, 31, 12)
+  int iext, do_adv;
+  ExtStepK(const Ctx* x, int ie, int adv) : KBase(x), iext(ie), do_adv(adv) {}
+  static constexpr int NV = 6, TY = 16, MINB = 2;
+  static constexpr int NF = 13, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = 18, NK = 1;
+  enum { D, UA, VA, UAB, VAB, AAM2D, DX, DY, EL, ELB, H, COR, EATM };
+  enum { FUA, FVA, FXU, FYU, FXV, FYV };
+  POM_HD void fields(const double** b) const {
+    b[D] = p.d; b[UA] = p.ua; b[VA] = p.va; b[UAB] = p.uab; b[VAB] = p.vab; b[AAM2D] = p.aam2d; b[DX] = p.dx;
+    b[DY] = p.dy; b[EL] = p.el; b[ELB] = p.elb; b[H] = p.h; b[COR] = p.cor; b[EATM] = p.e_atmos;
+  }
+  struct State { double au, av; };
+  POM_HD void pre(int i, int j, bool inside, State& s) const {
+    s.au = 0.; s.av = 0.;
+    // the 18 point-wise operands of phase C: start them towards L2 now, while the TMA stages
+    // the stencil operands (one thread per 128-byte line)
+    if (inside && ((i - 1) & 15) == 0) {
+      const int o = POM_I2(i,j);
+      POM_PREFETCH_L2(p.art+o); POM_PREFETCH_L2(p.vfluxf+o); POM_PREFETCH_L2(p.fsm+o); POM_PREFETCH_L2(p.aru+o);
+      POM_PREFETCH_L2(p.arv+o); POM_PREFETCH_L2(p.adx2d+o); POM_PREFETCH_L2(p.ady2d+o); POM_PREFETCH_L2(p.drx2d+o);
+      POM_PREFETCH_L2(p.dry2d+o); POM_PREFETCH_L2(p.wusurf+o); POM_PREFETCH_L2(p.wubot+o); POM_PREFETCH_L2(p.wvsurf+o);
+      POM_PREFETCH_L2(p.wvbot+o); POM_PREFETCH_L2(p.dum+o); POM_PREFETCH_L2(p.dvm+o); POM_PREFETCH_L2(p.egf+o);
+      POM_PREFETCH_L2(p.utf+o); POM_PREFETCH_L2(p.vtf+o);
+      if (iext >= c.isplit - 1) POM_PREFETCH_L2(p.etf+o);
+    }
+  }
+  template <class Op>
+  POM_HD void phaseA(int i, int j, State&, const Op& o, double* v) const {
+    POM_DIMS;
+    const int jlo = g.joff + 1, jhi = g.joff + g.jml;
+    const double d00=o(D,0,0);
+    if (i >= 2) v[FUA]=.25*(d00+o(D,-1,0))*(o(DY,0,0)+o(DY,-1,0))*o(UA,0,0);          // advance.f:213-214
+    if (j >= 2 && j - 1 >= jlo) v[FVA]=.25*(d00+o(D,0,-1))*(o(DX,0,0)+o(DX,0,-1))*o(VA,0,0);   // :215-216
+    if (!do_adv || i < 2 || j < 2 || j - 1 < jlo) return;
+    // ---- advave (solver.f:16-121), own-point fluxes of the u and the v half ----
+    const double dW=o(D,-1,0), dS=o(D,0,-1), dSW=o(D,-1,-1);
+    const double ua00=o(UA,0,0), va00=o(VA,0,0), uaS=o(UA,0,-1), vaW=o(VA,-1,0);
+    const double dx00=o(DX,0,0), dy00=o(DY,0,0);
+    const double dx4=dx00+o(DX,-1,0)+o(DX,0,-1)+o(DX,-1,-1);
+    const double dy4=dy00+o(DY,-1,0)+o(DY,0,-1)+o(DY,-1,-1);
+    const double am00=o(AAM2D,0,0), uab00=o(UAB,0,0), vab00=o(VAB,0,0);
+    // tps(i,j), 2<=i<=im, 2<=j<=jm (:47-53)
+    const double tp=.25*(d00+dW+dS+dSW)
+                    *(am00+o(AAM2D,0,-1)+o(AAM2D,-1,0)+o(AAM2D,-1,-1))
+                    *((uab00-o(UAB,0,-1))/dy4+(vab00-o(VAB,-1,0))/dx4);
+    {   // u half fluxva (:30-32,55-56) and v half fluxua (:80-82,106-107)
+      double a=.125*((d00+dS)*va00+(dW+dSW)*vaW)*(ua00+uaS);
+      v[FYU]=(a-tp)*.25*dx4;
+      double b=.125*((d00+dW)*ua00+(dS+dSW)*uaS)*(vaW+va00);
+      v[FXV]=(b-tp)*.25*dy4;
+    }
+    if (i <= imm1) {   // u half fluxua (:22-24,39-41,54)
+      const double dE=o(D,1,0), uaE=o(UA,1,0);
+      double a=.125*((dE+d00)*uaE+(d00+dW)*ua00)*(uaE+ua00);
+      a=a-d00*2.*am00*(o(UAB,1,0)-uab00)/dx00;
+      v[FXU]=a*dy00;
+    }
+    if (j <= jmm1 && j + 1 <= jhi) {   // v half fluxva (:88-90,97-99,105)
+      const double dN=o(D,0,1), vaN=o(VA,0,1);
+      double a=.125*((dN+d00)*vaN+(d00+dS)*va00)*(vaN+va00);
+      a=a-d00*2.*am00*(o(VAB,0,1)-vab00)/dy00;
+      v[FYV]=a*dx00;
+    }
+  }
+  // elf(i,j) after bcond(1) (bounds_forcing.f:21-39): W,E copies then S,N copies = the value
+  // at the index clamped into the interior, times fsm; advua/advva of interior points
+  template <class Op>
+  POM_HD double phaseB(int i, int j, State& s, const Op& o, const Tile2& S, bool nbr) const {
+    POM_DIMS;
+    const int ic = i < 2 ? 2 : (i > imm1 ? imm1 : i);
+    const int jc = j < 2 ? 2 : (j > jmm1 ? jmm1 : j);
+    const int di = ic - i, dj = jc - j;
+    const double ef=o(ELB,di,dj)+dte2*(-(S(FUA,di+1,dj)-S(FUA,di,dj)+S(FVA,di,dj+1)-S(FVA,di,dj))/art(ic,jc)
+                                     -vfluxf(ic,jc));                     // advance.f:224-227
+    if (nbr && i >= 2 && i <= imm1 && j >= 2 && j <= jmm1) {
+      if (do_adv) {
+        s.au=S(FXU,0,0)-S(FXU,-1,0)+S(FYU,0,1)-S(FYU,0,0);                // solver.f:65-66
+        s.av=S(FXV,1,0)-S(FXV,0,0)+S(FYV,0,0)-S(FYV,0,-1);                // :116-117
+      } else {
+        s.au=advua(i,j); s.av=advva(i,j);
+      }
+    }
+    return ef*fsm(i,j);
+  }
+  template <class Op>
+  POM_HD void phaseC(int i, int j, State& s, const Op& o, const Tile2&, const Tile2& E) const {
+    POM_DIMS;
+    const bool jin = (j >= 2 && j <= jmm1), iin = (i >= 2 && i <= imm1);
+    const double ef=E(0,0);
+    const double d00=o(D,0,0), el00=o(EL,0,0), elb00=o(ELB,0,0), h00=o(H,0,0), ua00=o(UA,0,0), va00=o(VA,0,0);
+    elf(i,j)=ef;
+    if (do_adv) { advua(i,j)=s.au; advva(i,j)=s.av; }
+    double un, vn;
+    // ---- uaf(i,j) after bcond(2); cells never assigned keep uaf's content ----
+    if (jin) {
+      if (i == 1 || i == 2) {                                             // bounds_forcing.f:48-50
+        const int q = 2 - i;
+        un=ramp*(uabw(j)-rfw*sqrt(grav/o(D,q,0))*(o(EL,q,0)-elw(j)));
+      } else if (i == im) {                                               // :57-59
+        un=ramp*(uabe(j)+rfe*sqrt(grav/o(D,-1,0))*(o(EL,-1,0)-ele(j)));
+      } else {                                                            // advance.f:239-260
+        const double dW=o(D,-1,0), ar=aru(i,j), efW=E(-1,0), elbW=o(ELB,-1,0), hW=o(H,-1,0);
+        double r=adx2d(i,j)+s.au
+                 -ar*.25
+                   *(o(COR,0,0)*d00*(o(VA,0,1)+va00)
+                    +o(COR,-1,0)*dW*(o(VA,-1,1)+o(VA,-1,0)))
+                 +.25*grav*(o(DY,0,0)+o(DY,-1,0))
+                   *(d00+dW)
+                   *((1.-2.*alpha)*(el00-o(EL,-1,0))
+                     +alpha*(elb00-elbW+ef-efW)
+                     +o(EATM,0,0)-o(EATM,-1,0))
+                 +drx2d(i,j)+ar*(wusurf(i,j)-wubot(i,j));
+        un=((h00+elb00+hW+elbW)*ar*o(UAB,0,0)
+            -4.*dte*r)
+           /((h00+ef+hW+efW)*ar);
+      }
+    } else if (iin) {
+      un = (j == 1) ? uabs(i) : uabn(i);
+    } else {
+      un = uaf(i,j);   // four corners: never assigned (advance.f:237-262, bcond(2))
+    }
+    if (iin) {
+      if (j == 1 || j == 2) {                                             // bounds_forcing.f:65-67
+        const int q = 2 - j;
+        vn=ramp*(vabs(i)-rfs*sqrt(grav/o(D,0,q))*(o(EL,0,q)-els(i)));
+      } else if (j == jm) {                                               // :74-76
+        vn=ramp*(vabn(i)+rfn*sqrt(grav/o(D,0,-1))*(o(EL,0,-1)-eln(i)));
+      } else {                                                            // advance.f:266-286
+        const double dS=o(D,0,-1), ar=arv(i,j), efS=E(0,-1), elbS=o(ELB,0,-1), hS=o(H,0,-1);
+        double r=ady2d(i,j)+s.av
+                 +ar*.25
+                   *(o(COR,0,0)*d00*(o(UA,1,0)+ua00)
+                    +o(COR,0,-1)*dS*(o(UA,1,-1)+o(UA,0,-1)))
+                 +.25*grav*(o(DX,0,0)+o(DX,0,-1))
+                   *(d00+dS)
+                   *((1.-2.*alpha)*(el00-o(EL,0,-1))
+                     +alpha*(elb00-elbS+ef-efS)
+                     +o(EATM,0,0)-o(EATM,0,-1))
+                 +dry2d(i,j)+ar*(wvsurf(i,j)-wvbot(i,j));
+        vn=((h00+elb00+hS+elbS)*ar*o(VAB,0,0)
+            -4.*dte*r)
+           /((h00+ef+hS+efS)*ar);
+      }
+    } else if (jin) {
+      vn = (i == 1) ? vabw(j) : vabe(j);
+    } else {
+      vn = vaf(i,j);
+    }
+    un=un*dum(i,j);                                      // bounds_forcing.f:80-81
+    vn=vn*dvm(i,j);
+    uaf(i,j)=un;
+    vaf(i,j)=vn;
+    // ---- etf accumulation on the last three substeps (advance.f:295-318) ----
+    if (iext == c.isplit-2) etf(i,j)=.25*smoth*ef;
+    else if (iext == c.isplit-1) etf(i,j)=etf(i,j)+.5*(1.-.5*smoth)*ef;
+    else if (iext == c.isplit) etf(i,j)=(etf(i,j)+.5*ef)*fsm(i,j);
+    // ---- Asselin filter (advance.f:321-323): the filtered n-level goes to buffers no
+    //      neighbour reads in this kernel ----
+    A2(p.s2a,i,j)=ua00+.5*smoth*(o(UAB,0,0)-2.*ua00+un);
+    A2(p.s2b,i,j)=va00+.5*smoth*(o(VAB,0,0)-2.*va00+vn);
+    el2(i,j)=el00+.5*smoth*(elb00-2.*el00+ef);
+    const double dn=h00+ef;                              // advance.f:326
+    d2(i,j)=dn;
+    // the four corners of uaf/vaf are never assigned by the reference and so persist;
+    // seed the buffer that becomes uaf/vaf after the rotation (no stencil ever reads them)
+    if (!jin && !iin) { ua(i,j)=un; va(i,j)=vn; }
+    // ---- running means (advance.f:332-347) ----
+    if (iext != c.isplit) {
+      egf(i,j)=egf(i,j)+ef*ispi;
+      if (i >= 2) utf(i,j)=utf(i,j)+un*(dn+(o(H,-1,0)+E(-1,0)))*isp2i;
+      if (j >= 2) vtf(i,j)=vtf(i,j)+vn*(dn+(o(H,0,-1)+E(0,-1)))*isp2i;
+    }
+  }
+};
+
 void run_advave(Ctx* c, int j0, int j1) { launch_tiles(c, AdvaveK(c), 1, c->g.im, j0, j1); }
 void run_mode_inter_tail(Ctx* c, int j0, int j1) { launch_cols(c, ModeInterTailK(c), 1, c->g.im, j0, j1); }
 void run_ext_elf(Ctx* c, int j0, int j1) { launch_cols(c, ExtElfK(c), 1, c->g.im, j0, j1); }
@@ -217,4 +404,9 @@ void run_ext_elf(Ctx* c, int j0, int j1) { launch_cols(c, ExtElfK(c), 1, c->g.im
 // ua<->uaf, va<->vaf, elb<->el2, el<->elf, d<->d2
 void run_ext_uv(Ctx* c, int iext, int j0, int j1) { launch_cols(c, ExtUvK(c, iext), 1, c->g.im, j0, j1); }
 
+}  // namespace pom
+
+namespace pom {
+// fused external substep; the caller rotates the time levels afterwards
+void run_ext_step(Ctx* c, int iext, int do_adv, int j0, int j1) { launch_tile3(c, ExtStepK(c, iext, do_adv), 1, c->g.im, j0, j1); }
 }  // namespace pom

@@ -26,6 +26,7 @@ void run_advave(Ctx*, int, int);
 void run_mode_inter_tail(Ctx*, int, int);
 void run_ext_elf(Ctx*, int, int);
 void run_ext_uv(Ctx*, int iext, int, int);
+void run_ext_step(Ctx*, int iext, int do_adv, int, int);
 void run_uvadjust(Ctx*, int, int);
 void run_vertvl(Ctx*, int, int);
 void run_advq(Ctx*, int, int);
@@ -111,23 +112,23 @@ static void k_mode_inter_tail(Group* G) {
   EACH(run_mode_inter_tail(c, j0, j1));
   MADE(e, F_adx2d, F_ady2d, F_egf, F_utf, F_vtf);
 }
-static void k_ext_elf(Group* G) {
-  int e = NEED({F_d, 1}, {F_va, 1}, {F_ua, 0}, {F_elb, 0});
-  EACH(run_ext_elf(c, j0, j1));
-  MADE(e, F_elf);
-}
-static void k_ext_uv(Group* G, int iext) {
+// one external substep (advance.f:205-353) in one kernel; output row j depends on the staged
+// operands of rows j-2..j+1 (elf(j-1) <- transports(j-1) <- d,va(j-2))
+static void k_ext_step(Group* G, int iext, int do_adv) {
   const int isplit = G->c[0]->c.isplit;
-  int e = NEED({F_adx2d, 0}, {F_advua, 0}, {F_ady2d, 0}, {F_advva, 0}, {F_d, 1}, {F_va, 1}, {F_ua, 1},
-               {F_el, 1}, {F_elb, 1}, {F_elf, 1}, {F_drx2d, 0}, {F_dry2d, 0}, {F_wubot, 0}, {F_wvbot, 0},
-               {F_uab, 0}, {F_vab, 0}, {F_egf, 0}, {F_utf, 0}, {F_vtf, 0});
+  int e = NEED({F_d, 2}, {F_ua, 2}, {F_va, 2}, {F_uab, 2}, {F_vab, 2}, {F_aam2d, 2}, {F_el, 1}, {F_elb, 1},
+               {F_adx2d, 0}, {F_ady2d, 0}, {F_drx2d, 0}, {F_dry2d, 0}, {F_wubot, 0}, {F_wvbot, 0},
+               {F_egf, 0}, {F_utf, 0}, {F_vtf, 0});
+  if (!do_adv) { const Req q[] = {{F_advua, 0}, {F_advva, 0}}; int e2 = group_need(G, q, 2); if (e2 < e) e = e2; }
   if (iext > isplit - 2) { const Req q[] = {{F_etf, 0}}; int e2 = group_need(G, q, 1); if (e2 < e) e = e2; }
-  EACH(run_ext_uv(c, iext, j0, j1));
-  MADE(e, F_uaf, F_vaf, F_uab, F_vab, F_el2, F_d2, F_ua, F_va);
+  EACH(run_ext_step(c, iext, do_adv, j0, j1));
+  MADE(e, F_elf, F_uaf, F_vaf, F_s2a, F_s2b, F_el2, F_d2, F_ua, F_va);
+  if (do_adv) MADE(e, F_advua, F_advva);
   if (iext >= isplit - 2) MADE(e, F_etf);
   if (iext != isplit) MADE(e, F_egf, F_utf, F_vtf);
   // time rotation (advance.f:324-330)
   group_swap(G, F_ua, F_uaf); group_swap(G, F_va, F_vaf);
+  group_swap(G, F_uab, F_s2a); group_swap(G, F_vab, F_s2b);
   group_swap(G, F_elb, F_el2); group_swap(G, F_el, F_elf);
   group_swap(G, F_d, F_d2);
 }
@@ -234,9 +235,7 @@ static int mode_interaction(Group* G) {
 // advance.f:205-353
 static int mode_external(Group* G, int iext) {
   G->c[0]->c.iext = iext; CSYNC();
-  k_ext_elf(G);
-  if (iext % G->c[0]->c.ispadv == 0) k_advave(G);
-  k_ext_uv(G, iext);
+  k_ext_step(G, iext, iext % G->c[0]->c.ispadv == 0);
   return 0;
 }
 // one block of mode_internal (same numbering as the oracle's pomo_internal_stage)

@@ -46,6 +46,7 @@ struct GlobalOp {
 struct Tile2 {
   const double* s; int tx, ty;
   POM_HD double operator()(int v, int di, int dj) const { return s[(v * TILE_Y + (ty + dj)) * TILE_X + (tx + di)]; }
+  POM_HD double operator()(int di, int dj) const { return s[(ty + dj) * TILE_X + (tx + di)]; }
 };
 
 #ifndef POMGPU_EMU
@@ -315,6 +316,137 @@ inline void launch_tma_tiles(Ctx* c, const F& f, int i0, int i1, int j0, int j1)
     }
   }
   if (!tma_ok) tilekernel_g<F><<<gr, b, 0, (cudaStream_t)c->stream>>>(f, i0, i1, j0, j1);
+  if (c->prof_on) prof_after(c);
+#endif
+}
+
+// ---- single-level tile kernel with TWO neighbour exchanges (the fused external substep) ----
+// phaseA: own-point flux-like values v[NV] -> shared tile S; phaseB: one derived value per
+// point from the neighbours' S (-> shared tile E) plus private results kept in State;
+// phaseC: outputs from S, E and the staged operands.  F provides NF, NV, TY, OH*, BW, BH, NK,
+// fields(), pre(i,j,inside,State&), phaseA(i,j,State&,op,v), phaseB(i,j,State&,op,Tile2 S) -> double,
+// phaseC(i,j,State&,op,Tile2 S,Tile2 E).  Thread-tile halo is 1 on every side: phase B runs
+// on tx<=30, ty<=14, phase C (the outputs) on 1<=tx<=30, 1<=ty<=14.
+#ifndef POMGPU_EMU
+template <class F, bool TMA>
+__global__ void __launch_bounds__(TILE_X * F::TY, F::MINB)
+tile3kernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1, int j0, int j1) {
+  constexpr int NF = F::NF, NV = F::NV, PL = tma_plane(F::BW, F::BH);
+  constexpr int OX = TILE_X - 2, OY = F::TY - 2;
+  extern __shared__ __align__(128) double pom_tsm[];
+  double* ring = pom_tsm;                         // [NF][PL]   (TMA only)
+  double* S = ring + (TMA ? NF * PL : 0);         // [NV][TILE_Y][TILE_X]
+  double* E = S + NV * TILE_Y * TILE_X;           // [TILE_Y][TILE_X]
+  uint64_t* bar = (uint64_t*)(E + TILE_Y * TILE_X);
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ti0 = i0 + blockIdx.x * OX - 1, tj0 = j0 + blockIdx.y * OY - 1;
+  const int i = ti0 + tx, j = tj0 + ty;
+  const int n0 = ti0 - 1 - F::OHL, shift = n0 & 1;
+  const bool inside = (i >= 1 && i <= f.g.im && j >= f.g.joff + 1 && j <= f.g.joff + f.g.jml);
+  const bool out = (tx >= 1 && tx <= TILE_X - 2 && ty >= 1 && ty <= F::TY - 2 && i <= i1 && j <= j1 && inside);
+  const bool bok = (tx <= TILE_X - 2 && ty <= F::TY - 2 && inside);
+  typename F::State st;
+  if (TMA) {
+    static_assert(F::BW % 2 == 0 && F::BW >= TILE_X + F::OHL + F::OHR + 1, "TMA box too narrow");
+    static_assert(F::BH >= F::TY + F::OHB + F::OHT, "TMA box too short");
+    const bool leader = (tx == 0 && ty == 0);
+    if (leader) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(bar, (uint32_t)(NF * F::BW * F::BH * sizeof(double)));
+      const int c0 = n0 - shift, c1 = tj0 - 1 - f.g.joff - F::OHB;
+#pragma unroll
+      for (int n = 0; n < NF; ++n) tma_load_3d(ring + n * PL, &maps.m[n], bar, c0, c1, 0);
+    }
+    f.pre(i, j, inside, st);        // plain loads of the point-wise operands overlap the TMA
+    __syncthreads();                // barrier init visible to every waiter
+    mbar_wait(bar, 0);
+  } else {
+    f.pre(i, j, inside, st);
+  }
+  const double* fld[NF];
+  if (!TMA) f.fields(fld);
+  const int own = (ty + F::OHB) * F::BW + tx + F::OHL + shift;
+  const SmemOp<F> sop{ring + own, ring + own};
+  const GlobalOp<F> gop{fld, f.g, i, j, 1};
+  double v[NV];
+#pragma unroll
+  for (int n = 0; n < NV; ++n) v[n] = 0.;
+  if (inside) { if (TMA) f.phaseA(i, j, st, sop, v); else f.phaseA(i, j, st, gop, v); }
+#pragma unroll
+  for (int n = 0; n < NV; ++n) S[(n * TILE_Y + ty) * TILE_X + tx] = v[n];
+  __syncthreads();
+  double e = 0.;
+  if (bok) e = TMA ? f.phaseB(i, j, st, sop, Tile2{S, tx, ty}, tx >= 1 && ty >= 1) : f.phaseB(i, j, st, gop, Tile2{S, tx, ty}, tx >= 1 && ty >= 1);
+  E[ty * TILE_X + tx] = e;
+  __syncthreads();
+  if (out) { if (TMA) f.phaseC(i, j, st, sop, Tile2{S, tx, ty}, Tile2{E, tx, ty}); else f.phaseC(i, j, st, gop, Tile2{S, tx, ty}, Tile2{E, tx, ty}); }
+}
+#endif
+
+template <class F>
+inline void launch_tile3(Ctx* c, const F& f, int i0, int i1, int j0, int j1) {
+  if (i1 < i0 || j1 < j0) return;
+  c->launches++;
+  constexpr int OX = TILE_X - 2, OY = F::TY - 2;
+  const int nbx = (i1 - i0 + OX) / OX, nby = (j1 - j0 + OY) / OY;
+#ifdef POMGPU_EMU
+  static typename F::State st[TILE_Y][TILE_X];
+  static double S[F::NV * TILE_Y * TILE_X], E[TILE_Y * TILE_X];
+  static bool ins[TILE_Y][TILE_X];
+  const double* fld[F::NF];
+  f.fields(fld);
+  for (int by = 0; by < nby; ++by)
+    for (int bx = 0; bx < nbx; ++bx) {
+#define POM_T3_LOOP for (int ty = 0; ty < F::TY; ++ty) for (int tx = 0; tx < TILE_X; ++tx)
+#define POM_T3_IJ const int i = i0 + bx * OX - 1 + tx, j = j0 + by * OY - 1 + ty
+      POM_T3_LOOP {
+        POM_T3_IJ;
+        ins[ty][tx] = (i >= 1 && i <= f.g.im && j >= f.g.joff + 1 && j <= f.g.joff + f.g.jml);
+        f.pre(i, j, ins[ty][tx], st[ty][tx]);
+        double v[F::NV];
+        for (int n = 0; n < F::NV; ++n) v[n] = 0.;
+        if (ins[ty][tx]) f.phaseA(i, j, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, 1}, v);
+        for (int n = 0; n < F::NV; ++n) S[(n * TILE_Y + ty) * TILE_X + tx] = v[n];
+      }
+      POM_T3_LOOP {
+        POM_T3_IJ;
+        double e = 0.;
+        if (tx <= TILE_X - 2 && ty <= F::TY - 2 && ins[ty][tx])
+          e = f.phaseB(i, j, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, 1}, Tile2{S, tx, ty}, tx >= 1 && ty >= 1);
+        E[ty * TILE_X + tx] = e;
+      }
+      POM_T3_LOOP {
+        POM_T3_IJ;
+        if (tx >= 1 && tx <= TILE_X - 2 && ty >= 1 && ty <= F::TY - 2 && i <= i1 && j <= j1 && ins[ty][tx])
+          f.phaseC(i, j, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, 1}, Tile2{S, tx, ty}, Tile2{E, tx, ty});
+      }
+    }
+#else
+  if (c->prof_on) {
+    const KInfo& k = F::info();
+    double cols = (double)(i1 - i0 + 1) * (j1 - j0 + 1);
+    prof_before(c, &k, 8. * cols * ((k.r3 + k.w3) * (double)c->g.kb + (k.r2 + k.w2)));
+  }
+  dim3 b(TILE_X, F::TY), gr(nbx, nby);
+  TmaMaps<F::NF> maps;
+  bool tma_ok = (c->g.im % 2 == 0) && !c->no_tma;
+  if (tma_ok) {
+    const double* fld[F::NF];
+    f.fields(fld);
+    for (int n = 0; n < F::NF && tma_ok; ++n)
+      if (tma_encode(c, &maps.m[n], fld[n], 1, F::BW, F::BH)) tma_ok = false;
+  }
+  constexpr size_t sm_se = (size_t)((F::NV + 1) * TILE_Y * TILE_X) * sizeof(double) + 8;
+  constexpr size_t sm_tma = sm_se + (size_t)F::NF * tma_plane(F::BW, F::BH) * sizeof(double);
+  static bool granted = false;
+  if (!granted) {
+    cudaFuncSetAttribute(tile3kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_tma);
+    cudaFuncSetAttribute(tile3kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_se);
+    granted = true;
+  }
+  if (tma_ok) tile3kernel<F, true><<<gr, b, sm_tma, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
+  else tile3kernel<F, false><<<gr, b, sm_se, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
   if (c->prof_on) prof_after(c);
 #endif
 }
