@@ -24,8 +24,6 @@ void run_baropg(Ctx*, int, int);
 void run_smag(Ctx*, int, int);
 void run_advave(Ctx*, int, int);
 void run_mode_inter_tail(Ctx*, int, int);
-void run_ext_elf(Ctx*, int, int);
-void run_ext_uv(Ctx*, int iext, int, int);
 void run_ext_step(Ctx*, int iext, int do_adv, int, int);
 void run_uvadjust(Ctx*, int, int);
 void run_vertvl(Ctx*, int, int);
