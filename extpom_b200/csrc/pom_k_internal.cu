@@ -531,6 +531,153 @@ struct AdvT2K : KBase {
   }
 };
 
+// ---------------------------------------------------------------------------
+// advt2 with nitera > 1 (solver.f:577-731 + smol_adif :1880-1967): the Smolarkiewicz
+// iterations need the anti-diffusive mass fluxes and the previous iterate as arrays, so the
+// scheme runs as mass -> { upwind step -> smol_adif } x nitera -> diffusion on three scratch
+// flux fields (xm, ym, zw) and a ping-pong pair for the iterate.
+// xmassflux, ymassflux (:602-616), zwflux=w (:621)
+struct AdvT2MassK : KBase {
+  POM_KINFO("advt2_mass", 3, 3, 4, 0)
+  double *xm_, *ym_, *zw_;
+  AdvT2MassK(const Ctx* x, double* xm, double* ym, double* zw) : KBase(x), xm_(xm), ym_(ym), zw_(zw) {}
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    const bool fx = (i >= 2 && j >= 2 && j <= jmm1), fy = (i >= 2 && i <= imm1 && j >= 2);
+    const double cx = fx ? 0.25*(dy(i-1,j)+dy(i,j))*(dt(i-1,j)+dt(i,j)) : 0.;
+    const double cy = fy ? 0.25*(dx(i,j-1)+dx(i,j))*(dt(i,j-1)+dt(i,j)) : 0.;
+    for (int k = 1; k <= kb; ++k) {
+      A3(xm_,i,j,k)=(fx && k <= kbm1) ? cx*u(i,j,k) : 0.;
+      A3(ym_,i,j,k)=(fy && k <= kbm1) ? cy*v(i,j,k) : 0.;
+      A3(zw_,i,j,k)=w(i,j,k);
+    }
+  }
+};
+
+// one upwind step (:628-677) followed by the mask of smol_adif (:1898-1900).  `stale` is what
+// the reference's ff array holds where the step does not assign it (boundary columns, level kb)
+struct AdvT2UpK : KBase {
+  POM_KINFO("advt2_up", 4, 1, 6, 0)
+  const double *fbm_, *f_, *xm_, *ym_, *zw_, *stale_;
+  double* ff_;
+  int first;
+  AdvT2UpK(const Ctx* x, const double* fbm, const double* f, const double* xm, const double* ym, const double* zw,
+           const double* stale, double* ff, int fst)
+      : KBase(x), fbm_(fbm), f_(f), xm_(xm), ym_(ym), zw_(zw), stale_(stale), ff_(ff), first(fst) {}
+  POM_HD double xfl(int i, int j, int k) const {
+    const double m=A3(xm_,i,j,k);
+    return 0.5*((m+fabs(m))*A3(fbm_,i-1,j,k)+(m-fabs(m))*A3(fbm_,i,j,k));       // :631-635
+  }
+  POM_HD double yfl(int i, int j, int k) const {
+    const double m=A3(ym_,i,j,k);
+    return 0.5*((m+fabs(m))*A3(fbm_,i,j-1,k)+(m-fabs(m))*A3(fbm_,i,j,k));       // :637-641
+  }
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    const double m=fsm(i,j);
+    if (!(i >= 2 && i <= imm1 && j >= 2 && j <= jmm1)) {
+      for (int k = 1; k <= kb; ++k) A3(ff_,i,j,k)=A3(stale_,i,j,k)*m;
+      return;
+    }
+    const double ar=art(i,j);
+    const double eta=first ? etb(i,j) : etf(i,j);                        // :620,684
+    const double hb=(h(i,j)+eta)*ar, hf=(h(i,j)+etf(i,j))*ar;
+    double zk=first ? w(i,j,1)*A3(f_,i,j,1)*ar : 0.;                     // :646-650
+    for (int k = 1; k <= kbm1; ++k) {
+      double zk1 = 0.;                                                   // :651
+      if (k + 1 <= kbm1) {
+        const double zw1=A3(zw_,i,j,k+1);
+        zk1=0.5*((zw1+fabs(zw1))*A3(fbm_,i,j,k+1)+(zw1-fabs(zw1))*A3(fbm_,i,j,k));   // :656-660
+        zk1=zk1*ar;                                                      // :661
+      }
+      double q=xfl(i+1,j,k)-xfl(i,j,k)+yfl(i,j+1,k)-yfl(i,j,k)+(zk-zk1)/dz(k);   // :670-672
+      q=(A3(fbm_,i,j,k)*hb-dti2*q)/hf;                                   // :673-674
+      A3(ff_,i,j,k)=q*m;                                                 // smol_adif :1899
+      zk=zk1;
+    }
+    A3(ff_,i,j,kb)=A3(stale_,i,j,kb)*m;
+  }
+};
+
+// smol_adif (:1903-1964): anti-diffusive mass fluxes from the masked iterate, in place
+struct SmolAdifK : KBase {
+  POM_KINFO("smol_adif", 4, 3, 4, 0)
+  const double* ff_;
+  double *xm_, *ym_, *zw_;
+  SmolAdifK(const Ctx* x, const double* ff, double* xm, double* ym, double* zw) : KBase(x), ff_(ff), xm_(xm), ym_(ym), zw_(zw) {}
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    const double value_min = 1.e-9, epsilon = 1.0e-14;
+    const bool fx = (i >= 2 && j >= 2 && j <= jmm1), fy = (i >= 2 && i <= imm1 && j >= 2);
+    const bool fz = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
+    for (int k = 1; k <= kbm1; ++k) {
+      const double f0=A3(ff_,i,j,k);
+      if (fx) {                                                          // :1903-1922
+        const double fW=A3(ff_,i-1,j,k), xm=A3(xm_,i,j,k);
+        double r = 0.;
+        if (!(f0 < value_min || fW < value_min)) {
+          double udx=fabs(xm);
+          double u2dt=dti2*xm*xm*2./(aru(i,j)*(dt(i-1,j)+dt(i,j)));
+          double mol=(f0-fW)/(fW+f0+epsilon);
+          r=(udx-u2dt)*mol*sw;
+          if (fabs(udx) < fabs(u2dt)) r=0.;
+        }
+        A3(xm_,i,j,k)=r;
+      }
+      if (fy) {                                                          // :1924-1943
+        const double fS=A3(ff_,i,j-1,k), ym=A3(ym_,i,j,k);
+        double r = 0.;
+        if (!(f0 < value_min || fS < value_min)) {
+          double vdy=fabs(ym);
+          double v2dt=dti2*ym*ym*2./(arv(i,j)*(dt(i,j-1)+dt(i,j)));
+          double mol=(f0-fS)/(fS+f0+epsilon);
+          r=(vdy-v2dt)*mol*sw;
+          if (fabs(vdy) < fabs(v2dt)) r=0.;
+        }
+        A3(ym_,i,j,k)=r;
+      }
+      if (fz && k >= 2) {                                                // :1945-1964
+        const double fU=A3(ff_,i,j,k-1), zw=A3(zw_,i,j,k);
+        double r = 0.;
+        if (!(f0 < value_min || fU < value_min)) {
+          double wdz=fabs(zw);
+          double w2dt=dti2*zw*zw/(dzz(k-1)*dt(i,j));
+          double mol=(fU-f0)/(f0+fU+epsilon);
+          r=(wdz-w2dt)*mol*sw;
+          if (fabs(wdz) < fabs(w2dt)) r=0.;
+        }
+        A3(zw_,i,j,k)=r;
+      }
+    }
+  }
+};
+
+// horizontal diffusion of (fb-fclim) added to the last iterate (:691-726)
+struct AdvT2DiffK : KBase {
+  POM_KINFO("advt2_diff", 4, 1, 8, 0)
+  const double *fb_, *fc_;
+  double* ff_;
+  AdvT2DiffK(const Ctx* x, const double* fb, const double* fc, double* ff) : KBase(x), fb_(fb), fc_(fc), ff_(ff) {}
+  POM_HD double fd(int i, int j, int k) const { return A3(fb_,i,j,k)-A3(fc_,i,j,k); }     // :691
+  POM_HD double xfl(int i, int j, int k) const {
+    const double xd=0.5*(aam(i,j,k)+aam(i-1,j,k));                                        // :696
+    return -xd*(h(i,j)+h(i-1,j))*tprni*(fd(i,j,k)-fd(i-1,j,k))*dum(i,j)
+           *(dy(i,j)+dy(i-1,j))*0.5/(dx(i,j)+dx(i-1,j));                                  // :705-707
+  }
+  POM_HD double yfl(int i, int j, int k) const {
+    const double yd=0.5*(aam(i,j,k)+aam(i,j-1,k));                                        // :697
+    return -yd*(h(i,j)+h(i,j-1))*tprni*(fd(i,j,k)-fd(i,j-1,k))*dvm(i,j)
+           *(dx(i,j)+dx(i,j-1))*0.5/(dy(i,j)+dy(i,j-1));                                  // :708-710
+  }
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    if (!(i >= 2 && i <= imm1 && j >= 2 && j <= jmm1)) return;
+    const double hf=(h(i,j)+etf(i,j))*art(i,j);
+    for (int k = 1; k <= kbm1; ++k)
+      A3(ff_,i,j,k)=A3(ff_,i,j,k)-dti2*(xfl(i+1,j,k)-xfl(i,j,k)+yfl(i,j+1,k)-yfl(i,j,k))/hf;   // :721-723
+  }
+};
+
 // advt1 (solver.f:480-574): centred advection + diffusion of (fb-fclim)
 struct AdvT1K : KBase {
   POM_KINFO("advt1", 7, 1, 10, 0)
@@ -1096,6 +1243,19 @@ void run_qfilter(Ctx* c, int j0, int j1) { launch_cols(c, QFilterK(c), ALLI, j0,
 void run_advt(Ctx* c, int nadv, const double* fb, const double* f, const double* fc, double* ff, int j0, int j1) {
   if (nadv == 1) launch_cols(c, AdvT1K(c, fb, f, fc, ff), ALLI, j0, j1);
   else launch_tma_tiles(c, AdvT2K(c, fb, f, fc, ff), ALLI, j0, j1);
+}
+void run_advt2_mass(Ctx* c, double* xm, double* ym, double* zw, int j0, int j1) {
+  launch_cols(c, AdvT2MassK(c, xm, ym, zw), ALLI, j0, j1);
+}
+void run_advt2_up(Ctx* c, const double* fbm, const double* f, const double* xm, const double* ym, const double* zw,
+                  const double* stale, double* ff, int first, int j0, int j1) {
+  launch_cols(c, AdvT2UpK(c, fbm, f, xm, ym, zw, stale, ff, first), ALLI, j0, j1);
+}
+void run_smol_adif(Ctx* c, const double* ff, double* xm, double* ym, double* zw, int j0, int j1) {
+  launch_cols(c, SmolAdifK(c, ff, xm, ym, zw), ALLI, j0, j1);
+}
+void run_advt2_diff(Ctx* c, const double* fb, const double* fc, double* ff, int j0, int j1) {
+  launch_cols(c, AdvT2DiffK(c, fb, fc, ff), ALLI, j0, j1);
 }
 void run_fb_roundtrip(Ctx* c, double* fb, const double* fc, double* f, int j0, int j1) {
   launch_cols(c, FbRoundTripK(c, fb, fc, f), ALLI, j0, j1);

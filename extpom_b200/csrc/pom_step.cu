@@ -32,6 +32,11 @@ void run_profq(Ctx*, int, int);
 void run_qfilter(Ctx*, int, int);
 void run_advt(Ctx*, int nadv, const double* fb, const double* f, const double* fc, double* ff, int, int);
 void run_fb_roundtrip(Ctx*, double* fb, const double* fc, double* f, int, int);
+void run_advt2_mass(Ctx*, double* xm, double* ym, double* zw, int, int);
+void run_advt2_up(Ctx*, const double* fbm, const double* f, const double* xm, const double* ym, const double* zw,
+                  const double* stale, double* ff, int first, int, int);
+void run_smol_adif(Ctx*, const double* ff, double* xm, double* ym, double* zw, int, int);
+void run_advt2_diff(Ctx*, const double* fb, const double* fc, double* ff, int, int);
 void run_proft(Ctx*, double* f, const double* wf, const double* fs, int nbc, int, int);
 void run_tsfilter(Ctx*, int, int);
 void run_dens(Ctx*, const double* si, const double* ti, double* ro, int, int);
@@ -65,7 +70,7 @@ static int check_switches(Group* G) {
   if (k.mode != 3 && k.mode != 4) bad = "mode (3 or 4 supported)";
   else if (k.npg != 1) bad = "npg";
   else if (k.nadv != 1 && k.nadv != 2) bad = "nadv";
-  else if (k.nadv == 2 && k.nitera != 1) bad = "nitera (1 supported with nadv=2)";
+  else if (k.nadv == 2 && k.nitera < 1) bad = "nitera";
   else if (k.isplit < 3) bad = "isplit";
   else if (k.ispadv < 1) bad = "ispadv";
   if (bad) {
@@ -158,7 +163,40 @@ static void k_qfilter(Group* G) {
   MADE(e, F_uf, F_vf, F_q2b, F_q2lb);
   group_swap(G, F_q2, F_uf); group_swap(G, F_q2l, F_vf);   // advance.f:418-421
 }
-static void k_advt(Group* G, int fb, int f, int fc, int ff) {
+// advt2 with nitera > 1 (solver.f:625-687): mass fluxes, then { upwind step + mask, smol_adif }
+// per iteration on scratch fields, then the diffusion.  `stale` = the field whose values the
+// reference's ff array holds where the scheme never assigns it (boundary columns, level kb):
+// in the step that is the new q2 / q2l, which `q2=uf` left in uf (advance.f:419-421).
+static void k_advt2_iter(Group* G, int fb, int f, int fc, int ff, int stale) {
+  const int XM = F_s3c, YM = F_s3d, ZW = F_s3e, PING = F_s3a;
+  const int nitera = G->c[0]->c.nitera;
+  {
+    int e = NEED({F_u, 0}, {F_v, 0}, {F_w, 0}, {F_dt, 1});
+    EACH(run_advt2_mass(c, FP(c, XM), FP(c, YM), FP(c, ZW), j0, j1));
+    MADE(e, XM, YM, ZW);
+  }
+  int src = fb;
+  for (int it = 1; it <= nitera; ++it) {
+    const int dst = ((nitera - it) % 2 == 0) ? ff : PING;   // the last iterate lands in ff
+    {
+      int e = NEED({src, 1}, {f, 0}, {XM, 0}, {YM, 1}, {ZW, 0}, {stale, 0}, {F_w, 0}, {F_etb, 0}, {F_etf, 0});
+      EACH(run_advt2_up(c, FP(c, src), FP(c, f), FP(c, XM), FP(c, YM), FP(c, ZW), FP(c, stale), FP(c, dst), it == 1, j0, j1));
+      MADE(e, dst);
+    }
+    if (it < nitera) {   // the fluxes after the last iteration are never used
+      int e = NEED({dst, 1}, {XM, 0}, {YM, 0}, {ZW, 0}, {F_dt, 1});
+      EACH(run_smol_adif(c, FP(c, dst), FP(c, XM), FP(c, YM), FP(c, ZW), j0, j1));
+      MADE(e, XM, YM, ZW);
+    }
+    src = dst;
+  }
+  int e = NEED({fb, 1}, {fc, 1}, {F_aam, 1}, {ff, 0}, {F_etf, 0});
+  EACH(run_advt2_diff(c, FP(c, fb), FP(c, fc), FP(c, ff), j0, j1));
+  MADE(e, ff);
+}
+static void k_advt(Group* G, int fb, int f, int fc, int ff, int stale) {
+  const Consts& k = G->c[0]->c;
+  if (k.nadv == 2 && k.nitera > 1) { k_advt2_iter(G, fb, f, fc, ff, stale); return; }
   int e = NEED({fb, 1}, {f, 0}, {F_u, 0}, {F_v, 1}, {F_w, 0}, {F_aam, 1}, {F_dt, 1}, {F_etb, 0}, {F_etf, 0});
   EACH(run_advt(c, c->c.nadv, FP(c, fb), FP(c, f), FP(c, fc), FP(c, ff), j0, j1));
   MADE(e, ff);
@@ -247,8 +285,8 @@ static int internal_stage(Group* G, int iint, int st) {
     case 2: k_advq(G); break;
     case 3: k_profq(G); break;
     case 4: k_qfilter(G); break;
-    case 5: if (ts) k_advt(G, F_tb, F_t, F_tclim, F_uf); break;
-    case 6: if (ts) k_advt(G, F_sb, F_s, F_sclim, F_vf); break;
+    case 5: if (ts) k_advt(G, F_tb, F_t, F_tclim, F_uf, F_q2); break;
+    case 6: if (ts) k_advt(G, F_sb, F_s, F_sclim, F_vf, F_q2l); break;
     case 7: if (ts) k_proft(G, F_uf, F_wtsurf, F_tsurf, k.nbct); break;
     case 8: if (ts) k_proft(G, F_vf, F_wssurf, F_ssurf, k.nbcs); break;
     case 9: if (ts) k_tsfilter(G); break;
@@ -490,10 +528,9 @@ static int advt(pomgpu_t* p, int nadv, const char* fb, const char* f, const char
   Ctx* c = X(p);
   int a = fid(fb), b = fid(f), cl = fid(fclim), o = fid(ff);
   if (a < 0 || b < 0 || cl < 0 || o < 0) return 2;
-  if (nadv == 2 && c->c.nitera != 1) return 2;
   const int keep = c->c.nadv;
   c->c.nadv = nadv;
-  k_advt(G, a, b, cl, o);
+  k_advt(G, a, b, cl, o, o);
   c->c.nadv = keep;
   // side effects the reference leaves on fb (and f for advt1): solver.f:496,511,532 / 618,691,715
   run_fb_roundtrip(c, FP(c, a), FP(c, cl), nadv == 1 ? FP(c, b) : nullptr, 1, c->g.jmg);

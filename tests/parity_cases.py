@@ -27,6 +27,8 @@ STEP_CASES = [
     ((6, 33, 7), 5, {}),
     ((21, 18, 8), 6, {"isplit": 5, "dte": 6.0}),
     ((21, 18, 8), 6, {"aam_init": 0.0}),
+    ((24, 19, 9), 6, {"nitera": 2, "island": True}),           # Smolarkiewicz iterations (solver.f:625-687)
+    ((24, 19, 9), 6, {"nitera": 3, "sw": 1.0}),
 ]
 
 
@@ -85,14 +87,17 @@ def _interior(a):
     return a[1:-1, 1:-1]
 
 
-ROUTINES = ["dens", "baropg", "advct", "advave", "vertvl", "advq", "profq", "advt1", "advt2",
+ROUTINES = ["dens", "baropg", "advct", "advave", "vertvl", "advq", "profq", "advt1", "advt2", "advt2_it3",
             "proft1", "proft2", "proft3", "advu", "advv", "profu", "profv", "realvertvl"]
 
 
 def check_routine(factory, routine, dims):
     """Call one reference subroutine on both sides from the same spun-up state and compare
     every array it writes (unit-level parity through the C ABI entry of the same name)."""
-    st, o, g = pair(factory, dims, island=True)
+    kw = {"nitera": 3, "sw": 1.0} if routine == "advt2_it3" else {}
+    st, o, g = pair(factory, dims, island=True, **kw)
+    if routine == "advt2_it3":
+        routine = "advt2"
     for i in range(1, 4):
         o.step(i); g.step(i)
     # bring both to the same mid-step state: the q/t/u kernels consume w and the filtered fields
