@@ -259,10 +259,10 @@ def main():
         "kernels": kernels,
     }
     if world == 1 and not a.no_cpu_baseline:
-        val, spt, cores = cpu_reference_rate(a.cpu_sample, kb, 3, 1)
+        val, spt, cores = cpu_reference_rate(a.cpu_sample, kb, 8, 1)
         out["cpu_baseline"] = {
             "value": val, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"3 internal steps at {a.cpu_sample}x{a.cpu_sample}x{kb} (isplit=30) after 1 warm-up; "
+            "sample": f"8 internal steps at {a.cpu_sample}x{a.cpu_sample}x{kb} (isplit=30) after 1 warm-up; "
                       "C restatement of advance.f/solver.f (oracle/), gcc -O2 -ffp-contract=off, OpenMP"}
     print(json.dumps(out), flush=True)
     if dist is not None:

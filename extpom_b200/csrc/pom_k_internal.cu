@@ -803,6 +803,136 @@ struct ProftK : KBase {
   }
 };
 
+// proft for T (in uf) and S (in vf) in one TMA-fed column kernel (advance.f:440-441): kh is read
+// once, and the matrix coefficients a, c and -- when both tracers have the same class of
+// surface condition -- the eliminated ee and the pivots are shared between the two systems.
+struct ProftTSK : KBase {
+  POM_KINFO("proft_ts", 3, 2, 6, 0)
+  double rn, ad1n, ad2n;   // Jerlov water type ntp (:1568-1575)
+  ProftTSK(const Ctx* x) : KBase(x) {
+    const double r[5] = {.58, .62, .67, .77, .78};
+    const double ad1[5] = {.35, .60, 1.0, 1.5, 1.4};
+    const double ad2[5] = {23., 20., 17., 14., 7.9};
+    const int n = (x->c.ntp >= 1 && x->c.ntp <= 5) ? x->c.ntp - 1 : 1;
+    rn = r[n]; ad1n = ad1[n]; ad2n = ad2[n];
+  }
+  static constexpr int TY = 8, MINB = 3;
+  static constexpr int NF = 3, NS = 4, OHL = 0, OHR = 0, OHB = 0, OHT = 0, BW = 34, BH = 8, NK = 0;
+  static constexpr bool UP = true;
+  enum { FT, FS, KH };
+  POM_HD void fields(const double** b) const { b[FT] = p.uf; b[FS] = p.vf; b[KH] = p.kh; }
+  struct Cols { double eeT[KMAX], eeS[KMAX], ggT[KMAX], ggS[KMAX]; };
+  struct State { double dh, swT, swS, radT, radS, eeT, eeS, ggT, ggS, fT, fS; };
+  POM_HD int k0() const { return 1; }
+  POM_HD int k1() const { return g.kb - 1; }
+  POM_HD int kl1() const { return g.kb - 1; }
+  POM_HD double rad(int k, double dh, double sw0) const {                // :1604-1615; rad(kb)=0
+    if (k >= g.kb) return 0.;
+    return sw0*(rn*exp(z(k)*dh/ad1n)+(1.-rn)*exp(z(k)*dh/ad2n));
+  }
+  POM_HD void pre(int i, int j, State& s, Cols&) const {
+    s.dh=h(i,j)+etf(i,j);                                               // :1580
+    s.swT=(c.nbct == 2 || c.nbct == 4) ? A2(p.swrad,i,j) : 0.;
+    s.swS=(c.nbcs == 2 || c.nbcs == 4) ? A2(p.swrad,i,j) : 0.;
+    s.radT = 0.; s.radS = 0.;
+  }
+  // surface condition of one tracer (:1617-1648): ee(1), gg(1)
+  POM_HD void surface(int i, int j, int nbc, double ak, double f1, double wfs, double fsf, double sw0, double dh,
+                      double& ee1, double& gg1) const {
+    if (nbc == 1) {                                                     // :1619-1625
+      ee1=ak/(ak-1.);
+      gg1=dti2*wfs/(dz(1)*dh)-f1;
+      gg1=gg1/(ak-1.);
+    } else if (nbc == 2) {                                              // :1629-1637
+      ee1=ak/(ak-1.);
+      gg1=dti2*(wfs+rad(1,dh,sw0)-rad(2,dh,sw0))/(dz(1)*dh)-f1;
+      gg1=gg1/(ak-1.);
+    } else if (nbc == 3 || nbc == 4) {                                  // :1641-1646
+      ee1=0.;
+      gg1=fsf;
+    } else {
+      ee1=0.; gg1=0.;
+    }
+  }
+  template <class Op>
+  POM_HD void level(int i, int j, int k, State& s, Cols& cm, const Op& o) const {
+    POM_DIMS;
+    const double dh=s.dh;
+    const bool penT = (c.nbct == 2 || c.nbct == 4), penS = (c.nbcs == 2 || c.nbcs == 4);
+    const bool same = ((c.nbct == 1 || c.nbct == 2) == (c.nbcs == 1 || c.nbcs == 2));
+    if (k == 1) {
+      // a(k-1), c(k) from kh(k), k=2..kbm1 (:1589-1598); a(kbm1)=0, c(1)=0 (zero fill)
+      const double ak=-dti2*(o.up(KH)+umol)/(dz(1)*dzz(1)*dh*dh);       // a(1)
+      surface(i,j,c.nbct,ak,o(FT,0,0),wtsurf(i,j),tsurf(i,j),s.swT,dh,s.eeT,s.ggT);
+      surface(i,j,c.nbcs,ak,o(FS,0,0),wssurf(i,j),ssurf(i,j),s.swS,dh,s.eeS,s.ggS);
+      cm.eeT[1]=s.eeT; cm.ggT[1]=s.ggT; cm.ggS[1]=s.ggS;
+      if (!same) cm.eeS[1]=s.eeS;
+      if (penT) s.radT=rad(2,dh,s.swT);
+      if (penS) s.radS=rad(2,dh,s.swS);
+      return;
+    }
+    const double ck=-dti2*(o(KH,0,0)+umol)/(dz(k)*dzz(k-1)*dh*dh);      // c(k)
+    if (k <= kbm2) {                                                    // :1650-1661
+      const double ak=-dti2*(o.up(KH)+umol)/(dz(k)*dzz(k)*dh*dh);       // a(k)
+      const double giT=1./(ak+ck*(1.-s.eeT)-1.);
+      const double giS=same ? giT : 1./(ak+ck*(1.-s.eeS)-1.);
+      s.eeT=ak*giT;
+      s.eeS=same ? s.eeT : ak*giS;
+      double rT=ck*s.ggT-o(FT,0,0), rS=ck*s.ggS-o(FS,0,0);
+      if (penT) { const double r0=s.radT; s.radT=rad(k+1,dh,s.swT); rT=rT+dti2*(r0-s.radT)/(dh*dz(k)); }
+      if (penS) { const double r0=s.radS; s.radS=rad(k+1,dh,s.swS); rS=rS+dti2*(r0-s.radS)/(dh*dz(k)); }
+      s.ggT=rT*giT; s.ggS=rS*giS;
+      cm.eeT[k]=s.eeT; cm.ggT[k]=s.ggT; cm.ggS[k]=s.ggS;
+      if (!same) cm.eeS[k]=s.eeS;          // shared with T otherwise: one array less to spill
+    } else {                                                            // k == kbm1 (:1664-1671)
+      double rT=ck*s.ggT-o(FT,0,0), rS=ck*s.ggS-o(FS,0,0);
+      if (penT) rT=rT+dti2*(s.radT-0.)/(dh*dz(kbm1));
+      if (penS) rS=rS+dti2*(s.radS-0.)/(dh*dz(kbm1));
+      s.fT=rT/(ck*(1.-s.eeT)-1.);
+      s.fS=rS/(ck*(1.-s.eeS)-1.);
+    }
+  }
+  POM_HD void post(int i, int j, State& s, Cols& cm) const {
+    POM_DIMS;
+    const bool same = ((c.nbct == 1 || c.nbct == 2) == (c.nbcs == 1 || c.nbcs == 2));
+    double fT=s.fT, fS=s.fS;
+    POM_STCS(&uf(i,j,kbm1),fT);
+    POM_STCS(&vf(i,j,kbm1),fS);
+    for (int ki = kb-2; ki >= 1; --ki) {                                // :1673-1680
+      const double eT=cm.eeT[ki];
+      fT=eT*fT+cm.ggT[ki];
+      fS=(same ? eT : cm.eeS[ki])*fS+cm.ggS[ki];
+      POM_STCS(&uf(i,j,ki),fT);
+      POM_STCS(&vf(i,j,ki),fS);
+    }
+  }
+};
+
+// x**1.5 for x>=0, rounded like a correctly-rounded pow(x,1.5): sqrt is IEEE-exact to
+// 0.5 ulp, its residual and the product are recovered exactly with fma.
+POM_HD double pow15(double x) {
+  if (!(x > 0.)) return 0.;
+  double sq=sqrt(x);
+  double res=fma(-sq,sq,x);          // x - sq*sq exactly
+  double ds=res/(2.*sq);             // sqrt(x) = sq + ds
+  double pr=x*sq;
+  double er=fma(x,sq,-pr);           // x*sq = pr + er exactly
+  return pr+(er+x*ds);
+}
+
+// the equation of state of one cell (solver.f:1175-1203): T, S (+bias), pressure from -zz*h
+POM_HD double dens_point(double tr, double sr, double pp, double rhoref_, double m) {
+  double tr2=tr*tr, tr3=tr2*tr, tr4=tr3*tr;
+  double rhor=-0.157406+6.793952e-2*tr-9.095290e-3*tr2+1.001685e-4*tr3
+              -1.120083e-6*tr4+6.536332e-9*tr4*tr;
+  rhor=rhor+(0.824493-4.0899e-3*tr+7.6438e-5*tr2-8.2467e-7*tr3+5.3875e-9*tr4)*sr
+           +(-5.72466e-3+1.0227e-4*tr-1.6546e-6*tr2)*pow15(fabs(sr))
+           +4.8314e-4*sr*sr;
+  double cr=1449.1+.0821*pp+4.55*tr-.045*tr2+1.34*(sr-35.);
+  rhor=rhor+1.e5*pp/(cr*cr)*(1.-2.*pp/(cr*cr));
+  return rhor/rhoref_*m;
+}
+
 // ---------------------------------------------------------------------------
 // bcond(4) (bounds_forcing.f:151-242) + Asselin filter/rotation of t,s
 // (advance.f:444-449) + restore_interior arithmetic and mask
@@ -811,7 +941,8 @@ struct ProftK : KBase {
 struct TsFilterK : KBase {
   POM_KINFO("ts_filter", 8, 4, 1, 0)
   double fold, fnew;
-  TsFilterK(const Ctx* x) : KBase(x) {
+  int with_dens;   // also dens(s,t,rho) of the new t,s (advance.f:454), saving a pass over both
+  TsFilterK(const Ctx* x, int wd) : KBase(x), with_dens(wd) {
     const double trst = 30.;                                             // bounds_forcing.f:1033
     int ntime = (int)(x->c.time / trst);
     fnew = x->c.time / trst - ntime;
@@ -896,25 +1027,16 @@ struct TsFilterK : KBase {
         b=b+2.*dti/86400.*ta*(sr-b);
         sf=sf+2.*dti/86400.*ta*(sr-sf);
       }
-      uf(i,j,k)=a*m;                                                    // :1113-1118
-      vf(i,j,k)=b*m;
+      a=a*m; b=b*m;                                                     // :1113-1118
+      uf(i,j,k)=a;
+      vf(i,j,k)=b;
       tb(i,j,k)=tf*m;
       sb(i,j,k)=sf*m;
+      if (with_dens)                                                    // solver.f:1175-1205
+        rho(i,j,k)=dens_point(a+tbias,b+sbias,grav*rhoref*(-zz(k)*h(i,j))*1.e-5,rhoref,m);
     }
   }
 };
-
-// x**1.5 for x>=0, rounded like a correctly-rounded pow(x,1.5): sqrt is IEEE-exact to
-// 0.5 ulp, its residual and the product are recovered exactly with fma.
-POM_HD double pow15(double x) {
-  if (!(x > 0.)) return 0.;
-  double sq=sqrt(x);
-  double res=fma(-sq,sq,x);          // x - sq*sq exactly
-  double ds=res/(2.*sq);             // sqrt(x) = sq + ds
-  double pr=x*sq;
-  double er=fma(x,sq,-pr);           // x*sq = pr + er exactly
-  return pr+(er+x*ds);
-}
 
 // dens (solver.f:1162-1209)
 struct DensK : KBase {
@@ -927,18 +1049,8 @@ struct DensK : KBase {
     const double m=fsm(i,j), hh=h(i,j);
     for (int k = 1; k <= kbm1; ++k) {
       PF3(ti_,i,j,k+2); PF3(si_,i,j,k+2);
-      double tr=A3(ti_,i,j,k)+tbias;
-      double sr=A3(si_,i,j,k)+sbias;
-      double tr2=tr*tr, tr3=tr2*tr, tr4=tr3*tr;
-      double pp=grav*rhoref*(-zz(k)*hh)*1.e-5;
-      double rhor=-0.157406+6.793952e-2*tr-9.095290e-3*tr2+1.001685e-4*tr3
-                  -1.120083e-6*tr4+6.536332e-9*tr4*tr;
-      rhor=rhor+(0.824493-4.0899e-3*tr+7.6438e-5*tr2-8.2467e-7*tr3+5.3875e-9*tr4)*sr
-               +(-5.72466e-3+1.0227e-4*tr-1.6546e-6*tr2)*pow15(fabs(sr))
-               +4.8314e-4*sr*sr;
-      double cr=1449.1+.0821*pp+4.55*tr-.045*tr2+1.34*(sr-35.);
-      rhor=rhor+1.e5*pp/(cr*cr)*(1.-2.*pp/(cr*cr));
-      A3(ro_,i,j,k)=rhor/rhoref*m;
+      const double pp=grav*rhoref*(-zz(k)*hh)*1.e-5;
+      A3(ro_,i,j,k)=dens_point(A3(ti_,i,j,k)+tbias,A3(si_,i,j,k)+sbias,pp,rhoref,m);
     }
   }
 };
@@ -1267,8 +1379,9 @@ void run_proft(Ctx* c, double* f, const double* wf, const double* fs, int nbc, i
   launch_cols(c, ProftK(c, f, wf, fs, nbc), ALLI, j0, j1);
 #endif
 }
+void run_proft_ts(Ctx* c, int j0, int j1) { launch_tma_cols(c, ProftTSK(c), ALLI, j0, j1); }
 // caller swaps t<->uf, s<->vf (advance.f:446-449)
-void run_tsfilter(Ctx* c, int j0, int j1) { launch_cols(c, TsFilterK(c), ALLI, j0, j1); }
+void run_tsfilter(Ctx* c, int with_dens, int j0, int j1) { launch_cols(c, TsFilterK(c, with_dens), ALLI, j0, j1); }
 void run_dens(Ctx* c, const double* si, const double* ti, double* ro, int j0, int j1) {
   launch_cols(c, DensK(c, si, ti, ro), ALLI, j0, j1);
 }

@@ -38,7 +38,8 @@ void run_advt2_up(Ctx*, const double* fbm, const double* f, const double* xm, co
 void run_smol_adif(Ctx*, const double* ff, double* xm, double* ym, double* zw, int, int);
 void run_advt2_diff(Ctx*, const double* fb, const double* fc, double* ff, int, int);
 void run_proft(Ctx*, double* f, const double* wf, const double* fs, int nbc, int, int);
-void run_tsfilter(Ctx*, int, int);
+void run_tsfilter(Ctx*, int with_dens, int, int);
+void run_proft_ts(Ctx*, int, int);
 void run_dens(Ctx*, const double* si, const double* ti, double* ro, int, int);
 void run_advu(Ctx*, int, int);
 void run_advv(Ctx*, int, int);
@@ -206,10 +207,16 @@ static void k_proft(Group* G, int f, int wf, int fs, int nbc) {
   EACH(run_proft(c, FP(c, f), FP(c, wf), FP(c, fs), nbc, j0, j1));
   MADE(e, f);
 }
-static void k_tsfilter(Group* G) {
+static void k_proft_ts(Group* G) {   // proft(uf,wtsurf,tsurf,nbct) and proft(vf,wssurf,ssurf,nbcs) in one pass
+  int e = NEED({F_uf, 0}, {F_vf, 0}, {F_kh, 0}, {F_etf, 0});
+  EACH(run_proft_ts(c, j0, j1));
+  MADE(e, F_uf, F_vf);
+}
+static void k_tsfilter(Group* G, int with_dens) {
   int e = NEED({F_uf, 0}, {F_vf, 0}, {F_t, 0}, {F_s, 0}, {F_tb, 0}, {F_sb, 0}, {F_u, 0}, {F_v, 0}, {F_w, 0}, {F_dt, 0});
-  EACH(run_tsfilter(c, j0, j1));
+  EACH(run_tsfilter(c, with_dens, j0, j1));
   MADE(e, F_uf, F_vf, F_tb, F_sb);
+  if (with_dens) MADE(e, F_rho);
   group_swap(G, F_t, F_uf); group_swap(G, F_s, F_vf);      // advance.f:446-449
 }
 static void k_dens(Group* G, int si, int ti, int ro) {
@@ -289,7 +296,9 @@ static int internal_stage(Group* G, int iint, int st) {
     case 6: if (ts) k_advt(G, F_sb, F_s, F_sclim, F_vf, F_q2l); break;
     case 7: if (ts) k_proft(G, F_uf, F_wtsurf, F_tsurf, k.nbct); break;
     case 8: if (ts) k_proft(G, F_vf, F_wssurf, F_ssurf, k.nbcs); break;
-    case 9: if (ts) k_tsfilter(G); break;
+    case 9: if (ts) k_tsfilter(G, 0); break;
+    case 107: if (ts) k_proft_ts(G); break;           // proft of T and S fused (what the step runs)
+    case 109: if (ts) k_tsfilter(G, 1); break;        // + dens fused (what the step runs)
     case 10: if (ts) k_dens(G, F_s, F_t, F_rho); break;
     case 11: k_advu(G); break;
     case 12: k_advv(G); break;
@@ -306,7 +315,11 @@ static int internal_stage(Group* G, int iint, int st) {
 static int mode_internal(Group* G, int iint) {
   const Consts& k = G->c[0]->c;
   if ((iint != 1 || k.time0 != 0.) && k.mode != 2)
-    for (int st = 0; st <= 15; ++st) internal_stage(G, iint, st);
+    for (int st = 0; st <= 15; ++st) {
+      if (st == 7) { internal_stage(G, iint, 107); ++st; continue; }   // proft T and S in one kernel
+      if (st == 9) { internal_stage(G, iint, 109); ++st; continue; }   // t/s filter with dens fused
+      internal_stage(G, iint, st);
+    }
   internal_stage(G, iint, 16);
   internal_stage(G, iint, 17);
   return 0;
