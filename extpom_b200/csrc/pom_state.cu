@@ -246,6 +246,11 @@ void ctx_destroy(Ctx* c) {
   free(c->d_red); free(c->h_red);
 #else
   cudaFree(c->d_red); cudaFreeHost(c->h_red);
+  for (int f = 0; f < 256; ++f) if (c->shadow[f]) cudaFree(c->shadow[f]);
+  if (c->copy_stream) cudaStreamDestroy((cudaStream_t)c->copy_stream);
+  if (c->ev_copied) cudaEventDestroy((cudaEvent_t)c->ev_copied);
+  if (c->ev_swapped) cudaEventDestroy((cudaEvent_t)c->ev_swapped);
+  if (c->ev_vel) cudaEventDestroy((cudaEvent_t)c->ev_vel);
   cudaStreamDestroy((cudaStream_t)c->own_stream);
 #endif
   free(c);

@@ -62,6 +62,30 @@ static inline double* FP(Ctx* c, int f) {
 #define EACH(stmt) for (int r_ = 0; r_ < G->n; ++r_) { Ctx* c = G->c[r_]; const int j0 = WLO(c, e), j1 = WHI(c, e); (void)j0; (void)j1; stmt; }
 #define CSYNC() for (int r_ = 1; r_ < G->n; ++r_) G->c[r_]->c = G->c[0]->c
 
+// pushes made with pomgpu_push_async since the last step: make the compute stream wait for the
+// copies and swap the shadow buffers in (the old buffers become the next shadows)
+static void apply_pending(Ctx* c) {
+  if (!c->npending) return;
+#ifndef POMGPU_EMU
+  cudaSetDevice(c->device);
+  cudaStreamWaitEvent((cudaStream_t)c->stream, (cudaEvent_t)c->ev_copied, 0);
+#endif
+  int ntab;
+  const FieldInfo* tab = field_table(&ntab);
+  for (int f = 0; f < ntab && f < 256; ++f)
+    if (c->pending[f]) {
+      double** slot = (double**)((char*)&c->p + tab[f].offset);
+      double* t = *slot; *slot = c->shadow[f]; c->shadow[f] = t;
+      c->pending[f] = 0;
+    }
+  c->npending = 0;
+#ifndef POMGPU_EMU
+  // copies into the (new) shadows must wait until everything enqueued so far has read them
+  cudaEventRecord((cudaEvent_t)c->ev_swapped, (cudaStream_t)c->stream);
+#endif
+}
+static void apply_pending(Group* G) { for (int r = 0; r < G->n; ++r) apply_pending(G->c[r]); }
+
 static int check_switches(Group* G) {
   // run-time switches honoured; others follow the reference's error
   // convention: error_status=1 and a message (advance.f:118-119,432-433)
@@ -327,6 +351,7 @@ static int mode_internal(Group* G, int iint) {
 
 static int step(Group* G, int iint, double time, double ramp) {
   Ctx* c0 = G->c[0];
+  apply_pending(G);
   c0->c.iint = iint; c0->c.time = time; c0->c.ramp = ramp; CSYNC();
   if (int r = check_switches(G)) return r;
   lateral_viscosity(G);
@@ -406,8 +431,8 @@ int pomgpu_row_offset(const pomgpu_t* p) { return ((const Ctx*)p)->g.joff; }
 const char* pomgpu_last_error(const pomgpu_t* p) { return ((const Ctx*)p)->err; }
 int pomgpu_set_const(pomgpu_t* p, const char* name, double v) { return ctx_set_const(X(p), name, v); }
 int pomgpu_get_const(pomgpu_t* p, const char* name, double* v) { return ctx_get_const(X(p), name, v); }
-int pomgpu_push(pomgpu_t* p, const char* name, const double* host) { return ctx_push(X(p), name, host); }
-int pomgpu_pull(pomgpu_t* p, const char* name, double* host) { return ctx_pull(X(p), name, host); }
+int pomgpu_push(pomgpu_t* p, const char* name, const double* host) { apply_pending(X(p)); return ctx_push(X(p), name, host); }
+int pomgpu_pull(pomgpu_t* p, const char* name, double* host) { apply_pending(X(p)); return ctx_pull(X(p), name, host); }
 long pomgpu_field_elems(pomgpu_t* p, const char* name) {
   const FieldInfo* f = find_field(name);
   return f ? (long)field_elems(X(p), f) : 0;
@@ -420,9 +445,25 @@ int pomgpu_push_async(pomgpu_t* p, const char* name, const double* host) {
 #ifdef POMGPU_EMU
   return dev_h2d(c, *slot, host, field_elems(c, f));
 #else
+  int ntab;
+  const int id = (int)(f - field_table(&ntab));
+  if (id < 0 || id >= 256) return 2;
   cudaSetDevice(c->device);
-  cudaError_t e = cudaMemcpyAsync(*slot, host, field_elems(c, f) * 8, cudaMemcpyHostToDevice, (cudaStream_t)c->stream);
+  if (!c->copy_stream) {
+    cudaStream_t s; cudaEvent_t e;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return 1;
+    c->copy_stream = (void*)s;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming); c->ev_copied = (void*)e;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming); c->ev_swapped = (void*)e;
+    cudaEventRecord((cudaEvent_t)c->ev_swapped, (cudaStream_t)c->stream);
+  }
+  if (!c->shadow[id] && dev_alloc(c, &c->shadow[id], field_elems(c, f))) return 1;
+  cudaStream_t cs = (cudaStream_t)c->copy_stream;
+  cudaStreamWaitEvent(cs, (cudaEvent_t)c->ev_swapped, 0);   // the shadow was live until the last swap
+  cudaError_t e = cudaMemcpyAsync(c->shadow[id], host, field_elems(c, f) * 8, cudaMemcpyHostToDevice, cs);
   if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "push_async(%s): %s", name, cudaGetErrorString(e)); c->c.error_status = 1; return 1; }
+  cudaEventRecord((cudaEvent_t)c->ev_copied, cs);
+  if (!c->pending[id]) { c->pending[id] = 1; c->npending++; }
   return 0;
 #endif
 }
@@ -443,6 +484,34 @@ int pomgpu_unpin_host(void* ptr) {
 int pomgpu_step(pomgpu_t* p, int iint, double time, double ramp) { return step(self_group(X(p)), iint, time, ramp); }
 int pomgpu_sync(pomgpu_t* p) { return dev_sync(X(p)); }
 double pomgpu_check_velocity(pomgpu_t* p) { return check_velocity(X(p)); }
+// enqueue the reduction for the step just enqueued and return the result of the PREVIOUS call
+// (0 on the first): the host never waits for the step it has just launched
+double pomgpu_check_velocity_lagged(pomgpu_t* p) {
+  Ctx* c = X(p);
+#ifdef POMGPU_EMU
+  return check_velocity(c);
+#else
+  double prev = 0.;
+  cudaSetDevice(c->device);
+  cudaStream_t s = (cudaStream_t)c->stream;
+  if (!c->ev_vel) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); c->ev_vel = (void*)e; }
+  if (c->vel_lag) {
+    cudaEventSynchronize((cudaEvent_t)c->ev_vel);
+    prev = c->h_red[1];
+    if (!(prev <= c->c.vmaxl)) c->c.error_status = 1;   // advance.f:631-638
+  }
+  const double* a = c->p.va + (size_t)(c->jown0 - 1 - c->g.joff) * c->g.im;
+  size_t n = (size_t)(c->jown1 - c->jown0 + 1) * c->g.im;
+  cudaMemsetAsync(c->d_red + 1, 0, 8, s);
+  int blocks = (int)((n + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+  c->launches++;
+  absmax_kernel<<<blocks, 256, 0, s>>>(a, n, (unsigned long long*)(c->d_red + 1));
+  cudaMemcpyAsync(c->h_red + 1, c->d_red + 1, 8, cudaMemcpyDeviceToHost, s);
+  cudaEventRecord((cudaEvent_t)c->ev_vel, s);
+  c->vel_lag = 1;
+  return prev;
+#endif
+}
 long pomgpu_launch_count(pomgpu_t* p, int reset) {
   long n = X(p)->launches;
   if (reset) X(p)->launches = 0;
@@ -505,13 +574,14 @@ static int fid(const char* name);
 int pomgpu_group_dens(pomgpu_group_t* g, const char* si, const char* ti, const char* rhoo) {
   int a = fid(si), b = fid(ti), o = fid(rhoo);
   if (a < 0 || b < 0 || o < 0) return 2;
+  apply_pending(GG(g));
   k_dens(GG(g), a, b, o);
   return 0;
 }
-int pomgpu_group_baropg(pomgpu_group_t* g) { k_baropg(GG(g)); return 0; }
+int pomgpu_group_baropg(pomgpu_group_t* g) { apply_pending(GG(g)); k_baropg(GG(g)); return 0; }
 
 // ---- the reference's subroutines on the resident state ----------------------------------------
-#define SG Group* G = self_group(X(p))
+#define SG Group* G = self_group(X(p)); apply_pending(G)
 int pomgpu_lateral_viscosity(pomgpu_t* p) { SG; if (int r = check_switches(G)) return r; return lateral_viscosity(G); }
 int pomgpu_mode_interaction(pomgpu_t* p) { SG; return mode_interaction(G); }
 int pomgpu_mode_external(pomgpu_t* p, int iext) { SG; if (int r = check_switches(G)) return r; return mode_external(G, iext); }

@@ -59,6 +59,8 @@ def _bind(path):
     L.pomgpu_check_velocity.restype = C.c_double
     L.pomgpu_check_velocity.argtypes = [P]
     L.pomgpu_push_async.argtypes = [P, C.c_char_p, P]
+    L.pomgpu_check_velocity_lagged.restype = C.c_double
+    L.pomgpu_check_velocity_lagged.argtypes = [P]
     L.pomgpu_pin_host.argtypes = [P, C.c_ulong]
     L.pomgpu_unpin_host.argtypes = [P]
     L.pomgpu_event_record.argtypes = [P, C.c_int]
@@ -223,6 +225,10 @@ class PomGpu:
 
     def check_velocity(self):
         return self.L.pomgpu_check_velocity(self.h)
+
+    def check_velocity_lagged(self):
+        """max|vaf| of the PREVIOUS call's step (0.0 first); never waits for the step just enqueued."""
+        return self.L.pomgpu_check_velocity_lagged(self.h)
 
     def launch_count(self, reset=False):
         return self.L.pomgpu_launch_count(self.h, int(reset))

@@ -51,7 +51,9 @@ int pomgpu_push(pomgpu_t* ctx, const char* name, const double* host);
 int pomgpu_pull(pomgpu_t* ctx, const char* name, double* host);
 long pomgpu_field_elems(pomgpu_t* ctx, const char* name); /* 0 if unknown */
 /* enqueue-only push (no host wait) for the per-step forcing; the host buffer should be
- * page-locked (pomgpu_pin_host registers a driver-owned array, e.g. a COMMON block) */
+ * page-locked (pomgpu_pin_host registers a driver-owned array, e.g. a COMMON block).  The copy
+ * goes to a shadow buffer on a copy stream, overlapping the step still running; the data
+ * becomes the field's content at the next pomgpu_step / pull / push (buffers are swapped). */
 int pomgpu_push_async(pomgpu_t* ctx, const char* name, const double* host);
 int pomgpu_pin_host(void* ptr, unsigned long bytes);
 int pomgpu_unpin_host(void* ptr);
@@ -66,6 +68,9 @@ int pomgpu_sync(pomgpu_t* ctx);
 /* check_velocity (advance.f:611-641) as a device max-reduction: returns
  * max|vaf| and sets error_status when it exceeds vmaxl. */
 double pomgpu_check_velocity(pomgpu_t* ctx);
+/* the same without waiting for the step just enqueued: starts the reduction and returns the
+ * value of the previous call (one step of lag; 0 on the first call) */
+double pomgpu_check_velocity_lagged(pomgpu_t* ctx);
 long pomgpu_launch_count(pomgpu_t* ctx, int reset);
 /* per-kernel device time from CUDA events recorded on the launch stream around every
  * kernel between begin and end; end writes a JSON array

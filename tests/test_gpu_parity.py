@@ -111,3 +111,35 @@ def test_strips_on_one_gpu_equal_single_domain_bitwise(nstrips, ghost):
             a, b = a[:, :, :-1], b[:, :, :-1]
         assert np.array_equal(a, b), n
     assert whole.check_velocity() == grp.check_velocity()
+
+
+def test_async_forcing_push_equals_blocking_push():
+    """pomgpu_push_async (shadow buffer + copy stream, swapped in by the next step) must give the
+    same fields as the blocking push; the forcing changes every step like surface_forcing does
+    (bounds_forcing.f:908-909)."""
+    from extpom_b200.pomgpu import PomGpu
+    dims = (96, 80, 16)
+    digs = []
+    for mode in ("sync", "async"):
+        st, g = syn.seamount(*dims, lambda a, b, c: PomGpu(a, b, c))
+        w0 = st["fields"]["wusurf"].copy(order="F")
+        pin = g.pinned("wusurf")
+        vl = []
+        for i in range(1, 7):
+            pin[...] = w0 * (1.0 + 0.1 * i)
+            if mode == "sync":
+                g.put("wusurf", pin)
+            else:
+                g.put_async("wusurf", pin)
+                g.sync() if i == 3 else None      # the host buffer may be rewritten only after the copy
+            g.step(i)
+            vl.append(g.check_velocity_lagged() if mode == "async" else g.check_velocity())
+            if mode == "async":
+                g.sync()                           # pin is rewritten next iteration
+        assert np.array_equal(g.get("wusurf"), w0 * 1.6)
+        digs.append({n: digest(g.get(n)) for n in ("u", "v", "t", "q2", "el", "ua", "wubot")})
+        if mode == "async":
+            assert vl[0] == 0.0 and vl[1:] == sync_v[:-1]
+        else:
+            sync_v = vl
+    assert digs[0] == digs[1]
