@@ -184,7 +184,8 @@ struct ProfqK : KBase {
   POM_KINFO("profq", 13, 8, 7, 0)
   double cgg, const1;
   double zr[KMAX];   // 1/|z(k)-z(1)| + 1/|z(k)-z(kb)| (:1429-1431), k-only: tabulated on the host
-  ProfqK(const Ctx* x, const double* hz) : KBase(x) {
+  int fuse;          // also bcond(6) + the Asselin filter of q2,q2l (advance.f:414-417) in the upward sweep
+  ProfqK(const Ctx* x, const double* hz, int fz) : KBase(x), fuse(fz) {
     // solver.f:1297: (15.8*cbcnst)**(2./3.) with single-precision literals promoted
     // to double; solver.f:1273 const1
     const double cbcnst = 100.;
@@ -267,7 +268,7 @@ struct ProfqK : KBase {
       // bcond(6) (advance.f:414) and km,kh,kq by the copies of :1510-1529
       if (k >= 2 && k <= kbm1) {
         double qb=fabs(o(Q2B,0,0)), qlb=fabs(o(Q2LB,0,0));
-        q2b(i,j,k)=qb; q2lb(i,j,k)=qlb;                                       // :1325-1326
+        if (!fuse) { q2b(i,j,k)=qb; q2lb(i,j,k)=qlb; }                        // :1325-1326
         double ll=fabs(qlb/qb);
         if (z(k) > -0.5) ll=fmax(ll,st.kl0);
         l(i,j,k)=ll;
@@ -312,8 +313,10 @@ struct ProfqK : KBase {
     double cv=1449.1+.00821*pp+4.55*tp-.045*(tp*tp)+1.34*(sp-35.0);
     double cck=cv/sqrt((1.-.01642*pp/cv)*(1.-0.40*pp/(cv*cv)));
     double qb=fabs(o(Q2B,0,0)), qlb=fabs(o(Q2LB,0,0));
-    q2b(i,j,k)=qb;                                                            // :1325-1326
-    q2lb(i,j,k)=qlb;
+    if (!fuse) {   // fused: the upward sweep takes the abs again and stores the FILTERED values
+      q2b(i,j,k)=qb;                                                          // :1325-1326
+      q2lb(i,j,k)=qlb;
+    }
     const double rhok=o(RHO,0,0);
     double boygr=grav*(st.rhom-rhok)/(dzz(k-1)*hh)
                  +(grav*grav)*2./(st.ccm*st.ccm+cck*cck);                     // :1327-1330
@@ -376,21 +379,76 @@ struct ProfqK : KBase {
   }
   // ---- back-substitutions (:1406-1413, :1448-1455) and abs (:1460-1471) ----
   // the recurrences use the signed iterate; abs() is applied by the reference afterwards
+  // fused tail of one level: mask + 1e-10 (bounds_forcing.f:318-319), new q2,q2l stay in uf,vf,
+  // filtered q2,q2l go to q2b,q2lb (advance.f:416-417); q2b,q2lb were left un-abs'ed on purpose
+  POM_HD void emit(int i, int j, int k, double a, double b, double m) const {
+    const int kbm1 = g.kb - 1;
+    a=a*m+1.e-10;
+    b=b*m+1.e-10;
+    uf(i,j,k)=a;
+    vf(i,j,k)=b;
+    double qb=q2b(i,j,k), qlb=q2lb(i,j,k);
+    if (k >= 2 && k <= kbm1) { qb=fabs(qb); qlb=fabs(qlb); }            // solver.f:1325-1326
+    const double q=q2(i,j,k), ql=q2l(i,j,k);
+    q2b(i,j,k)=q+.5*smoth*(a+qb-2.*q);                                  // advance.f:416
+    q2lb(i,j,k)=ql+.5*smoth*(b+qlb-2.*ql);                              // advance.f:417
+  }
   POM_HD void post(int i, int j, State& st, Cols& cm) const {
     POM_DIMS;
-    if (!st.interior) return;
-    double up=st.ufkb;
-    for (int ki = kbm1; ki >= 1; --ki) {
-      up=cm.ee[ki]*up+cm.gg[ki];
-      uf(i,j,ki)=(ki >= 2) ? fabs(up) : up;
+    if (!st.interior) {
+      if (!fuse) return;
+      // boundary columns: bcond(6) upstream values (bounds_forcing.f:264-311)
+      for (int k = kb; k >= 1; --k) {
+        double a, b;
+        if (j == 1) {                                                     // south (:290-299)
+          double u1=2.*v(i,2,k)*dti/(dy(i,1)+dy(i,2));
+          if (u1 >= 0.) { a=q2(i,1,k)-u1*(q2(i,1,k)-small); b=q2l(i,1,k)-u1*(q2l(i,1,k)-small); }
+          else { a=q2(i,1,k)-u1*(q2(i,2,k)-q2(i,1,k)); b=q2l(i,1,k)-u1*(q2l(i,2,k)-q2l(i,1,k)); }
+        } else if (j == jm) {                                             // north (:302-311)
+          double u1=2.*v(i,jm,k)*dti/(dy(i,jm)+dy(i,jmm1));
+          if (u1 <= 0.) { a=q2(i,jm,k)-u1*(small-q2(i,jm,k)); b=q2l(i,jm,k)-u1*(small-q2l(i,jm,k)); }
+          else { a=q2(i,jm,k)-u1*(q2(i,jm,k)-q2(i,jmm1,k)); b=q2l(i,jm,k)-u1*(q2l(i,jm,k)-q2l(i,jmm1,k)); }
+        } else if (i == 1) {                                              // west (:264-273)
+          double u1=2.*u(2,j,k)*dti/(dx(1,j)+dx(2,j));
+          if (u1 >= 0.) { a=q2(1,j,k)-u1*(q2(1,j,k)-small); b=q2l(1,j,k)-u1*(q2l(1,j,k)-small); }
+          else { a=q2(1,j,k)-u1*(q2(2,j,k)-q2(1,j,k)); b=q2l(1,j,k)-u1*(q2l(2,j,k)-q2l(1,j,k)); }
+        } else {                                                          // east (:276-285)
+          double u1=2.*u(im,j,k)*dti/(dx(im,j)+dx(imm1,j));
+          if (u1 <= 0.) { a=q2(im,j,k)-u1*(small-q2(im,j,k)); b=q2l(im,j,k)-u1*(small-q2l(im,j,k)); }
+          else { a=q2(im,j,k)-u1*(q2(im,j,k)-q2(imm1,j,k)); b=q2l(im,j,k)-u1*(q2l(im,j,k)-q2l(imm1,j,k)); }
+        }
+        emit(i,j,k,a,b,st.m);
+      }
+      return;
     }
-    double vp = 0.;                                                           // vf(kb)=0 (:1420)
-    vf(i,j,kb)=0.;
+    if (!fuse) {
+      double up=st.ufkb;
+      for (int ki = kbm1; ki >= 1; --ki) {
+        up=cm.ee[ki]*up+cm.gg[ki];
+        uf(i,j,ki)=(ki >= 2) ? fabs(up) : up;
+      }
+      double vp = 0.;                                                         // vf(kb)=0 (:1420)
+      vf(i,j,kb)=0.;
+      for (int ki = kbm1; ki >= 2; --ki) {
+        vp=cm.e2v[ki]*vp+cm.g2v[ki];
+        vf(i,j,ki)=fabs(vp);
+      }
+      vf(i,j,1)=0.;                                                           // :1419
+      return;
+    }
+    double up=st.ufkb, vp = 0.;
+    emit(i,j,kb,up,0.,st.m);                                                  // uf(kb) (:1285), vf(kb)=0 (:1420)
     for (int ki = kbm1; ki >= 2; --ki) {
+      {   // operands of the level below, towards L1 while this one is finished
+        const int o = POM_I3(i,j,ki-1);
+        POM_PREFETCH(p.q2+o); POM_PREFETCH(p.q2b+o); POM_PREFETCH(p.q2l+o); POM_PREFETCH(p.q2lb+o);
+      }
+      up=cm.ee[ki]*up+cm.gg[ki];
       vp=cm.e2v[ki]*vp+cm.g2v[ki];
-      vf(i,j,ki)=fabs(vp);
+      emit(i,j,ki,fabs(up),fabs(vp),st.m);
     }
-    vf(i,j,1)=0.;                                                             // :1419
+    up=cm.ee[1]*up+cm.gg[1];
+    emit(i,j,1,up,0.,st.m);                                                   // vf(1)=0 (:1419)
   }
 };
 
@@ -1349,7 +1407,15 @@ struct FbRoundTripK : KBase {
 void run_uvadjust(Ctx* c, int j0, int j1) { launch_cols(c, UvAdjustK(c), ALLI, j0, j1); }
 void run_vertvl(Ctx* c, int j0, int j1) { launch_cols(c, VertvlK(c), ALLI, j0, j1); }
 void run_advq(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvqK(c), ALLI, j0, j1); }
-void run_profq(Ctx* c, int j0, int j1) { launch_tma_cols(c, ProfqK(c, c->hz), ALLI, j0, j1); }
+// the fused variant under its own name / algorithmic byte count in the per-kernel profile
+struct ProfqFilterK : ProfqK {
+  POM_KINFO("profq_qfilter", 14, 8, 8, 0)
+  ProfqFilterK(const Ctx* x, const double* hz) : ProfqK(x, hz, 1) {}
+};
+void run_profq(Ctx* c, int fuse_filter, int j0, int j1) {
+  if (fuse_filter) launch_tma_cols(c, ProfqFilterK(c, c->hz), ALLI, j0, j1);
+  else launch_tma_cols(c, ProfqK(c, c->hz, 0), ALLI, j0, j1);
+}
 // caller swaps q2<->uf, q2l<->vf (advance.f:418-421)
 void run_qfilter(Ctx* c, int j0, int j1) { launch_cols(c, QFilterK(c), ALLI, j0, j1); }
 void run_advt(Ctx* c, int nadv, const double* fb, const double* f, const double* fc, double* ff, int j0, int j1) {

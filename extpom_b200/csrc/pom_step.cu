@@ -28,7 +28,7 @@ void run_ext_step(Ctx*, int iext, int do_adv, int, int);
 void run_uvadjust(Ctx*, int, int);
 void run_vertvl(Ctx*, int, int);
 void run_advq(Ctx*, int, int);
-void run_profq(Ctx*, int, int);
+void run_profq(Ctx*, int fuse_filter, int, int);
 void run_qfilter(Ctx*, int, int);
 void run_advt(Ctx*, int nadv, const double* fb, const double* f, const double* fc, double* ff, int, int);
 void run_fb_roundtrip(Ctx*, double* fb, const double* fc, double* f, int, int);
@@ -176,11 +176,13 @@ static void k_advq(Group* G) {
   EACH(run_advq(c, j0, j1));
   MADE(e, F_uf, F_vf);
 }
-static void k_profq(Group* G) {
+static void k_profq(Group* G, int fuse_filter) {
   int e = NEED({F_t, 0}, {F_s, 0}, {F_rho, 0}, {F_q2b, 0}, {F_q2lb, 0}, {F_q2, 0}, {F_u, 0}, {F_v, 1},
                {F_km, 0}, {F_kh, 0}, {F_kq, 0}, {F_uf, 0}, {F_vf, 0}, {F_etf, 0}, {F_wubot, 0}, {F_wvbot, 1});
-  EACH(run_profq(c, j0, j1));
+  if (fuse_filter) { const Req q[] = {{F_q2l, 0}}; int e2 = group_need(G, q, 1); if (e2 < e) e = e2; }
+  EACH(run_profq(c, fuse_filter, j0, j1));
   MADE(e, F_uf, F_vf, F_km, F_kh, F_kq, F_l, F_q2b, F_q2lb);
+  if (fuse_filter) { group_swap(G, F_q2, F_uf); group_swap(G, F_q2l, F_vf); }   // advance.f:418-421
 }
 static void k_qfilter(Group* G) {
   int e = NEED({F_uf, 0}, {F_vf, 0}, {F_q2, 0}, {F_q2b, 0}, {F_q2l, 0}, {F_q2lb, 0}, {F_u, 0}, {F_v, 0});
@@ -314,7 +316,8 @@ static int internal_stage(Group* G, int iint, int st) {
     case 0: k_uvadjust(G); break;
     case 1: k_vertvl(G); break;
     case 2: k_advq(G); break;
-    case 3: k_profq(G); break;
+    case 3: k_profq(G, 0); break;
+    case 103: k_profq(G, 1); break;                   // profq + bcond(6) + q filter fused (what the step runs)
     case 4: k_qfilter(G); break;
     case 5: if (ts) k_advt(G, F_tb, F_t, F_tclim, F_uf, F_q2); break;
     case 6: if (ts) k_advt(G, F_sb, F_s, F_sclim, F_vf, F_q2l); break;
@@ -340,6 +343,7 @@ static int mode_internal(Group* G, int iint) {
   const Consts& k = G->c[0]->c;
   if ((iint != 1 || k.time0 != 0.) && k.mode != 2)
     for (int st = 0; st <= 15; ++st) {
+      if (st == 3) { internal_stage(G, iint, 103); ++st; continue; }   // profq with the q2/q2l filter fused
       if (st == 7) { internal_stage(G, iint, 107); ++st; continue; }   // proft T and S in one kernel
       if (st == 9) { internal_stage(G, iint, 109); ++st; continue; }   // t/s filter with dens fused
       internal_stage(G, iint, st);
@@ -593,7 +597,7 @@ int pomgpu_advq(pomgpu_t* p) { SG; k_advq(G); return 0; }
 int pomgpu_advu(pomgpu_t* p) { SG; k_advu(G); return 0; }
 int pomgpu_advv(pomgpu_t* p) { SG; k_advv(G); return 0; }
 int pomgpu_baropg(pomgpu_t* p) { SG; k_baropg(G); return 0; }
-int pomgpu_profq(pomgpu_t* p) { SG; k_profq(G); return 0; }
+int pomgpu_profq(pomgpu_t* p) { SG; k_profq(G, 0); return 0; }
 int pomgpu_profu(pomgpu_t* p) { SG; k_profu(G); return 0; }
 int pomgpu_profv(pomgpu_t* p) { SG; k_profv(G); return 0; }
 int pomgpu_vertvl(pomgpu_t* p) { SG; k_vertvl(G); return 0; }

@@ -169,3 +169,31 @@ def check_golden(factory, name):
             a, b = a[:, :, :-1], b[:, :, :-1]
         assert rel_err(a, b) <= RTOL, n
     assert abs(float(z["vamax"]) - g.check_velocity()) <= RTOL
+
+
+def check_restore(factory, dims=(24, 19, 9), nstep=6):
+    """restore_interior arithmetic (bounds_forcing.f:1083-1118): the bracketing climatology
+    records and relaxation rates are pushed like the Fortran driver would after reading them
+    (:1039-1081); t, tb, s, sb are nudged every step, dens sees the nudged fields."""
+    st, o, g = pair(factory, dims, island=True)
+    rng = np.random.default_rng(7)
+    f = st["fields"]
+    rec = {
+        "trstrb": f["tclim"] + 0.5, "trstrf": f["tclim"] - 0.25,
+        "srstrb": f["sclim"] + 0.1, "srstrf": f["sclim"] - 0.05,
+        "taurstrb": np.asfortranarray(0.2 + 0.1 * rng.random(f["tclim"].shape)),
+        "taurstrf": np.asfortranarray(0.3 + 0.1 * rng.random(f["tclim"].shape)),
+    }
+    for s in (o, g):
+        for n, a in rec.items():
+            s.put(n, np.asfortranarray(a))
+        s.set("lrestore", 1)
+    for i in range(1, nstep + 1):
+        o.step(i); g.step(i)
+    worst = assert_close(o, g)
+    # the nudging must actually have moved t away from the un-restored run
+    _, o2, _g2 = pair(factory, dims, island=True)
+    for i in range(1, nstep + 1):
+        o2.step(i)
+    assert rel_err(o2.get("t")[:, :, :-1], o.get("t")[:, :, :-1]) > 1e-6
+    return worst

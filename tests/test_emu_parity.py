@@ -39,3 +39,7 @@ def test_unsupported_switches_set_error_status():
     with pytest.raises(Exception):
         g.step(1)
     assert g.getc("error_status") == 1
+
+
+def test_restore_interior_matches_oracle():
+    pc.check_restore(EmuPom)

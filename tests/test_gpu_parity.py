@@ -143,3 +143,7 @@ def test_async_forcing_push_equals_blocking_push():
         else:
             sync_v = vl
     assert digs[0] == digs[1]
+
+
+def test_restore_interior_matches_oracle():
+    pc.check_restore(_factory)
