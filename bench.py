@@ -177,9 +177,11 @@ def main():
     barrier()
     t0 = time.time()
     g.event_record(0)
+    th0 = time.perf_counter()
     for _ in range(K):
         iint += 1
         model.step(iint)
+    host_ms = (time.perf_counter() - th0) * 1e3 / K      # host time to ENQUEUE one step (asynchronous)
     g.event_record(1)
     barrier()
     t1 = time.time()
@@ -258,6 +260,7 @@ def main():
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "ms_per_step": ms_e2e / K, "vamax": vmax},
         "gpu_launches": launches,
+        "host_enqueue_ms_per_step": host_ms,
         "roofline": roof,
         "kernels": kernels,
     }

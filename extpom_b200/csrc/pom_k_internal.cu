@@ -495,23 +495,36 @@ struct QFilterK : KBase {
 // advt2 with nitera=1 (solver.f:577-731 + the fsm mask of smol_adif :1898-1900):
 // upstream advection, leapfrog update, horizontal diffusion of (fb-fclim); tile kernel:
 // every thread evaluates the upwind and the diffusive x/y fluxes of its own point once.
+template <int NT>   // NT tracers in one pass (T alone, or T and S sharing u, v, w, aam and the metrics)
 struct AdvT2K : KBase {
-  POM_KINFO("advt2", 6, 1, 10, 0)
-  const double *fb_, *f_, *fc_;
-  double* ff_;
-  AdvT2K(const Ctx* x, const double* fb, const double* f, const double* fc, double* ff)
-      : KBase(x), fb_(fb), f_(f), fc_(fc), ff_(ff) {}
-  static constexpr int NV = 4, HL = 0, HR = 1, HB = 0, HT = 1, TY = 16;
+  static const KInfo& info() {
+    static const KInfo k1{"advt2", 6, 1, 10, 0}, k2{"advt2_ts", 8, 2, 10, 0};
+    return NT == 1 ? k1 : k2;
+  }
+  const double *fb_[NT], *f_[NT], *fc_[NT];
+  double* ff_[NT];
+  AdvT2K(const Ctx* x, const double* fb, const double* f, const double* fc, double* ff) : KBase(x) {
+    fb_[0] = fb; f_[0] = f; fc_[0] = fc; ff_[0] = ff;
+  }
+  AdvT2K(const Ctx* x) : KBase(x) {   // T -> uf and S -> vf (advance.f:430-431)
+    fb_[0] = x->p.tb; f_[0] = x->p.t; fc_[0] = x->p.tclim; ff_[0] = x->p.uf;
+    fb_[NT - 1] = x->p.sb; f_[NT - 1] = x->p.s; fc_[NT - 1] = x->p.sclim; ff_[NT - 1] = x->p.vf;
+  }
+  static constexpr int NV = 4 * NT, HL = 0, HR = 1, HB = 0, HT = 1, TY = 16;
   // operands staged by the TMA: box = thread tile + one column W and one row S (34 x 17)
-  static constexpr int NF = 6, NS = 4, OHL = 1, OHR = 0, OHB = 1, OHT = 0, BW = 34, BH = 17, NK = 0;
+  static constexpr int NF = 2 * NT + 4, NS = 4, OHL = 1, OHR = 0, OHB = 1, OHT = 0, BW = 34, BH = 17, NK = 0;
   static constexpr bool UP = true;
-  enum { FB, FC, AAM, U, V, W };
-  enum { XF, YF, XD, YD };
-  POM_HD void fields(const double** b) const { b[FB] = fb_; b[FC] = fc_; b[AAM] = p.aam; b[U] = p.u; b[V] = p.v; b[W] = p.w; }
+  enum { AAM = 2 * NT, U, V, W };     // FB(t) = 2t, FC(t) = 2t+1
+  enum { XF, YF, XD, YD };            // + 4t
+  POM_HD void fields(const double** b) const {
+    for (int t = 0; t < NT; ++t) { b[2 * t] = fb_[t]; b[2 * t + 1] = fc_[t]; }
+    b[AAM] = p.aam; b[U] = p.u; b[V] = p.v; b[W] = p.w;
+  }
   struct State {
     double cx, cy, hx, hy, dumc, dvmc, dys, dxs;   // .25*(dy+dy)*(dt+dt), (h+h), masks, (dy+dy(i-1)), (dx+dx(j-1))
     RDiv ddxs, ddys, def;                          // (dx+dx(i-1)), (dy+dy(j-1)), (h+etf)*art
-    double eb, ar, m, zk, fb0;                     // (h+etb)*art, art, fsm, zflux(k), fb(i,j,k)
+    double eb, ar, m;                              // (h+etb)*art, art, fsm
+    double zk[NT], fb0[NT];                        // zflux(k), fb(i,j,k) of each tracer
     bool fxa, fya, interior;
   };
   POM_HD int k0() const { return 1; }
@@ -538,28 +551,33 @@ struct AdvT2K : KBase {
       s.ar = art(i,j);
       s.eb = (h(i,j)+etb(i,j))*s.ar;
       s.def.set((h(i,j)+etf(i,j))*s.ar);
-      s.zk = w(i,j,1)*A3(f_,i,j,1)*s.ar;                                // :648 (itera==1)
+      const double w1 = w(i,j,1);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) s.zk[t] = w1*A3(f_[t],i,j,1)*s.ar;   // :648 (itera==1)
     }
   }
   template <class Op>
   POM_HD void stage(int i, int j, int k, State& s, const Op& o, double* v) const {
     if (!(s.fxa || s.fya || s.interior)) return;
-    const double fb0=o(FB,0,0), a0=o(AAM,0,0);
-    const double fd0=fb0-o(FC,0,0);                                     // fb-fclim (:691)
-    s.fb0=fb0;
-    if (s.fxa) {
-      const double fbW=o(FB,-1,0);
-      const double xm=s.cx*o(U,0,0);                                    // :605-606
-      v[XF]=0.5*((xm+fabs(xm))*fbW+(xm-fabs(xm))*fb0);                  // :631-635
-      const double xd=0.5*(a0+o(AAM,-1,0));                             // :696
-      v[XD]=s.ddxs(-xd*s.hx*tprni*(fd0-(fbW-o(FC,-1,0)))*s.dumc*s.dys*0.5);   // :705-707
-    }
-    if (s.fya) {
-      const double fbS=o(FB,0,-1);
-      const double ym=s.cy*o(V,0,0);                                    // :612-613
-      v[YF]=0.5*((ym+fabs(ym))*fbS+(ym-fabs(ym))*fb0);                  // :637-641
-      const double yd=0.5*(a0+o(AAM,0,-1));                             // :697
-      v[YD]=s.ddys(-yd*s.hy*tprni*(fd0-(fbS-o(FC,0,-1)))*s.dvmc*s.dxs*0.5);   // :708-710
+    const double a0=o(AAM,0,0);
+    double xm = 0., xd = 0., ym = 0., yd = 0.;
+    if (s.fxa) { xm=s.cx*o(U,0,0); xd=0.5*(a0+o(AAM,-1,0)); }           // :605-606, :696
+    if (s.fya) { ym=s.cy*o(V,0,0); yd=0.5*(a0+o(AAM,0,-1)); }           // :612-613, :697
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const double fb0=o(2*t,0,0);
+      const double fd0=fb0-o(2*t+1,0,0);                                // fb-fclim (:691)
+      s.fb0[t]=fb0;
+      if (s.fxa) {
+        const double fbW=o(2*t,-1,0);
+        v[4*t+XF]=0.5*((xm+fabs(xm))*fbW+(xm-fabs(xm))*fb0);            // :631-635
+        v[4*t+XD]=s.ddxs(-xd*s.hx*tprni*(fd0-(fbW-o(2*t+1,-1,0)))*s.dumc*s.dys*0.5);   // :705-707
+      }
+      if (s.fya) {
+        const double fbS=o(2*t,0,-1);
+        v[4*t+YF]=0.5*((ym+fabs(ym))*fbS+(ym-fabs(ym))*fb0);            // :637-641
+        v[4*t+YD]=s.ddys(-yd*s.hy*tprni*(fd0-(fbS-o(2*t+1,0,-1)))*s.dvmc*s.dxs*0.5);   // :708-710
+      }
     }
   }
   template <class Op>
@@ -567,25 +585,32 @@ struct AdvT2K : KBase {
     if (!s.interior) {
       // ff is not assigned here by the reference (bcond(4) sets it afterwards); only the
       // smol_adif mask applies
-      A3(ff_,i,j,k)=A3(ff_,i,j,k)*s.m;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) A3(ff_[t],i,j,k)=A3(ff_[t],i,j,k)*s.m;
       return;
     }
-    double zk1 = 0.;                                                    // zflux(k+1); :651 at kb
-    if (k + 1 <= g.kb - 1) {
-      const double w1=o.up(W), fb1=o.up(FB);
-      zk1=0.5*((w1+fabs(w1))*fb1+(w1-fabs(w1))*s.fb0);                  // :656-660
-      zk1=zk1*s.ar;                                                     // :661
+    const bool more = (k + 1 <= g.kb - 1);
+    const double w1 = more ? o.up(W) : 0.;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      double zk1 = 0.;                                                  // zflux(k+1); :651 at kb
+      if (more) {
+        const double fb1=o.up(2*t);
+        zk1=0.5*((w1+fabs(w1))*fb1+(w1-fabs(w1))*s.fb0[t]);             // :656-660
+        zk1=zk1*s.ar;                                                   // :661
+      }
+      double q=tl(4*t+XF,1,0)-tl(4*t+XF,0,0)+tl(4*t+YF,0,1)-tl(4*t+YF,0,0)+(s.zk[t]-zk1)/dz(k);   // :670-672
+      q=s.def(s.fb0[t]*s.eb-dti2*q);                                    // :673-674
+      q=q*s.m;                                                          // smol_adif :1899
+      q=q-s.def(dti2*(tl(4*t+XD,1,0)-tl(4*t+XD,0,0)+tl(4*t+YD,0,1)-tl(4*t+YD,0,0)));   // :721-723
+      POM_STCS(&A3(ff_[t],i,j,k),q);
+      s.zk[t]=zk1;
     }
-    double q=tl(XF,1,0)-tl(XF,0,0)+tl(YF,0,1)-tl(YF,0,0)+(s.zk-zk1)/dz(k);   // :670-672
-    q=s.def(s.fb0*s.eb-dti2*q);                                         // :673-674
-    q=q*s.m;                                                            // smol_adif :1899
-    q=q-s.def(dti2*(tl(XD,1,0)-tl(XD,0,0)+tl(YD,0,1)-tl(YD,0,0)));      // :721-723
-    POM_STCS(&A3(ff_,i,j,k),q);
-    s.zk=zk1;
   }
   POM_HD void post(int i, int j, State& s) const {
     const int kb = g.kb;
-    A3(ff_,i,j,kb)=A3(ff_,i,j,kb)*s.m;                                  // smol_adif mask, level kb
+#pragma unroll
+    for (int t = 0; t < NT; ++t) A3(ff_[t],i,j,kb)=A3(ff_[t],i,j,kb)*s.m;   // smol_adif mask, level kb
   }
 };
 
@@ -1420,8 +1445,10 @@ void run_profq(Ctx* c, int fuse_filter, int j0, int j1) {
 void run_qfilter(Ctx* c, int j0, int j1) { launch_cols(c, QFilterK(c), ALLI, j0, j1); }
 void run_advt(Ctx* c, int nadv, const double* fb, const double* f, const double* fc, double* ff, int j0, int j1) {
   if (nadv == 1) launch_cols(c, AdvT1K(c, fb, f, fc, ff), ALLI, j0, j1);
-  else launch_tma_tiles(c, AdvT2K(c, fb, f, fc, ff), ALLI, j0, j1);
+  else launch_tma_tiles(c, AdvT2K<1>(c, fb, f, fc, ff), ALLI, j0, j1);
 }
+// advt2 of T (-> uf) and S (-> vf) in one pass (nitera=1)
+void run_advt2_ts(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvT2K<2>(c), ALLI, j0, j1); }
 void run_advt2_mass(Ctx* c, double* xm, double* ym, double* zw, int j0, int j1) {
   launch_cols(c, AdvT2MassK(c, xm, ym, zw), ALLI, j0, j1);
 }

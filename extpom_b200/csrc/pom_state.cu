@@ -141,7 +141,17 @@ int dev_sync(Ctx* c) {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// descriptors are cached per (buffer, levels, box): a step re-uses ~100 distinct ones ~600 times
+struct TmaCacheEnt { const double* base; int nk, bw, bh; CUtensorMap m; };
+static TmaCacheEnt* tma_cache_of(Ctx* c) {
+  if (!c->tma_cache) c->tma_cache = calloc(512, sizeof(TmaCacheEnt));
+  return (TmaCacheEnt*)c->tma_cache;
+}
 int tma_encode(Ctx* c, CUtensorMap* m, const double* base, int nk, int bw, int bh) {
+  TmaCacheEnt* tc = tma_cache_of(c);
+  const size_t hsh = (((size_t)base >> 8) * 2654435761u + (size_t)nk * 97 + (size_t)bw * 7 + (size_t)bh) & 511;
+  TmaCacheEnt& ce = tc[hsh];
+  if (ce.base == base && ce.nk == nk && ce.bw == bw && ce.bh == bh) { *m = ce.m; return 0; }
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -156,7 +166,9 @@ int tma_encode(Ctx* c, CUtensorMap* m, const double* base, int nk, int bw, int b
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : 1;
+  if (r != CUDA_SUCCESS) return 1;
+  ce.base = base; ce.nk = nk; ce.bw = bw; ce.bh = bh; ce.m = *m;
+  return 0;
 }
 #endif
 
@@ -247,6 +259,7 @@ void ctx_destroy(Ctx* c) {
 #else
   cudaFree(c->d_red); cudaFreeHost(c->h_red);
   for (int f = 0; f < 256; ++f) if (c->shadow[f]) cudaFree(c->shadow[f]);
+  free(c->tma_cache);
   if (c->copy_stream) cudaStreamDestroy((cudaStream_t)c->copy_stream);
   if (c->ev_copied) cudaEventDestroy((cudaEvent_t)c->ev_copied);
   if (c->ev_swapped) cudaEventDestroy((cudaEvent_t)c->ev_swapped);

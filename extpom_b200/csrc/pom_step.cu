@@ -40,6 +40,7 @@ void run_advt2_diff(Ctx*, const double* fb, const double* fc, double* ff, int, i
 void run_proft(Ctx*, double* f, const double* wf, const double* fs, int nbc, int, int);
 void run_tsfilter(Ctx*, int with_dens, int, int);
 void run_proft_ts(Ctx*, int, int);
+void run_advt2_ts(Ctx*, int, int);
 void run_dens(Ctx*, const double* si, const double* ti, double* ro, int, int);
 void run_advu(Ctx*, int, int);
 void run_advv(Ctx*, int, int);
@@ -233,6 +234,12 @@ static void k_proft(Group* G, int f, int wf, int fs, int nbc) {
   EACH(run_proft(c, FP(c, f), FP(c, wf), FP(c, fs), nbc, j0, j1));
   MADE(e, f);
 }
+static void k_advt2_ts(Group* G) {   // advt2(tb,t,tclim,uf) and advt2(sb,s,sclim,vf) in one pass (nitera=1)
+  int e = NEED({F_tb, 1}, {F_t, 0}, {F_sb, 1}, {F_s, 0}, {F_u, 0}, {F_v, 1}, {F_w, 0}, {F_aam, 1}, {F_dt, 1},
+               {F_etb, 0}, {F_etf, 0});
+  EACH(run_advt2_ts(c, j0, j1));
+  MADE(e, F_uf, F_vf);
+}
 static void k_proft_ts(Group* G) {   // proft(uf,wtsurf,tsurf,nbct) and proft(vf,wssurf,ssurf,nbcs) in one pass
   int e = NEED({F_uf, 0}, {F_vf, 0}, {F_kh, 0}, {F_etf, 0});
   EACH(run_proft_ts(c, j0, j1));
@@ -324,6 +331,7 @@ static int internal_stage(Group* G, int iint, int st) {
     case 7: if (ts) k_proft(G, F_uf, F_wtsurf, F_tsurf, k.nbct); break;
     case 8: if (ts) k_proft(G, F_vf, F_wssurf, F_ssurf, k.nbcs); break;
     case 9: if (ts) k_tsfilter(G, 0); break;
+    case 105: if (ts) { if (k.nadv == 2 && k.nitera == 1) k_advt2_ts(G); else { internal_stage(G, iint, 5); internal_stage(G, iint, 6); } } break;
     case 107: if (ts) k_proft_ts(G); break;           // proft of T and S fused (what the step runs)
     case 109: if (ts) k_tsfilter(G, 1); break;        // + dens fused (what the step runs)
     case 10: if (ts) k_dens(G, F_s, F_t, F_rho); break;
@@ -344,6 +352,7 @@ static int mode_internal(Group* G, int iint) {
   if ((iint != 1 || k.time0 != 0.) && k.mode != 2)
     for (int st = 0; st <= 15; ++st) {
       if (st == 3) { internal_stage(G, iint, 103); ++st; continue; }   // profq with the q2/q2l filter fused
+      if (st == 5) { internal_stage(G, iint, 105); ++st; continue; }   // advt2 of T and S in one kernel
       if (st == 7) { internal_stage(G, iint, 107); ++st; continue; }   // proft T and S in one kernel
       if (st == 9) { internal_stage(G, iint, 109); ++st; continue; }   // t/s filter with dens fused
       internal_stage(G, iint, st);

@@ -225,7 +225,7 @@ template <class F>
 __global__ void __launch_bounds__(TILE_X * F::TY, 1)
 tilekernel_g(const F f, int i0, int i1, int j0, int j1) {
   constexpr int OX = TILE_X - F::HL - F::HR, OY = F::TY - F::HB - F::HT, NV = F::NV;
-  __shared__ double S[2 * NV * TILE_Y * TILE_X];
+  __shared__ double S[NV * TILE_Y * TILE_X];   // single buffer (static shared memory is capped at 48 kB)
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i = i0 + blockIdx.x * OX - F::HL + tx, j = j0 + blockIdx.y * OY - F::HB + ty;
   const bool inside = (i >= 1 && i <= f.g.im && j >= f.g.joff + 1 && j <= f.g.joff + f.g.jml);
@@ -234,7 +234,6 @@ tilekernel_g(const F f, int i0, int i1, int j0, int j1) {
   f.fields(fld);
   typename F::State st;
   f.pre(i, j, inside, out, st);
-  int buf = 0;
   const int k1 = f.k1();
   for (int k = f.k0(); k <= k1; ++k) {
     const GlobalOp<F> op{fld, f.g, i, j, k};
@@ -242,12 +241,11 @@ tilekernel_g(const F f, int i0, int i1, int j0, int j1) {
 #pragma unroll
     for (int n = 0; n < NV; ++n) v[n] = 0.;
     if (inside) f.stage(i, j, k, st, op, v);
-    double* Sb = S + buf * NV * TILE_Y * TILE_X;
 #pragma unroll
-    for (int n = 0; n < NV; ++n) Sb[(n * TILE_Y + ty) * TILE_X + tx] = v[n];
+    for (int n = 0; n < NV; ++n) S[(n * TILE_Y + ty) * TILE_X + tx] = v[n];
     __syncthreads();
-    if (out) f.combine(i, j, k, st, op, Tile2{Sb, tx, ty});
-    buf ^= 1;
+    if (out) f.combine(i, j, k, st, op, Tile2{S, tx, ty});
+    __syncthreads();
   }
   if (out) f.post(i, j, st);
 }

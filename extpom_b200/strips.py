@@ -12,7 +12,7 @@ import numpy as np
 from . import synthetic as syn
 from .pomgpu import PomGpu, PomGroup
 
-GHOST = 4
+GHOST = 8   # rows of redundant computation per seam: one batched exchange every ~4 external substeps
 
 
 def partition(jm, world):
@@ -58,6 +58,7 @@ class StripSet:
         (NCCL backend on the GPU box) used once, to broadcast the NCCL unique id."""
         factory = factory or (lambda a, b, c, strip=None, ghost=0: PomGpu(a, b, c, device=device, strip=strip, ghost=ghost))
         own = partition(jm_global, world)[rank]
+        ghost = max(2, min(ghost, min(b - a + 1 for a, b in partition(jm_global, world)) - 4))
         st, g = make_strip(im, jm_global, kb, own, ghost, factory, **kw)
         grp = PomGroup([g])
         if world > 1:
