@@ -1293,6 +1293,118 @@ struct ProfvK : KBase {
 };
 
 // ---------------------------------------------------------------------------
+// advu + profu (VC=false) / advv + profv (VC=true) in one TMA-fed column kernel: the explicit
+// tendency uf(k) of solver.f:734-788 (791-845) is consumed by the forward elimination of
+// solver.f:1686-1780 (1783-1877) at the same level, so it never makes the round trip through
+// HBM.  B = the "back" neighbour (i-1 for u, j-1 for v), O = the other direction (j+1 / i+1).
+template <bool VC>
+struct AdvProfUVK : KBase {
+  static const KInfo& info() {
+    static const KInfo ku{"advu_profu", 7, 1, 14, 1}, kv{"advv_profv", 7, 1, 14, 1};
+    return VC ? kv : ku;
+  }
+  using KBase::KBase;
+  static constexpr int TY = 8, MINB = 2;
+  static constexpr int NF = 7, NS = 4, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = 10, NK = 0;
+  static constexpr bool UP = true;
+  static constexpr int BI = VC ? 0 : -1, BJ = VC ? -1 : 0, OI = VC ? 1 : 0, OJ = VC ? 0 : 1;
+  enum { W, X, Y, ADV, DRHO, XB, KM };
+  POM_HD void fields(const double** b) const {
+    b[W] = p.w; b[X] = VC ? p.v : p.u; b[Y] = VC ? p.u : p.v; b[ADV] = VC ? p.advy : p.advx;
+    b[DRHO] = VC ? p.drhoy : p.drhox; b[XB] = VC ? p.vb : p.ub; b[KM] = p.km;
+  }
+  POM_HD double* xf() const { return VC ? p.vf : p.uf; }
+  struct Cols { double ee[KMAX], gg[KMAX]; };
+  struct State { double ar, sl, hb, hf, c0, cB, dh, fk, xm, eem, ggm, ck, xfl; bool interior, live; };
+  POM_HD int k0() const { return 1; }
+  POM_HD int k1() const { return g.kb - 1; }
+  POM_HD int kl1() const { return g.kb - 1; }
+  POM_HD void pre(int i, int j, State& s, Cols&) const {
+    POM_DIMS;
+    s.interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
+    s.live = VC ? (j >= 2) : (i >= 2);          // the vertical-flux intermediate exists (:744-751, :801-808)
+    s.fk = 0.; s.xm = 0.;
+    double* f = xf();
+    A3(f,i,j,kb)=0.;
+    if (!s.interior) { A3(f,i,j,1)=0.; return; }
+    const int ib = i + BI, jb = j + BJ;
+    s.ar = VC ? arv(i,j) : aru(i,j);
+    const double dd = VC ? (dx(i,j)+dx(ib,jb)) : (dy(i,j)+dy(ib,jb));
+    s.sl=grav*.125*(dt(i,j)+dt(ib,jb))
+         *(egf(i,j)-egf(ib,jb)+egb(i,j)-egb(ib,jb)
+           +(e_atmos(i,j)-e_atmos(ib,jb))*2.)
+         *dd;                                                           // :765-768 / :822-825
+    s.hb=(h(i,j)+etb(i,j)+h(ib,jb)+etb(ib,jb))*s.ar;
+    s.hf=(h(i,j)+etf(i,j)+h(ib,jb)+etf(ib,jb))*s.ar;
+    s.c0=cor(i,j)*dt(i,j); s.cB=cor(ib,jb)*dt(ib,jb);
+    s.dh=(h(i,j)+etf(i,j)+h(ib,jb)+etf(ib,jb))*.5;                      // :1703 / :1801
+  }
+  template <class Op>
+  POM_HD void level(int i, int j, int k, State& s, Cols& cm, const Op& o) const {
+    POM_DIMS;
+    double* f = xf();
+    const double x0=o(X,0,0);
+    if (!s.interior) {
+      // outside the interior only the vertical-flux intermediate survives (:744-751)
+      if (k >= 2) A3(f,i,j,k)=s.live ? .25*(o(W,0,0)+o(W,BI,BJ))*(x0+s.xm) : 0.;
+      s.xm=x0;
+      return;
+    }
+    // ---- explicit tendency (advu :753-785 / advv :810-842) ----
+    const double fk1 = (k + 1 <= kbm1) ? .25*(o.up(W)+o.up(W,BI,BJ))*(o.up(X)+x0) : 0.;   // :747-748
+    const double ct=s.c0*(o(Y,OI,OJ)+o(Y,0,0))+s.cB*(o(Y,BI+OI,BJ+OJ)+o(Y,BI,BJ));
+    double r=o(ADV,0,0)+(s.fk-fk1)*s.ar/dz(k);
+    r = VC ? r+s.ar*.25*ct : r-s.ar*.25*ct;                             // :760-763 / :817-820
+    r=r+s.sl+o(DRHO,0,0);                                               // :764-769
+    const double xk=(s.hb*o(XB,0,0)-2.*dti2*r)/s.hf;                    // :778-782
+    s.fk=fk1;
+    // ---- forward elimination (profu :1711-1748 / profv :1809-1845) ----
+    const double dh=s.dh;
+    if (k == 1) {
+      const double cn=(o.up(KM)+o.up(KM,BI,BJ))*.5;                     // :1715 at k=2
+      const double ak=-dti2*(cn+umol)/(dz(1)*dzz(1)*dh*dh);             // a(1) (:1723)
+      const double ws = VC ? wvsurf(i,j) : wusurf(i,j);
+      s.eem=ak/(ak-1.);                                                 // :1733
+      s.ggm=(-dti2*ws/(-dz(1)*dh)-xk)/(ak-1.);                          // :1734-1736
+      s.ck=-dti2*(cn+umol)/(dz(2)*dzz(1)*dh*dh);                        // c(2) (:1725)
+      cm.ee[1]=s.eem; cm.gg[1]=s.ggm;
+    } else if (k <= kbm2) {                                             // :1740-1748
+      const double cn=(o.up(KM)+o.up(KM,BI,BJ))*.5;
+      const double ak=-dti2*(cn+umol)/(dz(k)*dzz(k)*dh*dh);             // a(k)
+      const double gi=1./(ak+s.ck*(1.-s.eem)-1.);
+      s.eem=ak*gi;
+      s.ggm=(s.ck*s.ggm-xk)*gi;
+      s.ck=-dti2*(cn+umol)/(dz(k+1)*dzz(k)*dh*dh);                      // c(k+1)
+      cm.ee[k]=s.eem; cm.gg[k]=s.ggm;
+    } else {
+      s.xfl=xk;                                                         // uf(kbm1), used by the bottom condition
+    }
+  }
+  POM_HD void post(int i, int j, State& s, Cols& cm) const {
+    POM_DIMS;
+    if (!s.interior) return;
+    double* f = xf();
+    const int ib = i + BI, jb = j + BJ;
+    const double* yb = VC ? p.ub : p.vb;
+    const double* xb = VC ? p.vb : p.ub;
+    const double ybar=.25*(A3(yb,i,j,kbm1)+A3(yb,i+OI,j+OJ,kbm1)+A3(yb,ib,jb,kbm1)+A3(yb,ib+OI,jb+OJ,kbm1));
+    const double xo=A3(xb,i,j,kbm1);
+    const double sp = VC ? sqrt(ybar*ybar+xo*xo) : sqrt(xo*xo+ybar*ybar);
+    const double tp=0.5*(cbc(i,j)+cbc(ib,jb))*sp;                       // :1752-1755 / :1849-1852
+    double fk=(s.ck*s.ggm-s.xfl)
+              /(tp*dti2/(-dz(kbm1)*s.dh)-1.-(s.eem-1.)*s.ck);           // :1756-1758
+    const double m = VC ? dvm(i,j) : dum(i,j);
+    fk=fk*m;                                                            // :1759
+    A3(f,i,j,kbm1)=fk;
+    if (VC) wvbot(i,j)=-tp*fk; else wubot(i,j)=-tp*fk;                  // :1774 / :1871
+    for (int ki = kb-2; ki >= 1; --ki) {                                // :1763-1770
+      fk=(cm.ee[ki]*fk+cm.gg[ki])*m;
+      A3(f,i,j,ki)=fk;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
 // bcondorl(3) (bounds_forcing.f:418-487) + Asselin filter with depth-mean
 // removal and rotation of u,v (advance.f:469-514).  The Orlanski points read ub,vb
 // of their neighbours, so the filtered u,v go to the scratch buffers s3a,s3b (which
@@ -1480,6 +1592,8 @@ void run_dens(Ctx* c, const double* si, const double* ti, double* ro, int j0, in
 }
 void run_advu(Ctx* c, int j0, int j1) { launch_cols(c, AdvuK(c), ALLI, j0, j1); }
 void run_advv(Ctx* c, int j0, int j1) { launch_cols(c, AdvvK(c), ALLI, j0, j1); }
+void run_advprof_u(Ctx* c, int j0, int j1) { launch_tma_cols(c, AdvProfUVK<false>(c), ALLI, j0, j1); }
+void run_advprof_v(Ctx* c, int j0, int j1) { launch_tma_cols(c, AdvProfUVK<true>(c), ALLI, j0, j1); }
 void run_profu(Ctx* c, int j0, int j1) { launch_cols(c, ProfuK(c), ALLI, j0, j1); }
 void run_profv(Ctx* c, int j0, int j1) { launch_cols(c, ProfvK(c), ALLI, j0, j1); }
 // caller swaps u<->uf, v<->vf, ub<->s3a, vb<->s3b (advance.f:511-514)

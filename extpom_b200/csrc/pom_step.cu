@@ -41,6 +41,8 @@ void run_proft(Ctx*, double* f, const double* wf, const double* fs, int nbc, int
 void run_tsfilter(Ctx*, int with_dens, int, int);
 void run_proft_ts(Ctx*, int, int);
 void run_advt2_ts(Ctx*, int, int);
+void run_advprof_u(Ctx*, int, int);
+void run_advprof_v(Ctx*, int, int);
 void run_dens(Ctx*, const double* si, const double* ti, double* ro, int, int);
 void run_advu(Ctx*, int, int);
 void run_advv(Ctx*, int, int);
@@ -279,6 +281,20 @@ static void k_profv(Group* G) {
   EACH(run_profv(c, j0, j1));
   MADE(e, F_vf, F_wvbot);
 }
+// advu+profu and advv+profv fused (the order advu, advv, profu, profv of advance.f:459-462 does
+// not matter: each pair only reads u, v, ub, vb, w and writes its own uf / vf, wubot / wvbot)
+static void k_advprof_u(Group* G) {
+  int e = NEED({F_w, 0}, {F_u, 0}, {F_v, 1}, {F_advx, 0}, {F_drhox, 0}, {F_ub, 0}, {F_vb, 1}, {F_km, 0}, {F_dt, 0},
+               {F_egf, 0}, {F_egb, 0}, {F_etb, 0}, {F_etf, 0}, {F_wubot, 0});
+  EACH(run_advprof_u(c, j0, j1));
+  MADE(e, F_uf, F_wubot);
+}
+static void k_advprof_v(Group* G) {
+  int e = NEED({F_w, 1}, {F_v, 0}, {F_u, 1}, {F_advy, 0}, {F_drhoy, 0}, {F_vb, 0}, {F_ub, 1}, {F_km, 1}, {F_dt, 1},
+               {F_egf, 1}, {F_egb, 1}, {F_etb, 1}, {F_etf, 1}, {F_wvbot, 0});
+  EACH(run_advprof_v(c, j0, j1));
+  MADE(e, F_vf, F_wvbot);
+}
 static void k_uvfilter(Group* G) {
   int e = NEED({F_uf, 0}, {F_vf, 0}, {F_u, 0}, {F_v, 0}, {F_ub, 0}, {F_vb, 0});
   EACH(run_uvfilter(c, j0, j1));
@@ -332,7 +348,8 @@ static int internal_stage(Group* G, int iint, int st) {
     case 8: if (ts) k_proft(G, F_vf, F_wssurf, F_ssurf, k.nbcs); break;
     case 9: if (ts) k_tsfilter(G, 0); break;
     case 105: if (ts) { if (k.nadv == 2 && k.nitera == 1) k_advt2_ts(G); else { internal_stage(G, iint, 5); internal_stage(G, iint, 6); } } break;
-    case 107: if (ts) k_proft_ts(G); break;           // proft of T and S fused (what the step runs)
+    case 107: if (ts) k_proft_ts(G); break;
+    case 111: k_advprof_u(G); k_advprof_v(G); break;   // stages 11-14 as two fused kernels (what the step runs)           // proft of T and S fused (what the step runs)
     case 109: if (ts) k_tsfilter(G, 1); break;        // + dens fused (what the step runs)
     case 10: if (ts) k_dens(G, F_s, F_t, F_rho); break;
     case 11: k_advu(G); break;
@@ -355,6 +372,7 @@ static int mode_internal(Group* G, int iint) {
       if (st == 5) { internal_stage(G, iint, 105); ++st; continue; }   // advt2 of T and S in one kernel
       if (st == 7) { internal_stage(G, iint, 107); ++st; continue; }   // proft T and S in one kernel
       if (st == 9) { internal_stage(G, iint, 109); ++st; continue; }   // t/s filter with dens fused
+      if (st == 11) { internal_stage(G, iint, 111); st = 14; continue; }  // advu+profu, advv+profv
       internal_stage(G, iint, st);
     }
   internal_stage(G, iint, 16);

@@ -41,6 +41,11 @@ struct GlobalOp {
     return fld[f][POM_I3(ii, jj, k)];
   }
   POM_HD double up(int f) const { return (k + 1 <= g.kb) ? fld[f][POM_I3(i, j, k + 1)] : 0.; }
+  POM_HD double up(int f, int di, int dj) const {
+    const int ii = i + di, jj = j + dj;
+    if (k + 1 > g.kb || ii < 1 || ii > g.im || jj < g.joff + 1 || jj > g.joff + g.jml) return 0.;
+    return fld[f][POM_I3(ii, jj, k + 1)];
+  }
 };
 
 struct Tile2 {
@@ -82,6 +87,7 @@ struct SmemOp {
   static constexpr int PL = tma_plane(F::BW, F::BH);
   __device__ __forceinline__ double operator()(int f, int di, int dj) const { return cur[f * PL + dj * F::BW + di]; }
   __device__ __forceinline__ double up(int f) const { return nxt[f * PL]; }
+  __device__ __forceinline__ double up(int f, int di, int dj) const { return nxt[f * PL + dj * F::BW + di]; }
 };
 
 template <class F>
