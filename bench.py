@@ -195,17 +195,24 @@ def main():
     for n, buf in pins.items():
         buf[...] = g.get(n)
     h2d = sum(b.nbytes for b in pins.values())
-    barrier()
-    g.event_record(2)
-    vmax = 0.0
-    for _ in range(K):
+
+    def e2e_step():
+        nonlocal iint
         iint += 1
         for n, buf in pins.items():
             g.put_async(n, buf)                 # per-step forcing (bounds_forcing.f:844-865,908-978)
         model.step(iint)
         # advance.f:52: one scalar back per step -- read with one step of lag, so that the host
         # can enqueue the next step's forcing copies while this step still computes
-        vmax = max(vmax, g.check_velocity_lagged())
+        return g.check_velocity_lagged()
+
+    for _ in range(2):                          # untimed: allocates the shadow buffers of the async pushes
+        e2e_step()
+    barrier()
+    g.event_record(2)
+    vmax = 0.0
+    for _ in range(K):
+        vmax = max(vmax, e2e_step())
     vmax = max(vmax, g.check_velocity())       # the last step's own value (waits)
     g.event_record(3)
     barrier()

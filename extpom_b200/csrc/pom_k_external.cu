@@ -118,8 +118,12 @@ struct ExtStepK : KBase {
   POM_KINFO("ext_step", 0, 0, 31, 12)
   int iext, do_adv;
   ExtStepK(const Ctx* x, int ie, int adv) : KBase(x), iext(ie), do_adv(adv) {}
-  static constexpr int NV = 6, TY = 16, MINB = 2;
-  static constexpr int NF = 13, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = 18, NK = 1;
+#ifndef POM_EXT_TY
+#define POM_EXT_TY 16
+#define POM_EXT_MINB 2
+#endif
+  static constexpr int NV = 6, TY = POM_EXT_TY, MINB = POM_EXT_MINB;
+  static constexpr int NF = 13, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = POM_EXT_TY + 2, NK = 1;
   enum { D = OP_D, UA = OP_UA, VA = OP_VA, UAB = OP_UAB, VAB = OP_VAB, AAM2D = OP_AAM2D, DX = OP_DX, DY = OP_DY,
          EL, ELB, H, COR, EATM };
   enum { FUA, FVA, FXU, FYU, FXV, FYV };

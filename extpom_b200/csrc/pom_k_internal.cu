@@ -1428,6 +1428,7 @@ struct UvFilterK : KBase {
     const double mu=dum(i,j), mv=dvm(i,j);
     double su = 0., sv = 0.;
     double nu[KMAX], nv[KMAX];
+    const bool edge0 = !(iin && jin) || i == 2 || j == 2;
     for (int k = 1; k <= kbm1; ++k) {
       PF3(p.uf,i,j,k+2); PF3(p.vf,i,j,k+2); PF3(p.ub,i,j,k+2); PF3(p.vb,i,j,k+2); PF3(p.u,i,j,k+2); PF3(p.v,i,j,k+2);
       double a=uf(i,j,k), b=vf(i,j,k);
@@ -1451,13 +1452,15 @@ struct UvFilterK : KBase {
       }
       a=a*mu;                                                           // :481-482
       b=b*mv;
-      nu[k]=a; nv[k]=b;
+      if (edge0) { nu[k]=a; nv[k]=b; }
       su=su+(a+ub(i,j,k)-2.*u(i,j,k))*dz(k);                            // advance.f:474-475
       sv=sv+(b+vb(i,j,k)-2.*v(i,j,k))*dz(k);                            // advance.f:495-496
     }
     const bool edge = !(iin && jin) || i == 2 || j == 2;
     for (int k = 1; k <= kbm1; ++k) {
-      double a=nu[k], b=nv[k];
+      // away from the open boundaries the masked tendency is recomputed from uf,vf (one more
+      // read) instead of making the round trip through the per-thread arrays (a write + a read)
+      double a = edge ? nu[k] : uf(i,j,k)*mu, b = edge ? nv[k] : vf(i,j,k)*mv;
       double un=u(i,j,k)+.5*smoth*(a+ub(i,j,k)-2.*u(i,j,k)-su);         // advance.f:483-485
       double vn=v(i,j,k)+.5*smoth*(b+vb(i,j,k)-2.*v(i,j,k)-sv);         // advance.f:504-506
       A3(p.s3a,i,j,k)=un;
