@@ -1543,6 +1543,75 @@ struct FbRoundTripK : KBase {
   }
 };
 
+// ---- domain_stats (advance.f:644-755): per-row partial sums ---------------------------------
+// One block per owned row j; a fixed-shape tree reduction, so the 7 partial sums of a row do not
+// depend on which strip holds it; the caller adds the rows in global order (deterministic and
+// decomposition-invariant).  Per row: atot, eavg*atot, vtot, mtot, tavg*vtot, stot, ekin.
+POM_HD void dstats_point(const KBase& kb_, int i, int j, double* acc) {
+  const Geo& g = kb_.g; const Ptrs& p = kb_.p; const Consts& c = kb_.c;
+  const int im = g.im, jm = g.jmg, imm1 = im - 1, jmm1 = jm - 1, kbm1 = g.kb - 1;
+  const bool jin = (j >= 2 && j <= jmm1), iin = (i >= 2 && i <= imm1);
+  if (!(jin || iin)) return;                                  // the four corners are never counted
+  const double darea=dx(i,j)*dy(i,j)*fsm(i,j);                // :668
+  acc[0]+=darea;                                              // :669-673
+  acc[1]+=et(i,j)*darea;                                      // :675-679
+  if (!(jin && iin)) return;                                  // dvol is zero outside the interior (:693-696)
+  for (int k = 1; k <= kbm1; ++k) {
+    const double dvol=darea*dt(i,j)*dz(k);
+    const double dmass=dvol*(rho(i,j,k)*rhoref+1000.);        // :704-705
+    acc[2]+=dvol;
+    acc[3]+=dmass;
+    acc[4]+=tb(i,j,k)*dvol;                                   // :709
+    acc[5]+=sb(i,j,k)*dvol;                                   // :710
+    acc[6]+=.5*(dmass*(u(i,j,k)*u(i,j,k)+v(i,j,k)*v(i,j,k)));   // :742-744
+  }
+}
+#ifndef POMGPU_EMU
+__global__ void __launch_bounds__(256) dstats_kernel(const KBase kb_, int j0, double* out) {
+  __shared__ double sh[7][256];
+  double acc[7] = {0., 0., 0., 0., 0., 0., 0.};
+  const int j = j0 + blockIdx.x;
+  for (int i = 1 + threadIdx.x; i <= kb_.g.im; i += 256) dstats_point(kb_, i, j, acc);
+  for (int q = 0; q < 7; ++q) sh[q][threadIdx.x] = acc[q];
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w)
+      for (int q = 0; q < 7; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x < 7) out[blockIdx.x * 7 + threadIdx.x] = sh[threadIdx.x][0];
+}
+#endif
+int domain_stats_rows(Ctx* c, double* rows) {
+  const int nrow = c->jown1 - c->jown0 + 1;
+  KBase kb_(c);
+#ifdef POMGPU_EMU
+  for (int r = 0; r < nrow; ++r) {
+    // same tree as the device: 256 strided lanes, then pairwise halving
+    double sh[7][256];
+    for (int t = 0; t < 256; ++t) {
+      double acc[7] = {0., 0., 0., 0., 0., 0., 0.};
+      for (int i = 1 + t; i <= c->g.im; i += 256) dstats_point(kb_, i, c->jown0 + r, acc);
+      for (int q = 0; q < 7; ++q) sh[q][t] = acc[q];
+    }
+    for (int w = 128; w > 0; w >>= 1)
+      for (int t = 0; t < w; ++t)
+        for (int q = 0; q < 7; ++q) sh[q][t] += sh[q][t + w];
+    for (int q = 0; q < 7; ++q) rows[r * 7 + q] = sh[q][0];
+  }
+  return 0;
+#else
+  cudaSetDevice(c->device);
+  double* d = nullptr;
+  if (dev_alloc(c, &d, (size_t)nrow * 7)) return 1;
+  c->launches++;
+  dstats_kernel<<<nrow, 256, 0, (cudaStream_t)c->stream>>>(kb_, c->jown0, d);
+  int rc = dev_d2h(c, rows, d, (size_t)nrow * 7);
+  dev_free(c, d);
+  return rc;
+#endif
+}
+
 #define ALLI 1, c->g.im
 void run_uvadjust(Ctx* c, int j0, int j1) { launch_cols(c, UvAdjustK(c), ALLI, j0, j1); }
 void run_vertvl(Ctx* c, int j0, int j1) { launch_cols(c, VertvlK(c), ALLI, j0, j1); }

@@ -51,6 +51,7 @@ void run_profv(Ctx*, int, int);
 void run_uvfilter(Ctx*, int, int);
 void run_endstep2d(Ctx*, int, int);
 void run_realvertvl(Ctx*, int, int);
+int domain_stats_rows(Ctx* c, double* rows);
 
 // ---- launch windows ---------------------------------------------------------------------
 static inline int WLO(const Ctx* c, int e) { return c->jown0 > 1 ? c->jown0 - e : 1; }
@@ -543,6 +544,7 @@ double pomgpu_check_velocity_lagged(pomgpu_t* p) {
   return prev;
 #endif
 }
+int pomgpu_domain_stats_rows(pomgpu_t* p, double* rows) { apply_pending(X(p)); return domain_stats_rows(X(p), rows); }
 long pomgpu_launch_count(pomgpu_t* p, int reset) {
   long n = X(p)->launches;
   if (reset) X(p)->launches = 0;

@@ -59,6 +59,7 @@ def _bind(path):
     L.pomgpu_check_velocity.restype = C.c_double
     L.pomgpu_check_velocity.argtypes = [P]
     L.pomgpu_push_async.argtypes = [P, C.c_char_p, P]
+    L.pomgpu_domain_stats_rows.argtypes = [P, P]
     L.pomgpu_check_velocity_lagged.restype = C.c_double
     L.pomgpu_check_velocity_lagged.argtypes = [P]
     L.pomgpu_pin_host.argtypes = [P, C.c_ulong]
@@ -226,6 +227,16 @@ class PomGpu:
     def check_velocity(self):
         return self.L.pomgpu_check_velocity(self.h)
 
+    def domain_stats_rows(self):
+        """Per-owned-row partial sums of domain_stats (advance.f:644-755), shape (rows, 7)."""
+        n = self.own[1] - self.own[0] + 1
+        out = np.empty((n, 7), dtype=np.float64)
+        self._ck(self.L.pomgpu_domain_stats_rows(self.h, out.ctypes.data_as(C.c_void_p)), "domain_stats")
+        return out
+
+    def domain_stats(self):
+        return finish_domain_stats(self.domain_stats_rows())
+
     def check_velocity_lagged(self):
         """max|vaf| of the PREVIOUS call's step (0.0 first); never waits for the step just enqueued."""
         return self.L.pomgpu_check_velocity_lagged(self.h)
@@ -262,6 +273,18 @@ class PomGpu:
 
     def proft(self, f, wfsurf, fsurf, nbc):
         self._ck(self.L.pomgpu_proft(self.h, f.encode(), wfsurf.encode(), fsurf.encode(), int(nbc)), "proft")
+
+
+def finish_domain_stats(rows):
+    """Add the per-row partial sums in global row order (sequentially, so the result does not depend
+    on the decomposition) and form vtot, atot, mtot, stot, tavg, savg, eavg, ekin (advance.f:685-739)."""
+    acc = [0.0] * 7
+    for r in rows:
+        for q in range(7):
+            acc[q] += float(r[q])
+    atot, ea, vtot, mtot, ta, stot, ekin = acc
+    return dict(vtot=vtot, atot=atot, mtot=mtot, stot=stot, tavg=ta / vtot if vtot else 0.0,
+                savg=stot / vtot if vtot else 0.0, eavg=ea / atot if atot else 0.0, ekin=ekin)
 
 
 HALO_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_long,
@@ -334,6 +357,9 @@ class PomGroup:
 
     def check_velocity(self):
         return self.L.pomgpu_group_check_velocity(self.h)
+
+    def domain_stats(self):
+        return finish_domain_stats(np.concatenate([s.domain_stats_rows() for s in self.strips], axis=0))
 
     def exchanges(self, reset=False):
         f = C.c_long(0)

@@ -71,6 +71,11 @@ double pomgpu_check_velocity(pomgpu_t* ctx);
 /* the same without waiting for the step just enqueued: starts the reduction and returns the
  * value of the previous call (one step of lag; 0 on the first call) */
 double pomgpu_check_velocity_lagged(pomgpu_t* ctx);
+/* domain_stats (advance.f:644-755) as a device reduction: 7 partial sums for each OWNED row
+ * (rows[owned_rows][7] = atot, sum(et*darea), vtot, mtot, sum(tb*dvol), sum(sb*dvol), ekin);
+ * adding the rows in global order and dividing (eavg/atot, tavg/vtot, savg=stot/vtot) gives
+ * the reference's eight numbers independently of the decomposition. */
+int pomgpu_domain_stats_rows(pomgpu_t* ctx, double* rows);
 long pomgpu_launch_count(pomgpu_t* ctx, int reset);
 /* per-kernel device time from CUDA events recorded on the launch stream around every
  * kernel between begin and end; end writes a JSON array

@@ -52,6 +52,7 @@ def lib():
         L.pomo_get.restype = C.c_double
         L.pomo_get.argtypes = [C.c_void_p, C.c_char_p]
         L.pomo_check_velocity.restype = C.c_double
+        L.pomo_domain_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         for n in ("step lateral_viscosity mode_interaction mode_external mode_internal advave "
                   "advct advu advv baropg profq profu profv vertvl realvertvl "
                   "restore_interior check_velocity").split():
@@ -143,6 +144,12 @@ class Oracle:
 
     def check_velocity(self):
         return self.L.pomo_check_velocity(self.h)
+
+    def domain_stats(self):
+        """advance.f:644-755 -> dict(vtot, atot, mtot, stot, tavg, savg, eavg, ekin)."""
+        out = (C.c_double * 8)()
+        self.L.pomo_domain_stats(self.h, out)
+        return dict(zip("vtot atot mtot stot tavg savg eavg ekin".split(), list(out)))
 
     def lateral_viscosity(self): self.L.pomo_lateral_viscosity(self.h)
     def mode_interaction(self): self.L.pomo_mode_interaction(self.h)

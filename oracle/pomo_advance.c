@@ -311,3 +311,43 @@ double pomo_check_velocity(pomo_t *S) {
   if (vamax > S->vmaxl) S->error_status = 1;
   return vamax;
 }
+
+/* advance.f:644-755 domain_stats for one sub-domain (all neighbours -1).  Fortran's sum() is
+ * restated as a plain sequential sum in array element order (i fastest). out[8] =
+ * vtot, atot, mtot, stot, tavg, savg, eavg, ekin. */
+void pomo_domain_stats(pomo_t *S, double *out) {
+  DIMS;
+  double vtot = 0., atot = 0., mtot = 0., stot = 0., tavg = 0., savg = 0., eavg = 0., ekin = 0.;
+#define DAREA(i, j) (dx(i,j)*dy(i,j)*fsm(i,j))
+#define INREG(i, j) (((i) >= 2 && (i) <= imm1 && (j) >= 2 && (j) <= jmm1) || (((i) == 1 || (i) == im) && (j) >= 2 && (j) <= jmm1) || (((j) == 1 || (j) == jm) && (i) >= 2 && (i) <= imm1))
+  /* :669-680 interior first, then W, E, S, N edges */
+  DO(j, 2, jmm1) DO(i, 2, imm1) atot += DAREA(i,j);
+  DO(j, 2, jmm1) atot += DAREA(1,j);
+  DO(j, 2, jmm1) atot += DAREA(im,j);
+  DO(i, 2, imm1) atot += DAREA(i,1);
+  DO(i, 2, imm1) atot += DAREA(i,jm);
+  DO(j, 2, jmm1) DO(i, 2, imm1) eavg += et(i,j)*DAREA(i,j);
+  DO(j, 2, jmm1) eavg += et(1,j)*DAREA(1,j);
+  DO(j, 2, jmm1) eavg += et(im,j)*DAREA(im,j);
+  DO(i, 2, imm1) eavg += et(i,1)*DAREA(i,1);
+  DO(i, 2, imm1) eavg += et(i,jm)*DAREA(i,jm);
+  eavg = (atot != 0.) ? eavg / atot : 0.;                     /* :685-691 */
+  /* :693-703: dvol is only assigned on the interior (2:imm1,2:jmm1); the edge sums add zeros */
+#define DVOL(i, j, k) (DAREA(i,j)*dt(i,j)*dz(k))
+  DO(k, 1, kbm1) DO(j, 2, jmm1) DO(i, 2, imm1) vtot += DVOL(i,j,k);
+  DO(k, 1, kbm1) DO(j, 2, jmm1) DO(i, 2, imm1) mtot += DVOL(i,j,k)*(rho(i,j,k)*rhoref+1000.);   /* :704-707 */
+  DO(k, 1, kbm1) DO(j, 2, jmm1) DO(i, 2, imm1) tavg += tb(i,j,k)*DVOL(i,j,k);                     /* :709-727 */
+  DO(k, 1, kbm1) DO(j, 2, jmm1) DO(i, 2, imm1) stot += sb(i,j,k)*DVOL(i,j,k);
+  if (vtot != 0.) { tavg = tavg / vtot; savg = stot / vtot; } else { tavg = 0.; savg = 0.; }     /* :731-739 */
+  /* :742-747 (dmass is zero outside the interior, so the E and N edge terms vanish) */
+  DO(k, 1, kbm1) {
+    double sk = 0.;
+    DO(j, 2, jmm1) DO(i, 2, imm1)
+      sk += DVOL(i,j,k)*(rho(i,j,k)*rhoref+1000.)*(u(i,j,k)*u(i,j,k)+v(i,j,k)*v(i,j,k));
+    ekin = ekin + .5*sk;
+  }
+  out[0] = vtot; out[1] = atot; out[2] = mtot; out[3] = stot; out[4] = tavg; out[5] = savg; out[6] = eavg; out[7] = ekin;
+#undef DAREA
+#undef DVOL
+#undef INREG
+}

@@ -197,3 +197,19 @@ def check_restore(factory, dims=(24, 19, 9), nstep=6):
         o2.step(i)
     assert rel_err(o2.get("t")[:, :, :-1], o.get("t")[:, :, :-1]) > 1e-6
     return worst
+
+
+def check_domain_stats(factory, dims=(26, 21, 10), nstep=4):
+    """domain_stats (advance.f:644-755) as a device reduction against the oracle's sequential
+    sums (summation order differs: relative 1e-12), and its physical content: the volume
+    equals sum(dx*dy*dt) over wet interior cells."""
+    st, o, g = pair(factory, dims, island=True)
+    for i in range(1, nstep + 1):
+        o.step(i); g.step(i)
+    a, b = o.domain_stats(), g.domain_stats()
+    for k in a:
+        assert abs(a[k] - b[k]) <= 1e-12 * max(abs(a[k]), 1e-300), (k, a[k], b[k])
+    f = st["fields"]
+    vol = (f["dx"] * f["dy"] * f["fsm"] * g.get("dt"))[1:-1, 1:-1].sum() * f["dz"][:-1].sum()
+    assert abs(vol - b["vtot"]) <= 1e-10 * vol
+    return b

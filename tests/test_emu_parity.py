@@ -43,3 +43,7 @@ def test_unsupported_switches_set_error_status():
 
 def test_restore_interior_matches_oracle():
     pc.check_restore(EmuPom)
+
+
+def test_domain_stats_matches_oracle():
+    pc.check_domain_stats(EmuPom)

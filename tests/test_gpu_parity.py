@@ -147,3 +147,7 @@ def test_async_forcing_push_equals_blocking_push():
 
 def test_restore_interior_matches_oracle():
     pc.check_restore(_factory)
+
+
+def test_domain_stats_matches_oracle():
+    pc.check_domain_stats(_factory)

@@ -65,6 +65,7 @@ def test_strips_equal_single_domain_bitwise(nstrips, ghost):
         grp.step(i)
     _assert_same(whole, grp)
     assert whole.check_velocity() == grp.check_velocity()
+    assert whole.domain_stats() == grp.domain_stats()      # per-row partial sums added in global order
     nex, nfields = grp.exchanges()
     # the reference does 29 3-D + 340 2-D exchanges per step
     print(f"{nstrips} strips ghost {ghost}: {nex / nstep:.1f} batched exchanges/step, {nfields / nstep:.0f} field-rows sets")
