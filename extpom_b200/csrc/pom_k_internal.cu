@@ -503,7 +503,8 @@ struct AdvT2K : KBase {
   }
   const double *fb_[NT], *f_[NT], *fc_[NT];
   double* ff_[NT];
-  AdvT2K(const Ctx* x, const double* fb, const double* f, const double* fc, double* ff) : KBase(x) {
+  bool upw = true;   // false: only the horizontal diffusion of (fb-fclim) is added to ff (:691-726, nitera>1)
+  AdvT2K(const Ctx* x, const double* fb, const double* f, const double* fc, double* ff, bool up = true) : KBase(x), upw(up) {
     fb_[0] = fb; f_[0] = f; fc_[0] = fc; ff_[0] = ff;
   }
   AdvT2K(const Ctx* x) : KBase(x) {   // T -> uf and S -> vf (advance.f:430-431)
@@ -561,8 +562,8 @@ struct AdvT2K : KBase {
     if (!(s.fxa || s.fya || s.interior)) return;
     const double a0=o(AAM,0,0);
     double xm = 0., xd = 0., ym = 0., yd = 0.;
-    if (s.fxa) { xm=s.cx*o(U,0,0); xd=0.5*(a0+o(AAM,-1,0)); }           // :605-606, :696
-    if (s.fya) { ym=s.cy*o(V,0,0); yd=0.5*(a0+o(AAM,0,-1)); }           // :612-613, :697
+    if (s.fxa) { xm=upw ? s.cx*o(U,0,0) : 0.; xd=0.5*(a0+o(AAM,-1,0)); }   // :605-606, :696
+    if (s.fya) { ym=upw ? s.cy*o(V,0,0) : 0.; yd=0.5*(a0+o(AAM,0,-1)); }   // :612-613, :697
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       const double fb0=o(2*t,0,0);
@@ -585,8 +586,16 @@ struct AdvT2K : KBase {
     if (!s.interior) {
       // ff is not assigned here by the reference (bcond(4) sets it afterwards); only the
       // smol_adif mask applies
+      if (upw) {
 #pragma unroll
-      for (int t = 0; t < NT; ++t) A3(ff_[t],i,j,k)=A3(ff_[t],i,j,k)*s.m;
+        for (int t = 0; t < NT; ++t) A3(ff_[t],i,j,k)=A3(ff_[t],i,j,k)*s.m;
+      }
+      return;
+    }
+    if (!upw) {   // diffusion only: ff=ff-dti2*div/((h+etf)*art) (:718-726)
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+        A3(ff_[t],i,j,k)=A3(ff_[t],i,j,k)-s.def(dti2*(tl(4*t+XD,1,0)-tl(4*t+XD,0,0)+tl(4*t+YD,0,1)-tl(4*t+YD,0,0)));
       return;
     }
     const bool more = (k + 1 <= g.kb - 1);
@@ -609,6 +618,7 @@ struct AdvT2K : KBase {
   }
   POM_HD void post(int i, int j, State& s) const {
     const int kb = g.kb;
+    if (!upw) return;
 #pragma unroll
     for (int t = 0; t < NT; ++t) A3(ff_[t],i,j,kb)=A3(ff_[t],i,j,kb)*s.m;   // smol_adif mask, level kb
   }
@@ -732,32 +742,6 @@ struct SmolAdifK : KBase {
         A3(zw_,i,j,k)=r;
       }
     }
-  }
-};
-
-// horizontal diffusion of (fb-fclim) added to the last iterate (:691-726)
-struct AdvT2DiffK : KBase {
-  POM_KINFO("advt2_diff", 4, 1, 8, 0)
-  const double *fb_, *fc_;
-  double* ff_;
-  AdvT2DiffK(const Ctx* x, const double* fb, const double* fc, double* ff) : KBase(x), fb_(fb), fc_(fc), ff_(ff) {}
-  POM_HD double fd(int i, int j, int k) const { return A3(fb_,i,j,k)-A3(fc_,i,j,k); }     // :691
-  POM_HD double xfl(int i, int j, int k) const {
-    const double xd=0.5*(aam(i,j,k)+aam(i-1,j,k));                                        // :696
-    return -xd*(h(i,j)+h(i-1,j))*tprni*(fd(i,j,k)-fd(i-1,j,k))*dum(i,j)
-           *(dy(i,j)+dy(i-1,j))*0.5/(dx(i,j)+dx(i-1,j));                                  // :705-707
-  }
-  POM_HD double yfl(int i, int j, int k) const {
-    const double yd=0.5*(aam(i,j,k)+aam(i,j-1,k));                                        // :697
-    return -yd*(h(i,j)+h(i,j-1))*tprni*(fd(i,j,k)-fd(i,j-1,k))*dvm(i,j)
-           *(dx(i,j)+dx(i,j-1))*0.5/(dy(i,j)+dy(i,j-1));                                  // :708-710
-  }
-  POM_HD void operator()(int i, int j) const {
-    POM_DIMS;
-    if (!(i >= 2 && i <= imm1 && j >= 2 && j <= jmm1)) return;
-    const double hf=(h(i,j)+etf(i,j))*art(i,j);
-    for (int k = 1; k <= kbm1; ++k)
-      A3(ff_,i,j,k)=A3(ff_,i,j,k)-dti2*(xfl(i+1,j,k)-xfl(i,j,k)+yfl(i,j+1,k)-yfl(i,j,k))/hf;   // :721-723
   }
 };
 
@@ -1644,7 +1628,7 @@ void run_smol_adif(Ctx* c, const double* ff, double* xm, double* ym, double* zw,
   launch_cols(c, SmolAdifK(c, ff, xm, ym, zw), ALLI, j0, j1);
 }
 void run_advt2_diff(Ctx* c, const double* fb, const double* fc, double* ff, int j0, int j1) {
-  launch_cols(c, AdvT2DiffK(c, fb, fc, ff), ALLI, j0, j1);
+  launch_tma_tiles(c, AdvT2K<1>(c, fb, fb, fc, ff, false), ALLI, j0, j1);   // the tile kernel's diffusion half
 }
 void run_fb_roundtrip(Ctx* c, double* fb, const double* fc, double* f, int j0, int j1) {
   launch_cols(c, FbRoundTripK(c, fb, fc, f), ALLI, j0, j1);
