@@ -57,7 +57,7 @@ POM_HD void advave_own_fluxes(const Geo& g, int i, int j, const Op& o, double* v
 struct AdvaveK : KBase {
   POM_KINFO("advave", 0, 0, 8, 2)
   using KBase::KBase;
-  static constexpr int NV = 4, HL = 1, HR = 1, HB = 1, HT = 1, TY = 16;
+  static constexpr int NV = 4, HL = 1, HR = 1, HB = 1, HT = 1, TY = 16, MINB = 1;
   static constexpr int NF = 8, NS = 1, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = 18, NK = 1;
   static constexpr bool UP = false;
   enum { FXU, FYU, FXV, FYV };

@@ -8,6 +8,11 @@
 #include "pom_names.h"
 
 #define KMAX 64
+#ifndef POM_TILE_TY
+#define POM_TILE_TY 16
+#define POM_TILE_MINB 1
+#define POM_TILE_NS 4
+#endif
 #ifndef POM_THOMAS_SMEM
 #define POM_THOMAS_SMEM 0
 #endif
@@ -79,8 +84,11 @@ struct VertvlK : KBase {
 struct AdvqK : KBase {
   POM_KINFO("advq", 8, 2, 9, 0)
   using KBase::KBase;
-  static constexpr int NV = 4, HL = 0, HR = 1, HB = 0, HT = 1, TY = 16;
-  static constexpr int NF = 8, NS = 4, OHL = 1, OHR = 0, OHB = 1, OHT = 0, BW = 34, BH = 17, NK = 0;
+  static constexpr int NV = 4, HL = 0, HR = 1, HB = 0, HT = 1, TY = POM_TILE_TY, MINB = POM_TILE_MINB;
+#ifndef POM_NS_ADVQ
+#define POM_NS_ADVQ POM_TILE_NS
+#endif
+  static constexpr int NF = 8, NS = POM_NS_ADVQ, OHL = 1, OHR = 0, OHB = 1, OHT = 0, BW = 34, BH = TY + 1, NK = 0;
   static constexpr bool UP = true;
   enum { Q2, Q2B, Q2L, Q2LB, U, V, AAM, W };
   enum { XA, YA, XB, YB };
@@ -511,9 +519,9 @@ struct AdvT2K : KBase {
     fb_[0] = x->p.tb; f_[0] = x->p.t; fc_[0] = x->p.tclim; ff_[0] = x->p.uf;
     fb_[NT - 1] = x->p.sb; f_[NT - 1] = x->p.s; fc_[NT - 1] = x->p.sclim; ff_[NT - 1] = x->p.vf;
   }
-  static constexpr int NV = 4 * NT, HL = 0, HR = 1, HB = 0, HT = 1, TY = 16;
+  static constexpr int NV = 4 * NT, HL = 0, HR = 1, HB = 0, HT = 1, TY = POM_TILE_TY, MINB = POM_TILE_MINB;
   // operands staged by the TMA: box = thread tile + one column W and one row S (34 x 17)
-  static constexpr int NF = 2 * NT + 4, NS = 4, OHL = 1, OHR = 0, OHB = 1, OHT = 0, BW = 34, BH = 17, NK = 0;
+  static constexpr int NF = 2 * NT + 4, NS = POM_TILE_NS, OHL = 1, OHR = 0, OHB = 1, OHT = 0, BW = 34, BH = TY + 1, NK = 0;
   static constexpr bool UP = true;
   enum { AAM = 2 * NT, U, V, W };     // FB(t) = 2t, FC(t) = 2t+1
   enum { XF, YF, XD, YD };            // + 4t

@@ -23,9 +23,17 @@ namespace pom {
 struct AdvctK : KBase {
   POM_KINFO("advct", 5, 2, 5, 2)
   using KBase::KBase;
-  static constexpr int NV = 6, HL = 1, HR = 1, HB = 1, HT = 1, TY = 16;
+#ifndef POM_TILE_TY
+#define POM_TILE_TY 16
+#define POM_TILE_MINB 1
+#define POM_TILE_NS 4
+#endif
+  static constexpr int NV = 6, HL = 1, HR = 1, HB = 1, HT = 1, TY = POM_TILE_TY, MINB = POM_TILE_MINB;
   // operands staged by the TMA: thread tile + one point all around (36 x 18 box)
-  static constexpr int NF = 5, NS = 4, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = 18, NK = 0;
+#ifndef POM_NS_ADVCT
+#define POM_NS_ADVCT POM_TILE_NS
+#endif
+  static constexpr int NF = 5, NS = POM_NS_ADVCT, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = TY + 2, NK = 0;
   static constexpr bool UP = false;
   enum { U, V, UB, VB, AAM };
   enum { X, Y, XP, YP, CV, CU };

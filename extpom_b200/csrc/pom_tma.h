@@ -49,8 +49,8 @@ struct GlobalOp {
 };
 
 struct Tile2 {
-  const double* s; int tx, ty;
-  POM_HD double operator()(int v, int di, int dj) const { return s[(v * TILE_Y + (ty + dj)) * TILE_X + (tx + di)]; }
+  const double* s; int tx, ty, ny;   // ny = rows of the thread tile (F::TY)
+  POM_HD double operator()(int v, int di, int dj) const { return s[(v * ny + (ty + dj)) * TILE_X + (tx + di)]; }
   POM_HD double operator()(int di, int dj) const { return s[(ty + dj) * TILE_X + (tx + di)]; }
 };
 
@@ -80,6 +80,19 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+// the same load with an L2 evict-first policy: operands that are streamed once should not push
+// the per-thread Thomas coefficients (local memory, re-read by the upward sweep) out of L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
+}
+
 template <class F>
 struct SmemOp {
   const double* cur;   // stage of level k, at this thread's own point
@@ -91,14 +104,14 @@ struct SmemOp {
 };
 
 template <class F>
-__global__ void __launch_bounds__(TILE_X * F::TY, 1)
+__global__ void __launch_bounds__(TILE_X * F::TY, F::MINB)
 tmakernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1, int j0, int j1) {
   constexpr int NF = F::NF, NS = F::NS, NV = F::NV, PL = tma_plane(F::BW, F::BH);
   constexpr int OX = TILE_X - F::HL - F::HR, OY = F::TY - F::HB - F::HT;
   extern __shared__ __align__(128) double pom_tsm[];
   double* ring = pom_tsm;                                  // [NS][NF][PL]
-  double* S = ring + NS * NF * PL;                         // [2][NV][TILE_Y][TILE_X]
-  uint64_t* bar = (uint64_t*)(S + 2 * NV * TILE_Y * TILE_X);   // [NS]
+  double* S = ring + NS * NF * PL;                         // [2][NV][TY][TILE_X]
+  uint64_t* bar = (uint64_t*)(S + 2 * NV * F::TY * TILE_X);   // [NS]
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ti0 = i0 + blockIdx.x * OX - F::HL, tj0 = j0 + blockIdx.y * OY - F::HB;
   const int i = ti0 + tx, j = tj0 + ty;
@@ -143,13 +156,13 @@ tmakernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1
 #pragma unroll
     for (int n = 0; n < NV; ++n) v[n] = 0.;
     if (inside) f.stage(i, j, k, st, op, v);
-    double* Sb = S + buf * NV * TILE_Y * TILE_X;
+    double* Sb = S + buf * NV * F::TY * TILE_X;
 #pragma unroll
-    for (int n = 0; n < NV; ++n) Sb[(n * TILE_Y + ty) * TILE_X + tx] = v[n];
+    for (int n = 0; n < NV; ++n) Sb[(n * F::TY + ty) * TILE_X + tx] = v[n];
     __syncthreads();
     // every thread is past combine(k-1): the stage of level k-1 is free for level k-1+NS
     if (leader && k - 1 >= k0 && k - 1 + NS <= kl1) issue(k - 1 + NS);
-    if (out) f.combine(i, j, k, st, op, Tile2{Sb, tx, ty});
+    if (out) f.combine(i, j, k, st, op, Tile2{Sb, tx, ty, F::TY});
     buf ^= 1;
   }
   if (out) f.post(i, j, st);
@@ -182,11 +195,19 @@ tmacolkernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+#ifdef POM_COL_EVICT_FIRST
+  const uint64_t pol = l2_evict_first_policy();
+#endif
   auto issue = [&](int L) {
     const int s = (L - k0) % NS;
     mbar_expect_tx(&bar[s], (uint32_t)(NF * F::BW * F::BH * sizeof(double)));
 #pragma unroll
-    for (int n = 0; n < NF; ++n) tma_load_3d(ring + (s * NF + n) * PL, &maps.m[n], &bar[s], c0, c1, L - 1);
+    for (int n = 0; n < NF; ++n)
+#ifdef POM_COL_EVICT_FIRST
+      tma_load_3d_hint(ring + (s * NF + n) * PL, &maps.m[n], &bar[s], c0, c1, L - 1, pol);
+#else
+      tma_load_3d(ring + (s * NF + n) * PL, &maps.m[n], &bar[s], c0, c1, L - 1);
+#endif
   };
   if (leader)
     for (int L = k0; L < k0 + NS && L <= kl1; ++L) issue(L);
@@ -228,10 +249,10 @@ colkernel_g(const F f, int i0, int i1, int j0, int j1) {
 
 // the same functor on direct global loads (layouts the TMA cannot address)
 template <class F>
-__global__ void __launch_bounds__(TILE_X * F::TY, 1)
+__global__ void __launch_bounds__(TILE_X * F::TY, F::MINB)
 tilekernel_g(const F f, int i0, int i1, int j0, int j1) {
   constexpr int OX = TILE_X - F::HL - F::HR, OY = F::TY - F::HB - F::HT, NV = F::NV;
-  __shared__ double S[NV * TILE_Y * TILE_X];   // single buffer (static shared memory is capped at 48 kB)
+  __shared__ double S[NV * F::TY * TILE_X];   // single buffer (static shared memory is capped at 48 kB)
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i = i0 + blockIdx.x * OX - F::HL + tx, j = j0 + blockIdx.y * OY - F::HB + ty;
   const bool inside = (i >= 1 && i <= f.g.im && j >= f.g.joff + 1 && j <= f.g.joff + f.g.jml);
@@ -248,9 +269,9 @@ tilekernel_g(const F f, int i0, int i1, int j0, int j1) {
     for (int n = 0; n < NV; ++n) v[n] = 0.;
     if (inside) f.stage(i, j, k, st, op, v);
 #pragma unroll
-    for (int n = 0; n < NV; ++n) S[(n * TILE_Y + ty) * TILE_X + tx] = v[n];
+    for (int n = 0; n < NV; ++n) S[(n * F::TY + ty) * TILE_X + tx] = v[n];
     __syncthreads();
-    if (out) f.combine(i, j, k, st, op, Tile2{S, tx, ty});
+    if (out) f.combine(i, j, k, st, op, Tile2{S, tx, ty, F::TY});
     __syncthreads();
   }
   if (out) f.post(i, j, st);
@@ -283,11 +304,11 @@ inline void launch_tma_tiles(Ctx* c, const F& f, int i0, int i1, int j0, int j1)
           double v[F::NV];
           for (int n = 0; n < F::NV; ++n) v[n] = 0.;
           if (ins[ty][tx]) f.stage(i, j, k, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, k}, v);
-          for (int n = 0; n < F::NV; ++n) S[(n * TILE_Y + ty) * TILE_X + tx] = v[n];
+          for (int n = 0; n < F::NV; ++n) S[(n * F::TY + ty) * TILE_X + tx] = v[n];
         }
         POM_TILE_LOOP {
           POM_TILE_IJ;
-          if (outm[ty][tx]) f.combine(i, j, k, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, k}, Tile2{S, tx, ty});
+          if (outm[ty][tx]) f.combine(i, j, k, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, k}, Tile2{S, tx, ty, F::TY});
         }
       }
       POM_TILE_LOOP {
@@ -310,7 +331,7 @@ inline void launch_tma_tiles(Ctx* c, const F& f, int i0, int i1, int j0, int j1)
     for (int n = 0; n < F::NF && tma_ok; ++n)
       if (tma_encode(c, &maps.m[n], fld[n], F::NK ? F::NK : c->g.kb, F::BW, F::BH)) tma_ok = false;
     if (tma_ok) {
-      constexpr size_t smem = (size_t)(F::NS * F::NF * tma_plane(F::BW, F::BH) + 2 * F::NV * TILE_Y * TILE_X) * sizeof(double) + F::NS * 8;
+      constexpr size_t smem = (size_t)(F::NS * F::NF * tma_plane(F::BW, F::BH) + 2 * F::NV * F::TY * TILE_X) * sizeof(double) + F::NS * 8;
       static bool granted = false;
       if (!granted) {
         cudaFuncSetAttribute(tmakernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -381,10 +402,10 @@ tile3kernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int 
   for (int n = 0; n < NV; ++n) S[(n * TILE_Y + ty) * TILE_X + tx] = v[n];
   __syncthreads();
   double e = 0.;
-  if (bok) e = TMA ? f.phaseB(i, j, st, sop, Tile2{S, tx, ty}, tx >= 1 && ty >= 1) : f.phaseB(i, j, st, gop, Tile2{S, tx, ty}, tx >= 1 && ty >= 1);
+  if (bok) e = TMA ? f.phaseB(i, j, st, sop, Tile2{S, tx, ty, TILE_Y}, tx >= 1 && ty >= 1) : f.phaseB(i, j, st, gop, Tile2{S, tx, ty, TILE_Y}, tx >= 1 && ty >= 1);
   E[ty * TILE_X + tx] = e;
   __syncthreads();
-  if (out) { if (TMA) f.phaseC(i, j, st, sop, Tile2{S, tx, ty}, Tile2{E, tx, ty}); else f.phaseC(i, j, st, gop, Tile2{S, tx, ty}, Tile2{E, tx, ty}); }
+  if (out) { if (TMA) f.phaseC(i, j, st, sop, Tile2{S, tx, ty, TILE_Y}, Tile2{E, tx, ty, TILE_Y}); else f.phaseC(i, j, st, gop, Tile2{S, tx, ty, TILE_Y}, Tile2{E, tx, ty, TILE_Y}); }
 }
 #endif
 
@@ -417,13 +438,13 @@ inline void launch_tile3(Ctx* c, const F& f, int i0, int i1, int j0, int j1) {
         POM_T3_IJ;
         double e = 0.;
         if (tx <= TILE_X - 2 && ty <= F::TY - 2 && ins[ty][tx])
-          e = f.phaseB(i, j, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, 1}, Tile2{S, tx, ty}, tx >= 1 && ty >= 1);
+          e = f.phaseB(i, j, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, 1}, Tile2{S, tx, ty, TILE_Y}, tx >= 1 && ty >= 1);
         E[ty * TILE_X + tx] = e;
       }
       POM_T3_LOOP {
         POM_T3_IJ;
         if (tx >= 1 && tx <= TILE_X - 2 && ty >= 1 && ty <= F::TY - 2 && i <= i1 && j <= j1 && ins[ty][tx])
-          f.phaseC(i, j, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, 1}, Tile2{S, tx, ty}, Tile2{E, tx, ty});
+          f.phaseC(i, j, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, 1}, Tile2{S, tx, ty, TILE_Y}, Tile2{E, tx, ty, TILE_Y});
       }
     }
 #else
