@@ -286,6 +286,28 @@ int ctx_push(Ctx* c, const char* name, const double* host) {
   return dev_h2d(c, *slot, host, field_elems(c, f));
 }
 
+// rows [row0, row0+nrows) (local, 0-based) of a j-dimensioned field from a host array shaped like
+// the field but with nrows rows: lets a driver fill a large strip band by band
+int ctx_push_rows(Ctx* c, const char* name, const double* host, int row0, int nrows) {
+  const FieldInfo* f;
+  double** slot = ctx_slot(c, name, &f);
+  if (!slot) { snprintf(c->err, sizeof(c->err), "unknown field '%s'", name); return 2; }
+  if (row0 < 0 || nrows < 1 || row0 + nrows > c->g.jml) return 2;
+  if (!*slot && dev_alloc(c, slot, field_elems(c, f))) return 1;
+  const int im = c->g.im, jml = c->g.jml, kb = c->g.kb;
+  size_t w, sp, dp, off; int nk;     // row run (doubles), source / destination level pitch, offset, levels
+  switch (f->kind) {
+    case K3D: w = (size_t)im * nrows; sp = w; dp = (size_t)im * jml; off = (size_t)im * row0; nk = kb; break;
+    case K2D: w = (size_t)im * nrows; sp = w; dp = (size_t)im * jml; off = (size_t)im * row0; nk = 1; break;
+    case KBJ: w = nrows; sp = w; dp = jml; off = row0; nk = 1; break;
+    case KBJK: w = nrows; sp = w; dp = jml; off = row0; nk = kb; break;
+    default: return ctx_push(c, name, host);   // no j dimension: the whole array
+  }
+  for (int k = 0; k < nk; ++k)
+    if (dev_h2d(c, *slot + off + (size_t)k * dp, host + (size_t)k * sp, w)) return 1;
+  return 0;
+}
+
 int ctx_pull(Ctx* c, const char* name, double* host) {
   const FieldInfo* f;
   double** slot = ctx_slot(c, name, &f);

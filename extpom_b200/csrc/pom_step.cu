@@ -15,6 +15,7 @@ void ctx_destroy(Ctx* c);
 double** ctx_slot(Ctx* c, const char* name, const FieldInfo** fi);
 int ctx_push(Ctx* c, const char* name, const double* host);
 int ctx_pull(Ctx* c, const char* name, double* host);
+int ctx_push_rows(Ctx* c, const char* name, const double* host, int row0, int nrows);
 int ctx_set_const(Ctx* c, const char* name, double v);
 int ctx_get_const(Ctx* c, const char* name, double* v);
 int prof_report(Ctx* c, char* buf, int n);
@@ -465,6 +466,10 @@ int pomgpu_set_const(pomgpu_t* p, const char* name, double v) { return ctx_set_c
 int pomgpu_get_const(pomgpu_t* p, const char* name, double* v) { return ctx_get_const(X(p), name, v); }
 int pomgpu_push(pomgpu_t* p, const char* name, const double* host) { apply_pending(X(p)); return ctx_push(X(p), name, host); }
 int pomgpu_pull(pomgpu_t* p, const char* name, double* host) { apply_pending(X(p)); return ctx_pull(X(p), name, host); }
+int pomgpu_push_rows(pomgpu_t* p, const char* name, const double* host, int row0, int nrows) {
+  apply_pending(X(p));
+  return ctx_push_rows(X(p), name, host, row0, nrows);
+}
 long pomgpu_field_elems(pomgpu_t* p, const char* name) {
   const FieldInfo* f = find_field(name);
   return f ? (long)field_elems(X(p), f) : 0;

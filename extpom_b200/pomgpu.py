@@ -52,6 +52,7 @@ def _bind(path):
     L.pomgpu_get_const.argtypes = [P, C.c_char_p, C.POINTER(C.c_double)]
     L.pomgpu_push.argtypes = [P, C.c_char_p, P]
     L.pomgpu_pull.argtypes = [P, C.c_char_p, P]
+    L.pomgpu_push_rows.argtypes = [P, C.c_char_p, P, C.c_int, C.c_int]
     L.pomgpu_field_elems.restype = C.c_long
     L.pomgpu_field_elems.argtypes = [P, C.c_char_p]
     L.pomgpu_step.argtypes = [P, C.c_int, C.c_double, C.c_double]
@@ -173,6 +174,22 @@ class PomGpu:
         a = np.asfortranarray(self._rows(name, arr), dtype=np.float64)
         assert a.shape == self.shapes[name], (name, a.shape, self.shapes[name])
         self._ck(self.L.pomgpu_push(self.h, name.encode(), a.ctypes.data_as(C.c_void_p)), f"push({name})")
+
+    def put_rows(self, name, arr, row0):
+        """Local rows row0.. of field `name` from an array holding just those rows."""
+        a = np.asfortranarray(arr, dtype=np.float64)
+        jdim = name in F2D or name in F3D or name in F3D_OPT
+        nrows = a.shape[1] if jdim else (a.shape[0] if (name in BJ or name in BJK) else 0)
+        self._ck(self.L.pomgpu_push_rows(self.h, name.encode(), a.ctypes.data_as(C.c_void_p), int(row0), int(max(nrows, 1))),
+                 f"push_rows({name})")
+
+    def load_rows(self, state, row0):
+        """Like load() for a state generated for a band of this strip's rows (synthetic.make_state(rows=...))."""
+        for k, v in state["consts"].items():
+            self.L.pomgpu_set_const(self.h, k.encode(), float(v))
+        for k, v in state["fields"].items():
+            if k in self.shapes and (k not in F3D_OPT):
+                self.put_rows(k, v, row0)
 
     def get(self, name):
         out = np.empty(self.shapes[name], dtype=np.float64, order="F")

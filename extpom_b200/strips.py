@@ -39,7 +39,21 @@ def make_strip(im, jm_global, kb, own, ghost, factory, **kw):
     it into a solver strip created by factory(im, jm_global, kb, strip=own, ghost=ghost)."""
     whole = own == (1, jm_global)
     g = factory(im, jm_global, kb, strip=None if whole else own, ghost=0 if whole else ghost)
-    st = syn.make_state(im, jm_global, kb, rows=held_rows(jm_global, own, 0 if whole else ghost), **kw)
+    lo, hi = held_rows(jm_global, own, 0 if whole else ghost)
+    band = kw.pop("band", 0)
+    if band and hi - lo + 1 > band:
+        # large strips: generate and push `band` rows at a time (host memory stays ~30 band-sized fields)
+        st = None
+        for b0 in range(lo, hi + 1, band):
+            st = syn.make_state(im, jm_global, kb, rows=(b0, min(b0 + band - 1, hi)), **kw)
+            g.load_rows(st, b0 - lo)
+        for n in ("tbn", "sbn", "tbs", "sbs"):     # rows 1 / jm live in the first / last band only
+            if lo == 1 and n[2] == "s":
+                g.put(n, syn.make_state(im, jm_global, kb, rows=(1, min(band, hi)), **kw)["fields"][n])
+            if hi == jm_global and n[2] == "n":
+                g.put(n, st["fields"][n])
+        return st, g
+    st = syn.make_state(im, jm_global, kb, rows=(lo, hi), **kw)
     assert st["dims"][1] == g.jml, (st["dims"], g.jml)
     g.load(st)
     return st, g
@@ -54,6 +68,7 @@ class StripSet:
 
     @classmethod
     def create(cls, im, jm_global, kb, rank=0, world=1, device=0, dist=None, ghost=GHOST, factory=None, **kw):
+        kw.setdefault("band", 256 if im * kb >= 1024 * 41 else 0)
         """One strip per process (rank of world).  dist = an initialised torch.distributed module
         (NCCL backend on the GPU box) used once, to broadcast the NCCL unique id."""
         factory = factory or (lambda a, b, c, strip=None, ghost=0: PomGpu(a, b, c, device=device, strip=strip, ghost=ghost))

@@ -49,6 +49,9 @@ int pomgpu_get_const(pomgpu_t* ctx, const char* name, double* value);
  * pull: device -> host (output/restart steps, pom/advance.f:35-49). */
 int pomgpu_push(pomgpu_t* ctx, const char* name, const double* host);
 int pomgpu_pull(pomgpu_t* ctx, const char* name, double* host);
+/* local rows [row0, row0+nrows) of a field from a host array with nrows rows (band-wise init of
+ * large strips); fields without a j dimension are pushed whole */
+int pomgpu_push_rows(pomgpu_t* ctx, const char* name, const double* host, int row0, int nrows);
 long pomgpu_field_elems(pomgpu_t* ctx, const char* name); /* 0 if unknown */
 /* enqueue-only push (no host wait) for the per-step forcing; the host buffer should be
  * page-locked (pomgpu_pin_host registers a driver-owned array, e.g. a COMMON block).  The copy

@@ -136,3 +136,18 @@ def test_two_processes_gloo_equal_single_domain(tmp_path):
             a, b = a[:, :, :-1], b[:, :, :-1]
         assert np.array_equal(a, b), n
     assert max(float(p["vamax"]) for p in parts) == whole.check_velocity()
+
+
+def test_bandwise_loading_equals_whole_loading():
+    """pomgpu_push_rows: a strip filled band by band (large grids) holds exactly the same state."""
+    dims = (20, 40, 7)
+    st, a = sp.make_strip(*dims, (1, 40), 0, _factory, island=True)
+    _, b = sp.make_strip(*dims, (1, 40), 0, _factory, island=True, band=7)
+    for n in list(F3[:8]) + ["h", "fsm", "dum", "uab", "wusurf", "tsurf", "cbc", "aru"] + ["tbe", "tbw", "tbn", "tbs", "uabe", "vabn", "els", "z"]:
+        assert np.array_equal(a.get(n), b.get(n)), n
+    for g in (a, b):
+        grp = PomGroup([g]); sp.finish_init_group(None, grp)
+        for i in range(1, 4):
+            grp.step(i)
+    for n in F3 + F2:
+        assert np.array_equal(a.get(n), b.get(n)), n
