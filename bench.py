@@ -260,8 +260,9 @@ def main():
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"seamount {im}x{a.jm}x{kb} per GPU (global {im}x{jm_global}x{kb}), isplit=30, "
-                               "nadv=2 nitera=1 mode=3 (BASELINE configs[1])",
-                   "parallelism": f"j-strips x{world}", "l2": "inputs larger than L2 (11 GB state per GPU)",
+                               "nadv=2 nitera=1 mode=3" + (" (BASELINE configs[1])" if (im, a.jm, kb) == (1024, 1024, 41) else ""),
+                   "parallelism": f"j-strips x{world}",
+                   "l2": f"inputs larger than L2 ({41 * im * a.jm * kb * 8 / 1e9:.0f} GB state per GPU)",
                    "seed": syn.SEED},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
