@@ -122,18 +122,18 @@ struct ExtStepK : KBase {
 #define POM_EXT_TY 16
 #define POM_EXT_MINB 2
 #endif
-  static constexpr int NV = 6, TY = POM_EXT_TY, MINB = POM_EXT_MINB;
+  static constexpr int NV = 7, TY = POM_EXT_TY, MINB = POM_EXT_MINB;
   static constexpr int NF = 13, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = POM_EXT_TY + 2, NK = 1;
   enum { D = OP_D, UA = OP_UA, VA = OP_VA, UAB = OP_UAB, VAB = OP_VAB, AAM2D = OP_AAM2D, DX = OP_DX, DY = OP_DY,
          EL, ELB, H, COR, EATM };
-  enum { FUA, FVA, FXU, FYU, FXV, FYV };
+  enum { FUA, FVA, FXU, FYU, FXV, FYV, CURV };   // CURV: curv2d of the mode=2 block (solver.f:145-152)
   POM_HD void fields(const double** b) const {
     b[D] = p.d; b[UA] = p.ua; b[VA] = p.va; b[UAB] = p.uab; b[VAB] = p.vab; b[AAM2D] = p.aam2d; b[DX] = p.dx;
     b[DY] = p.dy; b[EL] = p.el; b[ELB] = p.elb; b[H] = p.h; b[COR] = p.cor; b[EATM] = p.e_atmos;
   }
-  struct State { double au, av, artc, vflc, fsm0; };
+  struct State { double au, av, artc, vflc, fsm0, wub, wvb; bool m2; };
   POM_HD void pre(int i, int j, bool inside, State& s) const {
-    s.au = 0.; s.av = 0.; s.artc = 1.; s.vflc = 0.; s.fsm0 = 0.;
+    s.au = 0.; s.av = 0.; s.artc = 1.; s.vflc = 0.; s.fsm0 = 0.; s.wub = 0.; s.wvb = 0.; s.m2 = false;
     if (inside) {   // phase B's point-wise operands, in flight while the TMA stages the rest
       const int imm1 = g.im - 1, jmm1 = g.jmg - 1;
       const int ic = i < 2 ? 2 : (i > imm1 ? imm1 : i);
@@ -160,6 +160,10 @@ struct ExtStepK : KBase {
     if (i >= 2) v[FUA]=.25*(d00+o(D,-1,0))*(o(DY,0,0)+o(DY,-1,0))*o(UA,0,0);          // advance.f:213-214
     if (j >= 2 && j - 1 >= jlo) v[FVA]=.25*(d00+o(D,0,-1))*(o(DX,0,0)+o(DX,0,-1))*o(VA,0,0);   // :215-216
     if (do_adv) advave_own_fluxes<FXU>(g, i, j, o, v);       // advave (solver.f:16-121)
+    if (do_adv && c.mode == 2 && i >= 2 && i <= imm1 && j >= 2 && j <= jmm1 && j + 1 <= g.joff + g.jml)
+      v[CURV]=.25*((o(VA,0,1)+o(VA,0,0))*(o(DY,1,0)-o(DY,-1,0))
+                  -(o(UA,1,0)+o(UA,0,0))*(o(DX,0,1)-o(DX,0,-1)))
+              /(o(DX,0,0)*o(DY,0,0));                      // solver.f:145-152
   }
   // elf(i,j) after bcond(1) (bounds_forcing.f:21-39): W,E copies then S,N copies = the value
   // at the index clamped into the interior, times fsm; advua/advva of interior points
@@ -178,6 +182,21 @@ struct ExtStepK : KBase {
       } else {
         s.au=advua(i,j); s.av=advva(i,j);
       }
+      if (do_adv && c.mode == 2) {
+        // mode 2 (solver.f:123-195): bottom stress from the 2-D velocities, curvature terms
+        s.m2 = true;
+        const double d00=o(D,0,0), uab00=o(UAB,0,0), vab00=o(VAB,0,0);
+        const double qv=.25*(vab00+o(VAB,0,1)+o(VAB,-1,0)+o(VAB,-1,1));
+        s.wub=-0.5*(cbc(i,j)+cbc(i-1,j))*sqrt(uab00*uab00+qv*qv)*uab00;          // :125-133
+        const double qu=.25*(uab00+o(UAB,1,0)+o(UAB,0,-1)+o(UAB,1,-1));
+        s.wvb=-0.5*(cbc(i,j)+cbc(i,j-1))*sqrt(vab00*vab00+qu*qu)*vab00;          // :135-143
+        if (i >= 3)                                                               // :155-172 (n_west==-1)
+          s.au=s.au-aru(i,j)*.25*(S(CURV,0,0)*d00*(o(VA,0,1)+o(VA,0,0))
+                                  +S(CURV,-1,0)*o(D,-1,0)*(o(VA,-1,1)+o(VA,-1,0)));
+        if (j >= 3)                                                               // :174-191 (n_south==-1)
+          s.av=s.av+arv(i,j)*.25*(S(CURV,0,0)*d00*(o(UA,1,0)+o(UA,0,0))
+                                  +S(CURV,0,-1)*o(D,0,-1)*(o(UA,1,-1)+o(UA,0,-1)));
+      }
     }
     return ef*s.fsm0;
   }
@@ -188,14 +207,16 @@ struct ExtStepK : KBase {
     // every point-wise operand is loaded up front (before the first store), so that the
     // loads are in flight together instead of one L2 round trip after the other
     const double aru0=POM_LDG(&aru(i,j)), arv0=POM_LDG(&arv(i,j)), adx0=POM_LDG(&adx2d(i,j)), ady0=POM_LDG(&ady2d(i,j));
-    const double drx0=POM_LDG(&drx2d(i,j)), dry0=POM_LDG(&dry2d(i,j)), wus0=POM_LDG(&wusurf(i,j)), wub0=POM_LDG(&wubot(i,j));
-    const double wvs0=POM_LDG(&wvsurf(i,j)), wvb0=POM_LDG(&wvbot(i,j)), dum0=POM_LDG(&dum(i,j)), dvm0=POM_LDG(&dvm(i,j));
+    const double drx0=POM_LDG(&drx2d(i,j)), dry0=POM_LDG(&dry2d(i,j)), wus0=POM_LDG(&wusurf(i,j));
+    const double wub0=s.m2 ? s.wub : wubot(i,j), wvb0=s.m2 ? s.wvb : wvbot(i,j);
+    const double wvs0=POM_LDG(&wvsurf(i,j)), dum0=POM_LDG(&dum(i,j)), dvm0=POM_LDG(&dvm(i,j));
     const double egf0=egf(i,j), utf0=utf(i,j), vtf0=vtf(i,j);
     const double etf0=(iext >= c.isplit-1) ? etf(i,j) : 0.;
     const double ef=E(0,0);
     const double d00=o(D,0,0), el00=o(EL,0,0), elb00=o(ELB,0,0), h00=o(H,0,0), ua00=o(UA,0,0), va00=o(VA,0,0);
     elf(i,j)=ef;
     if (do_adv) { advua(i,j)=s.au; advva(i,j)=s.av; }
+    if (s.m2) { wubot(i,j)=s.wub; wvbot(i,j)=s.wvb; }
     double un, vn;
     // ---- uaf(i,j) after bcond(2); cells never assigned keep uaf's content ----
     if (jin) {

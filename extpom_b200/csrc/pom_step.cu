@@ -97,7 +97,7 @@ static int check_switches(Group* G) {
   Ctx* c = G->c[0];
   const Consts& k = c->c;
   const char* bad = nullptr;
-  if (k.mode != 3 && k.mode != 4) bad = "mode (3 or 4 supported)";
+  if (k.mode != 2 && k.mode != 3 && k.mode != 4) bad = "mode (2, 3 or 4)";
   else if (k.npg != 1) bad = "npg";
   else if (k.nadv != 1 && k.nadv != 2) bad = "nadv";
   else if (k.nadv == 2 && k.nitera < 1) bad = "nitera";
@@ -157,6 +157,7 @@ static void k_ext_step(Group* G, int iext, int do_adv) {
   EACH(run_ext_step(c, iext, do_adv, j0, j1));
   MADE(e, F_elf, F_uaf, F_vaf, F_s2a, F_s2b, F_el2, F_d2, F_ua, F_va);
   if (do_adv) MADE(e, F_advua, F_advva);
+  if (do_adv && G->c[0]->c.mode == 2) MADE(e, F_wubot, F_wvbot);
   if (iext >= isplit - 2) MADE(e, F_etf);
   if (iext != isplit) MADE(e, F_egf, F_utf, F_vtf);
   // time rotation (advance.f:324-330)

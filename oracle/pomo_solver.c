@@ -13,8 +13,8 @@ static void zero3(pomo_t *S, double *a) { memset(a, 0, sizeof(double) * (size_t)
 static void zero2(pomo_t *S, double *a) { memset(a, 0, sizeof(double) * (size_t)S->im * S->jm); }
 
 /* ------------------------------------------------------------------ */
-/* solver.f:6-198 advave (mode=3 branch; the mode=2 block :123-195 is a
- * "next" row) */
+/* solver.f:6-198 advave, including the mode=2 block :123-195 (bottom stress from the 2-D
+ * velocities and the curvature terms; curv2d lives in the scratch array scr2[1]) */
 void pomo_advave(pomo_t *S) {
   DIMS;
   /* :16-18 */
@@ -79,6 +79,46 @@ void pomo_advave(pomo_t *S) {
   DO(j, 2, jmm1) DO(i, 2, imm1)
     advva(i,j)=fluxua(i+1,j)-fluxua(i,j)
                +fluxva(i,j)-fluxva(i,j-1);
+  if (S->mode == 2) {
+    double *curv2dp = S->scr2[1];
+#define curv2d(i, j) (curv2dp[I2(i, j)])
+    zero2(S, curv2dp);                    /* COMMON curv2d: zero outside the interior */
+    /* :125-133 */
+    DO(j, 2, jmm1) DO(i, 2, imm1) {
+      double q=.25*(vab(i,j)+vab(i,j+1)+vab(i-1,j)+vab(i-1,j+1));
+      wubot(i,j)=-0.5*(cbc(i,j)+cbc(i-1,j))
+                 *sqrt(uab(i,j)*uab(i,j)+q*q)
+                 *uab(i,j);
+    }
+    /* :135-143 */
+    DO(j, 2, jmm1) DO(i, 2, imm1) {
+      double q=.25*(uab(i,j)+uab(i+1,j)+uab(i,j-1)+uab(i+1,j-1));
+      wvbot(i,j)=-0.5*(cbc(i,j)+cbc(i,j-1))
+                 *sqrt(vab(i,j)*vab(i,j)+q*q)
+                 *vab(i,j);
+    }
+    /* :145-152 */
+    DO(j, 2, jmm1) DO(i, 2, imm1)
+      curv2d(i,j)=.25
+                  *((va(i,j+1)+va(i,j))*(dy(i+1,j)-dy(i-1,j))
+                   -(ua(i+1,j)+ua(i,j))*(dx(i,j+1)-dx(i,j-1)))
+                  /(dx(i,j)*dy(i,j));
+    /* :155-172 (n_west == -1) */
+    DO(j, 2, jmm1) DO(i, 3, imm1)
+      advua(i,j)=advua(i,j)-aru(i,j)*.25
+                 *(curv2d(i,j)*d(i,j)
+                   *(va(i,j+1)+va(i,j))
+                   +curv2d(i-1,j)*d(i-1,j)
+                   *(va(i-1,j+1)+va(i-1,j)));
+    /* :174-191 (n_south == -1) */
+    DO(i, 2, imm1) DO(j, 3, jmm1)
+      advva(i,j)=advva(i,j)+arv(i,j)*.25
+                 *(curv2d(i,j)*d(i,j)
+                   *(ua(i+1,j)+ua(i,j))
+                   +curv2d(i,j-1)*d(i,j-1)
+                   *(ua(i+1,j-1)+ua(i,j-1)));
+#undef curv2d
+  }
 }
 
 /* ------------------------------------------------------------------ */

@@ -23,6 +23,7 @@ STEP_CASES = [
     ((24, 19, 9), 6, {"nbct": 3, "nbcs": 3}),
     ((24, 19, 9), 6, {"nbct": 4, "ntp": 3}),
     ((24, 19, 9), 6, {"mode": 4}),
+    ((24, 19, 9), 6, {"mode": 2, "island": True}),            # 2-D only: advave's mode=2 block (solver.f:123-195)
     ((33, 6, 6), 5, {}),          # minimum-width channel
     ((6, 33, 7), 5, {}),
     ((21, 18, 8), 6, {"isplit": 5, "dte": 6.0}),
