@@ -185,6 +185,79 @@ struct BaropgK : KBase {
   }
 };
 
+// baropg_mcc (solver.f:943-1159, npg=2): 4th-order McCalpin pressure gradient.  Same outputs and
+// side effects as BaropgK; reads rho-rmean and d two cells away (the order2d/3d_mpi width-2 halo
+// of the reference = ghost rows here).  Single-precision literals (1./24.), (1./16.) kept.
+struct BaropgMccK : KBase {
+  POM_KINFO("baropg_mcc", 2, 3, 6, 2)
+  using KBase::KBase;
+  POM_HD double rr(int i, int j, int k) const { return rho(i,j,k)-rmean(i,j,k); }   // :954
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    const double c24 = (double)(1.f / 24.f), c16 = (double)(1.f / 16.f);
+    const bool interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
+    double sx = 0., sy = 0.;
+    if (interior) {
+      const bool cx = (i >= 3), cy = (j >= 3);            // n_west == -1 / n_south == -1 ranges (:982,:1080)
+      const double mu=dum(i,j), mv=dvm(i,j);
+      const double muE=dum(i+1,j), muW=dum(i-1,j), mvN=dvm(i,j+1), mvS=dvm(i,j-1);
+      double ddxx=(d(i,j)-d(i-1,j))*mu, d4x=.5*(d(i,j)+d(i-1,j))*mu;                  // :976-977
+      double ddxy=(d(i,j)-d(i,j-1))*mv, d4y=.5*(d(i,j)+d(i,j-1))*mv;                  // :1074-1075
+      if (cx) {                                                                       // :994-1001
+        ddxx=ddxx-c24*(muE*(d(i+1,j)-d(i,j))-2*(d(i,j)-d(i-1,j))+muW*(d(i-1,j)-d(i-2,j)));
+        d4x=d4x+c16*(muE*(d(i,j)-d(i+1,j))+muW*(d(i-1,j)-d(i-2,j)));
+      }
+      if (cy) {                                                                       // :1092-1099
+        ddxy=ddxy-c24*(mvN*(d(i,j+1)-d(i,j))-2*(d(i,j)-d(i,j-1))+mvS*(d(i,j-1)-d(i,j-2)));
+        d4y=d4y+c16*(mvN*(d(i,j)-d(i,j+1))+mvS*(d(i,j-1)-d(i,j-2)));
+      }
+      const double dtx=dt(i,j)+dt(i-1,j), dty=dt(i,j)+dt(i,j-1);
+      const double dyx=dy(i,j)+dy(i-1,j), dxy=dx(i,j)+dx(i,j-1);
+      double px = 0., py = 0., drxm = 0., rhxm = 0., drym = 0., rhym = 0.;
+      for (int k = 1; k <= kbm1; ++k) {
+        const double r0=rr(i,j,k), rW=rr(i-1,j,k), rS=rr(i,j-1,k);
+        double drx=(r0-rW)*mu, rhx=0.5*(r0+rW)*mu;                                     // :972-973
+        double dry=(r0-rS)*mv, rhy=.5*(r0+rS)*mv;                                      // :1070-1071
+        if (cx) {                                                                     // :985-992
+          const double rE=rr(i+1,j,k), rWW=rr(i-2,j,k);
+          drx=drx-c24*(muE*(rE-r0)-2*(r0-rW)+muW*(rW-rWW));
+          rhx=rhx+c16*(muE*(r0-rE)+muW*(rW-rWW));
+        }
+        if (cy) {                                                                     // :1083-1090
+          const double rN=rr(i,j+1,k), rSS=rr(i,j-2,k);
+          dry=dry-c24*(mvN*(rN-r0)-2*(r0-rS)+mvS*(rS-rSS));
+          rhy=rhy+c16*(mvN*(r0-rN)+mvS*(rS-rSS));
+        }
+        if (k == 1) {
+          px=grav*(-zz(1))*d4x*drx;                                                   // :1031
+          py=grav*(-zz(1))*d4y*dry;                                                   // :1129
+        } else {
+          px=px+grav*0.5*dzz(k-1)*d4x*(drxm+drx)+grav*0.5*(zz(k-1)+zz(k))*ddxx*(rhx-rhxm);   // :1038-1042
+          py=py+grav*0.5*dzz(k-1)*d4y*(drym+dry)+grav*0.5*(zz(k-1)+zz(k))*ddxy*(rhy-rhym);   // :1136-1140
+        }
+        drxm=drx; rhxm=rhx; drym=dry; rhym=rhy;
+        const double ox=ramp*(.25*dtx*px*mu*dyx);                                     // :1050-1052,1160
+        const double oy=ramp*(.25*dty*py*mv*dxy);                                     // :1148-1150,1161
+        drhox(i,j,k)=ox;
+        drhoy(i,j,k)=oy;
+        sx=sx+ox*dz(k);                                                               // advance.f:163-164
+        sy=sy+oy*dz(k);
+      }
+      drhox(i,j,kb)=ramp*drhox(i,j,kb);
+      drhoy(i,j,kb)=ramp*drhoy(i,j,kb);
+    } else {
+      for (int k = 1; k <= kbm1; ++k) {  // edges keep their content (initialize.f:307-308)
+        sx=sx+drhox(i,j,k)*dz(k);
+        sy=sy+drhoy(i,j,k)*dz(k);
+      }
+    }
+    drx2d(i,j)=sx;
+    dry2d(i,j)=sy;
+    for (int k = 1; k <= kb; ++k)
+      rho2(i,j,k)=(rho(i,j,k)-rmean(i,j,k))+rmean(i,j,k);                             // :954,1166
+  }
+};
+
 // advance.f:122-136 + aam2d (advance.f:165)
 struct SmagK : KBase {
   POM_KINFO("smagorinsky", 2, 1, 2, 1)
@@ -219,6 +292,7 @@ struct SmagK : KBase {
 void run_advct(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvctK(c), 1, c->g.im, j0, j1); }
 // the caller swaps rho <-> rho2 afterwards
 void run_baropg(Ctx* c, int j0, int j1) { launch_cols(c, BaropgK(c), 1, c->g.im, j0, j1); }
+void run_baropg_mcc(Ctx* c, int j0, int j1) { launch_cols(c, BaropgMccK(c), 1, c->g.im, j0, j1); }
 void run_smag(Ctx* c, int j0, int j1) { launch_cols(c, SmagK(c), 1, c->g.im, j0, j1); }
 
 }  // namespace pom

@@ -22,6 +22,7 @@ int prof_report(Ctx* c, char* buf, int n);
 // kernels
 void run_advct(Ctx*, int, int);
 void run_baropg(Ctx*, int, int);
+void run_baropg_mcc(Ctx*, int, int);
 void run_smag(Ctx*, int, int);
 void run_advave(Ctx*, int, int);
 void run_mode_inter_tail(Ctx*, int, int);
@@ -98,7 +99,7 @@ static int check_switches(Group* G) {
   const Consts& k = c->c;
   const char* bad = nullptr;
   if (k.mode != 2 && k.mode != 3 && k.mode != 4) bad = "mode (2, 3 or 4)";
-  else if (k.npg != 1) bad = "npg";
+  else if (k.npg != 1 && k.npg != 2) bad = "npg";
   else if (k.nadv != 1 && k.nadv != 2) bad = "nadv";
   else if (k.nadv == 2 && k.nitera < 1) bad = "nitera";
   else if (k.isplit < 3) bad = "isplit";
@@ -123,10 +124,11 @@ static void k_advct(Group* G) {
   EACH(run_advct(c, j0, j1));
   MADE(e, F_advx, F_advy, F_adx2d, F_ady2d);
 }
-static void k_baropg(Group* G) {
+static void k_baropg(Group* G, int npg) {
   // (drhox/drhoy/aam/w are also read in place on the i=1,im columns, whose values never change)
-  int e = NEED({F_rho, 1}, {F_dt, 1});
-  EACH(run_baropg(c, j0, j1));
+  // npg=2: baropg_mcc reads rho-rmean and d two rows away (order2d/3d_mpi in the reference)
+  int e = (npg == 2) ? NEED({F_rho, 2}, {F_d, 2}, {F_dt, 1}) : NEED({F_rho, 1}, {F_dt, 1});
+  if (npg == 2) { EACH(run_baropg_mcc(c, j0, j1)); } else { EACH(run_baropg(c, j0, j1)); }
   MADE(e, F_drhox, F_drhoy, F_drx2d, F_dry2d, F_rho2);
   group_swap(G, F_rho, F_rho2);   // rho <- (rho-rmean)+rmean (solver.f:854,937)
 }
@@ -318,7 +320,7 @@ static void k_realvertvl(Group* G) {
 
 // ---- advance.f:96-141 ---------------------------------------------------------------------
 static int lateral_viscosity(Group* G) {
-  if (G->c[0]->c.mode != 2) { k_advct(G); k_baropg(G); k_smag(G); }
+  if (G->c[0]->c.mode != 2) { k_advct(G); k_baropg(G, G->c[0]->c.npg); k_smag(G); }
   return 0;
 }
 // advance.f:144-202 (the vertical integrals were accumulated by the producers)
@@ -617,7 +619,7 @@ int pomgpu_group_dens(pomgpu_group_t* g, const char* si, const char* ti, const c
   k_dens(GG(g), a, b, o);
   return 0;
 }
-int pomgpu_group_baropg(pomgpu_group_t* g) { apply_pending(GG(g)); k_baropg(GG(g)); return 0; }
+int pomgpu_group_baropg(pomgpu_group_t* g) { apply_pending(GG(g)); k_baropg(GG(g), GG(g)->c[0]->c.npg); return 0; }
 
 // ---- the reference's subroutines on the resident state ----------------------------------------
 #define SG Group* G = self_group(X(p)); apply_pending(G)
@@ -631,7 +633,8 @@ int pomgpu_advct(pomgpu_t* p) { SG; k_advct(G); return 0; }
 int pomgpu_advq(pomgpu_t* p) { SG; k_advq(G); return 0; }
 int pomgpu_advu(pomgpu_t* p) { SG; k_advu(G); return 0; }
 int pomgpu_advv(pomgpu_t* p) { SG; k_advv(G); return 0; }
-int pomgpu_baropg(pomgpu_t* p) { SG; k_baropg(G); return 0; }
+int pomgpu_baropg(pomgpu_t* p) { SG; k_baropg(G, 1); return 0; }
+int pomgpu_baropg_mcc(pomgpu_t* p) { SG; k_baropg(G, 2); return 0; }
 int pomgpu_profq(pomgpu_t* p) { SG; k_profq(G, 0); return 0; }
 int pomgpu_profu(pomgpu_t* p) { SG; k_profu(G); return 0; }
 int pomgpu_profv(pomgpu_t* p) { SG; k_profv(G); return 0; }

@@ -72,7 +72,7 @@ def _bind(path):
     L.pomgpu_profile_end.argtypes = [P, C.c_char_p, C.c_int]
     L.pomgpu_launch_count.restype = C.c_long
     L.pomgpu_launch_count.argtypes = [P, C.c_int]
-    for n in ("lateral_viscosity mode_interaction advave advct advq advu advv baropg profq profu "
+    for n in ("lateral_viscosity mode_interaction advave advct advq advu advv baropg baropg_mcc profq profu "
               "profv vertvl realvertvl").split():
         getattr(L, "pomgpu_" + n).argtypes = [P]
     L.pomgpu_mode_external.argtypes = [P, C.c_int]
@@ -273,6 +273,7 @@ class PomGpu:
     def advu(self): self._ck(self.L.pomgpu_advu(self.h), "advu")
     def advv(self): self._ck(self.L.pomgpu_advv(self.h), "advv")
     def baropg(self): self._ck(self.L.pomgpu_baropg(self.h), "baropg")
+    def baropg_mcc(self): self._ck(self.L.pomgpu_baropg_mcc(self.h), "baropg_mcc")
     def profq(self): self._ck(self.L.pomgpu_profq(self.h), "profq")
     def profu(self): self._ck(self.L.pomgpu_profu(self.h), "profu")
     def profv(self): self._ck(self.L.pomgpu_profv(self.h), "profv")

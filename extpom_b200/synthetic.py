@@ -210,7 +210,10 @@ def finish_init(state, solver):
     f = state["fields"]
     solver.dens("sclim", "tclim", "rmean")
     solver.dens("sb", "tb", "rho")
-    solver.baropg()
+    if int(state["consts"].get("npg", 1)) == 2:      # initialize.f:502-505
+        solver.baropg_mcc()
+    else:
+        solver.baropg()
     dz = f["dz"]
     for n in ("rmean", "rho", "drhox", "drhoy"):
         f[n] = solver.get(n)

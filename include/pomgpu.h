@@ -108,7 +108,7 @@ void pomgpu_group_set_transport(pomgpu_group_t* g, pomgpu_halo_cb cb, void* user
 int pomgpu_group_step(pomgpu_group_t* g, int iint, double time, double ramp);
 /* the two solver.f routines `initialize` calls (initialize.f:416,425,502), on a group */
 int pomgpu_group_dens(pomgpu_group_t* g, const char* si, const char* ti, const char* rhoo);
-int pomgpu_group_baropg(pomgpu_group_t* g);
+int pomgpu_group_baropg(pomgpu_group_t* g);   /* baropg or baropg_mcc by npg (initialize.f:502-505) */
 double pomgpu_group_check_velocity(pomgpu_group_t* g); /* max over this process's strips */
 long pomgpu_group_exchanges(pomgpu_group_t* g, long* fields, int reset); /* halo messages so far */
 
@@ -132,6 +132,7 @@ int pomgpu_advt2(pomgpu_t* ctx, const char* fb, const char* f, const char* fclim
 int pomgpu_advu(pomgpu_t* ctx);                    /* solver.f:734  */
 int pomgpu_advv(pomgpu_t* ctx);                    /* solver.f:791  */
 int pomgpu_baropg(pomgpu_t* ctx);                  /* solver.f:848  */
+int pomgpu_baropg_mcc(pomgpu_t* ctx);              /* solver.f:943 (npg=2) */
 int pomgpu_dens(pomgpu_t* ctx, const char* si, const char* ti, const char* rhoo); /* solver.f:1162 */
 int pomgpu_profq(pomgpu_t* ctx);                   /* solver.f:1212 */
 int pomgpu_proft(pomgpu_t* ctx, const char* f, const char* wfsurf, const char* fsurf, int nbc); /* :1541 */

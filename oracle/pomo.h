@@ -97,6 +97,7 @@ void pomo_mode_external(pomo_t *S);
 void pomo_mode_internal(pomo_t *S);
 void pomo_internal_stage(pomo_t *S, int stage); /* blocks of advance.f:356-537 */
 double pomo_check_velocity(pomo_t *S); /* advance.f:611-641, returns vamax */
+void pomo_baropg_mcc(pomo_t *S);   /* solver.f:943-1159 (npg=2) */
 void pomo_domain_stats(pomo_t *S, double *out8); /* advance.f:644-755: vtot atot mtot stot tavg savg eavg ekin */
 /* solver.f */
 void pomo_advave(pomo_t *S);

@@ -54,7 +54,7 @@ def lib():
         L.pomo_check_velocity.restype = C.c_double
         L.pomo_domain_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         for n in ("step lateral_viscosity mode_interaction mode_external mode_internal advave "
-                  "advct advu advv baropg profq profu profv vertvl realvertvl "
+                  "advct advu advv baropg baropg_mcc profq profu profv vertvl realvertvl "
                   "restore_interior check_velocity").split():
             getattr(L, "pomo_" + n).argtypes = [C.c_void_p]
         P = C.c_void_p
@@ -151,6 +151,7 @@ class Oracle:
         self.L.pomo_domain_stats(self.h, out)
         return dict(zip("vtot atot mtot stot tavg savg eavg ekin".split(), list(out)))
 
+    def baropg_mcc(self): self.L.pomo_baropg_mcc(self.h)
     def lateral_viscosity(self): self.L.pomo_lateral_viscosity(self.h)
     def mode_interaction(self): self.L.pomo_mode_interaction(self.h)
     def mode_external(self, iext):

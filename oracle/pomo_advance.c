@@ -15,8 +15,9 @@ void pomo_lateral_viscosity(pomo_t *S) {
     pomo_advct(S);
     if (S->npg == 1) {
       pomo_baropg(S);
+    } else if (S->npg == 2) {
+      pomo_baropg_mcc(S);
     } else {
-      /* npg=2 (baropg_mcc) is a "next" row */
       S->error_status = 1;
       fprintf(stderr, "\nError: invalid value for npg\n");
     }

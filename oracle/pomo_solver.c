@@ -693,6 +693,116 @@ void pomo_baropg(pomo_t *S) {
 }
 
 /* ------------------------------------------------------------------ */
+/* solver.f:943-1159 baropg_mcc: 4th-order (McCalpin) pressure gradient, one sub-domain
+ * (n_west == n_south == -1, so rho4th/d4th of order2d/3d_mpi are never read).  Note the
+ * single-precision literals (1./24.), (1./24), (1./16.), 0.5 and that d (not dt) is used. */
+void pomo_baropg_mcc(pomo_t *S) {
+  DIMS;
+  double *d4p = S->scr2[1], *ddxp = S->scr2[2], *drhop = S->scr3[0], *rhoup = S->scr3[1];
+#define d4(i, j) (d4p[I2(i, j)])
+#define ddx(i, j) (ddxp[I2(i, j)])
+#define drho(i, j, k) (drhop[I3(i, j, k)])
+#define rhou(i, j, k) (rhoup[I3(i, j, k)])
+  const double c24 = (double)(1.f / 24.f), c16 = (double)(1.f / 16.f);
+  for (size_t n = 0; n < N3; ++n) S->rho[n] = S->rho[n] - S->rmean[n];
+  zero2(S, ddxp); zero2(S, d4p); zero3(S, rhoup); zero3(S, drhop);
+  /* :970-980 */
+  DO(j, 1, jm) DO(i, 2, im) {
+    DO(k, 1, kbm1) {
+      drho(i,j,k)=(rho(i,j,k)-rho(i-1,j,k))*dum(i,j);
+      rhou(i,j,k)=0.5*(rho(i,j,k)+rho(i-1,j,k))*dum(i,j);
+    }
+    ddx(i,j)=(d(i,j)-d(i-1,j))*dum(i,j);
+    d4(i,j)=.5*(d(i,j)+d(i-1,j))*dum(i,j);
+  }
+  /* :982-1003 (n_west == -1) */
+  DO(j, 1, jm) DO(i, 3, imm1) {
+    DO(k, 1, kbm1) {
+      drho(i,j,k)=drho(i,j,k) - c24*
+                  (dum(i+1,j)*(rho(i+1,j,k)-rho(i,j,k))-
+                  2*(rho(i,j,k)-rho(i-1,j,k))+
+                  dum(i-1,j)*(rho(i-1,j,k)-rho(i-2,j,k)));
+      rhou(i,j,k)=rhou(i,j,k) + c16*
+                  (dum(i+1,j)*(rho(i,j,k)-rho(i+1,j,k))+
+                  dum(i-1,j)*(rho(i-1,j,k)-rho(i-2,j,k)));
+    }
+    ddx(i,j)=ddx(i,j)-c24*
+             (dum(i+1,j)*(d(i+1,j)-d(i,j))-
+             2*(d(i,j)-d(i-1,j))+
+             dum(i-1,j)*(d(i-1,j)-d(i-2,j)));
+    d4(i,j)=d4(i,j)+c16*
+            (dum(i+1,j)*(d(i,j)-d(i+1,j))+
+            dum(i-1,j)*(d(i-1,j)-d(i-2,j)));
+  }
+  /* :1029-1057 */
+  DO(j, 2, jmm1) DO(i, 2, imm1)
+    drhox(i,j,1)=grav*(-zz(1))*d4(i,j)*drho(i,j,1);
+  DO(k, 2, kbm1) DO(j, 2, jmm1) DO(i, 2, imm1)
+    drhox(i,j,k)=drhox(i,j,k-1)
+                 +grav*0.5*dzz(k-1)*d4(i,j)
+                 *(drho(i,j,k-1)+drho(i,j,k))
+                 +grav*0.5*(zz(k-1)+zz(k))*ddx(i,j)
+                 *(rhou(i,j,k)-rhou(i,j,k-1));
+  DO(k, 1, kbm1) DO(j, 2, jmm1) DO(i, 2, imm1)
+    drhox(i,j,k)=.25*(dt(i,j)+dt(i-1,j))
+                      *drhox(i,j,k)*dum(i,j)
+                      *(dy(i,j)+dy(i-1,j));
+  /* :1062-1065 */
+  zero2(S, ddxp); zero2(S, d4p); zero3(S, rhoup); zero3(S, drhop);
+  /* :1068-1078 */
+  DO(j, 2, jm) DO(i, 1, im) {
+    DO(k, 1, kbm1) {
+      drho(i,j,k)=(rho(i,j,k)-rho(i,j-1,k))*dvm(i,j);
+      rhou(i,j,k)=.5*(rho(i,j,k)+rho(i,j-1,k))*dvm(i,j);
+    }
+    ddx(i,j)=(d(i,j)-d(i,j-1))*dvm(i,j);
+    d4(i,j)=.5*(d(i,j)+d(i,j-1))*dvm(i,j);
+  }
+  /* :1080-1101 (n_south == -1) */
+  DO(j, 3, jmm1) DO(i, 1, im) {
+    DO(k, 1, kbm1) {
+      drho(i,j,k)=drho(i,j,k)-c24*
+                  (dvm(i,j+1)*(rho(i,j+1,k)-rho(i,j,k))-
+                  2*(rho(i,j,k)-rho(i,j-1,k))+
+                  dvm(i,j-1)*(rho(i,j-1,k)-rho(i,j-2,k)));
+      rhou(i,j,k)=rhou(i,j,k)+c16*
+                  (dvm(i,j+1)*(rho(i,j,k)-rho(i,j+1,k))+
+                  dvm(i,j-1)*(rho(i,j-1,k)-rho(i,j-2,k)));
+    }
+    ddx(i,j)=ddx(i,j)-c24*
+             (dvm(i,j+1)*(d(i,j+1)-d(i,j))-
+             2*(d(i,j)-d(i,j-1))+
+             dvm(i,j-1)*(d(i,j-1)-d(i,j-2)));
+    d4(i,j)=d4(i,j)+c16*
+            (dvm(i,j+1)*(d(i,j)-d(i,j+1))+
+            dvm(i,j-1)*(d(i,j-1)-d(i,j-2)));
+  }
+  /* :1127-1153 */
+  DO(j, 2, jmm1) DO(i, 2, imm1)
+    drhoy(i,j,1)=grav*(-zz(1))*d4(i,j)*drho(i,j,1);
+  DO(k, 2, kbm1) DO(j, 2, jmm1) DO(i, 2, imm1)
+    drhoy(i,j,k)=drhoy(i,j,k-1)
+                 +grav*0.5*dzz(k-1)*d4(i,j)
+                 *(drho(i,j,k-1)+drho(i,j,k))
+                 +grav*0.5*(zz(k-1)+zz(k))*ddx(i,j)
+                 *(rhou(i,j,k)-rhou(i,j,k-1));
+  DO(k, 1, kbm1) DO(j, 2, jmm1) DO(i, 2, imm1)
+    drhoy(i,j,k)=.25*(dt(i,j)+dt(i,j-1))
+                      *drhoy(i,j,k)*dvm(i,j)
+                      *(dx(i,j)+dx(i,j-1));
+  /* :1157-1164 */
+  DO(k, 1, kb) DO(j, 2, jmm1) DO(i, 2, imm1) {
+    drhox(i,j,k)=ramp*drhox(i,j,k);
+    drhoy(i,j,k)=ramp*drhoy(i,j,k);
+  }
+  for (size_t n = 0; n < N3; ++n) S->rho[n] = S->rho[n] + S->rmean[n];
+#undef d4
+#undef ddx
+#undef drho
+#undef rhou
+}
+
+/* ------------------------------------------------------------------ */
 /* |S|**1.5 (solver.f:1195).  pow_mode 0 (default): libm pow, what gfortran emits for a real
  * exponent.  pow_mode 1: x*sqrt(x) with the rounding errors of sqrt and of the product
  * recovered by fma -- the routine the CUDA path uses; tests switch to it to show that this

@@ -23,7 +23,8 @@ STEP_CASES = [
     ((24, 19, 9), 6, {"nbct": 3, "nbcs": 3}),
     ((24, 19, 9), 6, {"nbct": 4, "ntp": 3}),
     ((24, 19, 9), 6, {"mode": 4}),
-    ((24, 19, 9), 6, {"mode": 2, "island": True}),            # 2-D only: advave's mode=2 block (solver.f:123-195)
+    ((24, 19, 9), 6, {"mode": 2, "island": True}),
+    ((24, 19, 9), 6, {"npg": 2, "island": True}),             # baropg_mcc (solver.f:943-1159)            # 2-D only: advave's mode=2 block (solver.f:123-195)
     ((33, 6, 6), 5, {}),          # minimum-width channel
     ((6, 33, 7), 5, {}),
     ((21, 18, 8), 6, {"isplit": 5, "dte": 6.0}),
@@ -88,7 +89,7 @@ def _interior(a):
     return a[1:-1, 1:-1]
 
 
-ROUTINES = ["dens", "baropg", "advct", "advave", "vertvl", "advq", "profq", "advt1", "advt2", "advt2_it3",
+ROUTINES = ["dens", "baropg", "baropg_mcc", "advct", "advave", "vertvl", "advq", "profq", "advt1", "advt2", "advt2_it3",
             "proft1", "proft2", "proft3", "advu", "advv", "profu", "profv", "realvertvl"]
 
 
@@ -110,6 +111,8 @@ def check_routine(factory, routine, dims):
         o.dens("s", "t", "rho"); g.dens("s", "t", "rho"); out = ["rho"]
     elif routine == "baropg":
         o.baropg(); g.baropg(); out = ["drhox", "drhoy", "rho"]
+    elif routine == "baropg_mcc":
+        o.baropg_mcc(); g.baropg_mcc(); out = ["drhox", "drhoy", "rho", "drx2d"][:3]
     elif routine == "advct":
         o.advct(); g.advct(); out = ["advx", "advy"]
     elif routine == "advave":

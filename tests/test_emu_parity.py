@@ -35,7 +35,7 @@ def test_matches_golden(name):
 
 
 def test_unsupported_switches_set_error_status():
-    st, g = syn.seamount(20, 17, 8, EmuPom, npg=2)
+    st, g = syn.seamount(20, 17, 8, EmuPom, npg=3)
     with pytest.raises(Exception):
         g.step(1)
     assert g.getc("error_status") == 1

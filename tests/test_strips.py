@@ -72,7 +72,7 @@ def test_strips_equal_single_domain_bitwise(nstrips, ghost):
     assert 0 < nex / nstep < 369
 
 
-@pytest.mark.parametrize("kw", [{"nadv": 1}, {"mode": 4}, {"nbct": 2, "ntp": 3}, {"nitera": 3, "sw": 1.0}, {"mode": 2}])
+@pytest.mark.parametrize("kw", [{"nadv": 1}, {"mode": 4}, {"nbct": 2, "ntp": 3}, {"nitera": 3, "sw": 1.0}, {"mode": 2}, {"npg": 2}])
 def test_strips_namelist_variants(kw):
     dims, nstep = (20, 30, 7), 4
     whole = _whole(dims, nstep, **kw)
