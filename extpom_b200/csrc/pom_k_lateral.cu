@@ -146,7 +146,9 @@ struct BaropgK : KBase {
       const double ddx=dt(i,j)-dt(i-1,j), ddy=dt(i,j)-dt(i,j-1);
       const double dyx=dy(i,j)+dy(i-1,j), dxy=dx(i,j)+dx(i,j-1);
       // rho-rmean at (i,j),(i-1,j),(i,j-1), levels k-1 (a*) and k (b*)
-      double a0=rho(i,j,1)-rmean(i,j,1);
+      const double rm1=rmean(i,j,1);
+      double a0=rho(i,j,1)-rm1;
+      rho2(i,j,1)=a0+rm1;                                               // :854,937 folded into the sweep
       double ax=rho(i-1,j,1)-rmean(i-1,j,1);
       double ay=rho(i,j-1,1)-rmean(i,j-1,1);
       double px=.5*grav*(-zz(1))*dtx*(a0-ax);                          // :859-860
@@ -154,7 +156,9 @@ struct BaropgK : KBase {
       for (int k = 1; k <= kbm1; ++k) {
         PF3(p.rho,i,j,k+2); PF3(p.rmean,i,j,k+2); PF3(p.rho,i,j-1,k+2); PF3(p.rmean,i,j-1,k+2);
         if (k >= 2) {
-          double b0=rho(i,j,k)-rmean(i,j,k);
+          const double rmk=rmean(i,j,k);
+          double b0=rho(i,j,k)-rmk;
+          rho2(i,j,k)=b0+rmk;
           double bx=rho(i-1,j,k)-rmean(i-1,j,k);
           double by=rho(i,j-1,k)-rmean(i,j-1,k);
           px=px+grav*.25*(zz(k-1)-zz(k))*dtx*(b0-bx+a0-ax)
@@ -172,16 +176,17 @@ struct BaropgK : KBase {
       }
       drhox(i,j,kb)=ramp*drhox(i,j,kb);                                 // :928-932 (k=kb)
       drhoy(i,j,kb)=ramp*drhoy(i,j,kb);
+      rho2(i,j,kb)=(rho(i,j,kb)-rmean(i,j,kb))+rmean(i,j,kb);
     } else {
       for (int k = 1; k <= kbm1; ++k) {  // edges keep their content (initialize.f:307-308)
         sx=sx+drhox(i,j,k)*dz(k);
         sy=sy+drhoy(i,j,k)*dz(k);
       }
+      for (int k = 1; k <= kb; ++k)
+        rho2(i,j,k)=(rho(i,j,k)-rmean(i,j,k))+rmean(i,j,k);             // :854,937
     }
     drx2d(i,j)=sx;
     dry2d(i,j)=sy;
-    for (int k = 1; k <= kb; ++k)
-      rho2(i,j,k)=(rho(i,j,k)-rmean(i,j,k))+rmean(i,j,k);               // :854,937
   }
 };
 

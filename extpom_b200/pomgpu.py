@@ -10,6 +10,7 @@ the built library or without a CUDA device raises.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -199,8 +200,12 @@ class PomGpu:
     def pinned(self, name):
         """A page-locked host array shaped like field `name` (per-step forcing buffers)."""
         a = np.zeros(self.shapes[name], dtype=np.float64, order="F")
-        if self.L.pomgpu_pin_host(a.ctypes.data_as(C.c_void_p), a.nbytes) != 0:
+        ptr = a.ctypes.data
+        if self.L.pomgpu_pin_host(C.c_void_p(ptr), a.nbytes) != 0:
             raise PomGpuError("cudaHostRegister failed")
+        # the registration must not outlive the buffer: a later allocation that overlaps a stale
+        # page-locked range makes cudaMemcpy fail with "invalid argument"
+        weakref.finalize(a, self.L.pomgpu_unpin_host, C.c_void_p(ptr))
         return a
 
     def put_async(self, name, a):
