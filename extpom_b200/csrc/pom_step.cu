@@ -497,7 +497,15 @@ int pomgpu_push_async(pomgpu_t* p, const char* name, const double* host) {
     cudaEventCreateWithFlags(&e, cudaEventDisableTiming); c->ev_swapped = (void*)e;
     cudaEventRecord((cudaEvent_t)c->ev_swapped, (cudaStream_t)c->stream);
   }
-  if (!c->shadow[id] && dev_alloc(c, &c->shadow[id], field_elems(c, f))) return 1;
+  if (!c->shadow[id]) {
+    // plain allocation: dev_alloc's zero fill runs on the COMPUTE stream and could land after the
+    // copy below (which runs on the copy stream); the copy overwrites the whole buffer anyway
+    if (cudaMalloc((void**)&c->shadow[id], field_elems(c, f) * sizeof(double)) != cudaSuccess) {
+      snprintf(c->err, sizeof(c->err), "push_async(%s): out of device memory", name);
+      c->c.error_status = 1;
+      return 1;
+    }
+  }
   cudaStream_t cs = (cudaStream_t)c->copy_stream;
   cudaStreamWaitEvent(cs, (cudaEvent_t)c->ev_swapped, 0);   // the shadow was live until the last swap
   cudaError_t e = cudaMemcpyAsync(c->shadow[id], host, field_elems(c, f) * 8, cudaMemcpyHostToDevice, cs);
