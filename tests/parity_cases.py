@@ -24,7 +24,9 @@ STEP_CASES = [
     ((24, 19, 9), 6, {"nbct": 4, "ntp": 3}),
     ((24, 19, 9), 6, {"mode": 4}),
     ((24, 19, 9), 6, {"mode": 2, "island": True}),
-    ((24, 19, 9), 6, {"npg": 2, "island": True}),             # baropg_mcc (solver.f:943-1159)            # 2-D only: advave's mode=2 block (solver.f:123-195)
+    ((24, 19, 9), 6, {"npg": 2, "island": True}),
+    ((14, 12, 61), 4, {}),                                    # BASELINE configs[4]: kb=61
+    ((12, 10, 64), 3, {}),                                    # the largest kb the column solvers hold (KMAX)             # baropg_mcc (solver.f:943-1159)            # 2-D only: advave's mode=2 block (solver.f:123-195)
     ((33, 6, 6), 5, {}),          # minimum-width channel
     ((6, 33, 7), 5, {}),
     ((21, 18, 8), 6, {"isplit": 5, "dte": 6.0}),

@@ -63,3 +63,14 @@ def test_field_registry_matches_python_mirror():
             want *= s
         assert g.L.pomgpu_field_elems(g.h, n.encode()) == want, n
     del lib
+
+
+def test_kb_beyond_kmax_is_rejected():
+    """The column solvers keep their eliminated coefficients in KMAX=64 entries per thread:
+    pomgpu_create must refuse kb > 64 instead of overrunning them."""
+    import ctypes as C
+    from tests import emu
+    L = C.CDLL(emu.build_emu())
+    L.pomgpu_create.restype = C.c_void_p
+    assert not L.pomgpu_create(12, 10, 65, 0)
+    assert not L.pomgpu_create(4, 10, 10, 0)       # im < 6
