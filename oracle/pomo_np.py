@@ -6,6 +6,7 @@ compiled here, so the C oracle is itself a restatement; this module restates
     vertvl  pom/solver.f:1970-2021      advq    pom/solver.f:411-477
     advave  pom/solver.f:6-121          proft   pom/solver.f:1541-1683
     profq   pom/solver.f:1212-1538      advt2 + smol_adif  pom/solver.f:577-731,1880-1967
+    baropg_mcc  pom/solver.f:943-1159
     mode_external + bcond(1), bcond(2)  pom/advance.f:205-353, pom/bounds_forcing.f:18-83
 a second time, written from the Fortran text with whole-array slices instead of loops, and
 tests/test_oracle_np.py requires the two restatements to agree BITWISE (same IEEE operations in
@@ -542,3 +543,57 @@ def advt2(f, c, fb, fq, fclim, ff_in):
                                                 + yflux[Ii, sl(2, jmm1, 1), K] - yflux[Ii, Ji, K]) / (
             (h[Ii, Ji] + f["etf"][Ii, Ji]) * art[Ii, Ji])
     return ff, fb
+
+
+# ------------------------------------------------------------------- baropg_mcc
+def baropg_mcc(f, c, rho_in, drhox0, drhoy0):
+    """pom/solver.f:943-1159 (npg=2), one sub-domain.  Returns (drhox, drhoy, rho)."""
+    im, jm, kb = rho_in.shape
+    imm1, jmm1, kbm1 = im - 1, jm - 1, kb - 1
+    c24, c16 = float(np.float32(1.) / np.float32(24.)), float(np.float32(1.) / np.float32(16.))
+    grav, zz, dzz, d, dt = c["grav"], f["zz"], f["dzz"], f["d"], f["dt"]
+    rho = rho_in - f["rmean"]
+    res = []
+    for comp in (0, 1):
+        m = f["dum"] if comp == 0 else f["dvm"]
+        met = f["dy"] if comp == 0 else f["dx"]
+        sh = (lambda a, n: np.roll(a, -n, axis=comp))          # sh(a, n)[i] = a[i+n] along the component axis
+        lo_all = (sl(2, im), slice(None)) if comp == 0 else (slice(None), sl(2, jm))
+        lo_cor = (sl(3, imm1), slice(None)) if comp == 0 else (slice(None), sl(3, jmm1))
+        drho = np.zeros((im, jm, kb), order="F")
+        rhou = np.zeros((im, jm, kb), order="F")
+        ddx = np.zeros((im, jm), order="F")
+        d4 = np.zeros((im, jm), order="F")
+        for k in range(1, kbm1 + 1):
+            r = rho[:, :, k - 1]
+            drho[:, :, k - 1][lo_all] = ((r - sh(r, -1)) * m)[lo_all]
+            rhou[:, :, k - 1][lo_all] = (0.5 * (r + sh(r, -1)) * m)[lo_all]
+        ddx[lo_all] = ((d - sh(d, -1)) * m)[lo_all]
+        d4[lo_all] = (.5 * (d + sh(d, -1)) * m)[lo_all]
+        for k in range(1, kbm1 + 1):
+            r = rho[:, :, k - 1]
+            drho[:, :, k - 1][lo_cor] = (drho[:, :, k - 1] - c24 * (sh(m, 1) * (sh(r, 1) - r) - 2 * (r - sh(r, -1))
+                                                                    + sh(m, -1) * (sh(r, -1) - sh(r, -2))))[lo_cor]
+            rhou[:, :, k - 1][lo_cor] = (rhou[:, :, k - 1] + c16 * (sh(m, 1) * (r - sh(r, 1))
+                                                                    + sh(m, -1) * (sh(r, -1) - sh(r, -2))))[lo_cor]
+        ddx[lo_cor] = (ddx - c24 * (sh(m, 1) * (sh(d, 1) - d) - 2 * (d - sh(d, -1)) + sh(m, -1) * (sh(d, -1) - sh(d, -2))))[lo_cor]
+        d4[lo_cor] = (d4 + c16 * (sh(m, 1) * (d - sh(d, 1)) + sh(m, -1) * (sh(d, -1) - sh(d, -2))))[lo_cor]
+        I, J = sl(2, imm1), sl(2, jmm1)
+        g3 = np.zeros((im, jm, kb), order="F")
+        g3[I, J, 0] = grav * (-zz[0]) * d4[I, J] * drho[I, J, 0]
+        for k in range(2, kbm1 + 1):
+            g3[I, J, k - 1] = (g3[I, J, k - 2]
+                               + grav * 0.5 * dzz[k - 2] * d4[I, J] * (drho[I, J, k - 2] + drho[I, J, k - 1])
+                               + grav * 0.5 * (zz[k - 2] + zz[k - 1]) * ddx[I, J] * (rhou[I, J, k - 1] - rhou[I, J, k - 2]))
+        dsum = (dt + sh(dt, -1))
+        msum = (met + sh(met, -1))
+        for k in range(1, kbm1 + 1):
+            g3[I, J, k - 1] = .25 * dsum[I, J] * g3[I, J, k - 1] * m[I, J] * msum[I, J]
+        res.append(g3)
+    drhox, drhoy = drhox0.copy(order="F"), drhoy0.copy(order="F")
+    I, J = sl(2, imm1), sl(2, jmm1)
+    drhox[I, J, :kbm1] = res[0][I, J, :kbm1]
+    drhoy[I, J, :kbm1] = res[1][I, J, :kbm1]
+    drhox[I, J, :] = c["ramp"] * drhox[I, J, :]
+    drhoy[I, J, :] = c["ramp"] * drhoy[I, J, :]
+    return drhox, drhoy, rho + f["rmean"]

@@ -137,3 +137,15 @@ def test_advt2_smol_adif(nitera, sw):
     o.advt2("tb", "t", "tclim", "uf")
     assert np.array_equal(o.get("uf"), ff)
     assert np.array_equal(o.get("tb"), fb)
+
+
+def test_baropg_mcc(spun):
+    from oracle.pomo_np import baropg_mcc
+    o, n, f = spun
+    dx_, dy_, rho_ = baropg_mcc(n.f, n.c, f["rho"], f["drhox"], f["drhoy"])
+    o.baropg_mcc()
+    assert np.array_equal(o.get("drhox"), dx_)
+    assert np.array_equal(o.get("drhoy"), dy_)
+    assert np.array_equal(o.get("rho"), rho_)
+    for k in ("rho", "drhox", "drhoy"):
+        o.put(k, f[k])
