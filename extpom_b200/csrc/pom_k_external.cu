@@ -114,6 +114,7 @@ struct ModeInterTailK : KBase {
 // 13 fields are read with neighbours (staged, halo 1), 18 at the own point only.  The filtered
 // uab,vab go to the scratch buffers s2a,s2b (advave reads uab,vab of the neighbours); the
 // caller rotates ua<->uaf, va<->vaf, uab<->s2a, vab<->s2b, elb<->el2, el<->elf, d<->d2.
+template <bool M2>   // M2: mode=2 build with advave's bottom-stress / curvature block (solver.f:123-195)
 struct ExtStepK : KBase {
   POM_KINFO("ext_step", 0, 0, 31, 12)
   int iext, do_adv;
@@ -122,7 +123,7 @@ struct ExtStepK : KBase {
 #define POM_EXT_TY 16
 #define POM_EXT_MINB 2
 #endif
-  static constexpr int NV = 7, TY = POM_EXT_TY, MINB = POM_EXT_MINB;
+  static constexpr int NV = M2 ? 7 : 6, TY = POM_EXT_TY, MINB = POM_EXT_MINB;
   static constexpr int NF = 13, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = POM_EXT_TY + 2, NK = 1;
   enum { D = OP_D, UA = OP_UA, VA = OP_VA, UAB = OP_UAB, VAB = OP_VAB, AAM2D = OP_AAM2D, DX = OP_DX, DY = OP_DY,
          EL, ELB, H, COR, EATM };
@@ -160,7 +161,7 @@ struct ExtStepK : KBase {
     if (i >= 2) v[FUA]=.25*(d00+o(D,-1,0))*(o(DY,0,0)+o(DY,-1,0))*o(UA,0,0);          // advance.f:213-214
     if (j >= 2 && j - 1 >= jlo) v[FVA]=.25*(d00+o(D,0,-1))*(o(DX,0,0)+o(DX,0,-1))*o(VA,0,0);   // :215-216
     if (do_adv) advave_own_fluxes<FXU>(g, i, j, o, v);       // advave (solver.f:16-121)
-    if (do_adv && c.mode == 2 && i >= 2 && i <= imm1 && j >= 2 && j <= jmm1 && j + 1 <= g.joff + g.jml)
+    if (M2 && do_adv && i >= 2 && i <= imm1 && j >= 2 && j <= jmm1 && j + 1 <= g.joff + g.jml)
       v[CURV]=.25*((o(VA,0,1)+o(VA,0,0))*(o(DY,1,0)-o(DY,-1,0))
                   -(o(UA,1,0)+o(UA,0,0))*(o(DX,0,1)-o(DX,0,-1)))
               /(o(DX,0,0)*o(DY,0,0));                      // solver.f:145-152
@@ -182,7 +183,7 @@ struct ExtStepK : KBase {
       } else {
         s.au=advua(i,j); s.av=advva(i,j);
       }
-      if (do_adv && c.mode == 2) {
+      if (M2 && do_adv) {
         // mode 2 (solver.f:123-195): bottom stress from the 2-D velocities, curvature terms
         s.m2 = true;
         const double d00=o(D,0,0), uab00=o(UAB,0,0), vab00=o(VAB,0,0);
@@ -208,7 +209,7 @@ struct ExtStepK : KBase {
     // loads are in flight together instead of one L2 round trip after the other
     const double aru0=POM_LDG(&aru(i,j)), arv0=POM_LDG(&arv(i,j)), adx0=POM_LDG(&adx2d(i,j)), ady0=POM_LDG(&ady2d(i,j));
     const double drx0=POM_LDG(&drx2d(i,j)), dry0=POM_LDG(&dry2d(i,j)), wus0=POM_LDG(&wusurf(i,j));
-    const double wub0=s.m2 ? s.wub : wubot(i,j), wvb0=s.m2 ? s.wvb : wvbot(i,j);
+    const double wub0=(M2 && s.m2) ? s.wub : POM_LDG(&wubot(i,j)), wvb0=(M2 && s.m2) ? s.wvb : POM_LDG(&wvbot(i,j));
     const double wvs0=POM_LDG(&wvsurf(i,j)), dum0=POM_LDG(&dum(i,j)), dvm0=POM_LDG(&dvm(i,j));
     const double egf0=egf(i,j), utf0=utf(i,j), vtf0=vtf(i,j);
     const double etf0=(iext >= c.isplit-1) ? etf(i,j) : 0.;
@@ -216,7 +217,7 @@ struct ExtStepK : KBase {
     const double d00=o(D,0,0), el00=o(EL,0,0), elb00=o(ELB,0,0), h00=o(H,0,0), ua00=o(UA,0,0), va00=o(VA,0,0);
     elf(i,j)=ef;
     if (do_adv) { advua(i,j)=s.au; advva(i,j)=s.av; }
-    if (s.m2) { wubot(i,j)=s.wub; wvbot(i,j)=s.wvb; }
+    if (M2 && s.m2) { wubot(i,j)=s.wub; wvbot(i,j)=s.wvb; }
     double un, vn;
     // ---- uaf(i,j) after bcond(2); cells never assigned keep uaf's content ----
     if (jin) {
@@ -306,5 +307,8 @@ void run_mode_inter_tail(Ctx* c, int j0, int j1) { launch_cols(c, ModeInterTailK
 
 namespace pom {
 // fused external substep; the caller rotates the time levels afterwards
-void run_ext_step(Ctx* c, int iext, int do_adv, int j0, int j1) { launch_tile3(c, ExtStepK(c, iext, do_adv), 1, c->g.im, j0, j1); }
+void run_ext_step(Ctx* c, int iext, int do_adv, int j0, int j1) {
+  if (c->c.mode == 2) launch_tile3(c, ExtStepK<true>(c, iext, do_adv), 1, c->g.im, j0, j1);
+  else launch_tile3(c, ExtStepK<false>(c, iext, do_adv), 1, c->g.im, j0, j1);
+}
 }  // namespace pom

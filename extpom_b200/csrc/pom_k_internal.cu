@@ -878,13 +878,22 @@ struct ProftK : KBase {
   }
 };
 
+template <class K>
+POM_HD void ts_level(const K& kk, int i, int j, int k, double a, double b, double m, double fold, double fnew, int with_dens);
+
 // proft for T (in uf) and S (in vf) in one TMA-fed column kernel (advance.f:440-441): kh is read
 // once, and the matrix coefficients a, c and -- when both tracers have the same class of
 // surface condition -- the eliminated ee and the pivots are shared between the two systems.
 struct ProftTSK : KBase {
   POM_KINFO("proft_ts", 3, 2, 6, 0)
   double rn, ad1n, ad2n;   // Jerlov water type ntp (:1568-1575)
-  ProftTSK(const Ctx* x) : KBase(x) {
+  int fuse;                // the upward sweep also does bcond(4) + t/s filter + restore + dens (advance.f:442-454)
+  double fold, fnew;
+  ProftTSK(const Ctx* x, int fz = 0) : KBase(x), fuse(fz) {
+    const double trst = 30.;                                             // bounds_forcing.f:1033
+    int ntime = (int)(x->c.time / trst);
+    fnew = x->c.time / trst - ntime;
+    fold = 1. - fnew;
     const double r[5] = {.58, .62, .67, .77, .78};
     const double ad1[5] = {.35, .60, 1.0, 1.5, 1.4};
     const double ad2[5] = {23., 20., 17., 14., 7.9};
@@ -971,6 +980,23 @@ struct ProftTSK : KBase {
     POM_DIMS;
     const bool same = ((c.nbct == 1 || c.nbct == 2) == (c.nbcs == 1 || c.nbcs == 2));
     double fT=s.fT, fS=s.fS;
+    if (fuse) {
+      // the new T,S of a level go straight into the filter (which writes uf, vf, tb, sb, rho)
+      const double m = fsm(i,j);
+      ts_level(*this, i, j, kbm1, fT, fS, m, fold, fnew, 1);
+      for (int ki = kb-2; ki >= 1; --ki) {                              // :1673-1680
+        {   // the filter's operands of the level below, towards L1
+          const int o = POM_I3(i,j,ki-1);
+          if (ki > 1) { POM_PREFETCH(p.t+o); POM_PREFETCH(p.s+o); POM_PREFETCH(p.tb+o); POM_PREFETCH(p.sb+o);
+                        POM_PREFETCH(p.tclim+o); POM_PREFETCH(p.sclim+o); }
+        }
+        const double eT=cm.eeT[ki];
+        fT=eT*fT+cm.ggT[ki];
+        fS=(same ? eT : cm.eeS[ki])*fS+cm.ggS[ki];
+        ts_level(*this, i, j, ki, fT, fS, m, fold, fnew, 1);
+      }
+      return;
+    }
     POM_STCS(&uf(i,j,kbm1),fT);
     POM_STCS(&vf(i,j,kbm1),fS);
     for (int ki = kb-2; ki >= 1; --ki) {                                // :1673-1680
@@ -981,6 +1007,12 @@ struct ProftTSK : KBase {
       POM_STCS(&vf(i,j,ki),fS);
     }
   }
+};
+
+// the fused variant under its own name / algorithmic byte count in the per-kernel profile
+struct ProftFilterK : ProftTSK {
+  POM_KINFO("proft_tsfilter", 9, 5, 9, 0)
+  ProftFilterK(const Ctx* x) : ProftTSK(x, 1) {}
 };
 
 // x**1.5 for x>=0, rounded like a correctly-rounded pow(x,1.5): sqrt is IEEE-exact to
@@ -1008,13 +1040,102 @@ POM_HD double dens_point(double tr, double sr, double pp, double rhoref_, double
   return rhor/rhoref_*m;
 }
 
+// One level of bcond(4) (bounds_forcing.f:151-242) + Asselin filter/rotation of t,s
+// (advance.f:444-449) + restore_interior arithmetic and mask (bounds_forcing.f:1083-1118)
+// [+ dens(s,t,rho) of the new t,s (advance.f:454)] for the new values a (T), b (S) that proft
+// left at (i,j,k).  Shared by the stand-alone filter kernel and by proft's fused upward sweep.
+template <class K>
+POM_HD void ts_level(const K& kk, int i, int j, int k, double a, double b, double m, double fold, double fnew, int with_dens) {
+  const Geo& g = kk.g; const Ptrs& p = kk.p; const Consts& c = kk.c;
+  POM_DIMS;
+    const bool vadv = (k != 1 && k != kbm1);
+    if (j == 1) {                                                     // south (:196-211)
+      double u1=2.*v(i,2,k)*dti/(dy(i,1)+dy(i,2));
+      if (u1 >= 0.) {
+        a=t(i,1,k)-u1*(t(i,1,k)-tbs(i,k));
+        b=s(i,1,k)-u1*(s(i,1,k)-sbs(i,k));
+      } else {
+        a=t(i,1,k)-u1*(t(i,2,k)-t(i,1,k));
+        b=s(i,1,k)-u1*(s(i,2,k)-s(i,1,k));
+        if (vadv) {
+          double wm=.5*(w(i,2,k)+w(i,2,k+1))*dti/((zz(k-1)-zz(k+1))*dt(i,2));
+          a=a-wm*(t(i,2,k-1)-t(i,2,k+1));
+          b=b-wm*(s(i,2,k-1)-s(i,2,k+1));
+        }
+      }
+    } else if (j == jm) {                                             // north (:214-229)
+      double u1=2.*v(i,jm,k)*dti/(dy(i,jm)+dy(i,jmm1));
+      if (u1 <= 0.) {
+        a=t(i,jm,k)-u1*(tbn(i,k)-t(i,jm,k));
+        b=s(i,jm,k)-u1*(sbn(i,k)-s(i,jm,k));
+      } else {
+        a=t(i,jm,k)-u1*(t(i,jm,k)-t(i,jmm1,k));
+        b=s(i,jm,k)-u1*(s(i,jm,k)-s(i,jmm1,k));
+        if (vadv) {
+          double wm=.5*(w(i,jmm1,k)+w(i,jmm1,k+1))*dti/((zz(k-1)-zz(k+1))*dt(i,jmm1));
+          a=a-wm*(t(i,jmm1,k-1)-t(i,jmm1,k+1));
+          b=b-wm*(s(i,jmm1,k-1)-s(i,jmm1,k+1));
+        }
+      }
+    } else if (i == im) {                                             // east (:158-173)
+      double u1=2.*u(im,j,k)*dti/(dx(im,j)+dx(imm1,j));
+      if (u1 <= 0.) {
+        a=t(im,j,k)-u1*(tbe(j,k)-t(im,j,k));
+        b=s(im,j,k)-u1*(sbe(j,k)-s(im,j,k));
+      } else {
+        a=t(im,j,k)-u1*(t(im,j,k)-t(imm1,j,k));
+        b=s(im,j,k)-u1*(s(im,j,k)-s(imm1,j,k));
+        if (vadv) {
+          double wm=.5*(w(imm1,j,k)+w(imm1,j,k+1))*dti/((zz(k-1)-zz(k+1))*dt(imm1,j));
+          a=a-wm*(t(imm1,j,k-1)-t(imm1,j,k+1));
+          b=b-wm*(s(imm1,j,k-1)-s(imm1,j,k+1));
+        }
+      }
+    } else if (i == 1) {                                              // west (:176-191)
+      double u1=2.*u(2,j,k)*dti/(dx(1,j)+dx(2,j));
+      if (u1 >= 0.) {
+        a=t(1,j,k)-u1*(t(1,j,k)-tbw(j,k));
+        b=s(1,j,k)-u1*(s(1,j,k)-sbw(j,k));
+      } else {
+        a=t(1,j,k)-u1*(t(2,j,k)-t(1,j,k));
+        b=s(1,j,k)-u1*(s(2,j,k)-s(1,j,k));
+        if (vadv) {
+          double wm=.5*(w(2,j,k)+w(2,j,k+1))*dti/((zz(k-1)-zz(k+1))*dt(2,j));
+          a=a-wm*(t(2,j,k-1)-t(2,j,k+1));
+          b=b-wm*(s(2,j,k-1)-s(2,j,k+1));
+        }
+      }
+    }
+    a=a*m;                                                            // :236-237
+    b=b*m;
+    // tb,sb as left behind by advt1/advt2: (fb-fclim)+fclim (solver.f:691,715)
+    double tbr=(tb(i,j,k)-tclim(i,j,k))+tclim(i,j,k);
+    double sbr=(sb(i,j,k)-sclim(i,j,k))+sclim(i,j,k);
+    double tf=t(i,j,k)+.5*smoth*(a+tbr-2.*t(i,j,k));                  // advance.f:444
+    double sf=s(i,j,k)+.5*smoth*(b+sbr-2.*s(i,j,k));                  // advance.f:445
+    if (c.lrestore) {                                                 // bounds_forcing.f:1083-1110
+      double tr=fold*trstrb(i,j,k)+fnew*trstrf(i,j,k);
+      double sr=fold*srstrb(i,j,k)+fnew*srstrf(i,j,k);
+      double ta=fold*taurstrb(i,j,k)+fnew*taurstrf(i,j,k);
+      a=a+2.*dti/86400.*ta*(tr-a);
+      tf=tf+2.*dti/86400.*ta*(tr-tf);
+      b=b+2.*dti/86400.*ta*(sr-b);
+      sf=sf+2.*dti/86400.*ta*(sr-sf);
+    }
+    a=a*m; b=b*m;                                                     // :1113-1118
+    uf(i,j,k)=a;
+    vf(i,j,k)=b;
+    tb(i,j,k)=tf*m;
+    sb(i,j,k)=sf*m;
+    if (with_dens)                                                    // solver.f:1175-1205
+      rho(i,j,k)=dens_point(a+tbias,b+sbias,grav*rhoref*(-zz(k)*h(i,j))*1.e-5,rhoref,m);
+}
+
 // ---------------------------------------------------------------------------
-// bcond(4) (bounds_forcing.f:151-242) + Asselin filter/rotation of t,s
-// (advance.f:444-449) + restore_interior arithmetic and mask
-// (bounds_forcing.f:1083-1118).  Filtered t,s -> tb,sb buffers; new t,s stay
-// in uf,vf; the host rotates pointers.
+// bcond(4) + filter of t,s as a stand-alone kernel (the un-fused stage hook); new t,s stay in
+// uf,vf, filtered t,s go to tb,sb; the host rotates pointers.
 struct TsFilterK : KBase {
-  POM_KINFO("ts_filter", 8, 4, 1, 0)
+  POM_KINFO("ts_filter", 8, 5, 3, 0)
   double fold, fnew;
   int with_dens;   // also dens(s,t,rho) of the new t,s (advance.f:454), saving a pass over both
   TsFilterK(const Ctx* x, int wd) : KBase(x), with_dens(wd) {
@@ -1026,90 +1147,7 @@ struct TsFilterK : KBase {
   POM_HD void operator()(int i, int j) const {
     POM_DIMS;
     const double m = fsm(i,j);
-    for (int k = 1; k <= kbm1; ++k) {
-      double a=uf(i,j,k), b=vf(i,j,k);
-      const bool vadv = (k != 1 && k != kbm1);
-      if (j == 1) {                                                     // south (:196-211)
-        double u1=2.*v(i,2,k)*dti/(dy(i,1)+dy(i,2));
-        if (u1 >= 0.) {
-          a=t(i,1,k)-u1*(t(i,1,k)-tbs(i,k));
-          b=s(i,1,k)-u1*(s(i,1,k)-sbs(i,k));
-        } else {
-          a=t(i,1,k)-u1*(t(i,2,k)-t(i,1,k));
-          b=s(i,1,k)-u1*(s(i,2,k)-s(i,1,k));
-          if (vadv) {
-            double wm=.5*(w(i,2,k)+w(i,2,k+1))*dti/((zz(k-1)-zz(k+1))*dt(i,2));
-            a=a-wm*(t(i,2,k-1)-t(i,2,k+1));
-            b=b-wm*(s(i,2,k-1)-s(i,2,k+1));
-          }
-        }
-      } else if (j == jm) {                                             // north (:214-229)
-        double u1=2.*v(i,jm,k)*dti/(dy(i,jm)+dy(i,jmm1));
-        if (u1 <= 0.) {
-          a=t(i,jm,k)-u1*(tbn(i,k)-t(i,jm,k));
-          b=s(i,jm,k)-u1*(sbn(i,k)-s(i,jm,k));
-        } else {
-          a=t(i,jm,k)-u1*(t(i,jm,k)-t(i,jmm1,k));
-          b=s(i,jm,k)-u1*(s(i,jm,k)-s(i,jmm1,k));
-          if (vadv) {
-            double wm=.5*(w(i,jmm1,k)+w(i,jmm1,k+1))*dti/((zz(k-1)-zz(k+1))*dt(i,jmm1));
-            a=a-wm*(t(i,jmm1,k-1)-t(i,jmm1,k+1));
-            b=b-wm*(s(i,jmm1,k-1)-s(i,jmm1,k+1));
-          }
-        }
-      } else if (i == im) {                                             // east (:158-173)
-        double u1=2.*u(im,j,k)*dti/(dx(im,j)+dx(imm1,j));
-        if (u1 <= 0.) {
-          a=t(im,j,k)-u1*(tbe(j,k)-t(im,j,k));
-          b=s(im,j,k)-u1*(sbe(j,k)-s(im,j,k));
-        } else {
-          a=t(im,j,k)-u1*(t(im,j,k)-t(imm1,j,k));
-          b=s(im,j,k)-u1*(s(im,j,k)-s(imm1,j,k));
-          if (vadv) {
-            double wm=.5*(w(imm1,j,k)+w(imm1,j,k+1))*dti/((zz(k-1)-zz(k+1))*dt(imm1,j));
-            a=a-wm*(t(imm1,j,k-1)-t(imm1,j,k+1));
-            b=b-wm*(s(imm1,j,k-1)-s(imm1,j,k+1));
-          }
-        }
-      } else if (i == 1) {                                              // west (:176-191)
-        double u1=2.*u(2,j,k)*dti/(dx(1,j)+dx(2,j));
-        if (u1 >= 0.) {
-          a=t(1,j,k)-u1*(t(1,j,k)-tbw(j,k));
-          b=s(1,j,k)-u1*(s(1,j,k)-sbw(j,k));
-        } else {
-          a=t(1,j,k)-u1*(t(2,j,k)-t(1,j,k));
-          b=s(1,j,k)-u1*(s(2,j,k)-s(1,j,k));
-          if (vadv) {
-            double wm=.5*(w(2,j,k)+w(2,j,k+1))*dti/((zz(k-1)-zz(k+1))*dt(2,j));
-            a=a-wm*(t(2,j,k-1)-t(2,j,k+1));
-            b=b-wm*(s(2,j,k-1)-s(2,j,k+1));
-          }
-        }
-      }
-      a=a*m;                                                            // :236-237
-      b=b*m;
-      // tb,sb as left behind by advt1/advt2: (fb-fclim)+fclim (solver.f:691,715)
-      double tbr=(tb(i,j,k)-tclim(i,j,k))+tclim(i,j,k);
-      double sbr=(sb(i,j,k)-sclim(i,j,k))+sclim(i,j,k);
-      double tf=t(i,j,k)+.5*smoth*(a+tbr-2.*t(i,j,k));                  // advance.f:444
-      double sf=s(i,j,k)+.5*smoth*(b+sbr-2.*s(i,j,k));                  // advance.f:445
-      if (c.lrestore) {                                                 // bounds_forcing.f:1083-1110
-        double tr=fold*trstrb(i,j,k)+fnew*trstrf(i,j,k);
-        double sr=fold*srstrb(i,j,k)+fnew*srstrf(i,j,k);
-        double ta=fold*taurstrb(i,j,k)+fnew*taurstrf(i,j,k);
-        a=a+2.*dti/86400.*ta*(tr-a);
-        tf=tf+2.*dti/86400.*ta*(tr-tf);
-        b=b+2.*dti/86400.*ta*(sr-b);
-        sf=sf+2.*dti/86400.*ta*(sr-sf);
-      }
-      a=a*m; b=b*m;                                                     // :1113-1118
-      uf(i,j,k)=a;
-      vf(i,j,k)=b;
-      tb(i,j,k)=tf*m;
-      sb(i,j,k)=sf*m;
-      if (with_dens)                                                    // solver.f:1175-1205
-        rho(i,j,k)=dens_point(a+tbias,b+sbias,grav*rhoref*(-zz(k)*h(i,j))*1.e-5,rhoref,m);
-    }
+    for (int k = 1; k <= kbm1; ++k) ts_level(*this, i, j, k, uf(i,j,k), vf(i,j,k), m, fold, fnew, with_dens);
   }
 };
 
@@ -1648,7 +1686,10 @@ void run_proft(Ctx* c, double* f, const double* wf, const double* fs, int nbc, i
   launch_cols(c, ProftK(c, f, wf, fs, nbc), ALLI, j0, j1);
 #endif
 }
-void run_proft_ts(Ctx* c, int j0, int j1) { launch_tma_cols(c, ProftTSK(c), ALLI, j0, j1); }
+void run_proft_ts(Ctx* c, int fuse, int j0, int j1) {
+  if (fuse) launch_tma_cols(c, ProftFilterK(c), ALLI, j0, j1);
+  else launch_tma_cols(c, ProftTSK(c), ALLI, j0, j1);
+}
 // caller swaps t<->uf, s<->vf (advance.f:446-449)
 void run_tsfilter(Ctx* c, int with_dens, int j0, int j1) { launch_cols(c, TsFilterK(c, with_dens), ALLI, j0, j1); }
 void run_dens(Ctx* c, const double* si, const double* ti, double* ro, int j0, int j1) {

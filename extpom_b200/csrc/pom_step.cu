@@ -41,7 +41,7 @@ void run_smol_adif(Ctx*, const double* ff, double* xm, double* ym, double* zw, i
 void run_advt2_diff(Ctx*, const double* fb, const double* fc, double* ff, int, int);
 void run_proft(Ctx*, double* f, const double* wf, const double* fs, int nbc, int, int);
 void run_tsfilter(Ctx*, int with_dens, int, int);
-void run_proft_ts(Ctx*, int, int);
+void run_proft_ts(Ctx*, int fuse, int, int);
 void run_advt2_ts(Ctx*, int, int);
 void run_advprof_u(Ctx*, int, int);
 void run_advprof_v(Ctx*, int, int);
@@ -249,8 +249,16 @@ static void k_advt2_ts(Group* G) {   // advt2(tb,t,tclim,uf) and advt2(sb,s,scli
 }
 static void k_proft_ts(Group* G) {   // proft(uf,wtsurf,tsurf,nbct) and proft(vf,wssurf,ssurf,nbcs) in one pass
   int e = NEED({F_uf, 0}, {F_vf, 0}, {F_kh, 0}, {F_etf, 0});
-  EACH(run_proft_ts(c, j0, j1));
+  EACH(run_proft_ts(c, 0, j0, j1));
   MADE(e, F_uf, F_vf);
+}
+// proft of T and S + bcond(4) + t/s filter + restore_interior + dens in one kernel (advance.f:439-454)
+static void k_proft_tsfilter(Group* G) {
+  int e = NEED({F_uf, 0}, {F_vf, 0}, {F_kh, 0}, {F_etf, 0}, {F_t, 0}, {F_s, 0}, {F_tb, 0}, {F_sb, 0}, {F_u, 0},
+               {F_v, 0}, {F_w, 0}, {F_dt, 0});
+  EACH(run_proft_ts(c, 1, j0, j1));
+  MADE(e, F_uf, F_vf, F_tb, F_sb, F_rho);
+  group_swap(G, F_t, F_uf); group_swap(G, F_s, F_vf);      // advance.f:446-449
 }
 static void k_tsfilter(Group* G, int with_dens) {
   int e = NEED({F_uf, 0}, {F_vf, 0}, {F_t, 0}, {F_s, 0}, {F_tb, 0}, {F_sb, 0}, {F_u, 0}, {F_v, 0}, {F_w, 0}, {F_dt, 0});
@@ -354,6 +362,7 @@ static int internal_stage(Group* G, int iint, int st) {
     case 9: if (ts) k_tsfilter(G, 0); break;
     case 105: if (ts) { if (k.nadv == 2 && k.nitera == 1) k_advt2_ts(G); else { internal_stage(G, iint, 5); internal_stage(G, iint, 6); } } break;
     case 107: if (ts) k_proft_ts(G); break;
+    case 207: if (ts) k_proft_tsfilter(G); break;     // stages 7-10 in one kernel (what the step runs)
     case 111: k_advprof_u(G); k_advprof_v(G); break;   // stages 11-14 as two fused kernels (what the step runs)           // proft of T and S fused (what the step runs)
     case 109: if (ts) k_tsfilter(G, 1); break;        // + dens fused (what the step runs)
     case 10: if (ts) k_dens(G, F_s, F_t, F_rho); break;
@@ -375,8 +384,7 @@ static int mode_internal(Group* G, int iint) {
     for (int st = 0; st <= 15; ++st) {
       if (st == 3) { internal_stage(G, iint, 103); ++st; continue; }   // profq with the q2/q2l filter fused
       if (st == 5) { internal_stage(G, iint, 105); ++st; continue; }   // advt2 of T and S in one kernel
-      if (st == 7) { internal_stage(G, iint, 107); ++st; continue; }   // proft T and S in one kernel
-      if (st == 9) { internal_stage(G, iint, 109); ++st; continue; }   // t/s filter with dens fused
+      if (st == 7) { internal_stage(G, iint, 207); st = 10; continue; }  // proft T,S + t/s filter + dens in one kernel
       if (st == 11) { internal_stage(G, iint, 111); st = 14; continue; }  // advu+profu, advv+profv
       internal_stage(G, iint, st);
     }
