@@ -446,16 +446,21 @@ struct ProfqK : KBase {
     }
     double up=st.ufkb, vp = 0.;
     emit(i,j,kb,up,0.,st.m);                                                  // uf(kb) (:1285), vf(kb)=0 (:1420)
+    // the eliminated coefficients come back from local memory (L2): fetch them one level ahead
+    double e1n=cm.ee[kbm1], g1n=cm.gg[kbm1], e2n=cm.e2v[kbm1], g2n=cm.g2v[kbm1];
     for (int ki = kbm1; ki >= 2; --ki) {
+      const double e1c=e1n, g1c=g1n, e2c=e2n, g2c=g2n;
+      e1n=cm.ee[ki-1]; g1n=cm.gg[ki-1];
+      if (ki > 2) { e2n=cm.e2v[ki-1]; g2n=cm.g2v[ki-1]; }
       {   // operands of the level below, towards L1 while this one is finished
         const int o = POM_I3(i,j,ki-1);
         POM_PREFETCH(p.q2+o); POM_PREFETCH(p.q2b+o); POM_PREFETCH(p.q2l+o); POM_PREFETCH(p.q2lb+o);
       }
-      up=cm.ee[ki]*up+cm.gg[ki];
-      vp=cm.e2v[ki]*vp+cm.g2v[ki];
+      up=e1c*up+g1c;
+      vp=e2c*vp+g2c;
       emit(i,j,ki,fabs(up),fabs(vp),st.m);
     }
-    up=cm.ee[1]*up+cm.gg[1];
+    up=e1n*up+g1n;
     emit(i,j,1,up,0.,st.m);                                                   // vf(1)=0 (:1419)
   }
 };
@@ -983,6 +988,8 @@ struct ProftTSK : KBase {
     if (fuse) {
       // the new T,S of a level go straight into the filter (which writes uf, vf, tb, sb, rho)
       const double m = fsm(i,j);
+      // the eliminated coefficients come back from local memory (L2): fetch them one level ahead
+      double eTn=cm.eeT[kb-2], gTn=cm.ggT[kb-2], gSn=cm.ggS[kb-2], eSn=same ? eTn : cm.eeS[kb-2];
       ts_level(*this, i, j, kbm1, fT, fS, m, fold, fnew, 1);
       for (int ki = kb-2; ki >= 1; --ki) {                              // :1673-1680
         {   // the filter's operands of the level below, towards L1
@@ -990,9 +997,10 @@ struct ProftTSK : KBase {
           if (ki > 1) { POM_PREFETCH(p.t+o); POM_PREFETCH(p.s+o); POM_PREFETCH(p.tb+o); POM_PREFETCH(p.sb+o);
                         POM_PREFETCH(p.tclim+o); POM_PREFETCH(p.sclim+o); }
         }
-        const double eT=cm.eeT[ki];
-        fT=eT*fT+cm.ggT[ki];
-        fS=(same ? eT : cm.eeS[ki])*fS+cm.ggS[ki];
+        const double eT=eTn, gT=gTn, eS=eSn, gS=gSn;
+        if (ki > 1) { eTn=cm.eeT[ki-1]; gTn=cm.ggT[ki-1]; gSn=cm.ggS[ki-1]; eSn=same ? eTn : cm.eeS[ki-1]; }
+        fT=eT*fT+gT;
+        fS=eS*fS+gS;
         ts_level(*this, i, j, ki, fT, fS, m, fold, fnew, 1);
       }
       return;
