@@ -8,6 +8,22 @@
 #include "pom_names.h"
 
 #define KMAX 64
+// min blocks/SM of the plain column kernels whose occupancy (not traffic) limits them: capping
+// them at 64 registers (4 x 256 threads) was measured at 0.43 -> 0.28 ms for realvertvl
+#ifndef POM_RV_MINB
+#define POM_RV_MINB 4
+#endif
+#ifndef POM_PROFT_MINB
+#define POM_PROFT_MINB 4
+#endif
+#ifndef POM_ADVPROF_MINB
+#define POM_ADVPROF_MINB 3
+#define POM_ADVPROF_NS 3
+#endif
+#ifndef POM_PROFQ_MINB
+#define POM_PROFQ_MINB 2
+#define POM_PROFQ_NS 3
+#endif
 #ifndef POM_TILE_TY
 #define POM_TILE_TY 16
 #define POM_TILE_MINB 1
@@ -208,8 +224,8 @@ struct ProfqK : KBase {
   // sound, buoyancy gradient, length scale, gh, production, the forward eliminations of BOTH
   // tridiagonal systems and the km/kh/kq update (in place, old kq kept in rolling registers);
   // `post` back-substitutes.  Only the four ee/gg vectors live in per-thread memory.
-  static constexpr int TY = 8, MINB = 2;
-  static constexpr int NF = 13, NS = 3, OHL = 0, OHR = 1, OHB = 0, OHT = 1, BW = 34, BH = 9, NK = 0;
+  static constexpr int TY = 8, MINB = POM_PROFQ_MINB;
+  static constexpr int NF = 13, NS = POM_PROFQ_NS, OHL = 0, OHR = 1, OHB = 0, OHT = 1, BW = 34, BH = 9, NK = 0;
   static constexpr bool UP = true;
   enum { T, S, RHO, Q2B, Q2LB, Q2, U, V, KM, KH, KQ, UF, VF };
   POM_HD void fields(const double** b) const {
@@ -905,7 +921,7 @@ struct ProftTSK : KBase {
     const int n = (x->c.ntp >= 1 && x->c.ntp <= 5) ? x->c.ntp - 1 : 1;
     rn = r[n]; ad1n = ad1[n]; ad2n = ad2[n];
   }
-  static constexpr int TY = 8, MINB = 3;
+  static constexpr int TY = 8, MINB = POM_PROFT_MINB;
   static constexpr int NF = 3, NS = 4, OHL = 0, OHR = 0, OHB = 0, OHT = 0, BW = 34, BH = 8, NK = 0;
   static constexpr bool UP = true;
   enum { FT, FS, KH };
@@ -1342,8 +1358,8 @@ struct AdvProfUVK : KBase {
     return VC ? kv : ku;
   }
   using KBase::KBase;
-  static constexpr int TY = 8, MINB = 2;
-  static constexpr int NF = 7, NS = 4, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = 10, NK = 0;
+  static constexpr int TY = 8, MINB = POM_ADVPROF_MINB;
+  static constexpr int NF = 7, NS = POM_ADVPROF_NS, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = 10, NK = 0;
   static constexpr bool UP = true;
   static constexpr int BI = VC ? 0 : -1, BJ = VC ? -1 : 0, OI = VC ? 1 : 0, OJ = VC ? 0 : 1;
   enum { W, X, Y, ADV, DRHO, XB, KM };
@@ -1712,6 +1728,6 @@ void run_profv(Ctx* c, int j0, int j1) { launch_cols(c, ProfvK(c), ALLI, j0, j1)
 // caller swaps u<->uf, v<->vf, ub<->s3a, vb<->s3b (advance.f:511-514)
 void run_uvfilter(Ctx* c, int j0, int j1) { launch_cols(c, UvFilterK(c), ALLI, j0, j1); }
 void run_endstep2d(Ctx* c, int j0, int j1) { launch_cols(c, EndStep2dK(c), ALLI, j0, j1); }
-void run_realvertvl(Ctx* c, int j0, int j1) { launch_cols(c, RealvertvlK(c), ALLI, j0, j1); }
+void run_realvertvl(Ctx* c, int j0, int j1) { launch_cols<RealvertvlK, POM_RV_MINB>(c, RealvertvlK(c), ALLI, j0, j1); }
 
 }  // namespace pom

@@ -296,7 +296,10 @@ struct SmagK : KBase {
 
 void run_advct(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvctK(c), 1, c->g.im, j0, j1); }
 // the caller swaps rho <-> rho2 afterwards
-void run_baropg(Ctx* c, int j0, int j1) { launch_cols(c, BaropgK(c), 1, c->g.im, j0, j1); }
+#ifndef POM_RV_MINB
+#define POM_RV_MINB 4
+#endif
+void run_baropg(Ctx* c, int j0, int j1) { launch_cols<BaropgK, POM_RV_MINB>(c, BaropgK(c), 1, c->g.im, j0, j1); }
 void run_baropg_mcc(Ctx* c, int j0, int j1) { launch_cols(c, BaropgMccK(c), 1, c->g.im, j0, j1); }
 void run_smag(Ctx* c, int j0, int j1) { launch_cols(c, SmagK(c), 1, c->g.im, j0, j1); }
 
