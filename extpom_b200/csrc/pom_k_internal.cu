@@ -18,11 +18,24 @@
 #endif
 #ifndef POM_ADVPROF_MINB
 #define POM_ADVPROF_MINB 3
+#endif
+#ifndef POM_ADVPROF_NS
 #define POM_ADVPROF_NS 3
 #endif
 #ifndef POM_PROFQ_MINB
 #define POM_PROFQ_MINB 2
+#endif
+#ifndef POM_PROFQ_NS
 #define POM_PROFQ_NS 3
+#endif
+#ifndef POM_PROFQ_TY
+#define POM_PROFQ_TY 8
+#endif
+#ifndef POM_PROFT_TY
+#define POM_PROFT_TY 8
+#endif
+#ifndef POM_ADVPROF_TY
+#define POM_ADVPROF_TY 8
 #endif
 #ifndef POM_TILE_TY
 #define POM_TILE_TY 16
@@ -224,8 +237,8 @@ struct ProfqK : KBase {
   // sound, buoyancy gradient, length scale, gh, production, the forward eliminations of BOTH
   // tridiagonal systems and the km/kh/kq update (in place, old kq kept in rolling registers);
   // `post` back-substitutes.  Only the four ee/gg vectors live in per-thread memory.
-  static constexpr int TY = 8, MINB = POM_PROFQ_MINB;
-  static constexpr int NF = 13, NS = POM_PROFQ_NS, OHL = 0, OHR = 1, OHB = 0, OHT = 1, BW = 34, BH = 9, NK = 0;
+  static constexpr int TY = POM_PROFQ_TY, MINB = POM_PROFQ_MINB;
+  static constexpr int NF = 13, NS = POM_PROFQ_NS, OHL = 0, OHR = 1, OHB = 0, OHT = 1, BW = 34, BH = TY + 1, NK = 0;
   static constexpr bool UP = true;
   enum { T, S, RHO, Q2B, Q2LB, Q2, U, V, KM, KH, KQ, UF, VF };
   POM_HD void fields(const double** b) const {
@@ -921,8 +934,8 @@ struct ProftTSK : KBase {
     const int n = (x->c.ntp >= 1 && x->c.ntp <= 5) ? x->c.ntp - 1 : 1;
     rn = r[n]; ad1n = ad1[n]; ad2n = ad2[n];
   }
-  static constexpr int TY = 8, MINB = POM_PROFT_MINB;
-  static constexpr int NF = 3, NS = 4, OHL = 0, OHR = 0, OHB = 0, OHT = 0, BW = 34, BH = 8, NK = 0;
+  static constexpr int TY = POM_PROFT_TY, MINB = POM_PROFT_MINB;
+  static constexpr int NF = 3, NS = 4, OHL = 0, OHR = 0, OHB = 0, OHT = 0, BW = 34, BH = TY, NK = 0;
   static constexpr bool UP = true;
   enum { FT, FS, KH };
   POM_HD void fields(const double** b) const { b[FT] = p.uf; b[FS] = p.vf; b[KH] = p.kh; }
@@ -1358,8 +1371,8 @@ struct AdvProfUVK : KBase {
     return VC ? kv : ku;
   }
   using KBase::KBase;
-  static constexpr int TY = 8, MINB = POM_ADVPROF_MINB;
-  static constexpr int NF = 7, NS = POM_ADVPROF_NS, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = 10, NK = 0;
+  static constexpr int TY = POM_ADVPROF_TY, MINB = POM_ADVPROF_MINB;
+  static constexpr int NF = 7, NS = POM_ADVPROF_NS, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = TY + 2, NK = 0;
   static constexpr bool UP = true;
   static constexpr int BI = VC ? 0 : -1, BJ = VC ? -1 : 0, OI = VC ? 1 : 0, OJ = VC ? 0 : 1;
   enum { W, X, Y, ADV, DRHO, XB, KM };
