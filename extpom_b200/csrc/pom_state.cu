@@ -250,6 +250,7 @@ void ctx_destroy(Ctx* c) {
   int n;
   const FieldInfo* t = field_table(&n);
   dev_sync(c);
+  record_free(c);
   for (int i = 0; i < n; ++i) {
     double** slot = (double**)((char*)&c->p + t[i].offset);
     if (*slot) dev_free(c, *slot);

@@ -568,6 +568,21 @@ double pomgpu_check_velocity_lagged(pomgpu_t* p) {
   return prev;
 #endif
 }
+// ---- on-device time interpolation of forcing / boundary records (pom_forcing.cu) ----
+int pomgpu_push_record(pomgpu_t* p, const char* name, int slot, const double* host) { return record_push(X(p), name, slot, host); }
+int pomgpu_rotate_record(pomgpu_t* p, const char* name) { return record_rotate(X(p), name); }
+int pomgpu_interp(pomgpu_t* p, const char* name, double fnew) { apply_pending(X(p)); return record_interp(X(p), &name, 1, fnew); }
+int pomgpu_wind(pomgpu_t* p, double fnew) {   // bounds_forcing.f:904-909
+  static const char* const n[] = {"wusurf", "wvsurf"};
+  apply_pending(X(p));
+  return record_interp(X(p), n, 2, fnew);
+}
+int pomgpu_heat(pomgpu_t* p, double fnew) {   // bounds_forcing.f:949-957
+  static const char* const n[] = {"wtsurf", "swrad"};
+  apply_pending(X(p));
+  return record_interp(X(p), n, 2, fnew);
+}
+int pomgpu_lateral_bc(pomgpu_t* p, double fnew) { apply_pending(X(p)); return record_lateral_bc(X(p), fnew); }   // :841-865
 int pomgpu_domain_stats_rows(pomgpu_t* p, double* rows) { apply_pending(X(p)); return domain_stats_rows(X(p), rows); }
 long pomgpu_launch_count(pomgpu_t* p, int reset) {
   long n = X(p)->launches;

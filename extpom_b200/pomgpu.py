@@ -25,8 +25,8 @@ F2D = ("aam2d advua advva adx2d ady2d art aru arv cbc cor d drx2d dry2d dt dum d
        "vab vaf vtb vtf vfluxb vfluxf wssurf wtsurf wubot wusurf wvbot wvsurf").split()
 BJ = "ele elw uabe uabw vabe vabw".split()
 BI = "eln els vabn vabs uabn uabs".split()
-BJK = "tbe sbe tbw sbw".split()
-BIK = "tbn sbn tbs sbs".split()
+BJK = "tbe sbe tbw sbw ube ubw".split()
+BIK = "tbn sbn tbs sbs vbn vbs".split()
 F1D = "z zz dz dzz".split()
 
 
@@ -62,6 +62,11 @@ def _bind(path):
     L.pomgpu_check_velocity.argtypes = [P]
     L.pomgpu_push_async.argtypes = [P, C.c_char_p, P]
     L.pomgpu_domain_stats_rows.argtypes = [P, P]
+    L.pomgpu_push_record.argtypes = [P, C.c_char_p, C.c_int, P]
+    L.pomgpu_rotate_record.argtypes = [P, C.c_char_p]
+    L.pomgpu_interp.argtypes = [P, C.c_char_p, C.c_double]
+    for n in ("wind", "heat", "lateral_bc"):
+        getattr(L, "pomgpu_" + n).argtypes = [P, C.c_double]
     L.pomgpu_check_velocity_lagged.restype = C.c_double
     L.pomgpu_check_velocity_lagged.argtypes = [P]
     L.pomgpu_pin_host.argtypes = [P, C.c_ulong]
@@ -212,6 +217,23 @@ class PomGpu:
         """Enqueue host->HBM copy of a (pinned, Fortran-ordered) array; no host wait."""
         assert a.flags.f_contiguous and a.shape == self.shapes[name]
         self._ck(self.L.pomgpu_push_async(self.h, name.encode(), a.ctypes.data_as(C.c_void_p)), f"push_async({name})")
+
+    # -- forcing records, interpolated in time on the device (bounds_forcing.f:841-865,904-909,949-957)
+    def put_record(self, name, slot, arr):
+        """Record `slot` (0 = older "b", 1 = newer "f") of forcing field `name`; asynchronous if `arr` is pinned."""
+        a = np.asfortranarray(self._rows(name, arr), dtype=np.float64)
+        assert a.shape == self.shapes[name], (name, a.shape, self.shapes[name])
+        self._ck(self.L.pomgpu_push_record(self.h, name.encode(), int(slot), a.ctypes.data_as(C.c_void_p)), f"push_record({name})")
+
+    def rotate_record(self, name):
+        self._ck(self.L.pomgpu_rotate_record(self.h, name.encode()), f"rotate_record({name})")
+
+    def interp(self, name, fnew):
+        self._ck(self.L.pomgpu_interp(self.h, name.encode(), float(fnew)), f"interp({name})")
+
+    def wind(self, fnew): self._ck(self.L.pomgpu_wind(self.h, float(fnew)), "wind")
+    def heat(self, fnew): self._ck(self.L.pomgpu_heat(self.h, float(fnew)), "heat")
+    def lateral_bc(self, fnew): self._ck(self.L.pomgpu_lateral_bc(self.h, float(fnew)), "lateral_bc")
 
     def event_record(self, slot):
         self._ck(self.L.pomgpu_event_record(self.h, slot), "event_record")

@@ -58,6 +58,23 @@ long pomgpu_field_elems(pomgpu_t* ctx, const char* name); /* 0 if unknown */
  * goes to a shadow buffer on a copy stream, overlapping the step still running; the data
  * becomes the field's content at the next pomgpu_step / pull / push (buffers are swapped). */
 int pomgpu_push_async(pomgpu_t* ctx, const char* name, const double* host);
+/* Time interpolation of the forcing on the device.  The reference reads a new
+ * record every iwind / iheat / ibc internal steps but interpolates `x = fold*xb + fnew*xf`,
+ * fold = 1.-fnew, on the host EVERY step (pom/bounds_forcing.f:841-865 lateral_bc, :904-909 wind,
+ * :949-957 heat).  Here the driver pushes a record only when the reference reads one:
+ *   pomgpu_push_record(ctx,"wusurf",slot,host)  slot 0 = older record (wusurfb), 1 = newer (wusurff);
+ *                                               asynchronous when `host` is page-locked;
+ *   pomgpu_rotate_record(ctx,"wusurf")          `wusurfb = wusurff` (:888-893) as a pointer swap;
+ * and calls, every step, with fnew computed exactly as the reference does (time/twind-ntime):
+ *   pomgpu_wind (wusurf,wvsurf), pomgpu_heat (wtsurf,swrad), pomgpu_lateral_bc (tbw,sbw,ubw,tbe,sbe,ube,
+ *   tbn,sbn,vbn,tbs,sbs,vbs and the depth integrals uabw,uabe,vabn,vabs), or pomgpu_interp for one field.
+ * Fields are shaped like pomgpu_push's (local rows of a strip).  Returns 2 if a record is missing. */
+int pomgpu_push_record(pomgpu_t* ctx, const char* name, int slot, const double* host);
+int pomgpu_rotate_record(pomgpu_t* ctx, const char* name);
+int pomgpu_interp(pomgpu_t* ctx, const char* name, double fnew);
+int pomgpu_wind(pomgpu_t* ctx, double fnew);
+int pomgpu_heat(pomgpu_t* ctx, double fnew);
+int pomgpu_lateral_bc(pomgpu_t* ctx, double fnew);
 int pomgpu_pin_host(void* ptr, unsigned long bytes);
 int pomgpu_unpin_host(void* ptr);
 

@@ -42,16 +42,19 @@ extern "C" {
   X(egb) X(egf) X(el) X(elb) X(elf) X(et) X(etb) X(etf) X(fluxua) X(fluxva) \
   X(fsm) X(h) X(swrad) X(ssurf) X(tsurf) X(tps) X(ua) X(uab) X(uaf) X(utb) \
   X(utf) X(va) X(vab) X(vaf) X(vtb) X(vtf) X(vfluxb) X(vfluxf) X(wssurf) \
-  X(wtsurf) X(wubot) X(wusurf) X(wvbot) X(wvsurf)
+  X(wtsurf) X(wubot) X(wusurf) X(wvbot) X(wvsurf) \
+  X(wusurfb) X(wusurff) X(wvsurfb) X(wvsurff) X(wtsurfb) X(wtsurff) X(swradb) X(swradf)
 
 /* boundary arrays: (jm) */
 #define POMO_BJ(X) X(ele) X(elw) X(uabe) X(uabw) X(vabe) X(vabw)
 /* (im) */
 #define POMO_BI(X) X(eln) X(els) X(vabn) X(vabs) X(uabn) X(uabs)
 /* (jm,kb) */
-#define POMO_BJK(X) X(tbe) X(sbe) X(tbw) X(sbw)
+#define POMO_BJK(X) X(tbe) X(sbe) X(tbw) X(sbw) X(ube) X(ubw) \
+  X(tbeb) X(tbef) X(sbeb) X(sbef) X(ubeb) X(ubef) X(tbwb) X(tbwf) X(sbwb) X(sbwf) X(ubwb) X(ubwf)
 /* (im,kb) */
-#define POMO_BIK(X) X(tbn) X(sbn) X(tbs) X(sbs)
+#define POMO_BIK(X) X(tbn) X(sbn) X(tbs) X(sbs) X(vbn) X(vbs) \
+  X(tbnb) X(tbnf) X(sbnb) X(sbnf) X(vbnb) X(vbnf) X(tbsb) X(tbsf) X(sbsb) X(sbsf) X(vbsb) X(vbsf)
 /* (kb) */
 #define POMO_F1D(X) X(z) X(zz) X(dz) X(dzz)
 
@@ -98,6 +101,10 @@ void pomo_mode_internal(pomo_t *S);
 void pomo_internal_stage(pomo_t *S, int stage); /* blocks of advance.f:356-537 */
 double pomo_check_velocity(pomo_t *S); /* advance.f:611-641, returns vamax */
 void pomo_baropg_mcc(pomo_t *S);   /* solver.f:943-1159 (npg=2) */
+/* the per-step time interpolation of the forcing records (the file reads around it are out of scope) */
+void pomo_wind_interp(pomo_t *S, double fnew);        /* bounds_forcing.f:904-909 */
+void pomo_heat_interp(pomo_t *S, double fnew);        /* bounds_forcing.f:949-957 */
+void pomo_lateral_bc_interp(pomo_t *S, double fnew);  /* bounds_forcing.f:841-865 */
 void pomo_domain_stats(pomo_t *S, double *out8); /* advance.f:644-755: vtot atot mtot stot tavg savg eavg ekin */
 /* solver.f */
 void pomo_advave(pomo_t *S);
@@ -222,6 +229,7 @@ void pomo_restore_interior(pomo_t *S);
 #define vtf(i, j) (S->vtf[I2(i, j)])
 #define vfluxb(i, j) (S->vfluxb[I2(i, j)])
 #define vfluxf(i, j) (S->vfluxf[I2(i, j)])
+#define wtsurf(i, j) (S->wtsurf[I2(i, j)])
 #define wubot(i, j) (S->wubot[I2(i, j)])
 #define wusurf(i, j) (S->wusurf[I2(i, j)])
 #define wvbot(i, j) (S->wvbot[I2(i, j)])
@@ -247,6 +255,42 @@ void pomo_restore_interior(pomo_t *S);
 #define sbn(i, k) (S->sbn[(size_t)((i)-1) + (size_t)im * ((k)-1)])
 #define tbs(i, k) (S->tbs[(size_t)((i)-1) + (size_t)im * ((k)-1)])
 #define sbs(i, k) (S->sbs[(size_t)((i)-1) + (size_t)im * ((k)-1)])
+#define tbeb(j, k) (S->tbeb[(size_t)((j)-1) + (size_t)jm * ((k)-1)])
+#define tbef(j, k) (S->tbef[(size_t)((j)-1) + (size_t)jm * ((k)-1)])
+#define sbeb(j, k) (S->sbeb[(size_t)((j)-1) + (size_t)jm * ((k)-1)])
+#define sbef(j, k) (S->sbef[(size_t)((j)-1) + (size_t)jm * ((k)-1)])
+#define ubeb(j, k) (S->ubeb[(size_t)((j)-1) + (size_t)jm * ((k)-1)])
+#define ubef(j, k) (S->ubef[(size_t)((j)-1) + (size_t)jm * ((k)-1)])
+#define tbwb(j, k) (S->tbwb[(size_t)((j)-1) + (size_t)jm * ((k)-1)])
+#define tbwf(j, k) (S->tbwf[(size_t)((j)-1) + (size_t)jm * ((k)-1)])
+#define sbwb(j, k) (S->sbwb[(size_t)((j)-1) + (size_t)jm * ((k)-1)])
+#define sbwf(j, k) (S->sbwf[(size_t)((j)-1) + (size_t)jm * ((k)-1)])
+#define ubwb(j, k) (S->ubwb[(size_t)((j)-1) + (size_t)jm * ((k)-1)])
+#define ubwf(j, k) (S->ubwf[(size_t)((j)-1) + (size_t)jm * ((k)-1)])
+#define ube(j, k) (S->ube[(size_t)((j)-1) + (size_t)jm * ((k)-1)])
+#define ubw(j, k) (S->ubw[(size_t)((j)-1) + (size_t)jm * ((k)-1)])
+#define tbnb(i, k) (S->tbnb[(size_t)((i)-1) + (size_t)im * ((k)-1)])
+#define tbnf(i, k) (S->tbnf[(size_t)((i)-1) + (size_t)im * ((k)-1)])
+#define sbnb(i, k) (S->sbnb[(size_t)((i)-1) + (size_t)im * ((k)-1)])
+#define sbnf(i, k) (S->sbnf[(size_t)((i)-1) + (size_t)im * ((k)-1)])
+#define vbnb(i, k) (S->vbnb[(size_t)((i)-1) + (size_t)im * ((k)-1)])
+#define vbnf(i, k) (S->vbnf[(size_t)((i)-1) + (size_t)im * ((k)-1)])
+#define tbsb(i, k) (S->tbsb[(size_t)((i)-1) + (size_t)im * ((k)-1)])
+#define tbsf(i, k) (S->tbsf[(size_t)((i)-1) + (size_t)im * ((k)-1)])
+#define sbsb(i, k) (S->sbsb[(size_t)((i)-1) + (size_t)im * ((k)-1)])
+#define sbsf(i, k) (S->sbsf[(size_t)((i)-1) + (size_t)im * ((k)-1)])
+#define vbsb(i, k) (S->vbsb[(size_t)((i)-1) + (size_t)im * ((k)-1)])
+#define vbsf(i, k) (S->vbsf[(size_t)((i)-1) + (size_t)im * ((k)-1)])
+#define vbn(i, k) (S->vbn[(size_t)((i)-1) + (size_t)im * ((k)-1)])
+#define vbs(i, k) (S->vbs[(size_t)((i)-1) + (size_t)im * ((k)-1)])
+#define wusurfb(i, j) (S->wusurfb[I2(i, j)])
+#define wusurff(i, j) (S->wusurff[I2(i, j)])
+#define wvsurfb(i, j) (S->wvsurfb[I2(i, j)])
+#define wvsurff(i, j) (S->wvsurff[I2(i, j)])
+#define wtsurfb(i, j) (S->wtsurfb[I2(i, j)])
+#define wtsurff(i, j) (S->wtsurff[I2(i, j)])
+#define swradb(i, j) (S->swradb[I2(i, j)])
+#define swradf(i, j) (S->swradf[I2(i, j)])
 /* 1-D */
 #define z(k) (S->z[(k)-1])
 #define zz(k) (S->zz[(k)-1])

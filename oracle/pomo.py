@@ -22,11 +22,11 @@ F3D = ("aam advx advy drhox drhoy dtef kh km kq l q2b q2 q2lb q2l rho rmean sb s
 F2D = ("aam2d advua advva adx2d ady2d art aru arv cbc cor d drx2d dry2d dt dum dvm dx dy "
        "e_atmos egb egf el elb elf et etb etf fluxua fluxva fsm h swrad ssurf tsurf tps ua "
        "uab uaf utb utf va vab vaf vtb vtf vfluxb vfluxf wssurf wtsurf wubot wusurf wvbot "
-       "wvsurf").split()
+       "wvsurf wusurfb wusurff wvsurfb wvsurff wtsurfb wtsurff swradb swradf").split()
 BJ = "ele elw uabe uabw vabe vabw".split()
 BI = "eln els vabn vabs uabn uabs".split()
-BJK = "tbe sbe tbw sbw".split()
-BIK = "tbn sbn tbs sbs".split()
+BJK = ("tbe sbe tbw sbw ube ubw tbeb tbef sbeb sbef ubeb ubef tbwb tbwf sbwb sbwf ubwb ubwf").split()
+BIK = ("tbn sbn tbs sbs vbn vbs tbnb tbnf sbnb sbnf vbnb vbnf tbsb tbsf sbsb sbsf vbsb vbsf").split()
 F1D = "z zz dz dzz".split()
 
 
@@ -67,6 +67,8 @@ def lib():
         L.pomo_bcond.argtypes = [P, C.c_int]
         L.pomo_bcondorl.argtypes = [P, C.c_int]
         L.pomo_internal_stage.argtypes = [P, C.c_int]
+        for n in ("wind_interp", "heat_interp", "lateral_bc_interp"):
+            getattr(L, "pomo_" + n).argtypes = [P, C.c_double]
         _LIB = L
     return _LIB
 
@@ -151,6 +153,16 @@ class Oracle:
         self.L.pomo_domain_stats(self.h, out)
         return dict(zip("vtot atot mtot stot tavg savg eavg ekin".split(), list(out)))
 
+    # forcing records (bounds_forcing.f:841-865,904-909,949-957): same surface as PomGpu
+    def put_record(self, name, slot, arr):
+        self.put(name + "bf"[slot], arr)
+
+    def rotate_record(self, name):
+        self.put(name + "b", self.get(name + "f"))   # `wusurfb = wusurff`
+
+    def wind(self, fnew): self.L.pomo_wind_interp(self.h, fnew)
+    def heat(self, fnew): self.L.pomo_heat_interp(self.h, fnew)
+    def lateral_bc(self, fnew): self.L.pomo_lateral_bc_interp(self.h, fnew)
     def baropg_mcc(self): self.L.pomo_baropg_mcc(self.h)
     def lateral_viscosity(self): self.L.pomo_lateral_viscosity(self.h)
     def mode_interaction(self): self.L.pomo_mode_interaction(self.h)

@@ -294,3 +294,53 @@ void pomo_restore_interior(pomo_t *S) {
     sb(i,j,k)=sb(i,j,k)*fsm(i,j);
   }
 }
+
+/* ---- per-step time interpolation of the forcing records ------------------------
+ * The reads (read_wind_pnetcdf etc.) and the record bookkeeping stay in the Fortran
+ * driver; fnew = time/twind - ntime is computed there and passed in. */
+
+/* bounds_forcing.f:904-909 (subroutine wind) */
+void pomo_wind_interp(pomo_t *S, double fnew) {
+  DIMS;
+  double fold = 1. - fnew;
+  DO(j, 1, jm) DO(i, 1, im) wusurf(i,j)=fold*wusurfb(i,j)+fnew*wusurff(i,j);
+  DO(j, 1, jm) DO(i, 1, im) wvsurf(i,j)=fold*wvsurfb(i,j)+fnew*wvsurff(i,j);
+}
+
+/* bounds_forcing.f:949-957 (subroutine heat) */
+void pomo_heat_interp(pomo_t *S, double fnew) {
+  DIMS;
+  double fold = 1. - fnew;
+  DO(i, 1, im) DO(j, 1, jm) {
+    wtsurf(i,j)=fold*wtsurfb(i,j)+fnew*wtsurff(i,j);
+    swrad(i,j)=fold*swradb(i,j)+fnew*swradf(i,j);
+  }
+}
+
+/* bounds_forcing.f:841-865 (subroutine lateral_bc) */
+void pomo_lateral_bc_interp(pomo_t *S, double fnew) {
+  DIMS;
+  double fold = 1. - fnew;
+  DO(k, 1, kb) DO(j, 1, jm) tbw(j,k) = fold*tbwb(j,k)+fnew*tbwf(j,k);
+  DO(k, 1, kb) DO(j, 1, jm) sbw(j,k) = fold*sbwb(j,k)+fnew*sbwf(j,k);
+  DO(k, 1, kb) DO(j, 1, jm) ubw(j,k) = fold*ubwb(j,k)+fnew*ubwf(j,k);
+  DO(k, 1, kb) DO(j, 1, jm) tbe(j,k) = fold*tbeb(j,k)+fnew*tbef(j,k);
+  DO(k, 1, kb) DO(j, 1, jm) sbe(j,k) = fold*sbeb(j,k)+fnew*sbef(j,k);
+  DO(k, 1, kb) DO(j, 1, jm) ube(j,k) = fold*ubeb(j,k)+fnew*ubef(j,k);
+  DO(k, 1, kb) DO(i, 1, im) tbn(i,k) = fold*tbnb(i,k)+fnew*tbnf(i,k);
+  DO(k, 1, kb) DO(i, 1, im) sbn(i,k) = fold*sbnb(i,k)+fnew*sbnf(i,k);
+  DO(k, 1, kb) DO(i, 1, im) vbn(i,k) = fold*vbnb(i,k)+fnew*vbnf(i,k);
+  DO(k, 1, kb) DO(i, 1, im) tbs(i,k) = fold*tbsb(i,k)+fnew*tbsf(i,k);
+  DO(k, 1, kb) DO(i, 1, im) sbs(i,k) = fold*sbsb(i,k)+fnew*sbsf(i,k);
+  DO(k, 1, kb) DO(i, 1, im) vbs(i,k) = fold*vbsb(i,k)+fnew*vbsf(i,k);
+  DO(j, 1, jm) uabe(j) = 0.;
+  DO(j, 1, jm) uabw(j) = 0.;
+  DO(i, 1, im) vabn(i) = 0.;
+  DO(i, 1, im) vabs(i) = 0.;
+  DO(k, 1, kb) {
+    DO(j, 1, jm) uabe(j) = uabe(j) + ube(j,k)*dz(k);
+    DO(j, 1, jm) uabw(j) = uabw(j) + ubw(j,k)*dz(k);
+    DO(i, 1, im) vabn(i) = vabn(i) + vbn(i,k)*dz(k);
+    DO(i, 1, im) vabs(i) = vabs(i) + vbs(i,k)*dz(k);
+  }
+}

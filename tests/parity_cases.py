@@ -219,3 +219,69 @@ def check_domain_stats(factory, dims=(26, 21, 10), nstep=4):
     vol = (f["dx"] * f["dy"] * f["fsm"] * g.get("dt"))[1:-1, 1:-1].sum() * f["dz"][:-1].sum()
     assert abs(vol - b["vtot"]) <= 1e-10 * vol
     return b
+
+
+def check_forcing_interp(factory, dims=(24, 19, 9), nstep=8):
+    """Time interpolation of the forcing / open-boundary records on the device
+    (bounds_forcing.f:841-865 lateral_bc, :904-909 wind, :949-957 heat).  The driver pushes a record
+    only when the reference reads one and rotates `xb = xf`; every step both sides interpolate with
+    fnew computed as the reference does (incl. its single-precision `tbc=1./24.`).  The
+    interpolated arrays must agree BITWISE with the oracle and with a direct numpy evaluation, and
+    the model state driven by them must stay in parity."""
+    st, o, g = pair(factory, dims, island=True)
+    im, jm, kb = dims
+    rng = np.random.default_rng(11)
+    f = st["fields"]
+    surf = {"wusurf": 1e-4, "wvsurf": 1e-4, "wtsurf": 1e-5, "swrad": 1e-5}
+    edge_t = {"tbw": f["tbw"], "tbe": f["tbe"], "tbn": f["tbn"], "tbs": f["tbs"]}
+    edge_s = {"sbw": f["sbw"], "sbe": f["sbe"], "sbn": f["sbn"], "sbs": f["sbs"]}
+    edge_u = {"ubw": (jm, kb), "ube": (jm, kb), "vbn": (im, kb), "vbs": (im, kb)}
+
+    def record():
+        r = {}
+        for n, amp in surf.items():
+            r[n] = np.asfortranarray(-amp * rng.random((im, jm)))
+        for n, base in {**edge_t, **edge_s}.items():
+            r[n] = np.asfortranarray(base + 0.05 * rng.standard_normal(base.shape))
+        for n, shp in edge_u.items():
+            r[n] = np.asfortranarray((0.2 if n[0] == "u" else 0.0) + 0.01 * rng.standard_normal(shp))
+        return r
+
+    names = list(surf) + list(edge_t) + list(edge_s) + list(edge_u)
+    rec_b, rec_f = record(), record()
+    for s in (o, g):
+        for n in names:
+            s.put_record(n, 0, rec_b[n]); s.put_record(n, 1, rec_f[n])
+    dti = o.getc("dti")
+    twind, tbc = 0.125, float(np.float32(1.0) / np.float32(24.0))   # bounds_forcing.f:877,922,607
+    period = 3                                                       # steps between records in this test
+    dz = f["dz"]
+    for i in range(1, nstep + 1):
+        if i > 1 and (i - 1) % period == 0:      # `if (mod(iint,iwind).eq.0)`: xb = xf, read the next record
+            rec_b, rec_f = rec_f, record()
+            for s in (o, g):
+                for n in names:
+                    s.rotate_record(n); s.put_record(n, 1, rec_f[n])
+        time = dti * float(i) / 86400.0
+        # fnew = time/twind - ntime with a record interval shrunk to `period` steps
+        tw = twind * (period * dti / 86400.0) / twind
+        fw = time / tw - int(time / tw)
+        tb_ = tbc * (period * dti / 86400.0) / tbc
+        fb = time / tb_ - float(int(time / tb_))
+        for s in (o, g):
+            s.wind(fw); s.heat(fw); s.lateral_bc(fb)
+        for n in names:
+            fn = fb if n in edge_t or n in edge_s or n in edge_u else fw
+            want = (1.0 - fn) * rec_b[n] + fn * rec_f[n]
+            a, b = o.get(n), g.get(n)
+            assert np.array_equal(a, want), n
+            assert np.array_equal(a, b), n
+        for n, src in (("uabw", "ubw"), ("uabe", "ube"), ("vabn", "vbn"), ("vabs", "vbs")):
+            acc = np.zeros(o.get(n).shape)
+            u = o.get(src)
+            for k in range(kb):
+                acc = acc + u[:, k] * dz[k]
+            assert np.array_equal(o.get(n), acc), n
+            assert np.array_equal(o.get(n), g.get(n)), n
+        o.step(i); g.step(i)
+    return assert_close(o, g)

@@ -47,3 +47,7 @@ def test_restore_interior_matches_oracle():
 
 def test_domain_stats_matches_oracle():
     pc.check_domain_stats(EmuPom)
+
+
+def test_forcing_interpolation_matches_oracle():
+    pc.check_forcing_interp(EmuPom)

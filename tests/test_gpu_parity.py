@@ -151,3 +151,7 @@ def test_restore_interior_matches_oracle():
 
 def test_domain_stats_matches_oracle():
     pc.check_domain_stats(_factory)
+
+
+def test_forcing_interpolation_matches_oracle():
+    pc.check_forcing_interp(_factory)

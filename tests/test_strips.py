@@ -151,3 +151,35 @@ def test_bandwise_loading_equals_whole_loading():
             grp.step(i)
     for n in F3 + F2:
         assert np.array_equal(a.get(n), b.get(n)), n
+
+
+def test_forcing_interpolation_on_strips():
+    """Device-side time interpolation (bounds_forcing.f:841-865,904-909,949-957) per strip: every strip
+    holds the records of its own rows; the result equals the single-domain run bitwise."""
+    dims, nstep = (20, 30, 7), 4
+    im, jm, kb = dims
+    rng = np.random.default_rng(3)
+    whole = _whole(dims, 0)
+    grp = _group(dims, 2, 3)
+    shapes = {"wusurf": (im, jm), "wvsurf": (im, jm), "wtsurf": (im, jm), "swrad": (im, jm)}
+    for e in ("w", "e"):
+        shapes.update({"tb" + e: (jm, kb), "sb" + e: (jm, kb), "ub" + e: (jm, kb)})
+    for e in ("n", "s"):
+        shapes.update({"tb" + e: (im, kb), "sb" + e: (im, kb), "vb" + e: (im, kb)})
+    base = {"t": 10.0, "s": 35.0, "u": 0.2, "v": 0.0, "w": 0.0}
+    rec = [{n: np.asfortranarray(base[n[0]] + (1e-4 if n[0] == "w" else 1e-2) * rng.standard_normal(s))
+            for n, s in shapes.items()} for _ in range(2)]
+    for g in [whole] + grp.strips:
+        for n in shapes:
+            g.put_record(n, 0, rec[0][n]); g.put_record(n, 1, rec[1][n])
+    for i in range(1, nstep + 1):
+        fnew = i / float(nstep + 1)
+        for g in [whole] + grp.strips:
+            g.wind(fnew); g.heat(fnew); g.lateral_bc(fnew)
+        whole.step(i); grp.step(i)
+    _assert_same(whole, grp)
+    for n in ("wusurf", "wtsurf"):
+        assert np.array_equal(whole.get(n), grp.gather(n))
+    for s in grp.strips:
+        assert np.array_equal(whole.get("uabw")[s.joff:s.joff + s.jml], s.get("uabw"))
+        assert np.array_equal(whole.get("vabn"), s.get("vabn"))
