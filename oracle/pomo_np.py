@@ -1,4 +1,4 @@
-"""A SECOND, independent restatement (numpy) of a subset of the reference routines.
+"""A SECOND, independent restatement (numpy) of the WHOLE hot path.
 
 TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED (see oracle/pomo.h).  The reference cannot be
 compiled here, so the C oracle is itself a restatement; this module restates
@@ -6,12 +6,18 @@ compiled here, so the C oracle is itself a restatement; this module restates
     vertvl  pom/solver.f:1970-2021      advq    pom/solver.f:411-477
     advave  pom/solver.f:6-121          proft   pom/solver.f:1541-1683
     profq   pom/solver.f:1212-1538      advt2 + smol_adif  pom/solver.f:577-731,1880-1967
-    baropg_mcc  pom/solver.f:943-1159
+    baropg_mcc  pom/solver.f:943-1159   advct   pom/solver.f:201-409
+    advu / advv   pom/solver.f:734-845  profu / profv  pom/solver.f:1686-1877
+    realvertvl    pom/solver.f:2024-2066
     mode_external + bcond(1), bcond(2)  pom/advance.f:205-353, pom/bounds_forcing.f:18-83
+    lateral_viscosity, mode_interaction, mode_internal  pom/advance.f:96-202,356-537
+    bcond(4), bcond(6), bcondorl(3), bcondorl(5)  pom/bounds_forcing.f:151-324,418-487,550-561
+and `step` = pom/advance.f:21-32,
 a second time, written from the Fortran text with whole-array slices instead of loops, and
-tests/test_oracle_np.py requires the two restatements to agree BITWISE (same IEEE operations in
-the same order; numpy does not contract to FMA).  A transcription slip would have to be made
-twice, in two different notations, to go unnoticed.
+tests/test_oracle_np.py requires the two restatements to agree BITWISE -- routine by routine and
+for whole internal steps (same IEEE operations in the same order; numpy does not contract to
+FMA).  A transcription slip would have to be made twice, in two different notations, to go
+unnoticed.
 
 Arrays are (im,jm[,kb]) Fortran-ordered; `sl(a,b)` is the Fortran index range a:b (1-based,
 inclusive), optionally shifted: x[sl(2,imm1,-1), ...] is x(i-1,...) for i=2..imm1.
@@ -597,3 +603,466 @@ def baropg_mcc(f, c, rho_in, drhox0, drhoy0):
     drhox[I, J, :] = c["ramp"] * drhox[I, J, :]
     drhoy[I, J, :] = c["ramp"] * drhoy[I, J, :]
     return drhox, drhoy, rho + f["rmean"]
+
+
+# ---------------------------------------------------------------------------------------------
+# Second batch: the momentum path.  R(x, I, J, di, dj) is x(i+di, j+dj, 1:kbm1) for i in I=(a,b),
+# j in J=(c,d) (Fortran 1-based inclusive ranges); 2-D operands get a trailing axis for broadcast.
+def _R(x, I, J, di=0, dj=0, kbm1=None):
+    a = x[I[0] - 1 + di:I[1] + di, J[0] - 1 + dj:J[1] + dj]
+    if x.ndim == 2:
+        return a[:, :, None]
+    return a[:, :, :kbm1]
+
+
+def advct(f, c):
+    """pom/solver.f:201-409 -> (advx, advy); one sub-domain (n_west = n_south = -1)."""
+    u, v, ub, vb, aam, dt, dx, dy, aru, arv = (f[n] for n in "u v ub vb aam dt dx dy aru arv".split())
+    im, jm, kb = u.shape
+    imm1, jmm1, kbm1 = im - 1, jm - 1, kb - 1
+    Z = lambda: np.zeros((im, jm, kb), order="F")
+
+    def R(x, I, J, di=0, dj=0):
+        return _R(x, I, J, di, dj, kbm1)
+
+    def W(x, I, J):       # assignable view x(I, J, 1:kbm1)
+        return x[I[0] - 1:I[1], J[0] - 1:J[1], :kbm1]
+
+    curv, advx, xflux, yflux = Z(), Z(), Z(), Z()
+    I, J = (2, imm1), (2, jmm1)
+    W(curv, I, J)[...] = (.25 * ((R(v, I, J, 0, 1) + R(v, I, J)) * (R(dy, I, J, 1, 0) - R(dy, I, J, -1, 0))
+                                 - (R(u, I, J, 1, 0) + R(u, I, J)) * (R(dx, I, J, 0, 1) - R(dx, I, J, 0, -1)))
+                          / (R(dx, I, J) * R(dy, I, J)))
+    # x-component: advective fluxes
+    I, J = (2, imm1), (1, jm)
+    W(xflux, I, J)[...] = (.125 * ((R(dt, I, J, 1, 0) + R(dt, I, J)) * R(u, I, J, 1, 0)
+                                   + (R(dt, I, J) + R(dt, I, J, -1, 0)) * R(u, I, J))
+                           * (R(u, I, J, 1, 0) + R(u, I, J)))
+    I, J = (2, im), (2, jm)
+    W(yflux, I, J)[...] = (.125 * ((R(dt, I, J) + R(dt, I, J, 0, -1)) * R(v, I, J)
+                                   + (R(dt, I, J, -1, 0) + R(dt, I, J, -1, -1)) * R(v, I, J, -1, 0))
+                           * (R(u, I, J) + R(u, I, J, 0, -1)))
+    # diffusive fluxes
+    I, J = (2, imm1), (2, jm)
+    W(xflux, I, J)[...] = (R(xflux, I, J)
+                           - R(dt, I, J) * R(aam, I, J) * 2. * (R(ub, I, J, 1, 0) - R(ub, I, J)) / R(dx, I, J))
+    dtaam = (.25 * (R(dt, I, J) + R(dt, I, J, -1, 0) + R(dt, I, J, 0, -1) + R(dt, I, J, -1, -1))
+             * (R(aam, I, J) + R(aam, I, J, -1, 0) + R(aam, I, J, 0, -1) + R(aam, I, J, -1, -1)))
+    W(yflux, I, J)[...] = (R(yflux, I, J)
+                           - dtaam * ((R(ub, I, J) - R(ub, I, J, 0, -1))
+                                      / (R(dy, I, J) + R(dy, I, J, -1, 0) + R(dy, I, J, 0, -1) + R(dy, I, J, -1, -1))
+                                      + (R(vb, I, J) - R(vb, I, J, -1, 0))
+                                      / (R(dx, I, J) + R(dx, I, J, -1, 0) + R(dx, I, J, 0, -1) + R(dx, I, J, -1, -1))))
+    W(xflux, I, J)[...] = R(dy, I, J) * R(xflux, I, J)
+    W(yflux, I, J)[...] = (.25 * (R(dx, I, J) + R(dx, I, J, -1, 0) + R(dx, I, J, 0, -1) + R(dx, I, J, -1, -1))
+                           * R(yflux, I, J))
+    I, J = (2, imm1), (2, jmm1)
+    W(advx, I, J)[...] = R(xflux, I, J) - R(xflux, I, J, -1, 0) + R(yflux, I, J, 0, 1) - R(yflux, I, J)
+    I = (3, imm1)                                   # n_west == -1
+    W(advx, I, J)[...] = (R(advx, I, J)
+                          - R(aru, I, J) * .25
+                          * (R(curv, I, J) * R(dt, I, J) * (R(v, I, J, 0, 1) + R(v, I, J))
+                             + R(curv, I, J, -1, 0) * R(dt, I, J, -1, 0) * (R(v, I, J, -1, 1) + R(v, I, J, -1, 0))))
+    # y-component
+    advy, xflux, yflux = Z(), Z(), Z()
+    I, J = (2, im), (2, jm)
+    W(xflux, I, J)[...] = (.125 * ((R(dt, I, J) + R(dt, I, J, -1, 0)) * R(u, I, J)
+                                   + (R(dt, I, J, 0, -1) + R(dt, I, J, -1, -1)) * R(u, I, J, 0, -1))
+                           * (R(v, I, J) + R(v, I, J, -1, 0)))
+    I, J = (1, im), (2, jmm1)
+    W(yflux, I, J)[...] = (.125 * ((R(dt, I, J, 0, 1) + R(dt, I, J)) * R(v, I, J, 0, 1)
+                                   + (R(dt, I, J) + R(dt, I, J, 0, -1)) * R(v, I, J))
+                           * (R(v, I, J, 0, 1) + R(v, I, J)))
+    I, J = (2, im), (2, jmm1)
+    dtaam = (.25 * (R(dt, I, J) + R(dt, I, J, -1, 0) + R(dt, I, J, 0, -1) + R(dt, I, J, -1, -1))
+             * (R(aam, I, J) + R(aam, I, J, -1, 0) + R(aam, I, J, 0, -1) + R(aam, I, J, -1, -1)))
+    W(xflux, I, J)[...] = (R(xflux, I, J)
+                           - dtaam * ((R(ub, I, J) - R(ub, I, J, 0, -1))
+                                      / (R(dy, I, J) + R(dy, I, J, -1, 0) + R(dy, I, J, 0, -1) + R(dy, I, J, -1, -1))
+                                      + (R(vb, I, J) - R(vb, I, J, -1, 0))
+                                      / (R(dx, I, J) + R(dx, I, J, -1, 0) + R(dx, I, J, 0, -1) + R(dx, I, J, -1, -1))))
+    W(yflux, I, J)[...] = (R(yflux, I, J)
+                           - R(dt, I, J) * R(aam, I, J) * 2. * (R(vb, I, J, 0, 1) - R(vb, I, J)) / R(dy, I, J))
+    W(xflux, I, J)[...] = (.25 * (R(dy, I, J) + R(dy, I, J, -1, 0) + R(dy, I, J, 0, -1) + R(dy, I, J, -1, -1))
+                           * R(xflux, I, J))
+    W(yflux, I, J)[...] = R(dx, I, J) * R(yflux, I, J)
+    I, J = (2, imm1), (2, jmm1)
+    W(advy, I, J)[...] = R(xflux, I, J, 1, 0) - R(xflux, I, J) + R(yflux, I, J) - R(yflux, I, J, 0, -1)
+    J = (3, jmm1)                                   # n_south == -1
+    W(advy, I, J)[...] = (R(advy, I, J)
+                          + R(arv, I, J) * .25
+                          * (R(curv, I, J) * R(dt, I, J) * (R(u, I, J, 1, 0) + R(u, I, J))
+                             + R(curv, I, J, 0, -1) * R(dt, I, J, 0, -1) * (R(u, I, J, 1, -1) + R(u, I, J, 0, -1))))
+    return advx, advy
+
+
+def smagorinsky(f, c):
+    """lateral_viscosity's aam (pom/advance.f:122-136); boundary cells keep f['aam']."""
+    u, v, dx, dy = f["u"], f["v"], f["dx"], f["dy"]
+    im, jm, kb = u.shape
+    kbm1 = kb - 1
+    I, J = (2, im - 1), (2, jm - 1)
+    R = lambda x, di=0, dj=0: _R(x, I, J, di, dj, kbm1)
+    aam = f["aam"].copy(order="F")
+    aam[1:im - 1, 1:jm - 1, :kbm1] = (
+        c["horcon"] * R(dx) * R(dy)
+        * np.sqrt(((R(u, 1, 0) - R(u)) / R(dx)) ** 2
+                  + ((R(v, 0, 1) - R(v)) / R(dy)) ** 2
+                  + .5 * (.25 * (R(u, 0, 1) + R(u, 1, 1) - R(u, 0, -1) - R(u, 1, -1)) / R(dy)
+                          + .25 * (R(v, 1, 0) + R(v, 1, 1) - R(v, -1, 0) - R(v, -1, 1)) / R(dx)) ** 2))
+    return aam
+
+
+def advu(f, c):
+    """pom/solver.f:734-788 -> uf."""
+    u, v, w, ub, advx, drhox = (f[n] for n in "u v w ub advx drhox".split())
+    aru, cor, dt, dy, egf, egb, ea, h, etb, etf, dz = (f[n] for n in "aru cor dt dy egf egb e_atmos h etb etf dz".split())
+    im, jm, kb = u.shape
+    imm1, jmm1, kbm1 = im - 1, jm - 1, kb - 1
+    uf = np.zeros((im, jm, kb), order="F")
+    # k=2..kbm1, j=1..jm, i=2..im
+    uf[1:im, :, 1:kbm1] = .25 * (w[1:im, :, 1:kbm1] + w[0:im - 1, :, 1:kbm1]) * (u[1:im, :, 1:kbm1] + u[1:im, :, 0:kbm1 - 1])
+    I, J = (2, imm1), (2, jmm1)
+    R = lambda x, di=0, dj=0: _R(x, I, J, di, dj, kbm1)
+    ufk1 = uf[1:imm1, 1:jmm1, 1:kb]                 # uf(i,j,k+1), k=1..kbm1
+    new = (R(advx)
+           + (R(uf) - ufk1) * R(aru) / dz[None, None, :kbm1]
+           - R(aru) * .25 * (R(cor) * R(dt) * (R(v, 0, 1) + R(v)) + R(cor, -1, 0) * R(dt, -1, 0) * (R(v, -1, 1) + R(v, -1, 0)))
+           + c["grav"] * .125 * (R(dt) + R(dt, -1, 0))
+           * (R(egf) - R(egf, -1, 0) + R(egb) - R(egb, -1, 0) + (R(ea) - R(ea, -1, 0)) * 2.)
+           * (R(dy) + R(dy, -1, 0))
+           + R(drhox))
+    uf[1:imm1, 1:jmm1, :kbm1] = new
+    uf[1:imm1, 1:jmm1, :kbm1] = (((R(h) + R(etb) + R(h, -1, 0) + R(etb, -1, 0)) * R(aru) * R(ub) - 2. * c["dti2"] * R(uf))
+                                 / ((R(h) + R(etf) + R(h, -1, 0) + R(etf, -1, 0)) * R(aru)))
+    return uf
+
+
+def advv(f, c):
+    """pom/solver.f:791-845 -> vf."""
+    u, v, w, vb, advy, drhoy = (f[n] for n in "u v w vb advy drhoy".split())
+    arv, cor, dt, dx, egf, egb, ea, h, etb, etf, dz = (f[n] for n in "arv cor dt dx egf egb e_atmos h etb etf dz".split())
+    im, jm, kb = u.shape
+    imm1, jmm1, kbm1 = im - 1, jm - 1, kb - 1
+    vf = np.zeros((im, jm, kb), order="F")
+    vf[:, 1:jm, 1:kbm1] = .25 * (w[:, 1:jm, 1:kbm1] + w[:, 0:jm - 1, 1:kbm1]) * (v[:, 1:jm, 1:kbm1] + v[:, 1:jm, 0:kbm1 - 1])
+    I, J = (2, imm1), (2, jmm1)
+    R = lambda x, di=0, dj=0: _R(x, I, J, di, dj, kbm1)
+    vfk1 = vf[1:imm1, 1:jmm1, 1:kb]
+    new = (R(advy)
+           + (R(vf) - vfk1) * R(arv) / dz[None, None, :kbm1]
+           + R(arv) * .25 * (R(cor) * R(dt) * (R(u, 1, 0) + R(u)) + R(cor, 0, -1) * R(dt, 0, -1) * (R(u, 1, -1) + R(u, 0, -1)))
+           + c["grav"] * .125 * (R(dt) + R(dt, 0, -1))
+           * (R(egf) - R(egf, 0, -1) + R(egb) - R(egb, 0, -1) + (R(ea) - R(ea, 0, -1)) * 2.)
+           * (R(dx) + R(dx, 0, -1))
+           + R(drhoy))
+    vf[1:imm1, 1:jmm1, :kbm1] = new
+    vf[1:imm1, 1:jmm1, :kbm1] = (((R(h) + R(etb) + R(h, 0, -1) + R(etb, 0, -1)) * R(arv) * R(vb) - 2. * c["dti2"] * R(vf))
+                                 / ((R(h) + R(etf) + R(h, 0, -1) + R(etf, 0, -1)) * R(arv)))
+    return vf
+
+
+def _prof_uv(f, c, xf_in, km, wsurf, mask, tps, di, dj):
+    """Shared skeleton of profu / profv (pom/solver.f:1686-1780, 1783-1877): (i-di, j-dj) is the
+    neighbour that is averaged with; tps (the drag coefficient * speed) is computed by the caller."""
+    h, etf, dz, dzz = f["h"], f["etf"], f["dz"], f["dzz"]
+    im, jm, kb = xf_in.shape
+    imm1, jmm1, kbm1, kbm2 = im - 1, jm - 1, kb - 1, kb - 2
+    dti2, umol = c["dti2"], c["umol"]
+    xf = xf_in.copy(order="F")
+    dh = np.ones((im, jm), order="F")
+    if di:
+        dh[1:, 1:] = (h[1:, 1:] + etf[1:, 1:] + h[:-1, 1:] + etf[:-1, 1:]) * .5
+    else:
+        dh[1:, 1:] = .5 * (h[1:, 1:] + etf[1:, 1:] + h[1:, :-1] + etf[1:, :-1])
+    Z = lambda: np.zeros((im, jm, kb), order="F")
+    a, cc, ee, gg = Z(), Z(), Z(), Z()
+    if di:
+        cc[1:, 1:, :] = (km[1:, 1:, :] + km[:-1, 1:, :]) * .5
+    else:
+        cc[1:, 1:, :] = (km[1:, 1:, :] + km[1:, :-1, :]) * .5
+    for k in range(2, kbm1 + 1):
+        a[:, :, k - 2] = -dti2 * (cc[:, :, k - 1] + umol) / (dz[k - 2] * dzz[k - 2] * dh * dh)
+        cc[:, :, k - 1] = -dti2 * (cc[:, :, k - 1] + umol) / (dz[k - 1] * dzz[k - 2] * dh * dh)
+    ee[:, :, 0] = a[:, :, 0] / (a[:, :, 0] - 1.)
+    gg[:, :, 0] = (-dti2 * wsurf / (-dz[0] * dh) - xf[:, :, 0]) / (a[:, :, 0] - 1.)
+    for k in range(2, kbm2 + 1):
+        gg[:, :, k - 1] = 1. / (a[:, :, k - 1] + cc[:, :, k - 1] * (1. - ee[:, :, k - 2]) - 1.)
+        ee[:, :, k - 1] = a[:, :, k - 1] * gg[:, :, k - 1]
+        gg[:, :, k - 1] = (cc[:, :, k - 1] * gg[:, :, k - 2] - xf[:, :, k - 1]) * gg[:, :, k - 1]
+    In = (slice(1, imm1), slice(1, jmm1))
+    xf[In + (kbm1 - 1,)] = ((cc[In + (kbm1 - 1,)] * gg[In + (kbm2 - 1,)] - xf[In + (kbm1 - 1,)])
+                            / (tps * dti2 / (-dz[kbm1 - 1] * dh[In]) - 1. - (ee[In + (kbm2 - 1,)] - 1.) * cc[In + (kbm1 - 1,)]))
+    xf[In + (kbm1 - 1,)] = xf[In + (kbm1 - 1,)] * mask[In]
+    for k in range(2, kbm1 + 1):
+        ki = kb - k
+        xf[In + (ki - 1,)] = (ee[In + (ki - 1,)] * xf[In + (ki,)] + gg[In + (ki - 1,)]) * mask[In]
+    wbot = -tps * xf[In + (kbm1 - 1,)]
+    return xf, wbot
+
+
+def profu(f, c, uf_in):
+    """pom/solver.f:1686-1780 -> (uf, wubot interior (2:imm1,2:jmm1))."""
+    cbc, ub, vb = f["cbc"], f["ub"], f["vb"]
+    im, jm, kb = uf_in.shape
+    k = kb - 2          # level kbm1, 0-based
+    I, J = (2, im - 1), (2, jm - 1)
+    r = lambda x, di=0, dj=0: x[I[0] - 1 + di:I[1] + di, J[0] - 1 + dj:J[1] + dj]
+    ubk, vbk = ub[:, :, k], vb[:, :, k]
+    tps = (0.5 * (r(cbc) + r(cbc, -1, 0))
+           * np.sqrt(r(ubk) ** 2 + (.25 * (r(vbk) + r(vbk, 0, 1) + r(vbk, -1, 0) + r(vbk, -1, 1))) ** 2))
+    return _prof_uv(f, c, uf_in, f["km"], f["wusurf"], f["dum"], tps, 1, 0)
+
+
+def profv(f, c, vf_in):
+    """pom/solver.f:1783-1877 -> (vf, wvbot interior)."""
+    cbc, ub, vb = f["cbc"], f["ub"], f["vb"]
+    im, jm, kb = vf_in.shape
+    k = kb - 2
+    I, J = (2, im - 1), (2, jm - 1)
+    r = lambda x, di=0, dj=0: x[I[0] - 1 + di:I[1] + di, J[0] - 1 + dj:J[1] + dj]
+    ubk, vbk = ub[:, :, k], vb[:, :, k]
+    tps = (0.5 * (r(cbc) + r(cbc, 0, -1))
+           * np.sqrt((.25 * (r(ubk) + r(ubk, 1, 0) + r(ubk, 0, -1) + r(ubk, 1, -1))) ** 2 + r(vbk) ** 2))
+    return _prof_uv(f, c, vf_in, f["km"], f["wvsurf"], f["dvm"], tps, 0, 1)
+
+
+def realvertvl(f, c):
+    """pom/solver.f:2024-2066 -> wr (one sub-domain: all four edge copies)."""
+    w, u, v, dt, et, etf, etb, dx, dy, fsm, zz = (f[n] for n in "w u v dt et etf etb dx dy fsm zz".split())
+    im, jm, kb = w.shape
+    imm1, jmm1, kbm1 = im - 1, jm - 1, kb - 1
+    wr = np.zeros((im, jm, kb), order="F")
+    I, J = (2, imm1), (2, jmm1)
+    r = lambda x, di=0, dj=0: x[I[0] - 1 + di:I[1] + di, J[0] - 1 + dj:J[1] + dj]
+    two = np.float64(np.float32(2.0)); half = np.float64(np.float32(0.5)); one = np.float64(np.float32(1.0))
+    for k in range(1, kbm1 + 1):
+        tps = zz[k - 1] * dt + et
+        dxr = two / (r(dx, 1, 0) + r(dx)); dxl = two / (r(dx) + r(dx, -1, 0))
+        dyt = two / (r(dy, 0, 1) + r(dy)); dyb = two / (r(dy) + r(dy, 0, -1))
+        uk, vk = u[:, :, k - 1], v[:, :, k - 1]
+        wr[1:imm1, 1:jmm1, k - 1] = (half * (r(w[:, :, k - 1]) + r(w[:, :, k])) + half
+                                     * (r(uk, 1, 0) * (r(tps, 1, 0) - r(tps)) * dxr
+                                        + r(uk) * (r(tps) - r(tps, -1, 0)) * dxl
+                                        + r(vk, 0, 1) * (r(tps, 0, 1) - r(tps)) * dyt
+                                        + r(vk) * (r(tps) - r(tps, 0, -1)) * dyb)
+                                     + (one + zz[k - 1]) * (r(etf) - r(etb)) / c["dti2"])
+    wr[:, 0, :] = wr[:, 1, :]
+    wr[:, jm - 1, :] = wr[:, jmm1 - 1, :]
+    wr[0, :, :] = wr[1, :, :]
+    wr[im - 1, :, :] = wr[imm1 - 1, :, :]
+    for k in range(1, kbm1 + 1):
+        wr[:, :, k - 1] = fsm * wr[:, :, k - 1]
+    return wr
+
+
+# ---------------------------------------------------------------------------------------------
+# Third batch: the glue of advance.f and the open-boundary routines, so that one whole internal
+# step (pom/advance.f:21-32; mode=3, nadv=2, npg=1, nbct=nbcs=1 or 3, no restoring) exists a second
+# time.  f is a dict of ALL fields, updated in place like the COMMON blocks.
+def _upstream_edges(f, c, A, B, uf, vf, ea, eb, K, vertical):
+    """The four-edge upstream advection shared in FORM (not in code) by bcond(4) and bcond(6) of the
+    reference; written once here with the edge data passed in.  A, B: the two advected fields;
+    ea(side, k) / eb(side, k): the prescribed outside values; K: number of levels."""
+    u, v, w, dx, dy, dt, zz, dti = f["u"], f["v"], f["w"], f["dx"], f["dy"], f["dt"], f["zz"], c["dti"]
+    im, jm, kb = u.shape
+    imm1, jmm1, kbm1 = im - 1, jm - 1, kb - 1
+    for k in range(1, K + 1):
+        z = k - 1
+        mid = vertical and k != 1 and k != kbm1
+        # east (i = im)
+        u1 = 2. * u[im - 1, :, z] * dti / (dx[im - 1, :] + dx[imm1 - 1, :])
+        for X, xf, e in ((A, uf, ea), (B, vf, eb)):
+            inflow = X[im - 1, :, z] - u1 * (e("e", z) - X[im - 1, :, z])
+            out = X[im - 1, :, z] - u1 * (X[im - 1, :, z] - X[imm1 - 1, :, z])
+            if mid:
+                wm = .5 * (w[imm1 - 1, :, z] + w[imm1 - 1, :, z + 1]) * dti / ((zz[z - 1] - zz[z + 1]) * dt[imm1 - 1, :])
+                out = out - wm * (X[imm1 - 1, :, z - 1] - X[imm1 - 1, :, z + 1])
+            xf[im - 1, :, z] = np.where(u1 <= 0., inflow, out)
+        # west (i = 1, velocity at i = 2)
+        u1 = 2. * u[1, :, z] * dti / (dx[0, :] + dx[1, :])
+        for X, xf, e in ((A, uf, ea), (B, vf, eb)):
+            inflow = X[0, :, z] - u1 * (X[0, :, z] - e("w", z))
+            out = X[0, :, z] - u1 * (X[1, :, z] - X[0, :, z])
+            if mid:
+                wm = .5 * (w[1, :, z] + w[1, :, z + 1]) * dti / ((zz[z - 1] - zz[z + 1]) * dt[1, :])
+                out = out - wm * (X[1, :, z - 1] - X[1, :, z + 1])
+            xf[0, :, z] = np.where(u1 >= 0., inflow, out)
+        # south (j = 1, velocity at j = 2)
+        u1 = 2. * v[:, 1, z] * dti / (dy[:, 0] + dy[:, 1])
+        for X, xf, e in ((A, uf, ea), (B, vf, eb)):
+            inflow = X[:, 0, z] - u1 * (X[:, 0, z] - e("s", z))
+            out = X[:, 0, z] - u1 * (X[:, 1, z] - X[:, 0, z])
+            if mid:
+                wm = .5 * (w[:, 1, z] + w[:, 1, z + 1]) * dti / ((zz[z - 1] - zz[z + 1]) * dt[:, 1])
+                out = out - wm * (X[:, 1, z - 1] - X[:, 1, z + 1])
+            xf[:, 0, z] = np.where(u1 >= 0., inflow, out)
+        # north (j = jm)
+        u1 = 2. * v[:, jm - 1, z] * dti / (dy[:, jm - 1] + dy[:, jmm1 - 1])
+        for X, xf, e in ((A, uf, ea), (B, vf, eb)):
+            inflow = X[:, jm - 1, z] - u1 * (e("n", z) - X[:, jm - 1, z])
+            out = X[:, jm - 1, z] - u1 * (X[:, jm - 1, z] - X[:, jmm1 - 1, z])
+            if mid:
+                wm = .5 * (w[:, jmm1 - 1, z] + w[:, jmm1 - 1, z + 1]) * dti / ((zz[z - 1] - zz[z + 1]) * dt[:, jmm1 - 1])
+                out = out - wm * (X[:, jmm1 - 1, z - 1] - X[:, jmm1 - 1, z + 1])
+            xf[:, jm - 1, z] = np.where(u1 <= 0., inflow, out)
+
+
+def bcond4(f, c):
+    """pom/bounds_forcing.f:151-242: T, S open boundaries on uf, vf, then the fsm mask (k=1..kbm1)."""
+    kbm1 = f["u"].shape[2] - 1
+    te = {"e": f["tbe"], "w": f["tbw"], "s": f["tbs"], "n": f["tbn"]}
+    se = {"e": f["sbe"], "w": f["sbw"], "s": f["sbs"], "n": f["sbn"]}
+    _upstream_edges(f, c, f["t"], f["s"], f["uf"], f["vf"], lambda s, z: te[s][:, z], lambda s, z: se[s][:, z], kbm1, True)
+    f["uf"][:, :, :kbm1] = f["uf"][:, :, :kbm1] * f["fsm"][:, :, None]
+    f["vf"][:, :, :kbm1] = f["vf"][:, :, :kbm1] * f["fsm"][:, :, None]
+
+
+def bcond6(f, c):
+    """pom/bounds_forcing.f:257-324: q2, q2l open boundaries on uf, vf (k=1..kb; the reference does
+    west before east here, which only matters for im=1), then `*fsm + 1e-10`."""
+    kb = f["u"].shape[2]
+    small = c["small"]
+    _upstream_edges(f, c, f["q2"], f["q2l"], f["uf"], f["vf"], lambda s, z: small, lambda s, z: small, kb, False)
+    f["uf"][...] = f["uf"] * f["fsm"][:, :, None] + 1.e-10
+    f["vf"][...] = f["vf"] * f["fsm"][:, :, None] + 1.e-10
+
+
+def bcondorl3(f, c):
+    """pom/bounds_forcing.f:418-487: Orlanski radiation on uf, vf, then the dum / dvm masks."""
+    u, v, ub, vb, uf, vf = (f[n] for n in "u v ub vb uf vf".split())
+    im, jm, kb = u.shape
+    kbm1 = kb - 1
+    J = slice(1, jm - 1)      # j = 2..jmm1
+    I = slice(1, im - 1)
+
+    def rad(xf1, xb1, x2, xb0, x1):
+        denom = xf1 + xb1 - 2. * x2
+        denom = np.where(denom == 0., 0.01, denom)
+        cl = (xb1 - xf1) / denom
+        cl = np.where(cl > 1., 1., cl)
+        cl = np.where(cl < 0., 0., cl)
+        return (xb0 * (1. - cl) + 2. * cl * x1) / (1. + cl)
+
+    K = slice(0, kbm1)
+    # east
+    uf[im - 1, J, K] = rad(uf[im - 2, J, K], ub[im - 2, J, K], u[im - 3, J, K], ub[im - 1, J, K], u[im - 2, J, K])
+    vf[im - 1, J, K] = 0.
+    # west
+    uf[1, J, K] = rad(uf[2, J, K], ub[2, J, K], u[3, J, K], ub[1, J, K], u[2, J, K])
+    uf[0, J, K] = uf[1, J, K]
+    vf[0, J, K] = 0.
+    # south
+    vf[I, 1, K] = rad(vf[I, 2, K], vb[I, 2, K], v[I, 3, K], vb[I, 1, K], v[I, 2, K])
+    vf[I, 0, K] = vf[I, 1, K]
+    uf[I, 0, K] = 0.
+    # north
+    vf[I, jm - 1, K] = rad(vf[I, jm - 2, K], vb[I, jm - 2, K], v[I, jm - 3, K], vb[I, jm - 1, K], v[I, jm - 2, K])
+    uf[I, jm - 1, K] = 0.
+    uf[:, :, K] = uf[:, :, K] * f["dum"][:, :, None]
+    vf[:, :, K] = vf[:, :, K] * f["dvm"][:, :, None]
+
+
+def lateral_viscosity(f, c):
+    """pom/advance.f:96-141 (mode /= 2, npg = 1)."""
+    f["advx"], f["advy"] = advct(f, c)
+    f["drhox"], f["drhoy"], f["rho"] = NP(f, c).baropg(f["rho"], f["drhox"], f["drhoy"])
+    f["aam"] = smagorinsky(f, c)
+
+
+def mode_interaction(f, c):
+    """pom/advance.f:144-202."""
+    im, jm, kb = f["u"].shape
+    dz = f["dz"]
+    for n2, n3 in (("adx2d", "advx"), ("ady2d", "advy"), ("drx2d", "drhox"), ("dry2d", "drhoy"), ("aam2d", "aam")):
+        acc = np.zeros((im, jm), order="F")
+        for k in range(kb - 1):
+            acc = acc + f[n3][:, :, k] * dz[k]
+        f[n2] = acc
+    f["advua"], f["advva"] = NP(f, c).advave()
+    f["adx2d"] = f["adx2d"] - f["advua"]
+    f["ady2d"] = f["ady2d"] - f["advva"]
+    f["egf"] = f["el"] * c["ispi"]
+    d, ua, va = f["d"], f["ua"], f["va"]
+    f["utf"][1:, :] = ua[1:, :] * (d[1:, :] + d[:-1, :]) * c["isp2i"]
+    f["vtf"][:, 1:] = va[:, 1:] * (d[:, 1:] + d[:, :-1]) * c["isp2i"]
+
+
+def mode_internal(f, c, first_cold_step=False):
+    """pom/advance.f:356-537 for mode=3, nadv=2, nitera from c, nbct/nbcs in {1,3}, lrestore off."""
+    im, jm, kb = f["u"].shape
+    kbm1 = kb - 1
+    dz, dt, smoth = f["dz"], f["dt"], c["smoth"]
+    if not first_cold_step:
+        u, v = f["u"], f["v"]
+        tps = np.zeros((im, jm), order="F")
+        for k in range(kbm1):
+            tps = tps + u[:, :, k] * dz[k]
+        for k in range(kbm1):
+            u[1:, :, k] = (u[1:, :, k] - tps[1:, :]) + (f["utb"][1:, :] + f["utf"][1:, :]) / (dt[1:, :] + dt[:-1, :])
+        tps = np.zeros((im, jm), order="F")
+        for k in range(kbm1):
+            tps = tps + v[:, :, k] * dz[k]
+        for k in range(kbm1):
+            v[:, 1:, k] = (v[:, 1:, k] - tps[:, 1:]) + (f["vtb"][:, 1:] + f["vtf"][:, 1:]) / (dt[:, 1:] + dt[:, :-1])
+        n = NP(f, c)
+        w = n.vertvl(f["w"])
+        w[:, :, :kbm1] = w[:, :, :kbm1] * f["fsm"][:, :, None]          # bcondorl(5)
+        f["w"] = w
+        z3 = np.zeros((im, jm, kb), order="F")
+        uf = n.advq(f["q2b"], f["q2"], z3)
+        vf = n.advq(f["q2lb"], f["q2l"], z3)
+        out = profq(n, uf, vf)
+        for k_, a in out.items():
+            f[k_] = a
+        bcond6(f, c)
+        q2 = f["q2"] + .5 * smoth * (f["uf"] + f["q2b"] - 2. * f["q2"])
+        q2l = f["q2l"] + .5 * smoth * (f["vf"] + f["q2lb"] - 2. * f["q2l"])
+        f["q2b"], f["q2"] = q2, f["uf"].copy(order="F")
+        f["q2lb"], f["q2l"] = q2l, f["vf"].copy(order="F")
+        # tracers
+        f["uf"], f["tb"] = advt2(f, c, f["tb"], f["t"], f["tclim"], f["uf"])
+        f["vf"], f["sb"] = advt2(f, c, f["sb"], f["s"], f["sclim"], f["vf"])
+        n = NP(f, c)
+        f["uf"] = n.proft(f["uf"], f["wtsurf"], f["tsurf"], int(c["nbct"]))
+        f["vf"] = n.proft(f["vf"], f["wssurf"], f["ssurf"], int(c["nbcs"]))
+        bcond4(f, c)
+        t = f["t"] + .5 * smoth * (f["uf"] + f["tb"] - 2. * f["t"])
+        s = f["s"] + .5 * smoth * (f["vf"] + f["sb"] - 2. * f["s"])
+        f["tb"], f["t"] = t, f["uf"].copy(order="F")
+        f["sb"], f["s"] = s, f["vf"].copy(order="F")
+        for nme in ("t", "tb", "s", "sb"):                               # restore_interior's mask (:1113-1118)
+            f[nme][:, :, :kbm1] = f[nme][:, :, :kbm1] * f["fsm"][:, :, None]
+        f["rho"] = NP(f, c).dens(f["s"], f["t"])
+        # momentum
+        uf_, vf_ = advu(f, c), advv(f, c)
+        f["uf"], wub = profu(f, c, uf_)
+        f["wubot"][1:-1, 1:-1] = wub
+        f["vf"], wvb = profv(f, c, vf_)
+        f["wvbot"][1:-1, 1:-1] = wvb
+        bcondorl3(f, c)
+        for xn, xb, xf in (("u", "ub", "uf"), ("v", "vb", "vf")):
+            x, b, ff = f[xn], f[xb], f[xf]
+            tps = np.zeros((im, jm), order="F")
+            for k in range(kbm1):
+                tps = tps + (ff[:, :, k] + b[:, :, k] - 2. * x[:, :, k]) * dz[k]
+            for k in range(kbm1):
+                x[:, :, k] = x[:, :, k] + .5 * smoth * (ff[:, :, k] + b[:, :, k] - 2. * x[:, :, k] - tps)
+            f[xb], f[xn] = x, ff.copy(order="F")
+    f["egb"] = f["egf"].copy(order="F")
+    f["etb"] = f["et"].copy(order="F")
+    f["et"] = f["etf"].copy(order="F")
+    f["dt"] = f["h"] + f["et"]
+    f["utb"] = f["utf"].copy(order="F")
+    f["vtb"] = f["vtf"].copy(order="F")
+    f["vfluxb"] = f["vfluxf"].copy(order="F")
+    f["wr"] = realvertvl(f, c)
+
+
+def step(f, c, iint):
+    """One internal step, pom/advance.f:21-32 (time/ramp handling left to the caller)."""
+    lateral_viscosity(f, c)
+    mode_interaction(f, c)
+    for iext in range(1, int(c["isplit"]) + 1):
+        mode_external(f, c, iext)
+    mode_internal(f, c, first_cold_step=(iint == 1 and c["time0"] == 0.))

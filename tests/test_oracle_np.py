@@ -149,3 +149,104 @@ def test_baropg_mcc(spun):
     assert np.array_equal(o.get("rho"), rho_)
     for k in ("rho", "drhox", "drhoy"):
         o.put(k, f[k])
+
+
+MOM = ("h fsm dum dvm dx dy art aru arv cor dt d et etb etf egf egb e_atmos cbc wusurf wvsurf z zz dz dzz "
+       "u v w ub vb aam km advx advy drhox drhoy uf vf").split()
+MOMC = ("grav", "dti2", "umol", "horcon")
+
+
+@pytest.fixture(scope="module")
+def mom():
+    """State in the middle of internal step 5, just before advu/advv (u, v adjusted, w from vertvl)."""
+    st, o = syn.seamount(27, 22, 10, Oracle, island=True)
+    for i in range(1, 5):
+        o.step(i)
+    o.set("iint", 5); o.set("time", o.getc("dti") * 5 / 86400.0)
+    return o
+
+
+def _snap(o):
+    return {n: o.get(n) for n in MOM}, {n: o.getc(n) for n in MOMC}
+
+
+def test_advct_and_smagorinsky(mom):
+    from oracle.pomo_np import advct, smagorinsky
+    o = mom
+    f, c = _snap(o)
+    ax, ay = advct(f, c)
+    aam = smagorinsky(f, c)
+    o.lateral_viscosity()          # advct; baropg; aam (advance.f:110-138)
+    assert np.array_equal(o.get("advx"), ax)
+    assert np.array_equal(o.get("advy"), ay)
+    assert np.array_equal(o.get("aam"), aam)
+    assert np.abs(ax).max() > 0 and np.abs(aam - f["aam"]).max() > 0
+
+
+def test_advu_advv_profu_profv(mom):
+    from oracle.pomo_np import advu, advv, profu, profv
+    o = mom
+    o.mode_interaction()
+    for ie in range(1, int(o.getc("isplit")) + 1):
+        o.mode_external(ie)
+    for stg in range(0, 11):       # up to and including the t/s block: u, v adjusted, w, km updated
+        o.internal_stage(5, stg)
+    f, c = _snap(o)
+    uf, vf = advu(f, c), advv(f, c)
+    o.advu(); o.advv()
+    assert np.array_equal(o.get("uf"), uf)
+    assert np.array_equal(o.get("vf"), vf)
+    f["wusurf"], f["wvsurf"] = o.get("wusurf"), o.get("wvsurf")
+    uf2, wub = profu(f, c, uf)
+    vf2, wvb = profv(f, c, vf)
+    o.profu(); o.profv()
+    assert np.array_equal(o.get("uf"), uf2)
+    assert np.array_equal(o.get("vf"), vf2)
+    assert np.array_equal(o.get("wubot")[1:-1, 1:-1], wub)
+    assert np.array_equal(o.get("wvbot")[1:-1, 1:-1], wvb)
+    assert np.abs(uf2 - uf).max() > 0
+
+
+def test_realvertvl(mom):
+    from oracle.pomo_np import realvertvl
+    o = mom
+    f, c = _snap(o)
+    want = realvertvl(f, c)
+    o.realvertvl()
+    assert np.array_equal(o.get("wr"), want)
+    assert np.abs(want).max() > 0
+
+
+ALLC = ("alpha dte dti dti2 grav kappa ramp rfe rfn rfs rfw rhoref sbias small tbias time tprni umol vmaxl dte2 "
+        "horcon ispi isp2i smoth sw time0 iint mode ntp ispadv isplit nadv nbct nbcs nitera npg").split()
+STATE = ("aam advx advy drhox drhoy kh km kq l q2b q2 q2lb q2l rho sb s tb t ub uf u vb vf v w wr "
+         "aam2d advua advva adx2d ady2d d drx2d dry2d dt egb egf el elb elf et etb etf ua uab uaf utb utf va vab "
+         "vaf vtb vtf vfluxb wubot wvbot").split()
+
+
+@pytest.mark.parametrize("kw", [{}, {"nitera": 2, "sw": 1.0}, {"nbct": 3, "nbcs": 3}], ids=["default", "nitera2", "nbc3"])
+def test_whole_step_second_restatement(kw):
+    """One WHOLE internal step (advance.f:21-32: lateral_viscosity, mode_interaction, isplit x
+    mode_external, mode_internal with every solver.f routine and bcond / bcondorl call) through the
+    numpy restatement against the C oracle, from the same spun-up state, for three consecutive steps
+    (re-synchronised each step).  Everything must agree bitwise; only rho (|S|**1.5 through two
+    different pow implementations) gets one ulp."""
+    from oracle import pomo_np
+    st, o = syn.seamount(25, 20, 9, Oracle, island=True, isplit=6, dte=6.0, **kw)
+    for i in range(1, 4):
+        o.step(i)
+    for i in range(4, 7):
+        o.set("iint", i); o.set("time", o.getc("dti") * i / 86400.0)
+        f = {n: o.get(n) for n in o.f}
+        c = {n: o.getc(n) for n in ALLC}
+        pomo_np.step(f, c, i)
+        o.step(i)
+        for n in STATE:
+            a, b = o.get(n), f[n]
+            if n == "rho":
+                assert np.abs(a - b).max() <= 3e-16 * np.abs(a).max(), n
+            elif n in ("uf", "vf"):
+                # level kb of the work arrays keeps whatever the previous user left there
+                assert np.array_equal(a[:, :, :-1], b[:, :, :-1]), (i, n, float(np.abs(a - b).max()))
+            else:
+                assert np.array_equal(a, b), (i, n, float(np.abs(a - b).max()))
