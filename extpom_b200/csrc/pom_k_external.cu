@@ -60,6 +60,7 @@ struct AdvaveK : KBase {
   static constexpr int NV = 4, HL = 1, HR = 1, HB = 1, HT = 1, TY = 16, MINB = 1;
   static constexpr int NF = 8, NS = 1, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = 18, NK = 1;
   static constexpr bool UP = false;
+  static constexpr bool FULL = false;   // stage() may run for every thread and assigns every v[]
   enum { FXU, FYU, FXV, FYV };
   POM_HD void fields(const double** b) const {
     b[OP_D] = p.d; b[OP_UA] = p.ua; b[OP_VA] = p.va; b[OP_UAB] = p.uab; b[OP_VAB] = p.vab; b[OP_AAM2D] = p.aam2d;

@@ -119,6 +119,7 @@ struct AdvqK : KBase {
 #endif
   static constexpr int NF = 8, NS = POM_NS_ADVQ, OHL = 1, OHR = 0, OHB = 1, OHT = 0, BW = 34, BH = TY + 1, NK = 0;
   static constexpr bool UP = true;
+  static constexpr bool FULL = false;   // stage() may run for every thread and assigns every v[]
   enum { Q2, Q2B, Q2L, Q2LB, U, V, AAM, W };
   enum { XA, YA, XB, YB };
   POM_HD void fields(const double** b) const {
@@ -557,6 +558,7 @@ struct AdvT2K : KBase {
   // operands staged by the TMA: box = thread tile + one column W and one row S (34 x 17)
   static constexpr int NF = 2 * NT + 4, NS = POM_TILE_NS, OHL = 1, OHR = 0, OHB = 1, OHT = 0, BW = 34, BH = TY + 1, NK = 0;
   static constexpr bool UP = true;
+  static constexpr bool FULL = true;   // stage() may run for every thread and assigns every v[]
   enum { AAM = 2 * NT, U, V, W };     // FB(t) = 2t, FC(t) = 2t+1
   enum { XF, YF, XD, YD };            // + 4t
   POM_HD void fields(const double** b) const {
@@ -599,28 +601,23 @@ struct AdvT2K : KBase {
       for (int t = 0; t < NT; ++t) s.zk[t] = w1*A3(f_[t],i,j,1)*s.ar;   // :648 (itera==1)
     }
   }
+  // Branch-free (see AdvctK::stage): the definition-range flags select, nothing is skipped.
   template <class Op>
   POM_HD void stage(int i, int j, int k, State& s, const Op& o, double* v) const {
-    if (!(s.fxa || s.fya || s.interior)) return;
     const double a0=o(AAM,0,0);
-    double xm = 0., xd = 0., ym = 0., yd = 0.;
-    if (s.fxa) { xm=upw ? s.cx*o(U,0,0) : 0.; xd=0.5*(a0+o(AAM,-1,0)); }   // :605-606, :696
-    if (s.fya) { ym=upw ? s.cy*o(V,0,0) : 0.; yd=0.5*(a0+o(AAM,0,-1)); }   // :612-613, :697
+    const double xm=upw ? s.cx*o(U,0,0) : 0., xd=0.5*(a0+o(AAM,-1,0));   // :605-606, :696
+    const double ym=upw ? s.cy*o(V,0,0) : 0., yd=0.5*(a0+o(AAM,0,-1));   // :612-613, :697
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       const double fb0=o(2*t,0,0);
       const double fd0=fb0-o(2*t+1,0,0);                                // fb-fclim (:691)
       s.fb0[t]=fb0;
-      if (s.fxa) {
-        const double fbW=o(2*t,-1,0);
-        v[4*t+XF]=0.5*((xm+fabs(xm))*fbW+(xm-fabs(xm))*fb0);            // :631-635
-        v[4*t+XD]=s.ddxs(-xd*s.hx*tprni*(fd0-(fbW-o(2*t+1,-1,0)))*s.dumc*s.dys*0.5);   // :705-707
-      }
-      if (s.fya) {
-        const double fbS=o(2*t,0,-1);
-        v[4*t+YF]=0.5*((ym+fabs(ym))*fbS+(ym-fabs(ym))*fb0);            // :637-641
-        v[4*t+YD]=s.ddys(-yd*s.hy*tprni*(fd0-(fbS-o(2*t+1,0,-1)))*s.dvmc*s.dxs*0.5);   // :708-710
-      }
+      const double fbW=o(2*t,-1,0);
+      v[4*t+XF]=s.fxa ? 0.5*((xm+fabs(xm))*fbW+(xm-fabs(xm))*fb0) : 0.;            // :631-635
+      v[4*t+XD]=s.fxa ? s.ddxs(-xd*s.hx*tprni*(fd0-(fbW-o(2*t+1,-1,0)))*s.dumc*s.dys*0.5) : 0.;   // :705-707
+      const double fbS=o(2*t,0,-1);
+      v[4*t+YF]=s.fya ? 0.5*((ym+fabs(ym))*fbS+(ym-fabs(ym))*fb0) : 0.;            // :637-641
+      v[4*t+YD]=s.fya ? s.ddys(-yd*s.hy*tprni*(fd0-(fbS-o(2*t+1,0,-1)))*s.dvmc*s.dxs*0.5) : 0.;   // :708-710
     }
   }
   template <class Op>

@@ -35,6 +35,7 @@ struct AdvctK : KBase {
 #endif
   static constexpr int NF = 5, NS = POM_NS_ADVCT, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = TY + 2, NK = 0;
   static constexpr bool UP = false;
+  static constexpr bool FULL = true;   // stage() may run for every thread and assigns every v[]
   enum { U, V, UB, VB, AAM };
   enum { X, Y, XP, YP, CV, CU };
   POM_HD void fields(const double** b) const { b[U] = p.u; b[V] = p.v; b[UB] = p.ub; b[VB] = p.vb; b[AAM] = p.aam; }
@@ -81,43 +82,46 @@ struct AdvctK : KBase {
     }
     if (s.interior) { s.aru25 = aru(i,j)*.25; s.arv25 = arv(i,j)*.25; }
   }
+  // Branch-free: every thread evaluates every flux (operands outside the arrays read as zero, the
+  // hoisted metrics of a thread outside a definition range are zero) and the definition-range
+  // flags select the result; the arithmetic of a selected value is unchanged.
   template <class Op>
   POM_HD void stage(int i, int j, int k, State& s, const Op& o, double* v) const {
-    if (!(s.fx || s.fy || s.fxp || s.fyp)) return;
     const double u00 = o(U,0,0), v00 = o(V,0,0), ub00 = o(UB,0,0), vb00 = o(VB,0,0), a00 = o(AAM,0,0);
-    double uE = 0., vN = 0.;
-    if (s.fx || s.fyp) uE = o(U,1,0);
-    if (s.fx) {                                                          // :237-239,258-260,272
+    const double uE = o(U,1,0), vN = o(V,0,1);
+    {                                                                    // :237-239,258-260,272
       double a=.125*(s.dtE*uE+s.dtW*u00)*(uE+u00);
       a=a-s.ddx(s.dtc*a00*2.*(o(UB,1,0)-ub00));
-      v[X]=s.dyc*a;
+      v[X]=s.fx ? s.dyc*a : 0.;
     }
-    if (s.fy || s.fxp) {
+    {
       const double uS = o(U,0,-1), vW = o(V,-1,0);
       const double dtaam=s.q4*(a00+o(AAM,-1,0)+o(AAM,0,-1)+o(AAM,-1,-1));  // :261-263,348-350
       const double cd=dtaam*(s.ddy4(ub00-o(UB,0,-1))+s.ddx4(vb00-o(VB,-1,0)));   // :265-270,352-357
-      if (s.fy) { double a=.125*(s.dtS*v00+s.dtSW*vW)*(u00+uS); v[Y]=s.qdx4*(a-cd); }     // :247-249,273-274
-      if (s.fxp) { double a=.125*(s.dtW*u00+s.dtWS*uS)*(v00+vW); v[XP]=s.qdy4*(a-cd); }   // :327-329,362-363
+      const double ay=.125*(s.dtS*v00+s.dtSW*vW)*(u00+uS);                  // :247-249,273-274
+      v[Y]=s.fy ? s.qdx4*(ay-cd) : 0.;
+      const double ax=.125*(s.dtW*u00+s.dtWS*uS)*(v00+vW);                  // :327-329,362-363
+      v[XP]=s.fxp ? s.qdy4*(ax-cd) : 0.;
     }
-    if (s.fyp) {
-      vN = o(V,0,1);
+    {
       double a=.125*(s.dtN*vN+s.dtS*v00)*(vN+v00);                        // :337-339
       a=a-s.ddy(s.dtc*a00*2.*(o(VB,0,1)-vb00));                            // :358-360
-      v[YP]=s.dxc*a;                                                      // :364
+      v[YP]=s.fyp ? s.dxc*a : 0.;                                         // :364
       const double cv=s.ddxdy(.25*((vN+v00)*s.dyd-(uE+u00)*s.dxd));         // :221-225
-      v[CV]=cv*s.dtc*(vN+v00);                                            // :297-298
-      v[CU]=cv*s.dtc*(uE+u00);                                            // :387-388
+      v[CV]=s.fyp ? cv*s.dtc*(vN+v00) : 0.;                               // :297-298
+      v[CU]=s.fyp ? cv*s.dtc*(uE+u00) : 0.;                               // :387-388
     }
   }
   template <class Op>
   POM_HD void combine(int i, int j, int k, State& s, const Op&, const Tile2& tl) const {
-    double ax = 0., ay = 0.;
-    if (s.interior) {
-      ax=tl(X,0,0)-tl(X,-1,0)+tl(Y,0,1)-tl(Y,0,0);                            // :285-286
-      if (s.i3) ax=ax-s.aru25*(tl(CV,0,0)+tl(CV,-1,0));                     // :293-300 (n_west==-1)
-      ay=tl(XP,1,0)-tl(XP,0,0)+tl(YP,0,0)-tl(YP,0,-1);                        // :375-376
-      if (s.j3) ay=ay+s.arv25*(tl(CU,0,0)+tl(CU,0,-1));                     // :383-390 (n_south==-1)
-    }
+    double ax=tl(X,0,0)-tl(X,-1,0)+tl(Y,0,1)-tl(Y,0,0);                      // :285-286
+    const double cx=s.aru25*(tl(CV,0,0)+tl(CV,-1,0));                     // :293-300 (n_west==-1)
+    ax=s.i3 ? ax-cx : ax;
+    double ay=tl(XP,1,0)-tl(XP,0,0)+tl(YP,0,0)-tl(YP,0,-1);                  // :375-376
+    const double cy=s.arv25*(tl(CU,0,0)+tl(CU,0,-1));                     // :383-390 (n_south==-1)
+    ay=s.j3 ? ay+cy : ay;
+    ax=s.interior ? ax : 0.;
+    ay=s.interior ? ay : 0.;
     advx(i,j,k)=ax;
     advy(i,j,k)=ay;
     s.sx=s.sx+ax*dz(k);                                                   // advance.f:161-162

@@ -139,7 +139,7 @@ tmakernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1
     for (int L = k0; L < k0 + NS && L <= kl1; ++L) issue(L);
   const bool inside = (i >= 1 && i <= f.g.im && j >= f.g.joff + 1 && j <= f.g.joff + f.g.jml);
   const bool out = (tx >= F::HL && tx < TILE_X - F::HR && ty >= F::HB && ty < F::TY - F::HT && i <= i1 && j <= j1);
-  typename F::State st;
+  typename F::State st{};
   f.pre(i, j, inside, out, st);
   const int own = (ty + F::OHB) * F::BW + tx + F::OHL + shift;
   int buf = 0;
@@ -153,9 +153,11 @@ tmakernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1
     }
     const SmemOp<F> op{ring + s0 * NF * PL + own, ring + s1 * NF * PL + own};
     double v[NV];
+    if (!F::FULL) {
 #pragma unroll
-    for (int n = 0; n < NV; ++n) v[n] = 0.;
-    if (inside) f.stage(i, j, k, st, op, v);
+      for (int n = 0; n < NV; ++n) v[n] = 0.;
+    }
+    if (F::FULL || inside) f.stage(i, j, k, st, op, v);
     double* Sb = S + buf * NV * F::TY * TILE_X;
 #pragma unroll
     for (int n = 0; n < NV; ++n) Sb[(n * F::TY + ty) * TILE_X + tx] = v[n];
@@ -259,7 +261,7 @@ tilekernel_g(const F f, int i0, int i1, int j0, int j1) {
   const bool out = (tx >= F::HL && tx < TILE_X - F::HR && ty >= F::HB && ty < F::TY - F::HT && i <= i1 && j <= j1);
   const double* fld[F::NF];
   f.fields(fld);
-  typename F::State st;
+  typename F::State st{};
   f.pre(i, j, inside, out, st);
   const int k1 = f.k1();
   for (int k = f.k0(); k <= k1; ++k) {
