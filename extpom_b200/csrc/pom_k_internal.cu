@@ -200,10 +200,10 @@ struct AdvqK : KBase {
     if (s.interior) {
       const double w1=o.up(W), qa1=o.up(Q2), qb1=o.up(Q2L);
       const double dzk=dz(k)+dz(k-1);
-      double ra=(s.wm*s.qam-w1*qa1)*s.ar/dzk
+      double ra=pdiv((s.wm*s.qam-w1*qa1)*s.ar,dzk)
                 +tl(XA,1,0)-tl(XA,0,0)+tl(YA,0,1)-tl(YA,0,0);  // :465-468
       a=s.dhf(s.hb*s.qab-dti2*ra);                             // :469-471
-      double rb=(s.wm*s.qbm-w1*qb1)*s.ar/dzk
+      double rb=pdiv((s.wm*s.qbm-w1*qb1)*s.ar,dzk)
                 +tl(XB,1,0)-tl(XB,0,0)+tl(YB,0,1)-tl(YB,0,0);
       b=s.dhf(s.hb*s.qbb-dti2*rb);
       s.wm=s.w0; s.w0=w1;
@@ -349,19 +349,19 @@ struct ProfqK : KBase {
     double tp=o(T,0,0)+tbias, sp=o(S,0,0)+sbias;
     double pp=grav*rhoref*(-zz(k)*hh)*1.e-4;
     double cv=1449.1+.00821*pp+4.55*tp-.045*(tp*tp)+1.34*(sp-35.0);
-    double cck=cv/sqrt((1.-.01642*pp/cv)*(1.-0.40*pp/(cv*cv)));
+    double cck=pdiv(cv,sqrt((1.-pdiv(.01642*pp,cv))*(1.-pdiv(0.40*pp,cv*cv))));
     double qb=fabs(o(Q2B,0,0)), qlb=fabs(o(Q2LB,0,0));
     if (!fuse) {   // fused: the upward sweep takes the abs again and stores the FILTERED values
       q2b(i,j,k)=qb;                                                          // :1325-1326
       q2lb(i,j,k)=qlb;
     }
     const double rhok=o(RHO,0,0);
-    double boygr=grav*(st.rhom-rhok)/(dzz(k-1)*hh)
-                 +(grav*grav)*2./(st.ccm*st.ccm+cck*cck);                     // :1327-1330
+    double boygr=pdiv(grav*(st.rhom-rhok),dzz(k-1)*hh)
+                 +pdiv((grav*grav)*2.,st.ccm*st.ccm+cck*cck);                     // :1327-1330
     st.ccm=cck; st.rhom=rhok;
-    double ll=fabs(qlb/qb);                                                   // :1338
+    double ll=fabs(pdiv(qlb,qb));                                                   // :1338
     if (z(k) > -0.5) ll=fmax(ll,st.kl0);                                      // :1339
-    double gh=(ll*ll)*boygr/qb;                                               // :1343
+    double gh=pdiv((ll*ll)*boygr,qb);                                               // :1343
     gh=fmin(gh,.028);                                                         // :1344
     l(i,j,k)=ll;
     const double u0=o(U,0,0), uE=o(U,1,0), v0=o(V,0,0), vN=o(V,0,1);
@@ -371,26 +371,26 @@ struct ProfqK : KBase {
       double su=u0-st.um+uE-st.uEm;
       double sv=v0-st.vm+vN-st.vNm;
       double dd=dzz(k-1)*dh;
-      pr=kmk*.25*sef*(su*su+sv*sv)/(dd*dd)-shiw*kmk*boygr;                    // :1362-1369
+      pr=pdiv(kmk*.25*sef*(su*su+sv*sv),dd*dd)-shiw*kmk*boygr;                    // :1362-1369
       pr=pr+khk*boygr;                                                        // :1370
     }
     st.um=u0; st.uEm=uE; st.vm=v0; st.vNm=vN;
-    double dtf=sqrt(fabs(qb))*1./(b1*ll+small);                               // :1388-1389 (stf=1)
+    double dtf=pdiv(sqrt(fabs(qb))*1.,b1*ll+small);                               // :1388-1389 (stf=1)
     // tridiagonal coefficients from the OLD kq (:1258-1267)
     const double kqp=o.up(KQ);
     const double kq0=st.kq0;
-    const double a=-dti2*(kqp+kq0+2.*umol)*.5/(dzz(k-1)*dz(k)*dh*dh);
-    const double cq=-dti2*(st.kqm+kq0+2.*umol)*.5/(dzz(k-1)*dz(k-1)*dh*dh);
+    const double a=pdiv(-dti2*(kqp+kq0+2.*umol)*.5,dzz(k-1)*dz(k)*dh*dh);
+    const double cq=pdiv(-dti2*(st.kqm+kq0+2.*umol)*.5,dzz(k-1)*dz(k-1)*dh*dh);
     // q2 forward elimination (:1394-1404)
     {
-      double gi=1./(a+cq*(1.-st.eem)-(2.*dti2*dtf+1.));
+      double gi=pdiv(1.,a+cq*(1.-st.eem)-(2.*dti2*dtf+1.));
       st.eem=a*gi;
       st.ggm=(-2.*dti2*pr+cq*st.ggm-o(UF,0,0))*gi;
       cm.ee[k]=st.eem; cm.gg[k]=st.ggm;
     }
     // q2l forward elimination (:1417-1446)
     {
-      double r=zr[k]*ll/(dh*kappa);
+      double r=pdiv(zr[k]*ll,dh*kappa);
       double dtf2=dtf*(1.+e2*(r*r));                                          // :1429-1432
       if (k == 2) {
         st.e2m=0.;                                                            // :1421
@@ -398,7 +398,7 @@ struct ProfqK : KBase {
       } else {
         // :1423 assigns vf(kbm1)=kappa*(1+z(kbm1))*dh*q2(kbm1) before this sweep reads it
         double vk=(k == kbm1) ? kappa*(1+z(kbm1))*dh*o(Q2,0,0) : o(VF,0,0);
-        double gi=1./(a+cq*(1.-st.e2m)-(dti2*dtf2+1.));
+        double gi=pdiv(1.,a+cq*(1.-st.e2m)-(dti2*dtf2+1.));
         st.e2m=a*gi;
         st.g2m=(dti2*(-pr*ll*e1)+cq*st.g2m-vk)*gi;
       }
@@ -406,9 +406,9 @@ struct ProfqK : KBase {
     }
     // km, kh, kq (:1478-1506) -- in place; kq's old value stays in kqm for level k+1
     {
-      double sh=coef1/(1.-coef2*gh);
+      double sh=pdiv(coef1,1.-coef2*gh);
       double sm=coef3+sh*coef4*gh;
-      sm=sm/(1.-coef5*gh);
+      sm=pdiv(sm,1.-coef5*gh);
       double pq=ll*sqrt(fabs(o(Q2,0,0)));
       const double nq=(pq*.41*sh+kq0)*.5, nm=(pq*sm+kmk)*.5, nh=(pq*sh+khk)*.5;
       put_k(i,j,k,st,nq,nm,nh);
@@ -647,7 +647,7 @@ struct AdvT2K : KBase {
         zk1=0.5*((w1+fabs(w1))*fb1+(w1-fabs(w1))*s.fb0[t]);             // :656-660
         zk1=zk1*s.ar;                                                   // :661
       }
-      double q=tl(4*t+XF,1,0)-tl(4*t+XF,0,0)+tl(4*t+YF,0,1)-tl(4*t+YF,0,0)+(s.zk[t]-zk1)/dz(k);   // :670-672
+      double q=tl(4*t+XF,1,0)-tl(4*t+XF,0,0)+tl(4*t+YF,0,1)-tl(4*t+YF,0,0)+pdiv(s.zk[t]-zk1,dz(k));   // :670-672
       q=s.def(s.fb0[t]*s.eb-dti2*q);                                    // :673-674
       q=q*s.m;                                                          // smol_adif :1899
       q=q-s.def(dti2*(tl(4*t+XD,1,0)-tl(4*t+XD,0,0)+tl(4*t+YD,0,1)-tl(4*t+YD,0,0)));   // :721-723
@@ -986,11 +986,11 @@ struct ProftTSK : KBase {
       if (penS) s.radS=rad(2,dh,s.swS);
       return;
     }
-    const double ck=-dti2*(o(KH,0,0)+umol)/(dz(k)*dzz(k-1)*dh*dh);      // c(k)
+    const double ck=pdiv(-dti2*(o(KH,0,0)+umol),dz(k)*dzz(k-1)*dh*dh);  // c(k)
     if (k <= kbm2) {                                                    // :1650-1661
-      const double ak=-dti2*(o.up(KH)+umol)/(dz(k)*dzz(k)*dh*dh);       // a(k)
-      const double giT=1./(ak+ck*(1.-s.eeT)-1.);
-      const double giS=same ? giT : 1./(ak+ck*(1.-s.eeS)-1.);
+      const double ak=pdiv(-dti2*(o.up(KH)+umol),dz(k)*dzz(k)*dh*dh);   // a(k)
+      const double giT=pdiv(1.,ak+ck*(1.-s.eeT)-1.);
+      const double giS=same ? giT : pdiv(1.,ak+ck*(1.-s.eeS)-1.);
       s.eeT=ak*giT;
       s.eeS=same ? s.eeT : ak*giS;
       double rT=ck*s.ggT-o(FT,0,0), rS=ck*s.ggS-o(FS,0,0);
@@ -1055,7 +1055,7 @@ POM_HD double pow15(double x) {
   if (!(x > 0.)) return 0.;
   double sq=sqrt(x);
   double res=fma(-sq,sq,x);          // x - sq*sq exactly
-  double ds=res/(2.*sq);             // sqrt(x) = sq + ds
+  double ds=pdiv(res,2.*sq);             // sqrt(x) = sq + ds
   double pr=x*sq;
   double er=fma(x,sq,-pr);           // x*sq = pr + er exactly
   return pr+(er+x*ds);
@@ -1070,8 +1070,8 @@ POM_HD double dens_point(double tr, double sr, double pp, double rhoref_, double
            +(-5.72466e-3+1.0227e-4*tr-1.6546e-6*tr2)*pow15(fabs(sr))
            +4.8314e-4*sr*sr;
   double cr=1449.1+.0821*pp+4.55*tr-.045*tr2+1.34*(sr-35.);
-  rhor=rhor+1.e5*pp/(cr*cr)*(1.-2.*pp/(cr*cr));
-  return rhor/rhoref_*m;
+  rhor=rhor+pdiv(1.e5*pp,cr*cr)*(1.-pdiv(2.*pp,cr*cr));
+  return pdiv(rhor,rhoref_)*m;
 }
 
 // One level of bcond(4) (bounds_forcing.f:151-242) + Asselin filter/rotation of t,s
@@ -1417,10 +1417,10 @@ struct AdvProfUVK : KBase {
     // ---- explicit tendency (advu :753-785 / advv :810-842) ----
     const double fk1 = (k + 1 <= kbm1) ? .25*(o.up(W)+o.up(W,BI,BJ))*(o.up(X)+x0) : 0.;   // :747-748
     const double ct=s.c0*(o(Y,OI,OJ)+o(Y,0,0))+s.cB*(o(Y,BI+OI,BJ+OJ)+o(Y,BI,BJ));
-    double r=o(ADV,0,0)+(s.fk-fk1)*s.ar/dz(k);
+    double r=o(ADV,0,0)+pdiv((s.fk-fk1)*s.ar,dz(k));
     r = VC ? r+s.ar*.25*ct : r-s.ar*.25*ct;                             // :760-763 / :817-820
     r=r+s.sl+o(DRHO,0,0);                                               // :764-769
-    const double xk=(s.hb*o(XB,0,0)-2.*dti2*r)/s.hf;                    // :778-782
+    const double xk=pdiv(s.hb*o(XB,0,0)-2.*dti2*r,s.hf);                // :778-782
     s.fk=fk1;
     // ---- forward elimination (profu :1711-1748 / profv :1809-1845) ----
     const double dh=s.dh;
@@ -1434,11 +1434,11 @@ struct AdvProfUVK : KBase {
       cm.ee[1]=s.eem; cm.gg[1]=s.ggm;
     } else if (k <= kbm2) {                                             // :1740-1748
       const double cn=(o.up(KM)+o.up(KM,BI,BJ))*.5;
-      const double ak=-dti2*(cn+umol)/(dz(k)*dzz(k)*dh*dh);             // a(k)
-      const double gi=1./(ak+s.ck*(1.-s.eem)-1.);
+      const double ak=pdiv(-dti2*(cn+umol),dz(k)*dzz(k)*dh*dh);         // a(k)
+      const double gi=pdiv(1.,ak+s.ck*(1.-s.eem)-1.);
       s.eem=ak*gi;
       s.ggm=(s.ck*s.ggm-xk)*gi;
-      s.ck=-dti2*(cn+umol)/(dz(k+1)*dzz(k)*dh*dh);                      // c(k+1)
+      s.ck=pdiv(-dti2*(cn+umol),dz(k+1)*dzz(k)*dh*dh);                  // c(k+1)
       cm.ee[k]=s.eem; cm.gg[k]=s.ggm;
     } else {
       s.xfl=xk;                                                         // uf(kbm1), used by the bottom condition

@@ -568,6 +568,7 @@ double pomgpu_check_velocity_lagged(pomgpu_t* p) {
   return prev;
 #endif
 }
+long pomgpu_selftest_pdiv(pomgpu_t* p, long n, unsigned long seed, int emax) { return selftest_pdiv(X(p), n, seed, emax); }
 // ---- on-device time interpolation of forcing / boundary records (pom_forcing.cu) ----
 int pomgpu_push_record(pomgpu_t* p, const char* name, int slot, const double* host) { return record_push(X(p), name, slot, host); }
 int pomgpu_rotate_record(pomgpu_t* p, const char* name) { return record_rotate(X(p), name); }

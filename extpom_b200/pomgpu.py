@@ -62,6 +62,8 @@ def _bind(path):
     L.pomgpu_check_velocity.argtypes = [P]
     L.pomgpu_push_async.argtypes = [P, C.c_char_p, P]
     L.pomgpu_domain_stats_rows.argtypes = [P, P]
+    L.pomgpu_selftest_pdiv.restype = C.c_long
+    L.pomgpu_selftest_pdiv.argtypes = [P, C.c_long, C.c_ulong, C.c_int]
     L.pomgpu_push_record.argtypes = [P, C.c_char_p, C.c_int, P]
     L.pomgpu_rotate_record.argtypes = [P, C.c_char_p]
     L.pomgpu_interp.argtypes = [P, C.c_char_p, C.c_double]

@@ -75,6 +75,11 @@ int pomgpu_interp(pomgpu_t* ctx, const char* name, double fnew);
 int pomgpu_wind(pomgpu_t* ctx, double fnew);
 int pomgpu_heat(pomgpu_t* ctx, double fnew);
 int pomgpu_lateral_bc(pomgpu_t* ctx, double fnew);
+/* Self test of the two division helpers the kernels use to stay bit-identical to the reference's
+ * IEEE divisions (pdiv: nvcc's own fp64 division sequence without its operand-range test; RDiv:
+ * hoisted reciprocal + fma residual): number of operand pairs, out of n pseudo-random ones with
+ * magnitudes 10^-emax..10^emax, whose quotient differs in any bit from `a/b` on the device. */
+long pomgpu_selftest_pdiv(pomgpu_t* ctx, long n, unsigned long seed, int emax);
 int pomgpu_pin_host(void* ptr, unsigned long bytes);
 int pomgpu_unpin_host(void* ptr);
 

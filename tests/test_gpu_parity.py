@@ -155,3 +155,12 @@ def test_domain_stats_matches_oracle():
 
 def test_forcing_interpolation_matches_oracle():
     pc.check_forcing_interp(_factory)
+
+
+@pytest.mark.parametrize("emax", [30, 100, 140])
+def test_division_helpers_are_ieee_exact(emax):
+    """pdiv (nvcc's fp64 division sequence without the range test) and RDiv (hoisted reciprocal)
+    against `/` on the device: 2^26 pseudo-random operand pairs per magnitude range, every bit."""
+    g = _factory(8, 8, 4)
+    bad = g.L.pomgpu_selftest_pdiv(g.h, 1 << 26, 12345 + emax, emax)
+    assert bad == 0, bad
