@@ -127,7 +127,8 @@ struct ExtStepK : KBase {
   static constexpr int NV = M2 ? 7 : 6, TY = POM_EXT_TY, MINB = POM_EXT_MINB;
   static constexpr int NF = 13, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = POM_EXT_TY + 2, NK = 1;
   enum { D = OP_D, UA = OP_UA, VA = OP_VA, UAB = OP_UAB, VAB = OP_VAB, AAM2D = OP_AAM2D, DX = OP_DX, DY = OP_DY,
-         EL, ELB, H, COR, EATM };
+         ELB, EL, H, COR, EATM };
+  static constexpr int NFA = 9;   // D..DY, ELB: everything phases A and B read
   enum { FUA, FVA, FXU, FYU, FXV, FYV, CURV };   // CURV: curv2d of the mode=2 block (solver.f:145-152)
   POM_HD void fields(const double** b) const {
     b[D] = p.d; b[UA] = p.ua; b[VA] = p.va; b[UAB] = p.uab; b[VAB] = p.vab; b[AAM2D] = p.aam2d; b[DX] = p.dx;

@@ -378,16 +378,21 @@ tile3kernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int 
     static_assert(F::BH >= F::TY + F::OHB + F::OHT, "TMA box too short");
     const bool leader = (tx == 0 && ty == 0);
     if (leader) {
-      mbar_init(bar, 1);
+      // two transactions: the first F::NFA fields are all that phases A and B read, so they start
+      // while the operands only phase C needs are still in flight
+      mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      mbar_expect_tx(bar, (uint32_t)(NF * F::BW * F::BH * sizeof(double)));
       const int c0 = n0 - shift, c1 = tj0 - 1 - f.g.joff - F::OHB;
+      mbar_expect_tx(&bar[0], (uint32_t)(F::NFA * F::BW * F::BH * sizeof(double)));
 #pragma unroll
-      for (int n = 0; n < NF; ++n) tma_load_3d(ring + n * PL, &maps.m[n], bar, c0, c1, 0);
+      for (int n = 0; n < F::NFA; ++n) tma_load_3d(ring + n * PL, &maps.m[n], &bar[0], c0, c1, 0);
+      mbar_expect_tx(&bar[1], (uint32_t)((NF - F::NFA) * F::BW * F::BH * sizeof(double)));
+#pragma unroll
+      for (int n = F::NFA; n < NF; ++n) tma_load_3d(ring + n * PL, &maps.m[n], &bar[1], c0, c1, 0);
     }
     f.pre(i, j, inside, st);        // plain loads of the point-wise operands overlap the TMA
     __syncthreads();                // barrier init visible to every waiter
-    mbar_wait(bar, 0);
+    mbar_wait(&bar[0], 0);
   } else {
     f.pre(i, j, inside, st);
   }
@@ -406,6 +411,7 @@ tile3kernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int 
   double e = 0.;
   if (bok) e = TMA ? f.phaseB(i, j, st, sop, Tile2{S, tx, ty, TILE_Y}, tx >= 1 && ty >= 1) : f.phaseB(i, j, st, gop, Tile2{S, tx, ty, TILE_Y}, tx >= 1 && ty >= 1);
   E[ty * TILE_X + tx] = e;
+  if (TMA) mbar_wait(&bar[1], 0);
   __syncthreads();
   if (out) { if (TMA) f.phaseC(i, j, st, sop, Tile2{S, tx, ty, TILE_Y}, Tile2{E, tx, ty, TILE_Y}); else f.phaseC(i, j, st, gop, Tile2{S, tx, ty, TILE_Y}, Tile2{E, tx, ty, TILE_Y}); }
 }
@@ -464,7 +470,7 @@ inline void launch_tile3(Ctx* c, const F& f, int i0, int i1, int j0, int j1) {
     for (int n = 0; n < F::NF && tma_ok; ++n)
       if (tma_encode(c, &maps.m[n], fld[n], 1, F::BW, F::BH)) tma_ok = false;
   }
-  constexpr size_t sm_se = (size_t)((F::NV + 1) * TILE_Y * TILE_X) * sizeof(double) + 8;
+  constexpr size_t sm_se = (size_t)((F::NV + 1) * TILE_Y * TILE_X) * sizeof(double) + 16;
   constexpr size_t sm_tma = sm_se + (size_t)F::NF * tma_plane(F::BW, F::BH) * sizeof(double);
   static bool granted = false;
   if (!granted) {
