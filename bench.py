@@ -113,7 +113,7 @@ def run_reference(a, rank):
     sample = (f"{a.steps} internal steps of the seamount state at {a.cpu_sample}x{a.cpu_sample}x{a.kb} "
               f"(isplit=30) after {max(a.warmup, 1)} warm-up steps; C restatement of advance.f/solver.f, "
               f"gcc -O2 -ffp-contract=off, OpenMP x{cores}")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": spt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -121,11 +121,30 @@ def run_reference(a, rank):
                    "l2": "inputs larger than L2"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
+
+
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """stdout carries exactly ONE JSON line: anything a library prints there while the job runs
+    (e.g. NCCL's version banner) is sent to stderr; emit() writes to the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    f = _REAL_STDOUT or sys.stdout
+    f.write(json.dumps(obj) + "\n")
+    f.flush()
 
 
 def main():
     a = parse()
+    _guard_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -140,9 +159,9 @@ def main():
 
     dist = None
     if world > 1:
-        # NCCL_DEBUG=VERSION (set on some boxes) makes NCCL print to stdout; stdout carries ONE JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL_DEBUG=VERSION (set on some boxes) makes NCCL print its banner to stdout
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ.pop("NCCL_DEBUG")
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -278,7 +297,7 @@ def main():
             "value": val, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"8 internal steps at {a.cpu_sample}x{a.cpu_sample}x{kb} (isplit=30) after 1 warm-up; "
                       "C restatement of advance.f/solver.f (oracle/), gcc -O2 -ffp-contract=off, OpenMP"}
-    print(json.dumps(out), flush=True)
+    emit(out)
     if dist is not None:
         dist.destroy_process_group()
 
