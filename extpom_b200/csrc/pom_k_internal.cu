@@ -42,14 +42,8 @@
 #define POM_TILE_MINB 1
 #define POM_TILE_NS 4
 #endif
-#ifndef POM_THOMAS_SMEM
-#define POM_THOMAS_SMEM 0
-#endif
 #ifndef POM_PFD
 #define POM_PFD 2
-#endif
-#ifndef POM_THOMAS_BY
-#define POM_THOMAS_BY 4
 #endif
 
 namespace pom {
@@ -538,7 +532,7 @@ struct QFilterK : KBase {
 // advt2 with nitera=1 (solver.f:577-731 + the fsm mask of smol_adif :1898-1900):
 // upstream advection, leapfrog update, horizontal diffusion of (fb-fclim); tile kernel:
 // every thread evaluates the upwind and the diffusive x/y fluxes of its own point once.
-template <int NT>   // NT tracers in one pass (T alone, or T and S sharing u, v, w, aam and the metrics)
+template <int NT, bool UPW = true>   // NT tracers in one pass (T alone, or T and S sharing u, v, w, aam and the metrics)
 struct AdvT2K : KBase {
   static const KInfo& info() {
     static const KInfo k1{"advt2", 6, 1, 10, 0}, k2{"advt2_ts", 8, 2, 10, 0};
@@ -546,8 +540,8 @@ struct AdvT2K : KBase {
   }
   const double *fb_[NT], *f_[NT], *fc_[NT];
   double* ff_[NT];
-  bool upw = true;   // false: only the horizontal diffusion of (fb-fclim) is added to ff (:691-726, nitera>1)
-  AdvT2K(const Ctx* x, const double* fb, const double* f, const double* fc, double* ff, bool up = true) : KBase(x), upw(up) {
+  static constexpr bool upw = UPW;   // false: only the horizontal diffusion of (fb-fclim) is added to ff (:691-726, nitera>1)
+  AdvT2K(const Ctx* x, const double* fb, const double* f, const double* fc, double* ff) : KBase(x) {
     fb_[0] = fb; f_[0] = f; fc_[0] = fc; ff_[0] = ff;
   }
   AdvT2K(const Ctx* x) : KBase(x) {   // T -> uf and S -> vf (advance.f:430-431)
@@ -842,16 +836,10 @@ struct ProftK : KBase {
     if (k >= g.kb) return 0.;
     return sw0*(rn*exp(z(k)*dh/ad1n)+(1.-rn)*exp(z(k)*dh/ad2n));
   }
-#if POM_THOMAS_SMEM
-  POM_HD void operator()(int i, int j, const ColMem& cm) const {
-#define EE(k) cm(0, k)
-#define GG(k) cm(1, k)
-#else
   POM_HD void operator()(int i, int j) const {
     double ee_[KMAX], gg_[KMAX];
 #define EE(k) ee_[k]
 #define GG(k) gg_[k]
-#endif
     POM_DIMS;
     const double dh=h(i,j)+etf(i,j);                                    // :1580
     const bool pen = (nbc == 2 || nbc == 4);
@@ -1708,17 +1696,13 @@ void run_smol_adif(Ctx* c, const double* ff, double* xm, double* ym, double* zw,
   launch_cols(c, SmolAdifK(c, ff, xm, ym, zw), ALLI, j0, j1);
 }
 void run_advt2_diff(Ctx* c, const double* fb, const double* fc, double* ff, int j0, int j1) {
-  launch_tma_tiles(c, AdvT2K<1>(c, fb, fb, fc, ff, false), ALLI, j0, j1);   // the tile kernel's diffusion half
+  launch_tma_tiles(c, AdvT2K<1, false>(c, fb, fb, fc, ff), ALLI, j0, j1);   // the tile kernel's diffusion half
 }
 void run_fb_roundtrip(Ctx* c, double* fb, const double* fc, double* f, int j0, int j1) {
   launch_cols(c, FbRoundTripK(c, fb, fc, f), ALLI, j0, j1);
 }
 void run_proft(Ctx* c, double* f, const double* wf, const double* fs, int nbc, int j0, int j1) {
-#if POM_THOMAS_SMEM
-  launch_cols_sm(c, ProftK(c, f, wf, fs, nbc), ALLI, j0, j1, 2, 32, POM_THOMAS_BY);
-#else
   launch_cols(c, ProftK(c, f, wf, fs, nbc), ALLI, j0, j1);
-#endif
 }
 void run_proft_ts(Ctx* c, int fuse, int j0, int j1) {
   if (fuse) launch_tma_cols(c, ProftFilterK(c), ALLI, j0, j1);

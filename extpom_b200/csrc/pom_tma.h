@@ -80,19 +80,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-// the same load with an L2 evict-first policy: operands that are streamed once should not push
-// the per-thread Thomas coefficients (local memory, re-read by the upward sweep) out of L2
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint64_t pol) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
-}
-
 template <class F>
 struct SmemOp {
   const double* cur;   // stage of level k, at this thread's own point
@@ -197,19 +184,12 @@ tmacolkernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-#ifdef POM_COL_EVICT_FIRST
-  const uint64_t pol = l2_evict_first_policy();
-#endif
   auto issue = [&](int L) {
     const int s = (L - k0) % NS;
     mbar_expect_tx(&bar[s], (uint32_t)(NF * F::BW * F::BH * sizeof(double)));
 #pragma unroll
     for (int n = 0; n < NF; ++n)
-#ifdef POM_COL_EVICT_FIRST
-      tma_load_3d_hint(ring + (s * NF + n) * PL, &maps.m[n], &bar[s], c0, c1, L - 1, pol);
-#else
       tma_load_3d(ring + (s * NF + n) * PL, &maps.m[n], &bar[s], c0, c1, L - 1);
-#endif
   };
   if (leader)
     for (int L = k0; L < k0 + NS && L <= kl1; ++L) issue(L);
