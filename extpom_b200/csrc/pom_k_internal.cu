@@ -707,7 +707,8 @@ struct AdvT2UpK : KBase {
     }
     const double ar=art(i,j);
     const double eta=first ? etb(i,j) : etf(i,j);                        // :620,684
-    const double hb=(h(i,j)+eta)*ar, hf=(h(i,j)+etf(i,j))*ar;
+    const double hb=(h(i,j)+eta)*ar;
+    RDiv dhf; dhf.set((h(i,j)+etf(i,j))*ar);
     double zk=first ? w(i,j,1)*A3(f_,i,j,1)*ar : 0.;                     // :646-650
     for (int k = 1; k <= kbm1; ++k) {
       double zk1 = 0.;                                                   // :651
@@ -716,8 +717,8 @@ struct AdvT2UpK : KBase {
         zk1=0.5*((zw1+fabs(zw1))*A3(fbm_,i,j,k+1)+(zw1-fabs(zw1))*A3(fbm_,i,j,k));   // :656-660
         zk1=zk1*ar;                                                      // :661
       }
-      double q=xfl(i+1,j,k)-xfl(i,j,k)+yfl(i,j+1,k)-yfl(i,j,k)+(zk-zk1)/dz(k);   // :670-672
-      q=(A3(fbm_,i,j,k)*hb-dti2*q)/hf;                                   // :673-674
+      double q=xfl(i+1,j,k)-xfl(i,j,k)+yfl(i,j+1,k)-yfl(i,j,k)+pdiv(zk-zk1,dz(k));   // :670-672
+      q=dhf(A3(fbm_,i,j,k)*hb-dti2*q);                                   // :673-674
       A3(ff_,i,j,k)=q*m;                                                 // smol_adif :1899
       zk=zk1;
     }
@@ -736,44 +737,44 @@ struct SmolAdifK : KBase {
     const double value_min = 1.e-9, epsilon = 1.0e-14;
     const bool fx = (i >= 2 && j >= 2 && j <= jmm1), fy = (i >= 2 && i <= imm1 && j >= 2);
     const bool fz = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
+    // divisors that do not change along k (:1913,1934): hoisted reciprocals, exact quotients (RDiv).
+    // Every flux is evaluated and then selected (no data-dependent branches in the k loop).
+    RDiv dax, day;
+    dax.set(fx ? aru(i,j)*(dt(i-1,j)+dt(i,j)) : 1.);
+    day.set(fy ? arv(i,j)*(dt(i,j-1)+dt(i,j)) : 1.);
+    const double dtc=dt(i,j);
+    const int iw = fx ? i - 1 : i, js = fy ? j - 1 : j;
+    double fU = 0.;
     for (int k = 1; k <= kbm1; ++k) {
       const double f0=A3(ff_,i,j,k);
       if (fx) {                                                          // :1903-1922
-        const double fW=A3(ff_,i-1,j,k), xm=A3(xm_,i,j,k);
-        double r = 0.;
-        if (!(f0 < value_min || fW < value_min)) {
-          double udx=fabs(xm);
-          double u2dt=dti2*xm*xm*2./(aru(i,j)*(dt(i-1,j)+dt(i,j)));
-          double mol=(f0-fW)/(fW+f0+epsilon);
-          r=(udx-u2dt)*mol*sw;
-          if (fabs(udx) < fabs(u2dt)) r=0.;
-        }
-        A3(xm_,i,j,k)=r;
+        const double fW=A3(ff_,iw,j,k), xm=A3(xm_,i,j,k);
+        const double udx=fabs(xm);
+        const double u2dt=dax(dti2*xm*xm*2.);
+        const double mol=pdiv(f0-fW,fW+f0+epsilon);
+        double r=(udx-u2dt)*mol*sw;
+        r=(fabs(udx) < fabs(u2dt)) ? 0. : r;
+        A3(xm_,i,j,k)=(f0 < value_min || fW < value_min) ? 0. : r;
       }
       if (fy) {                                                          // :1924-1943
-        const double fS=A3(ff_,i,j-1,k), ym=A3(ym_,i,j,k);
-        double r = 0.;
-        if (!(f0 < value_min || fS < value_min)) {
-          double vdy=fabs(ym);
-          double v2dt=dti2*ym*ym*2./(arv(i,j)*(dt(i,j-1)+dt(i,j)));
-          double mol=(f0-fS)/(fS+f0+epsilon);
-          r=(vdy-v2dt)*mol*sw;
-          if (fabs(vdy) < fabs(v2dt)) r=0.;
-        }
-        A3(ym_,i,j,k)=r;
+        const double fS=A3(ff_,i,js,k), ym=A3(ym_,i,j,k);
+        const double vdy=fabs(ym);
+        const double v2dt=day(dti2*ym*ym*2.);
+        const double mol=pdiv(f0-fS,fS+f0+epsilon);
+        double r=(vdy-v2dt)*mol*sw;
+        r=(fabs(vdy) < fabs(v2dt)) ? 0. : r;
+        A3(ym_,i,j,k)=(f0 < value_min || fS < value_min) ? 0. : r;
       }
       if (fz && k >= 2) {                                                // :1945-1964
-        const double fU=A3(ff_,i,j,k-1), zw=A3(zw_,i,j,k);
-        double r = 0.;
-        if (!(f0 < value_min || fU < value_min)) {
-          double wdz=fabs(zw);
-          double w2dt=dti2*zw*zw/(dzz(k-1)*dt(i,j));
-          double mol=(fU-f0)/(f0+fU+epsilon);
-          r=(wdz-w2dt)*mol*sw;
-          if (fabs(wdz) < fabs(w2dt)) r=0.;
-        }
-        A3(zw_,i,j,k)=r;
+        const double zw=A3(zw_,i,j,k);
+        const double wdz=fabs(zw);
+        const double w2dt=pdiv(dti2*zw*zw,dzz(k-1)*dtc);
+        const double mol=pdiv(fU-f0,f0+fU+epsilon);
+        double r=(wdz-w2dt)*mol*sw;
+        r=(fabs(wdz) < fabs(w2dt)) ? 0. : r;
+        A3(zw_,i,j,k)=(f0 < value_min || fU < value_min) ? 0. : r;
       }
+      fU=f0;
     }
   }
 };
