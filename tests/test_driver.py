@@ -1,0 +1,48 @@
+"""The compiled C++ host (examples/pom_driver.cpp: the shape of pom/pom.f + advance.f:6-59 over the C
+ABI) must give bitwise the same fields as the Python-driven library from the same state file."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from extpom_b200 import synthetic as syn
+from extpom_b200.pomgpu import LIBPATH, PomGpu
+from scripts.dump_state import dump, read_out
+from tests import emu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(libdir, libname, exe):
+    src = os.path.join(ROOT, "examples", "pom_driver.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L", libdir, "-l" + libname, "-Wl,-rpath," + libdir])
+    return exe
+
+
+def _run(tmp_path, exe, factory, dims=(22, 18, 8), nstep=5, **kw):
+    state = str(tmp_path / "state.bin")
+    out = str(tmp_path / "out.bin")
+    dump(state, *dims, **kw)
+    r = subprocess.run([exe, state, str(nstep), out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = read_out(out)
+    _, g = syn.seamount(*dims, factory, **kw)
+    for i in range(1, nstep + 1):
+        g.step(i)
+    assert f"{g.check_velocity():.17g}" in r.stdout
+    for n, a in got.items():
+        assert np.array_equal(a, g.get(n).ravel(order="F")), n
+
+
+def test_compiled_driver_on_host_emulation(tmp_path):
+    so = emu.build_emu()
+    exe = _build(os.path.dirname(so), "pomgpu_emu", str(tmp_path / "pom_driver_emu"))
+    _run(tmp_path, exe, emu.EmuPom, island=True)
+
+
+@pytest.mark.gpu
+def test_compiled_driver_on_gpu(tmp_path):
+    exe = _build(os.path.dirname(LIBPATH), "pomgpu", str(tmp_path / "pom_driver"))
+    _run(tmp_path, exe, PomGpu, dims=(40, 36, 12), nstep=6, island=True)
