@@ -164,3 +164,17 @@ def test_division_helpers_are_ieee_exact(emax):
     g = _factory(8, 8, 4)
     bad = g.L.pomgpu_selftest_pdiv(g.h, 1 << 26, 12345 + emax, emax)
     assert bad == 0, bad
+
+
+def test_direct_load_fallback_equals_tma_path(monkeypatch):
+    """POMGPU_NO_TMA=1 (and every odd `im`) runs the same functors on direct global loads instead of
+    TMA-staged tiles: the two device paths must agree bitwise."""
+    dims, nstep = (48, 40, 12), 5
+    _, a = syn.seamount(*dims, _factory, island=True)
+    monkeypatch.setenv("POMGPU_NO_TMA", "1")
+    _, b = syn.seamount(*dims, _factory, island=True)
+    monkeypatch.delenv("POMGPU_NO_TMA")
+    for i in range(1, nstep + 1):
+        a.step(i); b.step(i)
+    for n in pc.F3 + pc.F2:
+        assert np.array_equal(a.get(n), b.get(n)), n
