@@ -102,6 +102,76 @@ struct VertvlK : KBase {
 };
 
 // ---------------------------------------------------------------------------
+// advance.f:365-393 + vertvl (solver.f:1970-2021) + bcondorl(5) in ONE sweep.  The depth sums
+// tps=sum_k u*dz(k), sum_k v*dz(k) come in as 2-D fields (s2c, s2d): the previous step's uv_filter
+// accumulated them, in the same k order, while it produced the arrays that are now u and v
+// (UvSumK recomputes them when u or v were pushed since).  With the sums known, the adjusted
+// velocity of the east / north neighbour that vertvl's flux difference needs is a point-wise
+// expression, so u, v are read once (2R+3W instead of 6+3 passes).  The adjusted fields go to
+// s3a, s3b (neighbours still read the raw u, v); the caller swaps the buffers.
+struct UvAdjVertvlK : KBase {
+  POM_KINFO("uvadjust_vertvl", 2, 3, 14, 0)
+  using KBase::KBase;
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    const double m = fsm(i,j);
+    const bool interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
+    const bool au = (i >= 2), av = (j >= 2);                              // :373, :386
+    const double tu=A2(p.s2c,i,j), tv=A2(p.s2d,i,j);
+    const double ru = au ? (utb(i,j)+utf(i,j))/(dt(i,j)+dt(i-1,j)) : 0.;
+    const double rv = av ? (vtb(i,j)+vtf(i,j))/(dt(i,j)+dt(i,j-1)) : 0.;
+    double tuE = 0., ruE = 0., tvN = 0., rvN = 0., wk = 0., de = 0., cW = 0., cE = 0., cS = 0., cN = 0.;
+    RDiv ddxy; ddxy.set(interior ? dx(i,j)*dy(i,j) : 1.);
+    if (interior) {
+      tuE=A2(p.s2c,i+1,j); ruE=(utb(i+1,j)+utf(i+1,j))/(dt(i+1,j)+dt(i,j));
+      tvN=A2(p.s2d,i,j+1); rvN=(vtb(i,j+1)+vtf(i,j+1))/(dt(i,j+1)+dt(i,j));
+      wk=0.5*(vfluxb(i,j)+vfluxf(i,j));                                 // solver.f:2004
+      de=(etf(i,j)-etb(i,j))/dti2;
+      cW=.25*(dy(i,j)+dy(i-1,j))*(dt(i,j)+dt(i-1,j));                   // :1984-1985,1993-1994
+      cE=.25*(dy(i+1,j)+dy(i,j))*(dt(i+1,j)+dt(i,j));
+      cS=.25*(dx(i,j)+dx(i,j-1))*(dt(i,j)+dt(i,j-1));
+      cN=.25*(dx(i,j+1)+dx(i,j))*(dt(i,j+1)+dt(i,j));
+    }
+    const int ie = interior ? i + 1 : i, jn = interior ? j + 1 : j;
+    for (int k = 1; k <= kbm1; ++k) {
+      PF3(p.u,i,j,k+3); PF3(p.v,i,j,k+3); PF3(p.v,i,jn,k+3);
+      const double u0=u(i,j,k), v0=v(i,j,k);
+      const double ua = au ? (u0-tu)+ru : u0;                           // advance.f:374-375
+      const double va = av ? (v0-tv)+rv : v0;                           // :387-388
+      A3(p.s3a,i,j,k)=ua;
+      A3(p.s3b,i,j,k)=va;
+      if (interior) {
+        const double uE=(u(ie,j,k)-tuE)+ruE, vN=(v(i,jn,k)-tvN)+rvN;
+        w(i,j,k)=wk*m;                                                  // bounds_forcing.f:553-559
+        wk=wk+dz(k)*(ddxy(cE*uE-cW*ua+cN*vN-cS*va)+de);                 // solver.f:2011-2015
+      } else {
+        w(i,j,k)=w(i,j,k)*m;
+      }
+    }
+    A3(p.s3a,i,j,kb)=u(i,j,kb);
+    A3(p.s3b,i,j,kb)=v(i,j,kb);
+    if (interior) w(i,j,kb)=wk;
+  }
+};
+
+// the depth sums of u and v (advance.f:367-369,380-382) when uv_filter's are not current
+struct UvSumK : KBase {
+  POM_KINFO("uv_sum", 2, 0, 0, 2)
+  using KBase::KBase;
+  POM_HD void operator()(int i, int j) const {
+    POM_DIMS;
+    double tu = 0., tv = 0.;
+    for (int k = 1; k <= kbm1; ++k) {
+      PF3(p.u,i,j,k+3); PF3(p.v,i,j,k+3);
+      tu=tu+u(i,j,k)*dz(k);
+      tv=tv+v(i,j,k)*dz(k);
+    }
+    A2(p.s2c,i,j)=tu;
+    A2(p.s2d,i,j)=tv;
+  }
+};
+
+// ---------------------------------------------------------------------------
 // advq (solver.f:411-477) for q2 -> uf and q2l -> vf in one pass, as a tile kernel: each
 // thread evaluates the x/y fluxes of both quantities at its own point once per level.
 struct AdvqK : KBase {
@@ -1463,7 +1533,7 @@ struct AdvProfUVK : KBase {
 // of their neighbours, so the filtered u,v go to the scratch buffers s3a,s3b (which
 // become ub,vb); new u,v stay in uf,vf; the host rotates pointers.
 struct UvFilterK : KBase {
-  POM_KINFO("uv_filter", 6, 2, 2, 0)
+  POM_KINFO("uv_filter", 6, 2, 2, 2)
   using KBase::KBase;
   // Orlanski radiation value from the point `1` cell inside (xf1,xb1), two inside (x2),
   // and the boundary point's own xb0 and x at one inside (x1)
@@ -1479,7 +1549,7 @@ struct UvFilterK : KBase {
     POM_DIMS;
     const bool jin = (j >= 2 && j <= jmm1), iin = (i >= 2 && i <= imm1);
     const double mu=dum(i,j), mv=dvm(i,j);
-    double su = 0., sv = 0.;
+    double su = 0., sv = 0., tu = 0., tv = 0.;
     double nu[KMAX], nv[KMAX];
     const bool edge0 = !(iin && jin) || i == 2 || j == 2;
     for (int k = 1; k <= kbm1; ++k) {
@@ -1508,7 +1578,11 @@ struct UvFilterK : KBase {
       if (edge0) { nu[k]=a; nv[k]=b; }
       su=su+(a+ub(i,j,k)-2.*u(i,j,k))*dz(k);                            // advance.f:474-475
       sv=sv+(b+vb(i,j,k)-2.*v(i,j,k))*dz(k);                            // advance.f:495-496
+      tu=tu+a*dz(k);                                                    // next step's advance.f:367-369:
+      tv=tv+b*dz(k);                                                    // uf, vf become u, v (:512,514)
     }
+    A2(p.s2c,i,j)=tu;
+    A2(p.s2d,i,j)=tv;
     const bool edge = !(iin && jin) || i == 2 || j == 2;
     for (int k = 1; k <= kbm1; ++k) {
       // away from the open boundaries the masked tendency is recomputed from uf,vf (one more
@@ -1668,6 +1742,8 @@ int domain_stats_rows(Ctx* c, double* rows) {
 #define ALLI 1, c->g.im
 void run_uvadjust(Ctx* c, int j0, int j1) { launch_cols(c, UvAdjustK(c), ALLI, j0, j1); }
 void run_vertvl(Ctx* c, int j0, int j1) { launch_cols(c, VertvlK(c), ALLI, j0, j1); }
+void run_uvadj_vertvl(Ctx* c, int j0, int j1) { launch_cols<UvAdjVertvlK, POM_RV_MINB>(c, UvAdjVertvlK(c), ALLI, j0, j1); }
+void run_uvsum(Ctx* c, int j0, int j1) { launch_cols(c, UvSumK(c), ALLI, j0, j1); }
 void run_advq(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvqK(c), ALLI, j0, j1); }
 // the fused variant under its own name / algorithmic byte count in the per-kernel profile
 struct ProfqFilterK : ProfqK {

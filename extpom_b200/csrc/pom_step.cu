@@ -29,6 +29,8 @@ void run_mode_inter_tail(Ctx*, int, int);
 void run_ext_step(Ctx*, int iext, int do_adv, int, int);
 void run_uvadjust(Ctx*, int, int);
 void run_vertvl(Ctx*, int, int);
+void run_uvadj_vertvl(Ctx*, int, int);
+void run_uvsum(Ctx*, int, int);
 void run_advq(Ctx*, int, int);
 void run_profq(Ctx*, int fuse_filter, int, int);
 void run_qfilter(Ctx*, int, int);
@@ -172,6 +174,23 @@ static void k_uvadjust(Group* G) {
   int e = NEED({F_u, 0}, {F_v, 0}, {F_utb, 0}, {F_utf, 0}, {F_vtb, 0}, {F_vtf, 0}, {F_dt, 1});
   EACH(run_uvadjust(c, j0, j1));
   MADE(e, F_u, F_v);
+  for (int r = 0; r < G->n; ++r) G->c[r]->uvsum_ok = 0;   // u, v changed in place
+}
+// stages 0+1 in one sweep (what the step runs); the depth sums come from the last uv_filter
+static void k_uvadjust_vertvl(Group* G) {
+  bool ok = true;
+  for (int r = 0; r < G->n; ++r) ok = ok && G->c[r]->uvsum_ok;
+  if (!ok) {
+    int e = NEED({F_u, 0}, {F_v, 0});
+    EACH(run_uvsum(c, j0, j1));
+    MADE(e, F_s2c, F_s2d);
+  }
+  int e = NEED({F_u, 0}, {F_v, 1}, {F_s2c, 0}, {F_s2d, 1}, {F_utb, 0}, {F_utf, 0}, {F_vtb, 1}, {F_vtf, 1}, {F_dt, 1},
+               {F_etf, 0}, {F_etb, 0}, {F_vfluxb, 0}, {F_w, 0});
+  EACH(run_uvadj_vertvl(c, j0, j1));
+  MADE(e, F_s3a, F_s3b, F_w);
+  group_swap(G, F_u, F_s3a); group_swap(G, F_v, F_s3b);
+  for (int r = 0; r < G->n; ++r) G->c[r]->uvsum_ok = 0;
 }
 static void k_vertvl(Group* G) {
   int e = NEED({F_u, 0}, {F_v, 1}, {F_dt, 1}, {F_etf, 0}, {F_etb, 0}, {F_vfluxb, 0});
@@ -311,7 +330,8 @@ static void k_advprof_v(Group* G) {
 static void k_uvfilter(Group* G) {
   int e = NEED({F_uf, 0}, {F_vf, 0}, {F_u, 0}, {F_v, 0}, {F_ub, 0}, {F_vb, 0});
   EACH(run_uvfilter(c, j0, j1));
-  MADE(e, F_uf, F_vf, F_s3a, F_s3b);
+  MADE(e, F_uf, F_vf, F_s3a, F_s3b, F_s2c, F_s2d);
+  for (int r = 0; r < G->n; ++r) G->c[r]->uvsum_ok = 1;   // s2c, s2d = depth sums of what becomes u, v
   group_swap(G, F_u, F_uf); group_swap(G, F_v, F_vf);      // advance.f:511-514
   group_swap(G, F_ub, F_s3a); group_swap(G, F_vb, F_s3b);
 }
@@ -351,6 +371,7 @@ static int internal_stage(Group* G, int iint, int st) {
   switch (st) {
     case 0: k_uvadjust(G); break;
     case 1: k_vertvl(G); break;
+    case 100: k_uvadjust_vertvl(G); break;          // stages 0-1 in one sweep (what the step runs)
     case 2: k_advq(G); break;
     case 3: k_profq(G, 0); break;
     case 103: k_profq(G, 1); break;                   // profq + bcond(6) + q filter fused (what the step runs)
@@ -382,6 +403,7 @@ static int mode_internal(Group* G, int iint) {
   const Consts& k = G->c[0]->c;
   if ((iint != 1 || k.time0 != 0.) && k.mode != 2)
     for (int st = 0; st <= 15; ++st) {
+      if (st == 0) { internal_stage(G, iint, 100); ++st; continue; }   // u,v adjustment + vertvl in one sweep
       if (st == 3) { internal_stage(G, iint, 103); ++st; continue; }   // profq with the q2/q2l filter fused
       if (st == 5) { internal_stage(G, iint, 105); ++st; continue; }   // advt2 of T and S in one kernel
       if (st == 7) { internal_stage(G, iint, 207); st = 10; continue; }  // proft T,S + t/s filter + dens in one kernel
@@ -475,10 +497,14 @@ int pomgpu_row_offset(const pomgpu_t* p) { return ((const Ctx*)p)->g.joff; }
 const char* pomgpu_last_error(const pomgpu_t* p) { return ((const Ctx*)p)->err; }
 int pomgpu_set_const(pomgpu_t* p, const char* name, double v) { return ctx_set_const(X(p), name, v); }
 int pomgpu_get_const(pomgpu_t* p, const char* name, double* v) { return ctx_get_const(X(p), name, v); }
-int pomgpu_push(pomgpu_t* p, const char* name, const double* host) { apply_pending(X(p)); return ctx_push(X(p), name, host); }
+static void touched(Ctx* c, const char* name) {   // a host push of u or v makes uv_filter's depth sums stale
+  if (!strcmp(name, "u") || !strcmp(name, "v") || !strcmp(name, "s2c") || !strcmp(name, "s2d")) c->uvsum_ok = 0;
+}
+int pomgpu_push(pomgpu_t* p, const char* name, const double* host) { apply_pending(X(p)); touched(X(p), name); return ctx_push(X(p), name, host); }
 int pomgpu_pull(pomgpu_t* p, const char* name, double* host) { apply_pending(X(p)); return ctx_pull(X(p), name, host); }
 int pomgpu_push_rows(pomgpu_t* p, const char* name, const double* host, int row0, int nrows) {
   apply_pending(X(p));
+  touched(X(p), name);
   return ctx_push_rows(X(p), name, host, row0, nrows);
 }
 long pomgpu_field_elems(pomgpu_t* p, const char* name) {
@@ -487,6 +513,7 @@ long pomgpu_field_elems(pomgpu_t* p, const char* name) {
 }
 int pomgpu_push_async(pomgpu_t* p, const char* name, const double* host) {
   Ctx* c = X(p);
+  touched(c, name);
   const FieldInfo* f;
   double** slot = ctx_slot(c, name, &f);
   if (!slot || !*slot) return 2;
