@@ -181,9 +181,15 @@ static void k_uvadjust_vertvl(Group* G) {
   bool ok = true;
   for (int r = 0; r < G->n; ++r) ok = ok && G->c[r]->uvsum_ok;
   if (!ok) {
+    // (a process whose driver pushed u or v; the others may not take this branch, so the ghost-row
+    // validity it records must be the one uv_filter left -- exchange decisions stay identical on
+    // every rank: u, v are at least as valid as the sums uv_filter produced with them)
     int e = NEED({F_u, 0}, {F_v, 0});
     EACH(run_uvsum(c, j0, j1));
-    MADE(e, F_s2c, F_s2d);
+    int eo = e;
+    if (G->valid[F_s2c] < eo) eo = G->valid[F_s2c];
+    if (G->valid[F_s2d] < eo) eo = G->valid[F_s2d];
+    MADE(eo, F_s2c, F_s2d);
   }
   int e = NEED({F_u, 0}, {F_v, 1}, {F_s2c, 0}, {F_s2d, 1}, {F_utb, 0}, {F_utf, 0}, {F_vtb, 1}, {F_vtf, 1}, {F_dt, 1},
                {F_etf, 0}, {F_etb, 0}, {F_vfluxb, 0}, {F_w, 0});

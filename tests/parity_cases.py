@@ -285,3 +285,17 @@ def check_forcing_interp(factory, dims=(24, 19, 9), nstep=8):
             assert np.array_equal(o.get(n), g.get(n)), n
         o.step(i); g.step(i)
     return assert_close(o, g)
+
+
+def check_push_midrun(factory, dims=(24, 19, 9)):
+    """A driver that overwrites u and v between steps (restart, nudging): the depth sums uv_filter
+    left for the next step's u,v adjustment are stale and must be recomputed (uv_sum)."""
+    st, o, g = pair(factory, dims, island=True)
+    for i in range(1, 4):
+        o.step(i); g.step(i)
+    for n, f in (("u", 0.9), ("v", 1.1)):
+        a = np.asfortranarray(o.get(n) * f)
+        o.put(n, a); g.put(n, a)
+    for i in range(4, 7):
+        o.step(i); g.step(i)
+    return assert_close(o, g)

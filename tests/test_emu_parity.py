@@ -51,3 +51,7 @@ def test_domain_stats_matches_oracle():
 
 def test_forcing_interpolation_matches_oracle():
     pc.check_forcing_interp(EmuPom)
+
+
+def test_push_of_u_v_between_steps():
+    pc.check_push_midrun(EmuPom)

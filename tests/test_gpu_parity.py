@@ -178,3 +178,7 @@ def test_direct_load_fallback_equals_tma_path(monkeypatch):
         a.step(i); b.step(i)
     for n in pc.F3 + pc.F2:
         assert np.array_equal(a.get(n), b.get(n)), n
+
+
+def test_push_of_u_v_between_steps():
+    pc.check_push_midrun(_factory)
