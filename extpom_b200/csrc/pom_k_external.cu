@@ -121,7 +121,7 @@ struct ExtStepK : KBase {
   int iext, do_adv;
   ExtStepK(const Ctx* x, int ie, int adv) : KBase(x), iext(ie), do_adv(adv) {}
 #ifndef POM_EXT_TY
-#define POM_EXT_TY 16
+#define POM_EXT_TY 12
 #define POM_EXT_MINB 2
 #endif
   static constexpr int NV = M2 ? 7 : 6, TY = POM_EXT_TY, MINB = POM_EXT_MINB;
