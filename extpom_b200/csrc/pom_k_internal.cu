@@ -23,13 +23,13 @@
 #define POM_ADVPROF_NS 3
 #endif
 #ifndef POM_PROFQ_MINB
-#define POM_PROFQ_MINB 2
+#define POM_PROFQ_MINB 3
 #endif
 #ifndef POM_PROFQ_NS
 #define POM_PROFQ_NS 3
 #endif
 #ifndef POM_PROFQ_TY
-#define POM_PROFQ_TY 8
+#define POM_PROFQ_TY 6
 #endif
 #ifndef POM_PROFT_TY
 #define POM_PROFT_TY 8
