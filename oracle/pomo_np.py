@@ -8,7 +8,7 @@ compiled here, so the C oracle is itself a restatement; this module restates
     profq   pom/solver.f:1212-1538      advt2 + smol_adif  pom/solver.f:577-731,1880-1967
     baropg_mcc  pom/solver.f:943-1159   advct   pom/solver.f:201-409
     advu / advv   pom/solver.f:734-845  profu / profv  pom/solver.f:1686-1877
-    realvertvl    pom/solver.f:2024-2066
+    realvertvl    pom/solver.f:2024-2066   advt1  pom/solver.f:480-574
     mode_external + bcond(1), bcond(2)  pom/advance.f:205-353, pom/bounds_forcing.f:18-83
     lateral_viscosity, mode_interaction, mode_internal  pom/advance.f:96-202,356-537
     bcond(4), bcond(6), bcondorl(3), bcondorl(5)  pom/bounds_forcing.f:151-324,418-487,550-561
@@ -989,7 +989,7 @@ def mode_interaction(f, c):
 
 
 def mode_internal(f, c, first_cold_step=False):
-    """pom/advance.f:356-537 for mode=3, nadv=2, nitera from c, nbct/nbcs in {1,3}, lrestore off."""
+    """pom/advance.f:356-537 for mode=3, nadv in {1,2}, nitera from c, nbct/nbcs in {1,3}, lrestore off."""
     im, jm, kb = f["u"].shape
     kbm1 = kb - 1
     dz, dt, smoth = f["dz"], f["dt"], c["smoth"]
@@ -1021,8 +1021,12 @@ def mode_internal(f, c, first_cold_step=False):
         f["q2b"], f["q2"] = q2, f["uf"].copy(order="F")
         f["q2lb"], f["q2l"] = q2l, f["vf"].copy(order="F")
         # tracers
-        f["uf"], f["tb"] = advt2(f, c, f["tb"], f["t"], f["tclim"], f["uf"])
-        f["vf"], f["sb"] = advt2(f, c, f["sb"], f["s"], f["sclim"], f["vf"])
+        if int(c["nadv"]) == 1:
+            f["uf"], f["tb"], f["t"] = advt1(f, c, f["tb"], f["t"], f["tclim"], f["uf"])
+            f["vf"], f["sb"], f["s"] = advt1(f, c, f["sb"], f["s"], f["sclim"], f["vf"])
+        else:
+            f["uf"], f["tb"] = advt2(f, c, f["tb"], f["t"], f["tclim"], f["uf"])
+            f["vf"], f["sb"] = advt2(f, c, f["sb"], f["s"], f["sclim"], f["vf"])
         n = NP(f, c)
         f["uf"] = n.proft(f["uf"], f["wtsurf"], f["tsurf"], int(c["nbct"]))
         f["vf"] = n.proft(f["vf"], f["wssurf"], f["ssurf"], int(c["nbcs"]))
@@ -1031,6 +1035,19 @@ def mode_internal(f, c, first_cold_step=False):
         s = f["s"] + .5 * smoth * (f["vf"] + f["sb"] - 2. * f["s"])
         f["tb"], f["t"] = t, f["uf"].copy(order="F")
         f["sb"], f["s"] = s, f["vf"].copy(order="F")
+        if int(c.get("lrestore", 0)):                                    # bounds_forcing.f:1083-1109
+            trst = np.float64(np.float32(30.))
+            ntime = int(c["time"] / trst)
+            fnew = c["time"] / trst - ntime
+            fold = 1. - fnew
+            K = slice(0, kbm1)
+            trstr = fold * f["trstrb"][:, :, K] + fnew * f["trstrf"][:, :, K]
+            srstr = fold * f["srstrb"][:, :, K] + fnew * f["srstrf"][:, :, K]
+            tau = fold * f["taurstrb"][:, :, K] + fnew * f["taurstrf"][:, :, K]
+            g2 = 2. * c["dti"] / 86400.
+            for nme, tgt in (("t", trstr), ("tb", trstr), ("s", srstr), ("sb", srstr)):
+                x = f[nme][:, :, K]
+                f[nme][:, :, K] = x + g2 * tau * (tgt - x)
         for nme in ("t", "tb", "s", "sb"):                               # restore_interior's mask (:1113-1118)
             f[nme][:, :, :kbm1] = f[nme][:, :, :kbm1] * f["fsm"][:, :, None]
         f["rho"] = NP(f, c).dens(f["s"], f["t"])
@@ -1066,3 +1083,41 @@ def step(f, c, iint):
     for iext in range(1, int(c["isplit"]) + 1):
         mode_external(f, c, iext)
     mode_internal(f, c, first_cold_step=(iint == 1 and c["time0"] == 0.))
+
+
+def advt1(f, c, fb_in, fq_in, fclim, ff_in):
+    """pom/solver.f:480-574 (nadv=1).  Returns (ff, fb, f) -- fb and f with the reference's side
+    effects (level kb copies, the (fb-fclim)+fclim round trip)."""
+    u, v, w, aam, dt, h, dx, dy, dum, dvm, art, etb, etf, dz = (
+        f[n] for n in "u v w aam dt h dx dy dum dvm art etb etf dz".split())
+    im, jm, kb = u.shape
+    imm1, jmm1, kbm1 = im - 1, jm - 1, kb - 1
+    fq = fq_in.copy(order="F"); fb = fb_in.copy(order="F"); ff = ff_in.copy(order="F")
+    fq[:, :, kb - 1] = fq[:, :, kbm1 - 1]
+    fb[:, :, kb - 1] = fb[:, :, kbm1 - 1]
+    xflux = np.zeros((im, jm, kb), order="F"); yflux = np.zeros((im, jm, kb), order="F")
+    I, J = (2, im), (2, jm)
+    R = lambda x, di=0, dj=0: _R(x, I, J, di, dj, kbm1)
+    xflux[1:, 1:, :kbm1] = .25 * ((R(dt) + R(dt, -1, 0)) * (R(fq) + R(fq, -1, 0)) * R(u))
+    yflux[1:, 1:, :kbm1] = .25 * ((R(dt) + R(dt, 0, -1)) * (R(fq) + R(fq, 0, -1)) * R(v))
+    fb = fb - fclim
+    xflux[1:, 1:, :kbm1] = (R(xflux) - .5 * (R(aam) + R(aam, -1, 0)) * (R(h) + R(h, -1, 0)) * c["tprni"]
+                            * (R(fb) - R(fb, -1, 0)) * R(dum) / (R(dx) + R(dx, -1, 0)))
+    yflux[1:, 1:, :kbm1] = (R(yflux) - .5 * (R(aam) + R(aam, 0, -1)) * (R(h) + R(h, 0, -1)) * c["tprni"]
+                            * (R(fb) - R(fb, 0, -1)) * R(dvm) / (R(dy) + R(dy, 0, -1)))
+    xflux[1:, 1:, :kbm1] = .5 * (R(dy) + R(dy, -1, 0)) * R(xflux)
+    yflux[1:, 1:, :kbm1] = .5 * (R(dx) + R(dx, 0, -1)) * R(yflux)
+    fb = fb + fclim
+    zflux = np.zeros((im, jm, kb + 1), order="F")          # zflux(:,:,kb)=0, and k+1 up to kb
+    In = (slice(1, imm1), slice(1, jmm1))
+    zflux[In + (0,)] = fq[In + (0,)] * w[In + (0,)] * art[In]
+    for k in range(2, kbm1 + 1):
+        zflux[In + (k - 1,)] = .5 * (fq[In + (k - 2,)] + fq[In + (k - 1,)]) * w[In + (k - 1,)] * art[In]
+    for k in range(1, kbm1 + 1):
+        z = k - 1
+        ff[In + (z,)] = (xflux[2:im, 1:jmm1, z] - xflux[1:imm1, 1:jmm1, z]
+                         + yflux[1:imm1, 2:jm, z] - yflux[1:imm1, 1:jmm1, z]
+                         + (zflux[In + (z,)] - zflux[In + (z + 1,)]) / dz[z])
+        ff[In + (z,)] = ((fb[In + (z,)] * (h[In] + etb[In]) * art[In] - c["dti2"] * ff[In + (z,)])
+                         / ((h[In] + etf[In]) * art[In]))
+    return ff, fb, fq

@@ -224,7 +224,8 @@ STATE = ("aam advx advy drhox drhoy kh km kq l q2b q2 q2lb q2l rho sb s tb t ub 
          "vaf vtb vtf vfluxb wubot wvbot").split()
 
 
-@pytest.mark.parametrize("kw", [{}, {"nitera": 2, "sw": 1.0}, {"nbct": 3, "nbcs": 3}], ids=["default", "nitera2", "nbc3"])
+@pytest.mark.parametrize("kw", [{}, {"nitera": 2, "sw": 1.0}, {"nbct": 3, "nbcs": 3}, {"nadv": 1}],
+                         ids=["default", "nitera2", "nbc3", "nadv1"])
 def test_whole_step_second_restatement(kw):
     """One WHOLE internal step (advance.f:21-32: lateral_viscosity, mode_interaction, isplit x
     mode_external, mode_internal with every solver.f routine and bcond / bcondorl call) through the
@@ -250,3 +251,26 @@ def test_whole_step_second_restatement(kw):
                 assert np.array_equal(a[:, :, :-1], b[:, :, :-1]), (i, n, float(np.abs(a - b).max()))
             else:
                 assert np.array_equal(a, b), (i, n, float(np.abs(a - b).max()))
+
+
+def test_whole_step_with_restoring():
+    """restore_interior's nudging (bounds_forcing.f:1083-1118) inside the whole step, both restatements."""
+    from oracle import pomo_np
+    st, o = syn.seamount(25, 20, 9, Oracle, island=True, isplit=6, dte=6.0)
+    rng = np.random.default_rng(5)
+    fl = st["fields"]
+    for n, a in (("trstrb", fl["tclim"] + 0.5), ("trstrf", fl["tclim"] - 0.25), ("srstrb", fl["sclim"] + 0.1),
+                 ("srstrf", fl["sclim"] - 0.05), ("taurstrb", 0.2 + 0.1 * rng.random(fl["tclim"].shape)),
+                 ("taurstrf", 0.3 + 0.1 * rng.random(fl["tclim"].shape))):
+        o.put(n, np.asfortranarray(a))
+    o.set("lrestore", 1)
+    for i in range(1, 4):
+        o.step(i)
+    i = 4
+    o.set("iint", i); o.set("time", o.getc("dti") * i / 86400.0)
+    f = {n: o.get(n) for n in o.f}
+    c = {n: o.getc(n) for n in ALLC + ["lrestore"]}
+    pomo_np.step(f, c, i)
+    o.step(i)
+    for n in ("t", "tb", "s", "sb", "u", "v", "q2", "el"):
+        assert np.array_equal(o.get(n), f[n]), n
