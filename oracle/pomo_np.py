@@ -194,8 +194,10 @@ class NP:
 
     # ----------------------------------------------------------------- proft
     def proft(self, fin, wfsurf, fsurf, nbc):
-        """nbc 1 or 3 (no short-wave penetration: rad == 0)."""
-        assert nbc in (1, 3)
+        """pom/solver.f:1541-1683.  nbc 2 and 4 add the short-wave penetration `rad` (:1602-1615), which
+        the reference evaluates in quad precision; numpy's long double (80-bit here) stands in for it, so
+        those two cases are compared with a 1-ulp-scale tolerance instead of bitwise."""
+        assert nbc in (1, 2, 3, 4)
         f, c = self.f, self.c
         im, jm, kb = self.im, self.jm, self.kb
         kbm1, kbm2 = kb - 1, kb - 2
@@ -209,9 +211,24 @@ class NP:
             a[:, :, k - 2] = -dti2 * (kh[:, :, k - 1] + umol) / (dz[k - 2] * dzz[k - 2] * dh * dh)
             cc[:, :, k - 1] = -dti2 * (kh[:, :, k - 1] + umol) / (dz[k - 1] * dzz[k - 2] * dh * dh)
         ff = fin.copy(order="F")
+        rad = np.zeros((im, jm, kb), order="F")
+        if nbc in (2, 4):
+            ntp = int(c["ntp"])
+            r_ = (.58, .62, .67, .77, .78)[ntp - 1]
+            ad1 = (.35, .60, 1.0, 1.5, 1.4)[ntp - 1]
+            ad2 = (23., 20., 17., 14., 7.9)[ntp - 1]
+            L = np.longdouble
+            for k in range(1, kbm1 + 1):
+                x1 = (f["z"][k - 1] * dh / ad1).astype(L)
+                x2 = (f["z"][k - 1] * dh / ad2).astype(L)
+                rad[:, :, k - 1] = (f["swrad"].astype(L) * (L(r_) * np.exp(x1) + L(1. - r_) * np.exp(x2))).astype(np.float64)
         if nbc == 1:
             ee[:, :, 0] = a[:, :, 0] / (a[:, :, 0] - 1.)
             gg[:, :, 0] = dti2 * wfsurf / (dz[0] * dh) - ff[:, :, 0]
+            gg[:, :, 0] = gg[:, :, 0] / (a[:, :, 0] - 1.)
+        elif nbc == 2:
+            ee[:, :, 0] = a[:, :, 0] / (a[:, :, 0] - 1.)
+            gg[:, :, 0] = dti2 * (wfsurf + rad[:, :, 0] - rad[:, :, 1]) / (dz[0] * dh) - ff[:, :, 0]
             gg[:, :, 0] = gg[:, :, 0] / (a[:, :, 0] - 1.)
         else:
             ee[:, :, 0] = 0.
@@ -220,9 +237,11 @@ class NP:
             K = k - 1
             gg[:, :, K] = 1. / (a[:, :, K] + cc[:, :, K] * (1. - ee[:, :, K - 1]) - 1.)
             ee[:, :, K] = a[:, :, K] * gg[:, :, K]
-            gg[:, :, K] = (cc[:, :, K] * gg[:, :, K - 1] - ff[:, :, K]) * gg[:, :, K]
+            gg[:, :, K] = ((cc[:, :, K] * gg[:, :, K - 1] - ff[:, :, K]
+                            + dti2 * (rad[:, :, K] - rad[:, :, K + 1]) / (dh * dz[K])) * gg[:, :, K])
         K = kbm1 - 1
-        ff[:, :, K] = ((cc[:, :, K] * gg[:, :, K - 1] - ff[:, :, K])
+        ff[:, :, K] = ((cc[:, :, K] * gg[:, :, K - 1] - ff[:, :, K]
+                        + dti2 * (rad[:, :, K] - rad[:, :, K + 1]) / (dh * dz[K]))
                        / (cc[:, :, K] * (1. - ee[:, :, K - 1]) - 1.))
         for k in range(2, kbm1 + 1):
             ki = kb - k
@@ -374,6 +393,8 @@ def mode_external(f, c, iext):
     elf[...] = elf * f["fsm"]
     if iext % int(c["ispadv"]) == 0:
         f["advua"][...], f["advva"][...] = NP(f, c).advave()
+        if int(c.get("mode", 3)) == 2:
+            advave_mode2(f)
     el, elb, uaf, vaf, cor, ea = f["el"], f["elb"], f["uaf"], f["vaf"], f["cor"], f["e_atmos"]
     aru, arv = f["aru"], f["arv"]
     I, J, Iw, Jn = sl(2, im), sl(2, jmm1), sl(2, im, -1), sl(2, jmm1, 1)
@@ -1121,3 +1142,33 @@ def advt1(f, c, fb_in, fq_in, fclim, ff_in):
         ff[In + (z,)] = ((fb[In + (z,)] * (h[In] + etb[In]) * art[In] - c["dti2"] * ff[In + (z,)])
                          / ((h[In] + etf[In]) * art[In]))
     return ff, fb, fq
+
+
+def advave_mode2(f):
+    """advave's mode=2 block (pom/solver.f:123-195): bottom stress from the depth-averaged velocity
+    and the curvature terms, in place on wubot, wvbot, advua, advva (one sub-domain)."""
+    cbc, uab, vab, ua, va, dx, dy, d, aru, arv = (f[n] for n in "cbc uab vab ua va dx dy d aru arv".split())
+    im, jm = d.shape
+    imm1, jmm1 = im - 1, jm - 1
+    I, J = (2, imm1), (2, jmm1)
+    r = lambda x, di=0, dj=0, I=I, J=J: x[I[0] - 1 + di:I[1] + di, J[0] - 1 + dj:J[1] + dj]
+    f["wubot"][1:imm1, 1:jmm1] = (-0.5 * (r(cbc) + r(cbc, -1, 0))
+                                  * np.sqrt(r(uab) ** 2 + (.25 * (r(vab) + r(vab, 0, 1) + r(vab, -1, 0) + r(vab, -1, 1))) ** 2)
+                                  * r(uab))
+    f["wvbot"][1:imm1, 1:jmm1] = (-0.5 * (r(cbc) + r(cbc, 0, -1))
+                                  * np.sqrt(r(vab) ** 2 + (.25 * (r(uab) + r(uab, 1, 0) + r(uab, 0, -1) + r(uab, 1, -1))) ** 2)
+                                  * r(vab))
+    curv = np.zeros((im, jm), order="F")
+    curv[1:imm1, 1:jmm1] = (.25 * ((r(va, 0, 1) + r(va)) * (r(dy, 1, 0) - r(dy, -1, 0))
+                                   - (r(ua, 1, 0) + r(ua)) * (r(dx, 0, 1) - r(dx, 0, -1)))
+                            / (r(dx) * r(dy)))
+    Iu = (3, imm1)                                   # n_west == -1
+    ru = lambda x, di=0, dj=0: r(x, di, dj, Iu, J)
+    f["advua"][2:imm1, 1:jmm1] = (ru(f["advua"]) - ru(aru) * .25
+                                  * (ru(curv) * ru(d) * (ru(va, 0, 1) + ru(va))
+                                     + ru(curv, -1, 0) * ru(d, -1, 0) * (ru(va, -1, 1) + ru(va, -1, 0))))
+    Jv = (3, jmm1)                                   # n_south == -1
+    rv = lambda x, di=0, dj=0: r(x, di, dj, I, Jv)
+    f["advva"][1:imm1, 2:jmm1] = (rv(f["advva"]) + rv(arv) * .25
+                                  * (rv(curv) * rv(d) * (rv(ua, 1, 0) + rv(ua))
+                                     + rv(curv, 0, -1) * rv(d, 0, -1) * (rv(ua, 1, -1) + rv(ua, 0, -1))))

@@ -9,7 +9,7 @@ from oracle.pomo import Oracle
 from oracle.pomo_np import NP
 
 NEED = ("h fsm dum dvm dx dy art dt d et etb etf ua va uab vab aam2d vfluxb vfluxf z zz dz dzz "
-        "u v w aam rmean rho t s kh q2 q2b q2l q2lb drhox drhoy uf vf wtsurf wssurf tsurf ssurf").split()
+        "u v w aam rmean rho t s kh q2 q2b q2l q2lb drhox drhoy uf vf wtsurf wssurf tsurf ssurf swrad").split()
 
 
 @pytest.fixture(scope="module")
@@ -19,7 +19,7 @@ def spun():
         o.step(i)
     o.set("iint", 5)
     f = {n: o.get(n) for n in NEED}
-    c = {n: o.getc(n) for n in ("grav", "rhoref", "tbias", "sbias", "dti2", "umol", "ramp")}
+    c = {n: o.getc(n) for n in ("grav", "rhoref", "tbias", "sbias", "dti2", "umol", "ramp", "ntp")}
     return o, NP(f, c), f
 
 
@@ -70,12 +70,17 @@ def test_advave(spun):
     assert np.array_equal(o.get("advva"), av)
 
 
-@pytest.mark.parametrize("nbc", [1, 3])
+@pytest.mark.parametrize("nbc", [1, 2, 3, 4])
 def test_proft(spun, nbc):
     o, n, f = spun
     o.put("uf", f["t"])
     o.proft("uf", "wtsurf", "tsurf", nbc)
-    assert np.array_equal(o.get("uf"), n.proft(f["t"], f["wtsurf"], f["tsurf"], nbc))
+    want = n.proft(f["t"], f["wtsurf"], f["tsurf"], nbc)
+    if nbc in (1, 3):
+        assert np.array_equal(o.get("uf"), want)
+    else:   # short-wave penetration: quad-precision exp in the reference / C oracle, long double here
+        assert np.abs(o.get("uf") - want).max() <= 4e-16 * np.abs(want).max()
+        assert np.abs(want - n.proft(f["t"], f["wtsurf"], f["tsurf"], nbc - 1)).max() > 1e-9
     o.put("uf", f["uf"])
 
 
@@ -274,3 +279,26 @@ def test_whole_step_with_restoring():
     o.step(i)
     for n in ("t", "tb", "s", "sb", "u", "v", "q2", "el"):
         assert np.array_equal(o.get(n), f[n]), n
+
+
+def test_mode2_external_substeps():
+    """mode=2 (2-D only): advave's bottom-stress / curvature block (solver.f:123-195) inside the
+    external substeps, both restatements."""
+    from oracle.pomo_np import mode_external
+    st, o = syn.seamount(27, 22, 10, Oracle, island=True, isplit=8, dte=6.0, mode=2)
+    for i in range(1, 3):
+        o.step(i)
+    o.set("iint", 3); o.set("time", o.getc("dti") * 3 / 86400.0)
+    o.lateral_viscosity(); o.mode_interaction()
+    names = ("h fsm dum dvm dx dy art aru arv cor cbc e_atmos d ua va uab vab el elb elf uaf vaf etf egf utf vtf "
+             "advua advva adx2d ady2d drx2d dry2d wusurf wvsurf wubot wvbot vfluxf aam2d z "
+             "uabw uabe vabw vabe elw ele vabs vabn uabs uabn els eln").split()
+    f = {n: o.get(n) for n in names}
+    c = {n: o.getc(n) for n in ("grav", "alpha", "dte", "dte2", "smoth", "ramp", "isplit", "ispadv", "ispi",
+                                "isp2i", "rfw", "rfe", "rfs", "rfn", "mode")}
+    for iext in range(1, 9):
+        o.mode_external(iext)
+        mode_external(f, c, iext)
+        for k in ("el", "ua", "va", "uaf", "vaf", "elf", "advua", "advva", "wubot", "wvbot", "utf", "vtf"):
+            assert np.array_equal(o.get(k), f[k]), (iext, k, float(np.abs(o.get(k) - f[k]).max()))
+    assert np.abs(f["wubot"]).max() > 0
