@@ -1,18 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- grid-cell updates/s of one internal step of the extPOM hot path on B200.
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --gpus N --steps K ...  # reference arm: CPU restatement
+  python bench.py --gpus N --steps K --warmup W [--config C]           # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K --warmup W ...   # reference arm: CPU restatement
 
 A "step" is one pass of advance.f:21-32 (lateral_viscosity, mode_interaction, isplit x
-mode_external, mode_internal) over the synthetic seamount state of BASELINE.json
-configs[1] (1024 x 1024 x 41, isplit=30) per GPU.  `value` = im*jm*kb*K / device time of
-the K steps with the state resident in HBM; `e2e` = the same K steps through the public
-API with the per-step forcing pushed from pinned host buffers and check_velocity's scalar
-read back, host<->device copies inside the timed region.
+mode_external, mode_internal) over a synthetic seamount state.  --config selects the BASELINE.json
+configuration (default: configs[1], the one the metric is quoted on):
 
-The reference (Fortran+MPI+PnetCDF) cannot be built in this image, so the reference arm
-and `cpu_baseline` time the C restatement under oracle/ (kind "port") on the host cores.
+  step1024     configs[1]  seamount 1024 x 1024 x 41 per GPU, isplit=30 (weak scaling in j-strips)
+  tracer2048   configs[2]  tracer-only bench: advt2 (MPDATA) of T and S + proft x2 on 2048 x 2048 x 41, 1 GPU
+  strong4096   configs[3]  seamount 4096 x 4096 x 41 GLOBAL, strong scaling over N >= 2 GPUs
+  weak2048x61  configs[4]  seamount 2048 x 2048 x 61 per GPU (weak scaling), full Mellor-Yamada closure
+
+`value` = cells*K / device time of K steps with the state resident in HBM; `e2e` = the same K steps
+through the public API with the per-step forcing pushed from pinned host buffers and one scalar read
+back, host<->device copies inside the timed region.
+
+The reference (Fortran+MPI+PnetCDF) cannot be built in this image, so the reference arm and
+`cpu_baseline` time the C restatement under oracle/ (kind "port") on the host cores.
 """
 import argparse
 import json
@@ -30,6 +36,15 @@ UNIT = "cell-updates/s"
 FORCING_2D = ("wusurf", "wvsurf", "wtsurf", "swrad", "tsurf")          # bounds_forcing.f:908-909,954-955,978
 FORCING_BDY = ("tbe", "sbe", "tbw", "sbw", "tbn", "sbn", "tbs", "sbs",  # bounds_forcing.f:844-865
                "uabe", "uabw", "vabn", "vabs", "ele", "els")
+TRACER_FORCING = ("wtsurf", "wssurf", "swrad", "tsurf", "ssurf")        # what proft reads (solver.f:1617-1648)
+
+# name -> (im, jm, kb, jm is per GPU?, scaling, BASELINE.json index)
+CONFIGS = {
+    "step1024": (1024, 1024, 41, True, "weak", 1),
+    "tracer2048": (2048, 2048, 41, True, "weak", 2),
+    "strong4096": (4096, 4096, 41, False, "strong", 3),
+    "weak2048x61": (2048, 2048, 61, True, "weak", 4),
+}
 
 
 def parse():
@@ -38,16 +53,54 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--im", type=int, default=1024)
-    ap.add_argument("--jm", type=int, default=1024, help="rows PER GPU (weak scaling)")
-    ap.add_argument("--kb", type=int, default=41)
-    ap.add_argument("--cpu-sample", type=int, default=512, help="im=jm of the CPU-baseline sample grid")
+    ap.add_argument("--config", default="step1024", choices=sorted(CONFIGS))
+    ap.add_argument("--im", type=int, default=0, help="override the configuration's im (development)")
+    ap.add_argument("--jm", type=int, default=0, help="override jm (per GPU for weak configurations)")
+    ap.add_argument("--kb", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="reference arm / cpu_baseline: im=jm of the sample grid (0 = the configuration's own "
+                         "grid for the reference arm at N=1, one GPU's strip at N>1; 512 for cpu_baseline)")
+    ap.add_argument("--cpu-budget", type=float, default=240.0, help="reference arm: stop after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-nrank-parity", action="store_true")
+    a = ap.parse_args()
+    im, jm, kb, per_gpu, scaling, idx = CONFIGS[a.config]
+    a.im, a.jm, a.kb = a.im or im, a.jm or jm, a.kb or kb
+    a.per_gpu, a.scaling, a.cfg_index = per_gpu, scaling, idx
+    a.overridden = (a.im, a.jm, a.kb) != (im, jm, kb)
+    return a
+
+
+def workload_label(a, world):
+    im, kb = a.im, a.kb
+    tag = "" if a.overridden else f" (BASELINE configs[{a.cfg_index}])"
+    if a.config == "tracer2048":
+        return (f"tracer-only advt2 (MPDATA, nitera=1) of T and S + proft x2, {im}x{a.jm}x{kb} on 1 GPU{tag}")
+    if a.per_gpu:
+        return (f"seamount {im}x{a.jm}x{kb} per GPU (global {im}x{a.jm * world}x{kb}), isplit=30, "
+                f"nadv=2 nitera=1 mode=3{tag}")
+    return (f"seamount {im}x{a.jm}x{kb} global, strong scaling over {world} GPU(s) in j-strips, isplit=30, "
+            f"nadv=2 nitera=1 mode=3{tag}")
+
+
+def host_cores():
+    """CPU cores this process may actually use (affinity mask and cgroup quota, not the host's count)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(p) + 0.5)))
+    except Exception:
+        pass
+    return n
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons; started BEFORE warm-up (nvidia-smi needs a few hundred ms
+    to deliver its first line), evaluated over the timed regions."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -56,7 +109,7 @@ class ClockSampler:
         self.rows, self.p = [], None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -69,59 +122,119 @@ class ClockSampler:
 
     def stop(self, t0, t1):
         if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.12)
         self.p.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, pw, reasons = [], None, [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for ts, line in self.rows:
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+            if len(f) < 7 or not (t0 <= ts <= t1 + 0.06):
                 continue
             try:
-                sm.append(float(f[0])); mx = float(f[1])
+                sm.append(float(f[0])); mx = float(f[1]); pw.append(float(f[2]))
             except ValueError:
                 continue
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw) if pw else None,
+                "window": "both timed regions (resident + e2e)"}
 
 
-def cpu_reference_rate(n, kb, steps, warmup):
-    """Oracle (C restatement, OpenMP over all host cores) on an n x n x kb seamount sample."""
-    from oracle.pomo import Oracle
+def cpu_rate(im, jm, kb, steps, warmup, threads, variant="", budget=1e9, tracer=False):
+    """Oracle (C restatement) on an im x jm x kb seamount: (cell-updates/s, s/step, steps actually timed)."""
+    from oracle import pomo
     from extpom_b200 import synthetic as syn
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    st, o = syn.seamount(n, n, kb, Oracle)
+    pomo.set_threads(threads)
+    st, o = syn.seamount(im, jm, kb, lambda a, b, c: pomo.Oracle(a, b, c, variant=variant))
+    del st
+
+    def one(i):
+        if tracer:   # configs[2]: advt2(tb,t,tclim,uf), advt2(sb,s,sclim,vf), proft x2 (advance.f:430-441)
+            o.set("iint", i)
+            o.advt2("tb", "t", "tclim", "uf"); o.advt2("sb", "s", "sclim", "vf")
+            o.proft("uf", "wtsurf", "tsurf", 1); o.proft("vf", "wssurf", "ssurf", 1)
+        else:
+            o.step(i)
+
     for i in range(1, warmup + 1):
-        o.step(i)
+        one(i)
     t0 = time.perf_counter()
+    done = 0
     for i in range(warmup + 1, warmup + steps + 1):
-        o.step(i)
+        one(i)
+        done += 1
+        if time.perf_counter() - t0 > budget:
+            break
     dt = time.perf_counter() - t0
-    return n * n * kb * steps / dt, dt / steps, cores
+    o.close()
+    return im * jm * kb * done / dt, dt / done, done
 
 
-def run_reference(a, rank):
+def run_reference(a, rank, world):
+    """Reference arm: the CPU restatement of the path on all host cores this process may use.
+    N=1: the configuration's own grid.  N>1: rank 0 alone, ONE strip of the global grid (1/N of the
+    workload -- the CPU is the same box whatever N, and its cell-updates/s do not depend on the grid
+    size); the sample is stated in cpu_baseline.sample and config.reference_sample."""
     if rank != 0:
         return
-    val, spt, cores = cpu_reference_rate(a.cpu_sample, a.kb, a.steps, max(a.warmup, 1))
-    sample = (f"{a.steps} internal steps of the seamount state at {a.cpu_sample}x{a.cpu_sample}x{a.kb} "
-              f"(isplit=30) after {max(a.warmup, 1)} warm-up steps; C restatement of advance.f/solver.f, "
-              f"gcc -O2 -ffp-contract=off, OpenMP x{cores}")
+    cores = host_cores()
+    tracer = a.config == "tracer2048"
+    if a.cpu_sample:
+        im = jm = a.cpu_sample
+    elif a.per_gpu:
+        im, jm = a.im, a.jm                                  # one GPU's share = the whole grid at N=1
+    else:
+        im, jm = a.im, max(64, a.jm // max(world, 1))        # strong scaling: one strip of the global grid
+    kb = a.kb
+    if im * jm * kb > 1024 * 1024 * 41 and not a.cpu_sample:  # keep the host footprint / run time bounded
+        jm = max(64, (1024 * 1024 * 41) // (im * kb))
+    W = max(min(a.warmup, 2), 1)
+    val, spt, done = cpu_rate(im, jm, kb, a.steps, W, cores, budget=a.cpu_budget, tracer=tracer)
+    jm_glob = a.jm * world if a.per_gpu else a.jm
+    whole = (im, jm) == (a.im, jm_glob)
+    what = "the whole grid of this configuration" if whole else (
+        f"a {im}x{jm}x{kb} sample of the {a.im}x{jm_glob}x{kb} global grid (same generator, same namelist)")
+    sample = (f"{done} internal steps on {what} after {W} warm-up step(s); C restatement of advance.f/solver.f "
+              f"(oracle/), gcc -O2 -ffp-contract=off, OpenMP on {cores} threads"
+              + ("" if done == a.steps else f"; stopped after {a.cpu_budget:.0f} s of the {a.steps} steps asked for"))
     emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": spt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"seamount {a.im}x{a.jm}x{a.kb} per GPU, isplit=30 (BASELINE configs[1])",
-                   "l2": "inputs larger than L2"},
+        "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_label(a, world), "parallelism": f"OpenMP x{cores} on the host",
+                   "reference_sample": "whole grid" if whole else f"{im}x{jm}x{kb}",
+                   "steps_timed": done, "l2": "inputs larger than any CPU cache"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
+
+
+def cpu_baseline(a):
+    """cpu_baseline of the GPU arm (N=1): the oracle on a bounded sample, plus SURVEY 8(d)'s variants
+    (-O0 like makefile_dist:17, -O3 -march=native; one thread = "one MPI rank", all threads)."""
+    cores = host_cores()
+    tracer = a.config == "tracer2048"
+    n = a.cpu_sample or 512
+    kb = a.kb
+    val, spt, done = cpu_rate(n, n, kb, 4, 1, cores, tracer=tracer)
+    out = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"{done} internal steps at {n}x{n}x{kb} (isplit=30) after 1 warm-up; C restatement of "
+                     f"advance.f/solver.f (oracle/), gcc -O2 -ffp-contract=off, OpenMP on {cores} threads",
+           "variants": []}
+    m = min(n, 256)
+    for flags, variant, threads in (("-O2", "", 1), ("-O0", "O0", 1), ("-O0", "O0", cores),
+                                    ("-O3 -march=native", "O3", 1), ("-O3 -march=native", "O3", cores)):
+        try:
+            v, s, d = cpu_rate(m, m, kb, 2, 1, threads, variant=variant, tracer=tracer)
+            out["variants"].append({"flags": flags + " -ffp-contract=off", "threads": threads, "value": v,
+                                    "sample": f"{d} steps at {m}x{m}x{kb}"})
+        except Exception as e:  # noqa: BLE001
+            out["variants"].append({"flags": flags, "threads": threads, "error": str(e)[:80]})
+    return out
 
 
 _REAL_STDOUT = None
@@ -142,6 +255,77 @@ def emit(obj):
     f.flush()
 
 
+def nrank_parity(rank, world, local, dist):
+    """SURVEY 8(e) acceptance, run before the timing: N strips connected over NCCL must reproduce the
+    single-domain run bitwise (parallel_mpi.f:154-351 semantics).  Every rank steps its strip of a
+    256 x 64N x 16 island case and compares its owned rows with a single-domain run on its own GPU."""
+    import numpy as np
+    import torch
+    from extpom_b200 import synthetic as syn
+    from extpom_b200.pomgpu import PomGpu
+    from extpom_b200.strips import StripSet
+    im, jm, kb, steps = 256, 64 * world, 16, 4
+    fields = "u v t s q2 q2l el ua va w km kh rho ub tb etf wubot aam advx".split()
+    m = StripSet.create(im, jm, kb, rank, world, device=local, dist=dist, ghost=4, island=True)
+    _, whole = syn.seamount(im, jm, kb, lambda x, y, z: PomGpu(x, y, z, device=local), island=True)
+    for i in range(1, steps + 1):
+        m.step(i); whole.step(i)
+    bad = []
+    j0, j1 = m.rows
+    for n in fields:
+        x = whole.get(n)[:, j0 - 1:j1]
+        y = m.group.gather(n)
+        if n in ("t", "tb", "s"):
+            x, y = x[:, :, :-1], y[:, :, :-1]
+        if not np.array_equal(x, y):
+            bad.append(n)
+    nex, _ = m.group.exchanges()
+    t = torch.tensor([len(bad)], device="cuda")
+    dist.all_reduce(t)
+    m.group.close(); m.gpu.close(); whole.close()
+    return {"bitwise": int(t.item()) == 0, "fields": len(fields), "grid": f"{im}x{jm}x{kb}", "steps": steps,
+            "ranks": world, "transport": "NCCL send/recv", "exchanges_per_step": nex / steps,
+            "mismatched_on_rank0": bad}
+
+
+def tracer_state(g, n, kb):
+    """configs[2]: only the fields advt2 and proft read are generated (one 3-D array at a time)."""
+    import numpy as np
+    from extpom_b200 import synthetic as syn
+    st = syn.make_state(n, n, 4)                      # 2-D fields and constants (independent of kb)
+    f2, c = st["fields"], st["consts"]
+    for k, v in c.items():
+        g.L.pomgpu_set_const(g.h, k.encode(), float(v))
+    z, zz, dz, dzz = syn.sigma_levels(kb)
+    for nme, arr in (("z", z), ("zz", zz), ("dz", dz), ("dzz", dzz)):
+        g.put(nme, arr)
+    for nme in "dx dy h fsm dum dvm art aru arv cor dt etb etf wtsurf wssurf swrad".split():
+        g.put(nme, f2[nme])
+    h, fsm, dum, dvm = f2["h"], f2["fsm"], f2["dum"], f2["dvm"]
+    rng = np.random.default_rng(syn.SEED)
+    shape = (n, n, kb)
+
+    def push(name, make):
+        arr = np.asfortranarray(make())
+        g.put(name, arr)
+        return arr
+
+    tb = push("tb", lambda: (5.0 + 15.0 * np.exp(zz[None, None, :] * h[:, :, None] / 1000.0)
+                             + 1e-2 * rng.standard_normal(shape)) * fsm[:, :, None])
+    g.put("t", tb); g.put("tclim", tb); g.put("tsurf", np.asfortranarray(tb[:, :, 0]))
+    del tb
+    sb = push("sb", lambda: (35.0 + 1e-2 * rng.standard_normal(shape)) * fsm[:, :, None])
+    g.put("s", sb); g.put("sclim", sb); g.put("ssurf", np.asfortranarray(sb[:, :, 0]))
+    del sb
+    push("u", lambda: (0.2 + 1e-2 * rng.uniform(-1, 1, shape)) * dum[:, :, None])
+    push("v", lambda: 1e-2 * rng.uniform(-1, 1, shape) * dvm[:, :, None])
+    push("w", lambda: 1e-5 * rng.uniform(-1, 1, shape) * fsm[:, :, None])
+    push("aam", lambda: np.full(shape, 500.0))
+    push("kh", lambda: 1e-3 * (1.0 + rng.random(shape)))
+    q = np.full(shape, 1e-9, order="F")
+    g.put("q2", q); g.put("q2l", q)
+
+
 def main():
     a = parse()
     _guard_stdout()
@@ -149,13 +333,23 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if a.impl == "reference":
-        return run_reference(a, rank)
+        return run_reference(a, rank, world)
 
     import numpy as np
     import torch
     from extpom_b200 import synthetic as syn
     from extpom_b200.pomgpu import PomGpu
     from extpom_b200.strips import StripSet
+
+    tracer = a.config == "tracer2048"
+    base = {"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+    if (tracer and world > 1) or (a.config == "strong4096" and world < 2 and not a.overridden):
+        why = ("the tracer-only bench is a single-GPU configuration" if tracer else
+               "4096x4096x41 needs ~176 GB of resident fields: 1 GPU does not fit (SURVEY.md App. B); run with --gpus >= 2")
+        if rank == 0:
+            emit(dict(base, value=None, ms_per_step=None, config={"workload": workload_label(a, world)}, unavailable=why))
+        return
 
     dist = None
     if world > 1:
@@ -165,11 +359,30 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sampler = ClockSampler(local)            # before anything else: its first sample takes a while
+    parity = None
+    if world > 1 and not a.no_nrank_parity:
+        parity = nrank_parity(rank, world, local, dist)
+
     K, W = a.steps, max(a.warmup, 3)
     im, kb = a.im, a.kb
-    jm_global = a.jm * world            # weak scaling: a.jm rows per GPU, strips stacked in j
-    model = StripSet.create(im, jm_global, kb, rank, world, device=local, dist=dist)
-    g = model.gpu
+    jm_global = a.jm * world if a.per_gpu else a.jm
+    if tracer:
+        g = PomGpu(im, a.jm, kb, device=local)
+        tracer_state(g, im, kb)
+        g.set("nitera", 1); g.set("sw", 0.5)
+
+        class _Tracer:
+            gpu = g
+
+            @staticmethod
+            def step(iint):
+                g.internal_stage(2, 105)      # advt2 of T (-> uf) and of S (-> vf), solver.f:577-731
+                g.internal_stage(2, 107)      # proft of both, solver.f:1541-1683
+        model = _Tracer
+    else:
+        model = StripSet.create(im, jm_global, kb, rank, world, device=local, dist=dist)
+        g = model.gpu
     cells = im * jm_global * kb
 
     def barrier():
@@ -191,7 +404,6 @@ def main():
     barrier()
 
     # ---- timed region 1: state resident in HBM --------------------------------------
-    sampler = ClockSampler(local)
     g.launch_count(reset=True)
     barrier()
     t0 = time.time()
@@ -203,14 +415,13 @@ def main():
     host_ms = (time.perf_counter() - th0) * 1e3 / K      # host time to ENQUEUE one step (asynchronous)
     g.event_record(1)
     barrier()
-    t1 = time.time()
     ms = maxreduce(g.event_elapsed_ms(0, 1))
     launches = g.launch_count(reset=True)
-    clocks = sampler.stop(t0, t1)
     value = cells * K / (ms * 1e-3)
 
     # ---- timed region 2: end to end through the public API with host buffers --------
-    pins = {n: g.pinned(n) for n in FORCING_2D + FORCING_BDY}
+    names = TRACER_FORCING if tracer else FORCING_2D + FORCING_BDY
+    pins = {n: g.pinned(n) for n in names}
     for n, buf in pins.items():
         buf[...] = g.get(n)
     h2d = sum(b.nbytes for b in pins.values())
@@ -223,7 +434,7 @@ def main():
         model.step(iint)
         # advance.f:52: one scalar back per step -- read with one step of lag, so that the host
         # can enqueue the next step's forcing copies while this step still computes
-        return g.check_velocity_lagged()
+        return g.field_absmax_lagged("uf") if tracer else g.check_velocity_lagged()
 
     for _ in range(2):                          # untimed: allocates the shadow buffers of the async pushes
         e2e_step()
@@ -232,11 +443,13 @@ def main():
     vmax = 0.0
     for _ in range(K):
         vmax = max(vmax, e2e_step())
-    vmax = max(vmax, g.check_velocity())       # the last step's own value (waits)
+    vmax = max(vmax, g.field_absmax_lagged("uf") if tracer else g.check_velocity())   # the last step's own value (waits)
     g.event_record(3)
     barrier()
+    t1 = time.time()
     ms_e2e = maxreduce(g.event_elapsed_ms(2, 3))
     e2e = cells * K / (ms_e2e * 1e-3)
+    clocks = sampler.stop(t0, t1)
 
     # ---- per-kernel CUDA-event times for the roofline of the dominant kernel ----------
     g.profile_begin()
@@ -274,29 +487,30 @@ def main():
         if dist is not None:
             dist.destroy_process_group()
         return
-    out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"seamount {im}x{a.jm}x{kb} per GPU (global {im}x{jm_global}x{kb}), isplit=30, "
-                               "nadv=2 nitera=1 mode=3" + (" (BASELINE configs[1])" if (im, a.jm, kb) == (1024, 1024, 41) else ""),
+    nfields = 41 if kb else 0
+    out = dict(base)
+    out.update({
+        "value": value, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "config": {"workload": workload_label(a, world), "name": a.config,
                    "parallelism": f"j-strips x{world}",
-                   "l2": f"inputs larger than L2 ({41 * im * a.jm * kb * 8 / 1e9:.0f} GB state per GPU)",
+                   "l2": f"inputs larger than L2 ({nfields * im * (jm_global // world) * kb * 8 / 1e9:.0f} GB state per GPU)",
                    "seed": syn.SEED},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-                "ms_per_step": ms_e2e / K, "vamax": vmax},
+                "ms_per_step": ms_e2e / K, "vamax": vmax,
+                "note": ("per step: the forcing arrays are pushed from pinned host buffers (double-buffered on a copy "
+                         "stream), the step runs, and check_velocity's scalar (advance.f:52) is read back with ONE STEP "
+                         "OF LAG so the host never waits for the step it has just enqueued; output / restart pulls "
+                         "(every iprint / irestart steps in the reference, advance.f:35-49) are not part of a step")},
         "gpu_launches": launches,
         "host_enqueue_ms_per_step": host_ms,
         "roofline": roof,
         "kernels": kernels,
-    }
+    })
+    if parity is not None:
+        out["nrank_parity"] = parity
     if world == 1 and not a.no_cpu_baseline:
-        val, spt, cores = cpu_reference_rate(a.cpu_sample, kb, 8, 1)
-        out["cpu_baseline"] = {
-            "value": val, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"8 internal steps at {a.cpu_sample}x{a.cpu_sample}x{kb} (isplit=30) after 1 warm-up; "
-                      "C restatement of advance.f/solver.f (oracle/), gcc -O2 -ffp-contract=off, OpenMP"}
+        out["cpu_baseline"] = cpu_baseline(a)
     emit(out)
     if dist is not None:
         dist.destroy_process_group()

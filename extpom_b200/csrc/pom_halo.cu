@@ -140,6 +140,11 @@ void group_destroy(Group* G) {
   }
 #ifndef POMGPU_EMU
   if (G->nccl) g_nccl.CommDestroy(G->nccl);
+  for (int b = 0; b < 4; ++b) if (G->hbuf[b]) cudaFreeHost(G->hbuf[b]);
+  for (int r = 0; r < 16; ++r) {
+    if (G->ev_pack[r]) cudaEventDestroy((cudaEvent_t)G->ev_pack[r]);
+    if (G->ev_copy[r]) cudaEventDestroy((cudaEvent_t)G->ev_copy[r]);
+  }
 #endif
   free(G);
 }
@@ -163,6 +168,34 @@ void group_set_callback(Group* G, halo_cb cb, void* user) { G->cb = cb; G->cb_us
 
 static bool has_s(const Ctx* c) { return c->jown0 > 1; }
 static bool has_n(const Ctx* c) { return c->jown1 < c->g.jmg; }
+
+// a transport failure: the ghost rows are stale from here on -- mark the group (nothing is
+// launched any more, pom_step.cu) and every strip (the reference's error convention)
+static int fail(Group* G, const char* msg) {
+  G->failed = 1;
+  for (int r = 0; r < G->n; ++r) {
+    snprintf(G->c[r]->err, sizeof(G->c[r]->err), "%s", msg);
+    G->c[r]->c.error_status = 1;
+  }
+  fprintf(stderr, "pomgpu: %s\n", msg);
+  return 1;
+}
+
+// copy between the staging buffers of two strips of this process, on the DESTINATION's stream
+static int dev_copy_between(Ctx* dc, double* dst, Ctx* sc, const double* src, size_t n) {
+#ifdef POMGPU_EMU
+  (void)sc; return dev_d2d(dc, dst, src, n);
+#else
+  if (dc->device == sc->device) return dev_d2d(dc, dst, src, n);
+  cudaSetDevice(dc->device);
+  if (cudaMemcpyPeerAsync(dst, dc->device, src, sc->device, n * 8, (cudaStream_t)dc->stream) != cudaSuccess) {
+    snprintf(dc->err, sizeof(dc->err), "peer copy between devices %d and %d failed", sc->device, dc->device);
+    dc->c.error_status = 1;
+    return 1;
+  }
+  return 0;
+#endif
+}
 
 // Exchange `ghost` rows of the listed fields across every seam; afterwards they are valid to
 // full depth.  One pack kernel, one transfer and one unpack kernel per direction and strip,
@@ -197,17 +230,44 @@ int group_exchange(Group* G, const int* fields, int nf) {
         if ((size_t)P.total > G->bufcap[r][b]) {
           if (G->buf[r][b]) { dev_sync(c); dev_free(c, G->buf[r][b]); }
           G->bufcap[r][b] = (size_t)P.total * 2;
-          if (dev_alloc(c, &G->buf[r][b], G->bufcap[r][b])) return 1;
+          if (dev_alloc(c, &G->buf[r][b], G->bufcap[r][b])) return fail(G, "halo exchange: out of device memory");
         }
       }
       if (has_s(c)) run_pack(c, J[r][0], G->buf[r][0], false);
       if (has_n(c)) run_pack(c, J[r][1], G->buf[r][1], false);
     }
-    // seams inside this process
+    // seams inside this process.  Strips on one device share a stream (program order); strips on
+    // different devices have their own streams, so the copy into b's receive buffer must wait for
+    // a's pack (and vice versa), and nobody may re-pack a send buffer the other side still reads.
     for (int r = 0; r + 1 < G->n; ++r) {
       Ctx *a = G->c[r], *b = G->c[r + 1];
-      dev_d2d(b, G->buf[r + 1][2], G->buf[r][1], (size_t)J[r][1].total);   // a's north rows -> b's south ghosts
-      dev_d2d(a, G->buf[r][3], G->buf[r + 1][0], (size_t)J[r + 1][0].total);
+#ifndef POMGPU_EMU
+      const bool cross = (a->stream != b->stream);
+      if (cross) {
+        for (int q = r; q <= r + 1; ++q)
+          if (!G->ev_pack[q]) {
+            cudaEvent_t e;
+            cudaSetDevice(G->c[q]->device);
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming); G->ev_pack[q] = (void*)e;
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming); G->ev_copy[q] = (void*)e;
+          }
+        cudaSetDevice(a->device); cudaEventRecord((cudaEvent_t)G->ev_pack[r], (cudaStream_t)a->stream);
+        cudaSetDevice(b->device); cudaEventRecord((cudaEvent_t)G->ev_pack[r + 1], (cudaStream_t)b->stream);
+        cudaStreamWaitEvent((cudaStream_t)b->stream, (cudaEvent_t)G->ev_pack[r], 0);
+        cudaSetDevice(a->device); cudaStreamWaitEvent((cudaStream_t)a->stream, (cudaEvent_t)G->ev_pack[r + 1], 0);
+      }
+#endif
+      int rc = dev_copy_between(b, G->buf[r + 1][2], a, G->buf[r][1], (size_t)J[r][1].total);   // a's north rows -> b's south ghosts
+      rc |= dev_copy_between(a, G->buf[r][3], b, G->buf[r + 1][0], (size_t)J[r + 1][0].total);
+      if (rc) return 1;
+#ifndef POMGPU_EMU
+      if (cross) {   // the next pack into a send buffer waits until the neighbour's copy has read it
+        cudaSetDevice(b->device); cudaEventRecord((cudaEvent_t)G->ev_copy[r + 1], (cudaStream_t)b->stream);
+        cudaSetDevice(a->device); cudaEventRecord((cudaEvent_t)G->ev_copy[r], (cudaStream_t)a->stream);
+        cudaStreamWaitEvent((cudaStream_t)a->stream, (cudaEvent_t)G->ev_copy[r + 1], 0);
+        cudaSetDevice(b->device); cudaStreamWaitEvent((cudaStream_t)b->stream, (cudaEvent_t)G->ev_copy[r], 0);
+      }
+#endif
     }
     // seams to other processes
     Ctx* cs = G->c[0];
@@ -215,15 +275,36 @@ int group_exchange(Group* G, const int* fields, int nf) {
     const bool xs = has_s(cs), xn = has_n(cn);
     if (xs || xn) {
       if (G->cb) {
+        const long ns = xs ? J[0][0].total : 0, nn = xn ? J[G->n - 1][1].total : 0;
+        double *ss = xs ? G->buf[0][0] : nullptr, *rs = xs ? G->buf[0][2] : nullptr;
+        double *sn = xn ? G->buf[G->n - 1][1] : nullptr, *rn = xn ? G->buf[G->n - 1][3] : nullptr;
+#ifndef POMGPU_EMU
+        // the callback works on host memory: mirror the device staging buffers in pinned memory
+        const long want[4] = {ns, nn, ns, nn};
+        for (int b = 0; b < 4; ++b)
+          if ((size_t)want[b] > G->hbufcap[b]) {
+            if (G->hbuf[b]) cudaFreeHost(G->hbuf[b]);
+            G->hbufcap[b] = (size_t)want[b] * 2;
+            if (cudaMallocHost((void**)&G->hbuf[b], G->hbufcap[b] * sizeof(double)) != cudaSuccess) { G->hbuf[b] = nullptr; G->hbufcap[b] = 0; return fail(G, "halo transport: out of pinned host memory"); }
+          }
+        if (xs && dev_d2h(cs, G->hbuf[0], ss, (size_t)ns)) return fail(G, "halo transport: D2H");
+        if (xn && dev_d2h(cn, G->hbuf[1], sn, (size_t)nn)) return fail(G, "halo transport: D2H");
+        ss = xs ? G->hbuf[0] : nullptr; sn = xn ? G->hbuf[1] : nullptr;
+        double *drs = rs, *drn = rn;
+        rs = xs ? G->hbuf[2] : nullptr; rn = xn ? G->hbuf[3] : nullptr;
+#else
         dev_sync(cs); if (cn != cs) dev_sync(cn);
-        int rc = G->cb(G->cb_user,
-                       xs ? G->buf[0][0] : nullptr, xs ? G->buf[0][2] : nullptr, xs ? J[0][0].total : 0,
-                       xn ? G->buf[G->n - 1][1] : nullptr, xn ? G->buf[G->n - 1][3] : nullptr, xn ? J[G->n - 1][1].total : 0);
-        if (rc) return 1;
+#endif
+        if (G->cb(G->cb_user, ss, rs, ns, sn, rn, nn)) return fail(G, "halo transport callback failed");
+#ifndef POMGPU_EMU
+        if (xs && dev_h2d(cs, drs, rs, (size_t)ns)) return fail(G, "halo transport: H2D");
+        if (xn && dev_h2d(cn, drn, rn, (size_t)nn)) return fail(G, "halo transport: H2D");
+#endif
       }
 #ifndef POMGPU_EMU
       else if (G->nccl) {
         const int ncclDouble = 8;
+        cudaSetDevice(cs->device);
         g_nccl.GroupStart();
         if (xs) {
           g_nccl.Send(G->buf[0][0], (size_t)J[0][0].total, ncclDouble, G->rank - 1, G->nccl, (cudaStream_t)cs->stream);
@@ -234,14 +315,10 @@ int group_exchange(Group* G, const int* fields, int nf) {
           g_nccl.Recv(G->buf[G->n - 1][3], (size_t)J[G->n - 1][1].total, ncclDouble, G->rank + 1, G->nccl, (cudaStream_t)cn->stream);
         }
         int rc = g_nccl.GroupEnd();
-        if (rc) { snprintf(cs->err, 256, "nccl exchange: %s", g_nccl.GetErrorString(rc)); cs->c.error_status = 1; return 1; }
+        if (rc) { char m[200]; snprintf(m, sizeof(m), "nccl exchange: %s", g_nccl.GetErrorString(rc)); return fail(G, m); }
       }
 #endif
-      else {
-        snprintf(cs->err, 256, "strip has a seam but no transport is connected");
-        cs->c.error_status = 1;
-        return 1;
-      }
+      else return fail(G, "strip has a seam but no transport is connected");
     }
     for (int r = 0; r < G->n; ++r) {
       Ctx* c = G->c[r];
@@ -284,7 +361,7 @@ int group_need(Group* G, const Req* in, int n) {
     }
     for (size_t q = 0; q < sizeof(live2d) / sizeof(int); ++q) add(live2d[q]);
     if (any3d) for (size_t q = 0; q < sizeof(live3d) / sizeof(int); ++q) add(live3d[q]);
-    group_exchange(G, stale, ns);
+    if (group_exchange(G, stale, ns)) return 0;   // G->failed is set: the caller launches nothing
   }
   int e = G->ghost;
   for (int q = 0; q < n; ++q) {

@@ -8,8 +8,10 @@ constexpr int HALO_MAXF = 16;   // fields per pack kernel launch
 
 struct NcclId { char internal[128]; };
 
-// host transport used by the CPU tests (gloo): exchange with the south / north neighbour
-// process; buffers are the strips' staging buffers (host memory in the emulation build)
+// host transport (gloo in the CPU tests, MPI in a Fortran driver): exchange with the south / north
+// neighbour process.  The buffers handed to the callback are always HOST memory: the strips'
+// staging buffers themselves in the emulation build, page-locked mirrors of the device staging
+// buffers (copied D2H before and H2D after the call) in the CUDA build.
 typedef int (*halo_cb)(void* user, const double* send_s, double* recv_s, long n_s,
                        const double* send_n, double* recv_n, long n_n);
 
@@ -26,6 +28,9 @@ struct Group {
   void* nccl;            // ncclComm_t (one process per GPU)
   int rank, world;
   halo_cb cb; void* cb_user;
+  double* hbuf[4]; size_t hbufcap[4];   // pinned host mirrors for the callback transport (CUDA build)
+  void* ev_pack[16]; void* ev_copy[16];  // cross-stream ordering of in-process seams between devices
+  int failed;            // a transport failed: ghost rows are stale, nothing is launched any more
   long n_exchanges, n_fields_exchanged;
 };
 

@@ -6,8 +6,8 @@
 #include "pom_core.h"
 #include "pom_tma.h"
 #include "pom_names.h"
+#include "pom_bcond.h"
 
-#define KMAX 64
 // min blocks/SM of the plain column kernels whose occupancy (not traffic) limits them: capping
 // them at 64 registers (4 x 256 threads) was measured at 0.43 -> 0.28 ms for realvertvl
 #ifndef POM_RV_MINB
@@ -310,7 +310,8 @@ struct ProfqK : KBase {
     b[T] = p.t; b[S] = p.s; b[RHO] = p.rho; b[Q2B] = p.q2b; b[Q2LB] = p.q2lb; b[Q2] = p.q2; b[U] = p.u; b[V] = p.v;
     b[KM] = p.km; b[KH] = p.kh; b[KQ] = p.kq; b[UF] = p.uf; b[VF] = p.vf;
   }
-  struct Cols { double ee[KMAX], gg[KMAX], e2v[KMAX], g2v[KMAX]; };
+  static constexpr int NVEC = 4;   // eliminated coefficients of the two systems (ee, gg of q2; ee, gg of q2l)
+  enum { C_EE, C_GG, C_E2, C_G2 };
   struct State {
     double hh, dh, kl0, m, ccm, kqm, kq0, rhom, um, uEm, vm, vNm, eem, ggm, e2m, g2m, q2_2, ufkb;
     int il, ir, jl, jr;
@@ -331,7 +332,8 @@ struct ProfqK : KBase {
           kq(i+di,j+dj,k)=nkq*me; km(i+di,j+dj,k)=nkm*me; kh(i+di,j+dj,k)=nkh*me;
         }
   }
-  POM_HD void pre(int i, int j, State& st, Cols& cm) const {
+  template <class CM>
+  POM_HD void pre(int i, int j, State& st, CM& cm) const {
     POM_DIMS;
     const double surfl = 2.e5;                                                // :1244
     st.interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
@@ -354,10 +356,10 @@ struct ProfqK : KBase {
     st.m = fsm(i,j);
     st.eem = 0.; st.ggm = cgg*utau2;                                          // ee(1), gg(1) :1296-1297
     st.e2m = 0.; st.g2m = 0.;
-    cm.ee[1]=st.eem; cm.gg[1]=st.ggm;
+    cm.put(C_EE,1,st.eem); cm.put(C_GG,1,st.ggm);
   }
-  template <class Op>
-  POM_HD void level(int i, int j, int k, State& st, Cols& cm, const Op& o) const {
+  template <class Op, class CM>
+  POM_HD void level(int i, int j, int k, State& st, CM& cm, const Op& o) const {
     POM_DIMS;
     const double a1 = 0.92, b1 = 16.6, a2 = 0.74, b2 = 10.1, c1 = 0.08;     // :1241
     const double e1 = 1.8, e2 = 1.33, sef = 1., shiw = 0.;                   // :1242-1244
@@ -450,7 +452,7 @@ struct ProfqK : KBase {
       double gi=pdiv(1.,a+cq*(1.-st.eem)-(2.*dti2*dtf+1.));
       st.eem=a*gi;
       st.ggm=(-2.*dti2*pr+cq*st.ggm-o(UF,0,0))*gi;
-      cm.ee[k]=st.eem; cm.gg[k]=st.ggm;
+      cm.put(C_EE,k,st.eem); cm.put(C_GG,k,st.ggm);
     }
     // q2l forward elimination (:1417-1446)
     {
@@ -466,7 +468,7 @@ struct ProfqK : KBase {
         st.e2m=a*gi;
         st.g2m=(dti2*(-pr*ll*e1)+cq*st.g2m-vk)*gi;
       }
-      cm.e2v[k]=st.e2m; cm.g2v[k]=st.g2m;
+      cm.put(C_E2,k,st.e2m); cm.put(C_G2,k,st.g2m);
     }
     // km, kh, kq (:1478-1506) -- in place; kq's old value stays in kqm for level k+1
     {
@@ -495,30 +497,15 @@ struct ProfqK : KBase {
     q2b(i,j,k)=q+.5*smoth*(a+qb-2.*q);                                  // advance.f:416
     q2lb(i,j,k)=ql+.5*smoth*(b+qlb-2.*ql);                              // advance.f:417
   }
-  POM_HD void post(int i, int j, State& st, Cols& cm) const {
+  template <class CM>
+  POM_HD void post(int i, int j, State& st, CM& cm) const {
     POM_DIMS;
     if (!st.interior) {
       if (!fuse) return;
       // boundary columns: bcond(6) upstream values (bounds_forcing.f:264-311)
       for (int k = kb; k >= 1; --k) {
         double a, b;
-        if (j == 1) {                                                     // south (:290-299)
-          double u1=2.*v(i,2,k)*dti/(dy(i,1)+dy(i,2));
-          if (u1 >= 0.) { a=q2(i,1,k)-u1*(q2(i,1,k)-small); b=q2l(i,1,k)-u1*(q2l(i,1,k)-small); }
-          else { a=q2(i,1,k)-u1*(q2(i,2,k)-q2(i,1,k)); b=q2l(i,1,k)-u1*(q2l(i,2,k)-q2l(i,1,k)); }
-        } else if (j == jm) {                                             // north (:302-311)
-          double u1=2.*v(i,jm,k)*dti/(dy(i,jm)+dy(i,jmm1));
-          if (u1 <= 0.) { a=q2(i,jm,k)-u1*(small-q2(i,jm,k)); b=q2l(i,jm,k)-u1*(small-q2l(i,jm,k)); }
-          else { a=q2(i,jm,k)-u1*(q2(i,jm,k)-q2(i,jmm1,k)); b=q2l(i,jm,k)-u1*(q2l(i,jm,k)-q2l(i,jmm1,k)); }
-        } else if (i == 1) {                                              // west (:264-273)
-          double u1=2.*u(2,j,k)*dti/(dx(1,j)+dx(2,j));
-          if (u1 >= 0.) { a=q2(1,j,k)-u1*(q2(1,j,k)-small); b=q2l(1,j,k)-u1*(q2l(1,j,k)-small); }
-          else { a=q2(1,j,k)-u1*(q2(2,j,k)-q2(1,j,k)); b=q2l(1,j,k)-u1*(q2l(2,j,k)-q2l(1,j,k)); }
-        } else {                                                          // east (:276-285)
-          double u1=2.*u(im,j,k)*dti/(dx(im,j)+dx(imm1,j));
-          if (u1 <= 0.) { a=q2(im,j,k)-u1*(small-q2(im,j,k)); b=q2l(im,j,k)-u1*(small-q2l(im,j,k)); }
-          else { a=q2(im,j,k)-u1*(q2(im,j,k)-q2(imm1,j,k)); b=q2l(im,j,k)-u1*(q2l(im,j,k)-q2l(imm1,j,k)); }
-        }
+        bcond6_edge(*this, i, j, k, a, b);                                // bounds_forcing.f:257-311
         emit(i,j,k,a,b,st.m);
       }
       return;
@@ -526,13 +513,13 @@ struct ProfqK : KBase {
     if (!fuse) {
       double up=st.ufkb;
       for (int ki = kbm1; ki >= 1; --ki) {
-        up=cm.ee[ki]*up+cm.gg[ki];
+        up=cm.get(C_EE,ki)*up+cm.get(C_GG,ki);
         uf(i,j,ki)=(ki >= 2) ? fabs(up) : up;
       }
       double vp = 0.;                                                         // vf(kb)=0 (:1420)
       vf(i,j,kb)=0.;
       for (int ki = kbm1; ki >= 2; --ki) {
-        vp=cm.e2v[ki]*vp+cm.g2v[ki];
+        vp=cm.get(C_E2,ki)*vp+cm.get(C_G2,ki);
         vf(i,j,ki)=fabs(vp);
       }
       vf(i,j,1)=0.;                                                           // :1419
@@ -540,12 +527,12 @@ struct ProfqK : KBase {
     }
     double up=st.ufkb, vp = 0.;
     emit(i,j,kb,up,0.,st.m);                                                  // uf(kb) (:1285), vf(kb)=0 (:1420)
-    // the eliminated coefficients come back from local memory (L2): fetch them one level ahead
-    double e1n=cm.ee[kbm1], g1n=cm.gg[kbm1], e2n=cm.e2v[kbm1], g2n=cm.g2v[kbm1];
+    // the eliminated coefficients come back from the column scratch (L2): fetch them one level ahead
+    double e1n=cm.get(C_EE,kbm1), g1n=cm.get(C_GG,kbm1), e2n=cm.get(C_E2,kbm1), g2n=cm.get(C_G2,kbm1);
     for (int ki = kbm1; ki >= 2; --ki) {
       const double e1c=e1n, g1c=g1n, e2c=e2n, g2c=g2n;
-      e1n=cm.ee[ki-1]; g1n=cm.gg[ki-1];
-      if (ki > 2) { e2n=cm.e2v[ki-1]; g2n=cm.g2v[ki-1]; }
+      e1n=cm.get(C_EE,ki-1); g1n=cm.get(C_GG,ki-1);
+      if (ki > 2) { e2n=cm.get(C_E2,ki-1); g2n=cm.get(C_G2,ki-1); }
       {   // operands of the level below, towards L1 while this one is finished
         const int o = POM_I3(i,j,ki-1);
         POM_PREFETCH(p.q2+o); POM_PREFETCH(p.q2b+o); POM_PREFETCH(p.q2l+o); POM_PREFETCH(p.q2lb+o);
@@ -571,23 +558,7 @@ struct QFilterK : KBase {
     const double m = fsm(i,j);
     for (int k = 1; k <= kb; ++k) {
       double a=uf(i,j,k), b=vf(i,j,k);
-      if (j == 1) {                                                     // south (:290-299)
-        double u1=2.*v(i,2,k)*dti/(dy(i,1)+dy(i,2));
-        if (u1 >= 0.) { a=q2(i,1,k)-u1*(q2(i,1,k)-small); b=q2l(i,1,k)-u1*(q2l(i,1,k)-small); }
-        else { a=q2(i,1,k)-u1*(q2(i,2,k)-q2(i,1,k)); b=q2l(i,1,k)-u1*(q2l(i,2,k)-q2l(i,1,k)); }
-      } else if (j == jm) {                                             // north (:302-311)
-        double u1=2.*v(i,jm,k)*dti/(dy(i,jm)+dy(i,jmm1));
-        if (u1 <= 0.) { a=q2(i,jm,k)-u1*(small-q2(i,jm,k)); b=q2l(i,jm,k)-u1*(small-q2l(i,jm,k)); }
-        else { a=q2(i,jm,k)-u1*(q2(i,jm,k)-q2(i,jmm1,k)); b=q2l(i,jm,k)-u1*(q2l(i,jm,k)-q2l(i,jmm1,k)); }
-      } else if (i == 1) {                                              // west (:264-273)
-        double u1=2.*u(2,j,k)*dti/(dx(1,j)+dx(2,j));
-        if (u1 >= 0.) { a=q2(1,j,k)-u1*(q2(1,j,k)-small); b=q2l(1,j,k)-u1*(q2l(1,j,k)-small); }
-        else { a=q2(1,j,k)-u1*(q2(2,j,k)-q2(1,j,k)); b=q2l(1,j,k)-u1*(q2l(2,j,k)-q2l(1,j,k)); }
-      } else if (i == im) {                                             // east (:276-285)
-        double u1=2.*u(im,j,k)*dti/(dx(im,j)+dx(imm1,j));
-        if (u1 <= 0.) { a=q2(im,j,k)-u1*(small-q2(im,j,k)); b=q2l(im,j,k)-u1*(small-q2l(im,j,k)); }
-        else { a=q2(im,j,k)-u1*(q2(im,j,k)-q2(imm1,j,k)); b=q2l(im,j,k)-u1*(q2l(im,j,k)-q2l(imm1,j,k)); }
-      }
+      bcond6_edge(*this, i, j, k, a, b);                                // bounds_forcing.f:257-311
       a=a*m+1.e-10;                                                     // :318-319
       b=b*m+1.e-10;
       uf(i,j,k)=a;
@@ -974,6 +945,7 @@ POM_HD void ts_level(const K& kk, int i, int j, int k, double a, double b, doubl
 // proft for T (in uf) and S (in vf) in one TMA-fed column kernel (advance.f:440-441): kh is read
 // once, and the matrix coefficients a, c and -- when both tracers have the same class of
 // surface condition -- the eliminated ee and the pivots are shared between the two systems.
+template <bool SAME>   // both tracers have the same class of surface condition: one ee vector serves both systems
 struct ProftTSK : KBase {
   POM_KINFO("proft_ts", 3, 2, 6, 0)
   double rn, ad1n, ad2n;   // Jerlov water type ntp (:1568-1575)
@@ -995,7 +967,8 @@ struct ProftTSK : KBase {
   static constexpr bool UP = true;
   enum { FT, FS, KH };
   POM_HD void fields(const double** b) const { b[FT] = p.uf; b[FS] = p.vf; b[KH] = p.kh; }
-  struct Cols { double eeT[KMAX], eeS[KMAX], ggT[KMAX], ggS[KMAX]; };
+  static constexpr int NVEC = SAME ? 3 : 4;   // ee of T (shared with S when SAME), gg of T, gg of S [, ee of S]
+  enum { C_EET, C_GGT, C_GGS, C_EES };
   struct State { double dh, swT, swS, radT, radS, eeT, eeS, ggT, ggS, fT, fS; };
   POM_HD int k0() const { return 1; }
   POM_HD int k1() const { return g.kb - 1; }
@@ -1004,7 +977,8 @@ struct ProftTSK : KBase {
     if (k >= g.kb) return 0.;
     return sw0*(rn*exp(z(k)*dh/ad1n)+(1.-rn)*exp(z(k)*dh/ad2n));
   }
-  POM_HD void pre(int i, int j, State& s, Cols&) const {
+  template <class CM>
+  POM_HD void pre(int i, int j, State& s, CM&) const {
     s.dh=h(i,j)+etf(i,j);                                               // :1580
     s.swT=(c.nbct == 2 || c.nbct == 4) ? A2(p.swrad,i,j) : 0.;
     s.swS=(c.nbcs == 2 || c.nbcs == 4) ? A2(p.swrad,i,j) : 0.;
@@ -1028,19 +1002,19 @@ struct ProftTSK : KBase {
       ee1=0.; gg1=0.;
     }
   }
-  template <class Op>
-  POM_HD void level(int i, int j, int k, State& s, Cols& cm, const Op& o) const {
+  template <class Op, class CM>
+  POM_HD void level(int i, int j, int k, State& s, CM& cm, const Op& o) const {
     POM_DIMS;
     const double dh=s.dh;
     const bool penT = (c.nbct == 2 || c.nbct == 4), penS = (c.nbcs == 2 || c.nbcs == 4);
-    const bool same = ((c.nbct == 1 || c.nbct == 2) == (c.nbcs == 1 || c.nbcs == 2));
+    constexpr bool same = SAME;
     if (k == 1) {
       // a(k-1), c(k) from kh(k), k=2..kbm1 (:1589-1598); a(kbm1)=0, c(1)=0 (zero fill)
       const double ak=-dti2*(o.up(KH)+umol)/(dz(1)*dzz(1)*dh*dh);       // a(1)
       surface(i,j,c.nbct,ak,o(FT,0,0),wtsurf(i,j),tsurf(i,j),s.swT,dh,s.eeT,s.ggT);
       surface(i,j,c.nbcs,ak,o(FS,0,0),wssurf(i,j),ssurf(i,j),s.swS,dh,s.eeS,s.ggS);
-      cm.eeT[1]=s.eeT; cm.ggT[1]=s.ggT; cm.ggS[1]=s.ggS;
-      if (!same) cm.eeS[1]=s.eeS;
+      cm.put(C_EET,1,s.eeT); cm.put(C_GGT,1,s.ggT); cm.put(C_GGS,1,s.ggS);
+      if (!same) cm.put(C_EES,1,s.eeS);
       if (penT) s.radT=rad(2,dh,s.swT);
       if (penS) s.radS=rad(2,dh,s.swS);
       return;
@@ -1056,8 +1030,8 @@ struct ProftTSK : KBase {
       if (penT) { const double r0=s.radT; s.radT=rad(k+1,dh,s.swT); rT=rT+dti2*(r0-s.radT)/(dh*dz(k)); }
       if (penS) { const double r0=s.radS; s.radS=rad(k+1,dh,s.swS); rS=rS+dti2*(r0-s.radS)/(dh*dz(k)); }
       s.ggT=rT*giT; s.ggS=rS*giS;
-      cm.eeT[k]=s.eeT; cm.ggT[k]=s.ggT; cm.ggS[k]=s.ggS;
-      if (!same) cm.eeS[k]=s.eeS;          // shared with T otherwise: one array less to spill
+      cm.put(C_EET,k,s.eeT); cm.put(C_GGT,k,s.ggT); cm.put(C_GGS,k,s.ggS);
+      if (!same) cm.put(C_EES,k,s.eeS);    // shared with T otherwise: one vector less to park
     } else {                                                            // k == kbm1 (:1664-1671)
       double rT=ck*s.ggT-o(FT,0,0), rS=ck*s.ggS-o(FS,0,0);
       if (penT) rT=rT+dti2*(s.radT-0.)/(dh*dz(kbm1));
@@ -1066,15 +1040,16 @@ struct ProftTSK : KBase {
       s.fS=rS/(ck*(1.-s.eeS)-1.);
     }
   }
-  POM_HD void post(int i, int j, State& s, Cols& cm) const {
+  template <class CM>
+  POM_HD void post(int i, int j, State& s, CM& cm) const {
     POM_DIMS;
-    const bool same = ((c.nbct == 1 || c.nbct == 2) == (c.nbcs == 1 || c.nbcs == 2));
+    constexpr bool same = SAME;
     double fT=s.fT, fS=s.fS;
     if (fuse) {
       // the new T,S of a level go straight into the filter (which writes uf, vf, tb, sb, rho)
       const double m = fsm(i,j);
-      // the eliminated coefficients come back from local memory (L2): fetch them one level ahead
-      double eTn=cm.eeT[kb-2], gTn=cm.ggT[kb-2], gSn=cm.ggS[kb-2], eSn=same ? eTn : cm.eeS[kb-2];
+      // the eliminated coefficients come back from the column scratch (L2): fetch them one level ahead
+      double eTn=cm.get(C_EET,kb-2), gTn=cm.get(C_GGT,kb-2), gSn=cm.get(C_GGS,kb-2), eSn=same ? eTn : cm.get(C_EES,kb-2);
       ts_level(*this, i, j, kbm1, fT, fS, m, fold, fnew, 1);
       for (int ki = kb-2; ki >= 1; --ki) {                              // :1673-1680
         {   // the filter's operands of the level below, towards L1
@@ -1083,7 +1058,7 @@ struct ProftTSK : KBase {
                         POM_PREFETCH(p.tclim+o); POM_PREFETCH(p.sclim+o); }
         }
         const double eT=eTn, gT=gTn, eS=eSn, gS=gSn;
-        if (ki > 1) { eTn=cm.eeT[ki-1]; gTn=cm.ggT[ki-1]; gSn=cm.ggS[ki-1]; eSn=same ? eTn : cm.eeS[ki-1]; }
+        if (ki > 1) { eTn=cm.get(C_EET,ki-1); gTn=cm.get(C_GGT,ki-1); gSn=cm.get(C_GGS,ki-1); eSn=same ? eTn : cm.get(C_EES,ki-1); }
         fT=eT*fT+gT;
         fS=eS*fS+gS;
         ts_level(*this, i, j, ki, fT, fS, m, fold, fnew, 1);
@@ -1093,9 +1068,9 @@ struct ProftTSK : KBase {
     POM_STCS(&uf(i,j,kbm1),fT);
     POM_STCS(&vf(i,j,kbm1),fS);
     for (int ki = kb-2; ki >= 1; --ki) {                                // :1673-1680
-      const double eT=cm.eeT[ki];
-      fT=eT*fT+cm.ggT[ki];
-      fS=(same ? eT : cm.eeS[ki])*fS+cm.ggS[ki];
+      const double eT=cm.get(C_EET,ki);
+      fT=eT*fT+cm.get(C_GGT,ki);
+      fS=(same ? eT : cm.get(C_EES,ki))*fS+cm.get(C_GGS,ki);
       POM_STCS(&uf(i,j,ki),fT);
       POM_STCS(&vf(i,j,ki),fS);
     }
@@ -1103,9 +1078,10 @@ struct ProftTSK : KBase {
 };
 
 // the fused variant under its own name / algorithmic byte count in the per-kernel profile
-struct ProftFilterK : ProftTSK {
+template <bool SAME>
+struct ProftFilterK : ProftTSK<SAME> {
   POM_KINFO("proft_tsfilter", 9, 5, 9, 0)
-  ProftFilterK(const Ctx* x) : ProftTSK(x, 1) {}
+  ProftFilterK(const Ctx* x) : ProftTSK<SAME>(x, 1) {}
 };
 
 // x**1.5 for x>=0, rounded like a correctly-rounded pow(x,1.5): sqrt is IEEE-exact to
@@ -1141,64 +1117,7 @@ template <class K>
 POM_HD void ts_level(const K& kk, int i, int j, int k, double a, double b, double m, double fold, double fnew, int with_dens) {
   const Geo& g = kk.g; const Ptrs& p = kk.p; const Consts& c = kk.c;
   POM_DIMS;
-    const bool vadv = (k != 1 && k != kbm1);
-    if (j == 1) {                                                     // south (:196-211)
-      double u1=2.*v(i,2,k)*dti/(dy(i,1)+dy(i,2));
-      if (u1 >= 0.) {
-        a=t(i,1,k)-u1*(t(i,1,k)-tbs(i,k));
-        b=s(i,1,k)-u1*(s(i,1,k)-sbs(i,k));
-      } else {
-        a=t(i,1,k)-u1*(t(i,2,k)-t(i,1,k));
-        b=s(i,1,k)-u1*(s(i,2,k)-s(i,1,k));
-        if (vadv) {
-          double wm=.5*(w(i,2,k)+w(i,2,k+1))*dti/((zz(k-1)-zz(k+1))*dt(i,2));
-          a=a-wm*(t(i,2,k-1)-t(i,2,k+1));
-          b=b-wm*(s(i,2,k-1)-s(i,2,k+1));
-        }
-      }
-    } else if (j == jm) {                                             // north (:214-229)
-      double u1=2.*v(i,jm,k)*dti/(dy(i,jm)+dy(i,jmm1));
-      if (u1 <= 0.) {
-        a=t(i,jm,k)-u1*(tbn(i,k)-t(i,jm,k));
-        b=s(i,jm,k)-u1*(sbn(i,k)-s(i,jm,k));
-      } else {
-        a=t(i,jm,k)-u1*(t(i,jm,k)-t(i,jmm1,k));
-        b=s(i,jm,k)-u1*(s(i,jm,k)-s(i,jmm1,k));
-        if (vadv) {
-          double wm=.5*(w(i,jmm1,k)+w(i,jmm1,k+1))*dti/((zz(k-1)-zz(k+1))*dt(i,jmm1));
-          a=a-wm*(t(i,jmm1,k-1)-t(i,jmm1,k+1));
-          b=b-wm*(s(i,jmm1,k-1)-s(i,jmm1,k+1));
-        }
-      }
-    } else if (i == im) {                                             // east (:158-173)
-      double u1=2.*u(im,j,k)*dti/(dx(im,j)+dx(imm1,j));
-      if (u1 <= 0.) {
-        a=t(im,j,k)-u1*(tbe(j,k)-t(im,j,k));
-        b=s(im,j,k)-u1*(sbe(j,k)-s(im,j,k));
-      } else {
-        a=t(im,j,k)-u1*(t(im,j,k)-t(imm1,j,k));
-        b=s(im,j,k)-u1*(s(im,j,k)-s(imm1,j,k));
-        if (vadv) {
-          double wm=.5*(w(imm1,j,k)+w(imm1,j,k+1))*dti/((zz(k-1)-zz(k+1))*dt(imm1,j));
-          a=a-wm*(t(imm1,j,k-1)-t(imm1,j,k+1));
-          b=b-wm*(s(imm1,j,k-1)-s(imm1,j,k+1));
-        }
-      }
-    } else if (i == 1) {                                              // west (:176-191)
-      double u1=2.*u(2,j,k)*dti/(dx(1,j)+dx(2,j));
-      if (u1 >= 0.) {
-        a=t(1,j,k)-u1*(t(1,j,k)-tbw(j,k));
-        b=s(1,j,k)-u1*(s(1,j,k)-sbw(j,k));
-      } else {
-        a=t(1,j,k)-u1*(t(2,j,k)-t(1,j,k));
-        b=s(1,j,k)-u1*(s(2,j,k)-s(1,j,k));
-        if (vadv) {
-          double wm=.5*(w(2,j,k)+w(2,j,k+1))*dti/((zz(k-1)-zz(k+1))*dt(2,j));
-          a=a-wm*(t(2,j,k-1)-t(2,j,k+1));
-          b=b-wm*(s(2,j,k-1)-s(2,j,k+1));
-        }
-      }
-    }
+    bcond4_edge(kk, i, j, k, a, b);                                   // bounds_forcing.f:151-231
     a=a*m;                                                            // :236-237
     b=b*m;
     // tb,sb as left behind by advt1/advt2: (fb-fclim)+fclim (solver.f:691,715)
@@ -1437,12 +1356,14 @@ struct AdvProfUVK : KBase {
     b[DRHO] = VC ? p.drhoy : p.drhox; b[XB] = VC ? p.vb : p.ub; b[KM] = p.km;
   }
   POM_HD double* xf() const { return VC ? p.vf : p.uf; }
-  struct Cols { double ee[KMAX], gg[KMAX]; };
+  static constexpr int NVEC = 2;
+  enum { C_EE, C_GG };
   struct State { double ar, sl, hb, hf, c0, cB, dh, fk, xm, eem, ggm, ck, xfl; bool interior, live; };
   POM_HD int k0() const { return 1; }
   POM_HD int k1() const { return g.kb - 1; }
   POM_HD int kl1() const { return g.kb - 1; }
-  POM_HD void pre(int i, int j, State& s, Cols&) const {
+  template <class CM>
+  POM_HD void pre(int i, int j, State& s, CM&) const {
     POM_DIMS;
     s.interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
     s.live = VC ? (j >= 2) : (i >= 2);          // the vertical-flux intermediate exists (:744-751, :801-808)
@@ -1462,8 +1383,8 @@ struct AdvProfUVK : KBase {
     s.c0=cor(i,j)*dt(i,j); s.cB=cor(ib,jb)*dt(ib,jb);
     s.dh=(h(i,j)+etf(i,j)+h(ib,jb)+etf(ib,jb))*.5;                      // :1703 / :1801
   }
-  template <class Op>
-  POM_HD void level(int i, int j, int k, State& s, Cols& cm, const Op& o) const {
+  template <class Op, class CM>
+  POM_HD void level(int i, int j, int k, State& s, CM& cm, const Op& o) const {
     POM_DIMS;
     double* f = xf();
     const double x0=o(X,0,0);
@@ -1490,7 +1411,7 @@ struct AdvProfUVK : KBase {
       s.eem=ak/(ak-1.);                                                 // :1733
       s.ggm=(-dti2*ws/(-dz(1)*dh)-xk)/(ak-1.);                          // :1734-1736
       s.ck=-dti2*(cn+umol)/(dz(2)*dzz(1)*dh*dh);                        // c(2) (:1725)
-      cm.ee[1]=s.eem; cm.gg[1]=s.ggm;
+      cm.put(C_EE,1,s.eem); cm.put(C_GG,1,s.ggm);
     } else if (k <= kbm2) {                                             // :1740-1748
       const double cn=(o.up(KM)+o.up(KM,BI,BJ))*.5;
       const double ak=pdiv(-dti2*(cn+umol),dz(k)*dzz(k)*dh*dh);         // a(k)
@@ -1498,12 +1419,13 @@ struct AdvProfUVK : KBase {
       s.eem=ak*gi;
       s.ggm=(s.ck*s.ggm-xk)*gi;
       s.ck=pdiv(-dti2*(cn+umol),dz(k+1)*dzz(k)*dh*dh);                  // c(k+1)
-      cm.ee[k]=s.eem; cm.gg[k]=s.ggm;
+      cm.put(C_EE,k,s.eem); cm.put(C_GG,k,s.ggm);
     } else {
       s.xfl=xk;                                                         // uf(kbm1), used by the bottom condition
     }
   }
-  POM_HD void post(int i, int j, State& s, Cols& cm) const {
+  template <class CM>
+  POM_HD void post(int i, int j, State& s, CM& cm) const {
     POM_DIMS;
     if (!s.interior) return;
     double* f = xf();
@@ -1520,8 +1442,12 @@ struct AdvProfUVK : KBase {
     fk=fk*m;                                                            // :1759
     A3(f,i,j,kbm1)=fk;
     if (VC) wvbot(i,j)=-tp*fk; else wubot(i,j)=-tp*fk;                  // :1774 / :1871
+    // the eliminated coefficients come back from the column scratch (L2): fetch them one level ahead
+    double en=cm.get(C_EE,kb-2), gn=cm.get(C_GG,kb-2);
     for (int ki = kb-2; ki >= 1; --ki) {                                // :1763-1770
-      fk=(cm.ee[ki]*fk+cm.gg[ki])*m;
+      const double e=en, gq=gn;
+      if (ki > 1) { en=cm.get(C_EE,ki-1); gn=cm.get(C_GG,ki-1); }
+      fk=(e*fk+gq)*m;
       A3(f,i,j,ki)=fk;
     }
   }
@@ -1535,64 +1461,66 @@ struct AdvProfUVK : KBase {
 struct UvFilterK : KBase {
   POM_KINFO("uv_filter", 6, 2, 2, 2)
   using KBase::KBase;
-  // Orlanski radiation value from the point `1` cell inside (xf1,xb1), two inside (x2),
-  // and the boundary point's own xb0 and x at one inside (x1)
-  POM_HD static double orl(double xf1, double xb1, double x2, double xb0, double x1) {
-    double denom=(xf1+xb1-2.*x2);
-    if (denom == 0.) denom=0.01;
-    double cl=(xb1-xf1)/denom;
-    if (cl > 1.) cl=1.;
-    if (cl < 0.) cl=0.;
-    return (xb0*(1.-cl)+2.*cl*x1)/(1.+cl);
-  }
-  POM_HD void operator()(int i, int j) const {
+  // TMA-fed column kernel: the downward sweep applies bcondorl(3) and the masks, accumulates the
+  // depth means and PARKS (uf+ub-2u, u) and (vf+vb-2v, v) of every level in the column scratch; the
+  // second sweep (`post`) reads them back from L2, so the six operands are read from HBM once
+  // (8 passes of traffic instead of 14).
+#ifndef POM_UVF_TY
+#define POM_UVF_TY 8
+#endif
+#ifndef POM_UVF_MINB
+#define POM_UVF_MINB 3
+#endif
+#ifndef POM_UVF_NS
+#define POM_UVF_NS 4
+#endif
+  static constexpr int TY = POM_UVF_TY, MINB = POM_UVF_MINB;
+  static constexpr int NF = 6, NS = POM_UVF_NS, OHL = 0, OHR = 0, OHB = 0, OHT = 0, BW = 34, BH = TY, NK = 0;
+  static constexpr bool UP = false;
+  static constexpr int NVEC = 4;
+  enum { UF, VF, UB, VB, U, V };
+  enum { C_PU, C_U, C_PV, C_V };
+  POM_HD void fields(const double** b) const { b[UF] = p.uf; b[VF] = p.vf; b[UB] = p.ub; b[VB] = p.vb; b[U] = p.u; b[V] = p.v; }
+  struct State { double mu, mv, su, sv, tu, tv; bool jin, iin, edge; };
+  POM_HD int k0() const { return 1; }
+  POM_HD int k1() const { return g.kb - 1; }
+  POM_HD int kl1() const { return g.kb - 1; }
+  template <class CM>
+  POM_HD void pre(int i, int j, State& s, CM&) const {
     POM_DIMS;
-    const bool jin = (j >= 2 && j <= jmm1), iin = (i >= 2 && i <= imm1);
-    const double mu=dum(i,j), mv=dvm(i,j);
-    double su = 0., sv = 0., tu = 0., tv = 0.;
-    double nu[KMAX], nv[KMAX];
-    const bool edge0 = !(iin && jin) || i == 2 || j == 2;
+    s.jin = (j >= 2 && j <= jmm1); s.iin = (i >= 2 && i <= imm1);
+    s.edge = !(s.iin && s.jin) || i == 2 || j == 2;
+    s.mu=dum(i,j); s.mv=dvm(i,j);
+    s.su = 0.; s.sv = 0.; s.tu = 0.; s.tv = 0.;
+  }
+  template <class Op, class CM>
+  POM_HD void level(int i, int j, int k, State& s, CM& cm, const Op& o) const {
+    POM_DIMS;
+    double a=o(UF,0,0), b=o(VF,0,0);
+    if (s.edge) bcondorl3_edge(*this, i, j, k, a, b);                    // bounds_forcing.f:418-474
+    a=a*s.mu;                                                           // :481-482
+    b=b*s.mv;
+    // interior values are already masked (profu :1767): only the open-boundary columns change
+    if (s.edge) { uf(i,j,k)=a; vf(i,j,k)=b; }
+    const double u0=o(U,0,0), v0=o(V,0,0);
+    const double pu=a+o(UB,0,0)-2.*u0, pv=b+o(VB,0,0)-2.*v0;
+    s.su=s.su+pu*dz(k);                                                 // advance.f:474-475
+    s.sv=s.sv+pv*dz(k);                                                 // advance.f:495-496
+    s.tu=s.tu+a*dz(k);                                                  // next step's advance.f:367-369:
+    s.tv=s.tv+b*dz(k);                                                  // uf, vf become u, v (:512,514)
+    cm.put(C_PU,k,pu); cm.put(C_U,k,u0); cm.put(C_PV,k,pv); cm.put(C_V,k,v0);
+  }
+  template <class CM>
+  POM_HD void post(int i, int j, State& s, CM& cm) const {
+    POM_DIMS;
+    A2(p.s2c,i,j)=s.tu;
+    A2(p.s2d,i,j)=s.tv;
+    double pun=cm.get(C_PU,1), un_=cm.get(C_U,1), pvn=cm.get(C_PV,1), vn_=cm.get(C_V,1);
     for (int k = 1; k <= kbm1; ++k) {
-      PF3(p.uf,i,j,k+2); PF3(p.vf,i,j,k+2); PF3(p.ub,i,j,k+2); PF3(p.vb,i,j,k+2); PF3(p.u,i,j,k+2); PF3(p.v,i,j,k+2);
-      double a=uf(i,j,k), b=vf(i,j,k);
-      if (jin) {
-        if (i == im) {                                                  // east (:425-434)
-          a=orl(uf(im-1,j,k),ub(im-1,j,k),u(im-2,j,k),ub(im,j,k),u(im-1,j,k));
-          b=0.;
-        } else if (i == 2 || i == 1) {                                  // west (:437-447)
-          a=orl(uf(3,j,k),ub(3,j,k),u(4,j,k),ub(2,j,k),u(3,j,k));
-          if (i == 1) b=0.;
-        }
-      }
-      if (iin) {
-        if (j == jm) {                                                  // north (:465-474)
-          b=orl(vf(i,jm-1,k),vb(i,jm-1,k),v(i,jm-2,k),vb(i,jm,k),v(i,jm-1,k));
-          a=0.;
-        } else if (j == 2 || j == 1) {                                  // south (:452-462)
-          b=orl(vf(i,3,k),vb(i,3,k),v(i,4,k),vb(i,2,k),v(i,3,k));
-          if (j == 1) a=0.;
-        }
-      }
-      a=a*mu;                                                           // :481-482
-      b=b*mv;
-      if (edge0) { nu[k]=a; nv[k]=b; }
-      su=su+(a+ub(i,j,k)-2.*u(i,j,k))*dz(k);                            // advance.f:474-475
-      sv=sv+(b+vb(i,j,k)-2.*v(i,j,k))*dz(k);                            // advance.f:495-496
-      tu=tu+a*dz(k);                                                    // next step's advance.f:367-369:
-      tv=tv+b*dz(k);                                                    // uf, vf become u, v (:512,514)
-    }
-    A2(p.s2c,i,j)=tu;
-    A2(p.s2d,i,j)=tv;
-    const bool edge = !(iin && jin) || i == 2 || j == 2;
-    for (int k = 1; k <= kbm1; ++k) {
-      // away from the open boundaries the masked tendency is recomputed from uf,vf (one more
-      // read) instead of making the round trip through the per-thread arrays (a write + a read)
-      double a = edge ? nu[k] : uf(i,j,k)*mu, b = edge ? nv[k] : vf(i,j,k)*mv;
-      double un=u(i,j,k)+.5*smoth*(a+ub(i,j,k)-2.*u(i,j,k)-su);         // advance.f:483-485
-      double vn=v(i,j,k)+.5*smoth*(b+vb(i,j,k)-2.*v(i,j,k)-sv);         // advance.f:504-506
-      A3(p.s3a,i,j,k)=un;
-      A3(p.s3b,i,j,k)=vn;
-      if (edge) { uf(i,j,k)=a; vf(i,j,k)=b; }   // interior values are already masked (profu :1767)
+      const double pu=pun, u0=un_, pv=pvn, v0=vn_;
+      if (k < kbm1) { pun=cm.get(C_PU,k+1); un_=cm.get(C_U,k+1); pvn=cm.get(C_PV,k+1); vn_=cm.get(C_V,k+1); }
+      POM_STCS(&A3(p.s3a,i,j,k),u0+.5*smoth*(pu-s.su));                 // advance.f:483-485
+      POM_STCS(&A3(p.s3b,i,j,k),v0+.5*smoth*(pv-s.sv));                 // advance.f:504-506
     }
     A3(p.s3a,i,j,kb)=u(i,j,kb);                                         // advance.f:511,513
     A3(p.s3b,i,j,kb)=v(i,j,kb);
@@ -1782,8 +1710,9 @@ void run_proft(Ctx* c, double* f, const double* wf, const double* fs, int nbc, i
   launch_cols(c, ProftK(c, f, wf, fs, nbc), ALLI, j0, j1);
 }
 void run_proft_ts(Ctx* c, int fuse, int j0, int j1) {
-  if (fuse) launch_tma_cols(c, ProftFilterK(c), ALLI, j0, j1);
-  else launch_tma_cols(c, ProftTSK(c), ALLI, j0, j1);
+  const bool same = ((c->c.nbct == 1 || c->c.nbct == 2) == (c->c.nbcs == 1 || c->c.nbcs == 2));
+  if (fuse) { if (same) launch_tma_cols(c, ProftFilterK<true>(c), ALLI, j0, j1); else launch_tma_cols(c, ProftFilterK<false>(c), ALLI, j0, j1); }
+  else { if (same) launch_tma_cols(c, ProftTSK<true>(c), ALLI, j0, j1); else launch_tma_cols(c, ProftTSK<false>(c), ALLI, j0, j1); }
 }
 // caller swaps t<->uf, s<->vf (advance.f:446-449)
 void run_tsfilter(Ctx* c, int with_dens, int j0, int j1) { launch_cols(c, TsFilterK(c, with_dens), ALLI, j0, j1); }
@@ -1797,7 +1726,7 @@ void run_advprof_v(Ctx* c, int j0, int j1) { launch_tma_cols(c, AdvProfUVK<true>
 void run_profu(Ctx* c, int j0, int j1) { launch_cols(c, ProfuK(c), ALLI, j0, j1); }
 void run_profv(Ctx* c, int j0, int j1) { launch_cols(c, ProfvK(c), ALLI, j0, j1); }
 // caller swaps u<->uf, v<->vf, ub<->s3a, vb<->s3b (advance.f:511-514)
-void run_uvfilter(Ctx* c, int j0, int j1) { launch_cols(c, UvFilterK(c), ALLI, j0, j1); }
+void run_uvfilter(Ctx* c, int j0, int j1) { launch_tma_cols(c, UvFilterK(c), ALLI, j0, j1); }
 void run_endstep2d(Ctx* c, int j0, int j1) { launch_cols(c, EndStep2dK(c), ALLI, j0, j1); }
 void run_realvertvl(Ctx* c, int j0, int j1) { launch_cols<RealvertvlK, POM_RV_MINB>(c, RealvertvlK(c), ALLI, j0, j1); }
 

@@ -95,6 +95,7 @@ int dev_init(Ctx* c) {
     return 1;
   }
   if (cuda_fail(c, cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+  if (cuda_fail(c, cudaDeviceGetAttribute(&c->nsm, cudaDevAttrMultiProcessorCount, c->device), "device attribute")) return 1;
   cudaStream_t s;
   if (cuda_fail(c, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
   c->stream = (void*)s;
@@ -221,7 +222,7 @@ int prof_report(Ctx* c, char* buf, int n) {
 
 // ---- lifecycle ------------------------------------------------------------------
 Ctx* ctx_create(int im, int jm_global, int kb, int j_first, int j_last, int ghost, int device) {
-  if (im < 6 || jm_global < 6 || kb < 4 || kb > 64) return nullptr;   // KMAX of the column solvers
+  if (im < 6 || jm_global < 6 || kb < 4 || kb > KMAX) return nullptr;   // most levels the column solvers hold
   Ctx* c = (Ctx*)calloc(1, sizeof(Ctx));
   c->no_tma = (getenv("POMGPU_NO_TMA") != nullptr);
   c->device = device;
@@ -259,12 +260,14 @@ void ctx_destroy(Ctx* c) {
   free(c->d_red); free(c->h_red);
 #else
   cudaFree(c->d_red); cudaFreeHost(c->h_red);
+  if (c->colscr) cudaFree(c->colscr);
   for (int f = 0; f < 256; ++f) if (c->shadow[f]) cudaFree(c->shadow[f]);
   free(c->tma_cache);
   if (c->copy_stream) cudaStreamDestroy((cudaStream_t)c->copy_stream);
   if (c->ev_copied) cudaEventDestroy((cudaEvent_t)c->ev_copied);
   if (c->ev_swapped) cudaEventDestroy((cudaEvent_t)c->ev_swapped);
   if (c->ev_vel) cudaEventDestroy((cudaEvent_t)c->ev_vel);
+  for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy((cudaEvent_t)c->ev[i]);
   cudaStreamDestroy((cudaStream_t)c->own_stream);
 #endif
   free(c);

@@ -56,6 +56,8 @@ void run_uvfilter(Ctx*, int, int);
 void run_endstep2d(Ctx*, int, int);
 void run_realvertvl(Ctx*, int, int);
 int domain_stats_rows(Ctx* c, double* rows);
+int run_bcond(Ctx*, int idx, int orl, int, int);
+void run_mask_fsm(Ctx*, double* ff, int, int);
 
 // ---- launch windows ---------------------------------------------------------------------
 static inline int WLO(const Ctx* c, int e) { return c->jown0 > 1 ? c->jown0 - e : 1; }
@@ -67,8 +69,16 @@ static inline double* FP(Ctx* c, int f) {
 }
 #define NEED(...) ([&]() { const Req rq[] = {__VA_ARGS__}; return group_need(G, rq, (int)(sizeof(rq) / sizeof(rq[0]))); }())
 #define MADE(e, ...) do { const int ou[] = {__VA_ARGS__}; group_produced(G, e, ou, (int)(sizeof(ou) / sizeof(ou[0]))); } while (0)
-#define EACH(stmt) for (int r_ = 0; r_ < G->n; ++r_) { Ctx* c = G->c[r_]; const int j0 = WLO(c, e), j1 = WHI(c, e); (void)j0; (void)j1; stmt; }
-#define CSYNC() for (int r_ = 1; r_ < G->n; ++r_) G->c[r_]->c = G->c[0]->c
+// (after a failed halo exchange nothing is launched any more: the kernels would read stale ghost rows)
+#define EACH(stmt) for (int r_ = 0; r_ < G->n && !G->failed; ++r_) { Ctx* c = G->c[r_]; const int j0 = WLO(c, e), j1 = WHI(c, e); (void)j0; (void)j1; stmt; }
+// the scalars of strip 0 are the group's; error_status stays per strip (a CUDA failure or a blow-up
+// on strip r must survive until the driver reads it, advance.f:556-563)
+#define CSYNC() for (int r_ = 1; r_ < G->n; ++r_) { const int es_ = G->c[r_]->c.error_status; G->c[r_]->c = G->c[0]->c; G->c[r_]->c.error_status = es_; }
+static int group_status(Group* G) {
+  int es = G->failed ? 1 : 0;
+  for (int r = 0; r < G->n; ++r) es |= G->c[r]->c.error_status;
+  return es;
+}
 
 // pushes made with pomgpu_push_async since the last step: make the compute stream wait for the
 // copies and swap the shadow buffers in (the old buffers become the next shadows)
@@ -431,7 +441,7 @@ static int step(Group* G, int iint, double time, double ramp) {
   for (int iext = 1; iext <= c0->c.isplit; ++iext) mode_external(G, iext);
   c0->c.iext = c0->c.isplit + 1; CSYNC();
   mode_internal(G, iint);
-  return c0->c.error_status ? 1 : 0;
+  return group_status(G) ? 1 : 0;
 }
 
 // ---- check_velocity: max|vaf| over the owned rows (after the rotation vaf lives in va) ----
@@ -575,10 +585,13 @@ int pomgpu_sync(pomgpu_t* p) { return dev_sync(X(p)); }
 double pomgpu_check_velocity(pomgpu_t* p) { return check_velocity(X(p)); }
 // enqueue the reduction for the step just enqueued and return the result of the PREVIOUS call
 // (0 on the first): the host never waits for the step it has just launched
-double pomgpu_check_velocity_lagged(pomgpu_t* p) {
-  Ctx* c = X(p);
+// max|a[0..n)| of the PREVIOUS call (0 on the first): the reduction of this call is only enqueued
+static double absmax_lagged(Ctx* c, const double* a, size_t n, bool is_velocity) {
 #ifdef POMGPU_EMU
-  return check_velocity(c);
+  double m = 0.;
+  for (size_t i = 0; i < n; ++i) { double v = fabs(a[i]); if (!(v <= m)) m = v; }
+  if (is_velocity && !(m <= c->c.vmaxl)) c->c.error_status = 1;
+  return m;
 #else
   double prev = 0.;
   cudaSetDevice(c->device);
@@ -587,19 +600,35 @@ double pomgpu_check_velocity_lagged(pomgpu_t* p) {
   if (c->vel_lag) {
     cudaEventSynchronize((cudaEvent_t)c->ev_vel);
     prev = c->h_red[1];
-    if (!(prev <= c->c.vmaxl)) c->c.error_status = 1;   // advance.f:631-638
+    if (c->vel_lag == 1 && !(prev <= c->c.vmaxl)) c->c.error_status = 1;   // advance.f:631-638
   }
-  const double* a = c->p.va + (size_t)(c->jown0 - 1 - c->g.joff) * c->g.im;
-  size_t n = (size_t)(c->jown1 - c->jown0 + 1) * c->g.im;
   cudaMemsetAsync(c->d_red + 1, 0, 8, s);
   int blocks = (int)((n + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
   c->launches++;
   absmax_kernel<<<blocks, 256, 0, s>>>(a, n, (unsigned long long*)(c->d_red + 1));
   cudaMemcpyAsync(c->h_red + 1, c->d_red + 1, 8, cudaMemcpyDeviceToHost, s);
   cudaEventRecord((cudaEvent_t)c->ev_vel, s);
-  c->vel_lag = 1;
+  c->vel_lag = is_velocity ? 1 : 2;
   return prev;
 #endif
+}
+double pomgpu_check_velocity_lagged(pomgpu_t* p) {
+  Ctx* c = X(p);
+#ifdef POMGPU_EMU
+  return check_velocity(c);
+#else
+  const double* a = c->p.va + (size_t)(c->jown0 - 1 - c->g.joff) * c->g.im;
+  return absmax_lagged(c, a, (size_t)(c->jown1 - c->jown0 + 1) * c->g.im, true);
+#endif
+}
+// the same one-scalar-per-step read-back for any field (max |x| over the rows this strip holds):
+// what a driver that runs single routines (the tracer-only bench) uses as its blow-up check
+double pomgpu_field_absmax_lagged(pomgpu_t* p, const char* name) {
+  Ctx* c = X(p);
+  const FieldInfo* f;
+  double** slot = ctx_slot(c, name, &f);
+  if (!slot || !*slot) return -1.;
+  return absmax_lagged(c, *slot, field_elems(c, f), false);
 }
 long pomgpu_selftest_pdiv(pomgpu_t* p, long n, unsigned long seed, int emax) { return selftest_pdiv(X(p), n, seed, emax); }
 // ---- on-device time interpolation of forcing / boundary records (pom_forcing.cu) ----
@@ -624,19 +653,17 @@ long pomgpu_launch_count(pomgpu_t* p, int reset) {
   return n;
 }
 
-// CUDA events on the library's launch stream (bench.py times the step loop with these)
-#ifndef POMGPU_EMU
-static cudaEvent_t g_ev[8];
-static bool g_ev_init = false;
-#endif
+// CUDA events on the library's launch stream (bench.py times the step loop with these); they
+// belong to the context, i.e. to its device
 int pomgpu_event_record(pomgpu_t* p, int slot) {
 #ifdef POMGPU_EMU
   (void)p; (void)slot; return 0;
 #else
   if (slot < 0 || slot >= 8) return 2;
-  cudaSetDevice(X(p)->device);
-  if (!g_ev_init) { for (int i = 0; i < 8; ++i) cudaEventCreate(&g_ev[i]); g_ev_init = true; }
-  return cudaEventRecord(g_ev[slot], (cudaStream_t)X(p)->stream) == cudaSuccess ? 0 : 1;
+  Ctx* c = X(p);
+  cudaSetDevice(c->device);
+  if (!c->ev[slot]) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return 1; c->ev[slot] = (void*)e; }
+  return cudaEventRecord((cudaEvent_t)c->ev[slot], (cudaStream_t)c->stream) == cudaSuccess ? 0 : 1;
 #endif
 }
 double pomgpu_event_elapsed_ms(pomgpu_t* p, int a, int b) {
@@ -644,9 +671,11 @@ double pomgpu_event_elapsed_ms(pomgpu_t* p, int a, int b) {
   (void)p; (void)a; (void)b; return 0.;
 #else
   float ms = -1.f;
-  cudaSetDevice(X(p)->device);
-  cudaEventSynchronize(g_ev[b]);
-  cudaEventElapsedTime(&ms, g_ev[a], g_ev[b]);
+  Ctx* c = X(p);
+  if (a < 0 || a >= 8 || b < 0 || b >= 8 || !c->ev[a] || !c->ev[b]) return -1.;
+  cudaSetDevice(c->device);
+  cudaEventSynchronize((cudaEvent_t)c->ev[b]);
+  cudaEventElapsedTime(&ms, (cudaEvent_t)c->ev[a], (cudaEvent_t)c->ev[b]);
   return ms;
 #endif
 }
@@ -706,6 +735,16 @@ int pomgpu_profv(pomgpu_t* p) { SG; k_profv(G); return 0; }
 int pomgpu_vertvl(pomgpu_t* p) { SG; k_vertvl(G); return 0; }
 int pomgpu_realvertvl(pomgpu_t* p) { SG; k_realvertvl(G); return 0; }
 
+// ---- bcond / bcondorl / smol_adif / single-quantity advq as stand-alone entries (unit mode) ----
+static int k_bcond(Group* G, int idx, int orl) {
+  const int e = 0;
+  int rc = 0;
+  EACH(rc |= run_bcond(c, idx, orl, j0, j1));
+  return rc;
+}
+int pomgpu_bcond(pomgpu_t* p, int idx) { SG; return k_bcond(G, idx, 0); }
+int pomgpu_bcondorl(pomgpu_t* p, int idx) { SG; return k_bcond(G, idx, 1); }
+
 static int fid(const char* name) {
   int n;
   const FieldInfo* t = field_table(&n);
@@ -733,6 +772,31 @@ int pomgpu_dens(pomgpu_t* p, const char* si, const char* ti, const char* rhoo) {
   int a = fid(si), b = fid(ti), o = fid(rhoo);
   if (a < 0 || b < 0 || o < 0) return 2;
   k_dens(G, a, b, o);
+  return 0;
+}
+// smol_adif(xmassflux,ymassflux,zwflux,ff) (solver.f:1880-1967): ff*fsm, then the anti-diffusive
+// mass fluxes in place
+int pomgpu_smol_adif(pomgpu_t* p, const char* xm, const char* ym, const char* zw, const char* ff) {
+  SG;
+  Ctx* c = X(p);
+  int a = fid(xm), b = fid(ym), w = fid(zw), o = fid(ff);
+  if (a < 0 || b < 0 || w < 0 || o < 0) return 2;
+  run_mask_fsm(c, FP(c, o), 1, c->g.jmg);
+  run_smol_adif(c, FP(c, o), FP(c, a), FP(c, b), FP(c, w), 1, c->g.jmg);
+  return 0;
+}
+// advq(qb,q,qf) (solver.f:411-477) for ONE quantity: the device kernel advances q2 and q2l together
+// (pomgpu_advq), so the same quantity is bound to both of its slots and the second result discarded
+int pomgpu_advq_fields(pomgpu_t* p, const char* qb, const char* q, const char* qf) {
+  SG;
+  Ctx* c = X(p);
+  int a = fid(qb), b = fid(q), o = fid(qf);
+  if (a < 0 || b < 0 || o < 0) return 2;
+  const Ptrs keep = c->p;
+  c->p.q2b = FP(c, a); c->p.q2lb = FP(c, a); c->p.q2 = FP(c, b); c->p.q2l = FP(c, b);
+  c->p.uf = FP(c, o); c->p.vf = keep.s3e;
+  run_advq(c, 1, c->g.jmg);
+  c->p = keep;
   return 0;
 }
 int pomgpu_proft(pomgpu_t* p, const char* f, const char* wfsurf, const char* fsurf, int nbc) {

@@ -157,61 +157,122 @@ tmakernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1
   if (out) f.post(i, j, st);
 }
 
-// Column kernels on the same TMA ring: no flux exchange between threads (thread tile = output
-// tile), only the operand staging.  F provides NF, NS, TY, OHL/OHR/OHB/OHT, BW, BH, UP, NK,
-// fields(), k0(), k1(), kl1(), pre(i,j,State&,Cols&), level(i,j,k,State&,Cols&,op),
-// post(i,j,State&,Cols&); Cols holds the dynamically indexed per-thread arrays (local memory) so
-// that the scalars of State stay in registers.
-// `post` runs the upward sweeps (Thomas back-substitution) on the thread's own column.
+#endif   // !POMGPU_EMU
+
+// ---- per-thread column vectors (the eliminated Thomas coefficients ee/gg) ---------------------
+// A column functor declares NVEC vectors of kb doubles per thread and uses them only through
+// put(v,k,x) / get(v,k).  LocalCols keeps them in per-thread local memory (host-emulated build and
+// the direct-load fallback).  ScratchCols keeps them in an explicit global scratch laid out
+// [block slot][vector][level][thread] (each warp access is one 256-byte run), read and written
+// through L2 only: the persistent kernel below re-uses a block's slot for every tile it processes
+// and DISCARDS the lines (discard.global.L2: dropped without write-back) once the upward sweep
+// has read them, so that the vectors make their round trip through L2 instead of HBM (measured,
+// scripts/probes/l2scratch_probe.cu: the write-backs of the local-memory variant disappear).
+template <int NVEC>
+struct LocalCols {
+  double a[NVEC][KMAX];
+  POM_HD void put(int v, int k, double x) { a[v][k] = x; }
+  POM_HD double get(int v, int k) const { return a[v][k]; }
+};
+
+#ifndef POMGPU_EMU
+template <int NVEC>
+struct ScratchCols {
+  double* base;   // this thread's element of level 0 of vector 0
+  int nt, kbs;    // threads per block, levels per vector
+  __device__ __forceinline__ void put(int v, int k, double x) { __stcg(base + (size_t)(v * kbs + k) * nt, x); }
+  __device__ __forceinline__ double get(int v, int k) const { return __ldcg(base + (size_t)(v * kbs + k) * nt); }
+};
+
+// Persistent column kernel on the TMA ring: one block per resident slot, each looping over tiles
+// (tile n of block b = b + n*gridDim.x).  The ring runs ACROSS tiles: while a tile's upward sweep
+// (`post`) runs, the first NS levels of the block's next tile are already in flight.  No flux
+// exchange between threads (thread tile = output tile), only the operand staging.  F provides NF,
+// NS, TY, OHL/OHR/OHB/OHT, BW, BH, UP, NK, NVEC, fields(), k0(), k1(), kl1(),
+// pre(i,j,State&,CM&), level(i,j,k,State&,CM&,op), post(i,j,State&,CM&) with CM = the column
+// vectors above.  `post` runs the upward sweeps (Thomas back-substitution) on the thread's own column.
 template <class F>
 __global__ void __launch_bounds__(TILE_X * F::TY, F::MINB)
-tmacolkernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1, int j0, int j1) {
-  constexpr int NF = F::NF, NS = F::NS, PL = tma_plane(F::BW, F::BH);
+tmacolkernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1, int j0, int j1,
+             int nbx, int ntiles, double* scratch, int kbs) {
+  constexpr int NF = F::NF, NS = F::NS, PL = tma_plane(F::BW, F::BH), NT = TILE_X * F::TY;
   extern __shared__ __align__(128) double pom_tsm[];
   double* ring = pom_tsm;
   uint64_t* bar = (uint64_t*)(ring + NS * NF * PL);
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int ti0 = i0 + blockIdx.x * TILE_X, tj0 = j0 + blockIdx.y * F::TY;
-  const int i = ti0 + tx, j = tj0 + ty;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TILE_X + tx;
   static_assert(F::BW % 2 == 0 && F::BW >= TILE_X + F::OHL + F::OHR + 1, "TMA box too narrow");
   static_assert(F::BH >= F::TY + F::OHB + F::OHT, "TMA box too short");
-  const int n0 = ti0 - 1 - F::OHL, shift = n0 & 1;
-  const int c0 = n0 - shift, c1 = tj0 - 1 - f.g.joff - F::OHB;
   const int k0 = f.k0(), k1 = f.k1(), kl1 = f.kl1();
-  const bool leader = (tx == 0 && ty == 0);
+  const int nl = kl1 - k0 + 1;                                        // levels staged per tile
+  const int ntl = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this block
+  const int total = ntl * nl;                                         // stage loads of this block
+  const bool leader = (tid == 0);
   if (leader) {
     for (int s = 0; s < NS; ++s) mbar_init(&bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto issue = [&](int L) {
-    const int s = (L - k0) % NS;
+  // stage load number q of this block = level k0 + q%nl of its tile q/nl
+  auto issue = [&](int q) {
+    const int n = q / nl, L = k0 + (q - n * nl), t = (int)blockIdx.x + n * (int)gridDim.x;
+    const int by = t / nbx, bx = t - by * nbx;
+    const int n0 = i0 + bx * TILE_X - 1 - F::OHL, c0 = n0 - (n0 & 1), c1 = j0 + by * F::TY - 1 - f.g.joff - F::OHB;
+    const int s = q % NS;
     mbar_expect_tx(&bar[s], (uint32_t)(NF * F::BW * F::BH * sizeof(double)));
 #pragma unroll
-    for (int n = 0; n < NF; ++n)
-      tma_load_3d(ring + (s * NF + n) * PL, &maps.m[n], &bar[s], c0, c1, L - 1);
+    for (int m = 0; m < NF; ++m) tma_load_3d(ring + (s * NF + m) * PL, &maps.m[m], &bar[s], c0, c1, L - 1);
   };
+  int qi = 0;                                                         // next load to issue (leader)
   if (leader)
-    for (int L = k0; L < k0 + NS && L <= kl1; ++L) issue(L);
-  const bool active = (i <= i1 && j <= j1);
-  typename F::State st;     // scalars: registers
-  typename F::Cols cm;      // per-thread column arrays (dynamically indexed: local memory)
-  if (active) f.pre(i, j, st, cm);
-  const int own = (ty + F::OHB) * F::BW + tx + F::OHL + shift;
-  for (int k = k0; k <= k1; ++k) {
-    const int q0 = k - k0, s0 = q0 % NS;
-    mbar_wait(&bar[s0], (q0 / NS) & 1);
-    int s1 = s0;
-    if (F::UP && k + 1 <= kl1) {
-      s1 = (q0 + 1) % NS;
-      mbar_wait(&bar[s1], ((q0 + 1) / NS) & 1);
+    for (; qi < NS && qi < total; ++qi) issue(qi);
+#ifdef POM_COLS_LOCAL   // (experiment) the vectors in per-thread local memory, like the round-1 kernels
+  LocalCols<F::NVEC> cm;
+#else
+  ScratchCols<F::NVEC> cm{scratch + (size_t)blockIdx.x * F::NVEC * kbs * NT + tid, NT, kbs};
+#endif
+  for (int n = 0; n < ntl; ++n) {
+    const int t = (int)blockIdx.x + n * (int)gridDim.x;
+    const int by = t / nbx, bx = t - by * nbx;
+    const int ti0 = i0 + bx * TILE_X, tj0 = j0 + by * F::TY;
+    const int i = ti0 + tx, j = tj0 + ty;
+    const int shift = (ti0 - 1 - F::OHL) & 1;
+    const bool active = (i <= i1 && j <= j1);
+    typename F::State st;     // scalars: registers
+    if (active) f.pre(i, j, st, cm);
+    const int own = (ty + F::OHB) * F::BW + tx + F::OHL + shift;
+    for (int k = k0; k <= k1; ++k) {
+      const int q0 = n * nl + (k - k0), s0 = q0 % NS;
+      mbar_wait(&bar[s0], (q0 / NS) & 1);
+      int s1 = s0;
+      if (F::UP && k + 1 <= kl1) {
+        s1 = (q0 + 1) % NS;
+        mbar_wait(&bar[s1], ((q0 + 1) / NS) & 1);
+      }
+      const SmemOp<F> op{ring + s0 * NF * PL + own, ring + s1 * NF * PL + own};
+      if (active) f.level(i, j, k, st, cm, op);
+      __syncthreads();
+      // everyone is done with the stage of level k (and, after the last computed level, with the
+      // stages that were only looked at through op.up): refill them with the loads NS ahead
+      if (leader) {
+        const int qfree = (k == k1) ? n * nl + nl - 1 : q0;
+        for (; qi <= qfree + NS && qi < total; ++qi) issue(qi);
+      }
     }
-    const SmemOp<F> op{ring + s0 * NF * PL + own, ring + s1 * NF * PL + own};
-    if (active) f.level(i, j, k, st, cm, op);
+    if (active) f.post(i, j, st, cm);
+    // drop this tile's column vectors from L2 without a write-back: every thread of the block has
+    // read its own (first barrier); nobody writes the next tile's before the lines are gone (second)
+#if !defined(POM_COLS_LOCAL) && !defined(POM_NO_DISCARD)
     __syncthreads();
-    if (leader && k + NS <= kl1) issue(k + NS);   // everyone is done with the stage of level k
+    {
+      constexpr int LPL = NT / 16;                                    // 128-byte lines per level of one vector
+      const int nlines = F::NVEC * kbs * LPL;
+      const double* slot = scratch + (size_t)blockIdx.x * F::NVEC * kbs * NT;
+      for (int ln = tid; ln < nlines; ln += NT)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(slot + (size_t)ln * 16) : "memory");
+    }
+    __syncthreads();
+#endif
   }
-  if (active) f.post(i, j, st, cm);
 }
 
 template <class F>
@@ -222,7 +283,7 @@ colkernel_g(const F f, int i0, int i1, int j0, int j1) {
   const double* fld[F::NF];
   f.fields(fld);
   typename F::State st;
-  typename F::Cols cm;
+  LocalCols<F::NVEC> cm;
   f.pre(i, j, st, cm);
   const int k1 = f.k1();
   for (int k = f.k0(); k <= k1; ++k) f.level(i, j, k, st, cm, GlobalOp<F>{fld, f.g, i, j, k});
@@ -304,6 +365,7 @@ inline void launch_tma_tiles(Ctx* c, const F& f, int i0, int i1, int j0, int j1)
     double cols = (double)(i1 - i0 + 1) * (j1 - j0 + 1);
     prof_before(c, &k, 8. * cols * ((k.r3 + k.w3) * (double)c->g.kb + (k.r2 + k.w2)));
   }
+  cudaSetDevice(c->device);
   dim3 b(TILE_X, F::TY), gr(nbx, nby);
   bool tma_ok = (c->g.im % 2 == 0) && !c->no_tma;
   if (tma_ok) {
@@ -314,11 +376,8 @@ inline void launch_tma_tiles(Ctx* c, const F& f, int i0, int i1, int j0, int j1)
       if (tma_encode(c, &maps.m[n], fld[n], F::NK ? F::NK : c->g.kb, F::BW, F::BH)) tma_ok = false;
     if (tma_ok) {
       constexpr size_t smem = (size_t)(F::NS * F::NF * tma_plane(F::BW, F::BH) + 2 * F::NV * F::TY * TILE_X) * sizeof(double) + F::NS * 8;
-      static bool granted = false;
-      if (!granted) {
-        cudaFuncSetAttribute(tmakernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        granted = true;
-      }
+      static DevOnce granted;
+      if (granted.need(c->device)) cudaFuncSetAttribute(tmakernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       tmakernel<F><<<gr, b, smem, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
     }
   }
@@ -441,6 +500,7 @@ inline void launch_tile3(Ctx* c, const F& f, int i0, int i1, int j0, int j1) {
     double cols = (double)(i1 - i0 + 1) * (j1 - j0 + 1);
     prof_before(c, &k, 8. * cols * ((k.r3 + k.w3) * (double)c->g.kb + (k.r2 + k.w2)));
   }
+  cudaSetDevice(c->device);
   dim3 b(TILE_X, F::TY), gr(nbx, nby);
   TmaMaps<F::NF> maps;
   bool tma_ok = (c->g.im % 2 == 0) && !c->no_tma;
@@ -452,11 +512,10 @@ inline void launch_tile3(Ctx* c, const F& f, int i0, int i1, int j0, int j1) {
   }
   constexpr size_t sm_se = (size_t)((F::NV + 1) * TILE_Y * TILE_X) * sizeof(double) + 16;
   constexpr size_t sm_tma = sm_se + (size_t)F::NF * tma_plane(F::BW, F::BH) * sizeof(double);
-  static bool granted = false;
-  if (!granted) {
+  static DevOnce granted;
+  if (granted.need(c->device)) {
     cudaFuncSetAttribute(tile3kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_tma);
     cudaFuncSetAttribute(tile3kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_se);
-    granted = true;
   }
   if (tma_ok) tile3kernel<F, true><<<gr, b, sm_tma, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
   else tile3kernel<F, false><<<gr, b, sm_se, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
@@ -472,7 +531,7 @@ inline void launch_tma_cols(Ctx* c, const F& f, int i0, int i1, int j0, int j1) 
   const double* fld[F::NF];
   f.fields(fld);
   static typename F::State st;
-  static typename F::Cols cm;
+  static LocalCols<F::NVEC> cm;
   for (int j = j0; j <= j1; ++j)
     for (int i = i0; i <= i1; ++i) {
       f.pre(i, j, st, cm);
@@ -485,7 +544,10 @@ inline void launch_tma_cols(Ctx* c, const F& f, int i0, int i1, int j0, int j1) 
     double cols = (double)(i1 - i0 + 1) * (j1 - j0 + 1);
     prof_before(c, &k, 8. * cols * ((k.r3 + k.w3) * (double)c->g.kb + (k.r2 + k.w2)));
   }
-  dim3 b(TILE_X, F::TY), gr((i1 - i0 + TILE_X) / TILE_X, (j1 - j0 + F::TY) / F::TY);
+  cudaSetDevice(c->device);
+  constexpr int NT = TILE_X * F::TY;
+  const int nbx = (i1 - i0 + TILE_X) / TILE_X, nby = (j1 - j0 + F::TY) / F::TY;
+  dim3 b(TILE_X, F::TY);
   bool tma_ok = (c->g.im % 2 == 0) && !c->no_tma;
   if (tma_ok) {
     TmaMaps<F::NF> maps;
@@ -495,15 +557,32 @@ inline void launch_tma_cols(Ctx* c, const F& f, int i0, int i1, int j0, int j1) 
       if (tma_encode(c, &maps.m[n], fld[n], F::NK ? F::NK : c->g.kb, F::BW, F::BH)) tma_ok = false;
     if (tma_ok) {
       constexpr size_t smem = (size_t)(F::NS * F::NF * tma_plane(F::BW, F::BH)) * sizeof(double) + F::NS * 8;
-      static bool granted = false;
-      if (!granted) {
+      static DevOnce granted;
+      static int resident[64];                       // blocks per SM of this kernel, per device
+      const int dv = c->device & 63;
+      if (granted.need(c->device)) {
         cudaFuncSetAttribute(tmacolkernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        granted = true;
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tmacolkernel<F>, NT, smem);
+        resident[dv] = occ > 0 ? occ : 1;
       }
-      tmacolkernel<F><<<gr, b, smem, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
+      const int slots = c->nsm * resident[dv], ntiles = nbx * nby;
+#ifdef POM_NONPERSIST   // (experiment, with POM_COLS_LOCAL) one tile per block
+      const int grid = ntiles;
+#else
+      const int grid = ntiles < slots ? ntiles : slots;
+#endif
+      const size_t need = (size_t)slots * F::NVEC * c->g.kb * NT;
+      if (need > c->colscr_cap) {
+        if (c->colscr) { cudaStreamSynchronize((cudaStream_t)c->stream); cudaFree(c->colscr); c->colscr = nullptr; c->colscr_cap = 0; }
+        if (cudaMalloc((void**)&c->colscr, need * sizeof(double)) == cudaSuccess) c->colscr_cap = need;
+        else { (void)cudaGetLastError(); tma_ok = false; }   // no room for the scratch: direct-load kernel below
+      }
+      if (tma_ok)
+        tmacolkernel<F><<<grid, b, smem, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1, nbx, ntiles, c->colscr, c->g.kb);
     }
   }
-  if (!tma_ok) colkernel_g<F><<<gr, b, 0, (cudaStream_t)c->stream>>>(f, i0, i1, j0, j1);
+  if (!tma_ok) colkernel_g<F><<<dim3(nbx, nby), b, 0, (cudaStream_t)c->stream>>>(f, i0, i1, j0, j1);
   if (c->prof_on) prof_after(c);
 #endif
 }

@@ -20,6 +20,7 @@ LIBPATH = os.path.join(_HERE, "libpomgpu.so")
 F3D = ("aam advx advy drhox drhoy kh km kq l q2b q2 q2lb q2l rho rmean sb sclim s tb tclim t "
        "ub uf u vb vf v w wr").split()
 F3D_OPT = "trstrb trstrf srstrb srstrf taurstrb taurstrf".split()
+F3D_SCR = "rho2 s3a s3b s3c s3d s3e".split()   # library-owned scratch, addressable for unit-mode calls (smol_adif's flux arrays)
 F2D = ("aam2d advua advva adx2d ady2d art aru arv cbc cor d drx2d dry2d dt dum dvm dx dy "
        "e_atmos egb egf el elb elf et etb etf fsm h swrad ssurf tsurf ua uab uaf utb utf va "
        "vab vaf vtb vtf vfluxb vfluxf wssurf wtsurf wubot wusurf wvbot wvsurf").split()
@@ -71,6 +72,8 @@ def _bind(path):
         getattr(L, "pomgpu_" + n).argtypes = [P, C.c_double]
     L.pomgpu_check_velocity_lagged.restype = C.c_double
     L.pomgpu_check_velocity_lagged.argtypes = [P]
+    L.pomgpu_field_absmax_lagged.restype = C.c_double
+    L.pomgpu_field_absmax_lagged.argtypes = [P, C.c_char_p]
     L.pomgpu_pin_host.argtypes = [P, C.c_ulong]
     L.pomgpu_unpin_host.argtypes = [P]
     L.pomgpu_event_record.argtypes = [P, C.c_int]
@@ -103,6 +106,10 @@ def _bind(path):
     L.pomgpu_advt2.argtypes = [P] + [C.c_char_p] * 4
     L.pomgpu_dens.argtypes = [P] + [C.c_char_p] * 3
     L.pomgpu_proft.argtypes = [P] + [C.c_char_p] * 3 + [C.c_int]
+    L.pomgpu_advq_fields.argtypes = [P] + [C.c_char_p] * 3
+    L.pomgpu_smol_adif.argtypes = [P] + [C.c_char_p] * 4
+    L.pomgpu_bcond.argtypes = [P, C.c_int]
+    L.pomgpu_bcondorl.argtypes = [P, C.c_int]
     return L
 
 
@@ -118,8 +125,8 @@ def _lib(path):
 class PomGpu:
     """One j-strip (default: the whole domain) of the model, resident in HBM on one B200."""
 
-    def __init__(self, im, jm, kb, device=0, strip=None, ghost=0, _libpath=None):
-        self.L = _lib(_libpath or LIBPATH)
+    def __init__(self, im, jm, kb, device=0, strip=None, ghost=0):
+        self.L = self._library()
         self.im, self.jm, self.kb = im, jm, kb
         if strip is None:
             self.h = self.L.pomgpu_create(im, jm, kb, device)
@@ -133,13 +140,19 @@ class PomGpu:
         self.joff = self.L.pomgpu_row_offset(self.h)
         jl = self.jml
         self.shapes = {}
-        for n in F3D + F3D_OPT: self.shapes[n] = (im, jl, kb)
+        for n in F3D + F3D_OPT + F3D_SCR: self.shapes[n] = (im, jl, kb)
         for n in F2D: self.shapes[n] = (im, jl)
         for n in BJ: self.shapes[n] = (jl,)
         for n in BI: self.shapes[n] = (im,)
         for n in BJK: self.shapes[n] = (jl, kb)
         for n in BIK: self.shapes[n] = (im, kb)
         for n in F1D: self.shapes[n] = (kb,)
+
+    @staticmethod
+    def _library():
+        """The CUDA library, and nothing else: the product class has no way to select another one
+        (the host-emulated build used by the CPU tests is bound by a subclass in tests/emu.py)."""
+        return _lib(LIBPATH)
 
     def close(self):
         if getattr(self, "h", None):
@@ -172,7 +185,7 @@ class PomGpu:
         if a.shape == shp:
             return a
         j0, j1 = self.joff, self.joff + self.jml
-        if name in F2D or name in F3D or name in F3D_OPT:
+        if name in F2D or name in F3D or name in F3D_OPT or name in F3D_SCR:
             return a[:, j0:j1]
         if name in BJ or name in BJK:
             return a[j0:j1]
@@ -196,7 +209,7 @@ class PomGpu:
         for k, v in state["consts"].items():
             self.L.pomgpu_set_const(self.h, k.encode(), float(v))
         for k, v in state["fields"].items():
-            if k in self.shapes and (k not in F3D_OPT):
+            if k in self.shapes and (k not in F3D_OPT) and (k not in F3D_SCR):
                 self.put_rows(k, v, row0)
 
     def get(self, name):
@@ -257,7 +270,7 @@ class PomGpu:
         for k, v in state["consts"].items():
             self.L.pomgpu_set_const(self.h, k.encode(), float(v))  # names outside blkcon are ignored
         for k, v in state["fields"].items():
-            if k in self.shapes and (k not in F3D_OPT):
+            if k in self.shapes and (k not in F3D_OPT) and (k not in F3D_SCR):
                 self.put(k, v)
 
     # -- the reference's subroutine surface ------------------------------------
@@ -286,6 +299,10 @@ class PomGpu:
     def check_velocity_lagged(self):
         """max|vaf| of the PREVIOUS call's step (0.0 first); never waits for the step just enqueued."""
         return self.L.pomgpu_check_velocity_lagged(self.h)
+
+    def field_absmax_lagged(self, name):
+        """max|field| of the PREVIOUS call's state (0.0 first): a one-scalar read-back that never waits."""
+        return self.L.pomgpu_field_absmax_lagged(self.h, name.encode())
 
     def launch_count(self, reset=False):
         return self.L.pomgpu_launch_count(self.h, int(reset))
@@ -317,6 +334,15 @@ class PomGpu:
 
     def dens(self, si, ti, rhoo):
         self._ck(self.L.pomgpu_dens(self.h, si.encode(), ti.encode(), rhoo.encode()), "dens")
+
+    def advq_fields(self, qb, q, qf):
+        self._ck(self.L.pomgpu_advq_fields(self.h, qb.encode(), q.encode(), qf.encode()), "advq")
+
+    def smol_adif(self, xm, ym, zw, ff):
+        self._ck(self.L.pomgpu_smol_adif(self.h, xm.encode(), ym.encode(), zw.encode(), ff.encode()), "smol_adif")
+
+    def bcond(self, idx): self._ck(self.L.pomgpu_bcond(self.h, int(idx)), f"bcond({idx})")
+    def bcondorl(self, idx): self._ck(self.L.pomgpu_bcondorl(self.h, int(idx)), f"bcondorl({idx})")
 
     def proft(self, f, wfsurf, fsurf, nbc):
         self._ck(self.L.pomgpu_proft(self.h, f.encode(), wfsurf.encode(), fsurf.encode(), int(nbc)), "proft")

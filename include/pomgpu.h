@@ -96,6 +96,9 @@ double pomgpu_check_velocity(pomgpu_t* ctx);
 /* the same without waiting for the step just enqueued: starts the reduction and returns the
  * value of the previous call (one step of lag; 0 on the first call) */
 double pomgpu_check_velocity_lagged(pomgpu_t* ctx);
+/* the same lagged one-scalar read-back for any field: max |x| over the rows this strip holds
+ * (-1 for an unknown field); does not touch error_status */
+double pomgpu_field_absmax_lagged(pomgpu_t* ctx, const char* name);
 /* domain_stats (advance.f:644-755) as a device reduction: 7 partial sums for each OWNED row
  * (rows[owned_rows][7] = atot, sum(et*darea), vtot, mtot, sum(tb*dvol), sum(sb*dvol), ekin);
  * adding the rows in global order and dividing (eavg/atot, tavg/vtot, savg=stot/vtot) gives
@@ -122,8 +125,12 @@ pomgpu_group_t* pomgpu_group_create(int n, pomgpu_t** strips);
 void pomgpu_group_destroy(pomgpu_group_t* g);
 int pomgpu_nccl_unique_id(void* out128);
 int pomgpu_group_connect_nccl(pomgpu_group_t* g, const void* id128, int rank, int world);
-/* host transport (CPU tests): called with the packed south / north send buffers and the
- * receive buffers to fill; n_* = doubles per direction (0 = no neighbour on that side) */
+/* host transport (gloo in the CPU tests; MPI_Sendrecv in a Fortran/MPI driver without NCCL):
+ * called with the packed south / north send buffers and the receive buffers to fill; n_* =
+ * doubles per direction (0 = no neighbour on that side).  All four pointers are HOST memory:
+ * page-locked mirrors that the library copies from / to its device staging buffers around the
+ * call.  A non-zero return marks the group failed: error_status=1 on every strip and no further
+ * kernel is launched (the ghost rows would be stale). */
 typedef int (*pomgpu_halo_cb)(void* user, const double* send_s, double* recv_s, long n_s,
                               const double* send_n, double* recv_n, long n_n);
 void pomgpu_group_set_transport(pomgpu_group_t* g, pomgpu_halo_cb cb, void* user);
@@ -162,6 +169,19 @@ int pomgpu_profu(pomgpu_t* ctx);                   /* solver.f:1686 */
 int pomgpu_profv(pomgpu_t* ctx);                   /* solver.f:1783 */
 int pomgpu_vertvl(pomgpu_t* ctx);                  /* solver.f:1970 (+ bcondorl(5)) */
 int pomgpu_realvertvl(pomgpu_t* ctx);              /* solver.f:2024 */
+/* advq(qb,q,qf) for ONE quantity (the reference's signature, solver.f:411); pomgpu_advq above does
+ * advq(q2b,q2,uf) and advq(q2lb,q2l,vf) in one pass, which is what the step runs */
+int pomgpu_advq_fields(pomgpu_t* ctx, const char* qb, const char* q, const char* qf);
+/* smol_adif(xmassflux,ymassflux,zwflux,ff) (solver.f:1880): ff*fsm, then the anti-diffusive mass
+ * fluxes in place; arguments name 3-D fields (COMMON members or the scratch fields "s3a".."s3e") */
+int pomgpu_smol_adif(pomgpu_t* ctx, const char* xmassflux, const char* ymassflux, const char* zwflux,
+                     const char* ff);
+/* bounds_forcing.f:6 bcond(idx) for idx = 1 (elf), 2 (uaf,vaf), 4 (T,S in uf,vf), 5 (w), 6 (q2,q2l in
+ * uf,vf) and :331 bcondorl(idx) for idx = 3 (uf,vf Orlanski), 5 (w) as stand-alone calls: the
+ * branches advance.f calls (:231,290,398,414,442,464).  Other idx return 2.  pomgpu_step runs the
+ * same point functions fused into its kernels and never calls these. */
+int pomgpu_bcond(pomgpu_t* ctx, int idx);
+int pomgpu_bcondorl(pomgpu_t* ctx, int idx);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = None
+_LIB = {}
 
 F3D = ("aam advx advy drhox drhoy dtef kh km kq l q2b q2 q2lb q2l rho rmean sb sclim s "
        "tb tclim t ub uf u vb vf v w wr zflux trstr trstrb trstrf srstr srstrb srstrf "
@@ -30,19 +30,29 @@ BIK = ("tbn sbn tbs sbs vbn vbs tbnb tbnf sbnb sbnf vbnb vbnf tbsb tbsf sbsb sbs
 F1D = "z zz dz dzz".split()
 
 
-def build(force=False):
-    """Compile oracle/libpomo.so with the committed Makefile (gcc, -ffp-contract=off)."""
-    so = os.path.join(_HERE, "libpomo.so")
+def build(force=False, variant=""):
+    """Compile oracle/libpomo[_O0|_O3].so with the committed Makefile (gcc, -ffp-contract=off).
+    variant "" = -O2 (the checker); "O0" / "O3" = the CPU-baseline variants of SURVEY.md 8(d)."""
+    name = "libpomo.so" if not variant else f"libpomo_{variant}.so"
+    so = os.path.join(_HERE, name)
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["make", "-s", "-C", _HERE, "libpomo.so"])
+        subprocess.check_call(["make", "-s", "-C", _HERE, name])
     return so
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        L = C.CDLL(build())
+def set_threads(n):
+    """OpenMP threads of the oracle from now on (bench.py: torchrun exports OMP_NUM_THREADS=1)."""
+    os.environ["OMP_NUM_THREADS"] = str(int(n))
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
+def lib(variant=""):
+    if variant not in _LIB:
+        L = C.CDLL(build(variant=variant))
         L.pomo_create.restype = C.c_void_p
         L.pomo_create.argtypes = [C.c_int] * 3
         L.pomo_destroy.argtypes = [C.c_void_p]
@@ -69,15 +79,15 @@ def lib():
         L.pomo_internal_stage.argtypes = [P, C.c_int]
         for n in ("wind_interp", "heat_interp", "lateral_bc_interp"):
             getattr(L, "pomo_" + n).argtypes = [P, C.c_double]
-        _LIB = L
-    return _LIB
+        _LIB[variant] = L
+    return _LIB[variant]
 
 
 class Oracle:
     """One sub-domain of the reference model on the CPU (fp64, no FMA)."""
 
-    def __init__(self, im, jm, kb):
-        self.L = lib()
+    def __init__(self, im, jm, kb, variant=""):
+        self.L = lib(variant)
         self.im, self.jm, self.kb = im, jm, kb
         self.h = self.L.pomo_create(im, jm, kb)
         self.f = {}

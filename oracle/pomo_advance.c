@@ -62,14 +62,18 @@ void pomo_mode_interaction(pomo_t *S) {
     }
     pomo_advave(S);
     /* :172-177 */
+    OMP_FOR
     DO(j, 1, jm) DO(i, 1, im) {
       adx2d(i,j)=adx2d(i,j)-advua(i,j);
       ady2d(i,j)=ady2d(i,j)-advva(i,j);
     }
   }
   /* :181-196 */
+  OMP_FOR
   DO(j, 1, jm) DO(i, 1, im) egf(i,j)=el(i,j)*ispi;
+  OMP_FOR
   DO(j, 1, jm) DO(i, 2, im) utf(i,j)=ua(i,j)*(d(i,j)+d(i-1,j))*isp2i;
+  OMP_FOR
   DO(j, 2, jm) DO(i, 1, im) vtf(i,j)=va(i,j)*(d(i,j)+d(i,j-1))*isp2i;
 }
 
@@ -142,10 +146,13 @@ void pomo_mode_external(pomo_t *S) {
   pomo_bcond(S, 2); /* :290 */
   /* :295-318 */
   if (iext == (isplit-2)) {
+    OMP_FOR
     DO(j, 1, jm) DO(i, 1, im) S->etf[I2(i,j)]=.25*smoth*elf(i,j);
   } else if (iext == (isplit-1)) {
+    OMP_FOR
     DO(j, 1, jm) DO(i, 1, im) S->etf[I2(i,j)]=S->etf[I2(i,j)]+.5*(1.-.5*smoth)*elf(i,j);
   } else if (iext == isplit) {
+    OMP_FOR
     DO(j, 1, jm) DO(i, 1, im) S->etf[I2(i,j)]=(S->etf[I2(i,j)]+.5*elf(i,j))*fsm(i,j);
   }
   /* :321-330 whole-array filter and time rotation */
@@ -164,8 +171,11 @@ void pomo_mode_external(pomo_t *S) {
   }
   /* :332-350 */
   if (iext != isplit) {
+    OMP_FOR
     DO(j, 1, jm) DO(i, 1, im) egf(i,j)=egf(i,j)+el(i,j)*ispi;
+    OMP_FOR
     DO(j, 1, jm) DO(i, 2, im) utf(i,j)=utf(i,j)+ua(i,j)*(d(i,j)+d(i-1,j))*isp2i;
+    OMP_FOR
     DO(j, 2, jm) DO(i, 1, im) vtf(i,j)=vtf(i,j)+va(i,j)*(d(i,j)+d(i,j-1))*isp2i;
   }
 }
@@ -181,13 +191,13 @@ void pomo_internal_stage(pomo_t *S, int stage) {
   switch (stage) {
   case 0: /* :365-393 */
     memset(S->tps, 0, sizeof(double) * N2);
-    DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im) tps(i,j)=tps(i,j)+u(i,j,k)*dz(k);
+    DO(k, 1, kbm1) OMP_FOR DO(j, 1, jm) DO(i, 1, im) tps(i,j)=tps(i,j)+u(i,j,k)*dz(k);
     OMP_FOR
     DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 2, im)
       u(i,j,k)=(u(i,j,k)-tps(i,j))+
                (utb(i,j)+utf(i,j))/(dt(i,j)+dt(i-1,j));
     memset(S->tps, 0, sizeof(double) * N2);
-    DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im) tps(i,j)=tps(i,j)+v(i,j,k)*dz(k);
+    DO(k, 1, kbm1) OMP_FOR DO(j, 1, jm) DO(i, 1, im) tps(i,j)=tps(i,j)+v(i,j,k)*dz(k);
     OMP_FOR
     DO(k, 1, kbm1) DO(j, 2, jm) DO(i, 1, im)
       v(i,j,k)=(v(i,j,k)-tps(i,j))+
@@ -251,7 +261,7 @@ void pomo_internal_stage(pomo_t *S, int stage) {
   case 15: /* :464-514 */
     pomo_bcondorl(S, 3);
     memset(S->tps, 0, sizeof(double) * N2);
-    DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im)
+    DO(k, 1, kbm1) OMP_FOR DO(j, 1, jm) DO(i, 1, im)
       tps(i,j)=tps(i,j)
                +(uf(i,j,k)+ub(i,j,k)-2.*u(i,j,k))*dz(k);
     OMP_FOR
@@ -260,7 +270,7 @@ void pomo_internal_stage(pomo_t *S, int stage) {
                +.5*smoth*(uf(i,j,k)+ub(i,j,k)
                           -2.*u(i,j,k)-tps(i,j));
     memset(S->tps, 0, sizeof(double) * N2);
-    DO(k, 1, kbm1) DO(j, 1, jm) DO(i, 1, im)
+    DO(k, 1, kbm1) OMP_FOR DO(j, 1, jm) DO(i, 1, im)
       tps(i,j)=tps(i,j)
                +(vf(i,j,k)+vb(i,j,k)-2.*v(i,j,k))*dz(k);
     OMP_FOR

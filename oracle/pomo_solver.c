@@ -20,21 +20,25 @@ void pomo_advave(pomo_t *S) {
   /* :16-18 */
   zero2(S, S->advua); zero2(S, S->fluxua); zero2(S, S->fluxva);
   /* :20-26 */
+  OMP_FOR
   DO(j, 2, jm) DO(i, 2, imm1)
     fluxua(i,j)=.125*((d(i+1,j)+d(i,j))*ua(i+1,j)
                       +(d(i,j)+d(i-1,j))*ua(i,j))
                      *(ua(i+1,j)+ua(i,j));
   /* :28-34 */
+  OMP_FOR
   DO(j, 2, jm) DO(i, 2, im)
     fluxva(i,j)=.125*((d(i,j)+d(i,j-1))*va(i,j)
                       +(d(i-1,j)+d(i-1,j-1))*va(i-1,j))
                      *(ua(i,j)+ua(i,j-1));
   /* :37-43 */
+  OMP_FOR
   DO(j, 2, jm) DO(i, 2, imm1)
     fluxua(i,j)=fluxua(i,j)
                 -d(i,j)*2.*aam2d(i,j)*(uab(i+1,j)-uab(i,j))
                   /dx(i,j);
   /* :45-58 */
+  OMP_FOR
   DO(j, 2, jm) DO(i, 2, im) {
     tps(i,j)=.25*(d(i,j)+d(i-1,j)+d(i,j-1)+d(i-1,j-1))
              *(aam2d(i,j)+aam2d(i,j-1)
@@ -49,33 +53,39 @@ void pomo_advave(pomo_t *S) {
   }
   /* :60-61 exchange2d_mpi no-op */
   /* :63-68 */
+  OMP_FOR
   DO(j, 2, jmm1) DO(i, 2, imm1)
     advua(i,j)=fluxua(i,j)-fluxua(i-1,j)
                +fluxva(i,j+1)-fluxva(i,j);
   /* :73-75 */
   zero2(S, S->advva); zero2(S, S->fluxua); zero2(S, S->fluxva);
   /* :78-84 */
+  OMP_FOR
   DO(j, 2, jm) DO(i, 2, im)
     fluxua(i,j)=.125*((d(i,j)+d(i-1,j))*ua(i,j)
                       +(d(i,j-1)+d(i-1,j-1))*ua(i,j-1))
                      *(va(i-1,j)+va(i,j));
   /* :86-92 */
+  OMP_FOR
   DO(j, 2, jmm1) DO(i, 2, im)
     fluxva(i,j)=.125*((d(i,j+1)+d(i,j))*va(i,j+1)
                       +(d(i,j)+d(i,j-1))*va(i,j))
                      *(va(i,j+1)+va(i,j));
   /* :95-101 */
+  OMP_FOR
   DO(j, 2, jmm1) DO(i, 2, im)
     fluxva(i,j)=fluxva(i,j)
                 -d(i,j)*2.*aam2d(i,j)*(vab(i,j+1)-vab(i,j))
                   /dy(i,j);
   /* :103-109 (tps reused from the u half, :47) */
+  OMP_FOR
   DO(j, 2, jm) DO(i, 2, im) {
     fluxva(i,j)=fluxva(i,j)*dx(i,j);
     fluxua(i,j)=(fluxua(i,j)-tps(i,j))*.25
                 *(dy(i,j)+dy(i-1,j)+dy(i,j-1)+dy(i-1,j-1));
   }
   /* :114-119 */
+  OMP_FOR
   DO(j, 2, jmm1) DO(i, 2, imm1)
     advva(i,j)=fluxua(i+1,j)-fluxua(i,j)
                +fluxva(i,j)-fluxva(i,j-1);
@@ -84,6 +94,7 @@ void pomo_advave(pomo_t *S) {
 #define curv2d(i, j) (curv2dp[I2(i, j)])
     zero2(S, curv2dp);                    /* COMMON curv2d: zero outside the interior */
     /* :125-133 */
+    OMP_FOR
     DO(j, 2, jmm1) DO(i, 2, imm1) {
       double q=.25*(vab(i,j)+vab(i,j+1)+vab(i-1,j)+vab(i-1,j+1));
       wubot(i,j)=-0.5*(cbc(i,j)+cbc(i-1,j))
@@ -91,6 +102,7 @@ void pomo_advave(pomo_t *S) {
                  *uab(i,j);
     }
     /* :135-143 */
+    OMP_FOR
     DO(j, 2, jmm1) DO(i, 2, imm1) {
       double q=.25*(uab(i,j)+uab(i+1,j)+uab(i,j-1)+uab(i+1,j-1));
       wvbot(i,j)=-0.5*(cbc(i,j)+cbc(i,j-1))
@@ -98,12 +110,14 @@ void pomo_advave(pomo_t *S) {
                  *vab(i,j);
     }
     /* :145-152 */
+    OMP_FOR
     DO(j, 2, jmm1) DO(i, 2, imm1)
       curv2d(i,j)=.25
                   *((va(i,j+1)+va(i,j))*(dy(i+1,j)-dy(i-1,j))
                    -(ua(i+1,j)+ua(i,j))*(dx(i,j+1)-dx(i,j-1)))
                   /(dx(i,j)*dy(i,j));
     /* :155-172 (n_west == -1) */
+    OMP_FOR
     DO(j, 2, jmm1) DO(i, 3, imm1)
       advua(i,j)=advua(i,j)-aru(i,j)*.25
                  *(curv2d(i,j)*d(i,j)

@@ -5,8 +5,15 @@ from extpom_b200 import synthetic as syn
 from extpom_b200.pomgpu import PomGpu
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 kb = int(sys.argv[2]) if len(sys.argv) > 2 else 41
-lib = os.environ.get("POMGPU_LIB")
-st, g = syn.seamount(n, n, kb, lambda a, b, c: PomGpu(a, b, c, _libpath=lib))
+lib = os.environ.get("POMGPU_LIB")      # a variant build of the CUDA library (extpom_b200/variants/*.so), for A/B timing
+if lib:
+    from extpom_b200 import pomgpu as _pg
+
+    class PomGpu(_pg.PomGpu):             # noqa: F811  (developer tool: never part of the product path)
+        @staticmethod
+        def _library():
+            return _pg._lib(lib)
+st, g = syn.seamount(n, n, kb, PomGpu)
 print("lib:", lib or "default")
 del st
 for i in range(1, 4): g.step(i)

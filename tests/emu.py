@@ -10,7 +10,7 @@ this test helper.
 import os
 import subprocess
 
-from extpom_b200.pomgpu import PomGpu
+from extpom_b200 import pomgpu as _pg
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU_SO = os.path.join(_ROOT, "tests", "_emu", "libpomgpu_emu.so")
@@ -21,5 +21,9 @@ def build_emu():
     return EMU_SO
 
 
-def EmuPom(im, jm, kb, **kw):
-    return PomGpu(im, jm, kb, _libpath=build_emu(), **kw)
+class EmuPom(_pg.PomGpu):
+    """PomGpu bound to the host-emulated library (test infrastructure; not importable from the package)."""
+
+    @staticmethod
+    def _library():
+        return _pg._lib(build_emu())

@@ -92,7 +92,8 @@ def _interior(a):
 
 
 ROUTINES = ["dens", "baropg", "baropg_mcc", "advct", "advave", "vertvl", "advq", "profq", "advt1", "advt2", "advt2_it3",
-            "proft1", "proft2", "proft3", "advu", "advv", "profu", "profv", "realvertvl"]
+            "proft1", "proft2", "proft3", "advu", "advv", "profu", "profv", "realvertvl",
+            "bcond1", "bcond2", "bcond4", "bcond6", "bcondorl3", "bcondorl5", "smol_adif", "advq_one"]
 
 
 def check_routine(factory, routine, dims):
@@ -158,6 +159,39 @@ def check_routine(factory, routine, dims):
         out = ["uf", "wubot"] if routine == "profu" else ["vf", "wvbot"]
     elif routine == "realvertvl":
         o.realvertvl(); g.realvertvl(); out = ["wr"]
+    elif routine.startswith("bcond"):
+        # the stand-alone entries of bounds_forcing.f:6,331 on arrays the interior schemes have NOT
+        # pre-masked: random values everywhere, so that edge assignment and mask pass both show
+        rng = np.random.default_rng(5)
+        idx, orl = int(routine[-1]), routine.startswith("bcondorl")
+        names = {1: ["elf"], 2: ["uaf", "vaf"], 3: ["uf", "vf"], 4: ["uf", "vf"], 5: ["w"], 6: ["uf", "vf"]}[idx]
+        for n in names:
+            a = np.asfortranarray(o.get(n) + rng.standard_normal(o.get(n).shape))
+            o.put(n, a); g.put(n, a)
+        (o.bcondorl if orl else o.bcond)(idx)
+        (g.bcondorl if orl else g.bcond)(idx)
+        out, tol = names, 0.0
+    elif routine == "smol_adif":
+        rng = np.random.default_rng(6)
+        shp = o.get("uf").shape
+        ff = np.asfortranarray(np.abs(o.get("t")) + 1e-3 * rng.random(shp))
+        fl = [np.asfortranarray(1e3 * rng.standard_normal(shp)) for _ in range(3)]
+        ffo = ff.copy(order="F")
+        flo = [a.copy(order="F") for a in fl]
+        o.L.pomo_smol_adif(o.h, *[a.ctypes.data for a in flo], ffo.ctypes.data)
+        for n, a in zip(("s3c", "s3d", "s3e", "uf"), fl + [ff]):
+            g.put(n, a)
+        g.smol_adif("s3c", "s3d", "s3e", "uf")
+        assert np.array_equal(ffo, g.get("uf"))
+        # the fluxes on the ranges smol_adif assigns (solver.f:1903,1924,1945)
+        x, y, z = [g.get(n) for n in ("s3c", "s3d", "s3e")]
+        assert np.array_equal(flo[0][1:, 1:-1, :kb - 1], x[1:, 1:-1, :kb - 1])
+        assert np.array_equal(flo[1][1:-1, 1:, :kb - 1], y[1:-1, 1:, :kb - 1])
+        assert np.array_equal(flo[2][1:-1, 1:-1, 1:kb - 1], z[1:-1, 1:-1, 1:kb - 1])
+    elif routine == "advq_one":
+        o.f["uf"][...] = 0
+        g.put("uf", o.get("uf"))
+        o.advq("q2b", "q2", "uf"); g.advq_fields("q2b", "q2", "uf"); out = ["uf"]
     for n in out:
         a, b = o.get(n), g.get(n)
         assert rel_err(a, b) <= tol, (routine, n, rel_err(a, b))

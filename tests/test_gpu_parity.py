@@ -46,6 +46,69 @@ def test_quarter_of_reference_default_grid_40_steps():
     print("worst rel max-abs error after 40 steps vs libm-pow oracle:", worst)
 
 
+def test_full_reference_default_grid_282x306x40_10_steps():
+    """BASELINE configs[0]: the reference's own grid (pom.h_dist:22-28: im_global=282, jm_global=306,
+    kb=40) as ONE sub-domain with the default namelist (mode=3, nadv=2, nitera=1, npg=1, isplit=30),
+    10 internal steps: bitwise when |S|**1.5 uses the same routine on both sides, <= 1e-10 (max-abs /
+    field max, every compared field) against the libm-pow oracle."""
+    case = ((282, 306, 40), 10, {})
+    assert pc.check_steps(_factory, case, pow_mode=1, tol=0.0) == 0.0
+    worst = pc.check_steps(_factory, case, pow_mode=0, tol=1e-10)
+    print("282x306x40, 10 steps: worst rel max-abs error vs libm-pow oracle:", worst)
+
+
+def test_kb61_128x128_columns_match_oracle():
+    """BASELINE configs[4] has kb=61: the column solvers (profq, proft, profu/v) with 61 levels on
+    128x128 columns, 3 internal steps (one cold-start step + two full ones)."""
+    pc.check_steps(_factory, ((128, 128, 61), 3, {"island": True}))
+
+
+def test_config1_1024x1024x41_matches_oracle():
+    """BASELINE configs[1] at FULL size against the oracle: seamount 1024x1024x41, isplit=30, three
+    internal steps (the first is the cold-start step that skips the 3-D block, advance.f:362), every
+    prognostic and diagnostic field of tests/common.py within RTOL.  One generated state feeds both."""
+    import gc
+    from oracle.pomo import Oracle
+    from tests.common import assert_close
+    im = jm = 1024; kb = 41
+    st = syn.make_state(im, jm, kb)
+    o = Oracle(im, jm, kb)
+    o.load(st)
+    g = _factory(im, jm, kb)
+    g.load(st)
+    syn.finish_init(st, o)
+    syn.finish_init(st, g)
+    del st
+    gc.collect()
+    for i in (1, 2, 3):
+        o.step(i)
+        g.step(i)
+    worst = assert_close(o, g, tol=RTOL)
+    vo, vg = o.check_velocity(), g.check_velocity()
+    assert abs(vo - vg) <= RTOL * max(1.0, abs(vo))
+    print("1024x1024x41, 3 steps: worst rel max-abs error vs oracle:", worst)
+    o.close(); g.close()
+
+
+def test_two_nccl_ranks_equal_single_domain_bitwise():
+    """SURVEY 8(e) acceptance through the NCCL transport: two processes, one strip per GPU, every
+    rank compares its rows bitwise with a single-domain run (scripts/strip_check.py).  Needs two
+    GPUs; bench.py repeats the same check before every multi-GPU timing (`nrank_parity`)."""
+    import os, socket, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0)); port = sk.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(root, "scripts", "strip_check.py"), "96", "160", "16", "6", "4"],
+                       capture_output=True, text=True, cwd=root, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("BITWISE EQUAL") == 2, r.stdout
+
+
 def test_full_size_properties():
     """1024x1024x41 (BASELINE configs[1]): (a) two independent runs are bitwise identical,
     (b) fields stay finite and below the blow-up bound, (c) land stays masked,
@@ -182,3 +245,63 @@ def test_direct_load_fallback_equals_tma_path(monkeypatch):
 
 def test_push_of_u_v_between_steps():
     pc.check_push_midrun(_factory)
+
+
+def test_host_callback_transport_on_the_device_build():
+    """pomgpu_group_set_transport with the CUDA library: the callback gets HOST buffers (pinned
+    mirrors of the device staging buffers).  Two strips, each in its own group and stepped by its
+    own thread, swap their packed halo rows through Python queues; the result must equal the
+    single-domain run bitwise.  A failing transport must stop the step and set error_status."""
+    import queue, threading
+    from extpom_b200 import strips as sp
+    from extpom_b200.pomgpu import PomGpu, PomGroup, PomGpuError
+    from tests.common import F2, F3
+    dims, nstep, ghost = (48, 60, 10), 4, 3
+    fac = lambda a, b, c, strip=None, ghost=0: PomGpu(a, b, c, strip=strip, ghost=ghost)
+    _, whole = syn.seamount(*dims, lambda a, b, c: PomGpu(a, b, c), island=True)
+    owns = sp.partition(dims[1], 2)
+    strips = [sp.make_strip(*dims, own, ghost, fac, island=True)[1] for own in owns]
+    groups = [PomGroup([s]) for s in strips]
+    box = [queue.Queue(), queue.Queue()]           # box[r]: rows on their way TO rank r
+
+    def transport(rank):
+        def fn(send_s, recv_s, send_n, recv_n):
+            if rank == 0:                           # north neighbour only
+                box[1].put(send_n.copy()); recv_n[...] = box[0].get(timeout=60)
+            else:
+                box[0].put(send_s.copy()); recv_s[...] = box[1].get(timeout=60)
+        return fn
+
+    errs = []
+
+    def run(rank):
+        try:
+            grp = groups[rank]
+            grp.set_transport(transport(rank))
+            sp.finish_init_group(None, grp)
+            for i in range(1, nstep + 1):
+                grp.step(i)
+            strips[rank].sync()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    for t in th: t.start()
+    for t in th: t.join()
+    assert not errs, errs
+    for i in range(1, nstep + 1):
+        whole.step(i)
+    for n in F3 + F2:
+        a = whole.get(n)
+        b = np.concatenate([g.gather(n) for g in groups], axis=1)
+        if n in ("t", "tb", "s", "sb"):
+            a, b = a[:, :, :-1], b[:, :, :-1]
+        assert np.array_equal(a, b), n
+
+    def broken(*_):
+        raise RuntimeError("link down")
+    groups[0].set_transport(broken)
+    with pytest.raises(PomGpuError):
+        for i in range(nstep + 1, nstep + 12):
+            groups[0].step(i)
+    assert strips[0].getc("error_status") == 1

@@ -19,7 +19,7 @@ from tests.common import F2, F3
 
 
 def _factory(im, jm, kb, strip=None, ghost=0):
-    return PomGpu(im, jm, kb, strip=strip, ghost=ghost, _libpath=emu.build_emu())
+    return emu.EmuPom(im, jm, kb, strip=strip, ghost=ghost)
 
 
 def _whole(dims, nstep, **kw):
@@ -97,6 +97,23 @@ def test_seam_without_transport_sets_error_status():
         for i in range(1, 4):
             grp.step(i)
     assert g.getc("error_status") == 1
+
+
+def test_failing_transport_stops_the_step_and_keeps_the_error():
+    """A transport failure must not be swallowed (ghost rows would be stale): the step raises,
+    error_status=1 survives the next CSYNC of the group's scalars, later steps keep failing."""
+    im, jm, kb = 20, 30, 7
+    st, g = sp.make_strip(im, jm, kb, (1, 15), 3, _factory)
+    grp = PomGroup([g])
+
+    def broken(*_):
+        raise RuntimeError("link down")
+    grp.set_transport(broken)
+    for attempt in range(2):
+        with pytest.raises(Exception):
+            for i in range(1, 4):
+                grp.step(i)
+        assert g.getc("error_status") == 1
 
 
 # ---- two processes over gloo: the host-callback transport ---------------------------------
