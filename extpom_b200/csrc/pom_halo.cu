@@ -51,18 +51,36 @@ __global__ void pack_kernel(PackJob J, double* buf, bool unpack) {
 }
 #endif
 
-static void run_pack(Ctx* c, const PackJob& J, double* buf, bool unpack) {
+static void run_pack(Ctx* c, const PackJob& J, double* buf, bool unpack, void* stream) {
   if (J.total == 0) return;
   c->launches++;
 #ifdef POMGPU_EMU
+  (void)stream;
   for (long e = 0; e < J.total; ++e) pack_one(J, buf, e, unpack);
 #else
   cudaSetDevice(c->device);
   int blocks = (int)((J.total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_kernel<<<blocks, 256, 0, (cudaStream_t)c->stream>>>(J, buf, unpack);
+  pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(J, buf, unpack);
 #endif
 }
+
+#ifndef POMGPU_EMU
+// the communication stream of a strip (high priority: its few blocks are scheduled ahead of the
+// compute kernels' when SM slots free up) and the two events that order it against the compute stream
+static bool comm_ready(Ctx* c) {
+  if (c->comm_stream) return true;
+  cudaSetDevice(c->device);
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  cudaStream_t s; cudaEvent_t e;
+  if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
+  c->comm_stream = (void*)s;
+  cudaEventCreateWithFlags(&e, cudaEventDisableTiming); c->ev_packed = (void*)e;
+  cudaEventCreateWithFlags(&e, cudaEventDisableTiming); c->ev_halo = (void*)e;
+  return true;
+}
+#endif
 
 // ---- NCCL through dlopen -----------------------------------------------------------------
 #ifndef POMGPU_EMU
@@ -127,6 +145,12 @@ Group* group_create(int n, Ctx** ctxs) {
     if ((c->jown0 > 1 || c->jown1 < c->g.jmg) && c->jown1 - c->jown0 + 1 < G->ghost + 4) { free(G); return nullptr; }
   }
   for (int f = 0; f < F_COUNT; ++f) G->valid[f] = G->ghost;
+  // overlap needs one compute stream per process side of a seam: strips of one device (shared stream)
+  // or a single strip per process; in-process seams between devices stay on the ordered path
+  G->overlap = (getenv("POMGPU_NO_OVERLAP") == nullptr);
+#ifndef POMGPU_EMU
+  for (int r = 1; r < n; ++r) if (ctxs[r]->device != ctxs[0]->device) G->overlap = 0;
+#endif
   return G;
 }
 
@@ -182,13 +206,19 @@ static int fail(Group* G, const char* msg) {
 }
 
 // copy between the staging buffers of two strips of this process, on the DESTINATION's stream
-static int dev_copy_between(Ctx* dc, double* dst, Ctx* sc, const double* src, size_t n) {
+static int dev_copy_between(Ctx* dc, double* dst, Ctx* sc, const double* src, size_t n, void* stream) {
 #ifdef POMGPU_EMU
-  (void)sc; return dev_d2d(dc, dst, src, n);
+  (void)sc; (void)stream; return dev_d2d(dc, dst, src, n);
 #else
-  if (dc->device == sc->device) return dev_d2d(dc, dst, src, n);
+  if (dc->device == sc->device) {
+    cudaSetDevice(dc->device);
+    if (cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) == cudaSuccess) return 0;
+    snprintf(dc->err, sizeof(dc->err), "halo copy failed");
+    dc->c.error_status = 1;
+    return 1;
+  }
   cudaSetDevice(dc->device);
-  if (cudaMemcpyPeerAsync(dst, dc->device, src, sc->device, n * 8, (cudaStream_t)dc->stream) != cudaSuccess) {
+  if (cudaMemcpyPeerAsync(dst, dc->device, src, sc->device, n * 8, (cudaStream_t)stream) != cudaSuccess) {
     snprintf(dc->err, sizeof(dc->err), "peer copy between devices %d and %d failed", sc->device, dc->device);
     dc->c.error_status = 1;
     return 1;
@@ -233,8 +263,32 @@ int group_exchange(Group* G, const int* fields, int nf) {
           if (dev_alloc(c, &G->buf[r][b], G->bufcap[r][b])) return fail(G, "halo exchange: out of device memory");
         }
       }
-      if (has_s(c)) run_pack(c, J[r][0], G->buf[r][0], false);
-      if (has_n(c)) run_pack(c, J[r][1], G->buf[r][1], false);
+      if (has_s(c)) run_pack(c, J[r][0], G->buf[r][0], false, c->stream);
+      if (has_n(c)) run_pack(c, J[r][1], G->buf[r][1], false, c->stream);
+    }
+    // from here on (transfer, unpack) on the communication stream when the transport can overlap:
+    // xs[r] = the stream the rest of strip r's exchange is enqueued on
+    void* xs_[16];
+    bool ov = false;
+#ifndef POMGPU_EMU
+    ov = G->overlap && !G->cb;
+    for (int r = 0; r < G->n && ov; ++r) ov = comm_ready(G->c[r]);
+#endif
+    for (int r = 0; r < G->n; ++r) {
+      Ctx* c = G->c[r];
+      xs_[r] = c->stream;
+#ifndef POMGPU_EMU
+      if (ov) {
+        // strips of one device share the compute stream and (strip 0's) communication stream
+        Ctx* c0 = G->c[0];
+        xs_[r] = c0->comm_stream;
+        if (r == 0) {
+          cudaSetDevice(c0->device);
+          cudaEventRecord((cudaEvent_t)c0->ev_packed, (cudaStream_t)c0->stream);
+          cudaStreamWaitEvent((cudaStream_t)c0->comm_stream, (cudaEvent_t)c0->ev_packed, 0);
+        }
+      }
+#endif
     }
     // seams inside this process.  Strips on one device share a stream (program order); strips on
     // different devices have their own streams, so the copy into b's receive buffer must wait for
@@ -257,8 +311,8 @@ int group_exchange(Group* G, const int* fields, int nf) {
         cudaSetDevice(a->device); cudaStreamWaitEvent((cudaStream_t)a->stream, (cudaEvent_t)G->ev_pack[r + 1], 0);
       }
 #endif
-      int rc = dev_copy_between(b, G->buf[r + 1][2], a, G->buf[r][1], (size_t)J[r][1].total);   // a's north rows -> b's south ghosts
-      rc |= dev_copy_between(a, G->buf[r][3], b, G->buf[r + 1][0], (size_t)J[r + 1][0].total);
+      int rc = dev_copy_between(b, G->buf[r + 1][2], a, G->buf[r][1], (size_t)J[r][1].total, xs_[r + 1]);   // a's north rows -> b's south ghosts
+      rc |= dev_copy_between(a, G->buf[r][3], b, G->buf[r + 1][0], (size_t)J[r + 1][0].total, xs_[r]);
       if (rc) return 1;
 #ifndef POMGPU_EMU
       if (cross) {   // the next pack into a send buffer waits until the neighbour's copy has read it
@@ -307,12 +361,12 @@ int group_exchange(Group* G, const int* fields, int nf) {
         cudaSetDevice(cs->device);
         g_nccl.GroupStart();
         if (xs) {
-          g_nccl.Send(G->buf[0][0], (size_t)J[0][0].total, ncclDouble, G->rank - 1, G->nccl, (cudaStream_t)cs->stream);
-          g_nccl.Recv(G->buf[0][2], (size_t)J[0][0].total, ncclDouble, G->rank - 1, G->nccl, (cudaStream_t)cs->stream);
+          g_nccl.Send(G->buf[0][0], (size_t)J[0][0].total, ncclDouble, G->rank - 1, G->nccl, (cudaStream_t)xs_[0]);
+          g_nccl.Recv(G->buf[0][2], (size_t)J[0][0].total, ncclDouble, G->rank - 1, G->nccl, (cudaStream_t)xs_[0]);
         }
         if (xn) {
-          g_nccl.Send(G->buf[G->n - 1][1], (size_t)J[G->n - 1][1].total, ncclDouble, G->rank + 1, G->nccl, (cudaStream_t)cn->stream);
-          g_nccl.Recv(G->buf[G->n - 1][3], (size_t)J[G->n - 1][1].total, ncclDouble, G->rank + 1, G->nccl, (cudaStream_t)cn->stream);
+          g_nccl.Send(G->buf[G->n - 1][1], (size_t)J[G->n - 1][1].total, ncclDouble, G->rank + 1, G->nccl, (cudaStream_t)xs_[G->n - 1]);
+          g_nccl.Recv(G->buf[G->n - 1][3], (size_t)J[G->n - 1][1].total, ncclDouble, G->rank + 1, G->nccl, (cudaStream_t)xs_[G->n - 1]);
         }
         int rc = g_nccl.GroupEnd();
         if (rc) { char m[200]; snprintf(m, sizeof(m), "nccl exchange: %s", g_nccl.GetErrorString(rc)); return fail(G, m); }
@@ -322,9 +376,19 @@ int group_exchange(Group* G, const int* fields, int nf) {
     }
     for (int r = 0; r < G->n; ++r) {
       Ctx* c = G->c[r];
-      if (has_s(c)) run_pack(c, J[r][2], G->buf[r][2], true);
-      if (has_n(c)) run_pack(c, J[r][3], G->buf[r][3], true);
+      if (has_s(c)) run_pack(c, J[r][2], G->buf[r][2], true, xs_[r]);
+      if (has_n(c)) run_pack(c, J[r][3], G->buf[r][3], true, xs_[r]);
     }
+#ifndef POMGPU_EMU
+    if (ov) {   // the kernel that asked for these rows waits for this event before it touches a seam band
+      Ctx* c0 = G->c[0];
+      cudaSetDevice(c0->device);
+      cudaEventRecord((cudaEvent_t)c0->ev_halo, (cudaStream_t)c0->comm_stream);
+      G->ov_active = 1;
+    }
+#else
+    if (G->overlap && !G->cb) G->ov_active = 1;   // the emulation runs everything in order, but splits the windows the same way
+#endif
   }
   for (int n = 0; n < nf; ++n) G->valid[fields[n]] = gh;
   return 0;
@@ -334,6 +398,8 @@ int group_exchange(Group* G, const int* fields, int nf) {
 // return how many ghost rows the kernel can also compute (its window extends that far).
 int group_need(Group* G, const Req* in, int n) {
   if (!G->seams) return 0;
+  for (int q = 0; q < n; ++q)
+    if (in[q].r > G->ov_r) G->ov_r = in[q].r;
   int stale[64], ns = 0;
   bool must = false;
   for (int q = 0; q < n; ++q)
@@ -361,6 +427,7 @@ int group_need(Group* G, const Req* in, int n) {
     }
     for (size_t q = 0; q < sizeof(live2d) / sizeof(int); ++q) add(live2d[q]);
     if (any3d) for (size_t q = 0; q < sizeof(live3d) / sizeof(int); ++q) add(live3d[q]);
+    if (G->ov_active) group_wait_halo(G);         // (a second exchange before the launch: keep the streams in order)
     if (group_exchange(G, stale, ns)) return 0;   // G->failed is set: the caller launches nothing
   }
   int e = G->ghost;
@@ -369,6 +436,37 @@ int group_need(Group* G, const Req* in, int n) {
     if (v < e) e = v;
   }
   return e < 0 ? 0 : e;
+}
+
+// ---- launch windows of the kernel that follows a group_need (pom_step.cu: EACH) ----------------
+// No exchange in flight: one part, the owned rows plus e ghost rows.  Exchange in flight: part 0 =
+// the rows that read no ghost row (everything at least ov_r rows away from a seam), then -- after
+// ev_halo -- part 1 = the band at the south seam, part 2 = the band at the north seam.  A cell gets
+// the same arithmetic whichever launch computes it, so the split does not change a bit.
+int group_parts(Group* G) { return (G->seams && G->ov_active) ? 3 : 1; }
+bool group_window(Group* G, const Ctx* c, int e, int part, int nparts, int* j0, int* j1) {
+  const int lo = c->jown0 > 1 ? c->jown0 - e : 1, hi = c->jown1 < c->g.jmg ? c->jown1 + e : c->g.jmg;
+  if (nparts == 1) { *j0 = lo; *j1 = hi; return true; }
+  const int a0 = has_s(c) ? c->jown0 + G->ov_r : lo, a1 = has_n(c) ? c->jown1 - G->ov_r : hi;
+  if (part == 0) { *j0 = a0; *j1 = a1; return a1 >= a0; }
+  if (part == 1) { *j0 = lo; *j1 = a0 - 1; return has_s(c) && a0 - 1 >= lo; }
+  *j0 = a1 + 1; *j1 = hi;
+  return has_n(c) && hi >= a1 + 1;
+}
+void group_wait_halo(Group* G) {
+#ifndef POMGPU_EMU
+  if (G->ov_active && G->c[0]->ev_halo)
+    for (int r = 0; r < G->n; ++r) {
+      if (r > 0 && G->c[r]->stream == G->c[0]->stream) continue;
+      cudaSetDevice(G->c[r]->device);
+      cudaStreamWaitEvent((cudaStream_t)G->c[r]->stream, (cudaEvent_t)G->c[0]->ev_halo, 0);
+    }
+#endif
+  G->ov_active = 0;
+}
+void group_launched(Group* G) {
+  if (G->ov_active) group_wait_halo(G);   // (nothing was launched on the bands: still order the streams)
+  G->ov_r = 0;
 }
 
 void group_produced(Group* G, int e, const int* out, int n) {

@@ -4,7 +4,7 @@
 
 namespace pom {
 
-constexpr int HALO_MAXF = 16;   // fields per pack kernel launch
+constexpr int HALO_MAXF = 64;   // fields per pack kernel launch (every live field fits: one pack / transfer / unpack per exchange)
 
 struct NcclId { char internal[128]; };
 
@@ -31,6 +31,12 @@ struct Group {
   double* hbuf[4]; size_t hbufcap[4];   // pinned host mirrors for the callback transport (CUDA build)
   void* ev_pack[16]; void* ev_copy[16];  // cross-stream ordering of in-process seams between devices
   int failed;            // a transport failed: ghost rows are stale, nothing is launched any more
+  // overlap of the exchange with interior compute: after the packs (compute stream) the transfer and
+  // the unpacks run on the communication stream; the kernel that asked for the rows is launched on
+  // the rows that read no ghost row first, then -- after ev_halo -- on the two seam bands
+  int overlap;           // transport supports it (NCCL, strips of one device); 0: everything on the compute stream
+  int ov_active;         // an exchange is in flight on the communication stream
+  int ov_r;              // largest j-radius the kernel about to be launched reads with
   long n_exchanges, n_fields_exchanged;
 };
 
@@ -43,5 +49,10 @@ int group_exchange(Group* G, const int* fields, int nf);
 int group_need(Group* G, const Req* in, int n);
 void group_produced(Group* G, int e, const int* out, int n);
 void group_swap(Group* G, int fa, int fb);
+// launch windows of the kernel about to run (pom_step.cu's EACH): 1 part, or interior + two seam bands
+int group_parts(Group* G);
+bool group_window(Group* G, const Ctx* c, int e, int part, int nparts, int* j0, int* j1);
+void group_wait_halo(Group* G);
+void group_launched(Group* G);
 
 }  // namespace pom

@@ -6,6 +6,9 @@
 #include "pom_core.h"
 #include "pom_tma.h"
 #include <cstdlib>
+#ifndef POMGPU_L2_PERSIST_DEFAULT_MB
+#define POMGPU_L2_PERSIST_DEFAULT_MB 0
+#endif
 
 namespace pom {
 
@@ -96,6 +99,16 @@ int dev_init(Ctx* c) {
   }
   if (cuda_fail(c, cudaSetDevice(c->device), "cudaSetDevice")) return 1;
   if (cuda_fail(c, cudaDeviceGetAttribute(&c->nsm, cudaDevAttrMultiProcessorCount, c->device), "device attribute")) return 1;
+  // L2 set-aside for the column scratch of the Thomas kernels (pom_tma.h: evict_last accesses only
+  // persist if the device reserves room for them); POMGPU_L2_PERSIST_MB overrides
+  {
+    int mx = 0;
+    cudaDeviceGetAttribute(&mx, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+    const char* e = getenv("POMGPU_L2_PERSIST_MB");
+    long want = e ? atol(e) * (1l << 20) : POMGPU_L2_PERSIST_DEFAULT_MB * (1l << 20);
+    if (want > mx) want = mx;
+    if (want >= 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)want);
+  }
   cudaStream_t s;
   if (cuda_fail(c, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
   c->stream = (void*)s;
@@ -225,6 +238,7 @@ Ctx* ctx_create(int im, int jm_global, int kb, int j_first, int j_last, int ghos
   if (im < 6 || jm_global < 6 || kb < 4 || kb > KMAX) return nullptr;   // most levels the column solvers hold
   Ctx* c = (Ctx*)calloc(1, sizeof(Ctx));
   c->no_tma = (getenv("POMGPU_NO_TMA") != nullptr);
+  c->no_pdl = (getenv("POMGPU_NO_PDL") != nullptr);
   c->device = device;
   c->jown0 = j_first; c->jown1 = j_last; c->ghost = ghost;
   int r0 = j_first - ghost; if (r0 < 1) r0 = 1;
@@ -268,6 +282,9 @@ void ctx_destroy(Ctx* c) {
   if (c->ev_swapped) cudaEventDestroy((cudaEvent_t)c->ev_swapped);
   if (c->ev_vel) cudaEventDestroy((cudaEvent_t)c->ev_vel);
   for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy((cudaEvent_t)c->ev[i]);
+  if (c->comm_stream) cudaStreamDestroy((cudaStream_t)c->comm_stream);
+  if (c->ev_packed) cudaEventDestroy((cudaEvent_t)c->ev_packed);
+  if (c->ev_halo) cudaEventDestroy((cudaEvent_t)c->ev_halo);
   cudaStreamDestroy((cudaStream_t)c->own_stream);
 #endif
   free(c);

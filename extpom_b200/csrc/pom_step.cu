@@ -21,6 +21,7 @@ int ctx_get_const(Ctx* c, const char* name, double* v);
 int prof_report(Ctx* c, char* buf, int n);
 // kernels
 void run_advct(Ctx*, int, int);
+void run_advct_smag(Ctx*, int, int);
 void run_baropg(Ctx*, int, int);
 void run_baropg_mcc(Ctx*, int, int);
 void run_smag(Ctx*, int, int);
@@ -70,7 +71,22 @@ static inline double* FP(Ctx* c, int f) {
 #define NEED(...) ([&]() { const Req rq[] = {__VA_ARGS__}; return group_need(G, rq, (int)(sizeof(rq) / sizeof(rq[0]))); }())
 #define MADE(e, ...) do { const int ou[] = {__VA_ARGS__}; group_produced(G, e, ou, (int)(sizeof(ou) / sizeof(ou[0]))); } while (0)
 // (after a failed halo exchange nothing is launched any more: the kernels would read stale ghost rows)
-#define EACH(stmt) for (int r_ = 0; r_ < G->n && !G->failed; ++r_) { Ctx* c = G->c[r_]; const int j0 = WLO(c, e), j1 = WHI(c, e); (void)j0; (void)j1; stmt; }
+// One launch per strip over its window [j0, j1] = owned rows + e ghost rows -- or, while a halo
+// exchange is in flight on the communication stream, three: the interior first, the seam bands once
+// the rows have arrived (pom_halo.cu: group_window).
+#define EACH(stmt) do {                                                                         \
+    const int np_ = group_parts(G);                                                             \
+    for (int part_ = 0; part_ < np_ && !G->failed; ++part_) {                                   \
+      if (part_ == 1) group_wait_halo(G);                                                       \
+      for (int r_ = 0; r_ < G->n; ++r_) {                                                       \
+        Ctx* c = G->c[r_];                                                                      \
+        int j0, j1;                                                                             \
+        if (!group_window(G, c, e, part_, np_, &j0, &j1)) continue;                             \
+        stmt;                                                                                   \
+      }                                                                                         \
+    }                                                                                           \
+    group_launched(G);                                                                          \
+  } while (0)
 // the scalars of strip 0 are the group's; error_status stays per strip (a CUDA failure or a blow-up
 // on strip r must survive until the driver reads it, advance.f:556-563)
 #define CSYNC() for (int r_ = 1; r_ < G->n; ++r_) { const int es_ = G->c[r_]->c.error_status; G->c[r_]->c = G->c[0]->c; G->c[r_]->c.error_status = es_; }
@@ -135,6 +151,14 @@ static void k_advct(Group* G) {
   int e = NEED({F_u, 1}, {F_v, 1}, {F_ub, 1}, {F_vb, 1}, {F_aam, 1}, {F_dt, 2});
   EACH(run_advct(c, j0, j1));
   MADE(e, F_advx, F_advy, F_adx2d, F_ady2d);
+}
+// advct + the Smagorinsky update of aam in one pass over u, v (what the step runs); baropg, which
+// the reference calls between the two (advance.f:110-120), touches neither
+static void k_advct_smag(Group* G) {
+  int e = NEED({F_u, 1}, {F_v, 1}, {F_ub, 1}, {F_vb, 1}, {F_aam, 1}, {F_dt, 2});
+  EACH(run_advct_smag(c, j0, j1));
+  MADE(e, F_advx, F_advy, F_adx2d, F_ady2d, F_s3c, F_aam2d);
+  group_swap(G, F_aam, F_s3c);
 }
 static void k_baropg(Group* G, int npg) {
   // (drhox/drhoy/aam/w are also read in place on the i=1,im columns, whose values never change)
@@ -364,7 +388,7 @@ static void k_realvertvl(Group* G) {
 
 // ---- advance.f:96-141 ---------------------------------------------------------------------
 static int lateral_viscosity(Group* G) {
-  if (G->c[0]->c.mode != 2) { k_advct(G); k_baropg(G, G->c[0]->c.npg); k_smag(G); }
+  if (G->c[0]->c.mode != 2) { k_advct_smag(G); k_baropg(G, G->c[0]->c.npg); }
   return 0;
 }
 // advance.f:144-202 (the vertical integrals were accumulated by the producers)

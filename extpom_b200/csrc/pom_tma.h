@@ -80,6 +80,24 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+// the same load with an L2 eviction-priority hint (createpolicy): the operand planes of the column
+// kernels are streamed once, so they are marked evict_first and leave the L2 to the column scratch
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
+}
+
 template <class F>
 struct SmemOp {
   const double* cur;   // stage of level k, at this thread's own point
@@ -180,8 +198,23 @@ template <int NVEC>
 struct ScratchCols {
   double* base;   // this thread's element of level 0 of vector 0
   int nt, kbs;    // threads per block, levels per vector
-  __device__ __forceinline__ void put(int v, int k, double x) { __stcg(base + (size_t)(v * kbs + k) * nt, x); }
-  __device__ __forceinline__ double get(int v, int k) const { return __ldcg(base + (size_t)(v * kbs + k) * nt); }
+  uint64_t pol;   // L2 evict_last policy
+  __device__ __forceinline__ void put(int v, int k, double x) {
+#ifdef POM_SCR_PLAIN
+    __stcg(base + (size_t)(v * kbs + k) * nt, x);
+#else
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(base + (size_t)(v * kbs + k) * nt), "d"(x), "l"(pol) : "memory");
+#endif
+  }
+  __device__ __forceinline__ double get(int v, int k) const {
+#ifdef POM_SCR_PLAIN
+    return __ldcg(base + (size_t)(v * kbs + k) * nt);
+#else
+    double x;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(x) : "l"(base + (size_t)(v * kbs + k) * nt), "l"(pol));
+    return x;
+#endif
+  }
 };
 
 // Persistent column kernel on the TMA ring: one block per resident slot, each looping over tiles
@@ -194,7 +227,7 @@ struct ScratchCols {
 template <class F>
 __global__ void __launch_bounds__(TILE_X * F::TY, F::MINB)
 tmacolkernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1, int j0, int j1,
-             int nbx, int ntiles, double* scratch, int kbs) {
+             int nbx, int ntiles, double* scratch, int kbs, unsigned long long* ringctl, int nslots) {
   constexpr int NF = F::NF, NS = F::NS, PL = tma_plane(F::BW, F::BH), NT = TILE_X * F::TY;
   extern __shared__ __align__(128) double pom_tsm[];
   double* ring = pom_tsm;
@@ -207,11 +240,34 @@ tmacolkernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int
   const int ntl = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this block
   const int total = ntl * nl;                                         // stage loads of this block
   const bool leader = (tid == 0);
+  // With one tile per block (gridDim.x == ntiles) the block borrows a scratch slot from a ring of
+  // free slot numbers: ringctl[0] counts the slots taken, ringctl[1] the slots given back, entry
+  // t % nslots of the ring holds (slot | generation t/nslots << 16).  At most nslots blocks are
+  // resident, so a free entry always exists; the generation tag makes a taker wait for the write of
+  // a giver that has claimed its entry but not stored it yet.  The persistent variant (gridDim.x <=
+  // nslots) simply uses slot blockIdx.x.
+  __shared__ int s_slot;
+  const bool borrowed = ((int)gridDim.x > nslots);
   if (leader) {
     for (int s = 0; s < NS; ++s) mbar_init(&bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    int slot = (int)blockIdx.x;
+    if (borrowed) {
+      const unsigned long long h = atomicAdd(&ringctl[0], 1ull);
+      volatile unsigned long long* ent = ringctl + 2 + (h % (unsigned long long)nslots);
+      unsigned long long e;
+      do { e = *ent; } while ((e >> 16) != h / (unsigned long long)nslots);
+      slot = (int)(e & 0xffffull);
+    }
+    s_slot = slot;
   }
   __syncthreads();
+  const int slot = s_slot;
+#ifdef POM_TMA_PLAIN
+  const uint64_t pol_ef = 0;
+#else
+  const uint64_t pol_ef = l2_policy_evict_first();
+#endif
   // stage load number q of this block = level k0 + q%nl of its tile q/nl
   auto issue = [&](int q) {
     const int n = q / nl, L = k0 + (q - n * nl), t = (int)blockIdx.x + n * (int)gridDim.x;
@@ -220,7 +276,13 @@ tmacolkernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int
     const int s = q % NS;
     mbar_expect_tx(&bar[s], (uint32_t)(NF * F::BW * F::BH * sizeof(double)));
 #pragma unroll
-    for (int m = 0; m < NF; ++m) tma_load_3d(ring + (s * NF + m) * PL, &maps.m[m], &bar[s], c0, c1, L - 1);
+    for (int m = 0; m < NF; ++m) {
+#ifdef POM_TMA_PLAIN
+      tma_load_3d(ring + (s * NF + m) * PL, &maps.m[m], &bar[s], c0, c1, L - 1);
+#else
+      tma_load_3d_hint(ring + (s * NF + m) * PL, &maps.m[m], &bar[s], c0, c1, L - 1, pol_ef);
+#endif
+    }
   };
   int qi = 0;                                                         // next load to issue (leader)
   if (leader)
@@ -228,7 +290,7 @@ tmacolkernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int
 #ifdef POM_COLS_LOCAL   // (experiment) the vectors in per-thread local memory, like the round-1 kernels
   LocalCols<F::NVEC> cm;
 #else
-  ScratchCols<F::NVEC> cm{scratch + (size_t)blockIdx.x * F::NVEC * kbs * NT + tid, NT, kbs};
+  ScratchCols<F::NVEC> cm{scratch + (size_t)slot * F::NVEC * kbs * NT + tid, NT, kbs, l2_policy_evict_last()};
 #endif
   for (int n = 0; n < ntl; ++n) {
     const int t = (int)blockIdx.x + n * (int)gridDim.x;
@@ -266,12 +328,20 @@ tmacolkernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int
     {
       constexpr int LPL = NT / 16;                                    // 128-byte lines per level of one vector
       const int nlines = F::NVEC * kbs * LPL;
-      const double* slot = scratch + (size_t)blockIdx.x * F::NVEC * kbs * NT;
+      const double* mine = scratch + (size_t)slot * F::NVEC * kbs * NT;
       for (int ln = tid; ln < nlines; ln += NT)
-        asm volatile("discard.global.L2 [%0], 128;" ::"l"(slot + (size_t)ln * 16) : "memory");
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(mine + (size_t)ln * 16) : "memory");
     }
     __syncthreads();
 #endif
+  }
+  __syncthreads();
+  if (borrowed && leader) {   // give the slot back: nobody of this block uses it any more
+    __threadfence();
+    const unsigned long long t = atomicAdd(&ringctl[1], 1ull);
+    volatile unsigned long long* ent = ringctl + 2 + (t % (unsigned long long)nslots);
+    *ent = (unsigned long long)slot | ((t / (unsigned long long)nslots) << 16);
+    __threadfence();
   }
 }
 
@@ -416,24 +486,37 @@ tile3kernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int 
     static_assert(F::BW % 2 == 0 && F::BW >= TILE_X + F::OHL + F::OHR + 1, "TMA box too narrow");
     static_assert(F::BH >= F::TY + F::OHB + F::OHT, "TMA box too short");
     const bool leader = (tx == 0 && ty == 0);
+    // Programmatic dependent launch: this grid may become resident while the previous kernel of the
+    // stream (the previous external substep) is still draining.  Everything that kernel does not
+    // write -- the operands F::is_static() names: metrics, depth, Coriolis, forcing -- is fetched
+    // BEFORE griddepcontrol.wait, the time-stepped fields after it.
     if (leader) {
       // two transactions: the first F::NFA fields are all that phases A and B read, so they start
       // while the operands only phase C needs are still in flight
       mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      const int c0 = n0 - shift, c1 = tj0 - 1 - f.g.joff - F::OHB;
       mbar_expect_tx(&bar[0], (uint32_t)(F::NFA * F::BW * F::BH * sizeof(double)));
-#pragma unroll
-      for (int n = 0; n < F::NFA; ++n) tma_load_3d(ring + n * PL, &maps.m[n], &bar[0], c0, c1, 0);
       mbar_expect_tx(&bar[1], (uint32_t)((NF - F::NFA) * F::BW * F::BH * sizeof(double)));
+      const int c0 = n0 - shift, c1 = tj0 - 1 - f.g.joff - F::OHB;
 #pragma unroll
-      for (int n = F::NFA; n < NF; ++n) tma_load_3d(ring + n * PL, &maps.m[n], &bar[1], c0, c1, 0);
+      for (int n = 0; n < NF; ++n)
+        if (F::is_static(n)) tma_load_3d(ring + n * PL, &maps.m[n], &bar[n < F::NFA ? 0 : 1], c0, c1, 0);
     }
-    f.pre(i, j, inside, st);        // plain loads of the point-wise operands overlap the TMA
+    f.pre(i, j, inside, st);        // plain loads of the static point-wise operands overlap the TMA
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (leader) {
+      const int c0 = n0 - shift, c1 = tj0 - 1 - f.g.joff - F::OHB;
+#pragma unroll
+      for (int n = 0; n < NF; ++n)
+        if (!F::is_static(n)) tma_load_3d(ring + n * PL, &maps.m[n], &bar[n < F::NFA ? 0 : 1], c0, c1, 0);
+    }
+    f.pre_dynamic(i, j, inside, st);
     __syncthreads();                // barrier init visible to every waiter
     mbar_wait(&bar[0], 0);
   } else {
     f.pre(i, j, inside, st);
+    f.pre_dynamic(i, j, inside, st);
   }
   const double* fld[NF];
   if (!TMA) f.fields(fld);
@@ -517,8 +600,17 @@ inline void launch_tile3(Ctx* c, const F& f, int i0, int i1, int j0, int j1) {
     cudaFuncSetAttribute(tile3kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_tma);
     cudaFuncSetAttribute(tile3kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_se);
   }
-  if (tma_ok) tile3kernel<F, true><<<gr, b, sm_tma, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
-  else tile3kernel<F, false><<<gr, b, sm_se, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
+  if (tma_ok) {
+    // launched with programmatic stream serialization: its blocks may start their static prologue
+    // while the previous kernel drains (they wait for it in griddepcontrol.wait)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = gr; cfg.blockDim = b; cfg.dynamicSmemBytes = sm_tma; cfg.stream = (cudaStream_t)c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = c->no_pdl ? 0 : 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, tile3kernel<F, true>, maps, f, i0, i1, j0, j1);
+  } else tile3kernel<F, false><<<gr, b, sm_se, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
   if (c->prof_on) prof_after(c);
 #endif
 }
@@ -559,16 +651,26 @@ inline void launch_tma_cols(Ctx* c, const F& f, int i0, int i1, int j0, int j1) 
       constexpr size_t smem = (size_t)(F::NS * F::NF * tma_plane(F::BW, F::BH)) * sizeof(double) + F::NS * 8;
       static DevOnce granted;
       static int resident[64];                       // blocks per SM of this kernel, per device
+      static unsigned long long* ringmem[64];        // free-slot ring of this kernel, per device (one tile per block mode)
       const int dv = c->device & 63;
       if (granted.need(c->device)) {
         cudaFuncSetAttribute(tmacolkernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int occ = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tmacolkernel<F>, NT, smem);
         resident[dv] = occ > 0 ? occ : 1;
+        // ring: [taken, given back, entries...]; initially every slot is free with generation 0
+        const int ns = c->nsm * resident[dv];
+        unsigned long long* h = (unsigned long long*)malloc((size_t)(ns + 2) * 8);
+        h[0] = 0; h[1] = (unsigned long long)ns;
+        for (int q = 0; q < ns; ++q) h[2 + q] = (unsigned long long)q;
+        if (cudaMalloc((void**)&ringmem[dv], (size_t)(ns + 2) * 8) == cudaSuccess)
+          cudaMemcpy(ringmem[dv], h, (size_t)(ns + 2) * 8, cudaMemcpyHostToDevice);
+        else ringmem[dv] = nullptr;
+        free(h);
       }
       const int slots = c->nsm * resident[dv], ntiles = nbx * nby;
-#ifdef POM_NONPERSIST   // (experiment, with POM_COLS_LOCAL) one tile per block
-      const int grid = ntiles;
+#ifdef POM_NONPERSIST   // one tile per block, scratch slots borrowed from the ring
+      const int grid = ringmem[dv] ? ntiles : (ntiles < slots ? ntiles : slots);
 #else
       const int grid = ntiles < slots ? ntiles : slots;
 #endif
@@ -579,7 +681,8 @@ inline void launch_tma_cols(Ctx* c, const F& f, int i0, int i1, int j0, int j1) 
         else { (void)cudaGetLastError(); tma_ok = false; }   // no room for the scratch: direct-load kernel below
       }
       if (tma_ok)
-        tmacolkernel<F><<<grid, b, smem, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1, nbx, ntiles, c->colscr, c->g.kb);
+        tmacolkernel<F><<<grid, b, smem, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1, nbx, ntiles, c->colscr, c->g.kb,
+                                                                    ringmem[dv], slots);
     }
   }
   if (!tma_ok) colkernel_g<F><<<dim3(nbx, nby), b, 0, (cudaStream_t)c->stream>>>(f, i0, i1, j0, j1);

@@ -89,7 +89,6 @@ const Member* find(const char* name) {
   return nullptr;
 }
 char* addr(const Member* m) { return (m && g_base[m->block]) ? g_base[m->block] + m->off : nullptr; }
-double* dptr(const char* name) { return (double*)addr(find(name)); }
 int iget(const char* name, int dflt) { const Member* m = find(name); char* a = addr(m); return (a && m->type != 'd') ? *(int*)a : dflt; }
 
 // the COMMON member a host pointer is the start of (array arguments of advq, advt1/2, dens, proft)
