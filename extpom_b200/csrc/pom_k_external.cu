@@ -129,9 +129,6 @@ struct ExtStepK : KBase {
   enum { D = OP_D, UA = OP_UA, VA = OP_VA, UAB = OP_UAB, VAB = OP_VAB, AAM2D = OP_AAM2D, DX = OP_DX, DY = OP_DY,
          ELB, EL, H, COR, EATM };
   static constexpr int NFA = 9;   // D..DY, ELB: everything phases A and B read
-  // operands no external substep writes (metrics, depth, Coriolis, atmospheric pressure, the viscosity
-  // integral of this internal step): the kernel may fetch them while the previous substep still runs
-  POM_HD static constexpr bool is_static(int n) { return n == AAM2D || n == DX || n == DY || n == H || n == COR || n == EATM; }
   enum { FUA, FVA, FXU, FYU, FXV, FYV, CURV };   // CURV: curv2d of the mode=2 block (solver.f:145-152)
   POM_HD void fields(const double** b) const {
     b[D] = p.d; b[UA] = p.ua; b[VA] = p.va; b[UAB] = p.uab; b[VAB] = p.vab; b[AAM2D] = p.aam2d; b[DX] = p.dx;
@@ -153,14 +150,8 @@ struct ExtStepK : KBase {
       POM_PREFETCH_L2(p.aru+o);
       POM_PREFETCH_L2(p.arv+o); POM_PREFETCH_L2(p.adx2d+o); POM_PREFETCH_L2(p.ady2d+o); POM_PREFETCH_L2(p.drx2d+o);
       POM_PREFETCH_L2(p.dry2d+o); POM_PREFETCH_L2(p.wusurf+o); POM_PREFETCH_L2(p.wubot+o); POM_PREFETCH_L2(p.wvsurf+o);
-      POM_PREFETCH_L2(p.wvbot+o); POM_PREFETCH_L2(p.dum+o); POM_PREFETCH_L2(p.dvm+o);
-    }
-  }
-  // the point-wise operands the previous substep wrote (only touched after griddepcontrol.wait)
-  POM_HD void pre_dynamic(int i, int j, bool inside, State&) const {
-    if (inside && ((i - 1) & 15) == 0) {
-      const int o = POM_I2(i,j);
-      POM_PREFETCH_L2(p.egf+o); POM_PREFETCH_L2(p.utf+o); POM_PREFETCH_L2(p.vtf+o);
+      POM_PREFETCH_L2(p.wvbot+o); POM_PREFETCH_L2(p.dum+o); POM_PREFETCH_L2(p.dvm+o); POM_PREFETCH_L2(p.egf+o);
+      POM_PREFETCH_L2(p.utf+o); POM_PREFETCH_L2(p.vtf+o);
       if (iext >= c.isplit - 1) POM_PREFETCH_L2(p.etf+o);
     }
   }
@@ -220,8 +211,7 @@ struct ExtStepK : KBase {
     // loads are in flight together instead of one L2 round trip after the other
     const double aru0=POM_LDG(&aru(i,j)), arv0=POM_LDG(&arv(i,j)), adx0=POM_LDG(&adx2d(i,j)), ady0=POM_LDG(&ady2d(i,j));
     const double drx0=POM_LDG(&drx2d(i,j)), dry0=POM_LDG(&dry2d(i,j)), wus0=POM_LDG(&wusurf(i,j));
-    // (mode 2 rewrites wubot, wvbot in the substeps that run advave: plain loads there, not the read-only path)
-    const double wub0=(M2 && s.m2) ? s.wub : (M2 ? wubot(i,j) : POM_LDG(&wubot(i,j))), wvb0=(M2 && s.m2) ? s.wvb : (M2 ? wvbot(i,j) : POM_LDG(&wvbot(i,j)));
+    const double wub0=(M2 && s.m2) ? s.wub : POM_LDG(&wubot(i,j)), wvb0=(M2 && s.m2) ? s.wvb : POM_LDG(&wvbot(i,j));
     const double wvs0=POM_LDG(&wvsurf(i,j)), dum0=POM_LDG(&dum(i,j)), dvm0=POM_LDG(&dvm(i,j));
     const double egf0=egf(i,j), utf0=utf(i,j), vtf0=vtf(i,j);
     const double etf0=(iext >= c.isplit-1) ? etf(i,j) : 0.;

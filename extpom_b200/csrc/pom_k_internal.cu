@@ -45,7 +45,6 @@
 #ifndef POM_PFD
 #define POM_PFD 2
 #endif
-
 namespace pom {
 
 // ---------------------------------------------------------------------------
@@ -527,7 +526,7 @@ struct ProfqK : KBase {
     }
     double up=st.ufkb, vp = 0.;
     emit(i,j,kb,up,0.,st.m);                                                  // uf(kb) (:1285), vf(kb)=0 (:1420)
-    // the eliminated coefficients come back from the column scratch (L2): fetch them one level ahead
+    // the eliminated coefficients come back from local memory (L2): fetch them one level ahead
     double e1n=cm.get(C_EE,kbm1), g1n=cm.get(C_GG,kbm1), e2n=cm.get(C_E2,kbm1), g2n=cm.get(C_G2,kbm1);
     for (int ki = kbm1; ki >= 2; --ki) {
       const double e1c=e1n, g1c=g1n, e2c=e2n, g2c=g2n;
@@ -1048,7 +1047,7 @@ struct ProftTSK : KBase {
     if (fuse) {
       // the new T,S of a level go straight into the filter (which writes uf, vf, tb, sb, rho)
       const double m = fsm(i,j);
-      // the eliminated coefficients come back from the column scratch (L2): fetch them one level ahead
+      // the eliminated coefficients come back from local memory (L2): fetch them one level ahead
       double eTn=cm.get(C_EET,kb-2), gTn=cm.get(C_GGT,kb-2), gSn=cm.get(C_GGS,kb-2), eSn=same ? eTn : cm.get(C_EES,kb-2);
       ts_level(*this, i, j, kbm1, fT, fS, m, fold, fnew, 1);
       for (int ki = kb-2; ki >= 1; --ki) {                              // :1673-1680
@@ -1442,12 +1441,8 @@ struct AdvProfUVK : KBase {
     fk=fk*m;                                                            // :1759
     A3(f,i,j,kbm1)=fk;
     if (VC) wvbot(i,j)=-tp*fk; else wubot(i,j)=-tp*fk;                  // :1774 / :1871
-    // the eliminated coefficients come back from the column scratch (L2): fetch them one level ahead
-    double en=cm.get(C_EE,kb-2), gn=cm.get(C_GG,kb-2);
     for (int ki = kb-2; ki >= 1; --ki) {                                // :1763-1770
-      const double e=en, gq=gn;
-      if (ki > 1) { en=cm.get(C_EE,ki-1); gn=cm.get(C_GG,ki-1); }
-      fk=(e*fk+gq)*m;
+      fk=(cm.get(C_EE,ki)*fk+cm.get(C_GG,ki))*m;
       A3(f,i,j,ki)=fk;
     }
   }
@@ -1461,66 +1456,37 @@ struct AdvProfUVK : KBase {
 struct UvFilterK : KBase {
   POM_KINFO("uv_filter", 6, 2, 2, 2)
   using KBase::KBase;
-  // TMA-fed column kernel: the downward sweep applies bcondorl(3) and the masks, accumulates the
-  // depth means and PARKS (uf+ub-2u, u) and (vf+vb-2v, v) of every level in the column scratch; the
-  // second sweep (`post`) reads them back from L2, so the six operands are read from HBM once
-  // (8 passes of traffic instead of 14).
-#ifndef POM_UVF_TY
-#define POM_UVF_TY 8
-#endif
-#ifndef POM_UVF_MINB
-#define POM_UVF_MINB 3
-#endif
-#ifndef POM_UVF_NS
-#define POM_UVF_NS 4
-#endif
-  static constexpr int TY = POM_UVF_TY, MINB = POM_UVF_MINB;
-  static constexpr int NF = 6, NS = POM_UVF_NS, OHL = 0, OHR = 0, OHB = 0, OHT = 0, BW = 34, BH = TY, NK = 0;
-  static constexpr bool UP = false;
-  static constexpr int NVEC = 4;
-  enum { UF, VF, UB, VB, U, V };
-  enum { C_PU, C_U, C_PV, C_V };
-  POM_HD void fields(const double** b) const { b[UF] = p.uf; b[VF] = p.vf; b[UB] = p.ub; b[VB] = p.vb; b[U] = p.u; b[V] = p.v; }
-  struct State { double mu, mv, su, sv, tu, tv; bool jin, iin, edge; };
-  POM_HD int k0() const { return 1; }
-  POM_HD int k1() const { return g.kb - 1; }
-  POM_HD int kl1() const { return g.kb - 1; }
-  template <class CM>
-  POM_HD void pre(int i, int j, State& s, CM&) const {
+  POM_HD void operator()(int i, int j) const {
     POM_DIMS;
-    s.jin = (j >= 2 && j <= jmm1); s.iin = (i >= 2 && i <= imm1);
-    s.edge = !(s.iin && s.jin) || i == 2 || j == 2;
-    s.mu=dum(i,j); s.mv=dvm(i,j);
-    s.su = 0.; s.sv = 0.; s.tu = 0.; s.tv = 0.;
-  }
-  template <class Op, class CM>
-  POM_HD void level(int i, int j, int k, State& s, CM& cm, const Op& o) const {
-    POM_DIMS;
-    double a=o(UF,0,0), b=o(VF,0,0);
-    if (s.edge) bcondorl3_edge(*this, i, j, k, a, b);                    // bounds_forcing.f:418-474
-    a=a*s.mu;                                                           // :481-482
-    b=b*s.mv;
-    // interior values are already masked (profu :1767): only the open-boundary columns change
-    if (s.edge) { uf(i,j,k)=a; vf(i,j,k)=b; }
-    const double u0=o(U,0,0), v0=o(V,0,0);
-    const double pu=a+o(UB,0,0)-2.*u0, pv=b+o(VB,0,0)-2.*v0;
-    s.su=s.su+pu*dz(k);                                                 // advance.f:474-475
-    s.sv=s.sv+pv*dz(k);                                                 // advance.f:495-496
-    s.tu=s.tu+a*dz(k);                                                  // next step's advance.f:367-369:
-    s.tv=s.tv+b*dz(k);                                                  // uf, vf become u, v (:512,514)
-    cm.put(C_PU,k,pu); cm.put(C_U,k,u0); cm.put(C_PV,k,pv); cm.put(C_V,k,v0);
-  }
-  template <class CM>
-  POM_HD void post(int i, int j, State& s, CM& cm) const {
-    POM_DIMS;
-    A2(p.s2c,i,j)=s.tu;
-    A2(p.s2d,i,j)=s.tv;
-    double pun=cm.get(C_PU,1), un_=cm.get(C_U,1), pvn=cm.get(C_PV,1), vn_=cm.get(C_V,1);
+    const bool jin = (j >= 2 && j <= jmm1), iin = (i >= 2 && i <= imm1);
+    const double mu=dum(i,j), mv=dvm(i,j);
+    double su = 0., sv = 0., tu = 0., tv = 0.;
+    double nu[KMAX], nv[KMAX];
+    const bool edge0 = !(iin && jin) || i == 2 || j == 2;
     for (int k = 1; k <= kbm1; ++k) {
-      const double pu=pun, u0=un_, pv=pvn, v0=vn_;
-      if (k < kbm1) { pun=cm.get(C_PU,k+1); un_=cm.get(C_U,k+1); pvn=cm.get(C_PV,k+1); vn_=cm.get(C_V,k+1); }
-      POM_STCS(&A3(p.s3a,i,j,k),u0+.5*smoth*(pu-s.su));                 // advance.f:483-485
-      POM_STCS(&A3(p.s3b,i,j,k),v0+.5*smoth*(pv-s.sv));                 // advance.f:504-506
+      PF3(p.uf,i,j,k+2); PF3(p.vf,i,j,k+2); PF3(p.ub,i,j,k+2); PF3(p.vb,i,j,k+2); PF3(p.u,i,j,k+2); PF3(p.v,i,j,k+2);
+      double a=uf(i,j,k), b=vf(i,j,k);
+      if (edge0) bcondorl3_edge(*this, i, j, k, a, b);                    // bounds_forcing.f:418-474
+      a=a*mu;                                                           // :481-482
+      b=b*mv;
+      if (edge0) { nu[k]=a; nv[k]=b; }
+      su=su+(a+ub(i,j,k)-2.*u(i,j,k))*dz(k);                            // advance.f:474-475
+      sv=sv+(b+vb(i,j,k)-2.*v(i,j,k))*dz(k);                            // advance.f:495-496
+      tu=tu+a*dz(k);                                                    // next step's advance.f:367-369:
+      tv=tv+b*dz(k);                                                    // uf, vf become u, v (:512,514)
+    }
+    A2(p.s2c,i,j)=tu;
+    A2(p.s2d,i,j)=tv;
+    const bool edge = !(iin && jin) || i == 2 || j == 2;
+    for (int k = 1; k <= kbm1; ++k) {
+      // away from the open boundaries the masked tendency is recomputed from uf,vf (one more
+      // read) instead of making the round trip through the per-thread arrays (a write + a read)
+      double a = edge ? nu[k] : uf(i,j,k)*mu, b = edge ? nv[k] : vf(i,j,k)*mv;
+      double un=u(i,j,k)+.5*smoth*(a+ub(i,j,k)-2.*u(i,j,k)-su);         // advance.f:483-485
+      double vn=v(i,j,k)+.5*smoth*(b+vb(i,j,k)-2.*v(i,j,k)-sv);         // advance.f:504-506
+      A3(p.s3a,i,j,k)=un;
+      A3(p.s3b,i,j,k)=vn;
+      if (edge) { uf(i,j,k)=a; vf(i,j,k)=b; }   // interior values are already masked (profu :1767)
     }
     A3(p.s3a,i,j,kb)=u(i,j,kb);                                         // advance.f:511,513
     A3(p.s3b,i,j,kb)=v(i,j,kb);
@@ -1726,7 +1692,7 @@ void run_advprof_v(Ctx* c, int j0, int j1) { launch_tma_cols(c, AdvProfUVK<true>
 void run_profu(Ctx* c, int j0, int j1) { launch_cols(c, ProfuK(c), ALLI, j0, j1); }
 void run_profv(Ctx* c, int j0, int j1) { launch_cols(c, ProfvK(c), ALLI, j0, j1); }
 // caller swaps u<->uf, v<->vf, ub<->s3a, vb<->s3b (advance.f:511-514)
-void run_uvfilter(Ctx* c, int j0, int j1) { launch_tma_cols(c, UvFilterK(c), ALLI, j0, j1); }
+void run_uvfilter(Ctx* c, int j0, int j1) { launch_cols(c, UvFilterK(c), ALLI, j0, j1); }
 void run_endstep2d(Ctx* c, int j0, int j1) { launch_cols(c, EndStep2dK(c), ALLI, j0, j1); }
 void run_realvertvl(Ctx* c, int j0, int j1) { launch_cols<RealvertvlK, POM_RV_MINB>(c, RealvertvlK(c), ALLI, j0, j1); }
 

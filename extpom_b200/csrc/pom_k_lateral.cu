@@ -20,16 +20,8 @@ namespace pom {
 // advct as a shared-memory tile kernel: per level every thread evaluates the five fluxes
 // of its own point once -- x-part xflux (X), x-part yflux (Y), y-part xflux (XP), y-part
 // yflux (YP), and the curvature products (CV, CU) -- and the tile interior differences them.
-// SMAG: the same pass also evaluates the Smagorinsky viscosity of lateral_viscosity (advance.f:
-// 122-136) from the u, v planes it has staged anyway, and its depth integral aam2d (:165).  advct
-// itself must see LAST step's aam (it runs before the update, advance.f:110-136) and neighbouring
-// tiles still read it, so the new viscosity goes to the scratch field s3c; the caller swaps.
-template <bool SMAG>
 struct AdvctK : KBase {
-  static const KInfo& info() {
-    static const KInfo k0{"advct", 5, 2, 5, 2}, k1{"advct_smagorinsky", 5, 3, 5, 3};
-    return SMAG ? k1 : k0;
-  }
+  POM_KINFO("advct", 5, 2, 5, 2)
   using KBase::KBase;
 #ifndef POM_TILE_TY
 #define POM_TILE_TY 16
@@ -52,7 +44,6 @@ struct AdvctK : KBase {
     double dtE, dtW, dtS, dtN, dtSW, dtWS, q4, dtc, dxc, dyc, qdx4, qdy4, dyd, dxd;
     RDiv ddx, ddy, ddy4, ddx4, ddxdy;   // hoisted divisors dx, dy, dy4, dx4, dx*dy
     double aru25, arv25, sx, sy;
-    double hdd, sa;                     // horcon*dx*dy, running aam2d (SMAG)
     bool fx, fy, fxp, fyp, interior, i3, j3;
   };
   POM_HD int k0() const { return 1; }
@@ -60,7 +51,7 @@ struct AdvctK : KBase {
   POM_HD void pre(int i, int j, bool inside, bool out, State& s) const {
     POM_DIMS;
     const int jlo = g.joff + 1, jhi = g.joff + g.jml;
-    s.sx = 0.; s.sy = 0.; s.sa = 0.; s.hdd = 0.;
+    s.sx = 0.; s.sy = 0.;
     // definition ranges (zero fill elsewhere, solver.f:213-216,319-321), limited to rows in memory
     s.fx  = inside && i >= 2 && i <= imm1 && j >= 2 && j <= jmm1;                 // :234-277
     s.fy  = inside && i >= 2 && i <= imm1 && j >= 2 && j <= jm && j - 1 >= jlo;   // :244-276
@@ -90,7 +81,6 @@ struct AdvctK : KBase {
       s.ddxdy.set(dx(i,j)*dy(i,j));
     }
     if (s.interior) { s.aru25 = aru(i,j)*.25; s.arv25 = arv(i,j)*.25; }
-    if (SMAG && s.interior) s.hdd=horcon*dx(i,j)*dy(i,j);                  // advance.f:124
   }
   // Branch-free: every thread evaluates every flux (operands outside the arrays read as zero, the
   // hoisted metrics of a thread outside a definition range are zero) and the definition-range
@@ -123,19 +113,7 @@ struct AdvctK : KBase {
     }
   }
   template <class Op>
-  POM_HD void combine(int i, int j, int k, State& s, const Op& o, const Tile2& tl) const {
-    if (SMAG) {
-      double a=o(AAM,0,0);                                                // edge columns keep their aam
-      if (s.interior) {                                                   // advance.f:122-136
-        const double a1=s.ddx(o(U,1,0)-o(U,0,0));
-        const double a2=s.ddy(o(V,0,1)-o(V,0,0));
-        const double a3=s.ddy(.25*(o(U,0,1)+o(U,1,1)-o(U,0,-1)-o(U,1,-1)))
-                       +s.ddx(.25*(o(V,1,0)+o(V,1,1)-o(V,-1,0)-o(V,-1,1)));
-        a=s.hdd*sqrt(a1*a1+a2*a2+.5*(a3*a3));
-      }
-      A3(p.s3c,i,j,k)=a;
-      s.sa=s.sa+a*dz(k);                                                  // advance.f:165
-    }
+  POM_HD void combine(int i, int j, int k, State& s, const Op&, const Tile2& tl) const {
     double ax=tl(X,0,0)-tl(X,-1,0)+tl(Y,0,1)-tl(Y,0,0);                      // :285-286
     const double cx=s.aru25*(tl(CV,0,0)+tl(CV,-1,0));                     // :293-300 (n_west==-1)
     ax=s.i3 ? ax-cx : ax;
@@ -155,7 +133,6 @@ struct AdvctK : KBase {
     advy(i,j,kb)=0.;
     adx2d(i,j)=s.sx;
     ady2d(i,j)=s.sy;
-    if (SMAG) { A3(p.s3c,i,j,kb)=aam(i,j,kb); aam2d(i,j)=s.sa; }
   }
 };
 
@@ -321,9 +298,7 @@ struct SmagK : KBase {
   }
 };
 
-void run_advct(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvctK<false>(c), 1, c->g.im, j0, j1); }
-// advct + Smagorinsky in one pass; the new aam is in s3c, the caller swaps
-void run_advct_smag(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvctK<true>(c), 1, c->g.im, j0, j1); }
+void run_advct(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvctK(c), 1, c->g.im, j0, j1); }
 // the caller swaps rho <-> rho2 afterwards
 #ifndef POM_RV_MINB
 #define POM_RV_MINB 4

@@ -6,9 +6,6 @@
 #include "pom_core.h"
 #include "pom_tma.h"
 #include <cstdlib>
-#ifndef POMGPU_L2_PERSIST_DEFAULT_MB
-#define POMGPU_L2_PERSIST_DEFAULT_MB 0
-#endif
 
 namespace pom {
 
@@ -99,16 +96,6 @@ int dev_init(Ctx* c) {
   }
   if (cuda_fail(c, cudaSetDevice(c->device), "cudaSetDevice")) return 1;
   if (cuda_fail(c, cudaDeviceGetAttribute(&c->nsm, cudaDevAttrMultiProcessorCount, c->device), "device attribute")) return 1;
-  // L2 set-aside for the column scratch of the Thomas kernels (pom_tma.h: evict_last accesses only
-  // persist if the device reserves room for them); POMGPU_L2_PERSIST_MB overrides
-  {
-    int mx = 0;
-    cudaDeviceGetAttribute(&mx, cudaDevAttrMaxPersistingL2CacheSize, c->device);
-    const char* e = getenv("POMGPU_L2_PERSIST_MB");
-    long want = e ? atol(e) * (1l << 20) : POMGPU_L2_PERSIST_DEFAULT_MB * (1l << 20);
-    if (want > mx) want = mx;
-    if (want >= 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)want);
-  }
   cudaStream_t s;
   if (cuda_fail(c, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
   c->stream = (void*)s;
@@ -238,7 +225,6 @@ Ctx* ctx_create(int im, int jm_global, int kb, int j_first, int j_last, int ghos
   if (im < 6 || jm_global < 6 || kb < 4 || kb > KMAX) return nullptr;   // most levels the column solvers hold
   Ctx* c = (Ctx*)calloc(1, sizeof(Ctx));
   c->no_tma = (getenv("POMGPU_NO_TMA") != nullptr);
-  c->no_pdl = (getenv("POMGPU_NO_PDL") != nullptr);
   c->device = device;
   c->jown0 = j_first; c->jown1 = j_last; c->ghost = ghost;
   int r0 = j_first - ghost; if (r0 < 1) r0 = 1;
@@ -274,7 +260,6 @@ void ctx_destroy(Ctx* c) {
   free(c->d_red); free(c->h_red);
 #else
   cudaFree(c->d_red); cudaFreeHost(c->h_red);
-  if (c->colscr) cudaFree(c->colscr);
   for (int f = 0; f < 256; ++f) if (c->shadow[f]) cudaFree(c->shadow[f]);
   free(c->tma_cache);
   if (c->copy_stream) cudaStreamDestroy((cudaStream_t)c->copy_stream);

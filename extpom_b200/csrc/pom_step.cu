@@ -21,7 +21,6 @@ int ctx_get_const(Ctx* c, const char* name, double* v);
 int prof_report(Ctx* c, char* buf, int n);
 // kernels
 void run_advct(Ctx*, int, int);
-void run_advct_smag(Ctx*, int, int);
 void run_baropg(Ctx*, int, int);
 void run_baropg_mcc(Ctx*, int, int);
 void run_smag(Ctx*, int, int);
@@ -151,14 +150,6 @@ static void k_advct(Group* G) {
   int e = NEED({F_u, 1}, {F_v, 1}, {F_ub, 1}, {F_vb, 1}, {F_aam, 1}, {F_dt, 2});
   EACH(run_advct(c, j0, j1));
   MADE(e, F_advx, F_advy, F_adx2d, F_ady2d);
-}
-// advct + the Smagorinsky update of aam in one pass over u, v (what the step runs); baropg, which
-// the reference calls between the two (advance.f:110-120), touches neither
-static void k_advct_smag(Group* G) {
-  int e = NEED({F_u, 1}, {F_v, 1}, {F_ub, 1}, {F_vb, 1}, {F_aam, 1}, {F_dt, 2});
-  EACH(run_advct_smag(c, j0, j1));
-  MADE(e, F_advx, F_advy, F_adx2d, F_ady2d, F_s3c, F_aam2d);
-  group_swap(G, F_aam, F_s3c);
 }
 static void k_baropg(Group* G, int npg) {
   // (drhox/drhoy/aam/w are also read in place on the i=1,im columns, whose values never change)
@@ -388,7 +379,7 @@ static void k_realvertvl(Group* G) {
 
 // ---- advance.f:96-141 ---------------------------------------------------------------------
 static int lateral_viscosity(Group* G) {
-  if (G->c[0]->c.mode != 2) { k_advct_smag(G); k_baropg(G, G->c[0]->c.npg); }
+  if (G->c[0]->c.mode != 2) { k_advct(G); k_baropg(G, G->c[0]->c.npg); k_smag(G); }
   return 0;
 }
 // advance.f:144-202 (the vertical integrals were accumulated by the producers)

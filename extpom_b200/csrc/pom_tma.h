@@ -80,24 +80,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-// the same load with an L2 eviction-priority hint (createpolicy): the operand planes of the column
-// kernels are streamed once, so they are marked evict_first and leave the L2 to the column scratch
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint64_t pol) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
-}
-
 template <class F>
 struct SmemOp {
   const double* cur;   // stage of level k, at this thread's own point
@@ -179,13 +161,11 @@ tmakernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1
 
 // ---- per-thread column vectors (the eliminated Thomas coefficients ee/gg) ---------------------
 // A column functor declares NVEC vectors of kb doubles per thread and uses them only through
-// put(v,k,x) / get(v,k).  LocalCols keeps them in per-thread local memory (host-emulated build and
-// the direct-load fallback).  ScratchCols keeps them in an explicit global scratch laid out
-// [block slot][vector][level][thread] (each warp access is one 256-byte run), read and written
-// through L2 only: the persistent kernel below re-uses a block's slot for every tile it processes
-// and DISCARDS the lines (discard.global.L2: dropped without write-back) once the upward sweep
-// has read them, so that the vectors make their round trip through L2 instead of HBM (measured,
-// scripts/probes/l2scratch_probe.cu: the write-backs of the local-memory variant disappear).
+// put(v,k,x) / get(v,k).  They live in per-thread local memory (dynamically indexed), so that the
+// scalars of the functor's State stay in registers.  (Parking them in an L2-resident global scratch
+// instead -- evict_last stores, discard.global.L2 after the upward sweep, a persisting-L2 set-aside --
+// does remove their HBM round trip, ncu: advu_profu 4.0 -> 2.9 GB, but not a microsecond of run time;
+// measured in round 2, DESIGN.md section 3, profiles/r2_colscratch_experiments.txt.)
 template <int NVEC>
 struct LocalCols {
   double a[NVEC][KMAX];
@@ -194,155 +174,60 @@ struct LocalCols {
 };
 
 #ifndef POMGPU_EMU
-template <int NVEC>
-struct ScratchCols {
-  double* base;   // this thread's element of level 0 of vector 0
-  int nt, kbs;    // threads per block, levels per vector
-  uint64_t pol;   // L2 evict_last policy
-  __device__ __forceinline__ void put(int v, int k, double x) {
-#ifdef POM_SCR_PLAIN
-    __stcg(base + (size_t)(v * kbs + k) * nt, x);
-#else
-    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(base + (size_t)(v * kbs + k) * nt), "d"(x), "l"(pol) : "memory");
-#endif
-  }
-  __device__ __forceinline__ double get(int v, int k) const {
-#ifdef POM_SCR_PLAIN
-    return __ldcg(base + (size_t)(v * kbs + k) * nt);
-#else
-    double x;
-    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(x) : "l"(base + (size_t)(v * kbs + k) * nt), "l"(pol));
-    return x;
-#endif
-  }
-};
-
-// Persistent column kernel on the TMA ring: one block per resident slot, each looping over tiles
-// (tile n of block b = b + n*gridDim.x).  The ring runs ACROSS tiles: while a tile's upward sweep
-// (`post`) runs, the first NS levels of the block's next tile are already in flight.  No flux
-// exchange between threads (thread tile = output tile), only the operand staging.  F provides NF,
-// NS, TY, OHL/OHR/OHB/OHT, BW, BH, UP, NK, NVEC, fields(), k0(), k1(), kl1(),
-// pre(i,j,State&,CM&), level(i,j,k,State&,CM&,op), post(i,j,State&,CM&) with CM = the column
-// vectors above.  `post` runs the upward sweeps (Thomas back-substitution) on the thread's own column.
+// Column kernel on the TMA ring: no flux exchange between threads (thread tile = output tile),
+// only the operand staging.  F provides NF, NS, TY, OHL/OHR/OHB/OHT, BW, BH, UP, NK, NVEC,
+// fields(), k0(), k1(), kl1(), pre(i,j,State&,CM&), level(i,j,k,State&,CM&,op),
+// post(i,j,State&,CM&) with CM = the column vectors above.
+// `post` runs the upward sweeps (Thomas back-substitution) on the thread's own column.
 template <class F>
 __global__ void __launch_bounds__(TILE_X * F::TY, F::MINB)
-tmacolkernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1, int j0, int j1,
-             int nbx, int ntiles, double* scratch, int kbs, unsigned long long* ringctl, int nslots) {
-  constexpr int NF = F::NF, NS = F::NS, PL = tma_plane(F::BW, F::BH), NT = TILE_X * F::TY;
+tmacolkernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1, int j0, int j1) {
+  constexpr int NF = F::NF, NS = F::NS, PL = tma_plane(F::BW, F::BH);
   extern __shared__ __align__(128) double pom_tsm[];
   double* ring = pom_tsm;
   uint64_t* bar = (uint64_t*)(ring + NS * NF * PL);
-  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TILE_X + tx;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ti0 = i0 + blockIdx.x * TILE_X, tj0 = j0 + blockIdx.y * F::TY;
+  const int i = ti0 + tx, j = tj0 + ty;
   static_assert(F::BW % 2 == 0 && F::BW >= TILE_X + F::OHL + F::OHR + 1, "TMA box too narrow");
   static_assert(F::BH >= F::TY + F::OHB + F::OHT, "TMA box too short");
+  const int n0 = ti0 - 1 - F::OHL, shift = n0 & 1;
+  const int c0 = n0 - shift, c1 = tj0 - 1 - f.g.joff - F::OHB;
   const int k0 = f.k0(), k1 = f.k1(), kl1 = f.kl1();
-  const int nl = kl1 - k0 + 1;                                        // levels staged per tile
-  const int ntl = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this block
-  const int total = ntl * nl;                                         // stage loads of this block
-  const bool leader = (tid == 0);
-  // With one tile per block (gridDim.x == ntiles) the block borrows a scratch slot from a ring of
-  // free slot numbers: ringctl[0] counts the slots taken, ringctl[1] the slots given back, entry
-  // t % nslots of the ring holds (slot | generation t/nslots << 16).  At most nslots blocks are
-  // resident, so a free entry always exists; the generation tag makes a taker wait for the write of
-  // a giver that has claimed its entry but not stored it yet.  The persistent variant (gridDim.x <=
-  // nslots) simply uses slot blockIdx.x.
-  __shared__ int s_slot;
-  const bool borrowed = ((int)gridDim.x > nslots);
+  const bool leader = (tx == 0 && ty == 0);
   if (leader) {
     for (int s = 0; s < NS; ++s) mbar_init(&bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    int slot = (int)blockIdx.x;
-    if (borrowed) {
-      const unsigned long long h = atomicAdd(&ringctl[0], 1ull);
-      volatile unsigned long long* ent = ringctl + 2 + (h % (unsigned long long)nslots);
-      unsigned long long e;
-      do { e = *ent; } while ((e >> 16) != h / (unsigned long long)nslots);
-      slot = (int)(e & 0xffffull);
-    }
-    s_slot = slot;
   }
   __syncthreads();
-  const int slot = s_slot;
-#ifdef POM_TMA_PLAIN
-  const uint64_t pol_ef = 0;
-#else
-  const uint64_t pol_ef = l2_policy_evict_first();
-#endif
-  // stage load number q of this block = level k0 + q%nl of its tile q/nl
-  auto issue = [&](int q) {
-    const int n = q / nl, L = k0 + (q - n * nl), t = (int)blockIdx.x + n * (int)gridDim.x;
-    const int by = t / nbx, bx = t - by * nbx;
-    const int n0 = i0 + bx * TILE_X - 1 - F::OHL, c0 = n0 - (n0 & 1), c1 = j0 + by * F::TY - 1 - f.g.joff - F::OHB;
-    const int s = q % NS;
+  auto issue = [&](int L) {
+    const int s = (L - k0) % NS;
     mbar_expect_tx(&bar[s], (uint32_t)(NF * F::BW * F::BH * sizeof(double)));
 #pragma unroll
-    for (int m = 0; m < NF; ++m) {
-#ifdef POM_TMA_PLAIN
-      tma_load_3d(ring + (s * NF + m) * PL, &maps.m[m], &bar[s], c0, c1, L - 1);
-#else
-      tma_load_3d_hint(ring + (s * NF + m) * PL, &maps.m[m], &bar[s], c0, c1, L - 1, pol_ef);
-#endif
-    }
+    for (int n = 0; n < NF; ++n)
+      tma_load_3d(ring + (s * NF + n) * PL, &maps.m[n], &bar[s], c0, c1, L - 1);
   };
-  int qi = 0;                                                         // next load to issue (leader)
   if (leader)
-    for (; qi < NS && qi < total; ++qi) issue(qi);
-#ifdef POM_COLS_LOCAL   // (experiment) the vectors in per-thread local memory, like the round-1 kernels
-  LocalCols<F::NVEC> cm;
-#else
-  ScratchCols<F::NVEC> cm{scratch + (size_t)slot * F::NVEC * kbs * NT + tid, NT, kbs, l2_policy_evict_last()};
-#endif
-  for (int n = 0; n < ntl; ++n) {
-    const int t = (int)blockIdx.x + n * (int)gridDim.x;
-    const int by = t / nbx, bx = t - by * nbx;
-    const int ti0 = i0 + bx * TILE_X, tj0 = j0 + by * F::TY;
-    const int i = ti0 + tx, j = tj0 + ty;
-    const int shift = (ti0 - 1 - F::OHL) & 1;
-    const bool active = (i <= i1 && j <= j1);
-    typename F::State st;     // scalars: registers
-    if (active) f.pre(i, j, st, cm);
-    const int own = (ty + F::OHB) * F::BW + tx + F::OHL + shift;
-    for (int k = k0; k <= k1; ++k) {
-      const int q0 = n * nl + (k - k0), s0 = q0 % NS;
-      mbar_wait(&bar[s0], (q0 / NS) & 1);
-      int s1 = s0;
-      if (F::UP && k + 1 <= kl1) {
-        s1 = (q0 + 1) % NS;
-        mbar_wait(&bar[s1], ((q0 + 1) / NS) & 1);
-      }
-      const SmemOp<F> op{ring + s0 * NF * PL + own, ring + s1 * NF * PL + own};
-      if (active) f.level(i, j, k, st, cm, op);
-      __syncthreads();
-      // everyone is done with the stage of level k (and, after the last computed level, with the
-      // stages that were only looked at through op.up): refill them with the loads NS ahead
-      if (leader) {
-        const int qfree = (k == k1) ? n * nl + nl - 1 : q0;
-        for (; qi <= qfree + NS && qi < total; ++qi) issue(qi);
-      }
+    for (int L = k0; L < k0 + NS && L <= kl1; ++L) issue(L);
+  const bool active = (i <= i1 && j <= j1);
+  typename F::State st;        // scalars: registers
+  LocalCols<F::NVEC> cm;       // per-thread column vectors (dynamically indexed: local memory)
+  if (active) f.pre(i, j, st, cm);
+  const int own = (ty + F::OHB) * F::BW + tx + F::OHL + shift;
+  for (int k = k0; k <= k1; ++k) {
+    const int q0 = k - k0, s0 = q0 % NS;
+    mbar_wait(&bar[s0], (q0 / NS) & 1);
+    int s1 = s0;
+    if (F::UP && k + 1 <= kl1) {
+      s1 = (q0 + 1) % NS;
+      mbar_wait(&bar[s1], ((q0 + 1) / NS) & 1);
     }
-    if (active) f.post(i, j, st, cm);
-    // drop this tile's column vectors from L2 without a write-back: every thread of the block has
-    // read its own (first barrier); nobody writes the next tile's before the lines are gone (second)
-#if !defined(POM_COLS_LOCAL) && !defined(POM_NO_DISCARD)
+    const SmemOp<F> op{ring + s0 * NF * PL + own, ring + s1 * NF * PL + own};
+    if (active) f.level(i, j, k, st, cm, op);
     __syncthreads();
-    {
-      constexpr int LPL = NT / 16;                                    // 128-byte lines per level of one vector
-      const int nlines = F::NVEC * kbs * LPL;
-      const double* mine = scratch + (size_t)slot * F::NVEC * kbs * NT;
-      for (int ln = tid; ln < nlines; ln += NT)
-        asm volatile("discard.global.L2 [%0], 128;" ::"l"(mine + (size_t)ln * 16) : "memory");
-    }
-    __syncthreads();
-#endif
+    if (leader && k + NS <= kl1) issue(k + NS);   // everyone is done with the stage of level k
   }
-  __syncthreads();
-  if (borrowed && leader) {   // give the slot back: nobody of this block uses it any more
-    __threadfence();
-    const unsigned long long t = atomicAdd(&ringctl[1], 1ull);
-    volatile unsigned long long* ent = ringctl + 2 + (t % (unsigned long long)nslots);
-    *ent = (unsigned long long)slot | ((t / (unsigned long long)nslots) << 16);
-    __threadfence();
-  }
+  if (active) f.post(i, j, st, cm);
 }
 
 template <class F>
@@ -486,37 +371,24 @@ tile3kernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int 
     static_assert(F::BW % 2 == 0 && F::BW >= TILE_X + F::OHL + F::OHR + 1, "TMA box too narrow");
     static_assert(F::BH >= F::TY + F::OHB + F::OHT, "TMA box too short");
     const bool leader = (tx == 0 && ty == 0);
-    // Programmatic dependent launch: this grid may become resident while the previous kernel of the
-    // stream (the previous external substep) is still draining.  Everything that kernel does not
-    // write -- the operands F::is_static() names: metrics, depth, Coriolis, forcing -- is fetched
-    // BEFORE griddepcontrol.wait, the time-stepped fields after it.
     if (leader) {
       // two transactions: the first F::NFA fields are all that phases A and B read, so they start
       // while the operands only phase C needs are still in flight
       mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const int c0 = n0 - shift, c1 = tj0 - 1 - f.g.joff - F::OHB;
       mbar_expect_tx(&bar[0], (uint32_t)(F::NFA * F::BW * F::BH * sizeof(double)));
+#pragma unroll
+      for (int n = 0; n < F::NFA; ++n) tma_load_3d(ring + n * PL, &maps.m[n], &bar[0], c0, c1, 0);
       mbar_expect_tx(&bar[1], (uint32_t)((NF - F::NFA) * F::BW * F::BH * sizeof(double)));
-      const int c0 = n0 - shift, c1 = tj0 - 1 - f.g.joff - F::OHB;
 #pragma unroll
-      for (int n = 0; n < NF; ++n)
-        if (F::is_static(n)) tma_load_3d(ring + n * PL, &maps.m[n], &bar[n < F::NFA ? 0 : 1], c0, c1, 0);
+      for (int n = F::NFA; n < NF; ++n) tma_load_3d(ring + n * PL, &maps.m[n], &bar[1], c0, c1, 0);
     }
-    f.pre(i, j, inside, st);        // plain loads of the static point-wise operands overlap the TMA
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (leader) {
-      const int c0 = n0 - shift, c1 = tj0 - 1 - f.g.joff - F::OHB;
-#pragma unroll
-      for (int n = 0; n < NF; ++n)
-        if (!F::is_static(n)) tma_load_3d(ring + n * PL, &maps.m[n], &bar[n < F::NFA ? 0 : 1], c0, c1, 0);
-    }
-    f.pre_dynamic(i, j, inside, st);
+    f.pre(i, j, inside, st);        // plain loads of the point-wise operands overlap the TMA
     __syncthreads();                // barrier init visible to every waiter
     mbar_wait(&bar[0], 0);
   } else {
     f.pre(i, j, inside, st);
-    f.pre_dynamic(i, j, inside, st);
   }
   const double* fld[NF];
   if (!TMA) f.fields(fld);
@@ -600,17 +472,8 @@ inline void launch_tile3(Ctx* c, const F& f, int i0, int i1, int j0, int j1) {
     cudaFuncSetAttribute(tile3kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_tma);
     cudaFuncSetAttribute(tile3kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_se);
   }
-  if (tma_ok) {
-    // launched with programmatic stream serialization: its blocks may start their static prologue
-    // while the previous kernel drains (they wait for it in griddepcontrol.wait)
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = gr; cfg.blockDim = b; cfg.dynamicSmemBytes = sm_tma; cfg.stream = (cudaStream_t)c->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = c->no_pdl ? 0 : 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, tile3kernel<F, true>, maps, f, i0, i1, j0, j1);
-  } else tile3kernel<F, false><<<gr, b, sm_se, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
+  if (tma_ok) tile3kernel<F, true><<<gr, b, sm_tma, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
+  else tile3kernel<F, false><<<gr, b, sm_se, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
   if (c->prof_on) prof_after(c);
 #endif
 }
@@ -637,9 +500,7 @@ inline void launch_tma_cols(Ctx* c, const F& f, int i0, int i1, int j0, int j1) 
     prof_before(c, &k, 8. * cols * ((k.r3 + k.w3) * (double)c->g.kb + (k.r2 + k.w2)));
   }
   cudaSetDevice(c->device);
-  constexpr int NT = TILE_X * F::TY;
-  const int nbx = (i1 - i0 + TILE_X) / TILE_X, nby = (j1 - j0 + F::TY) / F::TY;
-  dim3 b(TILE_X, F::TY);
+  dim3 b(TILE_X, F::TY), gr((i1 - i0 + TILE_X) / TILE_X, (j1 - j0 + F::TY) / F::TY);
   bool tma_ok = (c->g.im % 2 == 0) && !c->no_tma;
   if (tma_ok) {
     TmaMaps<F::NF> maps;
@@ -650,42 +511,11 @@ inline void launch_tma_cols(Ctx* c, const F& f, int i0, int i1, int j0, int j1) 
     if (tma_ok) {
       constexpr size_t smem = (size_t)(F::NS * F::NF * tma_plane(F::BW, F::BH)) * sizeof(double) + F::NS * 8;
       static DevOnce granted;
-      static int resident[64];                       // blocks per SM of this kernel, per device
-      static unsigned long long* ringmem[64];        // free-slot ring of this kernel, per device (one tile per block mode)
-      const int dv = c->device & 63;
-      if (granted.need(c->device)) {
-        cudaFuncSetAttribute(tmacolkernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tmacolkernel<F>, NT, smem);
-        resident[dv] = occ > 0 ? occ : 1;
-        // ring: [taken, given back, entries...]; initially every slot is free with generation 0
-        const int ns = c->nsm * resident[dv];
-        unsigned long long* h = (unsigned long long*)malloc((size_t)(ns + 2) * 8);
-        h[0] = 0; h[1] = (unsigned long long)ns;
-        for (int q = 0; q < ns; ++q) h[2 + q] = (unsigned long long)q;
-        if (cudaMalloc((void**)&ringmem[dv], (size_t)(ns + 2) * 8) == cudaSuccess)
-          cudaMemcpy(ringmem[dv], h, (size_t)(ns + 2) * 8, cudaMemcpyHostToDevice);
-        else ringmem[dv] = nullptr;
-        free(h);
-      }
-      const int slots = c->nsm * resident[dv], ntiles = nbx * nby;
-#ifdef POM_NONPERSIST   // one tile per block, scratch slots borrowed from the ring
-      const int grid = ringmem[dv] ? ntiles : (ntiles < slots ? ntiles : slots);
-#else
-      const int grid = ntiles < slots ? ntiles : slots;
-#endif
-      const size_t need = (size_t)slots * F::NVEC * c->g.kb * NT;
-      if (need > c->colscr_cap) {
-        if (c->colscr) { cudaStreamSynchronize((cudaStream_t)c->stream); cudaFree(c->colscr); c->colscr = nullptr; c->colscr_cap = 0; }
-        if (cudaMalloc((void**)&c->colscr, need * sizeof(double)) == cudaSuccess) c->colscr_cap = need;
-        else { (void)cudaGetLastError(); tma_ok = false; }   // no room for the scratch: direct-load kernel below
-      }
-      if (tma_ok)
-        tmacolkernel<F><<<grid, b, smem, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1, nbx, ntiles, c->colscr, c->g.kb,
-                                                                    ringmem[dv], slots);
+      if (granted.need(c->device)) cudaFuncSetAttribute(tmacolkernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      tmacolkernel<F><<<gr, b, smem, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
     }
   }
-  if (!tma_ok) colkernel_g<F><<<dim3(nbx, nby), b, 0, (cudaStream_t)c->stream>>>(f, i0, i1, j0, j1);
+  if (!tma_ok) colkernel_g<F><<<gr, b, 0, (cudaStream_t)c->stream>>>(f, i0, i1, j0, j1);
   if (c->prof_on) prof_after(c);
 #endif
 }
