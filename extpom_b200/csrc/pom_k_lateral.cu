@@ -305,6 +305,9 @@ void run_advct(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvctK(c), 1, c->g.
 #endif
 void run_baropg(Ctx* c, int j0, int j1) { launch_cols<BaropgK, POM_RV_MINB>(c, BaropgK(c), 1, c->g.im, j0, j1); }
 void run_baropg_mcc(Ctx* c, int j0, int j1) { launch_cols(c, BaropgMccK(c), 1, c->g.im, j0, j1); }
-void run_smag(Ctx* c, int j0, int j1) { launch_cols(c, SmagK(c), 1, c->g.im, j0, j1); }
+#ifndef POM_SMAG_MINB
+#define POM_SMAG_MINB 1
+#endif
+void run_smag(Ctx* c, int j0, int j1) { launch_cols<SmagK, POM_SMAG_MINB>(c, SmagK(c), 1, c->g.im, j0, j1); }
 
 }  // namespace pom

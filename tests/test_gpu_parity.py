@@ -307,3 +307,32 @@ def test_host_callback_transport_on_the_device_build():
         for i in range(nstep + 1, nstep + 12):
             groups[0].step(i)
     assert strips[0].getc("error_status") == 1
+
+
+def test_strips_on_two_devices_in_one_process():
+    """A group whose strips sit on DIFFERENT devices of one process: each strip launches on its own
+    stream, the seam copies are peer copies ordered by events (pack -> copy -> next pack), the
+    shared-memory opt-in of every kernel is granted per device.  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from extpom_b200 import strips as sp
+    from extpom_b200.pomgpu import PomGpu, PomGroup
+    from tests.common import F2, F3
+    dims, nstep, ghost = (96, 120, 16), 5, 4
+    _, whole = syn.seamount(*dims, lambda a, b, c: PomGpu(a, b, c), island=True)
+    owns = sp.partition(dims[1], 2)
+    strips = []
+    for dev, own in enumerate(owns):
+        fac = lambda a, b, c, strip=None, ghost=0, d=dev: PomGpu(a, b, c, device=d, strip=strip, ghost=ghost)
+        strips.append(sp.make_strip(*dims, own, ghost, fac, island=True)[1])
+    grp = PomGroup(strips)
+    sp.finish_init_group(None, grp)
+    for i in range(1, nstep + 1):
+        whole.step(i)
+        grp.step(i)
+    for n in F3 + F2:
+        a, b = whole.get(n), grp.gather(n)
+        if n in ("t", "tb", "s", "sb"):
+            a, b = a[:, :, :-1], b[:, :, :-1]
+        assert np.array_equal(a, b), n
