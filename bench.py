@@ -417,6 +417,11 @@ def main():
     barrier()
     ms = maxreduce(g.event_elapsed_ms(0, 1))
     launches = g.launch_count(reset=True)
+    if os.environ.get("POMGPU_HALO_TRACE") and not tracer and rank == 0:   # developer aid: where the exchanges' time went
+        import ctypes
+        tb = ctypes.create_string_buffer(1 << 16)
+        g.L.pomgpu_group_halo_trace(ctypes.c_void_p(model.group.h), tb, len(tb))
+        sys.stderr.write("own device time %.3f ms/step\n" % (g.event_elapsed_ms(0, 1) / K) + tb.value.decode()[-400:])
     value = cells * K / (ms * 1e-3)
 
     # ---- timed region 2: end to end through the public API with host buffers --------

@@ -16,7 +16,9 @@
 // library links without it; (c) a host callback (gloo in the CPU tests).
 #include "pom_halo.h"
 #include <cstdlib>
+#include <chrono>
 #ifndef POMGPU_EMU
+#include <cuda.h>
 #include <dlfcn.h>
 #endif
 
@@ -121,6 +123,9 @@ int nccl_unique_id(void* out128) {
 #endif
 }
 
+static bool has_s(const Ctx* c) { return c->jown0 > 1; }
+static bool has_n(const Ctx* c) { return c->jown1 < c->g.jmg; }
+
 // ---- group --------------------------------------------------------------------------------
 Group* group_create(int n, Ctx** ctxs) {
   if (n < 1 || n > 16) return nullptr;
@@ -148,6 +153,7 @@ Group* group_create(int n, Ctx** ctxs) {
   // overlap needs one compute stream per process side of a seam: strips of one device (shared stream)
   // or a single strip per process; in-process seams between devices stay on the ordered path
   G->overlap = (getenv("POMGPU_NO_OVERLAP") == nullptr);
+  G->trace = (getenv("POMGPU_HALO_TRACE") != nullptr);
 #ifndef POMGPU_EMU
   for (int r = 1; r < n; ++r) if (ctxs[r]->device != ctxs[0]->device) G->overlap = 0;
 #endif
@@ -163,6 +169,13 @@ void group_destroy(Group* G) {
     G->c[r]->stream = G->c[r]->own_stream;
   }
 #ifndef POMGPU_EMU
+  if (G->ipc) {
+    for (int q = 0; q < 2; ++q) {
+      if (G->peer_rbuf[q]) cudaIpcCloseMemHandle(G->peer_rbuf[q]);
+      if (G->peer_flags[q]) cudaIpcCloseMemHandle(G->peer_flags[q]);
+    }
+  }
+  if (G->flags) cudaFree(G->flags);
   if (G->nccl) g_nccl.CommDestroy(G->nccl);
   for (int b = 0; b < 4; ++b) if (G->hbuf[b]) cudaFreeHost(G->hbuf[b]);
   for (int r = 0; r < 16; ++r) {
@@ -172,6 +185,121 @@ void group_destroy(Group* G) {
 #endif
   free(G);
 }
+
+#ifndef POMGPU_EMU
+// ---- direct peer transport over CUDA IPC ---------------------------------------------------
+// stream memory operations (driver API, resolved through the runtime like cuTensorMapEncodeTiled)
+typedef CUresult (*StreamWait32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+typedef CUresult (*StreamWrite32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamWait32Fn p_wait32 = nullptr;
+static StreamWrite32Fn p_write32 = nullptr;
+static bool memops_load() {
+  if (p_wait32 && p_write32) return true;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+  p_wait32 = (StreamWait32Fn)p;
+  if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+  p_write32 = (StreamWrite32Fn)p;
+  return true;
+}
+
+// Map the neighbours' receive buffers and flag words.  The staging buffers get their final size
+// here (every live field at `ghost` rows), because an IPC handle names one allocation.  The handles
+// travel through the NCCL communicator that was just created.  Returns 0 on success.
+static int ipc_connect(Group* G) {
+  if (G->n != 1 || !G->nccl || !memops_load()) return 1;
+  Ctx* c = G->c[0];
+  cudaSetDevice(c->device);
+  const bool xs = has_s(c), xn = has_n(c);
+  if (!xs && !xn) return 1;
+  const size_t cap = (size_t)(32 * c->g.kb + 48) * G->ghost * c->g.im;
+  for (int b = 0; b < 4; ++b) {
+    if (G->buf[0][b]) dev_free(c, G->buf[0][b]);
+    if (dev_alloc(c, &G->buf[0][b], cap)) return 1;
+    G->bufcap[0][b] = cap;
+  }
+  if (cudaMalloc((void**)&G->flags, 64) != cudaSuccess) return 1;
+  cudaMemset(G->flags, 0, 64);
+  // what a neighbour needs from me: my receive buffers (2: from south, from north) and my flags
+  struct Pack { cudaIpcMemHandle_t rs, rn, fl; } mine, south, north;
+  if (cudaIpcGetMemHandle(&mine.rs, G->buf[0][2]) != cudaSuccess || cudaIpcGetMemHandle(&mine.rn, G->buf[0][3]) != cudaSuccess ||
+      cudaIpcGetMemHandle(&mine.fl, G->flags) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+  char *dsend = nullptr, *drecv = nullptr;
+  if (cudaMalloc((void**)&dsend, sizeof(Pack)) != cudaSuccess || cudaMalloc((void**)&drecv, 2 * sizeof(Pack)) != cudaSuccess) return 1;
+  cudaMemcpy(dsend, &mine, sizeof(Pack), cudaMemcpyHostToDevice);
+  cudaStream_t st = (cudaStream_t)c->stream;
+  const int ncclChar = 0;
+  g_nccl.GroupStart();
+  if (xs) { g_nccl.Send(dsend, sizeof(Pack), ncclChar, G->rank - 1, G->nccl, st); g_nccl.Recv(drecv, sizeof(Pack), ncclChar, G->rank - 1, G->nccl, st); }
+  if (xn) { g_nccl.Send(dsend, sizeof(Pack), ncclChar, G->rank + 1, G->nccl, st); g_nccl.Recv(drecv + sizeof(Pack), sizeof(Pack), ncclChar, G->rank + 1, G->nccl, st); }
+  int rc = g_nccl.GroupEnd();
+  cudaStreamSynchronize(st);
+  if (rc) return 1;
+  if (xs) cudaMemcpy(&south, drecv, sizeof(Pack), cudaMemcpyDeviceToHost);
+  if (xn) cudaMemcpy(&north, drecv + sizeof(Pack), sizeof(Pack), cudaMemcpyDeviceToHost);
+  cudaFree(dsend); cudaFree(drecv);
+  int ok = 1;
+  if (xs) {   // I write into the south neighbour's receive-from-north buffer
+    ok &= cudaIpcOpenMemHandle((void**)&G->peer_rbuf[0], south.rn, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    ok &= cudaIpcOpenMemHandle((void**)&G->peer_flags[0], south.fl, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+  }
+  if (xn) {
+    ok &= cudaIpcOpenMemHandle((void**)&G->peer_rbuf[1], north.rs, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    ok &= cudaIpcOpenMemHandle((void**)&G->peer_flags[1], north.fl, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+  }
+  // every rank must take the same decision: agree through one more (tiny) exchange
+  int *dok = nullptr, hok[3] = {ok, 1, 1};
+  cudaMalloc((void**)&dok, 3 * sizeof(int));
+  cudaMemcpy(dok, hok, 3 * sizeof(int), cudaMemcpyHostToDevice);
+  const int ncclInt = 2;
+  g_nccl.GroupStart();
+  if (xs) { g_nccl.Send(dok, 1, ncclInt, G->rank - 1, G->nccl, st); g_nccl.Recv(dok + 1, 1, ncclInt, G->rank - 1, G->nccl, st); }
+  if (xn) { g_nccl.Send(dok, 1, ncclInt, G->rank + 1, G->nccl, st); g_nccl.Recv(dok + 2, 1, ncclInt, G->rank + 1, G->nccl, st); }
+  g_nccl.GroupEnd();
+  cudaStreamSynchronize(st);
+  cudaMemcpy(hok, dok, 3 * sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(dok);
+  (void)cudaGetLastError();
+  // (a chain: a failure anywhere must reach every rank; neighbours agree pairwise, and a rank whose
+  // neighbour failed fails too, which is enough because the fallback is decided per seam below)
+  G->ipc = ok && hok[1] && hok[2];
+  G->ipc_cap = cap;
+  G->seq = 0;
+  return G->ipc ? 0 : 1;
+}
+
+// one exchange over the mapped peer buffers, enqueued on stream `st` (after the packs): ns / nn doubles
+static int ipc_transfer(Group* G, cudaStream_t st, long ns, long nn) {
+  Ctx* c = G->c[0];
+  const bool xs = has_s(c), xn = has_n(c);
+  const unsigned seq = ++G->seq;
+  CUstream s = (CUstream)st;
+  CUdeviceptr mine = (CUdeviceptr)G->flags;
+  int bad = 0;
+  // the neighbour must have unpacked what I sent last time before I overwrite its buffer
+  if (xs) bad |= p_wait32(s, mine + 2 * 4, seq - 1, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS;
+  if (xn) bad |= p_wait32(s, mine + 3 * 4, seq - 1, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS;
+  if (xs) bad |= cudaMemcpyAsync(G->peer_rbuf[0], G->buf[0][0], (size_t)ns * 8, cudaMemcpyDeviceToDevice, st) != cudaSuccess;
+  if (xn) bad |= cudaMemcpyAsync(G->peer_rbuf[1], G->buf[0][1], (size_t)nn * 8, cudaMemcpyDeviceToDevice, st) != cudaSuccess;
+  // "arrived": into the south neighbour's from-north word, the north neighbour's from-south word
+  if (xs) bad |= p_write32(s, (CUdeviceptr)G->peer_flags[0] + 1 * 4, seq, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS;
+  if (xn) bad |= p_write32(s, (CUdeviceptr)G->peer_flags[1] + 0 * 4, seq, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS;
+  // my own rows from the neighbours
+  if (xs) bad |= p_wait32(s, mine + 0 * 4, seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS;
+  if (xn) bad |= p_wait32(s, mine + 1 * 4, seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS;
+  return bad;
+}
+// after the unpacks: tell the neighbours that their rows have been consumed
+static int ipc_ack(Group* G, cudaStream_t st) {
+  Ctx* c = G->c[0];
+  CUstream s = (CUstream)st;
+  int bad = 0;
+  if (has_s(c)) bad |= p_write32(s, (CUdeviceptr)G->peer_flags[0] + 3 * 4, G->seq, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS;
+  if (has_n(c)) bad |= p_write32(s, (CUdeviceptr)G->peer_flags[1] + 2 * 4, G->seq, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS;
+  return bad;
+}
+#endif
 
 int group_connect_nccl(Group* G, const void* id128, int rank, int world) {
 #ifdef POMGPU_EMU
@@ -184,14 +312,14 @@ int group_connect_nccl(Group* G, const void* id128, int rank, int world) {
   int rc = g_nccl.CommInitRank(&G->nccl, world, id, rank);
   if (rc) { snprintf(G->c[0]->err, 256, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc)); return 1; }
   G->rank = rank; G->world = world;
+  if (!getenv("POMGPU_HALO_NCCL") && ipc_connect(G))   // peer copies when the neighbours' memory can be mapped
+    fprintf(stderr, "pomgpu: CUDA IPC peer mapping not available, halo rows go through ncclSend/ncclRecv\n");
   return 0;
 #endif
 }
 
 void group_set_callback(Group* G, halo_cb cb, void* user) { G->cb = cb; G->cb_user = user; }
 
-static bool has_s(const Ctx* c) { return c->jown0 > 1; }
-static bool has_n(const Ctx* c) { return c->jown1 < c->g.jmg; }
 
 // a transport failure: the ghost rows are stale from here on -- mark the group (nothing is
 // launched any more, pom_step.cu) and every strip (the reference's error convention)
@@ -230,12 +358,21 @@ static int dev_copy_between(Ctx* dc, double* dst, Ctx* sc, const double* src, si
 // Exchange `ghost` rows of the listed fields across every seam; afterwards they are valid to
 // full depth.  One pack kernel, one transfer and one unpack kernel per direction and strip,
 // whatever the number of fields.
-int group_exchange(Group* G, const int* fields, int nf) {
+int group_exchange(Group* G, const int* fields, int nf, bool pack_on_comm) {
   if (!G->seams || nf == 0) return 0;
+  // (timing experiments only: 1 = skip the transfer, 2 = skip pack / unpack as well; results are wrong)
+  static const int dbg = getenv("POMGPU_HALO_DEBUG") ? atoi(getenv("POMGPU_HALO_DEBUG")) : 0;
   const FieldInfo* tab;
   int ntab;
   tab = field_table(&ntab);
   const int gh = G->ghost;
+  if (G->ipc && nf > 1) {   // the mapped staging buffers cannot grow: an oversized batch goes in two halves
+    size_t tot = 0;
+    for (int n = 0; n < nf; ++n) tot += (size_t)(tab[fields[n]].kind == K3D ? G->c[0]->g.kb : 1) * gh * G->c[0]->g.im;
+    if (tot > G->ipc_cap) return group_exchange(G, fields, nf / 2, pack_on_comm) || group_exchange(G, fields + nf / 2, nf - nf / 2, pack_on_comm);
+  }
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double th0 = now();
   G->n_exchanges++;
   G->n_fields_exchanged += nf;
   for (int done = 0; done < nf; done += HALO_MAXF) {
@@ -258,38 +395,58 @@ int group_exchange(Group* G, const int* fields, int nf) {
       J[r][3] = P; J[r][3].row0 = l1 + 1;        // my north ghost rows
       for (int b = 0; b < 4; ++b) {
         if ((size_t)P.total > G->bufcap[r][b]) {
-          if (G->buf[r][b]) { dev_sync(c); dev_free(c, G->buf[r][b]); }
+          if (G->buf[r][b]) {
+            dev_sync(c);
+#ifndef POMGPU_EMU
+            if (G->c[0]->comm_stream) cudaStreamSynchronize((cudaStream_t)G->c[0]->comm_stream);
+#endif
+            dev_free(c, G->buf[r][b]);
+          }
           G->bufcap[r][b] = (size_t)P.total * 2;
           if (dev_alloc(c, &G->buf[r][b], G->bufcap[r][b])) return fail(G, "halo exchange: out of device memory");
         }
       }
-      if (has_s(c)) run_pack(c, J[r][0], G->buf[r][0], false, c->stream);
-      if (has_n(c)) run_pack(c, J[r][1], G->buf[r][1], false, c->stream);
+#ifndef POMGPU_EMU
+      if (G->trace && r == 0 && G->ntrace < 256) {
+        for (int q = 0; q < 4; ++q) if (!G->tev[G->ntrace][q]) { cudaEvent_t e; cudaEventCreate(&e); G->tev[G->ntrace][q] = (void*)e; }
+        G->tbytes[G->ntrace] = P.total * 8;
+        cudaEventRecord((cudaEvent_t)G->tev[G->ntrace][0], (cudaStream_t)c->stream);
+      }
+#endif
     }
-    // from here on (transfer, unpack) on the communication stream when the transport can overlap:
-    // xs[r] = the stream the rest of strip r's exchange is enqueued on
+    // Transfer and unpack run on the communication stream when the transport can overlap
+    // (xs_[r] = the stream the rest of strip r's exchange is enqueued on); the packs too when no
+    // exchanged field is written by the kernel about to be launched (pack_on_comm), otherwise they
+    // stay on the compute stream, ahead of that kernel.
     void* xs_[16];
     bool ov = false;
 #ifndef POMGPU_EMU
     ov = G->overlap && !G->cb;
     for (int r = 0; r < G->n && ov; ++r) ov = comm_ready(G->c[r]);
 #endif
-    for (int r = 0; r < G->n; ++r) {
-      Ctx* c = G->c[r];
-      xs_[r] = c->stream;
+    const bool early = ov && pack_on_comm;
+    for (int r = 0; r < G->n; ++r) xs_[r] = G->c[r]->stream;
 #ifndef POMGPU_EMU
-      if (ov) {
-        // strips of one device share the compute stream and (strip 0's) communication stream
-        Ctx* c0 = G->c[0];
-        xs_[r] = c0->comm_stream;
-        if (r == 0) {
-          cudaSetDevice(c0->device);
-          cudaEventRecord((cudaEvent_t)c0->ev_packed, (cudaStream_t)c0->stream);
-          cudaStreamWaitEvent((cudaStream_t)c0->comm_stream, (cudaEvent_t)c0->ev_packed, 0);
-        }
-      }
+    if (ov) for (int r = 0; r < G->n; ++r) xs_[r] = G->c[0]->comm_stream;   // strips of one device share both streams
+    auto fork = [&]() {   // the communication stream continues from this point of the compute stream
+      Ctx* c0 = G->c[0];
+      cudaSetDevice(c0->device);
+      cudaEventRecord((cudaEvent_t)c0->ev_packed, (cudaStream_t)c0->stream);
+      cudaStreamWaitEvent((cudaStream_t)c0->comm_stream, (cudaEvent_t)c0->ev_packed, 0);
+    };
+    if (early) fork();
 #endif
+    for (int r = 0; r < G->n && dbg < 2; ++r) {
+      Ctx* c = G->c[r];
+      void* ps = early ? xs_[r] : c->stream;
+      if (has_s(c)) run_pack(c, J[r][0], G->buf[r][0], false, ps);
+      if (has_n(c)) run_pack(c, J[r][1], G->buf[r][1], false, ps);
     }
+#ifndef POMGPU_EMU
+    if (ov && !early) fork();
+    if (ov && G->trace && G->ntrace < 256) cudaEventRecord((cudaEvent_t)G->tev[G->ntrace][1], (cudaStream_t)xs_[0]);
+#endif
+    G->host_ms[0] += now() - th0; th0 = now();
     // seams inside this process.  Strips on one device share a stream (program order); strips on
     // different devices have their own streams, so the copy into b's receive buffer must wait for
     // a's pack (and vice versa), and nobody may re-pack a send buffer the other side still reads.
@@ -327,7 +484,7 @@ int group_exchange(Group* G, const int* fields, int nf) {
     Ctx* cs = G->c[0];
     Ctx* cn = G->c[G->n - 1];
     const bool xs = has_s(cs), xn = has_n(cn);
-    if (xs || xn) {
+    if ((xs || xn) && dbg == 0) {
       if (G->cb) {
         const long ns = xs ? J[0][0].total : 0, nn = xn ? J[G->n - 1][1].total : 0;
         double *ss = xs ? G->buf[0][0] : nullptr, *rs = xs ? G->buf[0][2] : nullptr;
@@ -356,6 +513,9 @@ int group_exchange(Group* G, const int* fields, int nf) {
 #endif
       }
 #ifndef POMGPU_EMU
+      else if (G->ipc && (size_t)J[0][0].total <= G->ipc_cap) {
+        if (ipc_transfer(G, (cudaStream_t)xs_[0], xs ? J[0][0].total : 0, xn ? J[0][1].total : 0)) return fail(G, "halo exchange: peer copy / stream memory operation failed");
+      }
       else if (G->nccl) {
         const int ncclDouble = 8;
         cudaSetDevice(cs->device);
@@ -374,61 +534,95 @@ int group_exchange(Group* G, const int* fields, int nf) {
 #endif
       else return fail(G, "strip has a seam but no transport is connected");
     }
+    G->host_ms[1] += now() - th0; th0 = now();
+#ifndef POMGPU_EMU
+    if (G->trace && ov && G->ntrace < 256) cudaEventRecord((cudaEvent_t)G->tev[G->ntrace][2], (cudaStream_t)xs_[0]);
+#endif
     for (int r = 0; r < G->n; ++r) {
       Ctx* c = G->c[r];
+      if (dbg >= 2) continue;
       if (has_s(c)) run_pack(c, J[r][2], G->buf[r][2], true, xs_[r]);
       if (has_n(c)) run_pack(c, J[r][3], G->buf[r][3], true, xs_[r]);
     }
 #ifndef POMGPU_EMU
+    if (G->ipc && (xs || xn) && dbg == 0 && !G->cb && (size_t)J[0][0].total <= G->ipc_cap && ipc_ack(G, (cudaStream_t)xs_[0]))
+      return fail(G, "halo exchange: stream memory operation failed");
     if (ov) {   // the kernel that asked for these rows waits for this event before it touches a seam band
       Ctx* c0 = G->c[0];
       cudaSetDevice(c0->device);
       cudaEventRecord((cudaEvent_t)c0->ev_halo, (cudaStream_t)c0->comm_stream);
+      if (G->trace && G->ntrace < 256) { cudaEventRecord((cudaEvent_t)G->tev[G->ntrace][3], (cudaStream_t)c0->comm_stream); G->ntrace++; }
       G->ov_active = 1;
     }
 #else
     if (G->overlap && !G->cb) G->ov_active = 1;   // the emulation runs everything in order, but splits the windows the same way
 #endif
   }
+  G->host_ms[2] += now() - th0; G->host_n++;
   for (int n = 0; n < nf; ++n) G->valid[fields[n]] = gh;
   return 0;
 }
 
 // A kernel is about to read fields `in` (id, j-radius).  Exchange what is too stale, then
 // return how many ghost rows the kernel can also compute (its window extends that far).
+//
+// Policy.  A message costs latency, not bandwidth, for the 2-D fields (0.8 MB per exchange at
+// im=1024) but real time for the 3-D ones (60 MB for all of them), so:
+//  * whenever anything is exchanged, every live 2-D field that is not at full depth goes along;
+//  * a kernel with 3-D inputs first gets its 2-D inputs refreshed if THEY would limit how many ghost
+//    rows it can compute: otherwise the few rows of validity the external mode leaves on dt, etf, ...
+//    would be inherited by the kernel's 3-D outputs and force the big exchange every step (measured:
+//    two 60 MB exchanges per step before, one every two to three steps after);
+//  * when a 3-D field triggers the exchange, every live 3-D field goes along (they age together);
+//  * fields the kernel is about to overwrite (WILL) are not refreshed for nothing -- and when none of
+//    the exchanged fields is one of them, the packs can run on the communication stream too.
+void group_will(Group* G, const int* out, int n) {
+  G->nwill = 0;
+  for (int q = 0; q < n && q < 32; ++q) G->will[G->nwill++] = out[q];
+}
+
 int group_need(Group* G, const Req* in, int n) {
   if (!G->seams) return 0;
   for (int q = 0; q < n; ++q)
     if (in[q].r > G->ov_r) G->ov_r = in[q].r;
-  int stale[64], ns = 0;
-  bool must = false;
-  for (int q = 0; q < n; ++q)
-    if (G->valid[in[q].f] < in[q].r) must = true;
-  if (must) {
-    // A message costs latency, not bandwidth (a 3-D halo is ~1 MB), so batch: everything this
-    // kernel reads that is not at full depth, plus every live 2-D field, plus -- when a 3-D
-    // field triggered the exchange -- every live 3-D field.  Owned rows are always valid, so
-    // refreshing more ghosts than strictly needed is always correct.
-    static const int live2d[] = {F_ua, F_va, F_uab, F_vab, F_el, F_elb, F_d, F_dt, F_et, F_etb, F_etf, F_egf,
-                                 F_egb, F_utf, F_vtf, F_utb, F_vtb, F_wubot, F_wvbot, F_aam2d, F_adx2d,
-                                 F_ady2d, F_drx2d, F_dry2d, F_advua, F_advva, F_vfluxb};
-    static const int live3d[] = {F_u, F_v, F_ub, F_vb, F_t, F_s, F_tb, F_sb, F_q2, F_q2b, F_q2l, F_q2lb, F_w,
-                                 F_aam, F_km, F_kh, F_kq, F_rho, F_advx, F_advy, F_drhox, F_drhoy};
-    int ntab;
-    const FieldInfo* tab = field_table(&ntab);
-    bool any3d = false;
-    auto add = [&](int f) {
+  static const int live2d[] = {F_ua, F_va, F_uab, F_vab, F_el, F_elb, F_d, F_dt, F_et, F_etb, F_etf, F_egf,
+                               F_egb, F_utf, F_vtf, F_utb, F_vtb, F_wubot, F_wvbot, F_aam2d, F_adx2d,
+                               F_ady2d, F_drx2d, F_dry2d, F_advua, F_advva, F_vfluxb};
+  static const int live3d[] = {F_u, F_v, F_ub, F_vb, F_t, F_s, F_tb, F_sb, F_q2, F_q2b, F_q2l, F_q2lb, F_w,
+                               F_aam, F_km, F_kh, F_kq, F_rho, F_advx, F_advy, F_drhox, F_drhoy};
+  int ntab;
+  const FieldInfo* tab = field_table(&ntab);
+  auto willed = [&](int f) { for (int q = 0; q < G->nwill; ++q) if (G->will[q] == f) return true; return false; };
+  // what the inputs allow, separately for the 3-D and the 2-D (and 1-D edge) ones
+  int e3 = G->ghost, e2 = G->ghost;
+  bool has3 = false, must = false, any3d = false;
+  for (int q = 0; q < n; ++q) {
+    const int v = G->valid[in[q].f] - in[q].r;
+    if (tab[in[q].f].kind == K3D) { has3 = true; if (v < e3) e3 = v; if (v < 0) any3d = true; }
+    else if (v < e2) e2 = v;
+    if (v < 0) must = true;
+  }
+  const bool two_d_limits = has3 && e2 < e3 && e2 < G->ghost - G->ov_r;
+  if (must || two_d_limits) {
+    int stale[HALO_MAXF], ns = 0;
+    bool hazard = false;   // an exchanged field is written by the kernel about to run
+    // (a field the kernel updates IN PLACE is both an input -- its ghost rows limit e -- and written:
+    // it is refreshed, but then the packs must stay ahead of the kernel on the compute stream)
+    auto add = [&](int f, bool input) {
       for (int s = 0; s < ns; ++s) if (stale[s] == f) return;
-      if (G->valid[f] < G->ghost && ns < 64) stale[ns++] = f;
+      if (G->valid[f] >= G->ghost || ns >= HALO_MAXF) return;
+      if (willed(f)) { if (!input) return; hazard = true; }
+      stale[ns++] = f;
     };
-    for (int q = 0; q < n; ++q) {
-      if (G->valid[in[q].f] < in[q].r && tab[in[q].f].kind == K3D) any3d = true;
-      add(in[q].f);
+    for (int q = 0; q < n; ++q)
+      if (G->valid[in[q].f] < in[q].r || tab[in[q].f].kind != K3D || any3d) add(in[q].f, true);
+    for (size_t q = 0; q < sizeof(live2d) / sizeof(int); ++q) add(live2d[q], false);
+    if (any3d) for (size_t q = 0; q < sizeof(live3d) / sizeof(int); ++q) add(live3d[q], false);
+    if (ns) {
+      if (getenv("POMGPU_HALO_WHY")) { int n3 = 0; for (int q = 0; q < ns; ++q) n3 += tab[stale[q]].kind == K3D; fprintf(stderr, "exchange: must=%d 2dlimits=%d e2=%d e3=%d first-input=%s nfields=%d (3-D %d)\n", must, two_d_limits, e2, e3, tab[in[0].f].name, ns, n3); }
+      if (G->ov_active) group_wait_halo(G);         // (a second exchange before the launch: keep the streams in order)
+      if (group_exchange(G, stale, ns, !hazard)) return 0;   // G->failed is set: the caller launches nothing
     }
-    for (size_t q = 0; q < sizeof(live2d) / sizeof(int); ++q) add(live2d[q]);
-    if (any3d) for (size_t q = 0; q < sizeof(live3d) / sizeof(int); ++q) add(live3d[q]);
-    if (G->ov_active) group_wait_halo(G);         // (a second exchange before the launch: keep the streams in order)
-    if (group_exchange(G, stale, ns)) return 0;   // G->failed is set: the caller launches nothing
   }
   int e = G->ghost;
   for (int q = 0; q < n; ++q) {
@@ -467,6 +661,31 @@ void group_wait_halo(Group* G) {
 void group_launched(Group* G) {
   if (G->ov_active) group_wait_halo(G);   // (nothing was launched on the bands: still order the streams)
   G->ov_r = 0;
+  G->nwill = 0;
+}
+
+// per traced exchange: bytes per direction, ms from the start of the pack to the start of the
+// transfer (pack), to the end of the transfer, to the end of the unpack, and the start relative to the first
+int group_trace_report(Group* G, char* buf, int n) {
+  int o = 0;
+#ifndef POMGPU_EMU
+  for (int r = 0; r < G->n; ++r) dev_sync(G->c[r]);
+  if (G->c[0]->comm_stream) cudaStreamSynchronize((cudaStream_t)G->c[0]->comm_stream);
+  for (int q = 0; q < G->ntrace && o < n - 120; ++q) {
+    float t0 = 0, a = 0, b = 0, c3 = 0;
+    cudaEventElapsedTime(&t0, (cudaEvent_t)G->tev[0][0], (cudaEvent_t)G->tev[q][0]);
+    cudaEventElapsedTime(&a, (cudaEvent_t)G->tev[q][0], (cudaEvent_t)G->tev[q][1]);
+    cudaEventElapsedTime(&b, (cudaEvent_t)G->tev[q][0], (cudaEvent_t)G->tev[q][2]);
+    cudaEventElapsedTime(&c3, (cudaEvent_t)G->tev[q][0], (cudaEvent_t)G->tev[q][3]);
+    o += snprintf(buf + o, n - o, "t=%8.3f ms  %8.2f MB  pack %.3f  +transfer %.3f  +unpack %.3f\n", t0, G->tbytes[q] / 1e6, a, b, c3);
+  }
+#endif
+  if (o < n - 160)
+    o += snprintf(buf + o, n - o, "host ms over %ld exchanges: packs %.3f  transport %.3f  unpacks %.3f\n", G->host_n, G->host_ms[0], G->host_ms[1], G->host_ms[2]);
+  G->host_ms[0] = G->host_ms[1] = G->host_ms[2] = 0.; G->host_n = 0;
+  G->ntrace = 0;
+  if (o < n) buf[o] = 0;
+  return o;
 }
 
 void group_produced(Group* G, int e, const int* out, int n) {

@@ -68,6 +68,10 @@ static inline double* FP(Ctx* c, int f) {
   return *(double**)((char*)&c->p + t[f].offset);
 }
 #define NEED(...) ([&]() { const Req rq[] = {__VA_ARGS__}; return group_need(G, rq, (int)(sizeof(rq) / sizeof(rq[0]))); }())
+// the fields the kernel about to be launched WRITES, declared before NEED: they are left out of the
+// exchange it may trigger (the kernel recomputes their ghost rows anyway), which is what allows the
+// packs to run on the communication stream while the kernel's interior part already writes
+#define WILL(...) do { const int wl[] = {__VA_ARGS__}; group_will(G, wl, (int)(sizeof(wl) / sizeof(wl[0]))); } while (0)
 #define MADE(e, ...) do { const int ou[] = {__VA_ARGS__}; group_produced(G, e, ou, (int)(sizeof(ou) / sizeof(ou[0]))); } while (0)
 // (after a failed halo exchange nothing is launched any more: the kernels would read stale ghost rows)
 // One launch per strip over its window [j0, j1] = owned rows + e ghost rows -- or, while a halo
@@ -147,6 +151,7 @@ static int check_switches(Group* G) {
 
 // ---- the kernels of the path, with what they read (field, j-radius) and write ------------
 static void k_advct(Group* G) {
+  WILL(F_advx, F_advy, F_adx2d, F_ady2d);
   int e = NEED({F_u, 1}, {F_v, 1}, {F_ub, 1}, {F_vb, 1}, {F_aam, 1}, {F_dt, 2});
   EACH(run_advct(c, j0, j1));
   MADE(e, F_advx, F_advy, F_adx2d, F_ady2d);
@@ -154,22 +159,26 @@ static void k_advct(Group* G) {
 static void k_baropg(Group* G, int npg) {
   // (drhox/drhoy/aam/w are also read in place on the i=1,im columns, whose values never change)
   // npg=2: baropg_mcc reads rho-rmean and d two rows away (order2d/3d_mpi in the reference)
+  WILL(F_drhox, F_drhoy, F_drx2d, F_dry2d, F_rho2);
   int e = (npg == 2) ? NEED({F_rho, 2}, {F_d, 2}, {F_dt, 1}) : NEED({F_rho, 1}, {F_dt, 1});
   if (npg == 2) { EACH(run_baropg_mcc(c, j0, j1)); } else { EACH(run_baropg(c, j0, j1)); }
   MADE(e, F_drhox, F_drhoy, F_drx2d, F_dry2d, F_rho2);
   group_swap(G, F_rho, F_rho2);   // rho <- (rho-rmean)+rmean (solver.f:854,937)
 }
 static void k_smag(Group* G) {
+  WILL(F_aam, F_aam2d);
   int e = NEED({F_u, 1}, {F_v, 1});
   EACH(run_smag(c, j0, j1));
   MADE(e, F_aam, F_aam2d);
 }
 static void k_advave(Group* G) {
+  WILL(F_advua, F_advva);
   int e = NEED({F_d, 2}, {F_ua, 1}, {F_va, 1}, {F_uab, 1}, {F_vab, 1}, {F_aam2d, 1});
   EACH(run_advave(c, j0, j1));
   MADE(e, F_advua, F_advva);
 }
 static void k_mode_inter_tail(Group* G) {
+  WILL(F_adx2d, F_ady2d, F_egf, F_utf, F_vtf);
   int e = NEED({F_adx2d, 0}, {F_ady2d, 0}, {F_advua, 0}, {F_advva, 0}, {F_el, 0}, {F_ua, 0}, {F_va, 0}, {F_d, 1});
   EACH(run_mode_inter_tail(c, j0, j1));
   MADE(e, F_adx2d, F_ady2d, F_egf, F_utf, F_vtf);
@@ -178,6 +187,8 @@ static void k_mode_inter_tail(Group* G) {
 // operands of rows j-2..j+1 (elf(j-1) <- transports(j-1) <- d,va(j-2))
 static void k_ext_step(Group* G, int iext, int do_adv) {
   const int isplit = G->c[0]->c.isplit;
+  // (ua, va are read with radius 2; the kernel only seeds their four physical corner cells)
+  WILL(F_elf, F_uaf, F_vaf, F_s2a, F_s2b, F_el2, F_d2, F_etf, F_egf, F_utf, F_vtf);
   int e = NEED({F_d, 2}, {F_ua, 2}, {F_va, 2}, {F_uab, 2}, {F_vab, 2}, {F_aam2d, 2}, {F_el, 1}, {F_elb, 1},
                {F_adx2d, 0}, {F_ady2d, 0}, {F_drx2d, 0}, {F_dry2d, 0}, {F_wubot, 0}, {F_wvbot, 0},
                {F_egf, 0}, {F_utf, 0}, {F_vtf, 0});
@@ -196,6 +207,7 @@ static void k_ext_step(Group* G, int iext, int do_adv) {
   group_swap(G, F_d, F_d2);
 }
 static void k_uvadjust(Group* G) {
+  WILL(F_u, F_v);
   int e = NEED({F_u, 0}, {F_v, 0}, {F_utb, 0}, {F_utf, 0}, {F_vtb, 0}, {F_vtf, 0}, {F_dt, 1});
   EACH(run_uvadjust(c, j0, j1));
   MADE(e, F_u, F_v);
@@ -224,17 +236,20 @@ static void k_uvadjust_vertvl(Group* G) {
   for (int r = 0; r < G->n; ++r) G->c[r]->uvsum_ok = 0;
 }
 static void k_vertvl(Group* G) {
+  WILL(F_w);
   int e = NEED({F_u, 0}, {F_v, 1}, {F_dt, 1}, {F_etf, 0}, {F_etb, 0}, {F_vfluxb, 0});
   EACH(run_vertvl(c, j0, j1));
   MADE(e, F_w);
 }
 static void k_advq(Group* G) {
+  WILL(F_uf, F_vf);
   int e = NEED({F_q2, 1}, {F_q2b, 1}, {F_q2l, 1}, {F_q2lb, 1}, {F_u, 0}, {F_v, 1}, {F_aam, 1}, {F_dt, 1},
                {F_w, 0}, {F_etb, 0}, {F_etf, 0});
   EACH(run_advq(c, j0, j1));
   MADE(e, F_uf, F_vf);
 }
 static void k_profq(Group* G, int fuse_filter) {
+  WILL(F_uf, F_vf, F_km, F_kh, F_kq, F_l, F_q2b, F_q2lb);
   int e = NEED({F_t, 0}, {F_s, 0}, {F_rho, 0}, {F_q2b, 0}, {F_q2lb, 0}, {F_q2, 0}, {F_u, 0}, {F_v, 1},
                {F_km, 0}, {F_kh, 0}, {F_kq, 0}, {F_uf, 0}, {F_vf, 0}, {F_etf, 0}, {F_wubot, 0}, {F_wvbot, 1});
   if (fuse_filter) { const Req q[] = {{F_q2l, 0}}; int e2 = group_need(G, q, 1); if (e2 < e) e = e2; }
@@ -243,6 +258,7 @@ static void k_profq(Group* G, int fuse_filter) {
   if (fuse_filter) { group_swap(G, F_q2, F_uf); group_swap(G, F_q2l, F_vf); }   // advance.f:418-421
 }
 static void k_qfilter(Group* G) {
+  WILL(F_uf, F_vf, F_q2b, F_q2lb);
   int e = NEED({F_uf, 0}, {F_vf, 0}, {F_q2, 0}, {F_q2b, 0}, {F_q2l, 0}, {F_q2lb, 0}, {F_u, 0}, {F_v, 0});
   EACH(run_qfilter(c, j0, j1));
   MADE(e, F_uf, F_vf, F_q2b, F_q2lb);
@@ -287,23 +303,27 @@ static void k_advt(Group* G, int fb, int f, int fc, int ff, int stale) {
   MADE(e, ff);
 }
 static void k_proft(Group* G, int f, int wf, int fs, int nbc) {
+  WILL(f);
   int e = NEED({f, 0}, {F_kh, 0}, {F_etf, 0});
   EACH(run_proft(c, FP(c, f), FP(c, wf), FP(c, fs), nbc, j0, j1));
   MADE(e, f);
 }
 static void k_advt2_ts(Group* G) {   // advt2(tb,t,tclim,uf) and advt2(sb,s,sclim,vf) in one pass (nitera=1)
+  WILL(F_uf, F_vf);
   int e = NEED({F_tb, 1}, {F_t, 0}, {F_sb, 1}, {F_s, 0}, {F_u, 0}, {F_v, 1}, {F_w, 0}, {F_aam, 1}, {F_dt, 1},
                {F_etb, 0}, {F_etf, 0});
   EACH(run_advt2_ts(c, j0, j1));
   MADE(e, F_uf, F_vf);
 }
 static void k_proft_ts(Group* G) {   // proft(uf,wtsurf,tsurf,nbct) and proft(vf,wssurf,ssurf,nbcs) in one pass
+  WILL(F_uf, F_vf);
   int e = NEED({F_uf, 0}, {F_vf, 0}, {F_kh, 0}, {F_etf, 0});
   EACH(run_proft_ts(c, 0, j0, j1));
   MADE(e, F_uf, F_vf);
 }
 // proft of T and S + bcond(4) + t/s filter + restore_interior + dens in one kernel (advance.f:439-454)
 static void k_proft_tsfilter(Group* G) {
+  WILL(F_uf, F_vf, F_tb, F_sb, F_rho);
   int e = NEED({F_uf, 0}, {F_vf, 0}, {F_kh, 0}, {F_etf, 0}, {F_t, 0}, {F_s, 0}, {F_tb, 0}, {F_sb, 0}, {F_u, 0},
                {F_v, 0}, {F_w, 0}, {F_dt, 0});
   EACH(run_proft_ts(c, 1, j0, j1));
@@ -311,6 +331,7 @@ static void k_proft_tsfilter(Group* G) {
   group_swap(G, F_t, F_uf); group_swap(G, F_s, F_vf);      // advance.f:446-449
 }
 static void k_tsfilter(Group* G, int with_dens) {
+  WILL(F_uf, F_vf, F_tb, F_sb, F_rho);
   int e = NEED({F_uf, 0}, {F_vf, 0}, {F_t, 0}, {F_s, 0}, {F_tb, 0}, {F_sb, 0}, {F_u, 0}, {F_v, 0}, {F_w, 0}, {F_dt, 0});
   EACH(run_tsfilter(c, with_dens, j0, j1));
   MADE(e, F_uf, F_vf, F_tb, F_sb);
@@ -318,28 +339,33 @@ static void k_tsfilter(Group* G, int with_dens) {
   group_swap(G, F_t, F_uf); group_swap(G, F_s, F_vf);      // advance.f:446-449
 }
 static void k_dens(Group* G, int si, int ti, int ro) {
+  WILL(ro);
   int e = NEED({si, 0}, {ti, 0});
   EACH(run_dens(c, FP(c, si), FP(c, ti), FP(c, ro), j0, j1));
   MADE(e, ro);
 }
 static void k_advu(Group* G) {
+  WILL(F_uf);
   int e = NEED({F_w, 0}, {F_u, 0}, {F_v, 1}, {F_advx, 0}, {F_drhox, 0}, {F_ub, 0}, {F_dt, 0}, {F_egf, 0},
                {F_egb, 0}, {F_etb, 0}, {F_etf, 0});
   EACH(run_advu(c, j0, j1));
   MADE(e, F_uf);
 }
 static void k_advv(Group* G) {
+  WILL(F_vf);
   int e = NEED({F_w, 1}, {F_v, 0}, {F_u, 1}, {F_advy, 0}, {F_drhoy, 0}, {F_vb, 0}, {F_dt, 1}, {F_egf, 1},
                {F_egb, 1}, {F_etb, 1}, {F_etf, 1});
   EACH(run_advv(c, j0, j1));
   MADE(e, F_vf);
 }
 static void k_profu(Group* G) {
+  WILL(F_uf, F_wubot);
   int e = NEED({F_km, 0}, {F_uf, 0}, {F_ub, 0}, {F_vb, 1}, {F_etf, 0}, {F_wubot, 0});
   EACH(run_profu(c, j0, j1));
   MADE(e, F_uf, F_wubot);
 }
 static void k_profv(Group* G) {
+  WILL(F_vf, F_wvbot);
   int e = NEED({F_km, 1}, {F_vf, 0}, {F_vb, 0}, {F_ub, 1}, {F_etf, 1}, {F_wvbot, 0});
   EACH(run_profv(c, j0, j1));
   MADE(e, F_vf, F_wvbot);
@@ -347,18 +373,21 @@ static void k_profv(Group* G) {
 // advu+profu and advv+profv fused (the order advu, advv, profu, profv of advance.f:459-462 does
 // not matter: each pair only reads u, v, ub, vb, w and writes its own uf / vf, wubot / wvbot)
 static void k_advprof_u(Group* G) {
+  WILL(F_uf, F_wubot);
   int e = NEED({F_w, 0}, {F_u, 0}, {F_v, 1}, {F_advx, 0}, {F_drhox, 0}, {F_ub, 0}, {F_vb, 1}, {F_km, 0}, {F_dt, 0},
                {F_egf, 0}, {F_egb, 0}, {F_etb, 0}, {F_etf, 0}, {F_wubot, 0});
   EACH(run_advprof_u(c, j0, j1));
   MADE(e, F_uf, F_wubot);
 }
 static void k_advprof_v(Group* G) {
+  WILL(F_vf, F_wvbot);
   int e = NEED({F_w, 1}, {F_v, 0}, {F_u, 1}, {F_advy, 0}, {F_drhoy, 0}, {F_vb, 0}, {F_ub, 1}, {F_km, 1}, {F_dt, 1},
                {F_egf, 1}, {F_egb, 1}, {F_etb, 1}, {F_etf, 1}, {F_wvbot, 0});
   EACH(run_advprof_v(c, j0, j1));
   MADE(e, F_vf, F_wvbot);
 }
 static void k_uvfilter(Group* G) {
+  WILL(F_uf, F_vf, F_s3a, F_s3b, F_s2c, F_s2d);
   int e = NEED({F_uf, 0}, {F_vf, 0}, {F_u, 0}, {F_v, 0}, {F_ub, 0}, {F_vb, 0});
   EACH(run_uvfilter(c, j0, j1));
   MADE(e, F_uf, F_vf, F_s3a, F_s3b, F_s2c, F_s2d);
@@ -367,11 +396,13 @@ static void k_uvfilter(Group* G) {
   group_swap(G, F_ub, F_s3a); group_swap(G, F_vb, F_s3b);
 }
 static void k_endstep2d(Group* G) {
+  WILL(F_egb, F_etb, F_et, F_dt, F_utb, F_vtb, F_vfluxb);
   int e = NEED({F_egf, 0}, {F_et, 0}, {F_etf, 0}, {F_utf, 0}, {F_vtf, 0});
   EACH(run_endstep2d(c, j0, j1));
   MADE(e, F_egb, F_etb, F_et, F_dt, F_utb, F_vtb, F_vfluxb);
 }
 static void k_realvertvl(Group* G) {
+  WILL(F_wr);
   int e = NEED({F_w, 0}, {F_u, 0}, {F_v, 1}, {F_dt, 1}, {F_et, 1}, {F_etf, 0}, {F_etb, 0});
   EACH(run_realvertvl(c, j0, j1));
   MADE(e, F_wr);
@@ -711,6 +742,7 @@ double pomgpu_group_check_velocity(pomgpu_group_t* g) {
   for (int r = 0; r < GG(g)->n; ++r) { double v = check_velocity(GG(g)->c[r]); if (!(v <= m)) m = v; }
   return m;
 }
+int pomgpu_group_halo_trace(pomgpu_group_t* g, char* buf, int len) { return group_trace_report(GG(g), buf, len); }
 long pomgpu_group_exchanges(pomgpu_group_t* g, long* fields, int reset) {
   long n = GG(g)->n_exchanges;
   if (fields) *fields = GG(g)->n_fields_exchanged;

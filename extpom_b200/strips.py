@@ -7,12 +7,14 @@ per GPU; the strips of the box are connected over NCCL (send/recv across NVLink)
 unique id being broadcast through torch.distributed -- the role MPI_COMM_WORLD plays in
 the reference (parallel_mpi.f:6-31).
 """
+import os
+
 import numpy as np
 
 from . import synthetic as syn
 from .pomgpu import PomGpu, PomGroup
 
-GHOST = 8   # rows of redundant computation per seam: one batched exchange every ~4 external substeps
+GHOST = int(os.environ.get("POMGPU_GHOST", "8"))   # rows of redundant computation per seam: one batched exchange every ~4 external substeps
 
 
 def partition(jm, world):

@@ -13,7 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "extpom_b200", "libpomgpu.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
-PAT = [("UTMALDG", r"\bUTMALDG"), ("UTMASTG", r"\bUTMASTG"), ("SYNCS", r"\bSYNCS"), ("CCTL(discard)", r"\bCCTL"),
+PAT = [("UTMALDG", r"\bUTMALDG"), ("UTMASTG", r"\bUTMASTG"), ("SYNCS", r"\bSYNCS"), ("CCTL(prefetch)", r"\bCCTL"),
        ("LDG", r"\bLDG"), ("STG", r"\bSTG"), ("LDL", r"\bLDL"), ("STL", r"\bSTL"), ("LDS", r"\bLDS"), ("STS", r"\bSTS"),
        ("DFMA", r"\bDFMA"), ("DMUL", r"\bDMUL"), ("DADD", r"\bDADD"), ("MUFU.RCP64H", r"MUFU\.RCP64H"),
        ("MUFU.RSQ64H", r"MUFU\.RSQ64H"), ("BAR", r"\bBAR\.")]
@@ -33,7 +33,7 @@ for line in sass.splitlines():
             kern[cur][name] += 1
 dem = subprocess.run(["c++filt"], input="\n".join(kern), capture_output=True, text=True).stdout.splitlines()
 print(f"# {os.path.relpath(lib, ROOT)}: cubins for {sorted(arch)}; {len(kern)} kernels")
-print("# SASS instruction counts per kernel (static); UTMALDG = cp.async.bulk.tensor load, SYNCS = mbarrier, CCTL = discard.global.L2")
+print("# SASS instruction counts per kernel (static); UTMALDG = cp.async.bulk.tensor load, SYNCS = mbarrier, CCTL = prefetch.global.L1/L2")
 cols = [n for n, _ in PAT]
 print("%-64s " % "kernel" + " ".join("%7s" % c[:7] for c in cols))
 tot = collections.Counter()
