@@ -1493,6 +1493,137 @@ struct UvFilterK : KBase {
   }
 };
 
+// what is left of a window [jw0,jw1] around the parked kernel's rectangle [3,im-1] x [ja0,ja1]: whole rows
+// below and above it, and the columns i = 1, 2, im beside it, enumerated through a virtual (i, row) space
+struct UvFilterFrameK : UvFilterK {
+  int jw0, ja0, ja1, nlow, nfull, nin;
+  UvFilterFrameK(const Ctx* x, int w0, int w1, int a0, int a1) : UvFilterK(x), jw0(w0), ja0(a0), ja1(a1) {
+    nlow = a0 - w0; nfull = nlow + (w1 - a1); nin = a1 - a0 + 1;
+  }
+  POM_HD int rows() const { return nfull + (3 * nin + g.im - 1) / g.im; }
+  POM_HD bool cell(int vi, int vj, int& i, int& j) const {
+    if (vj <= nlow) { i = vi; j = jw0 + vj - 1; return true; }
+    if (vj <= nfull) { i = vi; j = ja1 + (vj - nlow); return true; }
+    const int t = (vj - nfull - 1) * g.im + (vi - 1);
+    if (t >= 3 * nin) return false;
+    const int col = t / nin;
+    i = col == 0 ? 1 : (col == 1 ? 2 : g.im); j = ja0 + t % nin;
+    return true;
+  }
+  POM_HD void operator()(int vi, int vj) const {
+    int i, j;
+    if (cell(vi, vj, i, j)) UvFilterK::operator()(i, j);
+  }
+#if !defined(POMGPU_EMU) && defined(__CUDACC__)
+  // One WARP per frame column, lane = level (k = lane+1, lane+33): every operand of the column is loaded at
+  // once instead of along a chain of 2 x (kb-1) dependent iterations; the depth sums are then accumulated in
+  // the reference's order k = 1, 2, ... from the lanes' products (shuffle broadcasts), so every bit is the
+  // two-sweep kernel's.  All frame columns are Orlanski/edge columns (edge0 of UvFilterK).
+  __device__ void warp_column(int i, int j, int lane) const {
+    POM_DIMS;
+    const double mu=dum(i,j), mv=dvm(i,j);
+    double a[2], b[2], uo[2], vo[2], xu[2], xv[2], pu[2], pv[2], qu[2], qv[2];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const int k = lane + 1 + 32 * sl;
+      a[sl] = b[sl] = uo[sl] = vo[sl] = xu[sl] = xv[sl] = pu[sl] = pv[sl] = qu[sl] = qv[sl] = 0.;
+      if (k <= kbm1) {
+        double aa=uf(i,j,k), bb=vf(i,j,k);
+        bcondorl3_edge(*this, i, j, k, aa, bb);                           // bounds_forcing.f:418-474
+        aa=aa*mu;                                                         // :481-482
+        bb=bb*mv;
+        const double uu=u(i,j,k), vv=v(i,j,k);
+        const double x=aa+ub(i,j,k)-2.*uu, y=bb+vb(i,j,k)-2.*vv;
+        a[sl]=aa; b[sl]=bb; uo[sl]=uu; vo[sl]=vv; xu[sl]=x; xv[sl]=y;
+        pu[sl]=x*dz(k); pv[sl]=y*dz(k); qu[sl]=aa*dz(k); qv[sl]=bb*dz(k);
+      }
+    }
+    double su = 0., sv = 0., tu = 0., tv = 0.;
+    for (int k = 1; k <= kbm1; ++k) {                                     // advance.f:474-475, 495-496
+      const int src = (k - 1) & 31;
+      const bool hi = k > 32;
+      su=su+__shfl_sync(0xffffffffu, hi ? pu[1] : pu[0], src);
+      sv=sv+__shfl_sync(0xffffffffu, hi ? pv[1] : pv[0], src);
+      tu=tu+__shfl_sync(0xffffffffu, hi ? qu[1] : qu[0], src);
+      tv=tv+__shfl_sync(0xffffffffu, hi ? qv[1] : qv[0], src);
+    }
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const int k = lane + 1 + 32 * sl;
+      if (k <= kbm1) {
+        A3(p.s3a,i,j,k)=uo[sl]+.5*smoth*(xu[sl]-su);                      // advance.f:483-485
+        A3(p.s3b,i,j,k)=vo[sl]+.5*smoth*(xv[sl]-sv);                      // advance.f:504-506
+        uf(i,j,k)=a[sl]; vf(i,j,k)=b[sl];
+      }
+    }
+    if (lane == 0) {
+      A2(p.s2c,i,j)=tu; A2(p.s2d,i,j)=tv;
+      A3(p.s3a,i,j,kb)=u(i,j,kb);                                         // advance.f:511,513
+      A3(p.s3b,i,j,kb)=v(i,j,kb);
+    }
+  }
+#endif
+};
+
+// The interior columns of the same filter (3<=i<=im-1, 3<=j<=jm-1: no Orlanski point, uf, vf already
+// masked by profu/profv) with the six operands read ONCE: sweep 1 parks (uf*mask+ub-2u, u) of every level
+// in shared memory while it forms the depth sums, sweep 2 finishes from the parked values
+// (pom_tma.h: tmaparkkernel; one component per tile).  Same expressions in the same order as UvFilterK.  The
+// frame around the rectangle is worked off by the side warps of the same launch.
+struct UvFilterParkK : UvFilterFrameK {
+  POM_KINFO("uv_filter", 6, 2, 2, 2)
+  using UvFilterFrameK::UvFilterFrameK;
+  static constexpr int NC = 2, NF = 3, NP = 2;
+  static constexpr int NSIDE = 2;   // warps per block that work the frame off while the rectangle streams
+  double columns(int i0, int i1, int j0, int j1) const {
+    return (double)(i1 - i0 + 1) * (j1 - j0 + 1) + (double)nfull * g.im + 3. * nin;
+  }
+#if !defined(POMGPU_EMU) && defined(__CUDACC__)
+  __device__ void side(int w, int nw, int lane) const {
+    const int nv = rows() * g.im;
+    for (int q = w; q < nv; q += nw) {
+      int i, j;
+      if (cell(q % g.im + 1, q / g.im + 1, i, j)) warp_column(i, j, lane);
+    }
+  }
+#endif
+  void side_host() const {
+    const int nr = rows();
+    for (int vj = 1; vj <= nr; ++vj)
+      for (int vi = 1; vi <= g.im; ++vi) UvFilterFrameK::operator()(vi, vj);
+  }
+  POM_HD void fields(int comp, const double** b) const {
+    b[0] = comp ? p.vf : p.uf; b[1] = comp ? p.vb : p.ub; b[2] = comp ? p.v : p.u;
+  }
+  struct State { double m, su, tu; };
+  static constexpr int NPL = 2;   // the column's mask and its bottom-level velocity
+  POM_HD void preload(int comp, int i, int j, double* pl) const {
+    const int kb = g.kb;
+    pl[0] = comp ? dvm(i,j) : dum(i,j);
+    pl[1] = comp ? v(i,j,kb) : u(i,j,kb);
+  }
+  POM_HD void pre(int, int, int, State& s, const double* pl) const { s.m = pl[0]; s.su = 0.; s.tu = 0.; }
+  POM_HD const double* ktab() const { return p.dz; }
+  POM_HD void sweep1(int, int, int, int, State& s, const double* f, double* pk, double dzk) const {
+    const double a=f[0]*s.m;                                            // bounds_forcing.f:481-482
+    const double x=a+f[1]-2.*f[2];
+    s.su=s.su+x*dzk;                                                    // advance.f:474-475 / 495-496
+    s.tu=s.tu+a*dzk;                                                    // next step's advance.f:367-369
+    pk[0]=x; pk[1]=f[2];
+  }
+  POM_HD void mid(int comp, int i, int j, State& s) const {
+    if (comp) A2(p.s2d,i,j)=s.tu; else A2(p.s2c,i,j)=s.tu;
+  }
+  POM_HD void sweep2(int comp, int i, int j, int k, State& s, const double* pk) const {
+    const double un=pk[1]+.5*smoth*(pk[0]-s.su);                        // advance.f:483-485 / 504-506
+    if (comp) A3(p.s3b,i,j,k)=un; else A3(p.s3a,i,j,k)=un;
+  }
+  POM_HD void fin(int comp, int i, int j, State&, const double* pl) const {
+    const int kb = g.kb;
+    if (comp) A3(p.s3b,i,j,kb)=pl[1]; else A3(p.s3a,i,j,kb)=pl[1];          // advance.f:511,513
+  }
+};
+
 // ---------------------------------------------------------------------------
 // advance.f:525-531: end-of-step 2-D rotations
 struct EndStep2dK : KBase {
@@ -1692,7 +1823,16 @@ void run_advprof_v(Ctx* c, int j0, int j1) { launch_tma_cols(c, AdvProfUVK<true>
 void run_profu(Ctx* c, int j0, int j1) { launch_cols(c, ProfuK(c), ALLI, j0, j1); }
 void run_profv(Ctx* c, int j0, int j1) { launch_cols(c, ProfvK(c), ALLI, j0, j1); }
 // caller swaps u<->uf, v<->vf, ub<->s3a, vb<->s3b (advance.f:511-514)
-void run_uvfilter(Ctx* c, int j0, int j1) { launch_cols(c, UvFilterK(c), ALLI, j0, j1); }
+void run_uvfilter(Ctx* c, int j0, int j1) {
+  // interior rectangle streamed once through the parked kernel, the frame around it (Orlanski rows / columns
+  // and their neighbours) on its side warps; layouts the TMA cannot address keep the two-sweep kernel
+  const int ja0 = j0 > 3 ? j0 : 3, ja1 = j1 < c->g.jmg - 1 ? j1 : c->g.jmg - 1;
+#ifndef POM_UVF_TWOSWEEP
+  if (c->g.im >= 4 && ja1 >= ja0 && c->g.kb - 1 <= KMAX &&
+      launch_tma_park(c, UvFilterParkK(c, j0, j1, ja0, ja1), 3, c->g.im - 1, ja0, ja1)) return;
+#endif
+  launch_cols(c, UvFilterK(c), ALLI, j0, j1);
+}
 void run_endstep2d(Ctx* c, int j0, int j1) { launch_cols(c, EndStep2dK(c), ALLI, j0, j1); }
 void run_realvertvl(Ctx* c, int j0, int j1) { launch_cols<RealvertvlK, POM_RV_MINB>(c, RealvertvlK(c), ALLI, j0, j1); }
 

@@ -298,6 +298,57 @@ struct SmagK : KBase {
   }
 };
 
+// The same arithmetic on the TMA ring (pom_tma.h: tmacolkernel): u, v of every level are staged with one
+// point of halo all around, two or more levels ahead, instead of ten dependent plain loads per cell.
+#ifndef POM_SMAG_TY
+#define POM_SMAG_TY 4
+#endif
+#ifndef POM_SMAG_NS
+#define POM_SMAG_NS 4
+#endif
+#ifndef POM_SMAG_MINB
+#define POM_SMAG_MINB 8
+#endif
+struct SmagTK : KBase {
+  POM_KINFO("smagorinsky", 2, 1, 2, 1)
+  using KBase::KBase;
+  static constexpr int TY = POM_SMAG_TY, MINB = POM_SMAG_MINB;
+  static constexpr int NF = 2, NS = POM_SMAG_NS, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = TY + 2, NK = 0;
+  static constexpr bool UP = false;
+  static constexpr int NVEC = 1;   // (unused)
+  enum { U, V };
+  POM_HD void fields(const double** b) const { b[U] = p.u; b[V] = p.v; }
+  struct State { RDiv ddx, ddy; double hdd, sa; bool interior; };
+  POM_HD int k0() const { return 1; }
+  POM_HD int k1() const { return g.kb - 1; }
+  POM_HD int kl1() const { return g.kb - 1; }
+  template <class CM>
+  POM_HD void pre(int i, int j, State& s, CM&) const {
+    POM_DIMS;
+    s.interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
+    s.sa = 0.; s.hdd = 0.;
+    if (s.interior) { s.ddx.set(dx(i,j)); s.ddy.set(dy(i,j)); s.hdd=horcon*dx(i,j)*dy(i,j); }
+  }
+  template <class Op, class CM>
+  POM_HD void level(int i, int j, int k, State& s, CM&, const Op& o) const {
+    double a;
+    if (s.interior) {
+      const double u00=o(U,0,0), v00=o(V,0,0);
+      double a1=s.ddx(o(U,1,0)-u00);
+      double a2=s.ddy(o(V,0,1)-v00);
+      double a3=s.ddy(.25*(o(U,0,1)+o(U,1,1)-o(U,0,-1)-o(U,1,-1)))
+               +s.ddx(.25*(o(V,1,0)+o(V,1,1)-o(V,-1,0)-o(V,-1,1)));
+      a=s.hdd*sqrt(a1*a1+a2*a2+.5*(a3*a3));
+      aam(i,j,k)=a;
+    } else {
+      a=aam(i,j,k);
+    }
+    s.sa=s.sa+a*dz(k);
+  }
+  template <class CM>
+  POM_HD void post(int i, int j, State& s, CM&) const { aam2d(i,j)=s.sa; }
+};
+
 void run_advct(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvctK(c), 1, c->g.im, j0, j1); }
 // the caller swaps rho <-> rho2 afterwards
 #ifndef POM_RV_MINB
@@ -305,9 +356,10 @@ void run_advct(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvctK(c), 1, c->g.
 #endif
 void run_baropg(Ctx* c, int j0, int j1) { launch_cols<BaropgK, POM_RV_MINB>(c, BaropgK(c), 1, c->g.im, j0, j1); }
 void run_baropg_mcc(Ctx* c, int j0, int j1) { launch_cols(c, BaropgMccK(c), 1, c->g.im, j0, j1); }
-#ifndef POM_SMAG_MINB
-#define POM_SMAG_MINB 1
+#ifdef POM_SMAG_PLAIN   // the round-1 kernel on plain loads (A/B timing only)
+void run_smag(Ctx* c, int j0, int j1) { launch_cols<SmagK, 1>(c, SmagK(c), 1, c->g.im, j0, j1); }
+#else
+void run_smag(Ctx* c, int j0, int j1) { launch_tma_cols(c, SmagTK(c), 1, c->g.im, j0, j1); }
 #endif
-void run_smag(Ctx* c, int j0, int j1) { launch_cols<SmagK, POM_SMAG_MINB>(c, SmagK(c), 1, c->g.im, j0, j1); }
 
 }  // namespace pom

@@ -148,8 +148,9 @@ static TmaCacheEnt* tma_cache_of(Ctx* c) {
   if (!c->tma_cache) c->tma_cache = calloc(512, sizeof(TmaCacheEnt));
   return (TmaCacheEnt*)c->tma_cache;
 }
-int tma_encode(Ctx* c, CUtensorMap* m, const double* base, int nk, int bw, int bh) {
+int tma_encode(Ctx* c, CUtensorMap* m, const double* base, int nk, int bw, int bh, int bk) {
   TmaCacheEnt* tc = tma_cache_of(c);
+  bh += 4096 * (bk - 1);   // (cache key: the box depth folded into the height)
   const size_t hsh = (((size_t)base >> 8) * 2654435761u + (size_t)nk * 97 + (size_t)bw * 7 + (size_t)bh) & 511;
   TmaCacheEnt& ce = tc[hsh];
   if (ce.base == base && ce.nk == nk && ce.bw == bw && ce.bh == bh) { *m = ce.m; return 0; }
@@ -162,7 +163,7 @@ int tma_encode(Ctx* c, CUtensorMap* m, const double* base, int nk, int bw, int b
   }
   const cuuint64_t dims[3] = {(cuuint64_t)c->g.im, (cuuint64_t)c->g.jml, (cuuint64_t)nk};
   const cuuint64_t strides[2] = {(cuuint64_t)c->g.im * 8, (cuuint64_t)c->g.n2 * 8};
-  const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)(bh % 4096), (cuuint32_t)bk};
   const cuuint32_t es[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -22,6 +22,7 @@
 // when the layout rules out a tensor map (odd im: row pitch not a multiple of 16 bytes).
 #pragma once
 #include "pom_core.h"
+#include <cstdlib>
 #ifndef POMGPU_EMU
 #include <cuda.h>
 #endif
@@ -56,7 +57,7 @@ struct Tile2 {
 
 #ifndef POMGPU_EMU
 template <int NF> struct TmaMaps { CUtensorMap m[NF]; };
-int tma_encode(Ctx* c, CUtensorMap* m, const double* base, int nk, int bw, int bh);   // pom_state.cu
+int tma_encode(Ctx* c, CUtensorMap* m, const double* base, int nk, int bw, int bh, int bk = 1);   // pom_state.cu (box bw x bh x bk)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
@@ -356,9 +357,9 @@ tile3kernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int 
   constexpr int OX = TILE_X - 2, OY = F::TY - 2;
   extern __shared__ __align__(128) double pom_tsm[];
   double* ring = pom_tsm;                         // [NF][PL]   (TMA only)
-  double* S = ring + (TMA ? NF * PL : 0);         // [NV][TILE_Y][TILE_X]
-  double* E = S + NV * TILE_Y * TILE_X;           // [TILE_Y][TILE_X]
-  uint64_t* bar = (uint64_t*)(E + TILE_Y * TILE_X);
+  double* S = ring + (TMA ? NF * PL : 0);         // [NV][TY][TILE_X]
+  double* E = S + NV * F::TY * TILE_X;           // [TILE_Y][TILE_X]
+  uint64_t* bar = (uint64_t*)(E + F::TY * TILE_X);
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ti0 = i0 + blockIdx.x * OX - 1, tj0 = j0 + blockIdx.y * OY - 1;
   const int i = ti0 + tx, j = tj0 + ty;
@@ -400,14 +401,14 @@ tile3kernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int 
   for (int n = 0; n < NV; ++n) v[n] = 0.;
   if (inside) { if (TMA) f.phaseA(i, j, st, sop, v); else f.phaseA(i, j, st, gop, v); }
 #pragma unroll
-  for (int n = 0; n < NV; ++n) S[(n * TILE_Y + ty) * TILE_X + tx] = v[n];
+  for (int n = 0; n < NV; ++n) S[(n * F::TY + ty) * TILE_X + tx] = v[n];
   __syncthreads();
   double e = 0.;
-  if (bok) e = TMA ? f.phaseB(i, j, st, sop, Tile2{S, tx, ty, TILE_Y}, tx >= 1 && ty >= 1) : f.phaseB(i, j, st, gop, Tile2{S, tx, ty, TILE_Y}, tx >= 1 && ty >= 1);
+  if (bok) e = TMA ? f.phaseB(i, j, st, sop, Tile2{S, tx, ty, F::TY}, tx >= 1 && ty >= 1) : f.phaseB(i, j, st, gop, Tile2{S, tx, ty, F::TY}, tx >= 1 && ty >= 1);
   E[ty * TILE_X + tx] = e;
   if (TMA) mbar_wait(&bar[1], 0);
   __syncthreads();
-  if (out) { if (TMA) f.phaseC(i, j, st, sop, Tile2{S, tx, ty, TILE_Y}, Tile2{E, tx, ty, TILE_Y}); else f.phaseC(i, j, st, gop, Tile2{S, tx, ty, TILE_Y}, Tile2{E, tx, ty, TILE_Y}); }
+  if (out) { if (TMA) f.phaseC(i, j, st, sop, Tile2{S, tx, ty, F::TY}, Tile2{E, tx, ty, F::TY}); else f.phaseC(i, j, st, gop, Tile2{S, tx, ty, F::TY}, Tile2{E, tx, ty, F::TY}); }
 }
 #endif
 
@@ -419,7 +420,7 @@ inline void launch_tile3(Ctx* c, const F& f, int i0, int i1, int j0, int j1) {
   const int nbx = (i1 - i0 + OX) / OX, nby = (j1 - j0 + OY) / OY;
 #ifdef POMGPU_EMU
   static typename F::State st[TILE_Y][TILE_X];
-  static double S[F::NV * TILE_Y * TILE_X], E[TILE_Y * TILE_X];
+  static double S[F::NV * F::TY * TILE_X], E[F::TY * TILE_X];
   static bool ins[TILE_Y][TILE_X];
   const double* fld[F::NF];
   f.fields(fld);
@@ -434,19 +435,19 @@ inline void launch_tile3(Ctx* c, const F& f, int i0, int i1, int j0, int j1) {
         double v[F::NV];
         for (int n = 0; n < F::NV; ++n) v[n] = 0.;
         if (ins[ty][tx]) f.phaseA(i, j, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, 1}, v);
-        for (int n = 0; n < F::NV; ++n) S[(n * TILE_Y + ty) * TILE_X + tx] = v[n];
+        for (int n = 0; n < F::NV; ++n) S[(n * F::TY + ty) * TILE_X + tx] = v[n];
       }
       POM_T3_LOOP {
         POM_T3_IJ;
         double e = 0.;
         if (tx <= TILE_X - 2 && ty <= F::TY - 2 && ins[ty][tx])
-          e = f.phaseB(i, j, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, 1}, Tile2{S, tx, ty, TILE_Y}, tx >= 1 && ty >= 1);
+          e = f.phaseB(i, j, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, 1}, Tile2{S, tx, ty, F::TY}, tx >= 1 && ty >= 1);
         E[ty * TILE_X + tx] = e;
       }
       POM_T3_LOOP {
         POM_T3_IJ;
         if (tx >= 1 && tx <= TILE_X - 2 && ty >= 1 && ty <= F::TY - 2 && i <= i1 && j <= j1 && ins[ty][tx])
-          f.phaseC(i, j, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, 1}, Tile2{S, tx, ty, TILE_Y}, Tile2{E, tx, ty, TILE_Y});
+          f.phaseC(i, j, st[ty][tx], GlobalOp<F>{fld, f.g, i, j, 1}, Tile2{S, tx, ty, F::TY}, Tile2{E, tx, ty, F::TY});
       }
     }
 #else
@@ -465,7 +466,7 @@ inline void launch_tile3(Ctx* c, const F& f, int i0, int i1, int j0, int j1) {
     for (int n = 0; n < F::NF && tma_ok; ++n)
       if (tma_encode(c, &maps.m[n], fld[n], 1, F::BW, F::BH)) tma_ok = false;
   }
-  constexpr size_t sm_se = (size_t)((F::NV + 1) * TILE_Y * TILE_X) * sizeof(double) + 16;
+  constexpr size_t sm_se = (size_t)((F::NV + 1) * F::TY * TILE_X) * sizeof(double) + 16;
   constexpr size_t sm_tma = sm_se + (size_t)F::NF * tma_plane(F::BW, F::BH) * sizeof(double);
   static DevOnce granted;
   if (granted.need(c->device)) {
@@ -517,6 +518,246 @@ inline void launch_tma_cols(Ctx* c, const F& f, int i0, int i1, int j0, int j1) 
   }
   if (!tma_ok) colkernel_g<F><<<gr, b, 0, (cudaStream_t)c->stream>>>(f, i0, i1, j0, j1);
   if (c->prof_on) prof_after(c);
+#endif
+}
+
+
+// ---- two-sweep column kernel with the first sweep's results PARKED in shared memory ----------
+// For column operations whose second sweep needs a depth sum of the first (the u, v Asselin filter with
+// its depth-mean removal, advance.f:469-514): the operands are read from HBM ONCE.  PERSISTENT,
+// WARP-SPECIALISED blocks, one per SM: TY consumer warps own 32 x TY columns of ONE component per tile,
+// one producer warp feeds the NF operand planes of every level through a TMA ring of `ns` stages (as deep
+// as the shared memory left over allows) guarded by full/empty mbarrier pairs -- no __syncthreads in the
+// loop, and the producer runs ahead into the NEXT tile while the consumers are still in sweep 2 of the
+// current one, so the loads never drain.  Sweep 1 reduces the staged operands and parks NP values per level
+// and column in shared memory ([level][value][thread]: thread-private slots, conflict-free), sweep 2
+// combines the parked values with the column sums and streams the results out.  F provides NC, NF, NP,
+// fields(comp, b), ktab() (a k-only table, handed to sweep1 level by level), State, NPL + preload(comp,i,j,pl) (the
+// column's plain loads, issued one tile ahead), pre(comp,i,j,State&,pl) (no memory access; also runs for columns
+// outside the rectangle, whose results are never stored), fin(comp,i,j,State&,pl),
+// sweep1(comp,i,j,k,State&,const double* f,double* pk,double tk),
+// mid(comp,i,j,State&), sweep2(comp,i,j,k,State&,const double* pk), fin(comp,i,j,State&); levels 1..kb-1;
+// and NSIDE extra warps per block that run side(w, nw, lane) = the w-th of nw shares of whatever columns the
+// rectangle leaves over (the Orlanski frame of the filter), concurrently with the streaming warps.
+#ifndef POMGPU_EMU
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+template <class F, int TY, int KL>
+__global__ void __launch_bounds__(TILE_X * TY + 32 + 32 * F::NSIDE, 1)
+tmaparkkernel(const __grid_constant__ TmaMaps<F::NC * F::NF> maps, const F f, int i0, int i1, int j0, int j1, int ns,
+              int nbx, int ntiles) {
+  constexpr int NF = F::NF, NP = F::NP, NC = F::NC, NT = TILE_X * TY;   // box = thread tile x KL levels
+  constexpr int STG = NF * KL * NT;                                    // doubles per stage: [field][level][thread]
+  extern __shared__ __align__(128) double pom_tsm[];
+  const int nk = f.g.kb - 1, nst = (nk + KL - 1) / KL;                 // stages per tile
+  double* ring = pom_tsm;                        // [ns][NF][KL][NT]
+  double* park = ring + ns * STG;                // [nk][NP][NT]
+  uint64_t* full = (uint64_t*)(park + nk * NP * NT);   // [ns] stage filled (TMA complete_tx)
+  uint64_t* empty = full + ns;                         // [ns] stage released by the TY consumer warps
+  double* kt = (double*)(empty + ns);                  // [nk] the functor's k-only table (dz), one LDS instead of a global load per level
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < ns; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TY); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int k = tid; k < nk; k += blockDim.x) kt[k] = f.ktab()[k];
+  __syncthreads();
+  if (warp > TY) {                               // ---- side warps: the functor's left-over columns, hidden behind the stream ----
+    f.side(blockIdx.x * F::NSIDE + (warp - TY - 1), gridDim.x * F::NSIDE, lane);
+    return;
+  }
+  // ring position: stage s, parity of its current use (no integer division in the loops)
+  int s = 0, ph = 0;
+  if (warp == TY) {                              // ---- producer warp: lane n issues the box of field n ----
+    if (lane >= NF) return;
+    bool first = true;                           // first pass over the ring: the stages are free
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int bx = t % nbx, r = t / nbx, comp = r % NC, by = r / NC;
+      const int c0 = i0 + bx * TILE_X - 1, c1 = j0 + by * TY - 1 - f.g.joff;   // even i-origin: the launcher checks i0
+      const CUtensorMap* m = &maps.m[comp * NF + lane];
+      for (int q = 0; q < nst; ++q) {
+        if (lane == 0) {
+          if (!first) mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], (uint32_t)(STG * sizeof(double)));
+        }
+        __syncwarp((1u << NF) - 1);
+        tma_load_3d(ring + s * STG + lane * KL * NT, m, &full[s], c0, c1, q * KL);
+        if (++s == ns) { s = 0; ph ^= 1; first = false; }
+      }
+    }
+    return;
+  }
+  // the column's own 2-D / bottom-level operands (F::NPL plain loads) are fetched ONE TILE AHEAD, while the
+  // previous tile is in its second sweep, so that no tile starts or ends on an exposed HBM round trip
+  double pl[F::NPL], pln[F::NPL];
+#pragma unroll
+  for (int n = 0; n < F::NPL; ++n) pln[n] = 0.;
+  {
+    const int t = blockIdx.x;
+    if (t < ntiles) {
+      const int bx = t % nbx, r = t / nbx, comp = r % NC, by = r / NC;
+      const int i = i0 + bx * TILE_X + lane, j = j0 + by * TY + warp;
+      if (i <= i1 && j <= j1) f.preload(comp, i, j, pln);
+    }
+  }
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int bx = t % nbx, r = t / nbx, comp = r % NC, by = r / NC;
+    const int i = i0 + bx * TILE_X + lane, j = j0 + by * TY + warp;
+    const bool active = (i <= i1 && j <= j1);
+#pragma unroll
+    for (int n = 0; n < F::NPL; ++n) pl[n] = pln[n];
+    typename F::State st;
+    f.pre(comp, i, j, st, pl);
+    double* pp = park + tid;
+    for (int q = 0; q < nst; ++q) {
+      mbar_wait(&full[s], ph);
+      const double* rp = ring + s * STG + tid;
+      double v[KL][NF], kk[KL];
+#pragma unroll
+      for (int l = 0; l < KL; ++l) {
+#pragma unroll
+        for (int n = 0; n < NF; ++n) v[l][n] = rp[(n * KL + l) * NT];
+        kk[l] = kt[min(q * KL + l, nk - 1)];
+      }
+#pragma unroll
+      for (int l = 0; l < KL; ++l) {
+        const int k = q * KL + l + 1;
+        if (k <= nk) {
+          double pk[NP];
+          f.sweep1(comp, i, j, k, st, v[l], pk, kk[l]);
+#pragma unroll
+          for (int n = 0; n < NP; ++n) pp[n * NT] = pk[n];
+          pp += NP * NT;
+        }
+      }
+      // release the stage only after the values read from it have been USED (the loads have landed)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      if (++s == ns) { s = 0; ph ^= 1; }
+    }
+    {
+      const int tn = t + gridDim.x;
+      if (tn < ntiles) {
+        const int bxn = tn % nbx, rn = tn / nbx, compn = rn % NC, byn = rn / NC;
+        const int in = i0 + bxn * TILE_X + lane, jn = j0 + byn * TY + warp;
+        if (in <= i1 && jn <= j1) f.preload(compn, in, jn, pln);
+      }
+    }
+    if (active) {
+      f.mid(comp, i, j, st);
+      pp = park + tid;
+#pragma unroll 4
+      for (int k = 1; k <= nk; ++k) {
+        double pk[NP];
+#pragma unroll
+        for (int n = 0; n < NP; ++n) pk[n] = pp[n * NT];
+        pp += NP * NT;
+        f.sweep2(comp, i, j, k, st, pk);
+      }
+      f.fin(comp, i, j, st, pl);
+    }
+  }
+}
+
+inline int park_bps() {   // blocks per SM (tuning knob; 1 = one block owns the SM's whole shared memory)
+  static const int b = getenv("POMGPU_PARK_BPS") ? atoi(getenv("POMGPU_PARK_BPS")) : 1;
+  return b < 1 ? 1 : (b > 8 ? 8 : b);
+}
+template <class F, int TY>
+inline size_t park_ring_bytes(const Ctx* c) {       // shared memory left for the ring with 32 x TY columns parked (0: does not fit)
+  const size_t park = (size_t)(c->g.kb - 1) * F::NP * TILE_X * TY * sizeof(double), stage = (size_t)F::NF * TILE_X * TY * sizeof(double) + 16;
+  // 228 kB per SM shared by the resident blocks, 1 kB of each reserved by the driver; less the k-table
+  const size_t cap = (233472 / park_bps() - 1024 - 512) & ~(size_t)127;
+  return park + 4 * stage > cap ? 0 : cap - park;
+}
+template <class F, int TY, int KL>
+inline void launch_park_ty(Ctx* c, const F& f, const TmaMaps<F::NC * F::NF>& maps, int i0, int i1, int j0, int j1) {
+  constexpr int NT = TILE_X * TY;
+  const size_t park = (size_t)(c->g.kb - 1) * F::NP * NT * sizeof(double), stage = (size_t)F::NF * KL * NT * sizeof(double) + 16;
+  int ns = (int)(park_ring_bytes<F, TY>(c) / stage);
+  if (ns > 32) ns = 32;
+  const size_t smem = park + ns * stage + (size_t)(c->g.kb - 1) * sizeof(double);
+  static DevOnce granted;
+  if (granted.need(c->device)) cudaFuncSetAttribute(tmaparkkernel<F, TY, KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  const int nbx = (i1 - i0 + TILE_X) / TILE_X, nby = (j1 - j0 + TY) / TY, ntiles = nbx * nby * F::NC;
+  const int nres = c->nsm * park_bps();
+  const int nblk = ntiles < nres ? ntiles : nres;
+  tmaparkkernel<F, TY, KL><<<nblk, NT + 32 + 32 * F::NSIDE, smem, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1, ns, nbx, ntiles);
+}
+template <class F, int TY>
+inline void launch_park_kl(Ctx* c, const F& f, const TmaMaps<F::NC * F::NF>& maps, int i0, int i1, int j0, int j1, int kl) {
+  if (kl == 4) launch_park_ty<F, TY, 4>(c, f, maps, i0, i1, j0, j1);
+  else if (kl == 2) launch_park_ty<F, TY, 2>(c, f, maps, i0, i1, j0, j1);
+  else launch_park_ty<F, TY, 1>(c, f, maps, i0, i1, j0, j1);
+}
+#endif
+
+// returns false (nothing launched) when the layout rules the TMA path out: the caller falls back
+template <class F>
+inline bool launch_tma_park(Ctx* c, const F& f, int i0, int i1, int j0, int j1) {
+  if (i1 < i0 || j1 < j0) return true;
+#ifdef POMGPU_EMU
+  c->launches++;
+  static double park[KMAX * F::NP];
+  typename F::State st;
+  const int nk = c->g.kb - 1;
+  for (int comp = 0; comp < F::NC; ++comp) {
+    const double* fld[F::NF];
+    f.fields(comp, fld);
+    for (int j = j0; j <= j1; ++j)
+      for (int i = i0; i <= i1; ++i) {
+        const Geo& g = f.g;
+        double pl[F::NPL];
+        f.preload(comp, i, j, pl);
+        f.pre(comp, i, j, st, pl);
+        for (int k = 1; k <= nk; ++k) {
+          double v[F::NF];
+          for (int n = 0; n < F::NF; ++n) v[n] = fld[n][POM_I3(i, j, k)];
+          f.sweep1(comp, i, j, k, st, v, park + (k - 1) * F::NP, f.ktab()[k - 1]);
+        }
+        f.mid(comp, i, j, st);
+        for (int k = 1; k <= nk; ++k) f.sweep2(comp, i, j, k, st, park + (k - 1) * F::NP);
+        f.fin(comp, i, j, st, pl);
+      }
+  }
+  f.side_host();
+  return true;
+#else
+  if ((c->g.im % 2) || c->no_tma || !(i0 & 1)) return false;   // box origin i0-1 must be even
+  // thread tile: the tallest whose ring still holds ~90 kB in flight per SM (what the HBM latency needs at
+  // full rate); else the tallest that fits at all
+  const size_t r8 = park_ring_bytes<F, 8>(c), r6 = park_ring_bytes<F, 6>(c), r4 = park_ring_bytes<F, 4>(c), r2 = park_ring_bytes<F, 2>(c);
+  const size_t want = 90 * 1024;
+  int ty = r8 >= want ? 8 : r6 >= want ? 6 : r4 >= want ? 4 : r8 ? 8 : r6 ? 6 : r4 ? 4 : r2 ? 2 : 0;
+  static const int force = getenv("POMGPU_PARK_TY") ? atoi(getenv("POMGPU_PARK_TY")) : 0;   // tuning experiments
+  if (force == 8 && r8) ty = 8; else if (force == 6 && r6) ty = 6; else if (force == 4 && r4) ty = 4; else if (force == 2 && r2) ty = 2;
+  if (!ty) return false;
+  static const int fkl = getenv("POMGPU_PARK_KL") ? atoi(getenv("POMGPU_PARK_KL")) : 0;
+  int kl = (fkl == 1 || fkl == 2 || fkl == 4) ? fkl : 4;   // levels per TMA box / ring stage (measured: 4 > 2 > 1)
+  {   // at least 3 stages in the ring
+    const size_t ring = ty == 8 ? r8 : ty == 6 ? r6 : ty == 4 ? r4 : r2;
+    while (kl > 1 && ring < 3 * ((size_t)F::NF * kl * TILE_X * ty * sizeof(double) + 16)) kl /= 2;
+  }
+  TmaMaps<F::NC * F::NF> maps;
+  for (int comp = 0; comp < F::NC; ++comp) {
+    const double* fld[F::NF];
+    f.fields(comp, fld);
+    for (int n = 0; n < F::NF; ++n)
+      if (tma_encode(c, &maps.m[comp * F::NF + n], fld[n], c->g.kb, TILE_X, ty, kl)) return false;
+  }
+  c->launches++;
+  if (c->prof_on) {
+    const KInfo& k = F::info();
+    prof_before(c, &k, 8. * f.columns(i0, i1, j0, j1) * ((k.r3 + k.w3) * (double)c->g.kb + (k.r2 + k.w2)));
+  }
+  cudaSetDevice(c->device);
+  if (ty == 8) launch_park_kl<F, 8>(c, f, maps, i0, i1, j0, j1, kl);
+  else if (ty == 6) launch_park_kl<F, 6>(c, f, maps, i0, i1, j0, j1, kl);
+  else if (ty == 4) launch_park_kl<F, 4>(c, f, maps, i0, i1, j0, j1, kl);
+  else launch_park_kl<F, 2>(c, f, maps, i0, i1, j0, j1, kl);
+  if (c->prof_on) prof_after(c);
+  return true;
 #endif
 }
 

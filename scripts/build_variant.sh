@@ -4,4 +4,5 @@
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 mkdir -p "$ROOT/extpom_b200/variants"
-make -s -C "$ROOT/extpom_b200/csrc" OUT="$ROOT/extpom_b200/variants/lib_$1.so" LOG="$ROOT/extpom_b200/variants/ptxas_$1.log" EXTRA="$2"
+# (its own object directory: the default build's objects were compiled with other flags)
+make -s -j8 -C "$ROOT/extpom_b200/csrc" "$ROOT/extpom_b200/variants/lib_$1.so" OUT="$ROOT/extpom_b200/variants/lib_$1.so" OBJ="$ROOT/extpom_b200/variants/obj_$1" LOG="$ROOT/extpom_b200/variants/ptxas_$1.log" EXTRA="$2"
