@@ -194,6 +194,78 @@ struct BaropgK : KBase {
   }
 };
 
+// baropg on the TMA ring (pom_tma.h: tmacolkernel): rho and rmean of every level are staged with their west
+// and south neighbours, two or more levels ahead; same expressions as BaropgK.
+#ifndef POM_BAROPG_TY
+#define POM_BAROPG_TY 4
+#define POM_BAROPG_MINB 8
+#define POM_BAROPG_NS 4
+#endif
+struct BaropgTK : KBase {
+  POM_KINFO("baropg", 2, 3, 5, 2)
+  using KBase::KBase;
+  static constexpr int TY = POM_BAROPG_TY, MINB = POM_BAROPG_MINB;
+  static constexpr int NF = 2, NS = POM_BAROPG_NS, OHL = 1, OHR = 0, OHB = 1, OHT = 0, BW = 34, BH = TY + 1, NK = 0;
+  static constexpr bool UP = false;
+  static constexpr int NVEC = 1;   // (unused)
+  enum { RHO, RMEAN };
+  POM_HD void fields(const double** b) const { b[RHO] = p.rho; b[RMEAN] = p.rmean; }
+  struct State { double dtx, dty, ddx, ddy, dyx, dxy, mu, mv, a0, ax, ay, px, py, sx, sy; bool interior; };
+  POM_HD int k0() const { return 1; }
+  POM_HD int k1() const { return g.kb; }
+  POM_HD int kl1() const { return g.kb; }
+  template <class CM>
+  POM_HD void pre(int i, int j, State& s, CM&) const {
+    POM_DIMS;
+    s.interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
+    s.sx = 0.; s.sy = 0.;
+    if (!s.interior) return;
+    s.dtx=dt(i,j)+dt(i-1,j); s.dty=dt(i,j)+dt(i,j-1);
+    s.ddx=dt(i,j)-dt(i-1,j); s.ddy=dt(i,j)-dt(i,j-1);
+    s.dyx=dy(i,j)+dy(i-1,j); s.dxy=dx(i,j)+dx(i,j-1);
+    s.mu=dum(i,j); s.mv=dvm(i,j);
+  }
+  template <class Op, class CM>
+  POM_HD void level(int i, int j, int k, State& s, CM&, const Op& o) const {
+    POM_DIMS;
+    const double rmk=o(RMEAN,0,0);
+    const double b0=o(RHO,0,0)-rmk;
+    rho2(i,j,k)=b0+rmk;                                                 // :854,937 folded into the sweep
+    if (!s.interior) {
+      if (k <= kbm1) {   // edges keep their content (initialize.f:307-308)
+        s.sx=s.sx+drhox(i,j,k)*dz(k);
+        s.sy=s.sy+drhoy(i,j,k)*dz(k);
+      }
+      return;
+    }
+    if (k == kb) {                                                      // :928-932 (k=kb)
+      drhox(i,j,kb)=ramp*drhox(i,j,kb);
+      drhoy(i,j,kb)=ramp*drhoy(i,j,kb);
+      return;
+    }
+    const double bx=o(RHO,-1,0)-o(RMEAN,-1,0);
+    const double by=o(RHO,0,-1)-o(RMEAN,0,-1);
+    if (k == 1) {
+      s.px=.5*grav*(-zz(1))*s.dtx*(b0-bx);                              // :859-860
+      s.py=.5*grav*(-zz(1))*s.dty*(b0-by);                              // :895-896
+    } else {
+      s.px=s.px+grav*.25*(zz(k-1)-zz(k))*s.dtx*(b0-bx+s.a0-s.ax)
+               +grav*.25*(zz(k-1)+zz(k))*s.ddx*(b0+bx-s.a0-s.ax);       // :867-875
+      s.py=s.py+grav*.25*(zz(k-1)-zz(k))*s.dty*(b0-by+s.a0-s.ay)
+               +grav*.25*(zz(k-1)+zz(k))*s.ddy*(b0+by-s.a0-s.ay);       // :903-911
+    }
+    s.a0=b0; s.ax=bx; s.ay=by;
+    const double ox=ramp*(.25*s.dtx*s.px*s.mu*s.dyx);                   // :883-885,931
+    const double oy=ramp*(.25*s.dty*s.py*s.mv*s.dxy);                   // :919-921,932
+    drhox(i,j,k)=ox;
+    drhoy(i,j,k)=oy;
+    s.sx=s.sx+ox*dz(k);                                                 // advance.f:163-164
+    s.sy=s.sy+oy*dz(k);
+  }
+  template <class CM>
+  POM_HD void post(int i, int j, State& s, CM&) const { drx2d(i,j)=s.sx; dry2d(i,j)=s.sy; }
+};
+
 // baropg_mcc (solver.f:943-1159, npg=2): 4th-order McCalpin pressure gradient.  Same outputs and
 // side effects as BaropgK; reads rho-rmean and d two cells away (the order2d/3d_mpi width-2 halo
 // of the reference = ghost rows here).  Single-precision literals (1./24.), (1./16.) kept.
@@ -354,7 +426,11 @@ void run_advct(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvctK(c), 1, c->g.
 #ifndef POM_RV_MINB
 #define POM_RV_MINB 4
 #endif
+#ifdef POM_BAROPG_PLAIN   // the round-1 kernel on plain loads (A/B timing only)
 void run_baropg(Ctx* c, int j0, int j1) { launch_cols<BaropgK, POM_RV_MINB>(c, BaropgK(c), 1, c->g.im, j0, j1); }
+#else
+void run_baropg(Ctx* c, int j0, int j1) { launch_tma_cols(c, BaropgTK(c), 1, c->g.im, j0, j1); }
+#endif
 void run_baropg_mcc(Ctx* c, int j0, int j1) { launch_cols(c, BaropgMccK(c), 1, c->g.im, j0, j1); }
 #ifdef POM_SMAG_PLAIN   // the round-1 kernel on plain loads (A/B timing only)
 void run_smag(Ctx* c, int j0, int j1) { launch_cols<SmagK, 1>(c, SmagK(c), 1, c->g.im, j0, j1); }

@@ -66,6 +66,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred P1;\n\t"
@@ -91,8 +94,15 @@ struct SmemOp {
   __device__ __forceinline__ double up(int f, int di, int dj) const { return nxt[f * PL + dj * F::BW + di]; }
 };
 
+// POM_TILE_PRODUCER: the TMA loads of the tile kernels are issued by one lane of an EXTRA warp (thread row
+// ty == F::TY) instead of by thread (0,0) of the computing warps: it takes part in the per-level block barrier
+// (which tells it that the stage of level k-1 is free) and then issues level k-1+NS while the computing warps
+// are already in combine(k) -- the NF serial TMA issues leave the critical path of every level.
+#ifndef POM_TILE_PRODUCER
+#define POM_TILE_PRODUCER 1
+#endif
 template <class F>
-__global__ void __launch_bounds__(TILE_X * F::TY, F::MINB)
+__global__ void __launch_bounds__(TILE_X * (F::TY + POM_TILE_PRODUCER), F::MINB)
 tmakernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1, int j0, int j1) {
   constexpr int NF = F::NF, NS = F::NS, NV = F::NV, PL = tma_plane(F::BW, F::BH);
   constexpr int OX = TILE_X - F::HL - F::HR, OY = F::TY - F::HB - F::HT;
@@ -111,7 +121,7 @@ tmakernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1
   const int n0 = ti0 - 1 - F::OHL, shift = n0 & 1;
   const int c0 = n0 - shift, c1 = tj0 - 1 - f.g.joff - F::OHB;
   const int k0 = f.k0(), k1 = f.k1(), kl1 = f.kl1();
-  const bool leader = (tx == 0 && ty == 0);
+  const bool leader = POM_TILE_PRODUCER ? (tx == 0 && ty == F::TY) : (tx == 0 && ty == 0);
   if (leader) {
     for (int s = 0; s < NS; ++s) mbar_init(&bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -125,6 +135,13 @@ tmakernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1
   };
   if (leader)
     for (int L = k0; L < k0 + NS && L <= kl1; ++L) issue(L);
+  if (POM_TILE_PRODUCER && ty == F::TY) {                  // the producer warp: one barrier per level, like the others
+    for (int k = k0; k <= k1; ++k) {
+      __syncthreads();
+      if (leader && k - 1 >= k0 && k - 1 + NS <= kl1) issue(k - 1 + NS);
+    }
+    return;
+  }
   const bool inside = (i >= 1 && i <= f.g.im && j >= f.g.joff + 1 && j <= f.g.joff + f.g.jml);
   const bool out = (tx >= F::HL && tx < TILE_X - F::HR && ty >= F::HB && ty < F::TY - F::HT && i <= i1 && j <= j1);
   typename F::State st{};
@@ -151,7 +168,7 @@ tmakernel(const __grid_constant__ TmaMaps<F::NF> maps, const F f, int i0, int i1
     for (int n = 0; n < NV; ++n) Sb[(n * F::TY + ty) * TILE_X + tx] = v[n];
     __syncthreads();
     // every thread is past combine(k-1): the stage of level k-1 is free for level k-1+NS
-    if (leader && k - 1 >= k0 && k - 1 + NS <= kl1) issue(k - 1 + NS);
+    if (!POM_TILE_PRODUCER && leader && k - 1 >= k0 && k - 1 + NS <= kl1) issue(k - 1 + NS);
     if (out) f.combine(i, j, k, st, op, Tile2{Sb, tx, ty, F::TY});
     buf ^= 1;
   }
@@ -334,7 +351,8 @@ inline void launch_tma_tiles(Ctx* c, const F& f, int i0, int i1, int j0, int j1)
       constexpr size_t smem = (size_t)(F::NS * F::NF * tma_plane(F::BW, F::BH) + 2 * F::NV * F::TY * TILE_X) * sizeof(double) + F::NS * 8;
       static DevOnce granted;
       if (granted.need(c->device)) cudaFuncSetAttribute(tmakernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      tmakernel<F><<<gr, b, smem, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
+      const dim3 bt(TILE_X, F::TY + POM_TILE_PRODUCER);     // (+ the producer warp)
+      tmakernel<F><<<gr, bt, smem, (cudaStream_t)c->stream>>>(maps, f, i0, i1, j0, j1);
     }
   }
   if (!tma_ok) tilekernel_g<F><<<gr, b, 0, (cudaStream_t)c->stream>>>(f, i0, i1, j0, j1);
@@ -540,9 +558,6 @@ inline void launch_tma_cols(Ctx* c, const F& f, int i0, int i1, int j0, int j1) 
 // and NSIDE extra warps per block that run side(w, nw, lane) = the w-th of nw shares of whatever columns the
 // rectangle leaves over (the Orlanski frame of the filter), concurrently with the streaming warps.
 #ifndef POMGPU_EMU
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
 template <class F, int TY, int KL>
 __global__ void __launch_bounds__(TILE_X * TY + 32 + 32 * F::NSIDE, 1)
 tmaparkkernel(const __grid_constant__ TmaMaps<F::NC * F::NF> maps, const F f, int i0, int i1, int j0, int j1, int ns,
