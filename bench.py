@@ -280,11 +280,12 @@ def nrank_parity(rank, world, local, dist):
         if not np.array_equal(x, y):
             bad.append(n)
     nex, _ = m.group.exchanges()
+    transport = m.group.transport()
     t = torch.tensor([len(bad)], device="cuda")
     dist.all_reduce(t)
     m.group.close(); m.gpu.close(); whole.close()
     return {"bitwise": int(t.item()) == 0, "fields": len(fields), "grid": f"{im}x{jm}x{kb}", "steps": steps,
-            "ranks": world, "transport": "NCCL send/recv", "exchanges_per_step": nex / steps,
+            "ranks": world, "transport": transport, "exchanges_per_step": nex / steps,
             "mismatched_on_rank0": bad}
 
 

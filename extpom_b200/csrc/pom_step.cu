@@ -743,6 +743,12 @@ double pomgpu_group_check_velocity(pomgpu_group_t* g) {
   return m;
 }
 int pomgpu_group_halo_trace(pomgpu_group_t* g, char* buf, int len) { return group_trace_report(GG(g), buf, len); }
+int pomgpu_group_transport(pomgpu_group_t* g) {
+  Group* G = GG(g);
+  if (G->cb) return 3;
+  if (G->ipc) return 2;
+  return G->nccl ? 1 : 0;
+}
 long pomgpu_group_exchanges(pomgpu_group_t* g, long* fields, int reset) {
   long n = GG(g)->n_exchanges;
   if (fields) *fields = GG(g)->n_fields_exchanged;

@@ -100,6 +100,8 @@ def _bind(path):
     L.pomgpu_group_baropg.argtypes = [P]
     L.pomgpu_group_check_velocity.restype = C.c_double
     L.pomgpu_group_check_velocity.argtypes = [P]
+    L.pomgpu_group_transport.restype = C.c_int
+    L.pomgpu_group_transport.argtypes = [P]
     L.pomgpu_group_exchanges.restype = C.c_long
     L.pomgpu_group_exchanges.argtypes = [P, C.POINTER(C.c_long), C.c_int]
     L.pomgpu_advt1.argtypes = [P] + [C.c_char_p] * 4
@@ -433,6 +435,10 @@ class PomGroup:
 
     def domain_stats(self):
         return finish_domain_stats(np.concatenate([s.domain_stats_rows() for s in self.strips], axis=0))
+
+    def transport(self):
+        """How the seam rows travel (pomgpu_group_transport)."""
+        return ("device copies", "NCCL send/recv", "CUDA IPC peer copies", "host callback")[self.L.pomgpu_group_transport(self.h)]
 
     def exchanges(self, reset=False):
         f = C.c_long(0)

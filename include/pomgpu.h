@@ -140,6 +140,9 @@ int pomgpu_group_dens(pomgpu_group_t* g, const char* si, const char* ti, const c
 int pomgpu_group_baropg(pomgpu_group_t* g);   /* baropg or baropg_mcc by npg (initialize.f:502-505) */
 double pomgpu_group_check_velocity(pomgpu_group_t* g); /* max over this process's strips */
 long pomgpu_group_exchanges(pomgpu_group_t* g, long* fields, int reset); /* halo messages so far */
+/* how the seam rows travel: 0 device copies between strips of this process, 1 ncclSend/ncclRecv,
+   2 peer copies into the neighbour's CUDA-IPC-mapped staging buffers, 3 host callback */
+int pomgpu_group_transport(pomgpu_group_t* g);
 /* developer tool (POMGPU_HALO_TRACE=1): one text line per exchange since the last call -- bytes per
  * direction and the device time of its pack, transfer and unpack from CUDA events; returns the length */
 int pomgpu_group_halo_trace(pomgpu_group_t* g, char* buf, int len);
