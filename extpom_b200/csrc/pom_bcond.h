@@ -25,7 +25,7 @@ POM_HD double orl(double xf1, double xb1, double x2, double xb0, double x1) {
 // correction for outflow (bounds_forcing.f:151-231)
 template <class K>
 POM_HD void bcond4_edge(const K& kk, int i, int j, int k, double& a, double& b) {
-  const Geo& g = kk.g; const Ptrs& p = kk.p; const Consts& c = kk.c;
+  const Geo& g = kk.g; const Ptrs& p = kk.p; const Consts& c = kk.c; const KTab& kt = kk.kt; (void)kt;
   POM_DIMS;
   const bool vadv = (k != 1 && k != kbm1);
   if (j == 1) {                                                     // south (:196-211)
@@ -90,7 +90,7 @@ POM_HD void bcond4_edge(const K& kk, int i, int j, int k, double& a, double& b) 
 // bcond(6): upstream advection of q2 (a) and q2l (b) on the four open edges (bounds_forcing.f:257-311)
 template <class K>
 POM_HD void bcond6_edge(const K& kk, int i, int j, int k, double& a, double& b) {
-  const Geo& g = kk.g; const Ptrs& p = kk.p; const Consts& c = kk.c;
+  const Geo& g = kk.g; const Ptrs& p = kk.p; const Consts& c = kk.c; const KTab& kt = kk.kt; (void)kt;
   POM_DIMS;
   if (j == 1) {                                                     // south (:290-299)
     double u1=2.*v(i,2,k)*dti/(dy(i,1)+dy(i,2));
@@ -115,7 +115,7 @@ POM_HD void bcond6_edge(const K& kk, int i, int j, int k, double& a, double& b) 
 // line itself (bounds_forcing.f:418-474); a = uf, b = vf
 template <class K>
 POM_HD void bcondorl3_edge(const K& kk, int i, int j, int k, double& a, double& b) {
-  const Geo& g = kk.g; const Ptrs& p = kk.p;
+  const Geo& g = kk.g; const Ptrs& p = kk.p; const KTab& kt = kk.kt; (void)kt;
   POM_DIMS;
   const bool jin = (j >= 2 && j <= jmm1), iin = (i >= 2 && i <= imm1);
   if (jin) {

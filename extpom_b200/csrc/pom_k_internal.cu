@@ -1114,7 +1114,7 @@ POM_HD double dens_point(double tr, double sr, double pp, double rhoref_, double
 // left at (i,j,k).  Shared by the stand-alone filter kernel and by proft's fused upward sweep.
 template <class K>
 POM_HD void ts_level(const K& kk, int i, int j, int k, double a, double b, double m, double fold, double fnew, int with_dens) {
-  const Geo& g = kk.g; const Ptrs& p = kk.p; const Consts& c = kk.c;
+  const Geo& g = kk.g; const Ptrs& p = kk.p; const Consts& c = kk.c; const KTab& kt = kk.kt; (void)kt;
   POM_DIMS;
     bcond4_edge(kk, i, j, k, a, b);                                   // bounds_forcing.f:151-231
     a=a*m;                                                            // :236-237
@@ -1700,7 +1700,7 @@ struct FbRoundTripK : KBase {
 // depend on which strip holds it; the caller adds the rows in global order (deterministic and
 // decomposition-invariant).  Per row: atot, eavg*atot, vtot, mtot, tavg*vtot, stot, ekin.
 POM_HD void dstats_point(const KBase& kb_, int i, int j, double* acc) {
-  const Geo& g = kb_.g; const Ptrs& p = kb_.p; const Consts& c = kb_.c;
+  const Geo& g = kb_.g; const Ptrs& p = kb_.p; const Consts& c = kb_.c; const KTab& kt = kb_.kt;
   const int im = g.im, jm = g.jmg, imm1 = im - 1, jmm1 = jm - 1, kbm1 = g.kb - 1;
   const bool jin = (j >= 2 && j <= jmm1), iin = (i >= 2 && i <= imm1);
   if (!(jin || iin)) return;                                  // the four corners are never counted

@@ -225,6 +225,7 @@ int prof_report(Ctx* c, char* buf, int n) {
 Ctx* ctx_create(int im, int jm_global, int kb, int j_first, int j_last, int ghost, int device) {
   if (im < 6 || jm_global < 6 || kb < 4 || kb > KMAX) return nullptr;   // most levels the column solvers hold
   Ctx* c = (Ctx*)calloc(1, sizeof(Ctx));
+  c->hz = c->hk[0];
   c->no_tma = (getenv("POMGPU_NO_TMA") != nullptr);
   c->device = device;
   c->jown0 = j_first; c->jown1 = j_last; c->ghost = ghost;
@@ -288,8 +289,9 @@ int ctx_push(Ctx* c, const char* name, const double* host) {
   double** slot = ctx_slot(c, name, &f);
   if (!slot) { snprintf(c->err, sizeof(c->err), "unknown field '%s'", name); return 2; }
   if (!*slot && dev_alloc(c, slot, field_elems(c, f))) return 1;
-  if (!strcmp(name, "z"))
-    for (int k = 0; k < c->g.kb && k < 128; ++k) c->hz[k] = host[k];
+  for (int t = 0; t < 4; ++t)
+    if (!strcmp(name, t == 0 ? "z" : t == 1 ? "zz" : t == 2 ? "dz" : "dzz"))
+      for (int k = 0; k < c->g.kb && k < KMAX; ++k) c->hk[t][k] = host[k];
   return dev_h2d(c, *slot, host, field_elems(c, f));
 }
 
