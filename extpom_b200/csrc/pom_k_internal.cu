@@ -153,6 +153,73 @@ struct UvAdjVertvlK : KBase {
   }
 };
 
+// The same sweep on the TMA ring (pom_tma.h: tmacolkernel): u, v of every level staged with their east / north
+// neighbours, two or more levels ahead.  Same expressions as UvAdjVertvlK.
+#ifndef POM_UVADJ_TY
+#define POM_UVADJ_TY 4
+#define POM_UVADJ_MINB 8
+#define POM_UVADJ_NS 4
+#endif
+struct UvAdjVertvlTK : KBase {
+  POM_KINFO("uvadjust_vertvl", 2, 3, 14, 0)
+  using KBase::KBase;
+  static constexpr int TY = POM_UVADJ_TY, MINB = POM_UVADJ_MINB;
+  static constexpr int NF = 2, NS = POM_UVADJ_NS, OHL = 0, OHR = 1, OHB = 0, OHT = 1, BW = 34, BH = TY + 1, NK = 0;
+  static constexpr bool UP = false;
+  static constexpr int NVEC = 1;   // (unused)
+  enum { U, V };
+  POM_HD void fields(const double** b) const { b[U] = p.u; b[V] = p.v; }
+  struct State { double m, tu, tv, ru, rv, tuE, ruE, tvN, rvN, wk, de, cW, cE, cS, cN; RDiv ddxy; bool interior, au, av; };
+  POM_HD int k0() const { return 1; }
+  POM_HD int k1() const { return g.kb; }
+  POM_HD int kl1() const { return g.kb; }
+  template <class CM>
+  POM_HD void pre(int i, int j, State& s, CM&) const {
+    POM_DIMS;
+    s.m = fsm(i,j);
+    s.interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
+    s.au = (i >= 2); s.av = (j >= 2);                                     // :373, :386
+    s.tu=A2(p.s2c,i,j); s.tv=A2(p.s2d,i,j);
+    s.ru = s.au ? (utb(i,j)+utf(i,j))/(dt(i,j)+dt(i-1,j)) : 0.;
+    s.rv = s.av ? (vtb(i,j)+vtf(i,j))/(dt(i,j)+dt(i,j-1)) : 0.;
+    s.tuE = 0.; s.ruE = 0.; s.tvN = 0.; s.rvN = 0.; s.wk = 0.; s.de = 0.; s.cW = 0.; s.cE = 0.; s.cS = 0.; s.cN = 0.;
+    s.ddxy.set(s.interior ? dx(i,j)*dy(i,j) : 1.);
+    if (s.interior) {
+      s.tuE=A2(p.s2c,i+1,j); s.ruE=(utb(i+1,j)+utf(i+1,j))/(dt(i+1,j)+dt(i,j));
+      s.tvN=A2(p.s2d,i,j+1); s.rvN=(vtb(i,j+1)+vtf(i,j+1))/(dt(i,j+1)+dt(i,j));
+      s.wk=0.5*(vfluxb(i,j)+vfluxf(i,j));                               // solver.f:2004
+      s.de=(etf(i,j)-etb(i,j))/dti2;
+      s.cW=.25*(dy(i,j)+dy(i-1,j))*(dt(i,j)+dt(i-1,j));                 // :1984-1985,1993-1994
+      s.cE=.25*(dy(i+1,j)+dy(i,j))*(dt(i+1,j)+dt(i,j));
+      s.cS=.25*(dx(i,j)+dx(i,j-1))*(dt(i,j)+dt(i,j-1));
+      s.cN=.25*(dx(i,j+1)+dx(i,j))*(dt(i,j+1)+dt(i,j));
+    }
+  }
+  template <class Op, class CM>
+  POM_HD void level(int i, int j, int k, State& s, CM&, const Op& o) const {
+    const double u0=o(U,0,0), v0=o(V,0,0);
+    if (k == g.kb) {
+      A3(p.s3a,i,j,k)=u0;
+      A3(p.s3b,i,j,k)=v0;
+      if (s.interior) w(i,j,k)=s.wk;
+      return;
+    }
+    const double ua = s.au ? (u0-s.tu)+s.ru : u0;                       // advance.f:374-375
+    const double va = s.av ? (v0-s.tv)+s.rv : v0;                       // :387-388
+    A3(p.s3a,i,j,k)=ua;
+    A3(p.s3b,i,j,k)=va;
+    if (s.interior) {
+      const double uE=(o(U,1,0)-s.tuE)+s.ruE, vN=(o(V,0,1)-s.tvN)+s.rvN;
+      w(i,j,k)=s.wk*s.m;                                                // bounds_forcing.f:553-559
+      s.wk=s.wk+dz(k)*(s.ddxy(s.cE*uE-s.cW*ua+s.cN*vN-s.cS*va)+s.de);   // solver.f:2011-2015
+    } else {
+      w(i,j,k)=w(i,j,k)*s.m;
+    }
+  }
+  template <class CM>
+  POM_HD void post(int, int, State&, CM&) const {}
+};
+
 // the depth sums of u and v (advance.f:367-369,380-382) when uv_filter's are not current
 struct UvSumK : KBase {
   POM_KINFO("uv_sum", 2, 0, 0, 2)
@@ -1679,6 +1746,64 @@ struct RealvertvlK : KBase {
   }
 };
 
+// realvertvl on the TMA ring: w (levels k and k+1), u, v staged with the halo the clamped index needs (one point
+// west / south, two east / north).  Same expressions as RealvertvlK.
+#ifndef POM_RVV_TY
+#define POM_RVV_TY 4
+#define POM_RVV_MINB 8
+#define POM_RVV_NS 4
+#endif
+struct RealvertvlTK : KBase {
+  POM_KINFO("realvertvl", 3, 1, 7, 0)
+  using KBase::KBase;
+  static constexpr int TY = POM_RVV_TY, MINB = POM_RVV_MINB;
+  static constexpr int NF = 3, NS = POM_RVV_NS, OHL = 1, OHR = 2, OHB = 1, OHT = 2, BW = 36, BH = TY + 3, NK = 0;
+  static constexpr bool UP = true;
+  static constexpr int NVEC = 1;   // (unused)
+  enum { W, U, V };
+  POM_HD void fields(const double** b) const { b[W] = p.w; b[U] = p.u; b[V] = p.v; }
+  struct State { double m, dxr, dxl, dyt, dyb, dt0, dtE, dtW, dtN, dtS, et0, etE, etW, etN, etS, de, w0; RDiv ddti2; int di, dj; };
+  POM_HD int k0() const { return 1; }
+  POM_HD int k1() const { return g.kb - 1; }
+  POM_HD int kl1() const { return g.kb; }
+  template <class CM>
+  POM_HD void pre(int i, int j, State& s, CM&) const {
+    POM_DIMS;
+    // edge copies S,N then W,E (:2057-2060) = value at the index clamped inside
+    const int ic = i < 2 ? 2 : (i > imm1 ? imm1 : i);
+    const int jc = j < 2 ? 2 : (j > jmm1 ? jmm1 : j);
+    s.di = ic - i; s.dj = jc - j;
+    s.m=fsm(i,j);
+    s.dxr=2.0/(dx(ic+1,jc)+dx(ic,jc));
+    s.dxl=2.0/(dx(ic,jc)+dx(ic-1,jc));
+    s.dyt=2.0/(dy(ic,jc+1)+dy(ic,jc));
+    s.dyb=2.0/(dy(ic,jc)+dy(ic,jc-1));
+    s.dt0=dt(ic,jc); s.dtE=dt(ic+1,jc); s.dtW=dt(ic-1,jc); s.dtN=dt(ic,jc+1); s.dtS=dt(ic,jc-1);
+    s.et0=et(ic,jc); s.etE=et(ic+1,jc); s.etW=et(ic-1,jc); s.etN=et(ic,jc+1); s.etS=et(ic,jc-1);
+    s.de=etf(ic,jc)-etb(ic,jc);
+    s.ddti2.set(dti2);
+    wr(i,j,kb)=0.;
+  }
+  template <class Op, class CM>
+  POM_HD void level(int i, int j, int k, State& s, CM&, const Op& o) const {
+    const int di = s.di, dj = s.dj;
+    if (k == 1) s.w0=o(W,di,dj);
+    const double zk=zz(k);
+    const double tp0=zk*s.dt0+s.et0;                                    // :2036
+    const double w1=o.up(W,di,dj);
+    const double r=0.5*(s.w0+w1)+0.5*
+         (o(U,di+1,dj)*((zk*s.dtE+s.etE)-tp0)*s.dxr+
+          o(U,di,dj)*(tp0-(zk*s.dtW+s.etW))*s.dxl+
+          o(V,di,dj+1)*((zk*s.dtN+s.etN)-tp0)*s.dyt+
+          o(V,di,dj)*(tp0-(zk*s.dtS+s.etS))*s.dyb)
+         +s.ddti2((1.0+zk)*s.de);                                       // :2045-2050
+    wr(i,j,k)=s.m*r;                                                    // :2063
+    s.w0=w1;
+  }
+  template <class CM>
+  POM_HD void post(int, int, State&, CM&) const {}
+};
+
 // in-place (fb-fclim)+fclim and fb(kb)=fb(kbm1): the side effects advt1/advt2 leave on
 // their fb argument (solver.f:496,511,532 / 618,691,715); used by the unit-mode entry
 struct FbRoundTripK : KBase {
@@ -1767,7 +1892,11 @@ int domain_stats_rows(Ctx* c, double* rows) {
 #define ALLI 1, c->g.im
 void run_uvadjust(Ctx* c, int j0, int j1) { launch_cols(c, UvAdjustK(c), ALLI, j0, j1); }
 void run_vertvl(Ctx* c, int j0, int j1) { launch_cols(c, VertvlK(c), ALLI, j0, j1); }
+#ifdef POM_COLS_PLAIN   // the round-1 kernels on plain loads (A/B timing only)
 void run_uvadj_vertvl(Ctx* c, int j0, int j1) { launch_cols<UvAdjVertvlK, POM_RV_MINB>(c, UvAdjVertvlK(c), ALLI, j0, j1); }
+#else
+void run_uvadj_vertvl(Ctx* c, int j0, int j1) { launch_tma_cols(c, UvAdjVertvlTK(c), ALLI, j0, j1); }
+#endif
 void run_uvsum(Ctx* c, int j0, int j1) { launch_cols(c, UvSumK(c), ALLI, j0, j1); }
 void run_advq(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvqK(c), ALLI, j0, j1); }
 // the fused variant under its own name / algorithmic byte count in the per-kernel profile
@@ -1834,6 +1963,10 @@ void run_uvfilter(Ctx* c, int j0, int j1) {
   launch_cols(c, UvFilterK(c), ALLI, j0, j1);
 }
 void run_endstep2d(Ctx* c, int j0, int j1) { launch_cols(c, EndStep2dK(c), ALLI, j0, j1); }
+#ifdef POM_COLS_PLAIN
 void run_realvertvl(Ctx* c, int j0, int j1) { launch_cols<RealvertvlK, POM_RV_MINB>(c, RealvertvlK(c), ALLI, j0, j1); }
+#else
+void run_realvertvl(Ctx* c, int j0, int j1) { launch_tma_cols(c, RealvertvlTK(c), ALLI, j0, j1); }
+#endif
 
 }  // namespace pom
