@@ -32,7 +32,7 @@ POM_HD void advave_own_fluxes(const Geo& g, int i, int j, const Op& o, double* v
   // tps(i,j), 2<=i<=im, 2<=j<=jm (:47-53)
   const double tp=.25*(d00+dW+dS+dSW)
                   *(am00+o(OP_AAM2D,0,-1)+o(OP_AAM2D,-1,0)+o(OP_AAM2D,-1,-1))
-                  *((uab00-o(OP_UAB,0,-1))/dy4+(vab00-o(OP_VAB,-1,0))/dx4);
+                  *(pdiv(uab00-o(OP_UAB,0,-1),dy4)+pdiv(vab00-o(OP_VAB,-1,0),dx4));
   {   // u half fluxva (:30-32,55-56) and v half fluxua (:80-82,106-107)
     double a=.125*((d00+dS)*va00+(dW+dSW)*vaW)*(ua00+uaS);
     v[FYU]=(a-tp)*.25*dx4;
@@ -42,13 +42,13 @@ POM_HD void advave_own_fluxes(const Geo& g, int i, int j, const Op& o, double* v
   if (i <= imm1) {   // u half fluxua (:22-24,39-41,54)
     const double dE=o(OP_D,1,0), uaE=o(OP_UA,1,0);
     double a=.125*((dE+d00)*uaE+(d00+dW)*ua00)*(uaE+ua00);
-    a=a-d00*2.*am00*(o(OP_UAB,1,0)-uab00)/dx00;
+    a=a-pdiv(d00*2.*am00*(o(OP_UAB,1,0)-uab00),dx00);
     v[FXU]=a*dy00;
   }
   if (j <= jmm1 && j + 1 <= jhi) {   // v half fluxva (:88-90,97-99,105)
     const double dN=o(OP_D,0,1), vaN=o(OP_VA,0,1);
     double a=.125*((dN+d00)*vaN+(d00+dS)*va00)*(vaN+va00);
-    a=a-d00*2.*am00*(o(OP_VAB,0,1)-vab00)/dy00;
+    a=a-pdiv(d00*2.*am00*(o(OP_VAB,0,1)-vab00),dy00);
     v[FYV]=a*dx00;
   }
 }
@@ -176,7 +176,7 @@ struct ExtStepK : KBase {
     const int ic = i < 2 ? 2 : (i > imm1 ? imm1 : i);
     const int jc = j < 2 ? 2 : (j > jmm1 ? jmm1 : j);
     const int di = ic - i, dj = jc - j;
-    const double ef=o(ELB,di,dj)+dte2*(-(S(FUA,di+1,dj)-S(FUA,di,dj)+S(FVA,di,dj+1)-S(FVA,di,dj))/s.artc
+    const double ef=o(ELB,di,dj)+dte2*(pdiv(-(S(FUA,di+1,dj)-S(FUA,di,dj)+S(FVA,di,dj+1)-S(FVA,di,dj)),s.artc)
                                      -s.vflc);                            // advance.f:224-227
     if (nbr && i >= 2 && i <= imm1 && j >= 2 && j <= jmm1) {
       if (do_adv) {
@@ -240,9 +240,9 @@ struct ExtStepK : KBase {
                      +alpha*(elb00-elbW+ef-efW)
                      +o(EATM,0,0)-o(EATM,-1,0))
                  +drx0+ar*(wus0-wub0);
-        un=((h00+elb00+hW+elbW)*ar*o(UAB,0,0)
-            -4.*dte*r)
-           /((h00+ef+hW+efW)*ar);
+        un=pdiv((h00+elb00+hW+elbW)*ar*o(UAB,0,0)
+                -4.*dte*r,
+                (h00+ef+hW+efW)*ar);
       }
     } else if (iin) {
       un = (j == 1) ? uabs(i) : uabn(i);
@@ -267,9 +267,9 @@ struct ExtStepK : KBase {
                      +alpha*(elb00-elbS+ef-efS)
                      +o(EATM,0,0)-o(EATM,0,-1))
                  +dry0+ar*(wvs0-wvb0);
-        vn=((h00+elb00+hS+elbS)*ar*o(VAB,0,0)
-            -4.*dte*r)
-           /((h00+ef+hS+efS)*ar);
+        vn=pdiv((h00+elb00+hS+elbS)*ar*o(VAB,0,0)
+                -4.*dte*r,
+                (h00+ef+hS+efS)*ar);
       }
     } else if (jin) {
       vn = (i == 1) ? vabw(j) : vabe(j);
