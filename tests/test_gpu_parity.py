@@ -245,6 +245,22 @@ def test_direct_load_fallback_equals_tma_path(monkeypatch):
         assert np.array_equal(a.get(n), b.get(n)), n
 
 
+@pytest.mark.parametrize("dims", [(320, 296, 41), (130, 120, 61), (282, 306, 40)], ids=lambda d: "x".join(map(str, d)))
+def test_persistent_tma_kernels_equal_direct_load_path_at_scale(dims, monkeypatch):
+    """The persistent parked uv_filter (pom_tma.h: tmaparkkernel; several tiles per block, ring stages re-used,
+    32x6 tiles at kb=41 / 32x4 at kb=61, a partial last TMA box at kb=40) and the other TMA-staged kernels against
+    the direct-load path of the same functors (POMGPU_NO_TMA=1: two-sweep uv_filter), every field, every bit."""
+    nstep = 3
+    _, a = syn.seamount(*dims, _factory, island=True)
+    monkeypatch.setenv("POMGPU_NO_TMA", "1")
+    _, b = syn.seamount(*dims, _factory, island=True)
+    monkeypatch.delenv("POMGPU_NO_TMA")
+    for i in range(1, nstep + 1):
+        a.step(i); b.step(i)
+    for n in pc.F3 + pc.F2:
+        assert np.array_equal(a.get(n), b.get(n)), n
+
+
 def test_push_of_u_v_between_steps():
     pc.check_push_midrun(_factory)
 
