@@ -657,14 +657,16 @@ struct AdvT2K : KBase {
   }
   static constexpr int NV = 4 * NT, HL = 0, HR = 1, HB = 0, HT = 1, TY = POM_TILE_TY, MINB = POM_TILE_MINB;
   // operands staged by the TMA: box = thread tile + one column W and one row S (34 x 17)
-  static constexpr int NF = 2 * NT + 4, NS = POM_TILE_NS, OHL = 1, OHR = 0, OHB = 1, OHT = 0, BW = 34, BH = TY + 1, NK = 0;
+  static constexpr int NF = UPW ? 2 * NT + 4 : 2 * NT + 1;   // (the diffusion-only pass reads no u, v, w)
+  static constexpr int NS = POM_TILE_NS, OHL = 1, OHR = 0, OHB = 1, OHT = 0, BW = 34, BH = TY + 1, NK = 0;
   static constexpr bool UP = true;
   static constexpr bool FULL = true;   // stage() may run for every thread and assigns every v[]
   enum { AAM = 2 * NT, U, V, W };     // FB(t) = 2t, FC(t) = 2t+1
   enum { XF, YF, XD, YD };            // + 4t
   POM_HD void fields(const double** b) const {
     for (int t = 0; t < NT; ++t) { b[2 * t] = fb_[t]; b[2 * t + 1] = fc_[t]; }
-    b[AAM] = p.aam; b[U] = p.u; b[V] = p.v; b[W] = p.w;
+    b[AAM] = p.aam;
+    if (UPW) { b[U] = p.u; b[V] = p.v; b[W] = p.w; }
   }
   struct State {
     double cx, cy, hx, hy, dumc, dvmc, dys, dxs;   // .25*(dy+dy)*(dt+dt), (h+h), masks, (dy+dy(i-1)), (dx+dx(j-1))
@@ -769,121 +771,151 @@ struct AdvT2K : KBase {
 // iterations need the anti-diffusive mass fluxes and the previous iterate as arrays, so the
 // scheme runs as mass -> { upwind step -> smol_adif } x nitera -> diffusion on three scratch
 // flux fields (xm, ym, zw) and a ping-pong pair for the iterate.
-// xmassflux, ymassflux (:602-616), zwflux=w (:621)
-struct AdvT2MassK : KBase {
-  POM_KINFO("advt2_mass", 3, 3, 4, 0)
-  double *xm_, *ym_, *zw_;
-  AdvT2MassK(const Ctx* x, double* xm, double* ym, double* zw) : KBase(x), xm_(xm), ym_(ym), zw_(zw) {}
-  POM_HD void operator()(int i, int j) const {
-    POM_DIMS;
-    const bool fx = (i >= 2 && j >= 2 && j <= jmm1), fy = (i >= 2 && i <= imm1 && j >= 2);
-    const double cx = fx ? 0.25*(dy(i-1,j)+dy(i,j))*(dt(i-1,j)+dt(i,j)) : 0.;
-    const double cy = fy ? 0.25*(dx(i,j-1)+dx(i,j))*(dt(i,j-1)+dt(i,j)) : 0.;
-    for (int k = 1; k <= kb; ++k) {
-      A3(xm_,i,j,k)=(fx && k <= kbm1) ? cx*u(i,j,k) : 0.;
-      A3(ym_,i,j,k)=(fy && k <= kbm1) ? cy*v(i,j,k) : 0.;
-      A3(zw_,i,j,k)=w(i,j,k);
-    }
-  }
-};
-
-// one upwind step (:628-677) followed by the mask of smol_adif (:1898-1900).  `stale` is what
-// the reference's ff array holds where the step does not assign it (boundary columns, level kb)
-struct AdvT2UpK : KBase {
+// One upwind step (:628-677) followed by the mask of smol_adif (:1898-1900), and smol_adif's anti-diffusive
+// mass fluxes (:1903-1964), as TMA column kernels (pom_tma.h: tmacolkernel): the iterate and the three mass-flux
+// fields of every level staged with the neighbours the fluxes need.  `stale` is what the reference's ff array
+// holds where the step does not assign it (boundary columns, level kb).  In the FIRST iteration the mass fluxes
+// are those of :602-621 -- 0.25*(dy+dy)*(dt+dt)*u, 0.25*(dx+dx)*(dt+dt)*v, w -- and are formed on the fly from
+// the staged u, v, w (same expressions), so that no mass-flux kernel and no round trip of three 3-D arrays is
+// needed; smol_adif then leaves its anti-diffusive fluxes in xm, ym, zw for the next iteration.
+#ifndef POM_SMOL_TY
+#define POM_SMOL_TY 4
+#define POM_SMOL_MINB 6
+#define POM_SMOL_NS 4
+#endif
+struct AdvT2UpTK : KBase {
   POM_KINFO("advt2_up", 4, 1, 6, 0)
   const double *fbm_, *f_, *xm_, *ym_, *zw_, *stale_;
   double* ff_;
   int first;
-  AdvT2UpK(const Ctx* x, const double* fbm, const double* f, const double* xm, const double* ym, const double* zw,
-           const double* stale, double* ff, int fst)
+  AdvT2UpTK(const Ctx* x, const double* fbm, const double* f, const double* xm, const double* ym, const double* zw,
+            const double* stale, double* ff, int fst)
       : KBase(x), fbm_(fbm), f_(f), xm_(xm), ym_(ym), zw_(zw), stale_(stale), ff_(ff), first(fst) {}
-  POM_HD double xfl(int i, int j, int k) const {
-    const double m=A3(xm_,i,j,k);
-    return 0.5*((m+fabs(m))*A3(fbm_,i-1,j,k)+(m-fabs(m))*A3(fbm_,i,j,k));       // :631-635
+  static constexpr int TY = POM_SMOL_TY, MINB = POM_SMOL_MINB;
+  static constexpr int NF = 4, NS = POM_SMOL_NS, OHL = 1, OHR = 1, OHB = 1, OHT = 1, BW = 36, BH = TY + 2, NK = 0;
+  static constexpr bool UP = true;
+  static constexpr int NVEC = 1;   // (unused)
+  enum { FBM, XM, YM, ZW };
+  POM_HD void fields(const double** b) const {
+    b[FBM] = fbm_; b[XM] = first ? p.u : xm_; b[YM] = first ? p.v : ym_; b[ZW] = first ? p.w : zw_;
   }
-  POM_HD double yfl(int i, int j, int k) const {
-    const double m=A3(ym_,i,j,k);
-    return 0.5*((m+fabs(m))*A3(fbm_,i,j-1,k)+(m-fabs(m))*A3(fbm_,i,j,k));       // :637-641
-  }
-  POM_HD void operator()(int i, int j) const {
+  struct State { double m, ar, hb, zk, cxC, cxE, cyC, cyN; RDiv dhf; bool interior; };
+  POM_HD int k0() const { return 1; }
+  POM_HD int k1() const { return g.kb - 1; }
+  POM_HD int kl1() const { return g.kb - 1; }
+  template <class CM>
+  POM_HD void pre(int i, int j, State& s, CM&) const {
     POM_DIMS;
-    const double m=fsm(i,j);
-    if (!(i >= 2 && i <= imm1 && j >= 2 && j <= jmm1)) {
-      for (int k = 1; k <= kb; ++k) A3(ff_,i,j,k)=A3(stale_,i,j,k)*m;
-      return;
-    }
-    const double ar=art(i,j);
+    s.m=fsm(i,j);
+    s.interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
+    if (!s.interior) return;
+    s.ar=art(i,j);
     const double eta=first ? etb(i,j) : etf(i,j);                        // :620,684
-    const double hb=(h(i,j)+eta)*ar;
-    RDiv dhf; dhf.set((h(i,j)+etf(i,j))*ar);
-    double zk=first ? w(i,j,1)*A3(f_,i,j,1)*ar : 0.;                     // :646-650
-    for (int k = 1; k <= kbm1; ++k) {
-      double zk1 = 0.;                                                   // :651
-      if (k + 1 <= kbm1) {
-        const double zw1=A3(zw_,i,j,k+1);
-        zk1=0.5*((zw1+fabs(zw1))*A3(fbm_,i,j,k+1)+(zw1-fabs(zw1))*A3(fbm_,i,j,k));   // :656-660
-        zk1=zk1*ar;                                                      // :661
-      }
-      double q=xfl(i+1,j,k)-xfl(i,j,k)+yfl(i,j+1,k)-yfl(i,j,k)+pdiv(zk-zk1,dz(k));   // :670-672
-      q=dhf(A3(fbm_,i,j,k)*hb-dti2*q);                                   // :673-674
-      A3(ff_,i,j,k)=q*m;                                                 // smol_adif :1899
-      zk=zk1;
+    s.hb=(h(i,j)+eta)*s.ar;
+    s.dhf.set((h(i,j)+etf(i,j))*s.ar);
+    s.zk=first ? w(i,j,1)*A3(f_,i,j,1)*s.ar : 0.;                        // :646-650
+    if (first) {                                                         // :605-606, :612-613 at (i,j), (i+1,j), (i,j+1)
+      s.cxC=0.25*(dy(i-1,j)+dy(i,j))*(dt(i-1,j)+dt(i,j));
+      s.cxE=0.25*(dy(i,j)+dy(i+1,j))*(dt(i,j)+dt(i+1,j));
+      s.cyC=0.25*(dx(i,j-1)+dx(i,j))*(dt(i,j-1)+dt(i,j));
+      s.cyN=0.25*(dx(i,j)+dx(i,j+1))*(dt(i,j)+dt(i,j+1));
     }
-    A3(ff_,i,j,kb)=A3(stale_,i,j,kb)*m;
+  }
+  template <class Op, class CM>
+  POM_HD void level(int i, int j, int k, State& s, CM&, const Op& o) const {
+    POM_DIMS;
+    if (!s.interior) { A3(ff_,i,j,k)=A3(stale_,i,j,k)*s.m; return; }
+    const double f0=o(FBM,0,0);
+    double zk1 = 0.;                                                     // :651
+    if (k + 1 <= kbm1) {
+      const double zw1=o.up(ZW);
+      zk1=0.5*((zw1+fabs(zw1))*o.up(FBM)+(zw1-fabs(zw1))*f0);            // :656-660
+      zk1=zk1*s.ar;                                                      // :661
+    }
+    const double mE=first ? s.cxE*o(XM,1,0) : o(XM,1,0), mC=first ? s.cxC*o(XM,0,0) : o(XM,0,0);
+    const double nN=first ? s.cyN*o(YM,0,1) : o(YM,0,1), nC=first ? s.cyC*o(YM,0,0) : o(YM,0,0);
+    const double xE=0.5*((mE+fabs(mE))*f0+(mE-fabs(mE))*o(FBM,1,0));     // :631-635 at i+1
+    const double xC=0.5*((mC+fabs(mC))*o(FBM,-1,0)+(mC-fabs(mC))*f0);
+    const double yN=0.5*((nN+fabs(nN))*f0+(nN-fabs(nN))*o(FBM,0,1));     // :637-641 at j+1
+    const double yC=0.5*((nC+fabs(nC))*o(FBM,0,-1)+(nC-fabs(nC))*f0);
+    double q=xE-xC+yN-yC+pdiv(s.zk-zk1,dz(k));                           // :670-672
+    q=s.dhf(f0*s.hb-dti2*q);                                             // :673-674
+    A3(ff_,i,j,k)=q*s.m;                                                 // smol_adif :1899
+    s.zk=zk1;
+  }
+  template <class CM>
+  POM_HD void post(int i, int j, State& s, CM&) const {
+    const int kb = g.kb;
+    A3(ff_,i,j,kb)=A3(stale_,i,j,kb)*s.m;
   }
 };
 
-// smol_adif (:1903-1964): anti-diffusive mass fluxes from the masked iterate, in place
-struct SmolAdifK : KBase {
+struct SmolAdifTK : KBase {
   POM_KINFO("smol_adif", 4, 3, 4, 0)
   const double* ff_;
   double *xm_, *ym_, *zw_;
-  SmolAdifK(const Ctx* x, const double* ff, double* xm, double* ym, double* zw) : KBase(x), ff_(ff), xm_(xm), ym_(ym), zw_(zw) {}
-  POM_HD void operator()(int i, int j) const {
-    POM_DIMS;
-    const double value_min = 1.e-9, epsilon = 1.0e-14;
-    const bool fx = (i >= 2 && j >= 2 && j <= jmm1), fy = (i >= 2 && i <= imm1 && j >= 2);
-    const bool fz = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
-    // divisors that do not change along k (:1913,1934): hoisted reciprocals, exact quotients (RDiv).
-    // Every flux is evaluated and then selected (no data-dependent branches in the k loop).
-    RDiv dax, day;
-    dax.set(fx ? aru(i,j)*(dt(i-1,j)+dt(i,j)) : 1.);
-    day.set(fy ? arv(i,j)*(dt(i,j-1)+dt(i,j)) : 1.);
-    const double dtc=dt(i,j);
-    const int iw = fx ? i - 1 : i, js = fy ? j - 1 : j;
-    double fU = 0.;
-    for (int k = 1; k <= kbm1; ++k) {
-      const double f0=A3(ff_,i,j,k);
-      if (fx) {                                                          // :1903-1922
-        const double fW=A3(ff_,iw,j,k), xm=A3(xm_,i,j,k);
-        const double udx=fabs(xm);
-        const double u2dt=dax(dti2*xm*xm*2.);
-        const double mol=pdiv(f0-fW,fW+f0+epsilon);
-        double r=(udx-u2dt)*mol*sw;
-        r=(fabs(udx) < fabs(u2dt)) ? 0. : r;
-        A3(xm_,i,j,k)=(f0 < value_min || fW < value_min) ? 0. : r;
-      }
-      if (fy) {                                                          // :1924-1943
-        const double fS=A3(ff_,i,js,k), ym=A3(ym_,i,j,k);
-        const double vdy=fabs(ym);
-        const double v2dt=day(dti2*ym*ym*2.);
-        const double mol=pdiv(f0-fS,fS+f0+epsilon);
-        double r=(vdy-v2dt)*mol*sw;
-        r=(fabs(vdy) < fabs(v2dt)) ? 0. : r;
-        A3(ym_,i,j,k)=(f0 < value_min || fS < value_min) ? 0. : r;
-      }
-      if (fz && k >= 2) {                                                // :1945-1964
-        const double zw=A3(zw_,i,j,k);
-        const double wdz=fabs(zw);
-        const double w2dt=pdiv(dti2*zw*zw,dzz(k-1)*dtc);
-        const double mol=pdiv(fU-f0,f0+fU+epsilon);
-        double r=(wdz-w2dt)*mol*sw;
-        r=(fabs(wdz) < fabs(w2dt)) ? 0. : r;
-        A3(zw_,i,j,k)=(f0 < value_min || fU < value_min) ? 0. : r;
-      }
-      fU=f0;
-    }
+  int first;   // the incoming mass fluxes are those of :602-621, formed here from u, v, w
+  SmolAdifTK(const Ctx* x, const double* ff, double* xm, double* ym, double* zw, int fst)
+      : KBase(x), ff_(ff), xm_(xm), ym_(ym), zw_(zw), first(fst) {}
+  static constexpr int TY = POM_SMOL_TY, MINB = POM_SMOL_MINB;
+  static constexpr int NF = 4, NS = POM_SMOL_NS, OHL = 1, OHR = 0, OHB = 1, OHT = 0, BW = 34, BH = TY + 1, NK = 0;
+  static constexpr bool UP = false;
+  static constexpr int NVEC = 1;   // (unused)
+  enum { FF, XM, YM, ZW };
+  POM_HD void fields(const double** b) const {
+    b[FF] = ff_; b[XM] = first ? p.u : xm_; b[YM] = first ? p.v : ym_; b[ZW] = first ? p.w : zw_;
   }
+  struct State { RDiv dax, day; double dtc, fU, cx, cy; bool fx, fy, fz; };
+  POM_HD int k0() const { return 1; }
+  POM_HD int k1() const { return g.kb - 1; }
+  POM_HD int kl1() const { return g.kb - 1; }
+  template <class CM>
+  POM_HD void pre(int i, int j, State& s, CM&) const {
+    POM_DIMS;
+    s.fx = (i >= 2 && j >= 2 && j <= jmm1); s.fy = (i >= 2 && i <= imm1 && j >= 2);
+    s.fz = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
+    s.dax.set(s.fx ? aru(i,j)*(dt(i-1,j)+dt(i,j)) : 1.);
+    s.day.set(s.fy ? arv(i,j)*(dt(i,j-1)+dt(i,j)) : 1.);
+    s.dtc=dt(i,j);
+    s.fU = 0.;
+    s.cx = (first && s.fx) ? 0.25*(dy(i-1,j)+dy(i,j))*(dt(i-1,j)+dt(i,j)) : 0.;   // :605-606
+    s.cy = (first && s.fy) ? 0.25*(dx(i,j-1)+dx(i,j))*(dt(i,j-1)+dt(i,j)) : 0.;   // :612-613
+  }
+  template <class Op, class CM>
+  POM_HD void level(int i, int j, int k, State& s, CM&, const Op& o) const {
+    const double value_min = 1.e-9, epsilon = 1.0e-14;
+    const double f0=o(FF,0,0);
+    if (s.fx) {                                                          // :1903-1922
+      const double fW=o(FF,-1,0), xm=first ? s.cx*o(XM,0,0) : o(XM,0,0);
+      const double udx=fabs(xm);
+      const double u2dt=s.dax(dti2*xm*xm*2.);
+      const double mol=pdiv(f0-fW,fW+f0+epsilon);
+      double r=(udx-u2dt)*mol*sw;
+      r=(fabs(udx) < fabs(u2dt)) ? 0. : r;
+      A3(xm_,i,j,k)=(f0 < value_min || fW < value_min) ? 0. : r;
+    }
+    if (s.fy) {                                                          // :1924-1943
+      const double fS=o(FF,0,-1), ym=first ? s.cy*o(YM,0,0) : o(YM,0,0);
+      const double vdy=fabs(ym);
+      const double v2dt=s.day(dti2*ym*ym*2.);
+      const double mol=pdiv(f0-fS,fS+f0+epsilon);
+      double r=(vdy-v2dt)*mol*sw;
+      r=(fabs(vdy) < fabs(v2dt)) ? 0. : r;
+      A3(ym_,i,j,k)=(f0 < value_min || fS < value_min) ? 0. : r;
+    }
+    if (s.fz && k >= 2) {                                                // :1945-1964
+      const double zw=o(ZW,0,0);
+      const double wdz=fabs(zw);
+      const double w2dt=pdiv(dti2*zw*zw,dzz(k-1)*s.dtc);
+      const double mol=pdiv(s.fU-f0,f0+s.fU+epsilon);
+      double r=(wdz-w2dt)*mol*sw;
+      r=(fabs(wdz) < fabs(w2dt)) ? 0. : r;
+      A3(zw_,i,j,k)=(f0 < value_min || s.fU < value_min) ? 0. : r;
+    }
+    s.fU=f0;
+  }
+  template <class CM>
+  POM_HD void post(int, int, State&, CM&) const {}
 };
 
 // advt1 (solver.f:480-574): centred advection + diffusion of (fb-fclim)
@@ -1916,15 +1948,12 @@ void run_advt(Ctx* c, int nadv, const double* fb, const double* f, const double*
 }
 // advt2 of T (-> uf) and S (-> vf) in one pass (nitera=1)
 void run_advt2_ts(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvT2K<2>(c), ALLI, j0, j1); }
-void run_advt2_mass(Ctx* c, double* xm, double* ym, double* zw, int j0, int j1) {
-  launch_cols(c, AdvT2MassK(c, xm, ym, zw), ALLI, j0, j1);
-}
 void run_advt2_up(Ctx* c, const double* fbm, const double* f, const double* xm, const double* ym, const double* zw,
                   const double* stale, double* ff, int first, int j0, int j1) {
-  launch_cols(c, AdvT2UpK(c, fbm, f, xm, ym, zw, stale, ff, first), ALLI, j0, j1);
+  launch_tma_cols(c, AdvT2UpTK(c, fbm, f, xm, ym, zw, stale, ff, first), ALLI, j0, j1);
 }
-void run_smol_adif(Ctx* c, const double* ff, double* xm, double* ym, double* zw, int j0, int j1) {
-  launch_cols(c, SmolAdifK(c, ff, xm, ym, zw), ALLI, j0, j1);
+void run_smol_adif(Ctx* c, const double* ff, double* xm, double* ym, double* zw, int first, int j0, int j1) {
+  launch_tma_cols(c, SmolAdifTK(c, ff, xm, ym, zw, first), ALLI, j0, j1);
 }
 void run_advt2_diff(Ctx* c, const double* fb, const double* fc, double* ff, int j0, int j1) {
   launch_tma_tiles(c, AdvT2K<1, false>(c, fb, fb, fc, ff), ALLI, j0, j1);   // the tile kernel's diffusion half

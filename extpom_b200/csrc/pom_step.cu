@@ -36,10 +36,9 @@ void run_profq(Ctx*, int fuse_filter, int, int);
 void run_qfilter(Ctx*, int, int);
 void run_advt(Ctx*, int nadv, const double* fb, const double* f, const double* fc, double* ff, int, int);
 void run_fb_roundtrip(Ctx*, double* fb, const double* fc, double* f, int, int);
-void run_advt2_mass(Ctx*, double* xm, double* ym, double* zw, int, int);
 void run_advt2_up(Ctx*, const double* fbm, const double* f, const double* xm, const double* ym, const double* zw,
                   const double* stale, double* ff, int first, int, int);
-void run_smol_adif(Ctx*, const double* ff, double* xm, double* ym, double* zw, int, int);
+void run_smol_adif(Ctx*, const double* ff, double* xm, double* ym, double* zw, int first, int, int);
 void run_advt2_diff(Ctx*, const double* fb, const double* fc, double* ff, int, int);
 void run_proft(Ctx*, double* f, const double* wf, const double* fs, int nbc, int, int);
 void run_tsfilter(Ctx*, int with_dens, int, int);
@@ -264,29 +263,27 @@ static void k_qfilter(Group* G) {
   MADE(e, F_uf, F_vf, F_q2b, F_q2lb);
   group_swap(G, F_q2, F_uf); group_swap(G, F_q2l, F_vf);   // advance.f:418-421
 }
-// advt2 with nitera > 1 (solver.f:625-687): mass fluxes, then { upwind step + mask, smol_adif }
+// advt2 with nitera > 1 (solver.f:625-687): { upwind step + mask, smol_adif }
 // per iteration on scratch fields, then the diffusion.  `stale` = the field whose values the
 // reference's ff array holds where the scheme never assigns it (boundary columns, level kb):
 // in the step that is the new q2 / q2l, which `q2=uf` left in uf (advance.f:419-421).
 static void k_advt2_iter(Group* G, int fb, int f, int fc, int ff, int stale) {
   const int XM = F_s3c, YM = F_s3d, ZW = F_s3e, PING = F_s3a;
   const int nitera = G->c[0]->c.nitera;
-  {
-    int e = NEED({F_u, 0}, {F_v, 0}, {F_w, 0}, {F_dt, 1});
-    EACH(run_advt2_mass(c, FP(c, XM), FP(c, YM), FP(c, ZW), j0, j1));
-    MADE(e, XM, YM, ZW);
-  }
+  // (first iteration: the mass fluxes of :602-621 are formed inside the kernels from u, v, w)
   int src = fb;
   for (int it = 1; it <= nitera; ++it) {
     const int dst = ((nitera - it) % 2 == 0) ? ff : PING;   // the last iterate lands in ff
+    const int first = (it == 1);
+    const int fx = first ? F_u : XM, fy = first ? F_v : YM, fz = first ? F_w : ZW;
     {
-      int e = NEED({src, 1}, {f, 0}, {XM, 0}, {YM, 1}, {ZW, 0}, {stale, 0}, {F_w, 0}, {F_etb, 0}, {F_etf, 0});
-      EACH(run_advt2_up(c, FP(c, src), FP(c, f), FP(c, XM), FP(c, YM), FP(c, ZW), FP(c, stale), FP(c, dst), it == 1, j0, j1));
+      int e = NEED({src, 1}, {f, 0}, {fx, 0}, {fy, 1}, {fz, 0}, {stale, 0}, {F_w, 0}, {F_dt, 1}, {F_etb, 0}, {F_etf, 0});
+      EACH(run_advt2_up(c, FP(c, src), FP(c, f), FP(c, XM), FP(c, YM), FP(c, ZW), FP(c, stale), FP(c, dst), first, j0, j1));
       MADE(e, dst);
     }
     if (it < nitera) {   // the fluxes after the last iteration are never used
-      int e = NEED({dst, 1}, {XM, 0}, {YM, 0}, {ZW, 0}, {F_dt, 1});
-      EACH(run_smol_adif(c, FP(c, dst), FP(c, XM), FP(c, YM), FP(c, ZW), j0, j1));
+      int e = NEED({dst, 1}, {fx, 0}, {fy, 0}, {fz, 0}, {F_dt, 1});
+      EACH(run_smol_adif(c, FP(c, dst), FP(c, XM), FP(c, YM), FP(c, ZW), first, j0, j1));
       MADE(e, XM, YM, ZW);
     }
     src = dst;
@@ -835,7 +832,7 @@ int pomgpu_smol_adif(pomgpu_t* p, const char* xm, const char* ym, const char* zw
   int a = fid(xm), b = fid(ym), w = fid(zw), o = fid(ff);
   if (a < 0 || b < 0 || w < 0 || o < 0) return 2;
   run_mask_fsm(c, FP(c, o), 1, c->g.jmg);
-  run_smol_adif(c, FP(c, o), FP(c, a), FP(c, b), FP(c, w), 1, c->g.jmg);
+  run_smol_adif(c, FP(c, o), FP(c, a), FP(c, b), FP(c, w), 0, 1, c->g.jmg);
   return 0;
 }
 // advq(qb,q,qf) (solver.f:411-477) for ONE quantity: the device kernel advances q2 and q2l together

@@ -10,6 +10,14 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 from extpom_b200 import synthetic as syn  # noqa: E402
 from extpom_b200.pomgpu import PomGpu  # noqa: E402
+if os.environ.get("POMGPU_LIB"):           # a variant build of the CUDA library, for A/B timing (developer tool)
+    from extpom_b200 import pomgpu as _pg
+    _lib = os.environ["POMGPU_LIB"]
+
+    class PomGpu(_pg.PomGpu):             # noqa: F811
+        @staticmethod
+        def _library():
+            return _pg._lib(_lib)
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 kb = int(sys.argv[2]) if len(sys.argv) > 2 else 41
