@@ -70,6 +70,7 @@ def test_strips_equal_single_domain_bitwise(nstrips, ghost):
     # the reference does 29 3-D + 340 2-D exchanges per step
     print(f"{nstrips} strips ghost {ghost}: {nex / nstep:.1f} batched exchanges/step, {nfields / nstep:.0f} field-rows sets")
     assert 0 < nex / nstep < 369
+    assert grp.transport() == "device copies"             # pomgpu_group_transport: strips of one process
 
 
 @pytest.mark.parametrize("kw", [{"nadv": 1}, {"mode": 4}, {"nbct": 2, "ntp": 3}, {"nitera": 3, "sw": 1.0}, {"mode": 2}, {"npg": 2}])
@@ -109,6 +110,7 @@ def test_failing_transport_stops_the_step_and_keeps_the_error():
     def broken(*_):
         raise RuntimeError("link down")
     grp.set_transport(broken)
+    assert grp.transport() == "host callback"
     for attempt in range(2):
         with pytest.raises(Exception):
             for i in range(1, 4):
