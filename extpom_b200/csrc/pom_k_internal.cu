@@ -10,9 +10,6 @@
 
 // min blocks/SM of the plain column kernels whose occupancy (not traffic) limits them: capping
 // them at 64 registers (4 x 256 threads) was measured at 0.43 -> 0.28 ms for realvertvl
-#ifndef POM_RV_MINB
-#define POM_RV_MINB 4
-#endif
 #ifndef POM_PROFT_MINB
 #define POM_PROFT_MINB 4
 #endif
@@ -108,53 +105,8 @@ struct VertvlK : KBase {
 // velocity of the east / north neighbour that vertvl's flux difference needs is a point-wise
 // expression, so u, v are read once (2R+3W instead of 6+3 passes).  The adjusted fields go to
 // s3a, s3b (neighbours still read the raw u, v); the caller swaps the buffers.
-struct UvAdjVertvlK : KBase {
-  POM_KINFO("uvadjust_vertvl", 2, 3, 14, 0)
-  using KBase::KBase;
-  POM_HD void operator()(int i, int j) const {
-    POM_DIMS;
-    const double m = fsm(i,j);
-    const bool interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
-    const bool au = (i >= 2), av = (j >= 2);                              // :373, :386
-    const double tu=A2(p.s2c,i,j), tv=A2(p.s2d,i,j);
-    const double ru = au ? (utb(i,j)+utf(i,j))/(dt(i,j)+dt(i-1,j)) : 0.;
-    const double rv = av ? (vtb(i,j)+vtf(i,j))/(dt(i,j)+dt(i,j-1)) : 0.;
-    double tuE = 0., ruE = 0., tvN = 0., rvN = 0., wk = 0., de = 0., cW = 0., cE = 0., cS = 0., cN = 0.;
-    RDiv ddxy; ddxy.set(interior ? dx(i,j)*dy(i,j) : 1.);
-    if (interior) {
-      tuE=A2(p.s2c,i+1,j); ruE=(utb(i+1,j)+utf(i+1,j))/(dt(i+1,j)+dt(i,j));
-      tvN=A2(p.s2d,i,j+1); rvN=(vtb(i,j+1)+vtf(i,j+1))/(dt(i,j+1)+dt(i,j));
-      wk=0.5*(vfluxb(i,j)+vfluxf(i,j));                                 // solver.f:2004
-      de=(etf(i,j)-etb(i,j))/dti2;
-      cW=.25*(dy(i,j)+dy(i-1,j))*(dt(i,j)+dt(i-1,j));                   // :1984-1985,1993-1994
-      cE=.25*(dy(i+1,j)+dy(i,j))*(dt(i+1,j)+dt(i,j));
-      cS=.25*(dx(i,j)+dx(i,j-1))*(dt(i,j)+dt(i,j-1));
-      cN=.25*(dx(i,j+1)+dx(i,j))*(dt(i,j+1)+dt(i,j));
-    }
-    const int ie = interior ? i + 1 : i, jn = interior ? j + 1 : j;
-    for (int k = 1; k <= kbm1; ++k) {
-      PF3(p.u,i,j,k+3); PF3(p.v,i,j,k+3); PF3(p.v,i,jn,k+3);
-      const double u0=u(i,j,k), v0=v(i,j,k);
-      const double ua = au ? (u0-tu)+ru : u0;                           // advance.f:374-375
-      const double va = av ? (v0-tv)+rv : v0;                           // :387-388
-      A3(p.s3a,i,j,k)=ua;
-      A3(p.s3b,i,j,k)=va;
-      if (interior) {
-        const double uE=(u(ie,j,k)-tuE)+ruE, vN=(v(i,jn,k)-tvN)+rvN;
-        w(i,j,k)=wk*m;                                                  // bounds_forcing.f:553-559
-        wk=wk+dz(k)*(ddxy(cE*uE-cW*ua+cN*vN-cS*va)+de);                 // solver.f:2011-2015
-      } else {
-        w(i,j,k)=w(i,j,k)*m;
-      }
-    }
-    A3(p.s3a,i,j,kb)=u(i,j,kb);
-    A3(p.s3b,i,j,kb)=v(i,j,kb);
-    if (interior) w(i,j,kb)=wk;
-  }
-};
-
-// The same sweep on the TMA ring (pom_tma.h: tmacolkernel): u, v of every level staged with their east / north
-// neighbours, two or more levels ahead.  Same expressions as UvAdjVertvlK.
+// A TMA column kernel (pom_tma.h: tmacolkernel): u, v of every level staged with their east / north neighbours,
+// two or more levels ahead (plain-load column kernel: 0.38 against 0.32 ms).
 #ifndef POM_UVADJ_TY
 #define POM_UVADJ_TY 4
 #define POM_UVADJ_MINB 8
@@ -1740,46 +1692,8 @@ struct EndStep2dK : KBase {
   }
 };
 
-// realvertvl (solver.f:2024-2066)
-struct RealvertvlK : KBase {
-  POM_KINFO("realvertvl", 3, 1, 7, 0)
-  using KBase::KBase;
-  POM_HD void operator()(int i, int j) const {
-    POM_DIMS;
-    // edge copies S,N then W,E (:2057-2060) = value at the index clamped inside
-    const int ic = i < 2 ? 2 : (i > imm1 ? imm1 : i);
-    const int jc = j < 2 ? 2 : (j > jmm1 ? jmm1 : j);
-    const double m=fsm(i,j);
-    // the 2-D operands of the column, hoisted out of the k loop (:2036,2041-2044)
-    const double dxr=2.0/(dx(ic+1,jc)+dx(ic,jc));
-    const double dxl=2.0/(dx(ic,jc)+dx(ic-1,jc));
-    const double dyt=2.0/(dy(ic,jc+1)+dy(ic,jc));
-    const double dyb=2.0/(dy(ic,jc)+dy(ic,jc-1));
-    const double dt0=dt(ic,jc), dtE=dt(ic+1,jc), dtW=dt(ic-1,jc), dtN=dt(ic,jc+1), dtS=dt(ic,jc-1);
-    const double et0=et(ic,jc), etE=et(ic+1,jc), etW=et(ic-1,jc), etN=et(ic,jc+1), etS=et(ic,jc-1);
-    const double de=etf(ic,jc)-etb(ic,jc);
-    RDiv ddti2; ddti2.set(dti2);
-    double w0=w(ic,jc,1);
-    for (int k = 1; k <= kbm1; ++k) {
-      PF3(p.w,ic,jc,k+3); PF3(p.u,ic,jc,k+2); PF3(p.v,ic,jc,k+2); PF3(p.v,ic,jc+1,k+2);
-      const double zk=zz(k);
-      const double tp0=zk*dt0+et0;                                      // :2036
-      const double w1=w(ic,jc,k+1);
-      const double r=0.5*(w0+w1)+0.5*
-           (u(ic+1,jc,k)*((zk*dtE+etE)-tp0)*dxr+
-            u(ic,jc,k)*(tp0-(zk*dtW+etW))*dxl+
-            v(ic,jc+1,k)*((zk*dtN+etN)-tp0)*dyt+
-            v(ic,jc,k)*(tp0-(zk*dtS+etS))*dyb)
-           +ddti2((1.0+zk)*de);                                         // :2045-2050
-      wr(i,j,k)=m*r;                                                    // :2063
-      w0=w1;
-    }
-    wr(i,j,kb)=0.;
-  }
-};
-
-// realvertvl on the TMA ring: w (levels k and k+1), u, v staged with the halo the clamped index needs (one point
-// west / south, two east / north).  Same expressions as RealvertvlK.
+// realvertvl (solver.f:2024-2066) as a TMA column kernel: w (levels k and k+1), u, v staged with the halo the
+// clamped index needs (one point west / south, two east / north).
 #ifndef POM_RVV_TY
 #define POM_RVV_TY 4
 #define POM_RVV_MINB 8
@@ -1924,11 +1838,7 @@ int domain_stats_rows(Ctx* c, double* rows) {
 #define ALLI 1, c->g.im
 void run_uvadjust(Ctx* c, int j0, int j1) { launch_cols(c, UvAdjustK(c), ALLI, j0, j1); }
 void run_vertvl(Ctx* c, int j0, int j1) { launch_cols(c, VertvlK(c), ALLI, j0, j1); }
-#ifdef POM_COLS_PLAIN   // the round-1 kernels on plain loads (A/B timing only)
-void run_uvadj_vertvl(Ctx* c, int j0, int j1) { launch_cols<UvAdjVertvlK, POM_RV_MINB>(c, UvAdjVertvlK(c), ALLI, j0, j1); }
-#else
 void run_uvadj_vertvl(Ctx* c, int j0, int j1) { launch_tma_cols(c, UvAdjVertvlTK(c), ALLI, j0, j1); }
-#endif
 void run_uvsum(Ctx* c, int j0, int j1) { launch_cols(c, UvSumK(c), ALLI, j0, j1); }
 void run_advq(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvqK(c), ALLI, j0, j1); }
 // the fused variant under its own name / algorithmic byte count in the per-kernel profile
@@ -1992,10 +1902,6 @@ void run_uvfilter(Ctx* c, int j0, int j1) {
   launch_cols(c, UvFilterK(c), ALLI, j0, j1);
 }
 void run_endstep2d(Ctx* c, int j0, int j1) { launch_cols(c, EndStep2dK(c), ALLI, j0, j1); }
-#ifdef POM_COLS_PLAIN
-void run_realvertvl(Ctx* c, int j0, int j1) { launch_cols<RealvertvlK, POM_RV_MINB>(c, RealvertvlK(c), ALLI, j0, j1); }
-#else
 void run_realvertvl(Ctx* c, int j0, int j1) { launch_tma_cols(c, RealvertvlTK(c), ALLI, j0, j1); }
-#endif
 
 }  // namespace pom

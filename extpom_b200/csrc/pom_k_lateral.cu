@@ -138,64 +138,8 @@ struct AdvctK : KBase {
 
 // solver.f:848-940.  rho is rewritten as (rho-rmean)+rmean (:854,937) into the
 // alternate buffer rho2 (neighbours still read the old rho); the caller swaps.
-struct BaropgK : KBase {
-  POM_KINFO("baropg", 2, 3, 5, 2)
-  using KBase::KBase;
-  POM_HD void operator()(int i, int j) const {
-    POM_DIMS;
-    const bool interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
-    double sx = 0., sy = 0.;
-    if (interior) {
-      const double dtx=dt(i,j)+dt(i-1,j), dty=dt(i,j)+dt(i,j-1);
-      const double ddx=dt(i,j)-dt(i-1,j), ddy=dt(i,j)-dt(i,j-1);
-      const double dyx=dy(i,j)+dy(i-1,j), dxy=dx(i,j)+dx(i,j-1);
-      // rho-rmean at (i,j),(i-1,j),(i,j-1), levels k-1 (a*) and k (b*)
-      const double rm1=rmean(i,j,1);
-      double a0=rho(i,j,1)-rm1;
-      rho2(i,j,1)=a0+rm1;                                               // :854,937 folded into the sweep
-      double ax=rho(i-1,j,1)-rmean(i-1,j,1);
-      double ay=rho(i,j-1,1)-rmean(i,j-1,1);
-      double px=.5*grav*(-zz(1))*dtx*(a0-ax);                          // :859-860
-      double py=.5*grav*(-zz(1))*dty*(a0-ay);                          // :895-896
-      for (int k = 1; k <= kbm1; ++k) {
-        PF3(p.rho,i,j,k+2); PF3(p.rmean,i,j,k+2); PF3(p.rho,i,j-1,k+2); PF3(p.rmean,i,j-1,k+2);
-        if (k >= 2) {
-          const double rmk=rmean(i,j,k);
-          double b0=rho(i,j,k)-rmk;
-          rho2(i,j,k)=b0+rmk;
-          double bx=rho(i-1,j,k)-rmean(i-1,j,k);
-          double by=rho(i,j-1,k)-rmean(i,j-1,k);
-          px=px+grav*.25*(zz(k-1)-zz(k))*dtx*(b0-bx+a0-ax)
-               +grav*.25*(zz(k-1)+zz(k))*ddx*(b0+bx-a0-ax);           // :867-875
-          py=py+grav*.25*(zz(k-1)-zz(k))*dty*(b0-by+a0-ay)
-               +grav*.25*(zz(k-1)+zz(k))*ddy*(b0+by-a0-ay);           // :903-911
-          a0=b0; ax=bx; ay=by;
-        }
-        double ox=ramp*(.25*dtx*px*dum(i,j)*dyx);                      // :883-885,931
-        double oy=ramp*(.25*dty*py*dvm(i,j)*dxy);                      // :919-921,932
-        drhox(i,j,k)=ox;
-        drhoy(i,j,k)=oy;
-        sx=sx+ox*dz(k);                                                 // advance.f:163-164
-        sy=sy+oy*dz(k);
-      }
-      drhox(i,j,kb)=ramp*drhox(i,j,kb);                                 // :928-932 (k=kb)
-      drhoy(i,j,kb)=ramp*drhoy(i,j,kb);
-      rho2(i,j,kb)=(rho(i,j,kb)-rmean(i,j,kb))+rmean(i,j,kb);
-    } else {
-      for (int k = 1; k <= kbm1; ++k) {  // edges keep their content (initialize.f:307-308)
-        sx=sx+drhox(i,j,k)*dz(k);
-        sy=sy+drhoy(i,j,k)*dz(k);
-      }
-      for (int k = 1; k <= kb; ++k)
-        rho2(i,j,k)=(rho(i,j,k)-rmean(i,j,k))+rmean(i,j,k);             // :854,937
-    }
-    drx2d(i,j)=sx;
-    dry2d(i,j)=sy;
-  }
-};
-
-// baropg on the TMA ring (pom_tma.h: tmacolkernel): rho and rmean of every level are staged with their west
-// and south neighbours, two or more levels ahead; same expressions as BaropgK.
+// A TMA column kernel (pom_tma.h: tmacolkernel): rho and rmean of every level are staged with their west and
+// south neighbours, two or more levels ahead (the plain-load column kernel of round 1 took 0.42 against 0.33 ms).
 #ifndef POM_BAROPG_TY
 #define POM_BAROPG_TY 4
 #define POM_BAROPG_MINB 8
@@ -340,38 +284,8 @@ struct BaropgMccK : KBase {
 };
 
 // advance.f:122-136 + aam2d (advance.f:165)
-struct SmagK : KBase {
-  POM_KINFO("smagorinsky", 2, 1, 2, 1)
-  using KBase::KBase;
-  POM_HD void operator()(int i, int j) const {
-    POM_DIMS;
-    const bool interior = (i >= 2 && i <= imm1 && j >= 2 && j <= jmm1);
-    double sa = 0.;
-    RDiv ddx, ddy;
-    double hdd = 0.;
-    if (interior) { ddx.set(dx(i,j)); ddy.set(dy(i,j)); hdd=horcon*dx(i,j)*dy(i,j); }
-    for (int k = 1; k <= kbm1; ++k) {
-      double a;
-      PF3(p.u,i,j,k+2); PF3(p.v,i,j,k+2);
-      if (interior) {
-        PF3(p.u,i,j+1,k+2); PF3(p.u,i,j-1,k+2); PF3(p.v,i,j+1,k+2);
-        double a1=ddx(u(i+1,j,k)-u(i,j,k));
-        double a2=ddy(v(i,j+1,k)-v(i,j,k));
-        double a3=ddy(.25*(u(i,j+1,k)+u(i+1,j+1,k)-u(i,j-1,k)-u(i+1,j-1,k)))
-                 +ddx(.25*(v(i+1,j,k)+v(i+1,j+1,k)-v(i-1,j,k)-v(i-1,j+1,k)));
-        a=hdd*sqrt(a1*a1+a2*a2+.5*(a3*a3));
-        aam(i,j,k)=a;
-      } else {
-        a=aam(i,j,k);
-      }
-      sa=sa+a*dz(k);
-    }
-    aam2d(i,j)=sa;
-  }
-};
-
-// The same arithmetic on the TMA ring (pom_tma.h: tmacolkernel): u, v of every level are staged with one
-// point of halo all around, two or more levels ahead, instead of ten dependent plain loads per cell.
+// A TMA column kernel (pom_tma.h: tmacolkernel): u, v of every level are staged with one point of halo all
+// around, two or more levels ahead, instead of ten dependent plain loads per cell (0.31 -> 0.22 ms).
 #ifndef POM_SMAG_TY
 #define POM_SMAG_TY 4
 #endif
@@ -423,19 +337,8 @@ struct SmagTK : KBase {
 
 void run_advct(Ctx* c, int j0, int j1) { launch_tma_tiles(c, AdvctK(c), 1, c->g.im, j0, j1); }
 // the caller swaps rho <-> rho2 afterwards
-#ifndef POM_RV_MINB
-#define POM_RV_MINB 4
-#endif
-#ifdef POM_BAROPG_PLAIN   // the round-1 kernel on plain loads (A/B timing only)
-void run_baropg(Ctx* c, int j0, int j1) { launch_cols<BaropgK, POM_RV_MINB>(c, BaropgK(c), 1, c->g.im, j0, j1); }
-#else
 void run_baropg(Ctx* c, int j0, int j1) { launch_tma_cols(c, BaropgTK(c), 1, c->g.im, j0, j1); }
-#endif
 void run_baropg_mcc(Ctx* c, int j0, int j1) { launch_cols(c, BaropgMccK(c), 1, c->g.im, j0, j1); }
-#ifdef POM_SMAG_PLAIN   // the round-1 kernel on plain loads (A/B timing only)
-void run_smag(Ctx* c, int j0, int j1) { launch_cols<SmagK, 1>(c, SmagK(c), 1, c->g.im, j0, j1); }
-#else
 void run_smag(Ctx* c, int j0, int j1) { launch_tma_cols(c, SmagTK(c), 1, c->g.im, j0, j1); }
-#endif
 
 }  // namespace pom
