@@ -7,6 +7,8 @@ import numpy as np
 from extpom_b200 import synthetic as syn
 from oracle.pomo import Oracle
 from scripts.make_golden import CASES
+from scripts.make_ref_golden import REF_CASES, ref_restore_setup
+from scripts import make_ref_golden as mrg
 from tests.common import F2, F3, RTOL, assert_close, compare, rel_err
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -333,3 +335,36 @@ def check_push_midrun(factory, dims=(24, 19, 9)):
     for i in range(4, 7):
         o.step(i); g.step(i)
     return assert_close(o, g)
+
+
+# ---- golden vectors from the reference's own source (scripts/make_ref_golden.py, oracle/f77ref.py) ------------
+REF_GOLDEN = sorted(REF_CASES)
+
+
+def check_ref_golden(factory, name, tol):
+    """A solver (C oracle, host-emulated or CUDA path) run on the case's state must reproduce the fields the
+    reference's own Fortran source produced (tests/golden/ref_<name>.npz); tol=0: bitwise."""
+    dims, steps, kw = REF_CASES[name]
+    gold = np.load(os.path.join(GOLD, f"ref_{name}.npz"))
+    st = syn.make_state(*dims, **kw)
+    g = factory(*dims)
+    g.load(st)
+    syn.finish_init(st, g)
+    ref_restore_setup(g, st)
+    for i in range(1, steps + 1):
+        g.step(i)
+    bad, worst = {}, 0.0
+    for n in mrg.F3 + mrg.F2:
+        if tol > 0 and n in ("uf", "vf"):      # work arrays, not state: the CUDA path rotates pointers instead of copying
+            continue
+        a, b = gold[n], g.get(n)
+        if n in ("t", "tb", "s", "sb", "uf", "vf") and a.ndim == 3:     # level kb is scratch (tests/common.py)
+            a, b = a[:, :, :-1], b[:, :, :-1]
+        e = rel_err(a, b) if tol > 0 else (0.0 if np.array_equal(a, b) else max(rel_err(a, b), 1e-300))
+        worst = max(worst, e)
+        if not (e <= tol):
+            bad[n] = e
+    assert not bad, f"{name}: fields differ from the reference's own output beyond {tol}: {bad}"
+    vr, vg = float(gold["vamax"]), g.check_velocity()
+    assert abs(vr - vg) <= max(tol, 0.0) * max(1.0, abs(vr)) + (0.0 if tol else 0.0)
+    return worst

@@ -34,6 +34,12 @@ def test_matches_golden(name):
     pc.check_golden(EmuPom, name)
 
 
+@pytest.mark.parametrize("name", pc.REF_GOLDEN)
+def test_matches_the_references_own_output(name):
+    """Host build of the CUDA kernel bodies against what the reference's own source computes (tests/golden/ref_*)."""
+    pc.check_ref_golden(EmuPom, name, tol=1e-11)
+
+
 def test_unsupported_switches_set_error_status():
     st, g = syn.seamount(20, 17, 8, EmuPom, npg=3)
     with pytest.raises(Exception):

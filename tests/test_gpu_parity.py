@@ -29,6 +29,13 @@ def test_routine_matches_oracle(routine):
     pc.check_routine(_factory, routine, (28, 22, 10))
 
 
+@pytest.mark.parametrize("name", pc.REF_GOLDEN)
+def test_cuda_path_matches_the_references_own_output(name):
+    """The CUDA path against the fields the reference's own Fortran source produced (tests/golden/ref_*.npz,
+    scripts/make_ref_golden.py + oracle/f77ref.py); 1e-11: the only non-identical operation is |S|**1.5."""
+    pc.check_ref_golden(_factory, name, tol=RTOL)
+
+
 @pytest.mark.parametrize("name", pc.GOLDEN)
 def test_matches_golden(name):
     pc.check_golden(_factory, name)
