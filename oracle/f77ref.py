@@ -26,6 +26,7 @@ import re
 import numpy as np
 
 REF_ROOT = os.environ.get("POM_REFERENCE", "/root/reference")
+LIVE_GRIDS = ((13, 11, 6), (16, 14, 7))     # grids of the live reference runs in tests/ (built into oracle/_ref by build())
 
 f8 = np.float64
 f4 = np.float32
@@ -722,12 +723,37 @@ class Translator:
         return src
 
 
+CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # built artefacts: git-ignored, travel with gpurun
+
+
 class Reference:
-    """The translated hot path bound to one COMMON state."""
+    """The translated hot path bound to one COMMON state.  Where the reference source is present it is read and
+    translated now; elsewhere (the GPU box) a translation built earlier for the same grid by
+    `build_cache` (oracle/_ref/f77_<im>x<jm>x<kb>.pkl, a build artefact like a compiled .so) is loaded."""
     FILES = ("pom/solver.f", "pom/advance.f", "pom/bounds_forcing.f")
+
+    @staticmethod
+    def cache_path(im, jm, kb):
+        return os.path.join(CACHE_DIR, f"f77_{im}x{jm}x{kb}.pkl")
+
+    @staticmethod
+    def available(im, jm, kb, root=REF_ROOT):
+        return os.path.exists(os.path.join(root, "pom", "solver.f")) or os.path.exists(Reference.cache_path(im, jm, kb))
 
     def __init__(self, im, jm, kb, root=REF_ROOT):
         self.root = root
+        self.R = {}
+        self.src = {}
+        self.externals = {}
+        if not os.path.exists(os.path.join(root, "pom", "solver.f")):
+            import pickle
+            with open(self.cache_path(im, jm, kb), "rb") as fh:
+                c = pickle.load(fh)
+            self.G = c["G"]
+            self.src = c["src"]
+            self.units = dict.fromkeys(self.src)
+            self.tr = None
+            return
         self.G = Globals(os.path.join(root, "pom.h_dist"),
                          dict(im_global=im, jm_global=jm, kb=kb, im_local=im, jm_local=jm, n_proc=1))
         v = self.G.v
@@ -736,27 +762,34 @@ class Reference:
         self.units = {}
         for f in self.FILES:
             self.units.update(split_units(os.path.join(root, f)))
-        self.R = {}
-        self.src = {}
-        self.externals = {}
         self.tr = Translator(self.G, self.units)
 
     def routine(self, name):
         if name not in self.R:
             if name not in self.units:
                 raise KeyError(f"the reference has no subroutine {name!r} in {self.FILES}")
-            src = self.tr.translate(self.units[name])
-            self.src[name] = src
+            if name not in self.src:
+                self.src[name] = self.tr.translate(self.units[name])
             env = dict(RUNTIME)
             env["G"] = self.G.v
             env["R"] = _Lazy(self)
-            exec(compile(src, f"<reference {name}>", "exec"), env)
+            exec(compile(self.src[name], f"<reference {name}>", "exec"), env)
             self.R[name] = env[name]
         return self.R[name]
 
     def call(self, name, *args):
         with np.errstate(all="ignore"):
             return self.routine(name)(*args)
+
+    def build_cache(self):
+        """Translate every subroutine of the three files and store the result for this grid under oracle/_ref/."""
+        import pickle
+        for n in self.units:
+            if n not in self.src:
+                self.src[n] = self.tr.translate(self.units[n])
+        os.makedirs(CACHE_DIR, exist_ok=True)
+        with open(self.cache_path(self.G.v["im_local"], self.G.v["jm_local"], self.G.v["kb"]), "wb") as fh:
+            pickle.dump({"G": self.G, "src": self.src}, fh)
 
 
 class _Lazy(dict):

@@ -4,10 +4,16 @@
  * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may build, link or call it.
  *
- * PARITY UNPINNED: the reference (RinceWND/extPOM, fixed-form Fortran) ships
- * no tests, no golden vectors and no input data, and cannot be compiled in
- * this image (no Fortran compiler, MPI or PnetCDF).  This file set is a
- * line-by-line restatement in C of
+ * PARITY PINNED AGAINST THE REFERENCE'S OWN SOURCE.  The reference (RinceWND/extPOM,
+ * fixed-form Fortran) ships no tests, no golden vectors and no input data, and cannot be
+ * COMPILED in this image (no Fortran compiler, MPI or PnetCDF) -- but its source can be
+ * EXECUTED: oracle/f77ref.py reads pom/solver.f, pom/advance.f, pom/bounds_forcing.f and
+ * pom.h_dist where they lie under /root/reference, translates them statement by statement
+ * (gfortran -O0 semantics: binary64, single-precision literals, integer division, powi) and
+ * runs them; scripts/make_ref_golden.py stores its outputs for 14 namelist variants under
+ * tests/golden/ref_*.npz, and this restatement equals every one of them BIT FOR BIT
+ * (tests/test_oracle.py; plus a live run of the reference source where it is present).
+ * This file set is a line-by-line restatement in C of
  *     pom/advance.f:96-537, pom/solver.f:6-940,1162-2067,
  *     pom/bounds_forcing.f:6-328,331-590,1083-1118
  * with 1-based column-major accessor macros named after the Fortran arrays

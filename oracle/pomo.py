@@ -1,6 +1,7 @@
 """ctypes front end of the CPU parity ORACLE (oracle/libpomo.so).
 
-TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED (see oracle/pomo.h).  Only tests/,
+TEST INFRASTRUCTURE ONLY -- parity pinned against the reference's own source run through
+oracle/f77ref.py (see oracle/pomo.h, tests/golden/ref_*.npz).  Only tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this module; the product (extpom_b200) never does.
 

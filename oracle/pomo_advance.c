@@ -1,7 +1,7 @@
 /* pomo_advance.c -- CPU ORACLE restatement of pom/advance.f:96-537
  * (lateral_viscosity, mode_interaction, mode_external, mode_internal) and
  * the hot-path part of advance (advance.f:21-32).
- * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (see pomo.h). */
+ * TEST INFRASTRUCTURE ONLY; parity pinned against the reference's own source (see pomo.h). */
 #define POMO_IMPL
 #include "pomo.h"
 #include <math.h>

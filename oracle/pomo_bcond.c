@@ -1,6 +1,6 @@
 /* pomo_bcond.c -- CPU ORACLE restatement of the boundary-condition and
  * restoring arithmetic of pom/bounds_forcing.f that runs inside the step.
- * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (see pomo.h).
+ * TEST INFRASTRUCTURE ONLY; parity pinned against the reference's own source (see pomo.h).
  * bcond: bounds_forcing.f:6-328 (idx 1,2,4,5,6; idx 3 is never called on
  * the path, advance.f:464 uses bcondorl(3)); bcondorl: :331-590 (idx 3,5;
  * the others are never called); restore_interior arithmetic: :1083-1118. */

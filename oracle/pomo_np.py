@@ -1,6 +1,7 @@
 """A SECOND, independent restatement (numpy) of the WHOLE hot path.
 
-TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED (see oracle/pomo.h).  The reference cannot be
+TEST INFRASTRUCTURE ONLY (see oracle/pomo.h: the C oracle is pinned bitwise against the reference's own
+source executed by oracle/f77ref.py; this older guard stays).  The reference cannot be
 compiled here, so the C oracle is itself a restatement; this module restates
     dens    pom/solver.f:1162-1209      baropg  pom/solver.f:848-940
     vertvl  pom/solver.f:1970-2021      advq    pom/solver.f:411-477

@@ -1,5 +1,5 @@
 /* pomo_solver.c -- CPU ORACLE restatement of pom/solver.f (reference).
- * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (see pomo.h).
+ * TEST INFRASTRUCTURE ONLY; parity pinned against the reference's own source (see pomo.h).
  * Each function cites the solver.f lines it follows; loop bounds, zero
  * fills, evaluation order and single-precision-literal quirks are kept.
  * Build: gcc -O2 -ffp-contract=off (no FMA, like the reference's -O0). */

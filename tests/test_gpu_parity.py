@@ -36,6 +36,28 @@ def test_cuda_path_matches_the_references_own_output(name):
     pc.check_ref_golden(_factory, name, tol=RTOL)
 
 
+def test_cuda_path_matches_a_live_run_of_the_reference_source():
+    """The reference's own Fortran source (oracle/f77ref.py; on the GPU box the translation that
+    __graft_entry__.build() left in oracle/_ref) run NOW next to the CUDA path, three steps on a small island case."""
+    from oracle.f77ref import F77Ref, Reference
+    from scripts.make_ref_golden import ref_restore_setup
+    from tests.common import F2, F3, KB_SCRATCH, rel_err
+    dims, kw = (13, 11, 6), {"island": True}
+    if not Reference.available(*dims):
+        pytest.skip("neither the reference source nor its translation (oracle/_ref) is on this machine")
+    _, r = syn.seamount(*dims, F77Ref, **kw)
+    st = syn.make_state(*dims, **kw)
+    g = _factory(*dims)
+    g.load(st); syn.finish_init(st, g); ref_restore_setup(g, st)
+    for i in (1, 2, 3):
+        r.step(i); g.step(i)
+    for n in F3 + F2:
+        a, b = r.get(n), g.get(n)
+        if n in KB_SCRATCH:
+            a, b = a[:, :, :-1], b[:, :, :-1]
+        assert rel_err(a, b) <= RTOL, (n, rel_err(a, b))
+
+
 @pytest.mark.parametrize("name", pc.GOLDEN)
 def test_matches_golden(name):
     pc.check_golden(_factory, name)

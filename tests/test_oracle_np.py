@@ -1,6 +1,6 @@
 """The two CPU restatements of the reference (C: oracle/pomo_*.c, numpy: oracle/pomo_np.py) must
-agree bitwise on a spun-up state -- the guard that stands in for the golden vectors the
-reference does not have (parity unpinned)."""
+agree bitwise on a spun-up state -- the round-1 guard from before the reference's own source could be
+executed (oracle/f77ref.py, tests/golden/ref_*.npz pin the oracle now)."""
 import numpy as np
 import pytest
 
