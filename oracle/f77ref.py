@@ -310,7 +310,15 @@ def _log(x):
 INTRINSICS = {"abs": "_abs", "dabs": "_abs", "sqrt": "_sqrt", "dsqrt": "_sqrt", "max": "_max", "min": "_min",
               "dmax1": "_max", "dmin1": "_min", "amax1": "_max", "amin1": "_min", "exp": "_exp", "sign": "_sign",
               "mod": "_mod", "float": "f4", "dble": "f8", "real": "_real", "int": "int", "log": "_log",
-              "maxval": "np.max", "minval": "np.min", "sum": "np.sum", "nint": "_nint"}
+              "maxval": "np.max", "minval": "np.min", "sum": "_sum", "nint": "_nint"}
+
+
+def _sum(a):
+    # gfortran's SUM: one accumulator, array element order (numpy's sum is pairwise)
+    r = f8(0.)
+    for x in np.asarray(a).ravel(order="F"):
+        r = r + x
+    return r
 
 
 def _nint(x):
@@ -324,7 +332,7 @@ def _mod(a, b):
 
 
 RUNTIME = dict(np=np, f4=f4, f8=f8, f16=f16, _div=_div, _pow=_pow, _sign=_sign, _max=_max, _min=_min, _real=_real,
-               _exp=_exp, _sqrt=_sqrt, _abs=_abs, _log=_log, _mod=_mod, _nint=_nint, int=int)
+               _exp=_exp, _sqrt=_sqrt, _abs=_abs, _log=_log, _mod=_mod, _nint=_nint, _sum=_sum, int=int)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -473,8 +481,9 @@ def split_units(path):
     return units
 
 
+# one rank: a sum / maximum / broadcast over the communicator leaves its argument as it is (parallel_mpi.f:125-151)
 NOOP_CALLS = {"exchange2d_mpi", "exchange3d_mpi", "order2d_mpi", "order3d_mpi", "psum0d_mpi", "sum0d_mpi", "max0d_mpi",
-              "finalize_mpi", "msg_print"}
+              "bcast0d_mpi", "finalize_mpi", "msg_print"}
 
 
 class Translator:
@@ -588,7 +597,7 @@ class Translator:
         """one non-block statement -> python line(s)"""
         low = s.lower()
         if low == "return":
-            return ["return"]
+            return ["return __RET__"]
         if low.startswith(("write", "print", "format", "open", "close", "read")):
             return ["pass"]
         if low.startswith("stop"):
@@ -719,8 +728,10 @@ class Translator:
                 raise NameError(f"{unit.name}: undeclared dummy argument {n}")
         garr = [f"    g_{n} = G[{n!r}]" for n in sorted(self.used_garrays)]
         head = f"def {unit.name}(" + ", ".join("l_" + a for a in args) + "):"
-        src = "\n".join([head] + garr + pro + ["    " + x for x in data_lines] + body + ["    return"])
-        return src
+        # scalar dummy arguments are passed by value: their final values are handed back as a tuple
+        ret = "(" + "".join(f"l_{a}, " for a in args if self.locals[a][1] is None) + ")"
+        src = "\n".join([head] + garr + pro + ["    " + x for x in data_lines] + body + ["    return __RET__"])
+        return src.replace("__RET__", ret)
 
 
 CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # built artefacts: git-ignored, travel with gpurun

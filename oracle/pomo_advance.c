@@ -332,16 +332,21 @@ void pomo_domain_stats(pomo_t *S, double *out) {
 #define DAREA(i, j) (dx(i,j)*dy(i,j)*fsm(i,j))
 #define INREG(i, j) (((i) >= 2 && (i) <= imm1 && (j) >= 2 && (j) <= jmm1) || (((i) == 1 || (i) == im) && (j) >= 2 && (j) <= jmm1) || (((j) == 1 || (j) == jm) && (i) >= 2 && (i) <= imm1))
   /* :669-680 interior first, then W, E, S, N edges */
-  DO(j, 2, jmm1) DO(i, 2, imm1) atot += DAREA(i,j);
-  DO(j, 2, jmm1) atot += DAREA(1,j);
-  DO(j, 2, jmm1) atot += DAREA(im,j);
-  DO(i, 2, imm1) atot += DAREA(i,1);
-  DO(i, 2, imm1) atot += DAREA(i,jm);
-  DO(j, 2, jmm1) DO(i, 2, imm1) eavg += et(i,j)*DAREA(i,j);
-  DO(j, 2, jmm1) eavg += et(1,j)*DAREA(1,j);
-  DO(j, 2, jmm1) eavg += et(im,j)*DAREA(im,j);
-  DO(i, 2, imm1) eavg += et(i,1)*DAREA(i,1);
-  DO(i, 2, imm1) eavg += et(i,jm)*DAREA(i,jm);
+  /* every `sum(section)` of the reference is a SEPARATE accumulation from zero that is then added to the total
+   * (atot = atot+sum(darea(1,2:jmm1))): found by running the reference source itself (oracle/f77ref.py) -- folding
+   * the edge values into the running total changes the last bit */
+  { double p;
+    DO(j, 2, jmm1) DO(i, 2, imm1) atot += DAREA(i,j);
+    p = 0.; DO(j, 2, jmm1) p += DAREA(1,j);  atot = atot + p;
+    p = 0.; DO(j, 2, jmm1) p += DAREA(im,j); atot = atot + p;
+    p = 0.; DO(i, 2, imm1) p += DAREA(i,1);  atot = atot + p;
+    p = 0.; DO(i, 2, imm1) p += DAREA(i,jm); atot = atot + p;
+    DO(j, 2, jmm1) DO(i, 2, imm1) eavg += et(i,j)*DAREA(i,j);
+    p = 0.; DO(j, 2, jmm1) p += et(1,j)*DAREA(1,j);   eavg = eavg + p;
+    p = 0.; DO(j, 2, jmm1) p += et(im,j)*DAREA(im,j); eavg = eavg + p;
+    p = 0.; DO(i, 2, imm1) p += et(i,1)*DAREA(i,1);   eavg = eavg + p;
+    p = 0.; DO(i, 2, imm1) p += et(i,jm)*DAREA(i,jm); eavg = eavg + p;
+  }
   eavg = (atot != 0.) ? eavg / atot : 0.;                     /* :685-691 */
   /* :693-703: dvol is only assigned on the interior (2:imm1,2:jmm1); the edge sums add zeros */
 #define DVOL(i, j, k) (DAREA(i,j)*dt(i,j)*dz(k))
