@@ -38,6 +38,12 @@ REF_CASES = {
     "isplit5":        ((16, 14, 7), 3, {"isplit": 5, "dte": 6.0}),
     "kb12":           ((12, 11, 12), 3, {}),
     "medium":         ((32, 26, 12), 6, {}),
+    # constants the generator does not take as keywords: set on the loaded solver ("_set")
+    "alpha_ramp_ispadv": ((16, 14, 7), 4, {"_set": {"alpha": 0.225, "ramp": 0.6, "ispadv": 3, "smoth": 0.05}}),
+    "bias_rf_visc":   ((16, 14, 7), 3, {"island": True, "_set": {"tbias": 1.0, "sbias": 0.5, "rfe": 0.5, "rfw": 0.25,
+                                                                   "rfn": 0.75, "rfs": 0.1, "horcon": 0.2, "tprni": 0.3,
+                                                                   "umol": 2.e-5}}),
+    "kb21":           ((14, 12, 21), 4, {}),
 }
 
 # the fields compared (state + diagnostics of the step; COMMON member names)
@@ -61,9 +67,22 @@ def ref_restore_setup(solver, st):
     assert kb == full.shape[2]
 
 
+def loaded(factory, dims, kw):
+    """state + solver: generate, load, apply the case's extra constants, then the initial dens / baropg calls."""
+    kw = dict(kw)
+    extra = kw.pop("_set", {})
+    st = syn.make_state(*dims, **kw)
+    sv = factory(*dims)
+    sv.load(st)
+    for k, v in extra.items():
+        sv.set(k, v)
+    syn.finish_init(st, sv)
+    return st, sv
+
+
 def run_reference(dims, steps, kw):
     from oracle.f77ref import F77Ref
-    st, r = syn.seamount(*dims, F77Ref, **kw)
+    st, r = loaded(F77Ref, dims, kw)
     for i in range(1, steps + 1):
         r.step(i)
     return st, r
@@ -83,10 +102,7 @@ def main(argv):
         msg = f"ref_{name}: {dims} {steps} steps {kw} in {time.time() - t0:.1f} s"
         if check:
             from oracle.pomo import Oracle
-            st2 = syn.make_state(*dims, **kw)
-            o = Oracle(*dims)
-            o.load(st2)
-            syn.finish_init(st2, o)
+            st2, o = loaded(Oracle, dims, kw)
             ref_restore_setup(o, st2)
             for i in range(1, steps + 1):
                 o.step(i)

@@ -346,10 +346,7 @@ def check_ref_golden(factory, name, tol):
     reference's own Fortran source produced (tests/golden/ref_<name>.npz); tol=0: bitwise."""
     dims, steps, kw = REF_CASES[name]
     gold = np.load(os.path.join(GOLD, f"ref_{name}.npz"))
-    st = syn.make_state(*dims, **kw)
-    g = factory(*dims)
-    g.load(st)
-    syn.finish_init(st, g)
+    st, g = mrg.loaded(factory, dims, kw)
     ref_restore_setup(g, st)
     for i in range(1, steps + 1):
         g.step(i)
