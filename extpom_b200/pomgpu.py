@@ -276,10 +276,13 @@ class PomGpu:
                 self.put(k, v)
 
     # -- the reference's subroutine surface ------------------------------------
-    def step(self, iint, time=None, ramp=1.0):
-        """pom/advance.f:21-32 for internal step iint; time as get_time (advance.f:66)."""
+    def step(self, iint, time=None, ramp=None):
+        """pom/advance.f:21-32 for internal step iint; time as get_time (advance.f:66); ramp: the value get_time
+        would set (advance.f:67-72), default = the context's current `ramp` constant (1 unless the caller set it)."""
         if time is None:
             time = self.getc("dti") * float(iint) / 86400.0 + self.getc("time0")
+        if ramp is None:
+            ramp = self.getc("ramp")
         self._ck(self.L.pomgpu_step(self.h, int(iint), float(time), float(ramp)), "step")
 
     def sync(self):
@@ -415,10 +418,12 @@ class PomGroup:
         self._cb = HALO_CB(cb)
         self.L.pomgpu_group_set_transport(self.h, C.cast(self._cb, C.c_void_p), None)
 
-    def step(self, iint, time=None, ramp=1.0):
+    def step(self, iint, time=None, ramp=None):
         s0 = self.strips[0]
         if time is None:
             time = s0.getc("dti") * float(iint) / 86400.0 + s0.getc("time0")
+        if ramp is None:
+            ramp = s0.getc("ramp")
         rc = self.L.pomgpu_group_step(self.h, int(iint), float(time), float(ramp))
         if rc != 0:
             raise PomGpuError(f"group_step failed (rc={rc}): {self.L.pomgpu_last_error(s0.h).decode()}")
