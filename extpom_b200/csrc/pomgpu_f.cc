@@ -23,6 +23,11 @@ extern char blk1d_[] __attribute__((weak));
 extern char blk2d_[] __attribute__((weak));
 extern char blk3d_[] __attribute__((weak));
 extern char bdry_[] __attribute__((weak));
+// The record half of restore_interior (bounds_forcing.f:1023-1081: the netCDF reads and the `b = f` copies that
+// precede "linear interpolation in time"), kept in Fortran: scripts/make_glue.py writes it into the glue file as
+// `subroutine restore_interior_records`.  The reference calls restore_interior from INSIDE mode_internal
+// (advance.f:452), which is now this library's, so mode_internal_ calls the record half back at the same place.
+void restore_interior_records_(void) __attribute__((weak));
 }
 
 namespace {
@@ -37,6 +42,9 @@ pomgpu_t* g_ctx = nullptr;
 std::vector<int> g_dev;        // COMMON members that are device fields (index into g_mem)
 bool g_full_pushed = false;    // the whole state has been pushed once (start of resident mode)
 bool g_device_ahead = false;   // step-level calls ran since the last full pull: host copies are stale
+int g_restore = -1;            // restore_interior's nudging (bounds_forcing.f:1083-1118): -1 = on iff the driver supplies
+                               // restore_interior_records or pushes a restoring record, 0 / 1 = pomgpu_f_set_restore_
+bool g_restore_pushed = false; // the driver pushed a restoring record by hand (pomgpu_f_push_)
 char g_err[256] = "";
 
 void fail(const char* what) {
@@ -223,6 +231,34 @@ void pull_error_status() {
   }
 }
 
+// ---- restore_interior (bounds_forcing.f:1023-1118), called from inside mode_internal (advance.f:452) -------
+typedef void (*records_fn)(void);
+records_fn records_hook() {
+  if (restore_interior_records_) return restore_interior_records_;
+  return (records_fn)dlsym(RTLD_DEFAULT, "restore_interior_records_");
+}
+const char* RESTORE = "trstrb trstrf srstrb srstrf taurstrb taurstrf";
+bool is_restore_member(const std::string& n) { return (" " + std::string(RESTORE) + " ").find(" " + n + " ") != std::string::npos; }
+// Runs where the reference runs the first half of restore_interior: only when mode_internal's tracer block does
+// (advance.f:362,424: not on the skipped first step of a cold start, not for mode 2 or 4).  The Fortran routine
+// re-reads its records when `iint.eq.2 .or. mod(iint,irst).eq.0` (:1038,1053); the six arrays travel to HBM on
+// exactly those steps.  The time interpolation and the nudging (:1083-1118) are part of the device step.
+bool restore_begin(int iint) {
+  records_fn hook = records_hook();
+  const int on = (g_restore >= 0) ? g_restore : ((hook || g_restore_pushed) ? 1 : 0);
+  pomgpu_set_const(g_ctx, "lrestore", (double)on);
+  if (!on || !hook) return true;
+  const Member *t0 = find("time0"), *dti = find("dti");
+  const double time0 = addr(t0) ? *(double*)addr(t0) : 0., dt_i = addr(dti) ? *(double*)addr(dti) : 0.;
+  const int mode = iget("mode", 3);
+  if (!((iint != 1 || time0 != 0.) && mode != 2 && mode != 4)) return true;
+  hook();
+  const double trst = 30.;                                   // bounds_forcing.f:1033
+  const int irst = (int)(trst * 86400. / dt_i);              // :1034
+  if (iint == 2 || (irst > 0 && iint % irst == 0)) return push_names(RESTORE);
+  return true;
+}
+
 // ---- step level: resident ------------------------------------------------------------------
 bool step_begin() {
   if (!ensure_ctx()) return false;
@@ -285,6 +321,7 @@ void mode_internal_(void) {       // advance.f:356-537
   g_device_ahead = true;
   const int iint = iget("iint", 1);
   pomgpu_set_const(g_ctx, "iext", (double)iget("iext", 0));
+  if (!restore_begin(iint)) return;
   if (!ck(pomgpu_mode_internal(g_ctx, iint), "mode_internal")) return;
   // what the Fortran glue reads on the host after EVERY step: vaf (check_velocity, advance.f:52,
   // 619-629).  On the device the rotation left the new vaf under the name va.
@@ -409,8 +446,10 @@ void pomgpu_f_push_(const double* member) {
   if (!ensure_ctx()) return;
   const Member* m = member_at(member);
   if (!m) { fail("pomgpu_f_push_: not the start of a COMMON array"); return; }
+  if (is_restore_member(m->name)) g_restore_pushed = true;
   ck(pomgpu_push(g_ctx, m->name.c_str(), member), m->name.c_str());
 }
+void pomgpu_f_set_restore_(const int* on) { g_restore = (*on < 0) ? -1 : (*on != 0); }
 void pomgpu_f_pull_(double* member) {
   if (!ensure_ctx()) return;
   const Member* m = member_at(member);
@@ -419,7 +458,7 @@ void pomgpu_f_pull_(double* member) {
 }
 void pomgpu_f_finalize_(void) {
   if (g_ctx) pomgpu_destroy(g_ctx);
-  g_ctx = nullptr; g_full_pushed = false; g_device_ahead = false;
+  g_ctx = nullptr; g_full_pushed = false; g_device_ahead = false; g_restore_pushed = false; g_restore = -1;
 }
 void* pomgpu_f_member(const char* name, long* elems) {
   const Member* m = find(name);

@@ -83,6 +83,16 @@ void pomgpu_f_push_all_(void);                  /* COMMON -> HBM, everything    
 void pomgpu_f_pull_all_(void);                  /* HBM -> COMMON, everything (output, restart) */
 void pomgpu_f_push_(const double* member);      /* one COMMON array, by address (e.g. trstrb after restore_interior re-read it) */
 void pomgpu_f_pull_(double* member);
+/* restore_interior (bounds_forcing.f:1023-1118) is called by the reference from INSIDE mode_internal (advance.f:452)
+ * and mixes netCDF reads with arithmetic.  The arithmetic (time interpolation of the records, nudging of t, tb, s, sb,
+ * masks: :1083-1118) is part of the device step; the reads stay in Fortran: when the executable defines
+ *     subroutine restore_interior_records        (written by scripts/make_glue.py: restore_interior's lines up to
+ *                                                 "linear interpolation in time", nothing else changed)
+ * mode_internal_ calls it at the place of advance.f:452 and pushes trstrb/f, srstrb/f, taurstrb/f on the steps the
+ * routine re-reads them (`iint.eq.2 .or. mod(iint,irst).eq.0`, :1038,1053).  Nudging is then ON, as in the reference;
+ * it is also switched on by pushing a restoring record by hand (pomgpu_f_push_(trstrb) ...).  pomgpu_f_set_restore_
+ * overrides: 0 = off, 1 = on, -1 = the automatic rule. */
+void pomgpu_f_set_restore_(const int* on);
 void pomgpu_f_finalize_(void);
 /* C-side access for tests: address of a COMMON member by name (NULL if unknown / unbound) */
 void* pomgpu_f_member(const char* name, long* elems);

@@ -48,6 +48,29 @@ static void put(FILE* f, const char* name, const double* a, long cnt) {
   fwrite(nm, 1, 32, f); fwrite(&cnt, 8, 1, f); fwrite(a, 8, (size_t)cnt, f);
 }
 
+#ifdef WITH_RESTORE
+/* `subroutine restore_interior_records`: the record half of restore_interior (bounds_forcing.f:1023-1081) that
+ * scripts/make_glue.py leaves in the Fortran glue.  libpomgpu_f's mode_internal_ calls it back at the place of
+ * advance.f:452.  The netCDF reader (read_restore_ts_interior_pnetcdf) is played by the climatology. */
+static void read_records(void) {
+  memcpy(D("trstrf"), D("tclim"), N3 * 8);                                   /* :1040-1041, 1066-1067 */
+  memcpy(D("srstrf"), D("sclim"), N3 * 8);
+  double* tau = D("taurstrf");
+  for (size_t q = 0; q < N3; ++q) tau[q] = 1.f / 30.;                        /* taurstrf = 1./trst, :1042 */
+}
+void restore_interior_records_(void) {
+  const double trst = 30.;
+  const int iint = (int)getc_("iint"), irst = (int)(trst * 86400. / getc_("dti")), iend = (int)getc_("iend");
+  if (iint == 2) read_records();                                             /* :1038 */
+  if (iint == 2 || iint % irst == 0) {                                       /* :1053 */
+    memcpy(D("trstrb"), D("trstrf"), N2 * (KB - 1) * 8);                     /* k = 1..kbm1, :1054-1062 */
+    memcpy(D("srstrb"), D("srstrf"), N2 * (KB - 1) * 8);
+    memcpy(D("taurstrb"), D("taurstrf"), N2 * (KB - 1) * 8);
+    if (iint != iend) read_records();                                        /* :1063-1067 */
+  }
+}
+#endif
+
 int main(int argc, char** argv) {
   if (argc < 4) { fprintf(stderr, "usage: fortran_abi_driver STATE.bin NSTEPS OUT.bin [unit]\n"); return 2; }
   const int unit = argc > 4 && !strcmp(argv[4], "unit");

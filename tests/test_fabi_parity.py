@@ -1,0 +1,131 @@
+"""The whole parity suite THROUGH THE GFORTRAN ABI.
+
+tests/fabi.py plays the reference's Fortran driver from Python: state lives in the COMMON blocks (`blk3d_` ...), the
+hot path is entered through the mangled names the reference's callers bind -- `lateral_viscosity_`, `mode_interaction_`,
+`mode_external_`, `mode_internal_` (advance.f:21-32) and every routine of solver.f / bounds_forcing.f with the
+reference's own argument lists (`advq_(qb,q,qf)`, `advt2_(fb,f,fclim,ff)`, `dens_(si,ti,rhoo)`,
+`proft_(f,wfsurf,fsurf,nbc)`, `smol_adif_(...)`, `bcond_(idx)`, `bcondorl_(idx)`), arrays by address, integers by
+reference.  The same checks the C-ABI path has to pass (tests/parity_cases.py) are run on that face:
+
+  * every routine against the oracle's routine of the same name, from the same spun-up state;
+  * whole internal steps for every namelist / shape case against the oracle;
+  * the reference's OWN output (tests/golden/ref_*.npz, produced by executing the reference's Fortran source);
+  * restore_interior's record half called back from inside mode_internal_ (advance.f:452).
+
+CPU: libpomgpu_f_emu.so over the host build of the kernel bodies; `-m gpu`: libpomgpu_f.so over the CUDA library.
+"""
+import numpy as np
+import pytest
+
+from scripts import make_ref_golden as mrg
+from tests import parity_cases as pc
+from tests.fabi import FabiEmu, FabiGpu
+
+DIMS = (22, 18, 8)
+
+
+def reference_records(sv):
+    """`subroutine restore_interior_records`: restore_interior up to "linear interpolation in time"
+    (bounds_forcing.f:1023-1081), the netCDF reader played by the climatology like the fixtures' generator does."""
+    iint, iend, kb = int(sv.getc("iint")), int(sv.getc("iend")), sv.kb
+    irst = int(30. * 86400. / sv.getc("dti"))                                   # :1033-1034
+    V = sv._view
+
+    def read():                                                                 # :1039-1042, 1064-1067
+        V("trstrf")[...] = V("tclim")
+        V("srstrf")[...] = V("sclim")
+        V("taurstrf")[...] = float(np.float32(1.) / np.float64(30.))
+
+    if iint == 2:
+        read()
+    if iint == 2 or iint % irst == 0:                                           # :1053
+        for n in ("trstr", "srstr", "taurstr"):
+            V(n + "b")[:, :, :kb - 1] = V(n + "f")[:, :, :kb - 1]               # :1054-1062
+        if iint != iend:
+            read()
+
+
+def _records_case(factory, name):
+    """A reference case with the nudging driven the reference's way: no records handed over, the callback reads them."""
+    dims, steps, kw = pc.REF_CASES[name]
+    gold = np.load(pc.os.path.join(pc.GOLD, f"ref_{name}.npz"))
+    st, g = mrg.loaded(factory, dims, kw)
+    g.set_records(reference_records)
+    try:
+        for i in range(1, steps + 1):
+            g.step(i)
+        for n in mrg.F3 + mrg.F2:
+            if n in ("uf", "vf"):
+                continue
+            a, b = gold[n], g.get(n)
+            if n in ("t", "tb", "s", "sb") and a.ndim == 3:
+                a, b = a[:, :, :-1], b[:, :, :-1]
+            assert pc.rel_err(a, b) <= 1e-11, (name, n, pc.rel_err(a, b))
+    finally:
+        g.set_records(None)
+        g.set_restore(0)
+
+
+# ---- CPU: host-emulated kernel bodies behind the Fortran face ---------------------------------------------------
+@pytest.mark.parametrize("routine", pc.ROUTINES)
+def test_routine_through_the_fortran_abi(routine):
+    pc.check_routine(FabiEmu, routine, DIMS)
+
+
+@pytest.mark.parametrize("case", pc.STEP_CASES, ids=pc.case_id)
+def test_steps_through_the_fortran_abi(case):
+    pc.check_steps(FabiEmu, case)
+
+
+@pytest.mark.parametrize("name", pc.REF_GOLDEN)
+def test_fortran_abi_matches_the_references_own_output(name):
+    pc.check_ref_golden(FabiEmu, name, tol=1e-11)
+
+
+@pytest.mark.parametrize("name", ["default", "medium"])
+def test_restore_interior_records_callback(name):
+    _records_case(FabiEmu, name)
+
+
+def test_records_callback_matters():
+    """Without the callback (and without records) the same driver must NOT reproduce the reference's nudged output."""
+    dims, steps, kw = pc.REF_CASES["medium"]
+    gold = np.load(pc.os.path.join(pc.GOLD, "ref_medium.npz"))
+    _, g = mrg.loaded(FabiEmu, dims, kw)
+    for i in range(1, steps + 1):
+        g.step(i)
+    assert pc.rel_err(gold["t"][:, :, :-1], g.get("t")[:, :, :-1]) > 1e-9
+
+
+def test_error_status_follows_the_reference_convention():
+    """advance.f:118-119: an invalid npg sets error_status=1 in blkcon (and prints); nothing exits."""
+    from tests.fabi import FabiError
+    _, g = pc.syn.seamount(*DIMS, FabiEmu)
+    g.set("npg", 7)
+    with pytest.raises(FabiError):
+        g.step(1)
+    assert int(g.getc("error_status")) == 1
+
+
+# ---- GPU: the CUDA library behind the Fortran face ----------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("routine", pc.ROUTINES)
+def test_routine_through_the_fortran_abi_on_gpu(routine):
+    pc.check_routine(FabiGpu, routine, (44, 36, 12))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", pc.STEP_CASES, ids=pc.case_id)
+def test_steps_through_the_fortran_abi_on_gpu(case):
+    pc.check_steps(FabiGpu, case)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", pc.REF_GOLDEN)
+def test_fortran_abi_on_gpu_matches_the_references_own_output(name):
+    pc.check_ref_golden(FabiGpu, name, tol=1e-11)
+
+
+@pytest.mark.gpu
+def test_restore_interior_records_callback_on_gpu():
+    _records_case(FabiGpu, "medium")

@@ -16,6 +16,7 @@ import pytest
 from extpom_b200 import synthetic as syn
 from extpom_b200.pomgpu import LIBPATH, PomGpu
 from scripts.dump_state import dump, read_out
+from scripts.make_ref_golden import ref_restore_setup
 from tests import emu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -73,21 +74,23 @@ def test_layout_header_matches_the_reference_include():
         assert open(tmp).read() == h
 
 
-def _build_driver(tmp_path, dims, libdir, flib, lib):
+def _build_driver(tmp_path, dims, libdir, flib, lib, *defs):
     exe = str(tmp_path / "fortran_abi_driver")
-    subprocess.check_call(["gcc", "-O1", f"-DIML={dims[0]}", f"-DJML={dims[1]}", f"-DKB={dims[2]}",
+    subprocess.check_call(["gcc", "-O1", f"-DIML={dims[0]}", f"-DJML={dims[1]}", f"-DKB={dims[2]}", *defs,
                            "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "fortran_abi_driver.c"),
                            "-o", exe, "-L", libdir, "-l" + flib, "-l" + lib, "-lm", "-Wl,-rpath," + libdir])
     return exe
 
 
-def _run_step(tmp_path, exe, factory, dims, nstep, **kw):
+def _run_step(tmp_path, exe, factory, dims, nstep, restore=False, **kw):
     state, out = str(tmp_path / "state.bin"), str(tmp_path / "out.bin")
     dump(state, *dims, **kw)
     r = subprocess.run([exe, state, str(nstep), out], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     got = read_out(out)
-    _, g = syn.seamount(*dims, factory, **kw)
+    st, g = syn.seamount(*dims, factory, **kw)
+    if restore:
+        ref_restore_setup(g, st)
     for i in range(1, nstep + 1):
         g.step(i)
     assert f"{g.check_velocity():.17g}" in r.stdout
@@ -154,6 +157,28 @@ def test_fortran_abi_npg2_and_nadv1_on_gpu(tmp_path):
     dims = (40, 36, 12)
     exe = _build_driver(tmp_path, dims, os.path.dirname(FLIB), "pomgpu_f", "pomgpu")
     _run_step(tmp_path, exe, PomGpu, dims, 4, npg=2, nadv=1)
+
+
+def test_restore_interior_records_are_called_back_from_mode_internal(tmp_path):
+    """restore_interior is called from INSIDE mode_internal (advance.f:452).  An executable that defines
+    `restore_interior_records_` (the record half, bounds_forcing.f:1023-1081, left in Fortran by make_glue.py) gets it
+    called at that place, the records pushed on the steps the routine re-reads them, and the nudging switched on:
+    equal, bit for bit, to the name-addressed run that was handed the same records."""
+    emu.build_emu()
+    dims = (22, 18, 8)
+    exe = _build_driver(tmp_path, dims, os.path.dirname(FLIB_EMU), "pomgpu_f_emu", "pomgpu_emu", "-DWITH_RESTORE")
+    assert _run_step(tmp_path, exe, emu.EmuPom, dims, 4, restore=True, island=True) >= 40
+    # and the nudging did change the result: without the records routine the same driver gives another t
+    exe0 = _build_driver(tmp_path, dims, os.path.dirname(FLIB_EMU), "pomgpu_f_emu", "pomgpu_emu")
+    with pytest.raises(AssertionError):
+        _run_step(tmp_path, exe0, emu.EmuPom, dims, 4, restore=True, island=True)
+
+
+@pytest.mark.gpu
+def test_restore_interior_records_on_gpu(tmp_path):
+    dims = (40, 36, 12)
+    exe = _build_driver(tmp_path, dims, os.path.dirname(FLIB), "pomgpu_f", "pomgpu", "-DWITH_RESTORE")
+    assert _run_step(tmp_path, exe, PomGpu, dims, 4, restore=True) >= 40
 
 
 def test_make_glue_cuts_exactly_the_four_step_routines(tmp_path):
