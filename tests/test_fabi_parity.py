@@ -87,6 +87,55 @@ def test_restore_interior_records_callback(name):
     _records_case(FabiEmu, name)
 
 
+def test_generated_fortran_glue_is_the_callback(tmp_path):
+    """End to end with the reference's own lines: scripts/make_glue.py cuts `restore_interior_records` out of the
+    reference's bounds_forcing.f, oracle/f77ref.py EXECUTES that generated Fortran as the callback (on a copy of the
+    COMMON state, its netCDF reader played by the climatology), the library does the rest of restore_interior on
+    its side -- and the run must reproduce what the reference's whole restore_interior produced (ref_medium)."""
+    src = "/root/reference/pom/bounds_forcing.f"
+    if not pc.os.path.exists(src):
+        pytest.skip("reference tree not present")
+    from oracle import f77ref
+    from scripts.make_glue import restore_records
+    from tests.fabi import RESTORE
+    glue = tmp_path / "restore_glue.f"
+    glue.write_text(restore_records(open(src).read()))
+    dims, steps, kw = pc.REF_CASES["medium"]
+    r = f77ref.F77Ref(*dims)
+    units = f77ref.split_units(str(glue))
+    assert list(units) == ["restore_interior_records"]
+    r.ref.units.update(units)
+    calls = []
+
+    def fortran_records(sv):
+        for n in ("iint", "iend"):
+            r.v[n] = int(sv.getc(n))
+        for n in ("dti", "time"):
+            r.v[n] = np.float64(sv.getc(n))
+        for n in ("tclim", "sclim") + RESTORE:
+            r.v[n][...] = sv._view(n)
+        r.ref.call("restore_interior_records")
+        for n in RESTORE:
+            sv._view(n)[...] = r.v[n]
+        calls.append(int(sv.getc("iint")))
+
+    gold = np.load(pc.os.path.join(pc.GOLD, "ref_medium.npz"))
+    _, g = mrg.loaded(FabiEmu, dims, kw)
+    g.set_records(fortran_records)
+    try:
+        for i in range(1, steps + 1):
+            g.step(i)
+        assert calls == list(range(2, steps + 1))        # not on the skipped first step of a cold start (advance.f:362)
+        for n in ("t", "s", "tb", "sb", "rho", "u", "v", "el"):
+            a, b = gold[n], g.get(n)
+            if a.ndim == 3 and n in ("t", "tb", "s", "sb"):
+                a, b = a[:, :, :-1], b[:, :, :-1]
+            assert pc.rel_err(a, b) <= 1e-11, n
+    finally:
+        g.set_records(None)
+        g.set_restore(0)
+
+
 def test_records_callback_matters():
     """Without the callback (and without records) the same driver must NOT reproduce the reference's nudged output."""
     dims, steps, kw = pc.REF_CASES["medium"]

@@ -199,3 +199,15 @@ def test_make_glue_cuts_exactly_the_four_step_routines(tmp_path):
     assert all(any(l == o for o in it) for l in kept)      # kept lines are a subsequence of the original
     for call in ("call lateral_viscosity", "call mode_interaction", "call mode_external", "call mode_internal"):
         assert call in text                                  # `advance` still calls them (advance.f:21-32)
+    # the record half of restore_interior (bounds_forcing.f:1023-1081) as `restore_interior_records`: the routine's
+    # own lines up to "linear interpolation in time", nothing after
+    from scripts.make_glue import restore_records
+    bf = open("/root/reference/pom/bounds_forcing.f").read()
+    rec = restore_records(bf)
+    body = [l for l in rec.splitlines() if not l.startswith("! [")]
+    assert body[0].split() == ["subroutine", "restore_interior_records"] and body[-2:] == ["      return", "      end"]
+    ref_lines = bf.splitlines()
+    it = iter(ref_lines)
+    assert all(any(l == o for o in it) for l in body[1:-2])   # verbatim, in order
+    assert "read_restore_ts_interior_pnetcdf" in rec and "trstrb(i,j,k)=trstrf(i,j,k)" in rec
+    assert "fold*trstrb" not in rec and "taurstr(i,j,k)*" not in rec      # the arithmetic half is the library's
