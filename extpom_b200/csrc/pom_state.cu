@@ -317,6 +317,57 @@ int ctx_push_rows(Ctx* c, const char* name, const double* host, int row0, int nr
   return 0;
 }
 
+// The same for a host array with GLOBAL extents (im, jm_global[, kb]) -- a COMMON member of a single-rank driver whose
+// domain is spread over several strips (libpomgpu_f with more than one device): push takes the rows this strip
+// holds (owned + ghost), pull returns the rows it OWNS, so the strips of a group assemble the array between them.
+int ctx_pull(Ctx* c, const char* name, double* host);
+size_t field_global_elems(const Ctx* c, const FieldInfo* f) {
+  const Geo& g = c->g;
+  switch (f->kind) {
+    case K3D: return (size_t)g.im * g.jmg * g.kb;
+    case K2D: return (size_t)g.im * g.jmg;
+    case KBJ: return g.jmg;
+    case KBJK: return (size_t)g.jmg * g.kb;
+    default: return field_elems(c, f);
+  }
+}
+int ctx_push_global(Ctx* c, const char* name, const double* host) {
+  const FieldInfo* f;
+  double** slot = ctx_slot(c, name, &f);
+  if (!slot) { snprintf(c->err, sizeof(c->err), "unknown field '%s'", name); return 2; }
+  if (!*slot && dev_alloc(c, slot, field_elems(c, f))) return 1;
+  const size_t im = c->g.im, jml = c->g.jml, jmg = c->g.jmg, joff = c->g.joff;
+  size_t w, sp, dp, off; int nk;     // run (doubles), source / destination level pitch, source offset, levels
+  switch (f->kind) {
+    case K3D: w = im * jml; sp = im * jmg; dp = w; off = im * joff; nk = c->g.kb; break;
+    case K2D: w = im * jml; sp = im * jmg; dp = w; off = im * joff; nk = 1; break;
+    case KBJ: w = jml; sp = jmg; dp = w; off = joff; nk = 1; break;
+    case KBJK: w = jml; sp = jmg; dp = w; off = joff; nk = c->g.kb; break;
+    default: return ctx_push(c, name, host);   // no j dimension: the whole array
+  }
+  for (int k = 0; k < nk; ++k)
+    if (dev_h2d(c, *slot + (size_t)k * dp, host + off + (size_t)k * sp, w)) return 1;
+  return 0;
+}
+int ctx_pull_global(Ctx* c, const char* name, double* host) {
+  const FieldInfo* f;
+  double** slot = ctx_slot(c, name, &f);
+  if (!slot || !*slot) { snprintf(c->err, sizeof(c->err), "unknown or unallocated field '%s'", name); return 2; }
+  const size_t im = c->g.im, jml = c->g.jml, jmg = c->g.jmg;
+  const size_t g0 = (size_t)(c->jown0 - 1), l0 = g0 - (size_t)c->g.joff, nown = (size_t)(c->jown1 - c->jown0 + 1);
+  size_t w, hp, dp, hoff, doff; int nk;   // run, host / device level pitch, host / device offset of the first owned row
+  switch (f->kind) {
+    case K3D: w = im * nown; hp = im * jmg; dp = im * jml; hoff = im * g0; doff = im * l0; nk = c->g.kb; break;
+    case K2D: w = im * nown; hp = im * jmg; dp = im * jml; hoff = im * g0; doff = im * l0; nk = 1; break;
+    case KBJ: w = nown; hp = jmg; dp = jml; hoff = g0; doff = l0; nk = 1; break;
+    case KBJK: w = nown; hp = jmg; dp = jml; hoff = g0; doff = l0; nk = c->g.kb; break;
+    default: return ctx_pull(c, name, host);
+  }
+  for (int k = 0; k < nk; ++k)
+    if (dev_d2h(c, host + hoff + (size_t)k * hp, *slot + doff + (size_t)k * dp, w)) return 1;
+  return 0;
+}
+
 int ctx_pull(Ctx* c, const char* name, double* host) {
   const FieldInfo* f;
   double** slot = ctx_slot(c, name, &f);

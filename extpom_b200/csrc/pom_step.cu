@@ -566,6 +566,12 @@ int pomgpu_push_rows(pomgpu_t* p, const char* name, const double* host, int row0
   touched(X(p), name);
   return ctx_push_rows(X(p), name, host, row0, nrows);
 }
+long pomgpu_field_global_elems(pomgpu_t* p, const char* name) {
+  const FieldInfo* f = find_field(name);
+  return f ? (long)field_global_elems(X(p), f) : 0;
+}
+int pomgpu_push_global(pomgpu_t* p, const char* name, const double* host) { apply_pending(X(p)); touched(X(p), name); return ctx_push_global(X(p), name, host); }
+int pomgpu_pull_global(pomgpu_t* p, const char* name, double* host) { apply_pending(X(p)); return ctx_pull_global(X(p), name, host); }
 long pomgpu_field_elems(pomgpu_t* p, const char* name) {
   const FieldInfo* f = find_field(name);
   return f ? (long)field_elems(X(p), f) : 0;
@@ -764,6 +770,26 @@ int pomgpu_group_dens(pomgpu_group_t* g, const char* si, const char* ti, const c
   return 0;
 }
 int pomgpu_group_baropg(pomgpu_group_t* g) { apply_pending(GG(g)); k_baropg(GG(g), GG(g)->c[0]->c.npg); return 0; }
+// the four step routines of advance.f:21-32 one by one on a group (a driver that keeps the reference's own
+// `advance`, e.g. libpomgpu_f over several strips); the constants are those of strip 0
+int pomgpu_group_lateral_viscosity(pomgpu_group_t* g) {
+  Group* G = GG(g); apply_pending(G); CSYNC();
+  if (int r = check_switches(G)) return r;
+  return lateral_viscosity(G);
+}
+int pomgpu_group_mode_interaction(pomgpu_group_t* g) { Group* G = GG(g); apply_pending(G); CSYNC(); return mode_interaction(G); }
+int pomgpu_group_mode_external(pomgpu_group_t* g, int iext) {
+  Group* G = GG(g); apply_pending(G); CSYNC();
+  if (int r = check_switches(G)) return r;
+  return mode_external(G, iext);
+}
+int pomgpu_group_mode_internal(pomgpu_group_t* g, int iint) {
+  Group* G = GG(g); apply_pending(G); CSYNC();
+  if (int r = check_switches(G)) return r;
+  return mode_internal(G, iint);
+}
+int pomgpu_group_error_status(pomgpu_group_t* g) { return group_status(GG(g)); }
+int pomgpu_group_baropg_kind(pomgpu_group_t* g, int npg) { Group* G = GG(g); apply_pending(G); CSYNC(); k_baropg(G, npg == 2 ? 2 : 1); return 0; }
 
 // ---- the reference's subroutines on the resident state ----------------------------------------
 #define SG Group* G = self_group(X(p)); apply_pending(G)

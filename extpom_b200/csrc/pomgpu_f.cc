@@ -38,7 +38,16 @@ int g_iml = POMF_IM_LOCAL, g_jml = POMF_JM_LOCAL, g_kb = POMF_KB, g_device = 0;
 bool g_resolved = false;
 std::vector<Member> g_mem;
 char* g_base[POMF_NBLOCKS];
-pomgpu_t* g_ctx = nullptr;
+pomgpu_t* g_ctx = nullptr;      // the whole domain on one device: the resident state (one device) and the unit-mode target
+// more than one device (pomgpu_f_set_devices_ / POMGPU_F_DEVICES): the single-rank driver's domain is cut into
+// j-strips, one per GPU of the box, inside this process; the COMMON arrays keep their global extents on the host
+int g_ndev = 0;                 // 0 = not set: POMGPU_F_DEVICES or 1;  < 0: |n| strips, all on g_device (tests on one GPU)
+int g_ghost = 8;
+std::vector<pomgpu_t*> g_strips;
+pomgpu_group_t* g_grp = nullptr;
+bool g_t_main = true;           // target of the t_* helpers: the resident state (true) or the unit-mode context g_ctx
+bool multi() { return !g_strips.empty(); }
+pomgpu_t* any_ctx() { return multi() ? g_strips[0] : g_ctx; }
 std::vector<int> g_dev;        // COMMON members that are device fields (index into g_mem)
 bool g_full_pushed = false;    // the whole state has been pushed once (start of resident mode)
 bool g_device_ahead = false;   // step-level calls ran since the last full pull: host copies are stale
@@ -107,8 +116,26 @@ const Member* member_at(const void* p) {
   return nullptr;
 }
 
+long dev_elems(const char* name) { pomgpu_t* c = any_ctx(); return c ? pomgpu_field_global_elems(c, name) : 0; }
+int t_push(const char* name, const double* host) {
+  if (!(g_t_main && multi())) return pomgpu_push(g_ctx, name, host);
+  for (pomgpu_t* c : g_strips)
+    if (int rc = pomgpu_push_global(c, name, host)) return rc;
+  return 0;
+}
+int t_pull(const char* name, double* host) {
+  if (!(g_t_main && multi())) return pomgpu_pull(g_ctx, name, host);
+  for (pomgpu_t* c : g_strips)
+    if (int rc = pomgpu_pull_global(c, name, host)) return rc;
+  return 0;
+}
+void t_set_const(const char* name, double v) {
+  for (pomgpu_t* c : g_strips) pomgpu_set_const(c, name, v);
+  if (g_ctx) pomgpu_set_const(g_ctx, name, v);
+}
+
 bool ensure_ctx() {
-  if (g_ctx) return true;
+  if (g_ctx || multi()) return true;
   resolve();
   if (!g_base[0] || !find("im")) { fail("the COMMON blocks of pom.h (blksiz_, blkcon_, blk1d_, blk2d_, blk3d_, bdry_) are not visible to libpomgpu_f: link the driver against it (or with -rdynamic)"); return false; }
   const int im = iget("im", 0), jm = iget("jm", 0);
@@ -121,21 +148,55 @@ bool ensure_ctx() {
     fail(m);
     return false;
   }
-  g_ctx = pomgpu_create(im, jm, g_kb, g_device);
-  if (!g_ctx) { fail("pomgpu_create failed (no CUDA device, bad extents or out of memory); libpomgpu has no CPU fallback"); return false; }
+  if (g_ndev == 0) { const char* e = getenv("POMGPU_F_DEVICES"); g_ndev = e ? atoi(e) : 1; if (g_ndev == 0) g_ndev = 1; }
+  if (const char* e = getenv("POMGPU_F_GHOST")) g_ghost = atoi(e);
+  const int ns = g_ndev < 0 ? -g_ndev : g_ndev;
+  if (ns == 1) {
+    g_ctx = pomgpu_create(im, jm, g_kb, g_device);
+    if (!g_ctx) { fail("pomgpu_create failed (no CUDA device, bad extents or out of memory); libpomgpu has no CPU fallback"); return false; }
+  } else {
+    // j-strips of (almost) equal height, south to north; strip r on device g_device + r
+    int j = 1;
+    for (int r = 0; r < ns; ++r) {
+      const int n = jm / ns + (r < jm % ns ? 1 : 0);
+      pomgpu_t* c = (n >= 1) ? pomgpu_create_strip(im, jm, g_kb, j, j + n - 1, g_ghost, g_ndev < 0 ? g_device : g_device + r) : nullptr;
+      if (!c) {
+        for (pomgpu_t* q : g_strips) pomgpu_destroy(q);
+        g_strips.clear();
+        fail("pomgpu_create_strip failed (fewer CUDA devices than pomgpu_f_set_devices_ asked for, too few rows per strip, or out of memory)");
+        return false;
+      }
+      g_strips.push_back(c);
+      j += n;
+    }
+    g_grp = pomgpu_group_create(ns, g_strips.data());
+    if (!g_grp) {
+      for (pomgpu_t* q : g_strips) pomgpu_destroy(q);
+      g_strips.clear();
+      fail("pomgpu_group_create failed: every strip needs at least ghost+4 rows (POMGPU_F_GHOST, default 8) and there are at most 16 strips");
+      return false;
+    }
+  }
   g_dev.clear();
   for (size_t n = 0; n < g_mem.size(); ++n) {
     const Member& m = g_mem[n];
     if (m.type != 'd' || m.elems < 2 || !g_base[m.block]) continue;
-    if (pomgpu_field_elems(g_ctx, m.name.c_str()) == (long)m.elems) g_dev.push_back((int)n);
+    if (dev_elems(m.name.c_str()) == (long)m.elems) g_dev.push_back((int)n);
   }
   return true;
+}
+// the unit-mode target of the routines that have no group entry point: the whole domain on one device
+bool ensure_unit() {
+  if (g_ctx) return true;
+  g_ctx = pomgpu_create(iget("im", 0), iget("jm", 0), g_kb, g_device);
+  if (!g_ctx) fail("unit mode with several devices runs the routine on ONE device and the whole domain does not fit there (dens, baropg, baropg_mcc run on the strips)");
+  return g_ctx != nullptr;
 }
 
 bool ck(int rc, const char* what) {
   if (rc == 0) return true;
   char m[300];
-  snprintf(m, sizeof(m), "%s failed (rc=%d): %s", what, rc, g_ctx ? pomgpu_last_error(g_ctx) : "");
+  snprintf(m, sizeof(m), "%s failed (rc=%d): %s", what, rc, any_ctx() ? pomgpu_last_error(g_t_main ? any_ctx() : g_ctx) : "");
   fail(m);
   return false;
 }
@@ -145,7 +206,7 @@ void push_consts() {   // blkcon scalars by name (names the device does not know
     if (strcmp(POMF_BLOCKS[m.block].block, "blkcon") || !g_base[m.block]) continue;
     const double v = (m.type == 'd') ? *(double*)addr(&m) : (double)*(int*)addr(&m);
     if (m.name == "error_status") continue;           // the device's own flag is not overwritten
-    pomgpu_set_const(g_ctx, m.name.c_str(), v);
+    t_set_const(m.name.c_str(), v);
   }
 }
 bool push_names(const char* list) {
@@ -157,8 +218,8 @@ bool push_names(const char* list) {
     if (b > a) {
       const std::string n = s.substr(a, b - a);
       const Member* m = find(n.c_str());
-      if (m && addr(m) && pomgpu_field_elems(g_ctx, n.c_str()) == (long)m->elems)
-        if (!ck(pomgpu_push(g_ctx, n.c_str(), (double*)addr(m)), ("push " + n).c_str())) return false;
+      if (m && addr(m) && dev_elems(n.c_str()) == (long)m->elems)
+        if (!ck(t_push(n.c_str(), (double*)addr(m)), ("push " + n).c_str())) return false;
     }
     a = b + 1;
   }
@@ -173,8 +234,8 @@ bool pull_names(const char* list) {
     if (b > a) {
       const std::string n = s.substr(a, b - a);
       const Member* m = find(n.c_str());
-      if (m && addr(m) && pomgpu_field_elems(g_ctx, n.c_str()) == (long)m->elems)
-        if (!ck(pomgpu_pull(g_ctx, n.c_str(), (double*)addr(m)), ("pull " + n).c_str())) return false;
+      if (m && addr(m) && dev_elems(n.c_str()) == (long)m->elems)
+        if (!ck(t_pull(n.c_str(), (double*)addr(m)), ("pull " + n).c_str())) return false;
     }
     a = b + 1;
   }
@@ -195,9 +256,10 @@ const char* STATIC = "z zz dz dzz dx dy art aru arv cor h fsm dum dvm cbc";
 
 bool push_all() {
   if (!ensure_ctx()) return false;
+  g_t_main = true;
   push_consts();
   for (int n : g_dev)
-    if (!ck(pomgpu_push(g_ctx, g_mem[n].name.c_str(), (double*)addr(&g_mem[n])), g_mem[n].name.c_str())) return false;
+    if (!ck(t_push(g_mem[n].name.c_str(), (double*)addr(&g_mem[n])), g_mem[n].name.c_str())) return false;
   g_full_pushed = true;
   g_device_ahead = false;
   return true;
@@ -215,9 +277,10 @@ void mirror_rotated() {
 }
 
 bool pull_all() {
-  if (!g_ctx) return true;
+  if (!any_ctx()) return true;
+  g_t_main = true;
   for (int n : g_dev)
-    if (!ck(pomgpu_pull(g_ctx, g_mem[n].name.c_str(), (double*)addr(&g_mem[n])), g_mem[n].name.c_str())) return false;
+    if (!ck(t_pull(g_mem[n].name.c_str(), (double*)addr(&g_mem[n])), g_mem[n].name.c_str())) return false;
   if (g_device_ahead) mirror_rotated();
   g_device_ahead = false;
   return true;
@@ -225,7 +288,9 @@ bool pull_all() {
 
 void pull_error_status() {
   double es = 0.;
-  if (g_ctx && pomgpu_get_const(g_ctx, "error_status", &es) == 0 && es != 0.) {
+  if (g_t_main && multi()) es = (double)pomgpu_group_error_status(g_grp);
+  else if (g_ctx) pomgpu_get_const(g_ctx, "error_status", &es);
+  if (es != 0.) {
     const Member* m = find("error_status");
     if (addr(m)) *(int*)addr(m) = 1;
   }
@@ -246,7 +311,7 @@ bool is_restore_member(const std::string& n) { return (" " + std::string(RESTORE
 bool restore_begin(int iint) {
   records_fn hook = records_hook();
   const int on = (g_restore >= 0) ? g_restore : ((hook || g_restore_pushed) ? 1 : 0);
-  pomgpu_set_const(g_ctx, "lrestore", (double)on);
+  t_set_const("lrestore", (double)on);
   if (!on || !hook) return true;
   const Member *t0 = find("time0"), *dti = find("dti");
   const double time0 = addr(t0) ? *(double*)addr(t0) : 0., dt_i = addr(dti) ? *(double*)addr(dti) : 0.;
@@ -262,6 +327,7 @@ bool restore_begin(int iint) {
 // ---- step level: resident ------------------------------------------------------------------
 bool step_begin() {
   if (!ensure_ctx()) return false;
+  g_t_main = true;
   if (!g_full_pushed && !push_all()) return false;
   return true;
 }
@@ -273,19 +339,23 @@ struct Arg { const double* host; const Member* mem; std::string dev; };
 bool bind_args(Arg* a, int n, const char* const* scratch) {
   for (int q = 0; q < n; ++q) {
     a[q].mem = member_at(a[q].host);
-    if (a[q].mem && pomgpu_field_elems(g_ctx, a[q].mem->name.c_str()) == (long)a[q].mem->elems) a[q].dev = a[q].mem->name;
+    if (a[q].mem && dev_elems(a[q].mem->name.c_str()) == (long)a[q].mem->elems) a[q].dev = a[q].mem->name;
     else { a[q].mem = nullptr; a[q].dev = scratch[q]; }    // a caller's local array: staged through a scratch field
   }
   return true;
 }
-bool unit_begin(const char* inputs) {
+// on_strips: the routine has a group entry point (dens, baropg, baropg_mcc: what `initialize` calls) and runs on the
+// strips when there are several devices; every other routine runs on ONE device holding the whole domain
+bool unit_begin(const char* inputs, bool on_strips = false) {
   if (!ensure_ctx()) return false;
   if (g_device_ahead && !pull_all()) return false;
+  g_t_main = !multi() || on_strips;
+  if (!g_t_main && !ensure_unit()) return false;
   push_consts();
   return push_names(STATIC) && push_names(BDRY) && push_names(inputs);
 }
-bool push_arg(const Arg& a) { return ck(pomgpu_push(g_ctx, a.dev.c_str(), a.host), ("push argument -> " + a.dev).c_str()); }
-bool pull_arg(const Arg& a, double* host) { return ck(pomgpu_pull(g_ctx, a.dev.c_str(), host), ("pull argument <- " + a.dev).c_str()); }
+bool push_arg(const Arg& a) { return ck(t_push(a.dev.c_str(), a.host), ("push argument -> " + a.dev).c_str()); }
+bool pull_arg(const Arg& a, double* host) { return ck(t_pull(a.dev.c_str(), host), ("pull argument <- " + a.dev).c_str()); }
 void unit_end(const char* outputs) {
   pull_names(outputs);
   pull_error_status();
@@ -304,29 +374,29 @@ void lateral_viscosity_(void) {   // advance.f:96-141
   push_consts();
   if (!push_names(FORCING)) return;
   g_device_ahead = true;
-  ck(pomgpu_lateral_viscosity(g_ctx), "lateral_viscosity");
+  ck(multi() ? pomgpu_group_lateral_viscosity(g_grp) : pomgpu_lateral_viscosity(g_ctx), "lateral_viscosity");
 }
 void mode_interaction_(void) {    // advance.f:144-202
   if (!step_begin()) return;
   g_device_ahead = true;
-  ck(pomgpu_mode_interaction(g_ctx), "mode_interaction");
+  ck(multi() ? pomgpu_group_mode_interaction(g_grp) : pomgpu_mode_interaction(g_ctx), "mode_interaction");
 }
 void mode_external_(void) {       // advance.f:205-353; iext is the driver's loop variable in blkcon (advance.f:27)
   if (!step_begin()) return;
   g_device_ahead = true;
-  ck(pomgpu_mode_external(g_ctx, iget("iext", 1)), "mode_external");
+  ck(multi() ? pomgpu_group_mode_external(g_grp, iget("iext", 1)) : pomgpu_mode_external(g_ctx, iget("iext", 1)), "mode_external");
 }
 void mode_internal_(void) {       // advance.f:356-537
   if (!step_begin()) return;
   g_device_ahead = true;
   const int iint = iget("iint", 1);
-  pomgpu_set_const(g_ctx, "iext", (double)iget("iext", 0));
+  t_set_const("iext", (double)iget("iext", 0));
   if (!restore_begin(iint)) return;
-  if (!ck(pomgpu_mode_internal(g_ctx, iint), "mode_internal")) return;
+  if (!ck(multi() ? pomgpu_group_mode_internal(g_grp, iint) : pomgpu_mode_internal(g_ctx, iint), "mode_internal")) return;
   // what the Fortran glue reads on the host after EVERY step: vaf (check_velocity, advance.f:52,
   // 619-629).  On the device the rotation left the new vaf under the name va.
   const Member* vaf = find("vaf");
-  if (addr(vaf)) ck(pomgpu_pull(g_ctx, "va", (double*)addr(vaf)), "pull vaf");
+  if (addr(vaf)) ck(t_pull("va", (double*)addr(vaf)), "pull vaf");
   pull_error_status();
   // print / output and restart steps read the whole state on the host (advance.f:35-49)
   const int iprint = iget("iprint", 0), irestart = iget("irestart", 0);
@@ -339,8 +409,14 @@ void mode_internal_(void) {       // advance.f:356-537
 UNIT0(advct_, pomgpu_advct, "u v ub vb aam dt", "advx advy")                                                     // solver.f:201
 UNIT0(advu_, pomgpu_advu, "w u v advx drhox ub dt egf egb e_atmos etb etf", "uf")                               // solver.f:734
 UNIT0(advv_, pomgpu_advv, "w u v advy drhoy vb dt egf egb e_atmos etb etf", "vf")                               // solver.f:791
-UNIT0(baropg_, pomgpu_baropg, "rho rmean dt", "drhox drhoy rho")                                                // solver.f:848
-UNIT0(baropg_mcc_, pomgpu_baropg_mcc, "rho rmean d dt", "drhox drhoy rho")                                      // solver.f:943
+void baropg_(void) {              // solver.f:848
+  if (!unit_begin("rho rmean dt", true)) return;
+  if (ck(multi() ? pomgpu_group_baropg_kind(g_grp, 1) : pomgpu_baropg(g_ctx), "baropg")) unit_end("drhox drhoy rho");
+}
+void baropg_mcc_(void) {          // solver.f:943
+  if (!unit_begin("rho rmean d dt", true)) return;
+  if (ck(multi() ? pomgpu_group_baropg_kind(g_grp, 2) : pomgpu_baropg_mcc(g_ctx), "baropg_mcc")) unit_end("drhox drhoy rho");
+}
 UNIT0(profq_, pomgpu_profq, "t s rho q2b q2lb q2 q2l u v km kh kq uf vf etf wusurf wvsurf wubot wvbot l",
       "uf vf km kh kq l q2b q2lb")                                                                              // solver.f:1212
 UNIT0(profu_, pomgpu_profu, "km uf ub vb etf wusurf wubot", "uf wubot")                                         // solver.f:1686
@@ -381,11 +457,12 @@ void advt1_(double* fb, double* f, double* fclim, double* ff) { advt(1, fb, f, f
 void advt2_(double* fb, double* f, double* fclim, double* ff) { advt(2, fb, f, fclim, ff); }   // solver.f:577
 
 void dens_(double* si, double* ti, double* rhoo) {   // solver.f:1162-1209; initialize.f:416,425: dens(sclim,tclim,rmean), dens(sb,tb,rho)
-  if (!unit_begin("")) return;
+  if (!unit_begin("", true)) return;
   Arg a[3] = {{si}, {ti}, {rhoo}};
   bind_args(a, 3, S3);
   if (!push_arg(a[0]) || !push_arg(a[1]) || !push_arg(a[2])) return;   // rhoo too: level kb is not assigned (:1175)
-  if (!ck(pomgpu_dens(g_ctx, a[0].dev.c_str(), a[1].dev.c_str(), a[2].dev.c_str()), "dens")) return;
+  if (!ck(multi() ? pomgpu_group_dens(g_grp, a[0].dev.c_str(), a[1].dev.c_str(), a[2].dev.c_str())
+                  : pomgpu_dens(g_ctx, a[0].dev.c_str(), a[1].dev.c_str(), a[2].dev.c_str()), "dens")) return;
   pull_arg(a[2], rhoo);
   unit_end("");
 }
@@ -434,8 +511,12 @@ void exchange2d_mpi_(double* work, int* nx, int* ny) { (void)work; (void)nx; (vo
 void exchange3d_mpi_(double* work, int* nx, int* ny, int* nz) { (void)work; (void)nx; (void)ny; (void)nz; }
 
 // ================================ control ==========================================================
+void pomgpu_f_set_devices_(const int* n) {
+  if (any_ctx()) { fail("pomgpu_f_set_devices_ must be called before the first entry point"); return; }
+  g_ndev = *n;
+}
 void pomgpu_f_set_dims_(const int* im_local, const int* jm_local, const int* kb) {
-  if (g_ctx) { fail("pomgpu_f_set_dims_ must be called before the first entry point"); return; }
+  if (any_ctx()) { fail("pomgpu_f_set_dims_ must be called before the first entry point"); return; }
   g_iml = *im_local; g_jml = *jm_local; g_kb = *kb;
   g_resolved = false;
 }
@@ -444,19 +525,24 @@ void pomgpu_f_push_all_(void) { push_all(); }
 void pomgpu_f_pull_all_(void) { pull_all(); }
 void pomgpu_f_push_(const double* member) {
   if (!ensure_ctx()) return;
+  g_t_main = true;
   const Member* m = member_at(member);
   if (!m) { fail("pomgpu_f_push_: not the start of a COMMON array"); return; }
   if (is_restore_member(m->name)) g_restore_pushed = true;
-  ck(pomgpu_push(g_ctx, m->name.c_str(), member), m->name.c_str());
+  ck(t_push(m->name.c_str(), member), m->name.c_str());
 }
 void pomgpu_f_set_restore_(const int* on) { g_restore = (*on < 0) ? -1 : (*on != 0); }
 void pomgpu_f_pull_(double* member) {
   if (!ensure_ctx()) return;
+  g_t_main = true;
   const Member* m = member_at(member);
   if (!m) { fail("pomgpu_f_pull_: not the start of a COMMON array"); return; }
-  ck(pomgpu_pull(g_ctx, m->name.c_str(), member), m->name.c_str());
+  ck(t_pull(m->name.c_str(), member), m->name.c_str());
 }
 void pomgpu_f_finalize_(void) {
+  if (g_grp) pomgpu_group_destroy(g_grp);
+  for (pomgpu_t* c : g_strips) pomgpu_destroy(c);
+  g_strips.clear(); g_grp = nullptr; g_ndev = 0; g_t_main = true;
   if (g_ctx) pomgpu_destroy(g_ctx);
   g_ctx = nullptr; g_full_pushed = false; g_device_ahead = false; g_restore_pushed = false; g_restore = -1;
 }

@@ -53,6 +53,13 @@ int pomgpu_pull(pomgpu_t* ctx, const char* name, double* host);
  * large strips); fields without a j dimension are pushed whole */
 int pomgpu_push_rows(pomgpu_t* ctx, const char* name, const double* host, int row0, int nrows);
 long pomgpu_field_elems(pomgpu_t* ctx, const char* name); /* 0 if unknown */
+/* The same for a host array with GLOBAL extents (im, jm_global[, kb]; (jm_global[, kb]) for the west / east edge
+ * arrays) -- a COMMON member of a single-rank driver whose domain is spread over several strips (libpomgpu_f with more
+ * than one device).  push takes the rows this strip HOLDS (owned + ghost rows), pull returns the rows it OWNS, so
+ * the strips of a group assemble the array between them; arrays without a j dimension are pushed / pulled whole. */
+long pomgpu_field_global_elems(pomgpu_t* ctx, const char* name);
+int pomgpu_push_global(pomgpu_t* ctx, const char* name, const double* host_global);
+int pomgpu_pull_global(pomgpu_t* ctx, const char* name, double* host_global);
 /* enqueue-only push (no host wait) for the per-step forcing; the host buffer should be
  * page-locked (pomgpu_pin_host registers a driver-owned array, e.g. a COMMON block).  The copy
  * goes to a shadow buffer on a copy stream, overlapping the step still running; the data
@@ -138,6 +145,14 @@ int pomgpu_group_step(pomgpu_group_t* g, int iint, double time, double ramp);
 /* the two solver.f routines `initialize` calls (initialize.f:416,425,502), on a group */
 int pomgpu_group_dens(pomgpu_group_t* g, const char* si, const char* ti, const char* rhoo);
 int pomgpu_group_baropg(pomgpu_group_t* g);   /* baropg or baropg_mcc by npg (initialize.f:502-505) */
+int pomgpu_group_baropg_kind(pomgpu_group_t* g, int npg);   /* 1: baropg (solver.f:848), 2: baropg_mcc (:943) */
+/* the four step routines of advance.f:21-32 one by one on a group, for a driver that keeps the reference's own
+ * `advance` (libpomgpu_f over several strips); pomgpu_group_error_status = OR of the strips' error_status */
+int pomgpu_group_lateral_viscosity(pomgpu_group_t* g);            /* advance.f:96  */
+int pomgpu_group_mode_interaction(pomgpu_group_t* g);             /* advance.f:144 */
+int pomgpu_group_mode_external(pomgpu_group_t* g, int iext);      /* advance.f:205 */
+int pomgpu_group_mode_internal(pomgpu_group_t* g, int iint);      /* advance.f:356 */
+int pomgpu_group_error_status(pomgpu_group_t* g);
 double pomgpu_group_check_velocity(pomgpu_group_t* g); /* max over this process's strips */
 long pomgpu_group_exchanges(pomgpu_group_t* g, long* fields, int reset); /* halo messages so far */
 /* how the seam rows travel: 0 device copies between strips of this process, 1 ncclSend/ncclRecv,

@@ -79,6 +79,14 @@ void exchange3d_mpi_(double* work, int* nx, int* ny, int* nz);
  * before any other entry point */
 void pomgpu_f_set_dims_(const int* im_local, const int* jm_local, const int* kb);
 void pomgpu_f_set_device_(const int* device);   /* CUDA device of this rank (default 0)        */
+/* Several GPUs behind ONE Fortran process: the (single-rank) driver's domain is cut into n j-strips, strip r on
+ * device `device + r`, inside the library; the COMMON arrays keep their global extents, pushes scatter their rows
+ * (with the strips' ghost rows), pulls gather the owned rows, the halo exchanges between the strips are the
+ * library's (device / peer copies).  Results are bitwise those of one device.  Also POMGPU_F_DEVICES=n in the
+ * environment; n < 0: |n| strips all on `device` (tests on one GPU); POMGPU_F_GHOST = ghost rows per seam (8).
+ * Routine-level entries other than dens_, baropg_, baropg_mcc_ then run on one device holding the whole domain.
+ * Call before the first entry point. */
+void pomgpu_f_set_devices_(const int* n);
 void pomgpu_f_push_all_(void);                  /* COMMON -> HBM, everything                   */
 void pomgpu_f_pull_all_(void);                  /* HBM -> COMMON, everything (output, restart) */
 void pomgpu_f_push_(const double* member);      /* one COMMON array, by address (e.g. trstrb after restore_interior re-read it) */

@@ -61,6 +61,8 @@ class FabiError(RuntimeError):
 class FabiPom:
     """See the module docstring.  Subclasses choose the library: host emulation (CPU tests) or CUDA."""
     FLIB = None
+    NDEV = None              # pomgpu_f_set_devices_: n strips on n devices; -n: n strips on one device
+    GHOST = None             # POMGPU_F_GHOST
     _live = None
 
     def __init__(self, im, jm, kb):
@@ -74,6 +76,12 @@ class FabiPom:
         self.im, self.jm, self.kb = im, jm, kb
         self.L.pomgpu_f_finalize_()
         self.L.pomgpu_f_set_dims_(C.byref(C.c_int(im)), C.byref(C.c_int(jm)), C.byref(C.c_int(kb)))
+        if self.NDEV:
+            self.L.pomgpu_f_set_devices_(C.byref(C.c_int(self.NDEV)))
+        if self.GHOST:
+            os.environ["POMGPU_F_GHOST"] = str(self.GHOST)
+        else:
+            os.environ.pop("POMGPU_F_GHOST", None)
         for n, blk in enumerate(("blksiz_", "blkpar_", "blkcon_", "blk1d_", "blk2d_", "blk3d_", "bdry_")):
             used = min(cm.pom_common_bytes(n), {4: 73 * im * jm * 8, 5: 40 * im * jm * kb * 8}.get(n, 1 << 62))
             C.memset(C.addressof(C.c_char.in_dll(cm, blk)), 0, used)
@@ -272,6 +280,11 @@ class FabiEmu(FabiPom):
         from tests import emu
         emu.build_emu()
         return FLIB_EMU
+
+
+def strips(base, n, ghost=None):
+    """`base` with the domain spread over n strips inside the library (pomgpu_f_set_devices_)."""
+    return type(f"{base.__name__}x{abs(n)}", (base,), {"NDEV": n, "GHOST": ghost})
 
 
 class FabiGpu(FabiPom):

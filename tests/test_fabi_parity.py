@@ -19,7 +19,7 @@ import pytest
 
 from scripts import make_ref_golden as mrg
 from tests import parity_cases as pc
-from tests.fabi import FabiEmu, FabiGpu
+from tests.fabi import FabiEmu, FabiGpu, strips
 
 DIMS = (22, 18, 8)
 
@@ -156,6 +156,60 @@ def test_error_status_follows_the_reference_convention():
     assert int(g.getc("error_status")) == 1
 
 
+# ---- several devices behind ONE Fortran process (pomgpu_f_set_devices_): the COMMON arrays keep their global extents,
+# ---- the library cuts the domain into j-strips; results must not change by a bit --------------------------------
+EMU2 = strips(FabiEmu, 2, ghost=2)
+EMU3 = strips(FabiEmu, 3, ghost=2)
+STRIP_CASES = [c for c in pc.STEP_CASES if c[0][1] >= 17]
+
+
+@pytest.mark.parametrize("case", STRIP_CASES, ids=pc.case_id)
+def test_steps_on_two_strips_behind_the_fortran_abi(case):
+    assert pc.check_steps(EMU2, case) == pc.check_steps(FabiEmu, case)
+
+
+def test_steps_on_three_strips_and_deep_ghost_rows():
+    case = ((40, 31, 16), 30, {})
+    ref = pc.check_steps(FabiEmu, case)
+    assert pc.check_steps(EMU3, case) == ref
+    assert pc.check_steps(strips(FabiEmu, 2, ghost=8), case) == ref
+
+
+def test_strips_are_bitwise_the_single_device_run():
+    dims, n, kw = (24, 19, 9), 6, {"island": True}
+    out = []
+    for F in (FabiEmu, EMU2):
+        _, g = pc.syn.seamount(*dims, F, **kw)
+        for i in range(1, n + 1):
+            g.step(i)
+        out.append({f: g.get(f) for f in list(mrg.F3) + list(mrg.F2) + ["vaf"]})
+    for f in out[0]:
+        assert np.array_equal(out[0][f], out[1][f]), f
+
+
+@pytest.mark.parametrize("name", pc.REF_GOLDEN)
+def test_two_strips_match_the_references_own_output(name):
+    if pc.REF_CASES[name][0][1] < 12:
+        pytest.skip("too few rows for two strips")
+    pc.check_ref_golden(EMU2, name, tol=1e-11)
+
+
+@pytest.mark.parametrize("routine", pc.ROUTINES)
+def test_routines_with_the_state_on_two_strips(routine):
+    """dens, baropg, baropg_mcc run on the strips; every other routine-level entry on one device holding the domain."""
+    pc.check_routine(EMU2, routine, DIMS)
+
+
+def test_restore_interior_records_callback_on_strips():
+    _records_case(EMU2, "medium")
+
+
+def test_too_many_strips_is_an_error_not_a_crash():
+    from tests.fabi import FabiError
+    with pytest.raises(FabiError, match="ghost"):
+        pc.syn.seamount(*DIMS, strips(FabiEmu, 4, ghost=8))
+
+
 # ---- GPU: the CUDA library behind the Fortran face ----------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("routine", pc.ROUTINES)
@@ -178,3 +232,47 @@ def test_fortran_abi_on_gpu_matches_the_references_own_output(name):
 @pytest.mark.gpu
 def test_restore_interior_records_callback_on_gpu():
     _records_case(FabiGpu, "medium")
+
+
+GPU2 = strips(FabiGpu, -2, ghost=4)     # two strips on ONE device: the driver's box has one GPU
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [pc.STEP_CASES[2], pc.STEP_CASES[3], pc.STEP_CASES[10], pc.STEP_CASES[-1]], ids=pc.case_id)
+def test_steps_on_two_strips_behind_the_fortran_abi_on_gpu(case):
+    pc.check_steps(GPU2, case)
+
+
+@pytest.mark.gpu
+def test_strips_behind_the_fortran_abi_are_bitwise_the_single_device_run_on_gpu():
+    dims, n, kw = (64, 48, 14), 5, {"island": True}
+    out = []
+    for F in (FabiGpu, GPU2, strips(FabiGpu, -3, ghost=8)):
+        _, g = pc.syn.seamount(*dims, F, **kw)
+        for i in range(1, n + 1):
+            g.step(i)
+        out.append({f: g.get(f) for f in list(mrg.F3) + list(mrg.F2) + ["vaf"]})
+    for f in out[0]:
+        assert np.array_equal(out[0][f], out[1][f]), f
+        assert np.array_equal(out[0][f], out[2][f]), f
+
+
+@pytest.mark.gpu
+def test_routines_and_records_with_the_state_on_two_strips_on_gpu():
+    for routine in ("dens", "baropg", "baropg_mcc", "advct", "profq", "smol_adif"):
+        pc.check_routine(GPU2, routine, (44, 36, 12))
+    _records_case(GPU2, "medium")
+
+
+@pytest.mark.gpu
+def test_two_devices_behind_the_fortran_abi():
+    """One strip per GPU (needs two visible devices)."""
+    import ctypes
+    try:
+        n = ctypes.c_int(0)
+        ctypes.CDLL("libcudart.so.12").cudaGetDeviceCount(ctypes.byref(n))
+    except OSError:
+        pytest.skip("libcudart not found")
+    if n.value < 2:
+        pytest.skip("one visible device")
+    pc.check_steps(strips(FabiGpu, 2, ghost=8), pc.STEP_CASES[3])
