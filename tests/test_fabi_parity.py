@@ -267,12 +267,7 @@ def test_routines_and_records_with_the_state_on_two_strips_on_gpu():
 @pytest.mark.gpu
 def test_two_devices_behind_the_fortran_abi():
     """One strip per GPU (needs two visible devices)."""
-    import ctypes
-    try:
-        n = ctypes.c_int(0)
-        ctypes.CDLL("libcudart.so.12").cudaGetDeviceCount(ctypes.byref(n))
-    except OSError:
-        pytest.skip("libcudart not found")
-    if n.value < 2:
-        pytest.skip("one visible device")
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible devices")
     pc.check_steps(strips(FabiGpu, 2, ghost=8), pc.STEP_CASES[3])
