@@ -44,6 +44,14 @@ REF_CASES = {
                                                                    "rfn": 0.75, "rfs": 0.1, "horcon": 0.2, "tprni": 0.3,
                                                                    "umol": 2.e-5}}),
     "kb21":           ((14, 12, 21), 4, {}),
+    # a restart (time0 != 0): the first internal step runs the 3-D block too (advance.f:362), restore_interior
+    # interpolates records that have not been read yet (bounds_forcing.f:1038: only at iint=2)
+    "hotstart":       ((16, 14, 7), 3, {"island": True, "_set": {"time0": 1.5}}),
+    # the other Jerlov water types of proft's short-wave penetration (solver.f:1560-1567, 1604-1615)
+    "nbct2_ntp1":     ((16, 14, 7), 3, {"nbct": 2, "ntp": 1}),
+    "nbct4_ntp5":     ((16, 14, 7), 3, {"nbct": 4, "ntp": 5}),
+    # three MPDATA iterations with the reference's default smoothing parameter (solver.f:625-687, 1915)
+    "nitera3_sw05":   ((16, 14, 7), 3, {"nitera": 3, "sw": 0.5, "island": True}),
 }
 
 # the fields compared (state + diagnostics of the step; COMMON member names)
@@ -65,6 +73,20 @@ def ref_restore_setup(solver, st):
     solver.put("taurstrb", full)
     solver.put("taurstrf", full)
     assert kb == full.shape[2]
+
+
+def ref_restore_records(solver, st, iint):
+    """The records as the reference's restore_interior holds them WHEN STEP `iint` RUNS, for the solvers that take
+    them as inputs: nothing has been read before iint=2 (bounds_forcing.f:1038), so a restart (time0 != 0), whose
+    first step already runs the tracer block (advance.f:362), interpolates zeros there -- tau=0, no nudging, only the
+    masks -- and gets the climatology from step 2 on.  Call before every step."""
+    if iint == 1:
+        solver.set("lrestore", 1)
+        zero = np.zeros(st["fields"]["tclim"].shape, order="F")
+        for n in ("trstrb", "trstrf", "srstrb", "srstrf", "taurstrb", "taurstrf"):
+            solver.put(n, zero)
+    elif iint == 2:
+        ref_restore_setup(solver, st)
 
 
 def loaded(factory, dims, kw):
@@ -103,8 +125,8 @@ def main(argv):
         if check:
             from oracle.pomo import Oracle
             st2, o = loaded(Oracle, dims, kw)
-            ref_restore_setup(o, st2)
             for i in range(1, steps + 1):
+                ref_restore_records(o, st2, i)
                 o.step(i)
             bad = {}
             for n in F3 + F2:

@@ -82,7 +82,7 @@ def test_fortran_abi_matches_the_references_own_output(name):
     pc.check_ref_golden(FabiEmu, name, tol=1e-11)
 
 
-@pytest.mark.parametrize("name", ["default", "medium"])
+@pytest.mark.parametrize("name", ["default", "medium", "hotstart"])
 def test_restore_interior_records_callback(name):
     _records_case(FabiEmu, name)
 
