@@ -76,13 +76,20 @@ def _row_noise(kind, tag, im, rows, nk):
     return out
 
 
-def make_state(im, jm, kb, delta=8000.0, wind=True, noise=True, island=False, rows=None, **nml):
+def make_state(im, jm, kb, delta=8000.0, wind=True, noise=True, island=False, rows=None, walls=True, fluxes=False,
+               obc=False, **nml):
     """Everything `initialize` sets that does not need dens/baropg.  Arrays are
     Fortran-ordered (i fastest) float64 with shapes (im,jm[,kb]).
 
     rows=(j_lo, j_hi) (global, 1-based, inclusive) generates only that band of rows of the
     (im, jm, kb) domain -- what one rank of distribute_mpi (pom/parallel_mpi.f:76-119) holds --
-    without ever materialising the global arrays; every value equals the whole-domain one."""
+    without ever materialising the global arrays; every value equals the whole-domain one.
+
+    Parity-test variants (the BASELINE workload keeps the defaults): walls=False opens the north and south sides too
+    (no land rows at j=1, jm), so that the north / south branches of bcond / bcondorl work on wet points; fluxes=True
+    makes e_atmos, vfluxb, vfluxf and wssurf non-zero (they multiply terms of vertvl, advu/advv, mode_external and
+    proft that are otherwise never seen); obc=True gives the open-boundary elevations and velocities
+    (ele..els, vabe..uabs, ube, ubw, vbn, vbs) non-zero values."""
     c = default_consts(**nml)
     F = lambda *shp: np.zeros(shp, order="F")
     f = {}
@@ -110,8 +117,9 @@ def make_state(im, jm, kb, delta=8000.0, wind=True, noise=True, island=False, ro
     r2 = (x[:, None] - xc) ** 2 + (y[None, :] - yc) ** 2
     h = F(im, jm)
     h[...] = 4500.0 * (1.0 - 0.9 * np.exp(-r2 / ra ** 2))
-    h[:, jall == 1] = 1.0
-    h[:, jall == jmg] = 1.0       # closed channel walls
+    if walls:
+        h[:, jall == 1] = 1.0
+        h[:, jall == jmg] = 1.0   # closed channel walls
     if island:                     # a dry patch so that interior masks are exercised
         ic, jc = im // 3, (2 * jmg) // 3
         h[ic - 1:ic + 2, (jall >= jc) & (jall <= jc + 2)] = 1.0
@@ -150,6 +158,11 @@ def make_state(im, jm, kb, delta=8000.0, wind=True, noise=True, island=False, ro
         f["wvsurf"][...] = 0.2e-4 * np.cos(2 * np.pi * i1 / im) * fsm
         f["wtsurf"][...] = 2.0e-5 * np.sin(2 * np.pi * i1 / im) * np.cos(np.pi * j1 / jmg) * fsm
         f["swrad"][...] = -1.0e-5 * fsm
+    if fluxes:
+        f["e_atmos"][...] = 0.05 * np.sin(2 * np.pi * i1 / im) * np.cos(2 * np.pi * j1 / jmg) * fsm
+        f["vfluxf"][...] = 2.0e-7 * (1.0 + 0.5 * np.cos(np.pi * i1 / im) * np.sin(np.pi * j1 / jmg)) * fsm
+        f["vfluxb"][...] = 0.9 * f["vfluxf"]
+        f["wssurf"][...] = 1.0e-6 * np.sin(np.pi * j1 / jmg) * np.cos(np.pi * i1 / im) * fsm
     f["tsurf"] = tb[:, :, 0].copy(order="F")                     # initialize.f:441-442
     f["ssurf"] = sb[:, :, 0].copy(order="F")
     km1 = kb - 1
@@ -163,6 +176,18 @@ def make_state(im, jm, kb, delta=8000.0, wind=True, noise=True, island=False, ro
     f["uabw"] = uab[1, :].copy(); f["uabe"] = uab[im - 2, :].copy()
     for n in ("ele", "elw", "vabe", "vabw"): f[n] = np.zeros(jm)
     for n in ("eln", "els", "vabn", "vabs", "uabn", "uabs"): f[n] = np.zeros(im)
+    if obc:
+        jj, ii = jall.astype(np.float64), np.arange(1, im + 1, dtype=np.float64)
+        sk = np.linspace(1.0, 0.6, kb)[None, :] * (np.arange(kb) < km1)[None, :]
+        f["ele"] = 0.02 * np.sin(2 * np.pi * jj / jmg); f["elw"] = -0.015 * np.cos(2 * np.pi * jj / jmg)
+        f["eln"] = 0.01 * np.sin(2 * np.pi * ii / im); f["els"] = -0.012 * np.cos(2 * np.pi * ii / im)
+        f["vabe"] = 0.01 * np.cos(np.pi * jj / jmg); f["vabw"] = -0.008 * np.sin(np.pi * jj / jmg)
+        f["vabn"] = 0.03 * np.sin(np.pi * ii / im); f["vabs"] = 0.025 * np.sin(np.pi * ii / im)
+        f["uabn"] = 0.004 * np.cos(np.pi * ii / im); f["uabs"] = -0.003 * np.cos(np.pi * ii / im)
+        f["ube"] = np.asfortranarray(0.18 * (1.0 + 0.1 * np.sin(np.pi * jj / jmg))[:, None] * sk)
+        f["ubw"] = np.asfortranarray(0.21 * (1.0 - 0.1 * np.sin(np.pi * jj / jmg))[:, None] * sk)
+        f["vbn"] = np.asfortranarray(0.03 * np.sin(np.pi * ii / im)[:, None] * sk)
+        f["vbs"] = np.asfortranarray(0.025 * np.sin(np.pi * ii / im)[:, None] * sk)
 
     # update_initial (initialize.f:472-495)
     f["ua"] = uab.copy(order="F"); f["va"] = vab.copy(order="F")

@@ -52,6 +52,12 @@ REF_CASES = {
     "nbct4_ntp5":     ((16, 14, 7), 3, {"nbct": 4, "ntp": 5}),
     # three MPDATA iterations with the reference's default smoothing parameter (solver.f:625-687, 1915)
     "nitera3_sw05":   ((16, 14, 7), 3, {"nitera": 3, "sw": 0.5, "island": True}),
+    # all four sides open (no channel walls: the north / south branches of bcond, bcondorl work on wet points),
+    # non-zero e_atmos, vfluxb, vfluxf, wssurf and open-boundary elevations / velocities
+    "open_fluxes_obc": ((16, 14, 7), 4, {"walls": False, "fluxes": True, "obc": True}),
+    "open_nadv1_npg2": ((16, 14, 7), 3, {"walls": False, "fluxes": True, "obc": True, "nadv": 1, "npg": 2, "island": True}),
+    "open_mode2":     ((16, 14, 7), 3, {"walls": False, "fluxes": True, "obc": True, "mode": 2}),
+    "open_nbct3_it2": ((16, 14, 7), 3, {"walls": False, "fluxes": True, "obc": True, "nbct": 3, "nbcs": 3, "nitera": 2}),
 }
 
 # the fields compared (state + diagnostics of the step; COMMON member names)

@@ -35,6 +35,9 @@ STEP_CASES = [
     ((21, 18, 8), 6, {"aam_init": 0.0}),
     ((24, 19, 9), 6, {"nitera": 2, "island": True}),           # Smolarkiewicz iterations (solver.f:625-687)
     ((24, 19, 9), 6, {"nitera": 3, "sw": 1.0}),
+    # all four sides open, non-zero e_atmos / vflux / wssurf and open-boundary values (synthetic.make_state)
+    ((24, 19, 9), 6, {"walls": False, "fluxes": True, "obc": True}),
+    ((26, 21, 10), 5, {"walls": False, "fluxes": True, "obc": True, "island": True, "npg": 2, "nadv": 1}),
 ]
 
 

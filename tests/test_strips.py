@@ -73,7 +73,9 @@ def test_strips_equal_single_domain_bitwise(nstrips, ghost):
     assert grp.transport() == "device copies"             # pomgpu_group_transport: strips of one process
 
 
-@pytest.mark.parametrize("kw", [{"nadv": 1}, {"mode": 4}, {"nbct": 2, "ntp": 3}, {"nitera": 3, "sw": 1.0}, {"mode": 2}, {"npg": 2}])
+@pytest.mark.parametrize("kw", [{"nadv": 1}, {"mode": 4}, {"nbct": 2, "ntp": 3}, {"nitera": 3, "sw": 1.0}, {"mode": 2}, {"npg": 2},
+                                {"walls": False, "fluxes": True, "obc": True},      # open north / south sides inside the end strips
+                                {"walls": False, "fluxes": True, "obc": True, "npg": 2, "island": True}])
 def test_strips_namelist_variants(kw):
     dims, nstep = (20, 30, 7), 4
     whole = _whole(dims, nstep, **kw)
