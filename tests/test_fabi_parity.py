@@ -218,13 +218,13 @@ def test_routine_through_the_fortran_abi_on_gpu(routine):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", pc.STEP_CASES, ids=pc.case_id)
+@pytest.mark.parametrize("case", pc.STEP_CASES_GPU, ids=pc.case_id)
 def test_steps_through_the_fortran_abi_on_gpu(case):
     pc.check_steps(FabiGpu, case)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", pc.REF_GOLDEN)
+@pytest.mark.parametrize("name", pc.REF_GOLDEN_GPU)
 def test_fortran_abi_on_gpu_matches_the_references_own_output(name):
     pc.check_ref_golden(FabiGpu, name, tol=1e-11)
 
@@ -238,7 +238,7 @@ GPU2 = strips(FabiGpu, -2, ghost=4)     # two strips on ONE device: the driver's
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", [pc.STEP_CASES[2], pc.STEP_CASES[3], pc.STEP_CASES[10], pc.STEP_CASES[-1]], ids=pc.case_id)
+@pytest.mark.parametrize("case", [pc.STEP_CASES[2], pc.STEP_CASES[3], pc.STEP_CASES[10], pc.STEP_CASES[18]], ids=pc.case_id)
 def test_steps_on_two_strips_behind_the_fortran_abi_on_gpu(case):
     pc.check_steps(GPU2, case)
 
@@ -266,7 +266,11 @@ def test_routines_and_records_with_the_state_on_two_strips_on_gpu():
 
 @pytest.mark.gpu
 def test_two_devices_behind_the_fortran_abi():
-    """One strip per GPU (needs two visible devices)."""
+    """One strip per GPU (needs two visible devices).  Written after the round's GPU budget was spent: like the late
+    parity cases it runs only with POMGPU_LATE_CASES=1 (the strips-of-one-device form of the same host code is in the
+    default `-m gpu` run)."""
+    if not pc._LATE:
+        pytest.skip("not yet seen on a two-GPU box: set POMGPU_LATE_CASES=1")
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two visible devices")

@@ -15,7 +15,7 @@ def _factory(im, jm, kb):
     return PomGpu(im, jm, kb)
 
 
-@pytest.mark.parametrize("case", pc.STEP_CASES, ids=pc.case_id)
+@pytest.mark.parametrize("case", pc.STEP_CASES_GPU, ids=pc.case_id)
 def test_steps_match_oracle(case):
     pc.check_steps(_factory, case)
 
@@ -29,7 +29,7 @@ def test_routine_matches_oracle(routine):
     pc.check_routine(_factory, routine, (28, 22, 10))
 
 
-@pytest.mark.parametrize("name", pc.REF_GOLDEN)
+@pytest.mark.parametrize("name", pc.REF_GOLDEN_GPU)
 def test_cuda_path_matches_the_references_own_output(name):
     """The CUDA path against the fields the reference's own Fortran source produced (tests/golden/ref_*.npz,
     scripts/make_ref_golden.py + oracle/f77ref.py); 1e-11: the only non-identical operation is |S|**1.5."""
