@@ -149,6 +149,7 @@ bool ensure_ctx() {
     return false;
   }
   if (g_ndev == 0) { const char* e = getenv("POMGPU_F_DEVICES"); g_ndev = e ? atoi(e) : 1; if (g_ndev == 0) g_ndev = 1; }
+  g_ghost = 8;
   if (const char* e = getenv("POMGPU_F_GHOST")) g_ghost = atoi(e);
   const int ns = g_ndev < 0 ? -g_ndev : g_ndev;
   if (ns == 1) {
