@@ -120,13 +120,15 @@ class FabiPom:
         p = self.L.pomgpu_f_member(name.encode(), C.byref(n))
         return p, n.value
 
-    def _view(self, name):
-        """numpy view of the COMMON member `name` (None if it is not one)."""
+    def _view(self, name, shape=None):
+        """numpy view of the COMMON member `name` (None if it is not one, or not of the given shape)."""
         p, n = self._member(name)
         if not p or self.L.pomgpu_f_member_type(name.encode()) != b"d" or n < 2:
             return None
         a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n,))
-        shp = self.shapes.get(name)
+        shp = shape or self.shapes.get(name)
+        if shape is not None and int(np.prod(shape)) != n:
+            return None
         if shp is None:
             shp = (self.im, self.jm, self.kb) if n == self.im * self.jm * self.kb else (self.im, self.jm)
         assert int(np.prod(shp)) == n, (name, shp, n)
