@@ -307,10 +307,14 @@ def _log(x):
     return f8(math.log(float(x)))
 
 
+def _sin(x):      # initialize.f:349 (Coriolis parameter); not on the hot path
+    return f8(math.sin(float(x)))
+
+
 INTRINSICS = {"abs": "_abs", "dabs": "_abs", "sqrt": "_sqrt", "dsqrt": "_sqrt", "max": "_max", "min": "_min",
               "dmax1": "_max", "dmin1": "_min", "amax1": "_max", "amin1": "_min", "exp": "_exp", "sign": "_sign",
               "mod": "_mod", "float": "f4", "dble": "f8", "real": "_real", "int": "int", "log": "_log",
-              "maxval": "np.max", "minval": "np.min", "sum": "_sum", "nint": "_nint"}
+              "maxval": "np.max", "minval": "np.min", "sum": "_sum", "nint": "_nint", "sin": "_sin"}
 
 
 def _sum(a):
@@ -332,7 +336,7 @@ def _mod(a, b):
 
 
 RUNTIME = dict(np=np, f4=f4, f8=f8, f16=f16, _div=_div, _pow=_pow, _sign=_sign, _max=_max, _min=_min, _real=_real,
-               _exp=_exp, _sqrt=_sqrt, _abs=_abs, _log=_log, _mod=_mod, _nint=_nint, _sum=_sum, int=int)
+               _exp=_exp, _sqrt=_sqrt, _abs=_abs, _log=_log, _mod=_mod, _nint=_nint, _sum=_sum, int=int, _sin=_sin)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -148,3 +148,173 @@ def test_the_references_own_advance_over_the_drop_in_library(kw, factory, tmp_pa
             x, y = x[:, :, :-1], y[:, :, :-1]
         e = np.abs(x - y).max() / (np.abs(x).max() + 1e-300)
         assert e <= 1e-11, (n, e)
+
+
+# ---- initialize.f: read_grid, initial_conditions, update_initial, bottom_friction executed from the source -------------
+RAW = ("z zz dx dy h fsm dum dvm").split()                       # what read_grid_pnetcdf delivers (io_pnetcdf.F)
+GIVEN = ("ub vb uab vab elb etb e_atmos vfluxb vfluxf wusurf wvsurf wtsurf wssurf swrad ele elw eln els vabe vabw vabn vabs "
+         "uabn uabs uabe uabw ube ubw vbn vbs").split()           # the state the synthetic case starts from (no file in the reference)
+
+
+def _initialize(kw, library=None):
+    """initialize.f:19-37 without read_input (a namelist): initialize_arrays, read_grid, initial_conditions,
+    update_initial, bottom_friction, executed from the reference source; the PnetCDF readers are played by the
+    synthetic generator's raw inputs.  library = a tests/fabi.py driver: `dens`, `baropg`, `baropg_mcc` are then
+    the symbols of libpomgpu_f (the GPU build drops solver.o), called with the reference's own argument lists
+    -- dens(sclim,tclim,rmean), dens(sb,tb,rho) (initialize.f:416,425) -- by address."""
+    from oracle import f77ref
+    st = syn.make_state(*DIMS, **{k: v for k, v in kw.items() if k != "_set"})
+    f, c = st["fields"], st["consts"]
+    r = f77ref.F77Ref(*DIMS)
+    r.ref.units.update(f77ref.split_units(os.path.join(REF, "initialize.f")))
+    for k, v in c.items():                                       # read_input (initialize.f:67-191)
+        if k in r.v and not isinstance(r.v[k], np.ndarray):
+            r.set(k, v)
+    r.v["pi"] = np.float64(np.arctan(np.float64(1.)) * 4.)      # initialize.f:179
+
+    def read_grid():
+        for n in RAW:
+            r.v[n][...] = f[n]
+        r.v["north_e"][...] = 43.3                               # cor is recomputed from the latitude (initialize.f:349)
+
+    def read_ic(kb, tb, sb):
+        tb[...] = f["tb"]; sb[...] = f["sb"]
+
+    def read_clim(kb, n, tclim, sclim):
+        tclim[...] = f["tclim"]; sclim[...] = f["sclim"]
+
+    r.ref.externals.update(read_grid_pnetcdf=read_grid, check_cflmin_mpi=lambda: None,
+                           read_initial_ts_pnetcdf=read_ic, read_clim_ts_pnetcdf=read_clim)
+    if library is not None:
+        lib = library
+        names = [n for n, a in r.v.items() if isinstance(a, np.ndarray) and a.dtype == np.float64 and lib._view(n, a.shape) is not None]
+        views = {n: lib._view(n, r.v[n].shape) for n in names}
+        scal = [n for n, a in r.v.items() if not isinstance(a, np.ndarray) and lib._member(n)[0]
+                and isinstance(a, (int, float, np.floating, np.integer)) and not isinstance(a, bool)]
+
+        def to_common():
+            for n in scal:
+                lib.set(n, r.v[n])
+            for n in names:
+                views[n][...] = r.v[n]
+
+        def from_common():
+            for n in names:
+                r.v[n][...] = views[n]
+            r.v["error_status"] = int(lib.getc("error_status"))
+
+        def name_of(a):
+            return next(n for n in names if r.v[n] is a)
+
+        def dens(si, ti, rhoo):
+            to_common()
+            lib.L.dens_(*[lib._addr(name_of(a)) for a in (si, ti, rhoo)])
+            from_common()
+
+        def bound(sym):
+            def call():
+                to_common(); getattr(lib.L, sym + "_")(); from_common()
+            return call
+
+        for n in ("dens", "baropg", "baropg_mcc"):
+            del r.ref.units[n]
+        r.ref.externals.update(dens=dens, baropg=bound("baropg"), baropg_mcc=bound("baropg_mcc"))
+    r.ref.call("initialize_arrays")
+    for n in GIVEN:
+        if n in f and n in r.v:
+            r.v[n][...] = f[n]
+    for n in ("read_grid", "initial_conditions", "update_initial", "bottom_friction"):
+        r.ref.call(n)
+    return st, r
+
+
+DERIVED = ("dz dzz art aru arv d dt rmean rho tsurf ssurf tbe tbw sbe sbw tbn tbs sbn sbs ua va el et etf w l q2b q2lb kh km kq aam "
+           "q2 q2l t s u v drhox drhoy drx2d dry2d cbc").split()
+
+
+@pytest.mark.parametrize("kw", [{"island": True, "fluxes": True}, {"walls": False, "obc": True, "npg": 2}], ids=["channel", "open_npg2"])
+def test_the_generators_initialisation_is_the_references(kw):
+    """extpom_b200/synthetic.py restates the derived-input formulas of initialize.f (:331-335, 363-384, 416-425,
+    437-460, 472-518, 534-541); here the reference's own routines produce them from the same raw
+    inputs: every derived array BITWISE (the oracle makes the dens / baropg calls for the generator)."""
+    from oracle.pomo import Oracle
+    st, r = _initialize(kw)
+    st2, o = syn.seamount(*DIMS, Oracle, **kw)
+    assert abs(float(r.v["cor"][3, 3]) - 1.0e-4) < 1e-6          # 2*7.29e-5*sin(43.3 deg): the reference's own formula
+    for n in DERIVED:
+        a = r.v[n]
+        b = o.get(n) if n in o.f else st2["fields"][n]
+        assert np.array_equal(a, np.asarray(b).reshape(a.shape, order="F")), n
+
+
+@pytest.mark.parametrize("factory", [FabiEmu, strips(FabiEmu, 2, ghost=2)], ids=["one_device", "two_strips"])
+def test_initialize_then_advance_with_solver_f_replaced_by_the_library(factory, tmp_path):
+    """The whole program minus its file I/O: initialize.f's routines and then `advance`, executed from the reference
+    source, (A) unmodified and (B) as the GPU build links it -- no solver.o, no step routines: dens, baropg and the
+    four step routines are libpomgpu_f's."""
+    from oracle import f77ref
+    kw = {"walls": False, "obc": True, "fluxes": True, "island": True}
+    out = []
+    for lib in (None, factory(*DIMS)):
+        st, r = _initialize(kw, lib)
+        _files(st, r)
+        r.v["iprint"] = 2; r.v["irestart"] = 10 ** 6; r.v["iend"] = 10 ** 6
+        r.v["netcdf_file"] = "nonetcdf"; r.v["iswtch"] = 10 ** 6
+        if lib is not None:
+            text, _ = cut(open(os.path.join(REF, "advance.f")).read())
+            glue = tmp_path / "advance_glue.f"
+            glue.write_text(text + "\n" + restore_records(open(os.path.join(REF, "bounds_forcing.f")).read()))
+            for n in CUT:
+                del r.ref.units[n]
+            r.ref.units.update(f77ref.split_units(str(glue)))
+            names = [n for n, a in r.v.items() if isinstance(a, np.ndarray) and a.dtype == np.float64 and lib._view(n, a.shape) is not None]
+            views = {n: lib._view(n, r.v[n].shape) for n in names}
+            scal = [n for n, a in r.v.items() if not isinstance(a, np.ndarray) and lib._member(n)[0]
+                    and isinstance(a, (int, float, np.floating, np.integer)) and not isinstance(a, bool)]
+
+            def to_common():
+                for n in scal:
+                    lib.set(n, r.v[n])
+                for n in names:
+                    views[n][...] = r.v[n]
+
+            def from_common():
+                for n in names:
+                    r.v[n][...] = views[n]
+                r.v["error_status"] = int(lib.getc("error_status"))
+
+            def bound(sym):
+                def call():
+                    to_common(); getattr(lib.L, sym + "_")(); from_common()
+                return call
+
+            def records(_):
+                for n in RESTORE:
+                    r.v[n][...] = views[n]
+                r.ref.call("restore_interior_records")
+                for n in RESTORE:
+                    views[n][...] = r.v[n]
+
+            r.ref.externals.update({n: bound(n) for n in CUT})
+            lib.set_records(records)
+        try:
+            for i in range(1, 4):
+                r.v["iint"] = i
+                r.ref.call("advance")
+            if lib is not None:
+                lib.L.pomgpu_f_pull_all_()
+                from_common()
+        finally:
+            if lib is not None:
+                lib.set_records(None); lib.set_restore(0)
+        out.append(r)
+    a, b = out
+    assert int(b.v["error_status"]) == 0
+    for n in list(mrg.F3) + list(mrg.F2) + ["rmean", "cbc", "tsurf", "wusurf"]:
+        if n in ("uf", "vf"):
+            continue
+        x, y = a.v[n], b.v[n]
+        if n in ("t", "tb", "s", "sb"):
+            x, y = x[:, :, :-1], y[:, :, :-1]
+        e = np.abs(x - y).max() / (np.abs(x).max() + 1e-300)
+        assert e <= 1e-11, (n, e)
