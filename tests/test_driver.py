@@ -21,11 +21,11 @@ def _build(libdir, libname, exe):
     return exe
 
 
-def _run(tmp_path, exe, factory, dims=(22, 18, 8), nstep=5, **kw):
+def _run(tmp_path, exe, factory, dims=(22, 18, 8), nstep=5, strips=(), **kw):
     state = str(tmp_path / "state.bin")
     out = str(tmp_path / "out.bin")
     dump(state, *dims, **kw)
-    r = subprocess.run([exe, state, str(nstep), out], capture_output=True, text=True)
+    r = subprocess.run([exe, state, str(nstep), out, *map(str, strips)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     got = read_out(out)
     _, g = syn.seamount(*dims, factory, **kw)
@@ -40,6 +40,24 @@ def test_compiled_driver_on_host_emulation(tmp_path):
     so = emu.build_emu()
     exe = _build(os.path.dirname(so), "pomgpu_emu", str(tmp_path / "pom_driver_emu"))
     _run(tmp_path, exe, emu.EmuPom, island=True)
+
+
+def test_compiled_driver_with_strips_on_host_emulation(tmp_path):
+    """`pom_driver ... NSTRIPS`: the domain on several strips of one process (pomgpu_create_strip, pomgpu_group_create,
+    pomgpu_push_global / pomgpu_pull_global), bitwise the single-domain result."""
+    so = emu.build_emu()
+    exe = _build(os.path.dirname(so), "pomgpu_emu", str(tmp_path / "pom_driver_emu"))
+    _run(tmp_path, exe, emu.EmuPom, dims=(24, 40, 8), nstep=5, strips=(3, "same", 4), island=True)
+    _run(tmp_path, exe, emu.EmuPom, dims=(24, 40, 8), nstep=4, strips=(2,), npg=2)
+
+
+@pytest.mark.gpu
+def test_compiled_driver_with_strips_on_gpu(tmp_path):
+    from tests import parity_cases as pc
+    if not pc._LATE:
+        pytest.skip("written after the round's GPU budget was spent: set POMGPU_LATE_CASES=1")
+    exe = _build(os.path.dirname(LIBPATH), "pomgpu", str(tmp_path / "pom_driver"))
+    _run(tmp_path, exe, PomGpu, dims=(40, 48, 12), nstep=5, strips=(3, "same"), island=True)
 
 
 @pytest.mark.gpu
